@@ -1,0 +1,103 @@
+/*
+ * scsommerclock_b200.h -- C ABI of the B200-native Poisson Tree (PT) test hot path.
+ *
+ * The reference (cbg-ethz/scSomMerClock, run_PT_test.py) is pure Python; the
+ * functions below are what a maintainer would bind (ctypes)
+ * in place of the NumPy/SciPy bodies of
+ *
+ *   get_mut_df          run_PT_test.py:27-207    -> scs_vcf_decode*
+ *   map_mutations_gt    run_PT_test.py:386-448   -> scs_placement_* / scs_map_mutations
+ *   _normalize_log_probs run_PT_test.py:368-383  -> fused in the placement epilogue
+ *   add_br_weights      run_PT_test.py:451-515   -> scs_branch_weights
+ *   get_LRT_poisson     run_PT_test.py:638-700   -> scs_lrt_poisson_batch
+ *
+ * Plain pointers and sizes only.  Functions whose buffer arguments are named
+ * d_* take DEVICE pointers (memory of the current CUDA primary context, e.g. a
+ * torch tensor's data_ptr()); everything else is HOST memory.  `stream` is a
+ * cudaStream_t passed as void* (NULL = the legacy default stream).
+ *
+ * Every function returns SCS_OK (0) or a negative error code; the message for
+ * the calling thread's last error is scs_last_error().  There is no CPU
+ * fallback: without a usable sm_100 device scs_ctx_create fails.
+ */
+#ifndef SCSOMMERCLOCK_B200_H
+#define SCSOMMERCLOCK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCS_OK 0
+#define SCS_ERR_ARG (-1)     /* invalid argument                               */
+#define SCS_ERR_CUDA (-2)    /* CUDA runtime / driver failure                  */
+#define SCS_ERR_OOM (-3)     /* device or host allocation failed               */
+#define SCS_ERR_DEVICE (-4)  /* no sm_100 device: the hot path cannot run      */
+#define SCS_ERR_PARSE (-5)   /* malformed VCF input                            */
+#define SCS_ERR_NUMERIC (-6) /* solver failed to converge                      */
+
+/* 2-bit genotype codes of the packed SNV x cell observation matrix; they are the
+ * values of the reference's `muts` DataFrame (run_PT_test.py:156-167): 0 wild
+ * type, 1 heterozygous, 2 homozygous, NaN missing.  Four cells per byte, cell c
+ * in bits [2*(c%4), 2*(c%4)+2) of byte c/4 of its row. */
+#define SCS_GT_WT 0
+#define SCS_GT_HET 1
+#define SCS_GT_HOM 2
+#define SCS_GT_MISSING 3
+
+typedef struct scs_ctx scs_ctx;
+typedef struct scs_placement scs_placement;
+
+/* ------------------------------------------------------------------ context */
+const char* scs_version(void);
+const char* scs_last_error(void);
+int scs_ctx_create(int32_t device, scs_ctx** out);
+int scs_ctx_destroy(scs_ctx* ctx);
+/* info[0..5] = sm_count, cc_major, cc_minor, total_mem_MiB, l2_bytes, device */
+int scs_ctx_info(scs_ctx* ctx, int64_t* info, int32_t n);
+
+/* ---------------------------------------------------------------- placement
+ * map_mutations_gt (run_PT_test.py:386-448): for every SNV, the normalised
+ * likelihood of sitting on each row of the clade matrix S (the 2n-1 tree nodes in
+ * ete3 level order plus a final all-zero "FP" row), summed over SNVs:
+ *     soft_weights[b] = sum_i M[i,b],   M[i,:] = softmax_b(probs[i,:]).
+ * A plan owns the device-resident operands and scratch for one (n_snv, n_cells,
+ * n_rows) shape and can be re-run with new genotypes / clades / error rates. */
+int scs_placement_create(scs_ctx* ctx, int64_t n_snv, int32_t n_cells, int32_t n_rows, scs_placement** out);
+int scs_placement_destroy(scs_placement* plan);
+/* d_gt: packed 2-bit genotypes [n_snv][pitch_bytes]; d_row_keep: optional
+ * [n_snv] bytes, 0 drops the SNV (the reference's `muts_red.sum(axis=1) > 0`
+ * filter, run_PT_test.py:352). */
+int scs_placement_set_genotypes(scs_placement* plan, const uint8_t* d_gt, int64_t pitch_bytes,
+                                const uint8_t* d_row_keep, void* stream);
+int scs_placement_set_genotypes_host(scs_placement* plan, const uint8_t* gt, int64_t pitch_bytes,
+                                     const uint8_t* row_keep, void* stream);
+/* d_bits: clade membership bit mask [n_rows][pitch_words] of uint32, bit c%32 of
+ * word c/32 set when cell c descends from the node (S, run_PT_test.py:389-397). */
+int scs_placement_set_clades(scs_placement* plan, const uint32_t* d_bits, int64_t pitch_words, void* stream);
+int scs_placement_set_clades_host(scs_placement* plan, const uint32_t* bits, int64_t pitch_words, void* stream);
+/* Asynchronous on `stream`.  d_soft_weights: [n_rows] doubles on the device, or
+ * NULL to leave the result in the plan (scs_placement_device_result). */
+int scs_placement_run(scs_placement* plan, double FP, double FN, double* d_soft_weights, void* stream);
+/* Same, then copies [n_rows] doubles to host memory and synchronises. */
+int scs_placement_run_host(scs_placement* plan, double FP, double FN, double* soft_weights, void* stream);
+const void* scs_placement_device_result(scs_placement* plan);
+/* info[0..9] = M_pad, N_pad, K_pad, tasks, run_len, superblock_width, grid,
+ * kernel launches so far, runs, dynamic smem bytes */
+int scs_placement_info(scs_placement* plan, int64_t* info, int32_t n);
+/* Parity aid for small problems: counts[i][b][0/1] = number of cells of clade b
+ * observed mutated / observed wild type for SNV i (exact integers). */
+int scs_placement_debug_counts(scs_placement* plan, int32_t* counts, void* stream);
+
+/* One-shot host call mirroring map_mutations_gt's signature: host buffers in,
+ * soft_weights[n_rows] out (H2D copy, both GEMM passes, D2H copy). */
+int scs_map_mutations(scs_ctx* ctx, const uint8_t* gt, int64_t pitch_bytes, const uint8_t* row_keep,
+                      int64_t n_snv, int32_t n_cells, const uint32_t* clade_bits, int64_t pitch_words,
+                      int32_t n_rows, double FP, double FN, double* soft_weights);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCSOMMERCLOCK_B200_H */

@@ -1,0 +1,27 @@
+// scs_internal.h -- shared host-side plumbing of the C-ABI library.
+#pragma once
+#include <cstdarg>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/scsommerclock_b200.h"
+
+struct scs_ctx {
+    int device;
+    int sm_count;
+    int cc_major, cc_minor;
+    size_t total_mem;
+    int l2_bytes;
+};
+
+namespace scs {
+// Records a printf-style message for scs_last_error() and returns `code`.
+int set_error(int code, const char* fmt, ...);
+}  // namespace scs
+
+#define SCS_CUDA(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return scs::set_error(SCS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)

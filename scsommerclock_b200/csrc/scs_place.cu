@@ -1,0 +1,756 @@
+// scs_place.cu -- mutation placement (reference: run_PT_test.py:386-448,
+// map_mutations_gt + _normalize_log_probs :368-383) as a two-pass tcgen05 GEMM.
+//
+// For SNV i and candidate row b of the clade matrix S (2n-1 tree nodes + one
+// empty "FP" row) the reference computes
+//     probs[i,b] = sum_c  S[b,c]*log(1-FN)*x + (1-S[b,c])*log(FP)*x
+//                       + (1-S[b,c])*log(1-FP)*(1-x) + S[b,c]*log(FN)*(1-x)
+// over the observed cells c (x in {0,1}, NaN cells dropped by nansum), then
+// M[i,:] = softmax_b(probs[i,:]) and Y[b] = sum_i M[i,b].  Everything that does
+// not depend on b cancels in the softmax, leaving
+//     logit[i,b] = a1 * C1[i,b] + a0 * C0[i,b],
+//     C1 = X1 . S^T,  C0 = X0 . S^T   (integer counts),
+//     a1 = log((1-FN)/FP),  a0 = log(FN/(1-FP)),
+// where X1/X0 are the 0/1 indicator planes "cell observed mutated / observed
+// wild type".  C1 and C0 are exact integer GEMMs: unsigned 8-bit operands with
+// s32 accumulators in TMEM (tcgen05.mma kind::i8), so the only floating-point
+// rounding in the whole placement is in the epilogue, which works on *exact
+// integer differences* against a per-row reference column.
+//
+// Pass 1 emits, per (row, 64-column half tile), the reference counts of the best
+// column and sum_b exp2(logit - logit_ref).  A small merge kernel turns those into
+// one (reference, log2-sum) record per SNV.  Pass 2 recomputes the tiles and
+// accumulates softmax column sums in registers; the SNV x branch matrix never
+// exists in HBM.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "scs_internal.h"
+#include "scs_ptx.cuh"
+
+namespace scs {
+
+// ------------------------------------------------------------------ tiling
+constexpr int BLOCK_M = 128;  // SNV rows per tile (= TMEM lanes)
+constexpr int BLOCK_N = 128;  // clade rows (GEMM columns) per tile
+constexpr int BLOCK_K = 128;  // cells per pipeline stage (bytes, u8 operands)
+constexpr int UMMA_K = 32;    // cells per tcgen05.mma (8-bit kinds)
+constexpr int NUM_STAGES = 4;
+constexpr int STAGE_A_BYTES = BLOCK_M * BLOCK_K;  // one genotype plane
+constexpr int STAGE_B_BYTES = BLOCK_N * BLOCK_K;
+constexpr int STAGE_BYTES = 2 * STAGE_A_BYTES + STAGE_B_BYTES;
+constexpr int NUM_EPI_WARPS = 8;  // 4 TMEM lane quarters x 2 column halves
+constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
+constexpr int TMEM_COLS = 512;  // 2 accumulator stages x 2 planes x 128 columns
+constexpr int SMEM_BARRIER_BYTES = 256;
+constexpr int SMEM_RED_BYTES = 4 * BLOCK_N * 4;
+constexpr int SMEM_TOTAL = NUM_STAGES * STAGE_BYTES + SMEM_BARRIER_BYTES + SMEM_RED_BYTES + 1024;
+
+// kind::i8 instruction descriptor: D = s32 (c_format 2 at bits [4,6)), A and B
+// unsigned 8 bit (format 0 at [7,10) / [10,13)), both K-major (bits 15, 16 = 0),
+// N >> 3 at [17,23), M >> 4 at [24,29).
+constexpr uint32_t IDESC_I8 = (2u << 4) | (uint32_t(BLOCK_N >> 3) << 17) | (uint32_t(BLOCK_M >> 4) << 24);
+
+enum { PASS_DUMP = 0, PASS_STATS = 1, PASS_COLSUM = 2 };
+
+struct PlaceParams {
+    int M, N;            // valid SNV rows / valid clade rows
+    int M_pad, N_pad;    // padded to BLOCK_M / BLOCK_N
+    int num_k_blocks;
+    int num_row_blocks, num_col_tiles;
+    int run_len, num_runs, sb_width, num_tasks;
+    float a1h, a1l, a0h, a0l;  // log2-unit constants, split so that a?h * count is exact
+    float a1f, a0f;            // plain fp32 copies, used only to rank columns
+    uint2* stats;              // pass 1 out: [num_col_tiles*2][M_pad] {ref counts, sum}
+    const uint2* rowref;       // pass 2 in : [M_pad] {ref counts, log2 sum}
+    float* colpart;            // pass 2 out: [num_runs][N_pad]
+    int* dump;                 // debug     : [M_pad][N_pad][2] raw counts
+};
+
+__host__ __device__ inline void decode_task(const PlaceParams& p, int t, int& j, int& r0, int& r1) {
+    // Tasks are ordered super-block (a group of sb_width column tiles whose slab of
+    // S stays L2 resident) -> run of row blocks -> column tile, so that CTAs that
+    // run concurrently share both the genotype rows and the clade slab in L2.
+    const int per_sb = p.num_runs * p.sb_width;
+    const int nsb_full = p.num_col_tiles / p.sb_width;
+    int sb = t / per_sb;
+    int w = p.sb_width;
+    if (sb >= nsb_full) {
+        sb = nsb_full;
+        w = p.num_col_tiles - nsb_full * p.sb_width;
+    }
+    const int rem = t - sb * per_sb;
+    const int run = rem / w;
+    j = sb * p.sb_width + (rem - run * w);
+    r0 = run * p.run_len;
+    r1 = min(r0 + p.run_len, p.num_row_blocks);
+}
+
+__device__ __forceinline__ float count_to_float(uint32_t c) {
+    // exact for 0 <= c < 2^23: plant the integer in the mantissa of 2^23
+    return __uint_as_float(c | 0x4B000000u) - 8388608.0f;
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x0,
+                 const __grid_constant__ CUtensorMap tm_s, const PlaceParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NUM_STAGES * STAGE_BYTES);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + NUM_STAGES;
+    uint64_t* tfull_bar = bars + 2 * NUM_STAGES;
+    uint64_t* tempty_bar = bars + 2 * NUM_STAGES + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * NUM_STAGES + 4);
+    float* red = reinterpret_cast<float*>(smem + NUM_STAGES * STAGE_BYTES + SMEM_BARRIER_BYTES);
+
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp_idx == 0 && ptx::elect_one()) {
+        ptx::prefetch_tmap(&tm_x1);
+        ptx::prefetch_tmap(&tm_x0);
+        ptx::prefetch_tmap(&tm_s);
+        for (int s = 0; s < NUM_STAGES; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            ptx::mbar_init(&tfull_bar[a], 1);
+            ptx::mbar_init(&tempty_bar[a], NUM_EPI_WARPS);
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp_idx == 1) {
+        ptx::tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp_idx == 0) {
+        // ======================= TMA producer (one lane) =======================
+        if (ptx::elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < p.num_tasks; t += gridDim.x) {
+                int j, r0, r1;
+                decode_task(p, t, j, r0, r1);
+                for (int r = r0; r < r1; ++r) {
+                    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* st = smem + stage * STAGE_BYTES;
+                        ptx::mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                        ptx::tma_load_2d(&tm_x1, &full_bar[stage], st, kb * BLOCK_K, r * BLOCK_M);
+                        ptx::tma_load_2d(&tm_x0, &full_bar[stage], st + STAGE_A_BYTES, kb * BLOCK_K, r * BLOCK_M);
+                        ptx::tma_load_2d(&tm_s, &full_bar[stage], st + 2 * STAGE_A_BYTES, kb * BLOCK_K, j * BLOCK_N);
+                        if (++stage == NUM_STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp_idx == 1) {
+        // ======================= MMA issuer (one lane) =========================
+        if (ptx::elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < p.num_tasks; t += gridDim.x) {
+                int j, r0, r1;
+                decode_task(p, t, j, r0, r1);
+                for (int r = r0; r < r1; ++r) {
+                    ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                    ptx::tc_fence_after();
+                    const uint32_t d1 = tmem_base + acc * 2 * BLOCK_N;
+                    const uint32_t d0 = d1 + BLOCK_N;
+                    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                        ptx::mbar_wait(&full_bar[stage], phase);
+                        ptx::tc_fence_after();
+                        const uint32_t st = ptx::smem_u32(smem + stage * STAGE_BYTES);
+                        const uint64_t dx1 = ptx::make_kmajor_sw128_desc(st);
+                        const uint64_t dx0 = ptx::make_kmajor_sw128_desc(st + STAGE_A_BYTES);
+                        const uint64_t ds = ptx::make_kmajor_sw128_desc(st + 2 * STAGE_A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                            // advance 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
+                            const uint64_t koff = uint64_t(k * (UMMA_K >> 4));
+                            const uint32_t accum = (kb | k) != 0;
+                            ptx::mma_i8_ss(d1, dx1 + koff, ds + koff, IDESC_I8, accum);
+                            ptx::mma_i8_ss(d0, dx0 + koff, ds + koff, IDESC_I8, accum);
+                        }
+                        ptx::mma_commit(&empty_bar[stage]);
+                        if (++stage == NUM_STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    ptx::mma_commit(&tfull_bar[acc]);
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ======================= epilogue warps ================================
+        const int ew = warp_idx - 2;
+        const int q = warp_idx & 3;   // TMEM lane quarter this warp may touch
+        const int hh = ew >> 2;       // column half of the tile
+        const uint32_t lane_base = uint32_t(q * 32) << 16;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < p.num_tasks; t += gridDim.x) {
+            int j, r0, r1;
+            decode_task(p, t, j, r0, r1);
+            const int col0 = j * BLOCK_N + hh * 64;
+            const int n_valid = max(0, min(64, p.N - col0));
+            float colacc[64];
+            if (PASS == PASS_COLSUM) {
+#pragma unroll
+                for (int i = 0; i < 64; ++i) colacc[i] = 0.f;
+            }
+            for (int r = r0; r < r1; ++r) {
+                ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+                ptx::tc_fence_after();
+                const int row = r * BLOCK_M + q * 32 + lane;
+                const uint32_t taddr = tmem_base + lane_base + acc * 2 * BLOCK_N + hh * 64;
+                uint32_t c1[32], c0[32];
+                if (PASS == PASS_DUMP) {
+#pragma unroll
+                    for (int ch = 0; ch < 2; ++ch) {
+                        ptx::tmem_ld_x32(taddr + ch * 32, c1);
+                        ptx::tmem_ld_x32(taddr + BLOCK_N + ch * 32, c0);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const size_t o = (size_t(row) * p.N_pad + col0 + ch * 32 + i) * 2;
+                            p.dump[o] = int(c1[i]);
+                            p.dump[o + 1] = int(c0[i]);
+                        }
+                    }
+                } else if (PASS == PASS_STATS) {
+                    float best = -INFINITY, b1 = 0.f, b0 = 0.f;
+#pragma unroll
+                    for (int ch = 0; ch < 2; ++ch) {
+                        ptx::tmem_ld_x32(taddr + ch * 32, c1);
+                        ptx::tmem_ld_x32(taddr + BLOCK_N + ch * 32, c0);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float f1 = count_to_float(c1[i]);
+                            const float f0 = count_to_float(c0[i]);
+                            const float v = fmaf(p.a1f, f1, p.a0f * f0);
+                            const bool take = (ch * 32 + i < n_valid) && (v > best);
+                            best = take ? v : best;
+                            b1 = take ? f1 : b1;
+                            b0 = take ? f0 : b0;
+                        }
+                    }
+                    float sum = 0.f;
+#pragma unroll
+                    for (int ch = 0; ch < 2; ++ch) {
+                        ptx::tmem_ld_x32(taddr + ch * 32, c1);
+                        ptx::tmem_ld_x32(taddr + BLOCK_N + ch * 32, c0);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float e1 = count_to_float(c1[i]) - b1;
+                            const float e0 = count_to_float(c0[i]) - b0;
+                            const float s = fmaf(p.a1h, e1, p.a0h * e0);   // exact operands, one rounding
+                            const float lo = fmaf(p.a1l, e1, p.a0l * e0);
+                            const float e = exp2f(s + lo);
+                            sum += (ch * 32 + i < n_valid) ? e : 0.f;
+                        }
+                    }
+                    const uint32_t pk = uint32_t(b1) | (uint32_t(b0) << 16);
+                    p.stats[size_t(j * 2 + hh) * p.M_pad + row] = make_uint2(pk, __float_as_uint(sum));
+                } else {
+                    const uint2 rr = p.rowref[row];
+                    const float r1f = float(rr.x & 0xFFFFu);
+                    const float r0f = float(rr.x >> 16);
+                    const float L = __uint_as_float(rr.y);
+                    const bool rowvalid = row < p.M;
+#pragma unroll
+                    for (int ch = 0; ch < 2; ++ch) {
+                        ptx::tmem_ld_x32(taddr + ch * 32, c1);
+                        ptx::tmem_ld_x32(taddr + BLOCK_N + ch * 32, c0);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float e1 = count_to_float(c1[i]) - r1f;
+                            const float e0 = count_to_float(c0[i]) - r0f;
+                            const float s = fmaf(p.a1h, e1, p.a0h * e0);
+                            const float tl = fmaf(p.a0l, e0, -L);
+                            const float lo = fmaf(p.a1l, e1, tl);
+                            const float e = exp2f(s + lo);
+                            colacc[ch * 32 + i] += rowvalid ? e : 0.f;
+                        }
+                    }
+                }
+                // accumulator stage drained: hand it back to the MMA warp
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+            if (PASS == PASS_COLSUM) {
+                // rows -> one number per column: lanes, then the four lane quarters
+#pragma unroll
+                for (int i = 0; i < 64; ++i) {
+                    float v = colacc[i];
+                    v += __shfl_xor_sync(0xffffffffu, v, 16);
+                    v += __shfl_xor_sync(0xffffffffu, v, 8);
+                    v += __shfl_xor_sync(0xffffffffu, v, 4);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    if (lane == (i & 31)) red[q * BLOCK_N + hh * 64 + i] = v;
+                }
+                asm volatile("bar.sync 1, %0;\n" ::"n"(NUM_EPI_WARPS * 32) : "memory");
+                const int et = threadIdx.x - 64;
+                if (et < BLOCK_N) {
+                    const float v = ((red[et] + red[BLOCK_N + et]) + red[2 * BLOCK_N + et]) + red[3 * BLOCK_N + et];
+                    const int run = r0 / p.run_len;
+                    p.colpart[size_t(run) * p.N_pad + j * BLOCK_N + et] = v;
+                }
+                asm volatile("bar.sync 1, %0;\n" ::"n"(NUM_EPI_WARPS * 32) : "memory");
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp_idx == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------- operand expansion
+// 2-bit genotype codes (0 wild type, 1 het, 2 hom, 3 missing; 4 cells per byte,
+// cell c in bits [2*(c%4), +2)) -> two 0/1 byte planes, K-major, zero padded.
+__global__ void scs_expand_genotypes_kernel(const uint8_t* __restrict__ gt, int64_t gt_pitch, int M, int n_cells,
+                                            uint8_t* __restrict__ x1, uint8_t* __restrict__ x0, int K_pad) {
+    const int kq = blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 cells
+    const int row = blockIdx.y;
+    if (kq * 4 >= K_pad || row >= M) return;
+    uint32_t o1 = 0, o0 = 0;
+    if (kq * 4 < n_cells) {
+        const uint32_t b = gt[size_t(row) * gt_pitch + kq];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t code = (b >> (2 * i)) & 3u;
+            const bool in = kq * 4 + i < n_cells;
+            o1 |= uint32_t(in && (code == 1u || code == 2u)) << (8 * i);
+            o0 |= uint32_t(in && code == 0u) << (8 * i);
+        }
+    }
+    *reinterpret_cast<uint32_t*>(x1 + size_t(row) * K_pad + kq * 4) = o1;
+    *reinterpret_cast<uint32_t*>(x0 + size_t(row) * K_pad + kq * 4) = o0;
+}
+
+// clade bit mask [N][words] (bit c%32 of word c/32 set when cell c is below the
+// node) -> 0/1 byte matrix, K-major, zero padded.
+__global__ void scs_expand_clades_kernel(const uint32_t* __restrict__ bits, int64_t pitch_words, int N, int n_cells,
+                                         uint8_t* __restrict__ s, int K_pad) {
+    const int kq = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = blockIdx.y;
+    if (kq * 4 >= K_pad || row >= N) return;
+    uint32_t o = 0;
+    if (kq * 4 < n_cells) {
+        const uint32_t w = bits[size_t(row) * pitch_words + (kq >> 3)] >> ((kq & 7) * 4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const bool in = kq * 4 + i < n_cells;
+            o |= uint32_t(in && ((w >> i) & 1u)) << (8 * i);
+        }
+    }
+    *reinterpret_cast<uint32_t*>(s + size_t(row) * K_pad + kq * 4) = o;
+}
+
+// ------------------------------------------------------------ small kernels
+// Merge the per-(row, half tile) partials of pass 1 into one record per SNV:
+// the reference counts of the globally best column and log2 sum_b 2^(logit-ref).
+__global__ void scs_merge_stats_kernel(const uint2* __restrict__ stats, int num_parts, int M, int M_pad,
+                                       const uint8_t* __restrict__ row_keep, double a1, double a0,
+                                       uint2* __restrict__ rowref) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= M_pad) return;
+    if (row >= M || (row_keep != nullptr && row_keep[row] == 0)) {
+        rowref[row] = make_uint2(0u, __float_as_uint(INFINITY));  // 2^(x - inf) = 0: row contributes nothing
+        return;
+    }
+    double best = -1e300;
+    uint32_t best_pk = 0;
+    for (int s = 0; s < num_parts; ++s) {
+        const uint2 v = stats[size_t(s) * M_pad + row];
+        if (__uint_as_float(v.y) > 0.f) {
+            const double l = a1 * double(v.x & 0xFFFFu) + a0 * double(v.x >> 16);
+            if (l > best) {
+                best = l;
+                best_pk = v.x;
+            }
+        }
+    }
+    double total = 0.0;
+    for (int s = 0; s < num_parts; ++s) {
+        const uint2 v = stats[size_t(s) * M_pad + row];
+        const float sm = __uint_as_float(v.y);
+        if (sm > 0.f) {
+            const double l = a1 * double(v.x & 0xFFFFu) + a0 * double(v.x >> 16);
+            total += double(sm) * exp2(l - best);
+        }
+    }
+    rowref[row] = make_uint2(best_pk, __float_as_uint(float(log2(total))));
+}
+
+// Y[b] = sum over runs of the per-run column partials, in a fixed order, in fp64.
+__global__ void scs_reduce_colpart_kernel(const float* __restrict__ colpart, int num_runs, int N, int N_pad,
+                                          double* __restrict__ y) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= N) return;
+    double acc = 0.0;
+    for (int r = 0; r < num_runs; ++r) acc += double(colpart[size_t(r) * N_pad + b]);
+    y[b] = acc;
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (fn) return fn;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+    return fn;
+}
+
+static int make_u8_tmap(CUtensorMap* tm, void* base, uint64_t rows, uint64_t k_pad, uint32_t box_rows) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) return set_error(SCS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[2] = {k_pad, rows};
+    cuuint64_t strides[1] = {k_pad};
+    cuuint32_t box[2] = {BLOCK_K, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(SCS_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", int(r));
+    return SCS_OK;
+}
+
+struct Placement {
+    scs_ctx* ctx = nullptr;
+    int64_t n_snv = 0;
+    int n_cells = 0, n_rows = 0;
+    int M_pad = 0, N_pad = 0, K_pad = 0;
+    uint8_t *x1 = nullptr, *x0 = nullptr, *s = nullptr;
+    uint8_t* row_keep = nullptr;  // optional, device
+    bool have_row_keep = false;
+    uint2* stats = nullptr;
+    uint2* rowref = nullptr;
+    float* colpart = nullptr;
+    double* y = nullptr;
+    int* dump = nullptr;
+    CUtensorMap tm_x1, tm_x0, tm_s;
+    PlaceParams prm;
+    int grid = 0;
+    uint8_t* stage_gt = nullptr;   // device staging for host-side genotype uploads
+    size_t stage_gt_bytes = 0;
+    uint32_t* stage_mask = nullptr;
+    size_t stage_mask_bytes = 0;
+    long long launches = 0;
+};
+
+static int round_up(int64_t v, int m) { return int((v + m - 1) / m * m); }
+
+static float round_to_bits(double v, int bits) {
+    if (v == 0.0) return 0.f;
+    int e;
+    const double m = frexp(v, &e);  // v = m * 2^e, 0.5 <= |m| < 1
+    const double sc = ldexp(1.0, bits);
+    return float(ldexp(nearbyint(m * sc) / sc, e));
+}
+
+}  // namespace scs
+
+using namespace scs;
+
+extern "C" {
+
+int scs_placement_create(scs_ctx* ctx, int64_t n_snv, int32_t n_cells, int32_t n_rows, scs_placement** out) {
+    if (!ctx || !out) return set_error(SCS_ERR_ARG, "null argument");
+    if (n_snv <= 0 || n_cells <= 0 || n_rows <= 0) return set_error(SCS_ERR_ARG, "empty problem (n_snv=%lld n_cells=%d n_rows=%d)", (long long)n_snv, n_cells, n_rows);
+    if (n_cells > 65535) return set_error(SCS_ERR_ARG, "n_cells %d exceeds the 16-bit count packing (65535)", n_cells);
+    if (n_snv > (int64_t(1) << 30)) return set_error(SCS_ERR_ARG, "n_snv too large for one placement plan; shard by SNV rows");
+    SCS_CUDA(cudaSetDevice(ctx->device));
+    Placement* pl = new Placement();
+    pl->ctx = ctx;
+    pl->n_snv = n_snv;
+    pl->n_cells = n_cells;
+    pl->n_rows = n_rows;
+    pl->M_pad = round_up(n_snv, BLOCK_M);
+    pl->N_pad = round_up(n_rows, BLOCK_N);
+    pl->K_pad = round_up(n_cells, BLOCK_K);
+    const size_t plane = size_t(pl->M_pad) * pl->K_pad;
+    const size_t sbytes = size_t(pl->N_pad) * pl->K_pad;
+    PlaceParams& p = pl->prm;
+    memset(&p, 0, sizeof(p));
+    p.M = int(n_snv);
+    p.N = n_rows;
+    p.M_pad = pl->M_pad;
+    p.N_pad = pl->N_pad;
+    p.num_k_blocks = pl->K_pad / BLOCK_K;
+    p.num_row_blocks = pl->M_pad / BLOCK_M;
+    p.num_col_tiles = pl->N_pad / BLOCK_N;
+    // Super-block: as many column tiles as keep the clade slab within ~40 MB of L2.
+    const size_t slab = size_t(BLOCK_N) * pl->K_pad;
+    int sbw = int(std::max<size_t>(1, (size_t(40) << 20) / slab));
+    p.sb_width = std::min(sbw, p.num_col_tiles);
+    // Runs: long enough to amortise the end-of-run column reduction, short enough
+    // that every SM gets several tasks.
+    int run_len = 32;
+    while (run_len > 1 && (int64_t(p.num_row_blocks + run_len - 1) / run_len) * p.num_col_tiles < 4 * ctx->sm_count) run_len >>= 1;
+    p.run_len = run_len;
+    p.num_runs = (p.num_row_blocks + run_len - 1) / run_len;
+    p.num_tasks = p.num_runs * p.num_col_tiles;
+    pl->grid = std::min(ctx->sm_count, p.num_tasks);
+
+    int rc = SCS_OK;
+    do {
+        if (cudaMalloc(&pl->x1, plane) != cudaSuccess || cudaMalloc(&pl->x0, plane) != cudaSuccess ||
+            cudaMalloc(&pl->s, sbytes) != cudaSuccess ||
+            cudaMalloc(&pl->stats, size_t(p.num_col_tiles) * 2 * pl->M_pad * sizeof(uint2)) != cudaSuccess ||
+            cudaMalloc(&pl->rowref, size_t(pl->M_pad) * sizeof(uint2)) != cudaSuccess ||
+            cudaMalloc(&pl->colpart, size_t(p.num_runs) * pl->N_pad * sizeof(float)) != cudaSuccess ||
+            cudaMalloc(&pl->y, size_t(pl->N_pad) * sizeof(double)) != cudaSuccess ||
+            cudaMalloc(&pl->row_keep, size_t(pl->M_pad)) != cudaSuccess) {
+            rc = set_error(SCS_ERR_OOM, "device allocation failed for placement plan (%s)", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        cudaMemset(pl->x1, 0, plane);
+        cudaMemset(pl->x0, 0, plane);
+        cudaMemset(pl->s, 0, sbytes);
+        p.stats = pl->stats;
+        p.rowref = pl->rowref;
+        p.colpart = pl->colpart;
+        if ((rc = make_u8_tmap(&pl->tm_x1, pl->x1, pl->M_pad, pl->K_pad, BLOCK_M)) != SCS_OK) break;
+        if ((rc = make_u8_tmap(&pl->tm_x0, pl->x0, pl->M_pad, pl->K_pad, BLOCK_M)) != SCS_OK) break;
+        if ((rc = make_u8_tmap(&pl->tm_s, pl->s, pl->N_pad, pl->K_pad, BLOCK_N)) != SCS_OK) break;
+        cudaFuncSetAttribute(scs_place_kernel<PASS_DUMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+        cudaFuncSetAttribute(scs_place_kernel<PASS_STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+        cudaFuncSetAttribute(scs_place_kernel<PASS_COLSUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+            rc = set_error(SCS_ERR_CUDA, "placement plan setup failed: %s", cudaGetErrorString(e));
+            break;
+        }
+    } while (0);
+    if (rc != SCS_OK) {
+        scs_placement_destroy(reinterpret_cast<scs_placement*>(pl));
+        return rc;
+    }
+    *out = reinterpret_cast<scs_placement*>(pl);
+    return SCS_OK;
+}
+
+int scs_placement_destroy(scs_placement* h) {
+    Placement* pl = reinterpret_cast<Placement*>(h);
+    if (!pl) return SCS_OK;
+    cudaFree(pl->x1);
+    cudaFree(pl->x0);
+    cudaFree(pl->s);
+    cudaFree(pl->stats);
+    cudaFree(pl->rowref);
+    cudaFree(pl->colpart);
+    cudaFree(pl->y);
+    cudaFree(pl->row_keep);
+    cudaFree(pl->dump);
+    cudaFree(pl->stage_gt);
+    cudaFree(pl->stage_mask);
+    delete pl;
+    return SCS_OK;
+}
+
+int scs_placement_set_genotypes(scs_placement* h, const uint8_t* d_gt, int64_t pitch_bytes, const uint8_t* d_row_keep, void* stream) {
+    Placement* pl = reinterpret_cast<Placement*>(h);
+    if (!pl || !d_gt) return set_error(SCS_ERR_ARG, "null argument");
+    if (pitch_bytes < (pl->n_cells + 3) / 4) return set_error(SCS_ERR_ARG, "genotype row pitch %lld is smaller than ceil(n_cells/4)", (long long)pitch_bytes);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    dim3 block(128), grid((pl->K_pad / 4 + 127) / 128, unsigned(pl->n_snv));
+    if (pl->n_snv > 65535) {
+        // grid.y is limited to 65535: walk the rows in slabs
+        for (int64_t r0 = 0; r0 < pl->n_snv; r0 += 65535) {
+            const int rows = int(std::min<int64_t>(65535, pl->n_snv - r0));
+            grid.y = rows;
+            scs_expand_genotypes_kernel<<<grid, block, 0, st>>>(d_gt + r0 * pitch_bytes, pitch_bytes, rows, pl->n_cells,
+                                                                 pl->x1 + size_t(r0) * pl->K_pad, pl->x0 + size_t(r0) * pl->K_pad, pl->K_pad);
+            pl->launches++;
+        }
+    } else {
+        scs_expand_genotypes_kernel<<<grid, block, 0, st>>>(d_gt, pitch_bytes, int(pl->n_snv), pl->n_cells, pl->x1, pl->x0, pl->K_pad);
+        pl->launches++;
+    }
+    if (d_row_keep) {
+        SCS_CUDA(cudaMemcpyAsync(pl->row_keep, d_row_keep, size_t(pl->n_snv), cudaMemcpyDeviceToDevice, st));
+        pl->have_row_keep = true;
+    } else {
+        pl->have_row_keep = false;
+    }
+    SCS_CUDA(cudaGetLastError());
+    return SCS_OK;
+}
+
+int scs_placement_set_clades(scs_placement* h, const uint32_t* d_bits, int64_t pitch_words, void* stream) {
+    Placement* pl = reinterpret_cast<Placement*>(h);
+    if (!pl || !d_bits) return set_error(SCS_ERR_ARG, "null argument");
+    if (pitch_words < (pl->n_cells + 31) / 32) return set_error(SCS_ERR_ARG, "clade mask pitch %lld is smaller than ceil(n_cells/32)", (long long)pitch_words);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    dim3 block(128), grid((pl->K_pad / 4 + 127) / 128, 1);
+    for (int r0 = 0; r0 < pl->n_rows; r0 += 65535) {
+        const int rows = std::min(65535, pl->n_rows - r0);
+        grid.y = rows;
+        scs_expand_clades_kernel<<<grid, block, 0, st>>>(d_bits + size_t(r0) * pitch_words, pitch_words, rows, pl->n_cells,
+                                                          pl->s + size_t(r0) * pl->K_pad, pl->K_pad);
+        pl->launches++;
+    }
+    SCS_CUDA(cudaGetLastError());
+    return SCS_OK;
+}
+
+int scs_placement_set_genotypes_host(scs_placement* h, const uint8_t* gt, int64_t pitch_bytes, const uint8_t* row_keep, void* stream) {
+    Placement* pl = reinterpret_cast<Placement*>(h);
+    if (!pl || !gt) return set_error(SCS_ERR_ARG, "null argument");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t bytes = size_t(pl->n_snv) * pitch_bytes + (row_keep ? size_t(pl->n_snv) : 0);
+    if (bytes > pl->stage_gt_bytes) {
+        cudaFree(pl->stage_gt);
+        pl->stage_gt = nullptr;
+        pl->stage_gt_bytes = 0;
+        if (cudaMalloc(&pl->stage_gt, bytes) != cudaSuccess) return set_error(SCS_ERR_OOM, "device staging allocation of %zu bytes failed", bytes);
+        pl->stage_gt_bytes = bytes;
+    }
+    SCS_CUDA(cudaMemcpyAsync(pl->stage_gt, gt, size_t(pl->n_snv) * pitch_bytes, cudaMemcpyHostToDevice, st));
+    uint8_t* d_keep = nullptr;
+    if (row_keep) {
+        d_keep = pl->stage_gt + size_t(pl->n_snv) * pitch_bytes;
+        SCS_CUDA(cudaMemcpyAsync(d_keep, row_keep, size_t(pl->n_snv), cudaMemcpyHostToDevice, st));
+    }
+    return scs_placement_set_genotypes(h, pl->stage_gt, pitch_bytes, d_keep, stream);
+}
+
+int scs_placement_set_clades_host(scs_placement* h, const uint32_t* bits, int64_t pitch_words, void* stream) {
+    Placement* pl = reinterpret_cast<Placement*>(h);
+    if (!pl || !bits) return set_error(SCS_ERR_ARG, "null argument");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t bytes = size_t(pl->n_rows) * pitch_words * 4;
+    if (bytes > pl->stage_mask_bytes) {
+        cudaFree(pl->stage_mask);
+        pl->stage_mask = nullptr;
+        pl->stage_mask_bytes = 0;
+        if (cudaMalloc(&pl->stage_mask, bytes) != cudaSuccess) return set_error(SCS_ERR_OOM, "device staging allocation of %zu bytes failed", bytes);
+        pl->stage_mask_bytes = bytes;
+    }
+    SCS_CUDA(cudaMemcpyAsync(pl->stage_mask, bits, bytes, cudaMemcpyHostToDevice, st));
+    return scs_placement_set_clades(h, pl->stage_mask, pitch_words, stream);
+}
+
+static void fill_constants(Placement* pl, double FP, double FN, double* a1_out, double* a0_out) {
+    const double LOG2E = 1.4426950408889634074;
+    const double a1 = (log1p(-FN) - log(FP)) * LOG2E;   // log2((1-FN)/FP)
+    const double a0 = (log(FN) - log1p(-FP)) * LOG2E;   // log2(FN/(1-FP))
+    int cbits = 1;
+    while ((1 << cbits) <= pl->n_cells) ++cbits;         // counts and their differences fit cbits (+sign)
+    const int hbits = std::max(4, 24 - cbits);
+    PlaceParams& p = pl->prm;
+    p.a1h = round_to_bits(a1, hbits);
+    p.a0h = round_to_bits(a0, hbits);
+    p.a1l = float(a1 - double(p.a1h));
+    p.a0l = float(a0 - double(p.a0h));
+    p.a1f = float(a1);
+    p.a0f = float(a0);
+    *a1_out = a1;
+    *a0_out = a0;
+}
+
+int scs_placement_run(scs_placement* h, double FP, double FN, double* d_soft_weights, void* stream) {
+    Placement* pl = reinterpret_cast<Placement*>(h);
+    if (!pl) return set_error(SCS_ERR_ARG, "null plan");
+    if (!(FP > 0.0 && FP < 1.0 && FN > 0.0 && FN < 1.0)) return set_error(SCS_ERR_ARG, "error rates must lie in (0,1): FP=%g FN=%g", FP, FN);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    double a1, a0;
+    fill_constants(pl, FP, FN, &a1, &a0);
+    const PlaceParams& p = pl->prm;
+    scs_place_kernel<PASS_STATS><<<pl->grid, NUM_THREADS, SMEM_TOTAL, st>>>(pl->tm_x1, pl->tm_x0, pl->tm_s, p);
+    scs_merge_stats_kernel<<<(p.M_pad + 255) / 256, 256, 0, st>>>(pl->stats, p.num_col_tiles * 2, p.M, p.M_pad,
+                                                                  pl->have_row_keep ? pl->row_keep : nullptr, a1, a0, pl->rowref);
+    scs_place_kernel<PASS_COLSUM><<<pl->grid, NUM_THREADS, SMEM_TOTAL, st>>>(pl->tm_x1, pl->tm_x0, pl->tm_s, p);
+    double* y = d_soft_weights ? d_soft_weights : pl->y;
+    scs_reduce_colpart_kernel<<<(p.N + 255) / 256, 256, 0, st>>>(pl->colpart, p.num_runs, p.N, p.N_pad, y);
+    pl->launches += 4;
+    SCS_CUDA(cudaGetLastError());
+    return SCS_OK;
+}
+
+int scs_placement_run_host(scs_placement* h, double FP, double FN, double* soft_weights, void* stream) {
+    Placement* pl = reinterpret_cast<Placement*>(h);
+    if (!pl || !soft_weights) return set_error(SCS_ERR_ARG, "null argument");
+    int rc = scs_placement_run(h, FP, FN, nullptr, stream);
+    if (rc != SCS_OK) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    SCS_CUDA(cudaMemcpyAsync(soft_weights, pl->y, size_t(pl->n_rows) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SCS_CUDA(cudaStreamSynchronize(st));
+    return SCS_OK;
+}
+
+// Debug / parity aid: raw integer counts C1, C0 for every (SNV, clade row).
+// Only meant for small problems (the buffer is M_pad x N_pad x 2 ints).
+int scs_placement_debug_counts(scs_placement* h, int32_t* counts_host, void* stream) {
+    Placement* pl = reinterpret_cast<Placement*>(h);
+    if (!pl || !counts_host) return set_error(SCS_ERR_ARG, "null argument");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t n = size_t(pl->M_pad) * pl->N_pad * 2;
+    if (n > (size_t(1) << 28)) return set_error(SCS_ERR_ARG, "debug count dump is limited to small problems");
+    if (!pl->dump && cudaMalloc(&pl->dump, n * sizeof(int)) != cudaSuccess) return set_error(SCS_ERR_OOM, "debug dump allocation failed");
+    PlaceParams p = pl->prm;
+    p.dump = pl->dump;
+    scs_place_kernel<PASS_DUMP><<<pl->grid, NUM_THREADS, SMEM_TOTAL, st>>>(pl->tm_x1, pl->tm_x0, pl->tm_s, p);
+    pl->launches++;
+    SCS_CUDA(cudaGetLastError());
+    std::vector<int> tmp(n);
+    SCS_CUDA(cudaMemcpyAsync(tmp.data(), pl->dump, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    SCS_CUDA(cudaStreamSynchronize(st));
+    for (int64_t i = 0; i < pl->n_snv; ++i)
+        memcpy(counts_host + size_t(i) * pl->n_rows * 2, tmp.data() + size_t(i) * pl->N_pad * 2, size_t(pl->n_rows) * 2 * sizeof(int));
+    return SCS_OK;
+}
+
+int scs_placement_info(scs_placement* h, int64_t* info, int32_t n) {
+    Placement* pl = reinterpret_cast<Placement*>(h);
+    if (!pl || !info) return set_error(SCS_ERR_ARG, "null argument");
+    const int64_t v[10] = {pl->M_pad, pl->N_pad, pl->K_pad, pl->prm.num_tasks, pl->prm.run_len, pl->prm.sb_width, pl->grid, pl->launches, pl->prm.num_runs, SMEM_TOTAL};
+    for (int i = 0; i < n && i < 10; ++i) info[i] = v[i];
+    return SCS_OK;
+}
+
+const void* scs_placement_device_result(scs_placement* h) {
+    Placement* pl = reinterpret_cast<Placement*>(h);
+    return pl ? pl->y : nullptr;
+}
+
+}  // extern "C"

@@ -1,0 +1,181 @@
+"""Host-side handles over the C ABI: context, placement plan, packing helpers.
+
+Only plumbing lives here (numpy packing, pointer passing, stream selection);
+every number the PT test reports is produced by the CUDA library.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import check, lib, ptr
+
+
+# ------------------------------------------------------------------ packing
+def pack_genotypes(muts):
+    """{0,1,2,NaN} SNV x cell matrix (the reference's ``muts`` values,
+    run_PT_test.py:156-167) -> 2-bit codes, 4 cells per byte, row pitch padded to
+    16 bytes.  Returns (packed uint8 [n_snv, pitch], pitch)."""
+    muts = np.asarray(muts)
+    n_snv, n_cells = muts.shape
+    if muts.dtype.kind == "f":
+        codes = np.where(np.isnan(muts), _cabi.GT_MISSING, np.nan_to_num(muts, nan=0.0)).astype(np.uint8)
+    else:
+        codes = muts.astype(np.uint8)
+    if codes.size and codes.max() > 3:
+        raise ValueError("genotype codes must be in {0,1,2,3}")
+    pitch = ((n_cells + 3) // 4 + 15) // 16 * 16
+    padded = np.zeros((n_snv, pitch * 4), dtype=np.uint8)
+    padded[:, :n_cells] = codes
+    q = padded.reshape(n_snv, pitch, 4)
+    packed = (q[:, :, 0] | (q[:, :, 1] << 2) | (q[:, :, 2] << 4) | (q[:, :, 3] << 6)).astype(np.uint8)
+    return np.ascontiguousarray(packed), pitch
+
+
+def unpack_genotypes(packed, n_cells):
+    """Inverse of pack_genotypes -> uint8 codes [n_snv, n_cells]."""
+    packed = np.asarray(packed, dtype=np.uint8)
+    n_snv = packed.shape[0]
+    out = np.empty((n_snv, packed.shape[1] * 4), dtype=np.uint8)
+    for i in range(4):
+        out[:, i::4] = (packed >> (2 * i)) & 3
+    return out[:, :n_cells]
+
+
+def pack_clades(S):
+    """0/1 clade matrix [n_rows, n_cells] (S of run_PT_test.py:389-397) -> uint32
+    bit mask [n_rows, words], bit c%32 of word c//32."""
+    S = np.asarray(S).astype(bool)
+    n_rows, n_cells = S.shape
+    words = (n_cells + 31) // 32
+    padded = np.zeros((n_rows, words * 32), dtype=np.uint8)
+    padded[:, :n_cells] = S
+    bits = np.packbits(padded.reshape(n_rows, words, 32), axis=2, bitorder="little")
+    return np.ascontiguousarray(bits.view("<u4").reshape(n_rows, words)), words
+
+
+def unpack_clades(bits, n_cells):
+    bits = np.ascontiguousarray(bits, dtype="<u4")
+    n_rows = bits.shape[0]
+    u8 = bits.view(np.uint8).reshape(n_rows, -1)
+    return np.unpackbits(u8, axis=1, bitorder="little")[:, :n_cells].astype(bool)
+
+
+# ------------------------------------------------------------------ handles
+def _stream_handle(stream):
+    if stream is None:
+        return None
+    if isinstance(stream, int):
+        return C.c_void_p(stream)
+    return C.c_void_p(stream.cuda_stream)  # torch.cuda.Stream
+
+
+def _dev_ptr(t):
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return C.c_void_p(t)
+    return C.c_void_p(t.data_ptr())  # torch tensor on the device
+
+
+class Context:
+    """One per process/GPU (scs_ctx)."""
+
+    def __init__(self, device=0):
+        h = C.c_void_p()
+        check(lib().scs_ctx_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+        info = (C.c_int64 * 6)()
+        check(lib().scs_ctx_info(self._h, info, 6))
+        self.sm_count, self.cc_major, self.cc_minor, self.total_mem_mib, self.l2_bytes = [int(v) for v in info[:5]]
+
+    def close(self):
+        if self._h:
+            lib().scs_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Placement:
+    """Device-resident placement plan (scs_placement) for one problem shape."""
+
+    def __init__(self, ctx, n_snv, n_cells, n_rows):
+        self.ctx = ctx
+        self.n_snv, self.n_cells, self.n_rows = int(n_snv), int(n_cells), int(n_rows)
+        h = C.c_void_p()
+        check(lib().scs_placement_create(ctx._h, self.n_snv, self.n_cells, self.n_rows, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if self._h:
+            lib().scs_placement_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        v = (C.c_int64 * 10)()
+        check(lib().scs_placement_info(self._h, v, 10))
+        keys = ("M_pad", "N_pad", "K_pad", "tasks", "run_len", "superblock_width", "grid", "launches", "runs", "smem_bytes")
+        return dict(zip(keys, (int(x) for x in v)))
+
+    # host buffers (numpy)
+    def set_genotypes_host(self, packed, pitch, row_keep=None, stream=None):
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        assert packed.shape == (self.n_snv, pitch)
+        if row_keep is not None:
+            row_keep = np.ascontiguousarray(row_keep, dtype=np.uint8)
+            assert row_keep.shape == (self.n_snv,)
+        check(lib().scs_placement_set_genotypes_host(self._h, ptr(packed), int(pitch), ptr(row_keep), _stream_handle(stream)))
+
+    def set_clades_host(self, bits, words, stream=None):
+        bits = np.ascontiguousarray(bits, dtype=np.uint32)
+        assert bits.shape == (self.n_rows, words)
+        check(lib().scs_placement_set_clades_host(self._h, ptr(bits), int(words), _stream_handle(stream)))
+
+    # device buffers (torch tensors or raw addresses)
+    def set_genotypes(self, d_packed, pitch, d_row_keep=None, stream=None):
+        check(lib().scs_placement_set_genotypes(self._h, _dev_ptr(d_packed), int(pitch), _dev_ptr(d_row_keep), _stream_handle(stream)))
+
+    def set_clades(self, d_bits, words, stream=None):
+        check(lib().scs_placement_set_clades(self._h, _dev_ptr(d_bits), int(words), _stream_handle(stream)))
+
+    def run(self, FP, FN, d_out=None, stream=None):
+        """Asynchronous; result in ``d_out`` (device, float64[n_rows]) or in the plan."""
+        check(lib().scs_placement_run(self._h, float(FP), float(FN), _dev_ptr(d_out), _stream_handle(stream)))
+
+    def run_host(self, FP, FN, stream=None):
+        out = np.empty(self.n_rows, dtype=np.float64)
+        check(lib().scs_placement_run_host(self._h, float(FP), float(FN), ptr(out), _stream_handle(stream)))
+        return out
+
+    def device_result_ptr(self):
+        return int(lib().scs_placement_device_result(self._h))
+
+    def debug_counts(self, stream=None):
+        out = np.empty((self.n_snv, self.n_rows, 2), dtype=np.int32)
+        check(lib().scs_placement_debug_counts(self._h, ptr(out), _stream_handle(stream)))
+        return out
+
+
+def map_mutations(ctx, packed, pitch, clade_bits, words, n_cells, FP, FN, row_keep=None):
+    """One-shot host call (scs_map_mutations): soft branch weights float64[n_rows]."""
+    packed = np.ascontiguousarray(packed, dtype=np.uint8)
+    clade_bits = np.ascontiguousarray(clade_bits, dtype=np.uint32)
+    n_snv, n_rows = packed.shape[0], clade_bits.shape[0]
+    if row_keep is not None:
+        row_keep = np.ascontiguousarray(row_keep, dtype=np.uint8)
+    out = np.empty(n_rows, dtype=np.float64)
+    check(lib().scs_map_mutations(ctx._h, ptr(packed), int(pitch), ptr(row_keep), n_snv, int(n_cells),
+                                  ptr(clade_bits), int(words), n_rows, float(FP), float(FN), ptr(out)))
+    return out
