@@ -49,6 +49,7 @@ extern "C" {
 
 typedef struct scs_ctx scs_ctx;
 typedef struct scs_placement scs_placement;
+typedef struct scs_vcf scs_vcf;
 
 /* ------------------------------------------------------------------ context */
 const char* scs_version(void);
@@ -57,6 +58,29 @@ int scs_ctx_create(int32_t device, scs_ctx** out);
 int scs_ctx_destroy(scs_ctx* ctx);
 /* info[0..5] = sm_count, cc_major, cc_minor, total_mem_MiB, l2_bytes, device */
 int scs_ctx_info(scs_ctx* ctx, int64_t* info, int32_t n);
+
+/* ------------------------------------------------------------------ VCF decode
+ * get_mut_df (run_PT_test.py:27-207, filter=True).  `text` is the decompressed
+ * VCF (header lines included; they are skipped like the reference does),
+ * n_samples the number of sample columns of the #CHROM line and incl_idx the
+ * file columns that survive -excl/-incl (run_PT_test.py:57-76, :187-189), in
+ * output order.  The decoded matrix stays on the device. */
+int scs_vcf_decode(scs_ctx* ctx, const char* text, int64_t nbytes, int32_t n_samples, const int32_t* incl_idx,
+                   int32_t n_incl, scs_vcf** out);
+int scs_vcf_destroy(scs_vcf* vcf);
+/* info[0..5] = kept SNVs, kept samples, row pitch (bytes), lines seen, lines
+ * skipped for lack of any call (:147), lines dropped by FILTER / ISA (:175-181) */
+int scs_vcf_info(scs_vcf* vcf, int64_t* info, int32_t n);
+const uint8_t* scs_vcf_device_genotypes(scs_vcf* vcf);
+/* Host copies: packed [kept][pitch] and pos [kept][2] = (chrom, pos); either may be NULL. */
+int scs_vcf_copy(scs_vcf* vcf, uint8_t* packed, int64_t* pos);
+/* get_gt_tree's filters (run_PT_test.py:350-358) on a device-resident packed
+ * matrix: d_row_keep[i] = 1 when SNV i has a call in an active cell (all ones when
+ * filter_rows == 0: the reference only filters when the outgroup is a column);
+ * missing_frac[c] = fraction of kept SNVs where cell c is missing. */
+int scs_gt_reduce(scs_ctx* ctx, const uint8_t* d_gt, int64_t pitch_bytes, int64_t n_snv, int32_t n_cells,
+                  const uint8_t* col_active, int32_t filter_rows, uint8_t* d_row_keep, int64_t* n_kept,
+                  double* missing_frac);
 
 /* ---------------------------------------------------------------- placement
  * map_mutations_gt (run_PT_test.py:386-448): for every SNV, the normalised
@@ -96,6 +120,27 @@ int scs_placement_debug_counts(scs_placement* plan, int32_t* counts, void* strea
 int scs_map_mutations(scs_ctx* ctx, const uint8_t* gt, int64_t pitch_bytes, const uint8_t* row_keep,
                       int64_t n_snv, int32_t n_cells, const uint32_t* clade_bits, int64_t pitch_words,
                       int32_t n_rows, double FP, double FN, double* soft_weights);
+
+/* -------------------------------------------------------------- branch weights
+ * add_br_weights (run_PT_test.py:451-515): clade_bits holds the tree's nodes
+ * only ([n_nodes][pitch_words], ete3 level order); missing_rate[c] is the clipped
+ * per-cell missing rate MS_i (run_PT_test.py:358), negative for cells that are not
+ * leaves of the tree.  For every w_max: weights[w][node] (inverse variance,
+ * clipped; -1 for the root) and weights_norm[w][node] (scaled to sum to the
+ * number of branches; -1 for the root).  root_row receives the root's row. */
+int scs_branch_weights(scs_ctx* ctx, const uint32_t* clade_bits, int64_t pitch_words, int32_t n_nodes,
+                       int32_t n_cells, const double* missing_rate, double FP, double FN, const double* w_max,
+                       int32_t n_w, double* weights, double* weights_norm, int32_t* root_row);
+
+/* ------------------------------------------------------------------------ LRT
+ * get_LRT_poisson (run_PT_test.py:638-700), batched: problem p owns branches
+ * [br_off[p], br_off[p+1]) of Y / w / child_int.  Branch k hangs below internal
+ * node k/2 (get_model_data's order, run_PT_test.py:569-622); child_int[k] is the
+ * internal node below it, or -1 for a leaf.  out[p][8] = {-2logLR, dof, on_bound,
+ * p-value, ll_H0, ll_H1, Newton iterations, status (0 = converged)}; x_out
+ * (optional, may be NULL) receives the fitted branch lengths. */
+int scs_lrt_poisson_batch(scs_ctx* ctx, int32_t n_prob, const int64_t* br_off, const double* Y, const double* w,
+                          const int32_t* child_int, double* out, double* x_out);
 
 #ifdef __cplusplus
 }

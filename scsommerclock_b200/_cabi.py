@@ -42,6 +42,17 @@ _SIGNATURES = {
     "scs_placement_debug_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "scs_map_mutations": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
                                     C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_void_p]),
+    "scs_vcf_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]),
+    "scs_vcf_destroy": (C.c_int, [C.c_void_p]),
+    "scs_vcf_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
+    "scs_vcf_device_genotypes": (C.c_void_p, [C.c_void_p]),
+    "scs_vcf_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scs_gt_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int32,
+                                C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
+    "scs_branch_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_double,
+                                     C.c_double, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
+    "scs_lrt_poisson_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -1,0 +1,518 @@
+// scs_lrt.cu -- clock-constrained Poisson branch-length MLE + likelihood-ratio
+// test (reference: run_PT_test.py:638-700, get_LRT_poisson) and branch weights
+// (reference: run_PT_test.py:451-502, add_br_weights), batched on the GPU.
+//
+// The reference minimises  -sum_b w_b (Y_b log l_b - l_b) / scale_fac  over branch
+// lengths l subject to  constr @ l = 0  (every root-to-tip path has the same
+// length, built in get_model_data :518-635) and  LAMBDA_MIN <= l_b <= sum(Y)  with
+// SciPy's trust-constr, an interior-point method that stops on the central path
+// at barrier parameter ~0.1 * 0.2^10 (it terminates when the Lagrangian gradient
+// drops below gtol = 1e-8).  The kernel solves that same barrier problem exactly:
+// the equality constraints are eliminated by parametrising the ultrametric tree
+// by its internal-node heights h (l_b = h_parent - h_child), which leaves a
+// smooth strictly convex problem in m-1 unknowns whose Hessian has the sparsity
+// of the tree, so each Newton system is solved in O(m) by leaf-to-root
+// elimination.  One CTA per (dataset, w_max) problem.
+//
+// Branch k hangs below internal node k/2 (get_model_data adds the two children of
+// each internal node, in post-order, as consecutive branches) and child_int[k] is
+// the internal node below branch k, or -1 for a leaf.
+#include <cmath>
+#include <cstdio>
+#include <vector>
+
+#include "scs_internal.h"
+
+namespace scs {
+
+constexpr int LRT_THREADS = 128;
+constexpr double LRT_LMIN = 1e-6;           // LAMBDA_MIN, run_PT_test.py:21
+constexpr double LRT_MU = 0.1 * 1.024e-7;   // 0.1 * 0.2^10, see above
+constexpr int LRT_MAX_ITER = 200;
+
+struct LrtProblem {
+    int br_off;      // offset into per-branch arrays
+    int n_br;        // 2 * (leaves - 1)
+    int node_off;    // offset into per-internal-node workspace
+};
+
+struct LrtWork {
+    // per branch
+    double *l, *g, *d, *dl;
+    // per internal node
+    double *h, *Hd, *e, *D, *r, *x, *G;
+    int *up, *order, *level, *levoff;
+};
+
+__device__ __forceinline__ double block_reduce(double v, double* sh, bool is_min) {
+    for (int o = 16; o > 0; o >>= 1) {
+        const double t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = is_min ? fmin(v, t) : v + t;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    double out = sh[0];
+    for (int i = 1; i < LRT_THREADS / 32; ++i) out = is_min ? fmin(out, sh[i]) : out + sh[i];
+    return out;
+}
+
+// Regularised upper incomplete gamma Q(a, x) = chi2.sf(2x, 2a): power series of
+// P for x < a+1, Lentz continued fraction of Q otherwise.
+__device__ double gamma_q(double a, double x) {
+    if (!(a > 0.0)) return NAN;
+    if (x <= 0.0) return 1.0;
+    const double lg = lgamma(a);
+    if (x < a + 1.0) {
+        double ap = a, del = 1.0 / a, sum = del;
+        for (int n = 0; n < 10000; ++n) {
+            ap += 1.0;
+            del *= x / ap;
+            sum += del;
+            if (fabs(del) < fabs(sum) * 1e-17) break;
+        }
+        return 1.0 - sum * exp(-x + a * log(x) - lg);
+    }
+    const double tiny = 1e-300;
+    double b = x + 1.0 - a, c = 1.0 / tiny, dd = 1.0 / b, hh = dd;
+    for (int i = 1; i < 10000; ++i) {
+        const double an = -double(i) * (double(i) - a);
+        b += 2.0;
+        dd = an * dd + b;
+        if (fabs(dd) < tiny) dd = tiny;
+        c = b + an / c;
+        if (fabs(c) < tiny) c = tiny;
+        dd = 1.0 / dd;
+        const double del = dd * c;
+        hh *= del;
+        if (fabs(del - 1.0) < 1e-16) break;
+    }
+    return exp(-x + a * log(x) - lg) * hh;
+}
+
+// out[p*8 ..] = {LR, dof, on_bound, p_value, ll_H0, ll_H1, newton iterations, status}
+__global__ void __launch_bounds__(LRT_THREADS)
+scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ Yall, const double* __restrict__ wall,
+               const int* __restrict__ child_all, LrtWork ws, double* __restrict__ out, double* __restrict__ x_out) {
+    __shared__ double sh[LRT_THREADS / 32];
+    __shared__ double s_bcast[4];
+    __shared__ int s_nlev;
+    const LrtProblem pb = probs[blockIdx.x];
+    const int nb = pb.n_br, m1 = nb / 2, tid = threadIdx.x;
+    const double* Y = Yall + pb.br_off;
+    const double* w = wall + pb.br_off;
+    const int* child = child_all + pb.br_off;
+    double *l = ws.l + pb.br_off, *g = ws.g + pb.br_off, *d = ws.d + pb.br_off, *dl = ws.dl + pb.br_off;
+    double *h = ws.h + pb.node_off, *Hd = ws.Hd + pb.node_off, *e = ws.e + pb.node_off, *D = ws.D + pb.node_off;
+    double *r = ws.r + pb.node_off, *x = ws.x + pb.node_off, *G = ws.G + pb.node_off;
+    int *up = ws.up + pb.node_off, *order = ws.order + pb.node_off, *level = ws.level + pb.node_off, *levoff = ws.levoff + pb.node_off;
+    double* res = out + size_t(blockIdx.x) * 8;
+
+    // ---- sums, scale factor (run_PT_test.py:639-643)
+    double sY = 0.0, sH1 = 0.0, sW = 0.0;
+    for (int k = tid; k < nb; k += LRT_THREADS) {
+        const double y = Y[k];
+        sY += y;
+        sH1 += (y * log(y > 0.0 ? y : 1.0) - y) * w[k];
+        sW += w[k];
+    }
+    const double U = block_reduce(sY, sh, false);
+    const double ll_H1 = block_reduce(sH1, sh, false);
+    const double wsum = block_reduce(sW, sh, false);
+    double sf = 0.0;
+    {
+        const double steps[6] = {10000.0, 1000.0, 100.0, 10.0, 1.0, 0.1};
+        for (int i = 0; i < 6; ++i) {
+            sf = floor(ll_H1 / steps[i]) * steps[i];
+            if (sf != 0.0) break;
+        }
+    }
+    if (!(sf != 0.0) || !(U > 2.0 * nb * LRT_LMIN) || !isfinite(ll_H1)) {
+        if (tid == 0) {
+            for (int i = 0; i < 7; ++i) res[i] = NAN;
+            res[7] = 2.0;   // degenerate input: the reference divides by scale_fac == 0
+        }
+        return;
+    }
+
+    // ---- topology: up-branch of every internal node, levels, level order (thread 0)
+    for (int i = tid; i < m1; i += LRT_THREADS) up[i] = -1;
+    __syncthreads();
+    for (int k = tid; k < nb; k += LRT_THREADS)
+        if (child[k] >= 0) up[child[k]] = k;
+    if (tid == 0) {
+        // children precede parents (post-order), so one ascending sweep gives the levels
+        int nlev = 0;
+        for (int i = 0; i < m1; ++i) {
+            int lv = 0;
+            const int c0 = child[2 * i], c1 = child[2 * i + 1];
+            if (c0 >= 0) lv = max(lv, level[c0] + 1);
+            if (c1 >= 0) lv = max(lv, level[c1] + 1);
+            level[i] = lv;
+            nlev = max(nlev, lv + 1);
+        }
+        // counting sort by level: levoff[q] = first slot of level q in `order`
+        for (int q = 0; q <= nlev; ++q) levoff[q] = 0;
+        for (int i = 0; i < m1; ++i) levoff[level[i] + 1]++;
+        for (int q = 0; q < nlev; ++q) levoff[q + 1] += levoff[q];
+        for (int i = 0; i < m1; ++i) order[levoff[level[i]]++] = i;
+        for (int q = nlev; q > 0; --q) levoff[q] = levoff[q - 1];
+        levoff[0] = 0;
+        s_nlev = nlev;
+    }
+    __syncthreads();
+    const int nlev = s_nlev;
+
+    // ---- strictly feasible start: heights from the counts themselves
+    if (tid == 0) {
+        const double dmin = 1e-3;
+        double lmax = 0.0;
+        for (int i = 0; i < m1; ++i) {
+            double hv = 0.0;
+            for (int s = 0; s < 2; ++s) {
+                const int k = 2 * i + s;
+                const double hc = child[k] >= 0 ? h[child[k]] : 0.0;
+                hv = fmax(hv, hc + fmax(Y[k], dmin));
+            }
+            h[i] = hv;
+        }
+        for (int k = 0; k < nb; ++k) {
+            const double hc = child[k] >= 0 ? h[child[k]] : 0.0;
+            lmax = fmax(lmax, h[k >> 1] - hc);
+        }
+        s_bcast[0] = lmax >= 0.9 * U ? 0.9 * U / lmax : 1.0;
+    }
+    __syncthreads();
+    {
+        const double sc = s_bcast[0];
+        if (sc != 1.0)
+            for (int i = tid; i < m1; i += LRT_THREADS) h[i] *= sc;
+    }
+    __syncthreads();
+
+    const double mu = LRT_MU;
+    int it = 0, status = 1;
+    for (; it < LRT_MAX_ITER; ++it) {
+        // branch lengths, barrier gradient and curvature
+        double f0p = 0.0;
+        for (int k = tid; k < nb; k += LRT_THREADS) {
+            const double hc = child[k] >= 0 ? h[child[k]] : 0.0;
+            const double lk = h[k >> 1] - hc;
+            const double a = lk - LRT_LMIN, b = U - lk;
+            l[k] = lk;
+            g[k] = w[k] * (1.0 - Y[k] / lk) / sf - mu / a + mu / b;
+            d[k] = w[k] * Y[k] / (lk * lk * sf) + mu / (a * a) + mu / (b * b);
+            f0p += w[k] * (lk - Y[k] * log(lk)) / sf - mu * (log(a) + log(b));
+        }
+        const double f0 = block_reduce(f0p, sh, false);
+        for (int i = tid; i < m1; i += LRT_THREADS) {
+            const int u = up[i];
+            G[i] = g[2 * i] + g[2 * i + 1] - (u >= 0 ? g[u] : 0.0);
+            Hd[i] = d[2 * i] + d[2 * i + 1] + (u >= 0 ? d[u] : 0.0);
+            e[i] = u >= 0 ? d[u] : 0.0;
+        }
+        __syncthreads();
+        // leaf-to-root elimination, level by level
+        for (int q = 0; q < nlev; ++q) {
+            const int a0 = levoff[q], a1 = levoff[q + 1];
+            for (int s = a0 + tid; s < a1; s += LRT_THREADS) {
+                const int i = order[s];
+                double Dv = Hd[i], rv = -G[i];
+                for (int c = 0; c < 2; ++c) {
+                    const int j = child[2 * i + c];
+                    if (j >= 0) {
+                        const double t = e[j] / D[j];
+                        Dv -= e[j] * t;
+                        rv += t * r[j];
+                    }
+                }
+                D[i] = Dv;
+                r[i] = rv;
+            }
+            __syncthreads();
+        }
+        // root-to-leaf back substitution
+        for (int q = nlev - 1; q >= 0; --q) {
+            const int a0 = levoff[q], a1 = levoff[q + 1];
+            for (int s = a0 + tid; s < a1; s += LRT_THREADS) {
+                const int i = order[s];
+                const int u = up[i];
+                x[i] = u >= 0 ? (r[i] + e[i] * x[u >> 1]) / D[i] : r[i] / D[i];
+            }
+            __syncthreads();
+        }
+        // Newton decrement and the largest step that stays strictly inside the bounds
+        double decp = 0.0, amaxp = 1.0;
+        for (int i = tid; i < m1; i += LRT_THREADS) decp -= G[i] * x[i];
+        for (int k = tid; k < nb; k += LRT_THREADS) {
+            const double xc = child[k] >= 0 ? x[child[k]] : 0.0;
+            const double dk = x[k >> 1] - xc;
+            dl[k] = dk;
+            if (dk < 0.0) amaxp = fmin(amaxp, 0.99 * (l[k] - LRT_LMIN) / -dk);
+            if (dk > 0.0) amaxp = fmin(amaxp, 0.99 * (U - l[k]) / dk);
+        }
+        const double dec = block_reduce(decp, sh, false);
+        const double amax = block_reduce(amaxp, sh, true);
+        if (!(dec == dec)) {
+            status = 3;   // NaN in the Newton system
+            break;
+        }
+        // backtracking (Armijo) on the barrier objective
+        double a = amax;
+        bool ok = false;
+        for (int bt = 0; bt < 60; ++bt) {
+            double fp = 0.0;
+            for (int k = tid; k < nb; k += LRT_THREADS) {
+                const double lk = l[k] + a * dl[k];
+                fp += w[k] * (lk - Y[k] * log(lk)) / sf - mu * (log(lk - LRT_LMIN) + log(U - lk));
+            }
+            const double f1 = block_reduce(fp, sh, false);
+            if (f1 <= f0 - 1e-4 * a * dec) {
+                ok = true;
+                break;
+            }
+            a *= 0.5;
+        }
+        if (ok)
+            for (int i = tid; i < m1; i += LRT_THREADS) h[i] += a * x[i];
+        __syncthreads();
+        if (!ok || dec < 1e-20 * fmax(1.0, fabs(f0)) || (a == 1.0 && dec < 1e-16)) {
+            status = 0;
+            ++it;
+            break;
+        }
+    }
+
+    // ---- statistic and p-value (run_PT_test.py:683-695)
+    double sH0 = 0.0, sOB = 0.0;
+    for (int k = tid; k < nb; k += LRT_THREADS) {
+        const double hc = child[k] >= 0 ? h[child[k]] : 0.0;
+        const double lk = h[k >> 1] - hc;
+        sH0 += (Y[k] * log(lk) - lk) * w[k];
+        sOB += (lk <= 1e-3) ? 1.0 : 0.0;
+        if (x_out) x_out[pb.br_off + k] = lk;
+    }
+    const double ll_H0 = block_reduce(sH0, sh, false);
+    const int on_bound = int(block_reduce(sOB, sh, false) + 0.5);
+    const double LR = -2.0 * (ll_H0 - ll_H1);
+    const double dof = rint(wsum - double(m1));
+    // mixture over the number of parameters on the bound, binomial weights, in log space
+    double num = 0.0, den = 0.0;
+    const double lg_n = lgamma(double(on_bound) + 1.0);
+    for (int k = tid; k <= on_bound; k += LRT_THREADS) {
+        const double df = dof - double(k);
+        if (df > 0.0) {
+            double pv = gamma_q(0.5 * df, 0.5 * LR);
+            pv = fmin(fmax(pv, 1e-100), 1.0);
+            // weights relative to the central binomial coefficient keep everything finite
+            const double lw = lg_n - lgamma(double(k) + 1.0) - lgamma(double(on_bound - k) + 1.0) - double(on_bound) * 0.6931471805599453;
+            const double wk = exp(lw);
+            num += wk * pv;
+            den += wk;
+        }
+    }
+    num = block_reduce(num, sh, false);
+    den = block_reduce(den, sh, false);
+    if (tid == 0) {
+        res[0] = LR;
+        res[1] = dof;
+        res[2] = double(on_bound);
+        res[3] = den > 0.0 ? num / den : NAN;
+        res[4] = ll_H0;
+        res[5] = ll_H1;
+        res[6] = double(it);
+        res[7] = double(status);
+    }
+}
+
+// ------------------------------------------------------------ branch weights
+// add_br_weights (run_PT_test.py:451-502): for every node, the probability that
+// all of its cells dropped out / went missing while the others read wild type:
+//   p_ADO = max(exp(sum_{c in clade} l_DO[c] + sum_{c not in clade} l_TN[c]), 1e-6)
+// One warp per node row of the clade bit mask.
+__global__ void scs_branch_padO_kernel(const uint32_t* __restrict__ bits, int64_t pitch_words, int n_nodes, int n_cells,
+                                       const double* __restrict__ l_do_minus_tn, double sum_tn, double* __restrict__ p_ado,
+                                       int* __restrict__ clade_size) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n_nodes) return;
+    const int words = (n_cells + 31) / 32;
+    double acc = 0.0;
+    int cnt = 0;
+    for (int wd = 0; wd < words; ++wd) {
+        const uint32_t b = bits[size_t(row) * pitch_words + wd];
+        const int c = wd * 32 + lane;
+        if (((b >> lane) & 1u) && c < n_cells) {
+            acc += l_do_minus_tn[c];
+            cnt++;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if (lane == 0) {
+        const double xlog = sum_tn + acc;
+        // the reference catches the FloatingPointError of an underflowing exp (:485)
+        const double pv = xlog < -708.3964185322641 ? 1e-6 : fmax(exp(xlog), 1e-6);
+        p_ado[row] = pv;
+        clade_size[row] = cnt;
+    }
+}
+
+}  // namespace scs
+
+using namespace scs;
+
+extern "C" {
+
+int scs_lrt_poisson_batch(scs_ctx* ctx, int32_t n_prob, const int64_t* br_off, const double* Y, const double* w,
+                          const int32_t* child_int, double* out, double* x_out) {
+    if (!ctx || !br_off || !Y || !w || !child_int || !out) return set_error(SCS_ERR_ARG, "null argument");
+    if (n_prob <= 0) return SCS_OK;
+    SCS_CUDA(cudaSetDevice(ctx->device));
+    const int64_t total_br = br_off[n_prob];
+    if (total_br > (int64_t(1) << 30)) return set_error(SCS_ERR_ARG, "batch too large: split it");
+    std::vector<LrtProblem> probs(n_prob);
+    int64_t node_off = 0;
+    for (int p = 0; p < n_prob; ++p) {
+        const int64_t nb = br_off[p + 1] - br_off[p];
+        if (nb < 2 || (nb & 1)) return set_error(SCS_ERR_ARG, "problem %d has %lld branches; a binary tree has an even number >= 2", p, (long long)nb);
+        for (int64_t k = 0; k < nb; ++k) {
+            const int c = child_int[br_off[p] + k];
+            if (c >= int(k / 2) || c < -1) return set_error(SCS_ERR_ARG, "problem %d branch %lld: child node %d is not below its parent %lld in post-order", p, (long long)k, c, (long long)(k / 2));
+        }
+        probs[p].br_off = int(br_off[p]);
+        probs[p].n_br = int(nb);
+        probs[p].node_off = int(node_off);
+        node_off += nb / 2 + 2;   // levoff needs (levels + 1) <= nodes + 1 entries
+    }
+    const size_t nbr = size_t(total_br), nnode = size_t(node_off);
+    double* d_buf = nullptr;
+    int* i_buf = nullptr;
+    LrtProblem* d_probs = nullptr;
+    const size_t dbl = 2 * nbr /*Y, w*/ + 4 * nbr /*l g d dl*/ + 7 * nnode + size_t(n_prob) * 8 + nbr /*x_out*/;
+    const size_t ints = nbr /*child*/ + 4 * nnode;
+    int rc = SCS_OK;
+    do {
+        if (cudaMalloc(&d_buf, dbl * sizeof(double)) != cudaSuccess || cudaMalloc(&i_buf, ints * sizeof(int)) != cudaSuccess ||
+            cudaMalloc(&d_probs, size_t(n_prob) * sizeof(LrtProblem)) != cudaSuccess) {
+            rc = set_error(SCS_ERR_OOM, "device allocation failed for the LRT batch");
+            break;
+        }
+        double* dY = d_buf;
+        double* dw = dY + nbr;
+        LrtWork ws;
+        ws.l = dw + nbr;
+        ws.g = ws.l + nbr;
+        ws.d = ws.g + nbr;
+        ws.dl = ws.d + nbr;
+        ws.h = ws.dl + nbr;
+        ws.Hd = ws.h + nnode;
+        ws.e = ws.Hd + nnode;
+        ws.D = ws.e + nnode;
+        ws.r = ws.D + nnode;
+        ws.x = ws.r + nnode;
+        ws.G = ws.x + nnode;
+        double* d_out = ws.G + nnode;
+        double* d_x = d_out + size_t(n_prob) * 8;
+        int* d_child = i_buf;
+        ws.up = d_child + nbr;
+        ws.order = ws.up + nnode;
+        ws.level = ws.order + nnode;
+        ws.levoff = ws.level + nnode;
+        cudaError_t e = cudaMemcpy(dY, Y, nbr * sizeof(double), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(dw, w, nbr * sizeof(double), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_child, child_int, nbr * sizeof(int), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_probs, probs.data(), size_t(n_prob) * sizeof(LrtProblem), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+            scs_lrt_kernel<<<n_prob, LRT_THREADS>>>(d_probs, dY, dw, d_child, ws, d_out, x_out ? d_x : nullptr);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaMemcpy(out, d_out, size_t(n_prob) * 8 * sizeof(double), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && x_out) e = cudaMemcpy(x_out, d_x, nbr * sizeof(double), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = set_error(SCS_ERR_CUDA, "LRT batch failed: %s", cudaGetErrorString(e));
+    } while (0);
+    cudaFree(d_buf);
+    cudaFree(i_buf);
+    cudaFree(d_probs);
+    return rc;
+}
+
+int scs_branch_weights(scs_ctx* ctx, const uint32_t* clade_bits, int64_t pitch_words, int32_t n_nodes, int32_t n_cells,
+                       const double* missing_rate, double FP, double FN, const double* w_max, int32_t n_w,
+                       double* weights, double* weights_norm, int32_t* root_row) {
+    if (!ctx || !clade_bits || !missing_rate || !w_max || !weights || !weights_norm) return set_error(SCS_ERR_ARG, "null argument");
+    if (n_nodes < 2 || n_cells < 1 || n_w < 1) return set_error(SCS_ERR_ARG, "empty problem");
+    SCS_CUDA(cudaSetDevice(ctx->device));
+    std::vector<double> diff(n_cells);
+    double sum_tn = 0.0;
+    for (int c = 0; c < n_cells; ++c) {
+        const double ms = missing_rate[c];
+        if (ms < 0.0) {   // cell not part of the tree
+            diff[c] = 0.0;
+            continue;
+        }
+        const double l_tn = log((1.0 - ms) * (1.0 - FP) + ms);   // :475
+        const double l_do = log((1.0 - ms) * FN + ms);           // :477
+        diff[c] = l_do - l_tn;
+        sum_tn += l_tn;
+    }
+    uint32_t* d_bits = nullptr;
+    double *d_diff = nullptr, *d_p = nullptr;
+    int* d_cnt = nullptr;
+    const size_t mask_bytes = size_t(n_nodes) * pitch_words * 4;
+    int rc = SCS_OK;
+    std::vector<double> p(n_nodes);
+    std::vector<int> cnt(n_nodes);
+    do {
+        if (cudaMalloc(&d_bits, mask_bytes) != cudaSuccess || cudaMalloc(&d_diff, n_cells * sizeof(double)) != cudaSuccess ||
+            cudaMalloc(&d_p, n_nodes * sizeof(double)) != cudaSuccess || cudaMalloc(&d_cnt, n_nodes * sizeof(int)) != cudaSuccess) {
+            rc = set_error(SCS_ERR_OOM, "device allocation failed for branch weights");
+            break;
+        }
+        cudaError_t e = cudaMemcpy(d_bits, clade_bits, mask_bytes, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_diff, diff.data(), n_cells * sizeof(double), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+            const int threads = 128, blocks = (n_nodes * 32 + threads - 1) / threads;
+            scs_branch_padO_kernel<<<blocks, threads>>>(d_bits, pitch_words, n_nodes, n_cells, d_diff, sum_tn, d_p, d_cnt);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaMemcpy(p.data(), d_p, n_nodes * sizeof(double), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(cnt.data(), d_cnt, n_nodes * sizeof(int), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = set_error(SCS_ERR_CUDA, "branch weight kernel failed: %s", cudaGetErrorString(e));
+    } while (0);
+    cudaFree(d_bits);
+    cudaFree(d_diff);
+    cudaFree(d_p);
+    cudaFree(d_cnt);
+    if (rc != SCS_OK) return rc;
+    // root = first node that holds every cell of the tree (:497); it is dropped from the normalisation
+    int n_tree_cells = 0;
+    for (int c = 0; c < n_cells; ++c) n_tree_cells += missing_rate[c] >= 0.0;
+    int root = -1;
+    for (int i = 0; i < n_nodes; ++i)
+        if (cnt[i] == n_tree_cells) {
+            root = i;
+            break;
+        }
+    if (root < 0) return set_error(SCS_ERR_ARG, "no node of the clade mask contains every cell: not a rooted tree");
+    if (root_row) *root_row = root;
+    for (int wi = 0; wi < n_w; ++wi) {
+        double sum = 0.0;
+        for (int i = 0; i < n_nodes; ++i) {
+            const double pa = p[i];
+            double wv = 1.0 / ((1.0 - pa) * pa);                  // :492 inverse variance
+            if (wv > w_max[wi]) wv = w_max[wi];
+            weights[size_t(wi) * n_nodes + i] = wv;
+            if (i != root) sum += wv;
+        }
+        for (int i = 0; i < n_nodes; ++i)
+            weights_norm[size_t(wi) * n_nodes + i] = i == root ? -1.0 : double(n_nodes - 1) * weights[size_t(wi) * n_nodes + i] / sum;   // :502
+        weights[size_t(wi) * n_nodes + root] = -1.0;                                                                                   // :513
+    }
+    return SCS_OK;
+}
+
+}  // extern "C"

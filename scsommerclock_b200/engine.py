@@ -179,3 +179,83 @@ def map_mutations(ctx, packed, pitch, clade_bits, words, n_cells, FP, FN, row_ke
     check(lib().scs_map_mutations(ctx._h, ptr(packed), int(pitch), ptr(row_keep), n_snv, int(n_cells),
                                   ptr(clade_bits), int(words), n_rows, float(FP), float(FN), ptr(out)))
     return out
+
+
+class DecodedVcf:
+    """Device-resident result of scs_vcf_decode (get_mut_df, run_PT_test.py:27-207)."""
+
+    def __init__(self, ctx, text, n_samples, incl_idx):
+        self.ctx = ctx
+        incl_idx = np.ascontiguousarray(incl_idx, dtype=np.int32)
+        h = C.c_void_p()
+        text = bytes(text)
+        check(lib().scs_vcf_decode(ctx._h, C.cast(C.c_char_p(text), C.c_void_p), len(text), int(n_samples),
+                                   ptr(incl_idx), int(incl_idx.size), C.byref(h)))
+        self._h = h
+        info = (C.c_int64 * 6)()
+        check(lib().scs_vcf_info(self._h, info, 6))
+        self.n_kept, self.n_incl, self.pitch, self.n_lines, self.n_noalt, self.n_filtered = [int(v) for v in info]
+
+    def device_ptr(self):
+        return int(lib().scs_vcf_device_genotypes(self._h) or 0)
+
+    def copy(self):
+        packed = np.zeros((self.n_kept, self.pitch), dtype=np.uint8)
+        pos = np.zeros((self.n_kept, 2), dtype=np.int64)
+        check(lib().scs_vcf_copy(self._h, ptr(packed), ptr(pos)))
+        return packed, pos
+
+    def close(self):
+        if self._h:
+            lib().scs_vcf_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def gt_reduce(ctx, d_gt, pitch, n_snv, n_cells, col_active, filter_rows, d_row_keep):
+    """scs_gt_reduce: fills the device buffer ``d_row_keep`` and returns
+    (n_kept, missing fraction per cell)."""
+    col_active = np.ascontiguousarray(col_active, dtype=np.uint8)
+    n_kept = C.c_int64()
+    miss = np.zeros(n_cells, dtype=np.float64)
+    check(lib().scs_gt_reduce(ctx._h, _dev_ptr(d_gt), int(pitch), int(n_snv), int(n_cells), ptr(col_active),
+                              int(bool(filter_rows)), _dev_ptr(d_row_keep), C.byref(n_kept), ptr(miss)))
+    return int(n_kept.value), miss
+
+
+def branch_weights(ctx, node_bits, words, n_cells, missing_rate, FP, FN, w_maxs):
+    """scs_branch_weights: (weights [n_w, n_nodes], weights_norm [n_w, n_nodes], root row)."""
+    node_bits = np.ascontiguousarray(node_bits, dtype=np.uint32)
+    n_nodes = node_bits.shape[0]
+    missing_rate = np.ascontiguousarray(missing_rate, dtype=np.float64)
+    w_maxs = np.ascontiguousarray(w_maxs, dtype=np.float64)
+    weights = np.zeros((w_maxs.size, n_nodes))
+    weights_norm = np.zeros((w_maxs.size, n_nodes))
+    root = C.c_int32()
+    check(lib().scs_branch_weights(ctx._h, ptr(node_bits), int(words), n_nodes, int(n_cells), ptr(missing_rate),
+                                   float(FP), float(FN), ptr(w_maxs), int(w_maxs.size), ptr(weights), ptr(weights_norm),
+                                   C.byref(root)))
+    return weights, weights_norm, int(root.value)
+
+
+def lrt_poisson_batch(ctx, Ys, ws, child_ints, want_x=False):
+    """scs_lrt_poisson_batch over a list of problems.  Returns (out [n, 8], x list or None);
+    out columns: LR, dof, on_bound, p_value, ll_H0, ll_H1, iterations, status."""
+    n = len(Ys)
+    sizes = np.array([len(y) for y in Ys], dtype=np.int64)
+    off = np.zeros(n + 1, dtype=np.int64)
+    off[1:] = np.cumsum(sizes)
+    Y = np.ascontiguousarray(np.concatenate(Ys), dtype=np.float64)
+    w = np.ascontiguousarray(np.concatenate(ws), dtype=np.float64)
+    ch = np.ascontiguousarray(np.concatenate(child_ints), dtype=np.int32)
+    assert Y.size == w.size == ch.size == off[-1]
+    out = np.zeros((n, 8), dtype=np.float64)
+    x = np.zeros(Y.size, dtype=np.float64) if want_x else None
+    check(lib().scs_lrt_poisson_batch(ctx._h, n, ptr(off), ptr(Y), ptr(w), ptr(ch), ptr(out), ptr(x)))
+    xs = [x[off[i]:off[i + 1]] for i in range(n)] if want_x else None
+    return out, xs

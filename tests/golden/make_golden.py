@@ -1,0 +1,273 @@
+#!/usr/bin/env python3
+"""Generate the golden fixtures by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+It imports /root/reference/run_PT_test.py as a module and calls its own
+functions on (a) the reference's example_data and (b) small synthetic VCF/tree
+pairs written to tests/golden/data/ that exercise the decoder's edge cases.
+Inputs, intermediates and outputs are stored in tests/golden/*.npz.
+
+Two environment notes, repeated in every fixture's ``meta``:
+  * ete3 cannot be installed here (no network, not in the wheelhouse); the
+    reference's ``from ete3 import Tree`` is served by
+    ``scsommerclock_b200.tree.Tree`` (a restatement of the ete3 3.1.x TreeNode
+    methods the reference calls).
+  * the reference's global ``np.seterr(all='raise')`` makes SciPy 1.18's
+    trust-constr raise FloatingPointError on harmless internal underflow, so
+    ``scipy.optimize.minimize`` is wrapped in ``np.errstate(under='ignore')``.
+    Nothing else of the reference is touched.
+"""
+import gzip
+import importlib.util
+import json
+import os
+import shutil
+import sys
+import types
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, REPO)
+warnings.filterwarnings("ignore")
+
+META = {
+    "reference": "cbg-ethz/scSomMerClock run_PT_test.py (unmodified, imported from /root/reference)",
+    "ete3": "absent; served by scsommerclock_b200.tree.Tree (ete3 3.1.x TreeNode semantics restated)",
+    "numpy_errstate": "scipy.optimize.minimize wrapped in np.errstate(under='ignore')",
+}
+
+
+def load_reference():
+    from scsommerclock_b200 import tree as T
+    ete3 = types.ModuleType("ete3")
+    ete3.Tree = T.Tree
+    parser = types.ModuleType("ete3.parser")
+    newick = types.ModuleType("ete3.parser.newick")
+    newick.NewickError = T.NewickError
+    parser.newick = newick
+    ete3.parser = parser
+    sys.modules.update({"ete3": ete3, "ete3.parser": parser, "ete3.parser.newick": newick})
+    spec = importlib.util.spec_from_file_location("ref_run_PT_test", os.path.join(REF, "run_PT_test.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    _min = ref.minimize
+
+    def minimize_no_underflow_trap(*a, **k):
+        with np.errstate(under="ignore"):
+            return _min(*a, **k)
+
+    ref.minimize = minimize_no_underflow_trap
+    import scipy, pandas
+    META.update(numpy=np.__version__, scipy=scipy.__version__, pandas=pandas.__version__)
+    return ref
+
+
+def codes_of(df):
+    v = df.values.astype(float)
+    return np.where(np.isnan(v), 3, np.nan_to_num(v)).astype(np.uint8)
+
+
+def run_case(ref, name, vcf, tree_file, w_maxs, exclude="", include="", FN_in=None, FP_in=None, rel_to=REPO):
+    out = {}
+    call_data = ref.get_mut_df(vcf, exclude, include)
+    muts = call_data[0]
+    out["muts_codes"] = codes_of(muts)
+    out["samples"] = np.array(list(muts.columns))
+    out["pos"] = np.array([list(p) for p in muts.index.values], dtype=np.int64).reshape(-1, 2)
+    per_w = []
+    tsv_header = "muts\tFN\tFP"
+    tsv_model = ""
+    for wi, w_max in enumerate(w_maxs):
+        tree, FP, FN, M = ref.get_gt_tree(tree_file, call_data, w_max, FN_in, FP_in)
+        nodes = list(tree.iter_descendants())
+        if wi == 0:
+            cols = [c for c in M.index.names] and list(muts.columns)
+            red_cols = [c for c in muts.columns if c != "healthycell"]
+            S = np.zeros((len(M.columns), len(red_cols)), dtype=np.uint8)
+            for i, node in enumerate(nodes):
+                for leaf in node.name.split("+"):
+                    S[i, red_cols.index(leaf)] = 1
+            out["S"] = S
+            out["red_cols"] = np.array(red_cols)
+            out["M_index_pos"] = np.array([list(p) for p in M.index.values], dtype=np.int64).reshape(-1, 2)
+            out["soft"] = M.values.sum(axis=0)
+            out["M_head"] = M.values[:64].copy()
+            out["FP"], out["FN"] = FP, FN
+            out["MS_leaf_names"] = np.array([l.name for l in tree.get_leaves()])
+            out["MS_leaf"] = np.array([l.missing for l in tree.get_leaves()])
+            out["node_names"] = np.array([n.name for n in nodes])
+        Y, constr, init, weights_norm, constr_cols = ref.get_model_data(tree)
+        LR, dof, on_bound, p_val, opt_vals = ref.get_LRT_poisson(Y, constr, init, weights_norm[:, 0])
+        x_opt = np.array([v[0] for v in opt_vals])
+        hyp = int(p_val < 0.05)
+        tsv_header += "\t" + "\t".join([f"{i}_{w_max:.0f}" for i in ["-2logLR", "dof", "p-value", "hypothesis"]])
+        tsv_model += f"\t{LR:0>5.3f}\t{dof}\t{p_val}\tH{hyp}"
+        raw_w = np.array([n.weights[0] for n in nodes])
+        per_w.append(dict(w_max=w_max, Y=Y, constr=constr, init=init, weights_norm=weights_norm[:, 0],
+                          constr_cols=constr_cols, LR=LR, dof=dof, on_bound=on_bound, p_val=p_val, x_opt=x_opt,
+                          raw_weights=raw_w, hyp=hyp))
+        print(f"  {name} w={w_max}: LR={LR:.4f} dof={dof} on_bound={on_bound} p={p_val:.6g} H{hyp}", flush=True)
+    tsv = f"{tsv_header}\n{M.shape[0]}\t{FN:.4f}\t{FP:.4f}{tsv_model}"
+    # also let the reference write its own file through its public entry point, to pin the TSV text
+    flat = {k: v for k, v in out.items()}
+    flat["w_maxs"] = np.array(w_maxs, dtype=float)
+    for k in ("Y", "init", "weights_norm", "x_opt", "raw_weights"):
+        flat[k] = np.stack([d[k] for d in per_w])
+    flat["constr"] = np.stack([d["constr"] for d in per_w])
+    flat["constr_cols"] = np.stack([d["constr_cols"] for d in per_w])
+    flat["LR"] = np.array([d["LR"] for d in per_w])
+    flat["dof"] = np.array([d["dof"] for d in per_w])
+    flat["on_bound"] = np.array([d["on_bound"] for d in per_w])
+    flat["p_val"] = np.array([d["p_val"] for d in per_w])
+    flat["hyp"] = np.array([d["hyp"] for d in per_w])
+    flat["tsv"] = np.array(tsv)
+    meta = dict(META, case=name, vcf=os.path.relpath(vcf, rel_to), tree=os.path.relpath(tree_file, rel_to),
+                exclude=exclude, include=include, FN_in=FN_in, FP_in=FP_in)
+    flat["meta"] = np.array(json.dumps(meta))
+    # the Newick input travels with the fixture (the GPU box has no /root/reference)
+    flat["tree_text"] = np.array(open(tree_file).read())
+    flat["tree_basename"] = np.array(os.path.basename(tree_file))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **flat)
+
+
+# ------------------------------------------------------- synthetic inputs
+def write_vcf(path, names, rows, with_tg=True, reads="RC", chrom_prefix="", sep="|"):
+    """rows: list of dicts(pos, ref, alts, filter, gts [list of str], tgs [list of str])."""
+    fmt = "GT:DP:%s" % reads + (":TG" if with_tg else "")
+    with gzip.open(path, "wt") if path.endswith(".gz") else open(path, "w") as f:
+        f.write("##fileformat=VCFv4.3\n##source=scsommerclock_b200 synthetic golden input\n")
+        f.write("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(names) + "\n")
+        for r in rows:
+            recs = []
+            for k, gt in enumerate(r["gts"]):
+                gt = gt.replace("|", sep)
+                rd = "5,0,3,0" if reads == "RC" else "5,3"
+                rec = f"{gt}:8:{rd}"
+                if with_tg:
+                    rec += ":" + r["tgs"][k]
+                recs.append(rec)
+            f.write(f"{chrom_prefix}1\t{r['pos']}\tsnv{r['pos']:06d}\t{r['ref']}\t{r['alts']}\t.\t{r['filter']}\t"
+                    f"NS={len(names)}\t{fmt}\t" + "\t".join(recs) + "\n")
+            if r.get("blank_after"):
+                f.write("\n")
+
+
+def make_synthetic(tag, n_cells, n_snv, seed, FN, FP, MS, with_tg=True, reads="RC", chrom_prefix="", sep="|",
+                   name_style="cell", quirks=True, log_rates=None, tree_suffix=".raxml.bestTree", rate_mult_clade=None):
+    from scsommerclock_b200 import synth
+    rng = np.random.default_rng(seed)
+    tree = synth.coalescent_tree(n_cells, rng)
+    rate = None
+    if rate_mult_clade is not None:
+        # amplify the rate in the largest proper subtree (a clock violation)
+        sizes = tree.hi - tree.lo
+        cand = np.argsort(-sizes)
+        top = [v for v in cand if sizes[v] <= n_cells // 2][0]
+        rate = np.ones(2 * n_cells - 1)
+        inside = (tree.lo >= tree.lo[top]) & (tree.hi <= tree.hi[top])
+        rate[inside] = rate_mult_clade
+    br = synth.throw_mutations(tree, n_snv, rng, rate)
+    codes = synth.observe(tree, br, FN, FP, MS, rng)
+    if name_style == "cell":
+        names = ["cell%04d" % (i + 1) for i in range(n_cells)] + ["outgcell"]
+    else:
+        names = ["tumcell%04d" % (i + 1) for i in range(n_cells)] + ["healthycell"]
+    bases = "ACGT"
+    rows = []
+    truth = (tree.leaf_rank[None, :] >= tree.lo[br][:, None]) & (tree.leaf_rank[None, :] < tree.hi[br][:, None])
+    for i in range(n_snv):
+        ref_b = bases[rng.integers(4)]
+        alts = [b for b in bases if b != ref_b]
+        alt_i = 1 + int(rng.integers(3))
+        if reads == "AD":                      # Monovar style: the reference needs a single ALT with AD
+            alts, alt_i = alts[:1], 1
+        gts, tgs = [], []
+        for c in range(n_cells):
+            code = codes[i, c]
+            if code == 3:
+                gts.append(".|.")
+            elif code == 0:
+                gts.append("0|0")
+            else:
+                gts.append(f"{alt_i}|{alt_i}" if rng.random() < 0.15 else f"0|{alt_i}")
+            tgs.append(f"0|{alt_i}" if truth[i, c] else "0|0")
+        gts.append("0|0" if rng.random() > 0.02 else ".|.")   # outgroup
+        tgs.append("0|0")
+        n_called = sum(g not in ("0|0", ".|.") for g in gts)
+        flt = "PASS"
+        if n_called == 0:
+            flt = "wildtype"
+        elif n_called == 1 and rng.random() < 0.5:
+            flt = "singleton"
+        elif rng.random() < 0.03:
+            flt = "s50"
+        elif rng.random() < 0.02:
+            flt = "LowQual"
+        rows.append(dict(pos=3 * i + 1, ref=ref_b, alts=",".join(alts), filter=flt, gts=gts, tgs=tgs))
+    if quirks:
+        n = len(names)
+        base = 3 * n_snv + 10
+
+        def row(pos, gts, tgs=None, flt="PASS"):
+            return dict(pos=pos, ref="A", alts="C,G,T", filter=flt, gts=gts, tgs=tgs or ["0|0"] * n)
+        g = ["0|0"] * n
+        # two different single alts -> ISA violation (dropped by the PASS filter)
+        q = list(g); q[0] = "0|1"; q[1] = "0|2"; rows.append(row(base, q))
+        # two alts, one of them twice -> majority alt kept, the other cell set to 0
+        q = list(g); q[0] = "0|1"; q[1] = "0|1"; q[2] = "0|3"; q[3] = ".|."; rows.append(row(base + 1, q))
+        # tie between two alts with counts (2,2): first (smaller) alt wins
+        q = list(g); q[0] = "0|2"; q[1] = "2|2"; q[2] = "0|3"; q[3] = "3|3"; rows.append(row(base + 2, q))
+        # '1|0' : the reference reads gt[-1] == '0' as the alt index
+        q = list(g); q[4] = "1|0"; q[5] = "0|1"; q[6] = "0|1"; rows.append(row(base + 3, q))
+        # only a true genotype, nothing called -> kept row of zeros (dropped later by sum > 0)
+        t = ["0|0"] * n; t[2] = "0|1"; rows.append(row(base + 4, list(g), t))
+        # nothing called, nothing true -> skipped entirely
+        rows.append(row(base + 5, list(g)))
+        # mutation only in the outgroup -> removed with the outgroup column
+        q = list(g); q[-1] = "0|1"; rows.append(row(base + 6, q))
+        # all missing except one hom call; filter text containing PASS as a substring
+        q = [".|."] * n; q[7 % (n - 1)] = "2|2"; rows.append(row(base + 7, q, flt="PASS;extra"))
+        # homozygous true genotype forms
+        t = ["0|0"] * n; t[1] = "1|1"; q = list(g); q[1] = "1|1"; r_ = row(base + 8, q, t); r_["blank_after"] = True; rows.append(r_)
+        q = list(g); q[3] = "0|2"; q[8 % (n - 1)] = "0|2"; rows.append(row(base + 9, q, flt="q20"))
+    d = os.path.join(HERE, "data")
+    os.makedirs(d, exist_ok=True)
+    vcf = os.path.join(d, tag + ".vcf.gz")
+    write_vcf(vcf, names, rows, with_tg=with_tg, reads=reads, chrom_prefix=chrom_prefix, sep=sep)
+    tree_file = os.path.join(d, tag + tree_suffix)
+    with open(tree_file, "w") as f:
+        f.write(tree.newick(names[:-1], names[-1], scale=0.05) + "\n")
+    if log_rates is not None:
+        with open(os.path.join(d, tag + ".raxml.log"), "w") as f:
+            f.write("CellPhy-style log (synthetic)\n   SEQ_ERROR: %s,  ADO_RATE: %s\n" % log_rates)
+    return vcf, tree_file
+
+
+def main():
+    ref = load_reference()
+    ex = os.path.join(REF, "example_data")
+    default_w = [100, 200, 300, 400, 500, 600, 700, 800, 900, 1000]
+    if "--skip-examples" not in sys.argv: run_case(ref, "example_clock", os.path.join(ex, "data_simulated_clock.vcf.gz"),
+             os.path.join(ex, "data_simulated_clock.raxml.bestTree"), default_w, rel_to="/root")
+    if "--skip-examples" not in sys.argv: run_case(ref, "example_noclock", os.path.join(ex, "data_simulated_noclock.vcf.gz"),
+             os.path.join(ex, "data_simulated_noclock.raxml.bestTree"), default_w, rel_to="/root")
+    v, t = make_synthetic("syn_a", 12, 240, 11, FN=0.12, FP=0.01, MS=0.1, log_rates=("0.010000", "0.240000"))
+    run_case(ref, "syn_a", v, t, [100, 400, 1000])
+    v, t = make_synthetic("syn_b", 20, 400, 12, FN=0.2, FP=0.005, MS=0.25, with_tg=False, reads="AD", chrom_prefix="chr",
+                          sep="/", name_style="tumcell", rate_mult_clade=6.0, quirks=False)
+    run_case(ref, "syn_b", v, t, [50, 1000], FN_in=0.2, FP_in=0.005)
+    v, t = make_synthetic("syn_c", 9, 150, 13, FN=0.05, FP=0.02, MS=0.05, quirks=False, tree_suffix=".newick")
+    run_case(ref, "syn_c", v, t, [1000], exclude="tumcell000[12]")
+    run_case(ref, "syn_c_incl", v, t, [300], include="(tumcell000[1-7])|healthycell")
+    print("golden fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()

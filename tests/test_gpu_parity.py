@@ -1,0 +1,318 @@
+"""GPU parity tests (run with ``-m gpu`` on a B200): every CUDA entry point,
+called through the C ABI, against the CPU oracle and the golden fixtures
+recorded from the reference.
+
+Tolerances (stated once, used below):
+  * genotype matrix, clade masks, integer counts, dof, on_bound, decisions: exact;
+  * soft branch weights Y: |gpu - ref| <= 2e-5 * max(1, |ref|)  (fp32 epilogue on
+    exact integer differences, fp64 accumulation across SNV runs);
+  * branch weights: relative 1e-10 (fp64, different summation order);
+  * -2logLR: relative 1e-4 (the reference's own SciPy solve is only converged to
+    about that), p-value: relative 2e-3.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import case_inputs, golden_path
+from oracle import pt_oracle as O
+from scsommerclock_b200 import engine, run_PT_test as P, synth
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["example_clock", "example_noclock", "syn_a", "syn_b", "syn_c", "syn_c_incl"]
+SYN = [c for c in CASES if c.startswith("syn")]
+Y_TOL = 2e-5
+
+
+def load(name):
+    return np.load(golden_path(name), allow_pickle=False)
+
+
+def oracle_counts(codes, S):
+    x1 = ((codes == 1) | (codes == 2)).astype(np.int64)
+    x0 = (codes == 0).astype(np.int64)
+    return x1 @ S.T.astype(np.int64), x0 @ S.T.astype(np.int64)
+
+
+def make_problem(n_snv, n_cells, seed, FN=0.1, FP=0.01, MS=0.15):
+    rng = np.random.default_rng(seed)
+    tree = synth.coalescent_tree(n_cells, rng) if n_cells > 1 else None
+    if tree is None:
+        S = np.array([[1], [0]], dtype=np.uint8)
+        codes = rng.integers(0, 4, size=(n_snv, 1)).astype(np.uint8)
+        codes[codes == 2] = 1
+    else:
+        S = tree.clade_matrix()
+        codes = synth.observe(tree, synth.throw_mutations(tree, n_snv, rng), FN, FP, MS, rng)
+    return codes, S
+
+
+def assert_soft_close(got, want):
+    err = np.abs(got - want) / np.maximum(1.0, np.abs(want))
+    assert err.max() <= Y_TOL, (err.max(), int(err.argmax()))
+
+
+# ------------------------------------------------------------ placement GEMM
+@pytest.mark.parametrize("n_snv,n_cells", [(1, 2), (5, 1), (127, 3), (128, 64), (129, 65), (300, 50), (1000, 200),
+                                            (2000, 300), (700, 513)])
+def test_counts_bit_exact_and_soft_weights(ctx, n_snv, n_cells):
+    codes, S = make_problem(n_snv, n_cells, seed=n_snv * 7 + n_cells)
+    FP, FN = 0.01, 0.1
+    packed, pitch = engine.pack_genotypes(codes)
+    bits, words = engine.pack_clades(S)
+    pl = engine.Placement(ctx, n_snv, n_cells, S.shape[0])
+    pl.set_genotypes_host(packed, pitch)
+    pl.set_clades_host(bits, words)
+    cnt = pl.debug_counts()
+    C1, C0 = oracle_counts(codes, S)
+    assert np.array_equal(cnt[:, :, 0], C1) and np.array_equal(cnt[:, :, 1], C0)      # integer work: bit exact
+    muts = np.where(codes == 3, np.nan, codes.astype(float))
+    want = O.map_mutations_gt(muts, S.astype(float), FP, FN)
+    got = pl.run_host(FP, FN)
+    assert_soft_close(got, want)
+    # one-shot host entry point gives the same numbers
+    got2 = engine.map_mutations(ctx, packed, pitch, bits, words, n_cells, FP, FN)
+    assert np.array_equal(got, got2)
+    pl.close()
+
+
+def test_row_keep_and_extreme_rates(ctx):
+    codes, S = make_problem(900, 120, seed=5)
+    packed, pitch = engine.pack_genotypes(codes)
+    bits, words = engine.pack_clades(S)
+    keep = (codes == 1).any(axis=1).astype(np.uint8)
+    keep[::7] = 0
+    muts = np.where(codes == 3, np.nan, codes.astype(float))
+    pl = engine.Placement(ctx, 900, 120, S.shape[0])
+    pl.set_clades_host(bits, words)
+    pl.set_genotypes_host(packed, pitch, keep)
+    for FP, FN in [(1e-6, 1e-6), (0.2, 0.4), (1e-3, 0.3)]:      # LAMBDA_MIN rates are the reference's default
+        want = O.map_mutations_gt(muts[keep.astype(bool)], S.astype(float), FP, FN)
+        assert_soft_close(pl.run_host(FP, FN), want)
+    pl.close()
+
+
+def test_all_missing_and_all_wildtype_rows(ctx):
+    n_cells = 40
+    rng = np.random.default_rng(9)
+    tree = synth.coalescent_tree(n_cells, rng)
+    S = tree.clade_matrix()
+    codes = np.zeros((6, n_cells), dtype=np.uint8)
+    codes[1] = 3                      # nothing observed: uniform over all rows of S
+    codes[2] = 1                      # everything mutated
+    codes[3, ::2] = 3
+    codes[4, 5] = 1
+    codes[5, :] = 2
+    muts = np.where(codes == 3, np.nan, codes.astype(float))
+    want = O.map_mutations_gt(muts, S.astype(float), 0.01, 0.1)
+    packed, pitch = engine.pack_genotypes(codes)
+    bits, words = engine.pack_clades(S)
+    got = engine.map_mutations(ctx, packed, pitch, bits, words, n_cells, 0.01, 0.1)
+    assert_soft_close(got, want)
+
+
+def test_placement_properties_at_scale(ctx):
+    """Size-independent properties on a problem the oracle would not finish:
+    every kept SNV distributes exactly one unit of mass, SNV order does not
+    matter, and two halves add up to the whole."""
+    import torch
+    n_cells, n_snv = 1000, 40000
+    rng = np.random.default_rng(2)
+    tree = synth.coalescent_tree(n_cells, rng)
+    S = tree.clade_matrix()
+    bits, words = engine.pack_clades(S)
+    dev = torch.device("cuda", ctx.device)
+    lo = torch.as_tensor(tree.lo[:-1], device=dev)
+    hi = torch.as_tensor(tree.hi[:-1], device=dev)
+    rate = torch.as_tensor(tree.branch_len[:-1], device=dev, dtype=torch.float32)
+    packed, pitch, keep = synth.observe_packed_torch(lo, hi, torch.as_tensor(tree.leaf_rank), n_snv, 0.1, 0.01, 0.2, dev,
+                                                      seed=4, rate=rate)
+    pl = engine.Placement(ctx, n_snv, n_cells, S.shape[0])
+    pl.set_clades_host(bits, words)
+    pl.set_genotypes(packed, pitch, keep)
+    y = pl.run_host(0.01, 0.1)
+    n_kept = int(keep.sum())
+    assert abs(y.sum() - n_kept) <= 1e-6 * n_kept
+    assert (y >= 0).all()
+    perm = torch.randperm(n_snv, device=dev)
+    pl.set_genotypes(packed[perm].contiguous(), pitch, keep[perm].contiguous())
+    y_perm = pl.run_host(0.01, 0.1)
+    np.testing.assert_allclose(y_perm, y, rtol=1e-5, atol=1e-4)
+    half = n_snv // 2
+    pa = engine.Placement(ctx, half, n_cells, S.shape[0])
+    pa.set_clades_host(bits, words)
+    pa.set_genotypes(packed[:half].contiguous(), pitch, keep[:half].contiguous())
+    ya = pa.run_host(0.01, 0.1)
+    pa.set_genotypes(packed[half:].contiguous(), pitch, keep[half:].contiguous())
+    yb = pa.run_host(0.01, 0.1)
+    np.testing.assert_allclose(ya + yb, y, rtol=1e-5, atol=1e-4)
+    # same inputs, same bits: the reduction order is fixed
+    pl.set_genotypes(packed, pitch, keep)
+    assert np.array_equal(pl.run_host(0.01, 0.1), y)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_placement_on_golden_cases(ctx, name):
+    g = load(name)
+    vcf, tree_file, meta = case_inputs(g)
+    tree, outg, FP0, FN0 = P.read_tree(tree_file, g["samples"])
+    columns = list(g["samples"])
+    active = np.array([c != outg for c in columns], dtype=np.uint8)
+    bits, words, nodes = P._clade_bits(tree, columns, active)
+    codes = g["muts_codes"]
+    packed, pitch = engine.pack_genotypes(codes)
+    keep = (((codes == 1) | (codes == 2)) & active.astype(bool)[None, :]).any(axis=1).astype(np.uint8)
+    if outg not in columns:
+        keep[:] = 1
+    got = engine.map_mutations(ctx, packed, pitch, bits, words, len(columns), float(g["FP"]), float(g["FN"]), keep)
+    assert got.shape == g["soft"].shape
+    assert_soft_close(got, g["soft"])
+
+
+# ------------------------------------------------------------------ decode
+@pytest.mark.parametrize("name", CASES)
+def test_vcf_decode_bit_exact(ctx, name):
+    g = load(name)
+    vcf, tree_file, meta = case_inputs(g)
+    if not os.path.exists(vcf):
+        pytest.skip("reference example_data not present on this machine")
+    muts, _, _ = P.get_mut_df(vcf, meta["exclude"], meta["include"], ctx=ctx)
+    assert list(muts.columns) == list(g["samples"])
+    assert np.array_equal(muts.codes, g["muts_codes"])
+    assert np.array_equal(np.array(muts.index).reshape(-1, 2), g["pos"])
+    want = O.get_mut_df(vcf, meta["exclude"], meta["include"])
+    assert muts._dec.n_noalt == want["skipped"][0] and muts._dec.n_filtered == want["skipped"][1]
+
+
+def test_vcf_decode_rejects_malformed_input(ctx, tmp_path):
+    good = ("##fileformat=VCFv4.3\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tcell1\tcell2\toutgcell\n"
+            "1\t10\t.\tA\tC\t.\tPASS\t.\tGT:DP\t0|1:3\t0|0:4\t0|0:2\n")
+    p = tmp_path / "ok.vcf"
+    p.write_text(good)
+    m, _, _ = P.get_mut_df(str(p), "", "", ctx=ctx)
+    assert m.shape == (1, 3) and m.codes.tolist() == [[1, 0, 0]]
+    for bad in (good.replace("0|0:4\t0|0:2", "0|0:4"),                 # a sample column is missing
+                good.replace("0|1:3", "0|x:3"),                         # GT does not end in a digit
+                good.replace("1\t10", "chrX\t10"),                      # int('X') fails in the reference
+                good.replace("GT:DP", "DP:AD")):                        # no GT in FORMAT
+        q = tmp_path / "bad.vcf"
+        q.write_text(bad)
+        with pytest.raises(engine._cabi.ScsError):
+            P.get_mut_df(str(q), "", "", ctx=ctx)
+
+
+def test_gt_reduce_matches_numpy(ctx):
+    import torch
+    rng = np.random.default_rng(8)
+    codes = rng.choice([0, 0, 0, 1, 2, 3], size=(5000, 77)).astype(np.uint8)
+    codes[::9] = np.where(codes[::9] == 3, 3, 0)
+    packed, pitch = engine.pack_genotypes(codes)
+    active = np.ones(77, dtype=np.uint8)
+    active[[3, 76]] = 0
+    dev = torch.device("cuda", ctx.device)
+    d = torch.as_tensor(packed, device=dev)
+    keep = torch.empty(5000, dtype=torch.uint8, device=dev)
+    n_kept, miss = engine.gt_reduce(ctx, d, pitch, 5000, 77, active, True, keep)
+    want_keep = (((codes == 1) | (codes == 2)) & active.astype(bool)[None, :]).any(axis=1)
+    assert np.array_equal(keep.cpu().numpy().astype(bool), want_keep) and n_kept == want_keep.sum()
+    np.testing.assert_array_equal(miss, (codes[want_keep] == 3).mean(axis=0))
+    n_all, miss_all = engine.gt_reduce(ctx, d, pitch, 5000, 77, active, False, keep)
+    assert n_all == 5000
+    np.testing.assert_array_equal(miss_all, (codes == 3).mean(axis=0))
+
+
+# ------------------------------------------------------ weights and the LRT
+@pytest.mark.parametrize("name", CASES)
+def test_branch_weights_on_golden_cases(ctx, name):
+    g = load(name)
+    vcf, tree_file, meta = case_inputs(g)
+    tree, outg, FP0, FN0 = P.read_tree(tree_file, g["samples"])
+    MS = dict(zip(g["MS_leaf_names"], g["MS_leaf"]))
+    for k, w in enumerate(g["w_maxs"]):
+        P.add_br_weights(tree, float(g["FP"]), float(g["FN"]), MS, float(w))
+        raw = np.array([n.weights[0] for n in tree.iter_descendants()])
+        np.testing.assert_allclose(raw, g["raw_weights"][k], rtol=1e-10)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_lrt_on_golden_model_data(ctx, name):
+    g = load(name)
+    problems = [(g["Y"][k], g["constr"][k], g["weights_norm"][k]) for k in range(len(g["w_maxs"]))]
+    res = P.get_LRT_poisson_batch(problems, ctx=ctx)
+    for k, (LR, dof, on_bound, p_val, opt) in enumerate(res):
+        assert dof == int(g["dof"][k])
+        assert on_bound == int(g["on_bound"][k])
+        assert abs(LR - g["LR"][k]) <= 1e-4 * max(1.0, abs(g["LR"][k]))
+        assert abs(p_val - g["p_val"][k]) <= 2e-3 * g["p_val"][k]
+        assert int(p_val < 0.05) == int(g["hyp"][k])                     # identical clock / no-clock decision
+        x = np.array([v[0] for v in opt])
+        assert np.abs(g["constr"][k] @ x).max() < 1e-8                    # the fit is exactly ultrametric
+        assert (x > 1e-6).all()
+
+
+def test_lrt_is_at_least_as_good_as_the_reference_optimum(ctx):
+    """The fitted lengths must not have a worse (barrier-free) null likelihood than
+    the reference's SciPy solution by more than the interior-point slack."""
+    g = load("example_clock")
+    for k in (0, len(g["w_maxs"]) - 1):
+        Y, w = g["Y"][k], g["weights_norm"][k]
+        (LR, dof, ob, p, opt), = P.get_LRT_poisson_batch([(Y, g["constr"][k], w)], ctx=ctx)
+        assert LR <= g["LR"][k] + 1e-3
+
+
+def test_lrt_batch_of_replicates(ctx):
+    """1,000 independent replicate problems in one launch equal 1,000 single launches."""
+    g = load("syn_a")
+    base = (g["Y"][0], g["constr"][0], g["weights_norm"][0])
+    rng = np.random.default_rng(0)
+    probs = []
+    for i in range(1000):
+        Y = base[0] * rng.uniform(0.5, 1.5, size=base[0].size)
+        probs.append((Y, base[1], base[2]))
+    res = P.get_LRT_poisson_batch(probs, ctx=ctx)
+    for i in (0, 17, 999):
+        single, = P.get_LRT_poisson_batch([probs[i]], ctx=ctx)
+        assert single[:4] == res[i][:4]
+    # spot-check against SciPy on a few replicates
+    for i in (3, 500):
+        LR, dof, ob, p, x = O.get_LRT_poisson(probs[i][0], g["constr"][0], g["init"][0], probs[i][2])
+        assert abs(res[i][0] - LR) <= 1e-4 * max(1.0, LR) and res[i][1] == dof and res[i][2] == ob
+
+
+def test_lrt_degenerate_input_reports_failure(ctx):
+    g = load("syn_c")
+    (res,) = P.get_LRT_poisson_batch([(np.zeros_like(g["Y"][0]), g["constr"][0], g["weights_norm"][0])], ctx=ctx)
+    assert len(res) == 6 and all(np.isnan(v) for v in res)            # the reference's failure tuple (:678)
+
+
+# ------------------------------------------------------------- whole path
+@pytest.mark.parametrize("name", CASES)
+def test_run_poisson_tree_test_tsv(ctx, name, tmp_path):
+    g = load(name)
+    vcf, tree_file, meta = case_inputs(g)
+    if not os.path.exists(vcf):
+        pytest.skip("reference example_data not present on this machine")
+    out = tmp_path / "out.tsv"
+    P.run_poisson_tree_test(vcf, tree_file, str(out), [float(w) for w in g["w_maxs"]], meta["exclude"], meta["include"],
+                            meta["FN_in"], meta["FP_in"])
+    got = out.read_text().split("\n")
+    ref = str(g["tsv"]).split("\n")
+    assert got[0] == ref[0]
+    rc, gc = ref[1].split("\t"), got[1].split("\t")
+    assert rc[:3] == gc[:3]                                              # muts, FN, FP
+    for i in range(3, len(rc), 4):
+        assert abs(float(rc[i]) - float(gc[i])) <= 1e-4 * max(1.0, abs(float(rc[i]))) + 6e-4   # 3 printed decimals
+        assert rc[i + 1] == gc[i + 1]                                    # dof
+        assert abs(float(rc[i + 2]) - float(gc[i + 2])) <= 2e-3 * float(rc[i + 2])
+        assert rc[i + 3] == gc[i + 3]                                    # H0 / H1
+
+
+def test_cli_entry_point(ctx, tmp_path):
+    g = load("syn_a")
+    vcf, tree_file, meta = case_inputs(g)
+    out = tmp_path / "cli.tsv"
+    P.main([vcf, tree_file, "-o", str(out), "-w", "100", "1000"])
+    lines = out.read_text().split("\n")
+    assert lines[0].split("\t")[:4] == ["muts", "FN", "FP", "-2logLR_100"] and len(lines) == 2

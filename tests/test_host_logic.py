@@ -1,0 +1,133 @@
+"""CPU tests of the host-side logic: tree surgery, clade masks, LRT model data,
+packing, and that the C-ABI library exports what the header declares."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import REPO, case_inputs, golden_path
+from oracle import pt_oracle as O
+from scsommerclock_b200 import engine, run_PT_test as P, synth
+from scsommerclock_b200.tree import NewickError, Tree
+
+CASES = ["example_clock", "example_noclock", "syn_a", "syn_b", "syn_c", "syn_c_incl"]
+
+
+def load(name):
+    return np.load(golden_path(name), allow_pickle=False)
+
+
+def _mut_from_golden(g):
+    c = g["muts_codes"].astype(float)
+    c[c == 3] = np.nan
+    return {"muts": c, "samples": g["samples"]}
+
+
+def test_header_declares_what_the_library_exports():
+    hdr = open(os.path.join(REPO, "include", "scsommerclock_b200.h")).read()
+    declared = set(re.findall(r"\b(scs_[a-z0-9_]+)\s*\(", hdr))
+    lib_path = os.path.join(REPO, "scsommerclock_b200", "libscs_b200.so")
+    if not os.path.exists(lib_path):
+        from scsommerclock_b200 import build
+        build.build()
+    L = ctypes.CDLL(lib_path)      # loads without a GPU: no compute call is made here
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, missing
+    from scsommerclock_b200 import _cabi
+    assert declared == set(_cabi.EXPORTED_SYMBOLS)
+    assert L.scs_version is not None
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(engine._cabi.ScsError):
+        engine.Context(0)
+
+
+def test_newick_formats_and_errors():
+    t = Tree("((a:1,b:2):0.5,(c:1,(d:1,e:1):2):1,f:3);", format=1)
+    assert t.get_leaf_names() == list("abcdef") and len(t) == 6
+    assert [n.name for n in t.traverse()] == ["", "", "", "f", "a", "b", "c", "", "d", "e"]
+    with pytest.raises(NewickError):
+        Tree("((a:1,b:2):0.5,(c:1,(d:1,e:1):2):1,f:3);", format=2)
+    t2 = Tree("((a:1,b:2)0.9:0.5,c:3)1:0;", format=2)
+    assert t2.children[0].support == 0.9
+    with pytest.raises(NewickError):
+        Tree("((a:1,b:2):0.5,(c:1", format=1)
+    with pytest.raises(NewickError):
+        Tree("(a:1,,b:1);", format=1)
+
+
+def test_set_outgroup_and_delete_child_order():
+    t = Tree("((a:1,b:2):0.5,(c:1,(d:1,e:1):2):1,f:3);", format=1)
+    t.set_outgroup(t & "d")
+    assert t.write() == "(d:0.5,(e:1,(c:1,((a:1,b:2):0.5,f:3):1):2):0.5);"
+    (t & "d").delete()
+    assert len(t.children) == 1                     # the root keeps a single child, like ete3
+    (t & "c").delete()                              # parent collapses, its other child is appended to the grandparent
+    assert [n.name for n in t.iter_leaves()] == ["e", "a", "b", "f"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_read_tree_and_clade_bits_match_golden(name):
+    g = load(name)
+    vcf, tree_file, meta = case_inputs(g)
+    if not os.path.exists(tree_file):
+        pytest.skip("reference example_data not present on this machine")
+    tree, outg, FP, FN = P.read_tree(tree_file, g["samples"])
+    assert [n.name for n in tree.iter_descendants()] == list(g["node_names"])
+    columns = list(g["samples"])
+    active = np.array([c != outg for c in columns], dtype=np.uint8)
+    bits, words, nodes = P._clade_bits(tree, columns, active)
+    S = engine.unpack_clades(bits, len(columns))[:, active.astype(bool)]
+    assert np.array_equal(S.astype(np.uint8), g["S"])                   # bit exact
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_get_model_data_matches_golden(name):
+    g = load(name)
+    vcf, tree_file, meta = case_inputs(g)
+    if not os.path.exists(tree_file):
+        pytest.skip("reference example_data not present on this machine")
+    for k, w in enumerate(g["w_maxs"]):
+        r = O.get_gt_tree(tree_file, _mut_from_golden(g), float(w), meta["FN_in"], meta["FP_in"])   # oracle fills the node attributes
+        Y, constr, init, wn, cols = P.get_model_data(r["tree"])
+        assert list(cols) == list(g["constr_cols"][k])
+        assert np.array_equal(constr.toarray(), g["constr"][k])
+        np.testing.assert_allclose(Y, g["Y"][k], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(init, g["init"][k], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(wn[:, 0], g["weights_norm"][k], rtol=1e-12)
+        back = P.ClockConstraints.from_dense(g["constr"][k])
+        assert np.array_equal(back.child_int, constr.child_int)
+        assert np.array_equal(back.toarray(), g["constr"][k])
+        np.testing.assert_allclose(constr @ init, g["constr"][k] @ init, atol=1e-9)
+
+
+def test_packing_round_trips():
+    rng = np.random.default_rng(3)
+    for n_cells in (1, 3, 4, 31, 32, 33, 257):
+        codes = rng.integers(0, 4, size=(17, n_cells)).astype(np.uint8)
+        packed, pitch = engine.pack_genotypes(codes)
+        assert pitch % 16 == 0 and packed.shape == (17, pitch)
+        assert np.array_equal(engine.unpack_genotypes(packed, n_cells), codes)
+        S = rng.integers(0, 2, size=(9, n_cells)).astype(np.uint8)
+        bits, words = engine.pack_clades(S)
+        assert np.array_equal(engine.unpack_clades(bits, n_cells), S.astype(bool))
+    f = np.array([[0.0, 1.0, 2.0, np.nan]])
+    assert np.array_equal(engine.unpack_genotypes(engine.pack_genotypes(f)[0], 4), [[0, 1, 2, 3]])
+
+
+def test_synthetic_tree_is_a_laminar_family():
+    rng = np.random.default_rng(0)
+    t = synth.coalescent_tree(37, rng)
+    S = t.clade_matrix()
+    assert S.shape == (74, 37) and S[-2].sum() == 37 and S[-1].sum() == 0
+    for v in range(37, 73):
+        a, b = t.left[v - 37], t.right[v - 37]
+        assert (S[v] == (S[a] | S[b])).all() and not (S[a] & S[b]).any()
+    nw = t.newick(["c%d" % i for i in range(37)], "outg")
+    assert len(Tree(nw, format=1)) == 38

@@ -1,0 +1,120 @@
+"""The CPU oracle (oracle/pt_oracle.py) against fixtures recorded from the
+unmodified reference (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import case_inputs, golden_path
+from oracle import pt_oracle as O
+
+CASES = ["example_clock", "example_noclock", "syn_a", "syn_b", "syn_c", "syn_c_incl"]
+SYN = [c for c in CASES if c.startswith("syn")]
+
+
+def load(name):
+    return np.load(golden_path(name), allow_pickle=False)
+
+
+def codes(muts):
+    return np.where(np.isnan(muts), 3, np.nan_to_num(muts)).astype(np.uint8)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_get_mut_df_bit_exact(name):
+    g = load(name)
+    vcf, tree, meta = case_inputs(g)
+    if not os.path.exists(vcf):
+        pytest.skip("reference example_data not present on this machine")
+    m = O.get_mut_df(vcf, meta["exclude"], meta["include"])
+    assert list(m["samples"]) == list(g["samples"])
+    assert np.array_equal(codes(m["muts"]), g["muts_codes"])
+    assert np.array_equal(np.array(m["pos"]).reshape(-1, 2), g["pos"])
+
+
+def _mut_from_golden(g):
+    c = g["muts_codes"].astype(float)
+    c[c == 3] = np.nan
+    return {"muts": c, "samples": g["samples"]}
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_tree_clades_and_placement(name):
+    g = load(name)
+    vcf, tree, meta = case_inputs(g)
+    if not os.path.exists(tree):
+        pytest.skip("reference example_data not present on this machine")
+    r = O.get_gt_tree(tree, _mut_from_golden(g), float(g["w_maxs"][0]), meta["FN_in"], meta["FP_in"])
+    assert r["FP"] == float(g["FP"]) and r["FN"] == float(g["FN"])
+    assert list(r["columns"]) == list(g["red_cols"])
+    assert np.array_equal(r["S"].astype(np.uint8), g["S"])              # clade masks: bit exact
+    assert r["n_muts"] == g["M_index_pos"].shape[0]
+    np.testing.assert_allclose(r["soft"], g["soft"], rtol=1e-9, atol=1e-12)
+    names = [l.name for l in r["tree"].get_leaves()]
+    assert names == list(g["MS_leaf_names"])
+    ms = dict(zip(r["columns"], r["MS"]))
+    np.testing.assert_allclose([ms[n] for n in names], g["MS_leaf"], rtol=0, atol=0)
+    raw = np.array([n.weights[0] for n in r["tree"].iter_descendants()])
+    np.testing.assert_allclose(raw, g["raw_weights"][0], rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", SYN)
+def test_placement_literal_loop_matches_vectorised(name):
+    g = load(name)
+    vcf, tree, meta = case_inputs(g)
+    r = O.get_gt_tree(tree, _mut_from_golden(g), float(g["w_maxs"][0]), meta["FN_in"], meta["FP_in"])
+    soft_lit, M = O.map_mutations_gt_literal(r["muts_red"], r["S"], r["FP"], r["FN"])
+    np.testing.assert_allclose(soft_lit, r["soft"], rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(M[:64], g["M_head"][:M.shape[0]], rtol=1e-9, atol=1e-300)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_model_data_and_lrt(name):
+    g = load(name)
+    vcf, tree, meta = case_inputs(g)
+    if not os.path.exists(tree):
+        pytest.skip("reference example_data not present on this machine")
+    mut = _mut_from_golden(g)
+    ws = list(g["w_maxs"])
+    if name.startswith("example"):
+        ws = ws[:1] + ws[-1:]           # the SciPy solve takes seconds per w
+    for w in ws:
+        k = list(g["w_maxs"]).index(w)
+        r = O.get_gt_tree(tree, mut, float(w), meta["FN_in"], meta["FP_in"])
+        Y, constr, init, wn, cols = O.get_model_data(r["tree"])
+        np.testing.assert_allclose(Y, g["Y"][k], rtol=1e-9, atol=1e-12)
+        assert np.array_equal(constr, g["constr"][k])
+        assert list(cols) == list(g["constr_cols"][k])
+        np.testing.assert_allclose(init, g["init"][k], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(wn[:, 0], g["weights_norm"][k], rtol=1e-12)
+        # same SciPy call on the fixture's own model data -> same optimiser path
+        LR, dof, on_bound, p, x = O.get_LRT_poisson(g["Y"][k], g["constr"][k], g["init"][k], g["weights_norm"][k])
+        assert dof == int(g["dof"][k]) and on_bound == int(g["on_bound"][k])
+        np.testing.assert_allclose(LR, g["LR"][k], rtol=1e-6)
+        np.testing.assert_allclose(p, g["p_val"][k], rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", SYN)
+def test_tsv_text(name):
+    g = load(name)
+    vcf, tree, meta = case_inputs(g)
+    tsv, res = O.run_poisson_tree_test(vcf, tree, [float(w) for w in g["w_maxs"]], meta["exclude"], meta["include"],
+                                       meta["FN_in"], meta["FP_in"])
+    ref = str(g["tsv"]).split("\n")
+    got = tsv.split("\n")
+    assert got[0] == ref[0]
+    rc, gc = ref[1].split("\t"), got[1].split("\t")
+    assert rc[:3] == gc[:3]
+    for i in range(3, len(rc), 4):
+        assert abs(float(rc[i]) - float(gc[i])) <= 2e-3 * max(1.0, abs(float(rc[i])))
+        assert rc[i + 1] == gc[i + 1] and rc[i + 3] == gc[i + 3]
+        assert abs(float(rc[i + 2]) - float(gc[i + 2])) <= 1e-3 * float(rc[i + 2])
+
+
+def test_pvalue_mixture_known_values():
+    from scipy.stats.distributions import chi2
+    assert O.lrt_pvalue(30.0, 29, 0) == pytest.approx(chi2.sf(30.0, 29))
+    want = 0.5 * chi2.sf(30.0, 29) + 0.5 * chi2.sf(30.0, 28)
+    assert O.lrt_pvalue(30.0, 29, 1) == pytest.approx(want)
+    # dof - k <= 0 terms are NaN in SciPy and get weight 0
+    assert np.isfinite(O.lrt_pvalue(3.0, 2, 3))
