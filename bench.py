@@ -1,0 +1,347 @@
+#!/usr/bin/env python3
+"""bench.py -- the PT-test hot path on synthetic coalescent-shaped data.
+
+    python bench.py --gpus 1 --steps 3 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...        (the reference's CPU algorithm, rank 0 only)
+
+Workload (BASELINE.json configs[3]): 10,000 cells x 1,000,000 SNVs PER GPU, SNV
+rows sharded over ranks (weak scaling), one all-reduce of the 2n branch weights,
+then the clock LRT for the ten default w_max values.  One "step" is one pass of
+the hot path over the resident packed genotype matrix:
+    row filter + missing rates (scs_gt_reduce) -> operand planes -> GEMM pass 1 ->
+    merge -> GEMM pass 2 -> reduce -> [all-reduce] -> LRT batch -> result to host.
+`value` times that with CUDA events, inputs already in HBM; `e2e` adds the H2D copy
+of the packed matrix from pinned host memory every step.  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+W_MAXS = [100.0, 200.0, 300.0, 400.0, 500.0, 600.0, 700.0, 800.0, 900.0, 1000.0]
+FN_TRUE, FP_TRUE, MS_TRUE = 0.10, 0.01, 0.15
+METRIC = "snv_branch_placements_per_s"
+# dram__bytes_read.sum + dram__bytes_write.sum of one scs_place_kernel launch at the default
+# workload, from the ncu --set full capture under profiles/ (None until a capture exists)
+NCU_TRAFFIC_BYTES = None
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cells", type=int, default=10000)
+    ap.add_argument("--snvs", type=int, default=1000000, help="SNVs per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def make_tree(n_cells, seed=1234):
+    from scsommerclock_b200 import synth
+    rng = np.random.default_rng(seed)
+    return synth.coalescent_tree(n_cells, rng)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks and throttle reasons while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            return
+        while not self.stop_flag.is_set():
+            line = p.stdout.readline()
+            if not line:
+                break
+            self.rows.append([c.strip() for c in line.split(",")])
+        p.terminate()
+
+    def summary(self):
+        sm, reasons, mx = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except Exception:
+                continue
+            for k, nm in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": mx, "reasons": [], "samples": 0}
+        busy = sorted(sm)[len(sm) // 2:]        # upper half: samples taken under load
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------- CPU arms
+def cpu_sample_inputs(tree, n_cells, n_sample, seed=99):
+    from scsommerclock_b200 import synth
+    rng = np.random.default_rng(seed)
+    br = synth.throw_mutations(tree, n_sample, rng)
+    codes = synth.observe(tree, br, FN_TRUE, FP_TRUE, MS_TRUE, rng)
+    return codes
+
+
+def cpu_port_baseline(tree, S, n_cells, seconds):
+    """The plain-C/OpenMP oracle (oracle/place_oracle.c) on a bounded sample."""
+    from oracle import c_oracle
+    cores = os.cpu_count() or 1
+    n_rows = S.shape[0]
+    probe = max(cores, 8)
+    codes = cpu_sample_inputs(tree, n_cells, probe)
+    t0 = time.perf_counter()
+    c_oracle.place(codes, S, FP_TRUE, FN_TRUE, cores)
+    dt = time.perf_counter() - t0
+    n_sample = int(min(max(probe, seconds / max(dt / probe, 1e-9)), 200000))
+    n_sample = max(cores, n_sample // cores * cores)
+    codes = cpu_sample_inputs(tree, n_cells, n_sample)
+    t0 = time.perf_counter()
+    c_oracle.place(codes, S, FP_TRUE, FN_TRUE, cores)
+    dt = time.perf_counter() - t0
+    return {"value": n_sample * n_rows / dt, "unit": "placements/s", "cores": cores, "kind": "port",
+            "sample": "%d SNVs x %d clade rows x %d cells of the same workload, oracle/place_oracle.c (OpenMP), %.1f s" % (n_sample, n_rows, n_cells, dt)}
+
+
+def reference_arm(args):
+    """The reference's own algorithm for the path -- map_mutations_gt's per-SNV NumPy
+    loop (run_PT_test.py:421-430), restated in oracle/pt_oracle.py because the Python
+    reference cannot travel to the GPU box -- on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import pt_oracle as O
+    tree = make_tree(args.cells)
+    S = tree.clade_matrix().astype(np.float64)
+    n_rows = S.shape[0]
+    # a bounded sample: a few SNVs per step (each costs ~8 passes over a 2n x n float64 matrix)
+    per_snv = 2.0e-8 * n_rows * args.cells * 1.0
+    n_sample = int(max(1, min(64, round(12.0 / max(per_snv, 1e-3)))))
+    codes = cpu_sample_inputs(tree, args.cells, n_sample * (args.steps + args.warmup))
+    muts = np.where(codes == 3, np.nan, codes.astype(float))
+    times = []
+    for it in range(args.warmup + args.steps):
+        chunk = muts[it * n_sample:(it + 1) * n_sample]
+        t0 = time.perf_counter()
+        O.map_mutations_gt_literal(chunk, S, FP_TRUE, FN_TRUE)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = n_sample * n_rows / (ms / 1e3)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "placements/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "coalescent %d cells x %d SNVs per GPU (BASELINE configs[3]); reference arm runs a bounded sample" % (args.cells, args.snvs),
+                       "cells": args.cells, "snvs_per_gpu": args.snvs, "clade_rows": n_rows, "w_max": W_MAXS},
+            "cpu_baseline": {"value": value, "unit": "placements/s", "cores": 1, "kind": "port",
+                             "sample": "%d SNVs per step: map_mutations_gt's per-SNV NumPy loop (run_PT_test.py:421-430) as restated in "
+                                       "oracle/pt_oracle.py; single process (the loop is single-threaded NumPy and needs ~%.0f GB at this size)"
+                                       % (n_sample, 6 * 8 * n_rows * args.cells / 1e9)},
+            "e2e": {"value": value, "unit": "placements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ GPU arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+    import torch
+    from scsommerclock_b200 import engine, run_PT_test as P, sharding, synth
+    rank, world, local = sharding.init_distributed()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ctx = engine.Context(local)
+    n_cells, n_snv = args.cells, args.snvs
+    pk, pk_kind = peaks()
+
+    # ---- the tree (same on every rank), through the product's own tree code
+    tree_s = make_tree(n_cells)
+    names = ["tumcell%05d" % (i + 1) for i in range(n_cells)]
+    columns = names + ["healthycell"]
+    tmp = tempfile.mkdtemp(prefix="scs_bench_")
+    tree_file = os.path.join(tmp, "bench_r%d.newick" % rank)
+    with open(tree_file, "w") as f:
+        f.write(tree_s.newick(names, "healthycell", scale=0.05))
+    tree, outg, _, _ = P.read_tree(tree_file, np.array(columns))
+    active = np.array([c != outg for c in columns], dtype=np.uint8)
+    bits, words, nodes = P._clade_bits(tree, columns, active)
+    n_rows = bits.shape[0]
+    n_cols = len(columns)
+
+    # ---- this rank's shard of SNV rows, generated on the device in the packed layout
+    lo = torch.as_tensor(tree_s.lo[:-1], device=dev)
+    hi = torch.as_tensor(tree_s.hi[:-1], device=dev)
+    rate = torch.as_tensor(tree_s.branch_len[:-1], device=dev, dtype=torch.float32)
+    packed, pitch, _ = synth.observe_packed_torch(lo, hi, torch.as_tensor(tree_s.leaf_rank), n_snv, FN_TRUE, FP_TRUE, MS_TRUE, dev,
+                                                  seed=1000 + rank, rate=rate, extra_cols=1)
+    torch.cuda.synchronize()
+    FP, FN = FP_TRUE, FN_TRUE / 2        # what get_gt_tree would pass for a CellPhy log with these rates
+
+    plan = engine.Placement(ctx, n_snv, n_cols, n_rows)
+    plan.set_clades_host(bits, words)
+    row_keep = torch.empty(n_snv, dtype=torch.uint8, device=dev)
+    y_dev = torch.zeros(n_rows, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def place_step():
+        n_kept, miss = engine.gt_reduce(ctx, packed, pitch, n_snv, n_cols, active, True, row_keep)
+        plan.set_genotypes(packed, pitch, row_keep, stream=stream)
+        plan.run(FP, FN, y_dev, stream=stream)
+        sharding.allreduce_soft_weights(y_dev)
+        return n_kept, miss
+
+    # ---- one untimed pass fixes the LRT model (branch order, weights) for the timed steps
+    n_kept, miss = place_step()
+    torch.cuda.synchronize()
+    soft = y_dev.cpu().numpy()
+    if world > 1:
+        t = torch.tensor(np.concatenate([[float(n_kept)], miss * n_kept]), dtype=torch.float64, device=dev)
+        sharding.allreduce_soft_weights(t)
+        n_kept_all = float(t[0].item())
+        miss = (t[1:] / n_kept_all).cpu().numpy()
+    MS_i = {c: float(np.clip(miss[i], P.LAMBDA_MIN, 1 - FN - 0.2)) for i, c in enumerate(columns) if active[i]}
+    st = {"soft": soft, "MS_i": MS_i, "n_muts": n_kept, "bits": bits, "words": words, "columns": columns, "weights": {}}
+    P._apply_placement(tree, st)
+    row_of = {id(n): i for i, n in enumerate(nodes)}
+    name_row = {n.name: i for i, n in enumerate(nodes)}
+    childs, weights, gathers = [], [], []
+    for w_max in W_MAXS:
+        P.add_br_weights(tree, FP, FN, MS_i, w_max, _state=st)
+        Y, constr, init, wn, cols = P.get_model_data(tree)
+        childs.append(constr.child_int)
+        weights.append(wn[:, 0].copy())
+        gathers.append(np.array([name_row[c] for c in cols], dtype=np.int32))
+    lrt = engine.LrtPlan(ctx, childs)
+    lrt.set_weights(weights)
+    lrt.set_gather(np.concatenate(gathers), n_rows)
+    lrt_out = torch.zeros((len(W_MAXS), 8), dtype=torch.float64, device=dev)
+
+    def step():
+        place_step()
+        lrt.run(y_dev, lrt_out, stream=stream)
+        return lrt_out.cpu()             # the step's result, read back to the host
+
+    pinned = None
+    if not args.no_e2e:
+        pinned = torch.empty(packed.shape, dtype=torch.uint8, pin_memory=True)
+        pinned.copy_(packed)
+        torch.cuda.synchronize()
+
+    def step_e2e():
+        packed.copy_(pinned, non_blocking=True)      # H2D of this step's input from pinned host memory
+        return step()
+
+    def timed(fn, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        sharding.barrier()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.start()
+        l0 = plan.info()["launches"]
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        gemm = []
+        e0.record()
+        for _ in range(steps):
+            res = fn()
+            gemm.append(plan.last_times())
+        e1.record()
+        torch.cuda.synchronize()
+        sharding.barrier()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.stop_flag.set()
+        ms = e0.elapsed_time(e1)
+        # this library's kernels inside the timed region: plan launches (operand expansion, two GEMM
+        # passes, merge, reduce) + 2 per step in scs_gt_reduce + 1 LRT kernel per step
+        n_launch = plan.info()["launches"] - l0 + 3 * steps
+        return sharding.max_over_ranks(ms, dev), gemm, res, n_launch
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_total, gemm_times, res, launches = timed(step, args.steps, args.warmup, sampler)
+    ms_step = ms_total / args.steps
+    placements = float(n_snv) * n_rows * world
+    value = placements / (ms_step / 1e3)
+
+    e2e = None
+    if not args.no_e2e:
+        ms_e2e, _, _, _ = timed(step_e2e, args.steps, min(args.warmup, 1))
+        e2e = {"value": placements / (ms_e2e / args.steps / 1e3), "unit": "placements/s",
+               "h2d_bytes_per_step": int(packed.numel()) * world, "d2h_bytes_per_step": int(lrt_out.numel() * 8 + n_cols * 4 + 8) * world,
+               "ms_per_step": ms_e2e / args.steps}
+
+    if rank == 0:
+        g = np.array(gemm_times)                         # [steps][pass1, merge, pass2, reduce]
+        t_gemm = float(np.mean(np.concatenate([g[:, 0], g[:, 2]])))      # average launch of the dominant kernel
+        flop = 2.0 * n_snv * n_rows * n_cols                             # algorithmic: SNV x cells x clade rows, 2 flop per MAC
+        achieved = flop / (t_gemm / 1e3) / 1e12
+        peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
+        out = res.numpy()
+        line = {
+            "metric": METRIC, "value": value, "unit": "placements/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": "coalescent %d cells x %d SNVs per GPU (BASELINE configs[3]), SNV rows sharded, one all-reduce of the branch weights, LRT for 10 w_max"
+                                   % (n_cells, n_snv),
+                       "cells": n_cells, "snvs_per_gpu": n_snv, "clade_rows": n_rows, "w_max": W_MAXS, "FN": FN_TRUE, "FP": FP_TRUE, "missing": MS_TRUE,
+                       "l2": "inputs larger than L2 (operand planes %.1f GB per GPU)" % (2.0 * plan.info()["M_pad"] * plan.info()["K_pad"] / 1e9),
+                       "tiling": plan.info()},
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": NCU_TRAFFIC_BYTES, "peak_source": pk_kind + " cuBLAS bf16, sustained (kernel timed inside a long step)",
+                         "kernel": "scs_place_kernel (tcgen05 kind::i8), avg of pass 1 and pass 2 launches",
+                         "algorithmic_flop_per_launch": flop, "ms_per_launch": t_gemm,
+                         "pass1_ms": float(g[:, 0].mean()), "merge_ms": float(g[:, 1].mean()), "pass2_ms": float(g[:, 2].mean()),
+                         "reduce_ms": float(g[:, 3].mean()),
+                         "executed_tensor_TOPs": 2 * achieved, "note": "each launch executes two exact 0/1 integer GEMMs (mutated / wild-type planes) per algorithmic contraction"},
+            "pt_tests": {"per_step": len(W_MAXS), "LR": [float(v) for v in out[:, 0]], "p_value": [float(v) for v in out[:, 3]],
+                         "newton_iterations": [int(v) for v in out[:, 6]], "status": [int(v) for v in out[:, 7]]},
+            "clocks": sampler.summary() if sampler else None,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            S = engine.unpack_clades(bits, n_cols)[:, :n_cells].astype(np.uint8)
+            line["cpu_baseline"] = cpu_port_baseline(tree_s, np.ascontiguousarray(S), n_cells, args.cpu_seconds)
+        print(json.dumps(line), flush=True)
+    sharding.barrier()
+
+
+if __name__ == "__main__":
+    main()

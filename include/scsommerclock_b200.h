@@ -50,6 +50,7 @@ extern "C" {
 typedef struct scs_ctx scs_ctx;
 typedef struct scs_placement scs_placement;
 typedef struct scs_vcf scs_vcf;
+typedef struct scs_lrt_plan scs_lrt_plan;
 
 /* ------------------------------------------------------------------ context */
 const char* scs_version(void);
@@ -108,6 +109,10 @@ int scs_placement_run(scs_placement* plan, double FP, double FN, double* d_soft_
 /* Same, then copies [n_rows] doubles to host memory and synchronises. */
 int scs_placement_run_host(scs_placement* plan, double FP, double FN, double* soft_weights, void* stream);
 const void* scs_placement_device_result(scs_placement* plan);
+/* Device durations (CUDA events on the launching stream) of the four kernels of the
+ * last scs_placement_run: ms[0] GEMM pass 1 (row statistics), ms[1] merge, ms[2]
+ * GEMM pass 2 (column sums), ms[3] reduction.  Waits for that run to finish. */
+int scs_placement_last_times(scs_placement* plan, float* ms);
 /* info[0..9] = M_pad, N_pad, K_pad, tasks, run_len, superblock_width, grid,
  * kernel launches so far, runs, dynamic smem bytes */
 int scs_placement_info(scs_placement* plan, int64_t* info, int32_t n);
@@ -141,6 +146,18 @@ int scs_branch_weights(scs_ctx* ctx, const uint32_t* clade_bits, int64_t pitch_w
  * (optional, may be NULL) receives the fitted branch lengths. */
 int scs_lrt_poisson_batch(scs_ctx* ctx, int32_t n_prob, const int64_t* br_off, const double* Y, const double* w,
                           const int32_t* child_int, double* out, double* x_out);
+/* The same batch as a reusable, device-resident plan (topology and workspace are
+ * uploaded once).  With a gather index the counts are taken from a per-node vector
+ * (e.g. the placement's soft weights, still on the device): Y[k] = d_Y[index[k]]. */
+int scs_lrt_plan_create(scs_ctx* ctx, int32_t n_prob, const int64_t* br_off, const int32_t* child_int,
+                        scs_lrt_plan** out);
+int scs_lrt_plan_destroy(scs_lrt_plan* plan);
+int scs_lrt_plan_set_weights(scs_lrt_plan* plan, const double* w);
+int scs_lrt_plan_set_gather(scs_lrt_plan* plan, const int32_t* index, int64_t src_len);
+/* Asynchronous on `stream`; d_out ([n_prob][8]) and d_x may be NULL (results stay in the plan). */
+int scs_lrt_plan_run(scs_lrt_plan* plan, const double* d_Y, double* d_out, double* d_x, void* stream);
+int scs_lrt_plan_run_host(scs_lrt_plan* plan, const double* Y, double* out, double* x_out, void* stream);
+const void* scs_lrt_plan_device_result(scs_lrt_plan* plan);
 
 #ifdef __cplusplus
 }

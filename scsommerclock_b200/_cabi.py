@@ -38,6 +38,7 @@ _SIGNATURES = {
     "scs_placement_run": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
     "scs_placement_run_host": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
     "scs_placement_device_result": (C.c_void_p, [C.c_void_p]),
+    "scs_placement_last_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "scs_placement_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
     "scs_placement_debug_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "scs_map_mutations": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
@@ -53,6 +54,13 @@ _SIGNATURES = {
                                      C.c_double, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
     "scs_lrt_poisson_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p]),
+    "scs_lrt_plan_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "scs_lrt_plan_destroy": (C.c_int, [C.c_void_p]),
+    "scs_lrt_plan_set_weights": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "scs_lrt_plan_set_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "scs_lrt_plan_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scs_lrt_plan_run_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scs_lrt_plan_device_result": (C.c_void_p, [C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

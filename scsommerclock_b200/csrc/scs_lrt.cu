@@ -93,14 +93,18 @@ __device__ double gamma_q(double a, double x) {
 
 // out[p*8 ..] = {LR, dof, on_bound, p_value, ll_H0, ll_H1, newton iterations, status}
 __global__ void __launch_bounds__(LRT_THREADS)
-scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ Yall, const double* __restrict__ wall,
-               const int* __restrict__ child_all, LrtWork ws, double* __restrict__ out, double* __restrict__ x_out) {
+scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ Ysrc, const int* __restrict__ gather,
+               double* __restrict__ Yall, const double* __restrict__ wall, const int* __restrict__ child_all, LrtWork ws,
+               double* __restrict__ out, double* __restrict__ x_out) {
     __shared__ double sh[LRT_THREADS / 32];
     __shared__ double s_bcast[4];
     __shared__ int s_nlev;
     const LrtProblem pb = probs[blockIdx.x];
     const int nb = pb.n_br, m1 = nb / 2, tid = threadIdx.x;
-    const double* Y = Yall + pb.br_off;
+    // counts in branch order: straight copy, or a gather from per-node soft weights
+    double* Y = Yall + pb.br_off;
+    for (int k = tid; k < nb; k += LRT_THREADS) Y[k] = gather ? Ysrc[gather[pb.br_off + k]] : Ysrc[pb.br_off + k];
+    __syncthreads();
     const double* w = wall + pb.br_off;
     const int* child = child_all + pb.br_off;
     double *l = ws.l + pb.br_off, *g = ws.g + pb.br_off, *d = ws.d + pb.br_off, *dl = ws.dl + pb.br_off;
@@ -367,10 +371,24 @@ using namespace scs;
 
 extern "C" {
 
-int scs_lrt_poisson_batch(scs_ctx* ctx, int32_t n_prob, const int64_t* br_off, const double* Y, const double* w,
-                          const int32_t* child_int, double* out, double* x_out) {
-    if (!ctx || !br_off || !Y || !w || !child_int || !out) return set_error(SCS_ERR_ARG, "null argument");
-    if (n_prob <= 0) return SCS_OK;
+struct LrtPlanImpl {
+    scs_ctx* ctx = nullptr;
+    int n_prob = 0;
+    size_t nbr = 0, nnode = 0;
+    double* d_buf = nullptr;
+    int* i_buf = nullptr;
+    LrtProblem* d_probs = nullptr;
+    double *dYsrc = nullptr, *dY = nullptr, *dw = nullptr, *d_out = nullptr, *d_x = nullptr;
+    int *d_child = nullptr, *d_gather = nullptr;
+    bool have_gather = false, have_w = false;
+    size_t src_len = 0;
+    LrtWork ws;
+    long long launches = 0;
+};
+
+int scs_lrt_plan_create(scs_ctx* ctx, int32_t n_prob, const int64_t* br_off, const int32_t* child_int, scs_lrt_plan** out) {
+    if (!ctx || !br_off || !child_int || !out) return set_error(SCS_ERR_ARG, "null argument");
+    if (n_prob <= 0) return set_error(SCS_ERR_ARG, "empty LRT batch");
     SCS_CUDA(cudaSetDevice(ctx->device));
     const int64_t total_br = br_off[n_prob];
     if (total_br > (int64_t(1) << 30)) return set_error(SCS_ERR_ARG, "batch too large: split it");
@@ -388,55 +406,128 @@ int scs_lrt_poisson_batch(scs_ctx* ctx, int32_t n_prob, const int64_t* br_off, c
         probs[p].node_off = int(node_off);
         node_off += nb / 2 + 2;   // levoff needs (levels + 1) <= nodes + 1 entries
     }
-    const size_t nbr = size_t(total_br), nnode = size_t(node_off);
-    double* d_buf = nullptr;
-    int* i_buf = nullptr;
-    LrtProblem* d_probs = nullptr;
-    const size_t dbl = 2 * nbr /*Y, w*/ + 4 * nbr /*l g d dl*/ + 7 * nnode + size_t(n_prob) * 8 + nbr /*x_out*/;
-    const size_t ints = nbr /*child*/ + 4 * nnode;
-    int rc = SCS_OK;
-    do {
-        if (cudaMalloc(&d_buf, dbl * sizeof(double)) != cudaSuccess || cudaMalloc(&i_buf, ints * sizeof(int)) != cudaSuccess ||
-            cudaMalloc(&d_probs, size_t(n_prob) * sizeof(LrtProblem)) != cudaSuccess) {
-            rc = set_error(SCS_ERR_OOM, "device allocation failed for the LRT batch");
-            break;
-        }
-        double* dY = d_buf;
-        double* dw = dY + nbr;
-        LrtWork ws;
-        ws.l = dw + nbr;
-        ws.g = ws.l + nbr;
-        ws.d = ws.g + nbr;
-        ws.dl = ws.d + nbr;
-        ws.h = ws.dl + nbr;
-        ws.Hd = ws.h + nnode;
-        ws.e = ws.Hd + nnode;
-        ws.D = ws.e + nnode;
-        ws.r = ws.D + nnode;
-        ws.x = ws.r + nnode;
-        ws.G = ws.x + nnode;
-        double* d_out = ws.G + nnode;
-        double* d_x = d_out + size_t(n_prob) * 8;
-        int* d_child = i_buf;
-        ws.up = d_child + nbr;
-        ws.order = ws.up + nnode;
-        ws.level = ws.order + nnode;
-        ws.levoff = ws.level + nnode;
-        cudaError_t e = cudaMemcpy(dY, Y, nbr * sizeof(double), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(dw, w, nbr * sizeof(double), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(d_child, child_int, nbr * sizeof(int), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(d_probs, probs.data(), size_t(n_prob) * sizeof(LrtProblem), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) {
-            scs_lrt_kernel<<<n_prob, LRT_THREADS>>>(d_probs, dY, dw, d_child, ws, d_out, x_out ? d_x : nullptr);
-            e = cudaGetLastError();
-        }
-        if (e == cudaSuccess) e = cudaMemcpy(out, d_out, size_t(n_prob) * 8 * sizeof(double), cudaMemcpyDeviceToHost);
-        if (e == cudaSuccess && x_out) e = cudaMemcpy(x_out, d_x, nbr * sizeof(double), cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) rc = set_error(SCS_ERR_CUDA, "LRT batch failed: %s", cudaGetErrorString(e));
-    } while (0);
-    cudaFree(d_buf);
-    cudaFree(i_buf);
-    cudaFree(d_probs);
+    LrtPlanImpl* pl = new LrtPlanImpl();
+    pl->ctx = ctx;
+    pl->n_prob = n_prob;
+    pl->nbr = size_t(total_br);
+    pl->nnode = size_t(node_off);
+    const size_t nbr = pl->nbr, nnode = pl->nnode;
+    const size_t dbl = 8 * nbr /*Ysrc Y w l g d dl x*/ + 7 * nnode + size_t(n_prob) * 8;
+    const size_t ints = 2 * nbr /*child gather*/ + 4 * nnode;
+    if (cudaMalloc(&pl->d_buf, dbl * sizeof(double)) != cudaSuccess || cudaMalloc(&pl->i_buf, ints * sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&pl->d_probs, size_t(n_prob) * sizeof(LrtProblem)) != cudaSuccess) {
+        scs_lrt_plan_destroy(reinterpret_cast<scs_lrt_plan*>(pl));
+        return set_error(SCS_ERR_OOM, "device allocation failed for the LRT batch");
+    }
+    double* q = pl->d_buf;
+    pl->dYsrc = q; q += nbr;
+    pl->dY = q; q += nbr;
+    pl->dw = q; q += nbr;
+    pl->ws.l = q; q += nbr;
+    pl->ws.g = q; q += nbr;
+    pl->ws.d = q; q += nbr;
+    pl->ws.dl = q; q += nbr;
+    pl->d_x = q; q += nbr;
+    pl->ws.h = q; q += nnode;
+    pl->ws.Hd = q; q += nnode;
+    pl->ws.e = q; q += nnode;
+    pl->ws.D = q; q += nnode;
+    pl->ws.r = q; q += nnode;
+    pl->ws.x = q; q += nnode;
+    pl->ws.G = q; q += nnode;
+    pl->d_out = q;
+    int* iq = pl->i_buf;
+    pl->d_child = iq; iq += nbr;
+    pl->d_gather = iq; iq += nbr;
+    pl->ws.up = iq; iq += nnode;
+    pl->ws.order = iq; iq += nnode;
+    pl->ws.level = iq; iq += nnode;
+    pl->ws.levoff = iq;
+    cudaError_t e = cudaMemcpy(pl->d_child, child_int, nbr * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(pl->d_probs, probs.data(), size_t(n_prob) * sizeof(LrtProblem), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        scs_lrt_plan_destroy(reinterpret_cast<scs_lrt_plan*>(pl));
+        return set_error(SCS_ERR_CUDA, "LRT plan upload failed: %s", cudaGetErrorString(e));
+    }
+    *out = reinterpret_cast<scs_lrt_plan*>(pl);
+    return SCS_OK;
+}
+
+int scs_lrt_plan_destroy(scs_lrt_plan* h) {
+    LrtPlanImpl* pl = reinterpret_cast<LrtPlanImpl*>(h);
+    if (!pl) return SCS_OK;
+    cudaFree(pl->d_buf);
+    cudaFree(pl->i_buf);
+    cudaFree(pl->d_probs);
+    delete pl;
+    return SCS_OK;
+}
+
+int scs_lrt_plan_set_weights(scs_lrt_plan* h, const double* w) {
+    LrtPlanImpl* pl = reinterpret_cast<LrtPlanImpl*>(h);
+    if (!pl || !w) return set_error(SCS_ERR_ARG, "null argument");
+    SCS_CUDA(cudaMemcpy(pl->dw, w, pl->nbr * sizeof(double), cudaMemcpyHostToDevice));
+    pl->have_w = true;
+    return SCS_OK;
+}
+
+int scs_lrt_plan_set_gather(scs_lrt_plan* h, const int32_t* index, int64_t src_len) {
+    LrtPlanImpl* pl = reinterpret_cast<LrtPlanImpl*>(h);
+    if (!pl) return set_error(SCS_ERR_ARG, "null argument");
+    if (!index) {
+        pl->have_gather = false;
+        return SCS_OK;
+    }
+    for (size_t k = 0; k < pl->nbr; ++k)
+        if (index[k] < 0 || index[k] >= src_len) return set_error(SCS_ERR_ARG, "gather index %d out of range [0,%lld)", index[k], (long long)src_len);
+    SCS_CUDA(cudaMemcpy(pl->d_gather, index, pl->nbr * sizeof(int), cudaMemcpyHostToDevice));
+    pl->have_gather = true;
+    pl->src_len = size_t(src_len);
+    return SCS_OK;
+}
+
+int scs_lrt_plan_run(scs_lrt_plan* h, const double* d_Y, double* d_out, double* d_x, void* stream) {
+    LrtPlanImpl* pl = reinterpret_cast<LrtPlanImpl*>(h);
+    if (!pl || !d_Y) return set_error(SCS_ERR_ARG, "null argument");
+    if (!pl->have_w) return set_error(SCS_ERR_ARG, "scs_lrt_plan_set_weights has not been called");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    scs_lrt_kernel<<<pl->n_prob, LRT_THREADS, 0, st>>>(pl->d_probs, d_Y, pl->have_gather ? pl->d_gather : nullptr, pl->dY, pl->dw,
+                                                        pl->d_child, pl->ws, d_out ? d_out : pl->d_out, d_x ? d_x : pl->d_x);
+    pl->launches++;
+    SCS_CUDA(cudaGetLastError());
+    return SCS_OK;
+}
+
+int scs_lrt_plan_run_host(scs_lrt_plan* h, const double* Y, double* out, double* x_out, void* stream) {
+    LrtPlanImpl* pl = reinterpret_cast<LrtPlanImpl*>(h);
+    if (!pl || !Y || !out) return set_error(SCS_ERR_ARG, "null argument");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t n = pl->have_gather ? pl->src_len : pl->nbr;
+    if (n > pl->nbr) return set_error(SCS_ERR_ARG, "gather source longer than the batch");
+    SCS_CUDA(cudaMemcpyAsync(pl->dYsrc, Y, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    int rc = scs_lrt_plan_run(h, pl->dYsrc, nullptr, nullptr, stream);
+    if (rc != SCS_OK) return rc;
+    SCS_CUDA(cudaMemcpyAsync(out, pl->d_out, size_t(pl->n_prob) * 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (x_out) SCS_CUDA(cudaMemcpyAsync(x_out, pl->d_x, pl->nbr * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SCS_CUDA(cudaStreamSynchronize(st));
+    return SCS_OK;
+}
+
+const void* scs_lrt_plan_device_result(scs_lrt_plan* h) {
+    LrtPlanImpl* pl = reinterpret_cast<LrtPlanImpl*>(h);
+    return pl ? pl->d_out : nullptr;
+}
+
+int scs_lrt_poisson_batch(scs_ctx* ctx, int32_t n_prob, const int64_t* br_off, const double* Y, const double* w,
+                          const int32_t* child_int, double* out, double* x_out) {
+    if (!ctx || !br_off || !Y || !w || !child_int || !out) return set_error(SCS_ERR_ARG, "null argument");
+    if (n_prob <= 0) return SCS_OK;
+    scs_lrt_plan* pl = nullptr;
+    int rc = scs_lrt_plan_create(ctx, n_prob, br_off, child_int, &pl);
+    if (rc != SCS_OK) return rc;
+    rc = scs_lrt_plan_set_weights(pl, w);
+    if (rc == SCS_OK) rc = scs_lrt_plan_run_host(pl, Y, out, x_out, nullptr);
+    scs_lrt_plan_destroy(pl);
     return rc;
 }
 

@@ -475,6 +475,8 @@ struct Placement {
     uint32_t* stage_mask = nullptr;
     size_t stage_mask_bytes = 0;
     long long launches = 0;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // brackets of the four kernels of run()
+    bool timed = false;
 };
 
 static int round_up(int64_t v, int m) { return int((v + m - 1) / m * m); }
@@ -555,6 +557,7 @@ int scs_placement_create(scs_ctx* ctx, int64_t n_snv, int32_t n_cells, int32_t n
         cudaFuncSetAttribute(scs_place_kernel<PASS_DUMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
         cudaFuncSetAttribute(scs_place_kernel<PASS_STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
         cudaFuncSetAttribute(scs_place_kernel<PASS_COLSUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+        for (int i = 0; i < 5; ++i) cudaEventCreate(&pl->ev[i]);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) {
             rc = set_error(SCS_ERR_CUDA, "placement plan setup failed: %s", cudaGetErrorString(e));
@@ -583,6 +586,8 @@ int scs_placement_destroy(scs_placement* h) {
     cudaFree(pl->dump);
     cudaFree(pl->stage_gt);
     cudaFree(pl->stage_mask);
+    for (int i = 0; i < 5; ++i)
+        if (pl->ev[i]) cudaEventDestroy(pl->ev[i]);
     delete pl;
     return SCS_OK;
 }
@@ -696,12 +701,18 @@ int scs_placement_run(scs_placement* h, double FP, double FN, double* d_soft_wei
     double a1, a0;
     fill_constants(pl, FP, FN, &a1, &a0);
     const PlaceParams& p = pl->prm;
+    cudaEventRecord(pl->ev[0], st);
     scs_place_kernel<PASS_STATS><<<pl->grid, NUM_THREADS, SMEM_TOTAL, st>>>(pl->tm_x1, pl->tm_x0, pl->tm_s, p);
+    cudaEventRecord(pl->ev[1], st);
     scs_merge_stats_kernel<<<(p.M_pad + 255) / 256, 256, 0, st>>>(pl->stats, p.num_col_tiles * 2, p.M, p.M_pad,
                                                                   pl->have_row_keep ? pl->row_keep : nullptr, a1, a0, pl->rowref);
+    cudaEventRecord(pl->ev[2], st);
     scs_place_kernel<PASS_COLSUM><<<pl->grid, NUM_THREADS, SMEM_TOTAL, st>>>(pl->tm_x1, pl->tm_x0, pl->tm_s, p);
+    cudaEventRecord(pl->ev[3], st);
     double* y = d_soft_weights ? d_soft_weights : pl->y;
     scs_reduce_colpart_kernel<<<(p.N + 255) / 256, 256, 0, st>>>(pl->colpart, p.num_runs, p.N, p.N_pad, y);
+    cudaEventRecord(pl->ev[4], st);
+    pl->timed = true;
     pl->launches += 4;
     SCS_CUDA(cudaGetLastError());
     return SCS_OK;
@@ -745,6 +756,15 @@ int scs_placement_info(scs_placement* h, int64_t* info, int32_t n) {
     if (!pl || !info) return set_error(SCS_ERR_ARG, "null argument");
     const int64_t v[10] = {pl->M_pad, pl->N_pad, pl->K_pad, pl->prm.num_tasks, pl->prm.run_len, pl->prm.sb_width, pl->grid, pl->launches, pl->prm.num_runs, SMEM_TOTAL};
     for (int i = 0; i < n && i < 10; ++i) info[i] = v[i];
+    return SCS_OK;
+}
+
+int scs_placement_last_times(scs_placement* h, float* ms) {
+    Placement* pl = reinterpret_cast<Placement*>(h);
+    if (!pl || !ms) return set_error(SCS_ERR_ARG, "null argument");
+    if (!pl->timed) return set_error(SCS_ERR_ARG, "scs_placement_run has not been called yet");
+    SCS_CUDA(cudaEventSynchronize(pl->ev[4]));
+    for (int i = 0; i < 4; ++i) SCS_CUDA(cudaEventElapsedTime(&ms[i], pl->ev[i], pl->ev[i + 1]));
     return SCS_OK;
 }
 

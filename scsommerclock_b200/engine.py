@@ -159,6 +159,12 @@ class Placement:
         check(lib().scs_placement_run_host(self._h, float(FP), float(FN), ptr(out), _stream_handle(stream)))
         return out
 
+    def last_times(self):
+        """Device ms of (GEMM pass 1, merge, GEMM pass 2, reduce) of the last run."""
+        ms = (C.c_float * 4)()
+        check(lib().scs_placement_last_times(self._h, ms))
+        return [float(v) for v in ms]
+
     def device_result_ptr(self):
         return int(lib().scs_placement_device_result(self._h))
 
@@ -259,3 +265,53 @@ def lrt_poisson_batch(ctx, Ys, ws, child_ints, want_x=False):
     check(lib().scs_lrt_poisson_batch(ctx._h, n, ptr(off), ptr(Y), ptr(w), ptr(ch), ptr(out), ptr(x)))
     xs = [x[off[i]:off[i + 1]] for i in range(n)] if want_x else None
     return out, xs
+
+
+class LrtPlan:
+    """Reusable device-resident LRT batch (scs_lrt_plan): fixed topologies, weights
+    set once, counts fed per run from the host or straight from device memory."""
+
+    def __init__(self, ctx, child_ints):
+        self.ctx = ctx
+        sizes = np.array([len(c) for c in child_ints], dtype=np.int64)
+        self.off = np.zeros(len(child_ints) + 1, dtype=np.int64)
+        self.off[1:] = np.cumsum(sizes)
+        self.n_prob = len(child_ints)
+        ch = np.ascontiguousarray(np.concatenate(child_ints), dtype=np.int32)
+        h = C.c_void_p()
+        check(lib().scs_lrt_plan_create(ctx._h, self.n_prob, ptr(self.off), ptr(ch), C.byref(h)))
+        self._h = h
+        self.launches = 0
+
+    def set_weights(self, ws):
+        w = np.ascontiguousarray(np.concatenate(ws), dtype=np.float64)
+        assert w.size == self.off[-1]
+        check(lib().scs_lrt_plan_set_weights(self._h, ptr(w)))
+
+    def set_gather(self, index, src_len):
+        index = np.ascontiguousarray(index, dtype=np.int32)
+        assert index.size == self.off[-1]
+        check(lib().scs_lrt_plan_set_gather(self._h, ptr(index), int(src_len)))
+
+    def run(self, d_Y, d_out=None, stream=None):
+        check(lib().scs_lrt_plan_run(self._h, _dev_ptr(d_Y), _dev_ptr(d_out), None, _stream_handle(stream)))
+        self.launches += 1
+
+    def run_host(self, Y, want_x=False, stream=None):
+        Y = np.ascontiguousarray(Y, dtype=np.float64)
+        out = np.zeros((self.n_prob, 8))
+        x = np.zeros(int(self.off[-1])) if want_x else None
+        check(lib().scs_lrt_plan_run_host(self._h, ptr(Y), ptr(out), ptr(x), _stream_handle(stream)))
+        self.launches += 1
+        return out, x
+
+    def close(self):
+        if self._h:
+            lib().scs_lrt_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

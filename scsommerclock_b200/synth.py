@@ -118,7 +118,7 @@ def observe(tree, snv_branch, FN, FP, MS, rng):
     return np.where(miss, 3, called.astype(np.uint8)).astype(np.uint8)
 
 
-def observe_packed_torch(lo, hi, leaf_rank, n_snv, FN, FP, MS, device, seed=0, chunk=8192, rate=None):
+def observe_packed_torch(lo, hi, leaf_rank, n_snv, FN, FP, MS, device, seed=0, chunk=8192, rate=None, extra_cols=0):
     """Same model, generated on the GPU straight into the packed 2-bit layout
     (bench-sized inputs: 10^10 entries never exist on the host).  ``lo/hi`` are the
     per-branch clade intervals (torch int64 on ``device``), ``rate`` optional branch
@@ -128,7 +128,7 @@ def observe_packed_torch(lo, hi, leaf_rank, n_snv, FN, FP, MS, device, seed=0, c
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     n = leaf_rank.numel()
-    pitch = ((n + 3) // 4 + 15) // 16 * 16
+    pitch = ((n + extra_cols + 3) // 4 + 15) // 16 * 16
     packed = torch.zeros((n_snv, pitch), dtype=torch.uint8, device=device)
     keep = torch.zeros(n_snv, dtype=torch.uint8, device=device)
     if rate is None:
