@@ -63,6 +63,7 @@ struct PlaceParams {
     int num_k_blocks;
     int num_row_blocks, num_col_tiles;
     int run_len, num_runs, sb_width, num_tasks;
+    int l2_hints;              // 1: clade tiles evict-last, genotype tiles evict-first
     float a1h, a1l, a0h, a0l;  // log2-unit constants, split so that a?h * count is exact
     float a1f, a0f;            // plain fp32 copies, used only to rank columns
     uint2* stats;              // pass 1 out: [num_col_tiles*2][M_pad] {ref counts, sum}
@@ -140,6 +141,8 @@ scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constan
         if (ptx::elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
+            const uint64_t pol_x = p.l2_hints ? ptx::L2_EVICT_FIRST : ptx::L2_EVICT_NORMAL;
+            const uint64_t pol_s = p.l2_hints ? ptx::L2_EVICT_LAST : ptx::L2_EVICT_NORMAL;
             for (int t = blockIdx.x; t < p.num_tasks; t += gridDim.x) {
                 int j, r0, r1;
                 decode_task(p, t, j, r0, r1);
@@ -148,9 +151,11 @@ scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constan
                         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* st = smem + stage * STAGE_BYTES;
                         ptx::mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-                        ptx::tma_load_2d(&tm_x1, &full_bar[stage], st, kb * BLOCK_K, r * BLOCK_M);
-                        ptx::tma_load_2d(&tm_x0, &full_bar[stage], st + STAGE_A_BYTES, kb * BLOCK_K, r * BLOCK_M);
-                        ptx::tma_load_2d(&tm_s, &full_bar[stage], st + 2 * STAGE_A_BYTES, kb * BLOCK_K, j * BLOCK_N);
+                        // the clade slab is re-read by this CTA for every row block of the run and shared
+                        // by the whole super-block: keep it; genotype rows stream through once per super-block
+                        ptx::tma_load_2d_hint(&tm_x1, &full_bar[stage], st, kb * BLOCK_K, r * BLOCK_M, pol_x);
+                        ptx::tma_load_2d_hint(&tm_x0, &full_bar[stage], st + STAGE_A_BYTES, kb * BLOCK_K, r * BLOCK_M, pol_x);
+                        ptx::tma_load_2d_hint(&tm_s, &full_bar[stage], st + 2 * STAGE_A_BYTES, kb * BLOCK_K, j * BLOCK_N, pol_s);
                         if (++stage == NUM_STAGES) {
                             stage = 0;
                             phase ^= 1;
@@ -520,13 +525,22 @@ int scs_placement_create(scs_ctx* ctx, int64_t n_snv, int32_t n_cells, int32_t n
     p.num_k_blocks = pl->K_pad / BLOCK_K;
     p.num_row_blocks = pl->M_pad / BLOCK_M;
     p.num_col_tiles = pl->N_pad / BLOCK_N;
-    // Super-block: as many column tiles as keep the clade slab within ~40 MB of L2.
+    // Super-block: the w column tiles whose clade slab the concurrently running CTAs share.
+    // With sm_count CTAs in flight the live L2 footprint is  w * slab + (sm_count / w) * 2 planes
+    // * rows, smallest near w ~ sqrt(sm_count).  B200's L2 is two ~63 MB halves that replicate
+    // lines read from both dies, so this matters: measured at 10k cells x 1M SNVs
+    // (profiles/r01_l2_sweep.txt) w = 32 (41 MB slab) runs at a 48% L2 hit rate and 6.6 TB/s of
+    // DRAM reads, w = 12..16 at ~225 ms per pass instead of ~330 ms.
     const size_t slab = size_t(BLOCK_N) * pl->K_pad;
-    int sbw = int(std::max<size_t>(1, (size_t(40) << 20) / slab));
+    int sbw = std::max(1, int(std::lround(std::sqrt(double(ctx->sm_count)))));
+    if (const char* e = getenv("SCS_SLAB_MB")) sbw = int(std::max<size_t>(1, (size_t(std::max(1, atoi(e))) << 20) / slab));
     p.sb_width = std::min(sbw, p.num_col_tiles);
+    p.l2_hints = 1;
+    if (const char* e = getenv("SCS_L2_HINTS")) p.l2_hints = atoi(e) != 0;
     // Runs: long enough to amortise the end-of-run column reduction, short enough
     // that every SM gets several tasks.
     int run_len = 32;
+    if (const char* e = getenv("SCS_RUN_LEN")) run_len = std::max(1, atoi(e));
     while (run_len > 1 && (int64_t(p.num_row_blocks + run_len - 1) / run_len) * p.num_col_tiles < 4 * ctx->sm_count) run_len >>= 1;
     p.run_len = run_len;
     p.num_runs = (p.num_row_blocks + run_len - 1) / run_len;
