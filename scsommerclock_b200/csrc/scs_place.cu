@@ -37,23 +37,43 @@ namespace scs {
 // ------------------------------------------------------------------ tiling
 constexpr int BLOCK_M = 128;  // SNV rows per tile (= TMEM lanes)
 constexpr int BLOCK_N = 128;  // clade rows (GEMM columns) per tile
-constexpr int BLOCK_K = 128;  // cells per pipeline stage (bytes, u8 operands)
+constexpr int BLOCK_K = 128;  // cells per pipeline stage (bytes, 8-bit operands)
 constexpr int UMMA_K = 32;    // cells per tcgen05.mma (8-bit kinds)
-constexpr int NUM_STAGES = 4;
-constexpr int STAGE_A_BYTES = BLOCK_M * BLOCK_K;  // one genotype plane
-constexpr int STAGE_B_BYTES = BLOCK_N * BLOCK_K;
-constexpr int STAGE_BYTES = 2 * STAGE_A_BYTES + STAGE_B_BYTES;
+constexpr int TILE_BYTES = BLOCK_M * BLOCK_K;  // one 128 x 128 operand tile
 constexpr int NUM_EPI_WARPS = 8;  // 4 TMEM lane quarters x 2 column halves
 constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
-constexpr int TMEM_COLS = 512;  // 2 accumulator stages x 2 planes x 128 columns
+constexpr int TMEM_COLS = 512;
 constexpr int SMEM_BARRIER_BYTES = 256;
 constexpr int SMEM_RED_BYTES = 4 * BLOCK_N * 4;
-constexpr int SMEM_TOTAL = NUM_STAGES * STAGE_BYTES + SMEM_BARRIER_BYTES + SMEM_RED_BYTES + 1024;
 
-// kind::i8 instruction descriptor: D = s32 (c_format 2 at bits [4,6)), A and B
-// unsigned 8 bit (format 0 at [7,10) / [10,13)), both K-major (bits 15, 16 = 0),
+// Two ways to get the two count matrices out of the tensor cores:
+//  MODE_PLANES  two unsigned-8-bit 0/1 planes (mutated / wild type), two kind::i8 MMAs
+//               per K step, s32 accumulators: exact by construction, any cell count.
+//  MODE_RADIX   one FP8 (e5m2) plane holding 1 for "mutated" and 4096 for "wild type",
+//               one kind::f8f6f4 MMA per K step, f32 accumulator = C1 + 4096 * C0.  Both
+//               counts stay below 4096 per accumulator because K is cut into chunks of
+//               31 * 128 = 3968 cells, each with its own TMEM columns, so every partial sum
+//               is an integer < 2^24 and exact in fp32.  Half the tensor work and half the
+//               genotype bytes; up to 4 chunks (15,872 cells).
+enum { MODE_PLANES = 0, MODE_RADIX = 1 };
+constexpr int RADIX_KB_PER_CHUNK = 31;
+constexpr int RADIX_MAX_CHUNKS = 4;
+constexpr uint8_t E5M2_ONE = 0x3C;    // 1.0
+constexpr uint8_t E5M2_4096 = 0x6C;   // 2^12
+
+template <int MODE>
+struct ModeCfg {
+    static constexpr int A_TILES = MODE == MODE_PLANES ? 2 : 1;
+    static constexpr int NUM_STAGES = MODE == MODE_PLANES ? 4 : 6;
+    static constexpr int STAGE_BYTES = (A_TILES + 1) * TILE_BYTES;
+    static constexpr int SMEM_TOTAL = NUM_STAGES * STAGE_BYTES + SMEM_BARRIER_BYTES + SMEM_RED_BYTES + 1024;
+};
+
+// Instruction descriptors (bit layout of the tcgen05 instruction descriptor): D format at
+// [4,6) (1 = f32, 2 = s32), A format [7,10), B format [10,13), both K-major (bits 15, 16 = 0),
 // N >> 3 at [17,23), M >> 4 at [24,29).
-constexpr uint32_t IDESC_I8 = (2u << 4) | (uint32_t(BLOCK_N >> 3) << 17) | (uint32_t(BLOCK_M >> 4) << 24);
+constexpr uint32_t IDESC_I8 = (2u << 4) | (uint32_t(BLOCK_N >> 3) << 17) | (uint32_t(BLOCK_M >> 4) << 24);            // u8 x u8 -> s32
+constexpr uint32_t IDESC_E5M2 = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BLOCK_N >> 3) << 17) | (uint32_t(BLOCK_M >> 4) << 24);   // e5m2 x e5m2 -> f32
 
 enum { PASS_DUMP = 0, PASS_STATS = 1, PASS_COLSUM = 2 };
 
@@ -64,6 +84,7 @@ struct PlaceParams {
     int num_row_blocks, num_col_tiles;
     int run_len, num_runs, sb_width, num_tasks;
     int l2_hints;              // 1: clade tiles evict-last, genotype tiles evict-first
+    int nchunk;                // radix mode: K chunks (accumulators) per tile
     float a1h, a1l, a0h, a0l;  // log2-unit constants, split so that a?h * count is exact
     float a1f, a0f;            // plain fp32 copies, used only to rank columns
     uint2* stats;              // pass 1 out: [num_col_tiles*2][M_pad] {ref counts, sum}
@@ -96,18 +117,62 @@ __device__ __forceinline__ float count_to_float(uint32_t c) {
     return __uint_as_float(c | 0x4B000000u) - 8388608.0f;
 }
 
-template <int PASS>
+// 32 consecutive columns of this thread's row: number of clade cells observed mutated (f1)
+// and observed wild type (f0), as exact integer-valued floats.
+// `taddr` = TMEM base + lane quarter + column offset inside a slot; `use0` = the tile's first
+// slot-use number (slot of accumulator c is (use0 + c) & 3, at column 128 * slot).
+template <int MODE>
+__device__ __forceinline__ void load_counts(uint32_t taddr, uint32_t use0, int nchunk, float (&f1)[32], float (&f0)[32]) {
+    uint32_t raw[32];
+    if (MODE == MODE_PLANES) {
+        ptx::tmem_ld_x32(taddr + (use0 & 3) * BLOCK_N, raw);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f1[i] = count_to_float(raw[i]);
+        ptx::tmem_ld_x32(taddr + ((use0 + 1) & 3) * BLOCK_N, raw);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f0[i] = count_to_float(raw[i]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f1[i] = f0[i] = 0.f;
+#pragma unroll
+        for (int c = 0; c < RADIX_MAX_CHUNKS; ++c) {
+            if (c < nchunk) {
+                ptx::tmem_ld_x32(taddr + ((use0 + c) & 3) * BLOCK_N, raw);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float v = __uint_as_float(raw[i]);           // C1 + 4096 * C0, exact
+                    const float hi = truncf(v * (1.0f / 4096.0f));
+                    f0[i] += hi;
+                    f1[i] += fmaf(-4096.0f, hi, v);
+                }
+            }
+        }
+    }
+}
+
+template <int PASS, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x0,
                  const __grid_constant__ CUtensorMap tm_s, const PlaceParams p) {
+    using Cfg = ModeCfg<MODE>;
+    constexpr int NUM_STAGES = Cfg::NUM_STAGES;
+    constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
+    constexpr int A_TILES = Cfg::A_TILES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NUM_STAGES * STAGE_BYTES);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + NUM_STAGES;
-    uint64_t* tfull_bar = bars + 2 * NUM_STAGES;
-    uint64_t* tempty_bar = bars + 2 * NUM_STAGES + 2;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * NUM_STAGES + 4);
+    // TMEM is a rotating pool of four 128-column accumulator slots.  A tile takes SPT
+    // consecutive slots (2 planes, or one per K chunk); the MMA warp may start a slot as
+    // soon as the epilogue of the tile that used it last has drained it, so the epilogue
+    // overlaps the next tile's MMAs whenever SPT < 4.
+    uint64_t* tfull_bar = bars + 2 * NUM_STAGES;        // [4] tile n -> n & 3
+    uint64_t* sempty_bar = bars + 2 * NUM_STAGES + 4;   // [4] one per slot
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * NUM_STAGES + 8);
     float* red = reinterpret_cast<float*>(smem + NUM_STAGES * STAGE_BYTES + SMEM_BARRIER_BYTES);
 
     const int warp_idx = threadIdx.x >> 5;
@@ -115,15 +180,15 @@ scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constan
 
     if (warp_idx == 0 && ptx::elect_one()) {
         ptx::prefetch_tmap(&tm_x1);
-        ptx::prefetch_tmap(&tm_x0);
+        if (A_TILES == 2) ptx::prefetch_tmap(&tm_x0);
         ptx::prefetch_tmap(&tm_s);
         for (int s = 0; s < NUM_STAGES; ++s) {
             ptx::mbar_init(&full_bar[s], 1);
             ptx::mbar_init(&empty_bar[s], 1);
         }
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < 4; ++a) {
             ptx::mbar_init(&tfull_bar[a], 1);
-            ptx::mbar_init(&tempty_bar[a], NUM_EPI_WARPS);
+            ptx::mbar_init(&sempty_bar[a], NUM_EPI_WARPS);
         }
         ptx::fence_mbar_init();
     }
@@ -154,8 +219,9 @@ scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constan
                         // the clade slab is re-read by this CTA for every row block of the run and shared
                         // by the whole super-block: keep it; genotype rows stream through once per super-block
                         ptx::tma_load_2d_hint(&tm_x1, &full_bar[stage], st, kb * BLOCK_K, r * BLOCK_M, pol_x);
-                        ptx::tma_load_2d_hint(&tm_x0, &full_bar[stage], st + STAGE_A_BYTES, kb * BLOCK_K, r * BLOCK_M, pol_x);
-                        ptx::tma_load_2d_hint(&tm_s, &full_bar[stage], st + 2 * STAGE_A_BYTES, kb * BLOCK_K, j * BLOCK_N, pol_s);
+                        if (A_TILES == 2)
+                            ptx::tma_load_2d_hint(&tm_x0, &full_bar[stage], st + TILE_BYTES, kb * BLOCK_K, r * BLOCK_M, pol_x);
+                        ptx::tma_load_2d_hint(&tm_s, &full_bar[stage], st + A_TILES * TILE_BYTES, kb * BLOCK_K, j * BLOCK_N, pol_s);
                         if (++stage == NUM_STAGES) {
                             stage = 0;
                             phase ^= 1;
@@ -169,30 +235,52 @@ scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constan
         if (ptx::elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
+            const int spt = MODE == MODE_PLANES ? 2 : p.nchunk;   // slots per tile
+            uint32_t tile_n = 0;                                   // tiles issued by this CTA
             for (int t = blockIdx.x; t < p.num_tasks; t += gridDim.x) {
                 int j, r0, r1;
                 decode_task(p, t, j, r0, r1);
-                for (int r = r0; r < r1; ++r) {
-                    ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-                    ptx::tc_fence_after();
-                    const uint32_t d1 = tmem_base + acc * 2 * BLOCK_N;
-                    const uint32_t d0 = d1 + BLOCK_N;
+                for (int r = r0; r < r1; ++r, ++tile_n) {
+                    const uint32_t use0 = tile_n * spt;            // running slot-use counter
+                    if (MODE == MODE_PLANES) {
+                        // both planes accumulate over the whole K loop: claim both slots up front
+                        for (int c = 0; c < 2; ++c) ptx::mbar_wait(&sempty_bar[(use0 + c) & 3], (((use0 + c) >> 2) & 1) ^ 1);
+                        ptx::tc_fence_after();
+                    }
                     for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                        int chunk = 0, kin = kb;
+                        if (MODE == MODE_RADIX) {
+                            chunk = kb / RADIX_KB_PER_CHUNK;
+                            kin = kb - chunk * RADIX_KB_PER_CHUNK;
+                            if (kin == 0) {                        // first K block of a chunk: claim its slot
+                                ptx::mbar_wait(&sempty_bar[(use0 + chunk) & 3], (((use0 + chunk) >> 2) & 1) ^ 1);
+                                ptx::tc_fence_after();
+                            }
+                        }
                         ptx::mbar_wait(&full_bar[stage], phase);
                         ptx::tc_fence_after();
                         const uint32_t st = ptx::smem_u32(smem + stage * STAGE_BYTES);
                         const uint64_t dx1 = ptx::make_kmajor_sw128_desc(st);
-                        const uint64_t dx0 = ptx::make_kmajor_sw128_desc(st + STAGE_A_BYTES);
-                        const uint64_t ds = ptx::make_kmajor_sw128_desc(st + 2 * STAGE_A_BYTES);
+                        const uint64_t ds = ptx::make_kmajor_sw128_desc(st + A_TILES * TILE_BYTES);
+                        if (MODE == MODE_PLANES) {
+                            const uint64_t dx0 = ptx::make_kmajor_sw128_desc(st + TILE_BYTES);
+                            const uint32_t d1 = tmem_base + ((use0 & 3) * BLOCK_N);
+                            const uint32_t d0 = tmem_base + (((use0 + 1) & 3) * BLOCK_N);
 #pragma unroll
-                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                            // advance 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
-                            const uint64_t koff = uint64_t(k * (UMMA_K >> 4));
-                            const uint32_t accum = (kb | k) != 0;
-                            ptx::mma_i8_ss(d1, dx1 + koff, ds + koff, IDESC_I8, accum);
-                            ptx::mma_i8_ss(d0, dx0 + koff, ds + koff, IDESC_I8, accum);
+                            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                                // advance 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
+                                const uint64_t koff = uint64_t(k * (UMMA_K >> 4));
+                                const uint32_t accum = (kb | k) != 0;
+                                ptx::mma_i8_ss(d1, dx1 + koff, ds + koff, IDESC_I8, accum);
+                                ptx::mma_i8_ss(d0, dx0 + koff, ds + koff, IDESC_I8, accum);
+                            }
+                        } else {
+                            const uint32_t d = tmem_base + (((use0 + chunk) & 3) * BLOCK_N);
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                                const uint64_t koff = uint64_t(k * (UMMA_K >> 4));
+                                ptx::mma_f8_ss(d, dx1 + koff, ds + koff, IDESC_E5M2, (kin | k) != 0);
+                            }
                         }
                         ptx::mma_commit(&empty_bar[stage]);
                         if (++stage == NUM_STAGES) {
@@ -200,9 +288,7 @@ scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constan
                             phase ^= 1;
                         }
                     }
-                    ptx::mma_commit(&tfull_bar[acc]);
-                    acc ^= 1;
-                    if (acc == 0) acc_phase ^= 1;
+                    ptx::mma_commit(&tfull_bar[tile_n & 3]);
                 }
             }
         }
@@ -212,8 +298,8 @@ scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constan
         const int q = warp_idx & 3;   // TMEM lane quarter this warp may touch
         const int hh = ew >> 2;       // column half of the tile
         const uint32_t lane_base = uint32_t(q * 32) << 16;
-        int acc = 0;
-        uint32_t acc_phase = 0;
+        const int spt = MODE == MODE_PLANES ? 2 : p.nchunk;
+        uint32_t tile_n = 0;
         for (int t = blockIdx.x; t < p.num_tasks; t += gridDim.x) {
             int j, r0, r1;
             decode_task(p, t, j, r0, r1);
@@ -224,53 +310,46 @@ scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constan
 #pragma unroll
                 for (int i = 0; i < 64; ++i) colacc[i] = 0.f;
             }
-            for (int r = r0; r < r1; ++r) {
-                ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+            for (int r = r0; r < r1; ++r, ++tile_n) {
+                ptx::mbar_wait(&tfull_bar[tile_n & 3], (tile_n >> 2) & 1);
                 ptx::tc_fence_after();
                 const int row = r * BLOCK_M + q * 32 + lane;
-                const uint32_t taddr = tmem_base + lane_base + acc * 2 * BLOCK_N + hh * 64;
-                uint32_t c1[32], c0[32];
+                const uint32_t use0 = tile_n * spt;
+                const uint32_t taddr = tmem_base + lane_base + hh * 64;
+                float f1[32], f0[32];
                 if (PASS == PASS_DUMP) {
 #pragma unroll
                     for (int ch = 0; ch < 2; ++ch) {
-                        ptx::tmem_ld_x32(taddr + ch * 32, c1);
-                        ptx::tmem_ld_x32(taddr + BLOCK_N + ch * 32, c0);
-                        ptx::tmem_ld_wait();
+                        load_counts<MODE>(taddr + ch * 32, use0, p.nchunk, f1, f0);
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             const size_t o = (size_t(row) * p.N_pad + col0 + ch * 32 + i) * 2;
-                            p.dump[o] = int(c1[i]);
-                            p.dump[o + 1] = int(c0[i]);
+                            p.dump[o] = int(f1[i]);
+                            p.dump[o + 1] = int(f0[i]);
                         }
                     }
                 } else if (PASS == PASS_STATS) {
                     float best = -INFINITY, b1 = 0.f, b0 = 0.f;
 #pragma unroll
                     for (int ch = 0; ch < 2; ++ch) {
-                        ptx::tmem_ld_x32(taddr + ch * 32, c1);
-                        ptx::tmem_ld_x32(taddr + BLOCK_N + ch * 32, c0);
-                        ptx::tmem_ld_wait();
+                        load_counts<MODE>(taddr + ch * 32, use0, p.nchunk, f1, f0);
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            const float f1 = count_to_float(c1[i]);
-                            const float f0 = count_to_float(c0[i]);
-                            const float v = fmaf(p.a1f, f1, p.a0f * f0);
+                            const float v = fmaf(p.a1f, f1[i], p.a0f * f0[i]);
                             const bool take = (ch * 32 + i < n_valid) && (v > best);
                             best = take ? v : best;
-                            b1 = take ? f1 : b1;
-                            b0 = take ? f0 : b0;
+                            b1 = take ? f1[i] : b1;
+                            b0 = take ? f0[i] : b0;
                         }
                     }
                     float sum = 0.f;
 #pragma unroll
                     for (int ch = 0; ch < 2; ++ch) {
-                        ptx::tmem_ld_x32(taddr + ch * 32, c1);
-                        ptx::tmem_ld_x32(taddr + BLOCK_N + ch * 32, c0);
-                        ptx::tmem_ld_wait();
+                        load_counts<MODE>(taddr + ch * 32, use0, p.nchunk, f1, f0);
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            const float e1 = count_to_float(c1[i]) - b1;
-                            const float e0 = count_to_float(c0[i]) - b0;
+                            const float e1 = f1[i] - b1;
+                            const float e0 = f0[i] - b0;
                             const float s = fmaf(p.a1h, e1, p.a0h * e0);   // exact operands, one rounding
                             const float lo = fmaf(p.a1l, e1, p.a0l * e0);
                             const float e = exp2f(s + lo);
@@ -287,13 +366,11 @@ scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constan
                     const bool rowvalid = row < p.M;
 #pragma unroll
                     for (int ch = 0; ch < 2; ++ch) {
-                        ptx::tmem_ld_x32(taddr + ch * 32, c1);
-                        ptx::tmem_ld_x32(taddr + BLOCK_N + ch * 32, c0);
-                        ptx::tmem_ld_wait();
+                        load_counts<MODE>(taddr + ch * 32, use0, p.nchunk, f1, f0);
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            const float e1 = count_to_float(c1[i]) - r1f;
-                            const float e0 = count_to_float(c0[i]) - r0f;
+                            const float e1 = f1[i] - r1f;
+                            const float e0 = f0[i] - r0f;
                             const float s = fmaf(p.a1h, e1, p.a0h * e0);
                             const float tl = fmaf(p.a0l, e0, -L);
                             const float lo = fmaf(p.a1l, e1, tl);
@@ -302,12 +379,11 @@ scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constan
                         }
                     }
                 }
-                // accumulator stage drained: hand it back to the MMA warp
+                // this tile's slots are drained: hand them back to the MMA warp
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
+                if (lane == 0)
+                    for (int c = 0; c < spt; ++c) ptx::mbar_arrive(&sempty_bar[(use0 + c) & 3]);
             }
             if (PASS == PASS_COLSUM) {
                 // rows -> one number per column: lanes, then the four lane quarters
@@ -345,7 +421,7 @@ scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constan
 // 2-bit genotype codes (0 wild type, 1 het, 2 hom, 3 missing; 4 cells per byte,
 // cell c in bits [2*(c%4), +2)) -> two 0/1 byte planes, K-major, zero padded.
 __global__ void scs_expand_genotypes_kernel(const uint8_t* __restrict__ gt, int64_t gt_pitch, int M, int n_cells,
-                                            uint8_t* __restrict__ x1, uint8_t* __restrict__ x0, int K_pad) {
+                                            uint8_t* __restrict__ x1, uint8_t* __restrict__ x0, int K_pad, int radix) {
     const int kq = blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 cells
     const int row = blockIdx.y;
     if (kq * 4 >= K_pad || row >= M) return;
@@ -356,18 +432,23 @@ __global__ void scs_expand_genotypes_kernel(const uint8_t* __restrict__ gt, int6
         for (int i = 0; i < 4; ++i) {
             const uint32_t code = (b >> (2 * i)) & 3u;
             const bool in = kq * 4 + i < n_cells;
-            o1 |= uint32_t(in && (code == 1u || code == 2u)) << (8 * i);
-            o0 |= uint32_t(in && code == 0u) << (8 * i);
+            const bool mut = in && (code == 1u || code == 2u), wt = in && code == 0u;
+            if (radix) {
+                o1 |= uint32_t(mut ? E5M2_ONE : (wt ? E5M2_4096 : 0)) << (8 * i);   // one e5m2 plane: 1 / 4096 / 0
+            } else {
+                o1 |= uint32_t(mut) << (8 * i);
+                o0 |= uint32_t(wt) << (8 * i);
+            }
         }
     }
     *reinterpret_cast<uint32_t*>(x1 + size_t(row) * K_pad + kq * 4) = o1;
-    *reinterpret_cast<uint32_t*>(x0 + size_t(row) * K_pad + kq * 4) = o0;
+    if (!radix) *reinterpret_cast<uint32_t*>(x0 + size_t(row) * K_pad + kq * 4) = o0;
 }
 
 // clade bit mask [N][words] (bit c%32 of word c/32 set when cell c is below the
 // node) -> 0/1 byte matrix, K-major, zero padded.
 __global__ void scs_expand_clades_kernel(const uint32_t* __restrict__ bits, int64_t pitch_words, int N, int n_cells,
-                                         uint8_t* __restrict__ s, int K_pad) {
+                                         uint8_t* __restrict__ s, int K_pad, uint32_t one) {
     const int kq = blockIdx.x * blockDim.x + threadIdx.x;
     const int row = blockIdx.y;
     if (kq * 4 >= K_pad || row >= N) return;
@@ -377,7 +458,7 @@ __global__ void scs_expand_clades_kernel(const uint32_t* __restrict__ bits, int6
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const bool in = kq * 4 + i < n_cells;
-            o |= uint32_t(in && ((w >> i) & 1u)) << (8 * i);
+            o |= ((in && ((w >> i) & 1u)) ? one : 0u) << (8 * i);
         }
     }
     *reinterpret_cast<uint32_t*>(s + size_t(row) * K_pad + kq * 4) = o;
@@ -459,6 +540,21 @@ static int make_u8_tmap(CUtensorMap* tm, void* base, uint64_t rows, uint64_t k_p
     return SCS_OK;
 }
 
+template <int PASS>
+static void launch_place(int mode, int grid, cudaStream_t st, const CUtensorMap& a1, const CUtensorMap& a0, const CUtensorMap& b,
+                         const PlaceParams& p) {
+    if (mode == MODE_RADIX)
+        scs_place_kernel<PASS, MODE_RADIX><<<grid, NUM_THREADS, ModeCfg<MODE_RADIX>::SMEM_TOTAL, st>>>(a1, a0, b, p);
+    else
+        scs_place_kernel<PASS, MODE_PLANES><<<grid, NUM_THREADS, ModeCfg<MODE_PLANES>::SMEM_TOTAL, st>>>(a1, a0, b, p);
+}
+
+template <int PASS>
+static void set_place_smem() {
+    cudaFuncSetAttribute(scs_place_kernel<PASS, MODE_PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModeCfg<MODE_PLANES>::SMEM_TOTAL);
+    cudaFuncSetAttribute(scs_place_kernel<PASS, MODE_RADIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModeCfg<MODE_RADIX>::SMEM_TOTAL);
+}
+
 struct Placement {
     scs_ctx* ctx = nullptr;
     int64_t n_snv = 0;
@@ -480,9 +576,14 @@ struct Placement {
     uint32_t* stage_mask = nullptr;
     size_t stage_mask_bytes = 0;
     long long launches = 0;
+    int mode = MODE_PLANES;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // brackets of the four kernels of run()
     bool timed = false;
 };
+
+// Radix packing is the default wherever it applies (<= 15,872 cells); its integer exactness is
+// asserted bit-for-bit by tests/test_gpu_parity.py::test_counts_bit_exact_* in both modes.
+static int g_default_mode = MODE_RADIX;
 
 static int round_up(int64_t v, int m) { return int((v + m - 1) / m * m); }
 
@@ -523,6 +624,17 @@ int scs_placement_create(scs_ctx* ctx, int64_t n_snv, int32_t n_cells, int32_t n
     p.M_pad = pl->M_pad;
     p.N_pad = pl->N_pad;
     p.num_k_blocks = pl->K_pad / BLOCK_K;
+    // Operand mode: radix packing halves the tensor work but needs K <= 4 chunks of 3968 cells.
+    {
+        const int nchunk = (p.num_k_blocks + RADIX_KB_PER_CHUNK - 1) / RADIX_KB_PER_CHUNK;
+        int mode = nchunk <= RADIX_MAX_CHUNKS ? g_default_mode : MODE_PLANES;
+        if (const char* e = getenv("SCS_PLACE_MODE")) {
+            if (!strcmp(e, "radix") && nchunk <= RADIX_MAX_CHUNKS) mode = MODE_RADIX;
+            if (!strcmp(e, "planes")) mode = MODE_PLANES;
+        }
+        pl->mode = mode;
+        p.nchunk = mode == MODE_RADIX ? nchunk : 1;
+    }
     p.num_row_blocks = pl->M_pad / BLOCK_M;
     p.num_col_tiles = pl->N_pad / BLOCK_N;
     // Super-block: the w column tiles whose clade slab the concurrently running CTAs share.
@@ -568,9 +680,9 @@ int scs_placement_create(scs_ctx* ctx, int64_t n_snv, int32_t n_cells, int32_t n
         if ((rc = make_u8_tmap(&pl->tm_x1, pl->x1, pl->M_pad, pl->K_pad, BLOCK_M)) != SCS_OK) break;
         if ((rc = make_u8_tmap(&pl->tm_x0, pl->x0, pl->M_pad, pl->K_pad, BLOCK_M)) != SCS_OK) break;
         if ((rc = make_u8_tmap(&pl->tm_s, pl->s, pl->N_pad, pl->K_pad, BLOCK_N)) != SCS_OK) break;
-        cudaFuncSetAttribute(scs_place_kernel<PASS_DUMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
-        cudaFuncSetAttribute(scs_place_kernel<PASS_STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
-        cudaFuncSetAttribute(scs_place_kernel<PASS_COLSUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+        set_place_smem<PASS_DUMP>();
+        set_place_smem<PASS_STATS>();
+        set_place_smem<PASS_COLSUM>();
         for (int i = 0; i < 5; ++i) cudaEventCreate(&pl->ev[i]);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) {
@@ -618,11 +730,13 @@ int scs_placement_set_genotypes(scs_placement* h, const uint8_t* d_gt, int64_t p
             const int rows = int(std::min<int64_t>(65535, pl->n_snv - r0));
             grid.y = rows;
             scs_expand_genotypes_kernel<<<grid, block, 0, st>>>(d_gt + r0 * pitch_bytes, pitch_bytes, rows, pl->n_cells,
-                                                                 pl->x1 + size_t(r0) * pl->K_pad, pl->x0 + size_t(r0) * pl->K_pad, pl->K_pad);
+                                                                 pl->x1 + size_t(r0) * pl->K_pad, pl->x0 + size_t(r0) * pl->K_pad, pl->K_pad,
+                                                                 pl->mode == MODE_RADIX);
             pl->launches++;
         }
     } else {
-        scs_expand_genotypes_kernel<<<grid, block, 0, st>>>(d_gt, pitch_bytes, int(pl->n_snv), pl->n_cells, pl->x1, pl->x0, pl->K_pad);
+        scs_expand_genotypes_kernel<<<grid, block, 0, st>>>(d_gt, pitch_bytes, int(pl->n_snv), pl->n_cells, pl->x1, pl->x0, pl->K_pad,
+                                                             pl->mode == MODE_RADIX);
         pl->launches++;
     }
     if (d_row_keep) {
@@ -645,7 +759,7 @@ int scs_placement_set_clades(scs_placement* h, const uint32_t* d_bits, int64_t p
         const int rows = std::min(65535, pl->n_rows - r0);
         grid.y = rows;
         scs_expand_clades_kernel<<<grid, block, 0, st>>>(d_bits + size_t(r0) * pitch_words, pitch_words, rows, pl->n_cells,
-                                                          pl->s + size_t(r0) * pl->K_pad, pl->K_pad);
+                                                          pl->s + size_t(r0) * pl->K_pad, pl->K_pad, pl->mode == MODE_RADIX ? uint32_t(E5M2_ONE) : 1u);
         pl->launches++;
     }
     SCS_CUDA(cudaGetLastError());
@@ -716,12 +830,12 @@ int scs_placement_run(scs_placement* h, double FP, double FN, double* d_soft_wei
     fill_constants(pl, FP, FN, &a1, &a0);
     const PlaceParams& p = pl->prm;
     cudaEventRecord(pl->ev[0], st);
-    scs_place_kernel<PASS_STATS><<<pl->grid, NUM_THREADS, SMEM_TOTAL, st>>>(pl->tm_x1, pl->tm_x0, pl->tm_s, p);
+    launch_place<PASS_STATS>(pl->mode, pl->grid, st, pl->tm_x1, pl->tm_x0, pl->tm_s, p);
     cudaEventRecord(pl->ev[1], st);
     scs_merge_stats_kernel<<<(p.M_pad + 255) / 256, 256, 0, st>>>(pl->stats, p.num_col_tiles * 2, p.M, p.M_pad,
                                                                   pl->have_row_keep ? pl->row_keep : nullptr, a1, a0, pl->rowref);
     cudaEventRecord(pl->ev[2], st);
-    scs_place_kernel<PASS_COLSUM><<<pl->grid, NUM_THREADS, SMEM_TOTAL, st>>>(pl->tm_x1, pl->tm_x0, pl->tm_s, p);
+    launch_place<PASS_COLSUM>(pl->mode, pl->grid, st, pl->tm_x1, pl->tm_x0, pl->tm_s, p);
     cudaEventRecord(pl->ev[3], st);
     double* y = d_soft_weights ? d_soft_weights : pl->y;
     scs_reduce_colpart_kernel<<<(p.N + 255) / 256, 256, 0, st>>>(pl->colpart, p.num_runs, p.N, p.N_pad, y);
@@ -754,7 +868,7 @@ int scs_placement_debug_counts(scs_placement* h, int32_t* counts_host, void* str
     if (!pl->dump && cudaMalloc(&pl->dump, n * sizeof(int)) != cudaSuccess) return set_error(SCS_ERR_OOM, "debug dump allocation failed");
     PlaceParams p = pl->prm;
     p.dump = pl->dump;
-    scs_place_kernel<PASS_DUMP><<<pl->grid, NUM_THREADS, SMEM_TOTAL, st>>>(pl->tm_x1, pl->tm_x0, pl->tm_s, p);
+    launch_place<PASS_DUMP>(pl->mode, pl->grid, st, pl->tm_x1, pl->tm_x0, pl->tm_s, p);
     pl->launches++;
     SCS_CUDA(cudaGetLastError());
     std::vector<int> tmp(n);
@@ -768,8 +882,9 @@ int scs_placement_debug_counts(scs_placement* h, int32_t* counts_host, void* str
 int scs_placement_info(scs_placement* h, int64_t* info, int32_t n) {
     Placement* pl = reinterpret_cast<Placement*>(h);
     if (!pl || !info) return set_error(SCS_ERR_ARG, "null argument");
-    const int64_t v[10] = {pl->M_pad, pl->N_pad, pl->K_pad, pl->prm.num_tasks, pl->prm.run_len, pl->prm.sb_width, pl->grid, pl->launches, pl->prm.num_runs, SMEM_TOTAL};
-    for (int i = 0; i < n && i < 10; ++i) info[i] = v[i];
+    const int64_t v[12] = {pl->M_pad, pl->N_pad, pl->K_pad, pl->prm.num_tasks, pl->prm.run_len, pl->prm.sb_width, pl->grid, pl->launches, pl->prm.num_runs,
+                           pl->mode == MODE_RADIX ? ModeCfg<MODE_RADIX>::SMEM_TOTAL : ModeCfg<MODE_PLANES>::SMEM_TOTAL, pl->mode, pl->prm.nchunk};
+    for (int i = 0; i < n && i < 12; ++i) info[i] = v[i];
     return SCS_OK;
 }
 

@@ -124,9 +124,10 @@ class Placement:
             pass
 
     def info(self):
-        v = (C.c_int64 * 10)()
-        check(lib().scs_placement_info(self._h, v, 10))
-        keys = ("M_pad", "N_pad", "K_pad", "tasks", "run_len", "superblock_width", "grid", "launches", "runs", "smem_bytes")
+        v = (C.c_int64 * 12)()
+        check(lib().scs_placement_info(self._h, v, 12))
+        keys = ("M_pad", "N_pad", "K_pad", "tasks", "run_len", "superblock_width", "grid", "launches", "runs", "smem_bytes",
+                "mode", "k_chunks")
         return dict(zip(keys, (int(x) for x in v)))
 
     # host buffers (numpy)

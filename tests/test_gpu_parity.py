@@ -55,14 +55,17 @@ def assert_soft_close(got, want):
 
 
 # ------------------------------------------------------------ placement GEMM
+@pytest.mark.parametrize("mode", ["radix", "planes"])
 @pytest.mark.parametrize("n_snv,n_cells", [(1, 2), (5, 1), (127, 3), (128, 64), (129, 65), (300, 50), (1000, 200),
                                             (2000, 300), (700, 513)])
-def test_counts_bit_exact_and_soft_weights(ctx, n_snv, n_cells):
+def test_counts_bit_exact_and_soft_weights(ctx, monkeypatch, mode, n_snv, n_cells):
+    monkeypatch.setenv("SCS_PLACE_MODE", mode)      # one e5m2 radix plane (kind::f8f6f4) / two u8 planes (kind::i8)
     codes, S = make_problem(n_snv, n_cells, seed=n_snv * 7 + n_cells)
     FP, FN = 0.01, 0.1
     packed, pitch = engine.pack_genotypes(codes)
     bits, words = engine.pack_clades(S)
     pl = engine.Placement(ctx, n_snv, n_cells, S.shape[0])
+    assert pl.info()["mode"] == (1 if mode == "radix" else 0)
     pl.set_genotypes_host(packed, pitch)
     pl.set_clades_host(bits, words)
     cnt = pl.debug_counts()
@@ -75,6 +78,44 @@ def test_counts_bit_exact_and_soft_weights(ctx, n_snv, n_cells):
     # one-shot host entry point gives the same numbers
     got2 = engine.map_mutations(ctx, packed, pitch, bits, words, n_cells, FP, FN)
     assert np.array_equal(got, got2)
+    pl.close()
+
+
+@pytest.mark.parametrize("mode", ["radix", "planes"])
+@pytest.mark.parametrize("n_snv,n_cells", [(300, 3968), (260, 4100), (140, 8100), (130, 10000)])
+def test_counts_bit_exact_dense_many_cells(ctx, monkeypatch, mode, n_snv, n_cells):
+    """Worst case for the radix packing: dense random clade rows and genotypes put both
+    counts of every K chunk (3968 cells) near their maximum; 1, 2 and 3 chunks."""
+    monkeypatch.setenv("SCS_PLACE_MODE", mode)
+    rng = np.random.default_rng(n_cells)
+    n_rows = 256 if n_cells > 5000 else 384
+    S = (rng.random((n_rows, n_cells)) < 0.9).astype(np.uint8)
+    S[-1] = 0
+    S[0] = 1
+    codes = rng.choice([0, 1, 2, 3], size=(n_snv, n_cells), p=[0.5, 0.3, 0.15, 0.05]).astype(np.uint8)
+    codes[0] = 0
+    codes[1] = 1
+    packed, pitch = engine.pack_genotypes(codes)
+    bits, words = engine.pack_clades(S)
+    pl = engine.Placement(ctx, n_snv, n_cells, n_rows)
+    pl.set_genotypes_host(packed, pitch)
+    pl.set_clades_host(bits, words)
+    cnt = pl.debug_counts()
+    x1 = ((codes == 1) | (codes == 2)).astype(np.float32)
+    x0 = (codes == 0).astype(np.float32)
+    C1 = (x1 @ S.T.astype(np.float32)).astype(np.int64)            # fp32 BLAS is exact below 2^24
+    C0 = (x0 @ S.T.astype(np.float32)).astype(np.int64)
+    assert C0.max() >= 0.85 * min(n_cells, 3968) * 0.5
+    assert np.array_equal(cnt[:, :, 0], C1) and np.array_equal(cnt[:, :, 1], C0)
+    muts = np.where(codes == 3, np.nan, codes.astype(float))
+    assert_soft_close(pl.run_host(0.01, 0.1), O.map_mutations_gt(muts, S.astype(float), 0.01, 0.1))
+    pl.close()
+
+
+def test_radix_mode_falls_back_beyond_four_chunks(ctx, monkeypatch):
+    monkeypatch.setenv("SCS_PLACE_MODE", "radix")
+    pl = engine.Placement(ctx, 128, 16000, 64)         # 125 K blocks = 5 chunks: exact u8 planes instead
+    assert pl.info()["mode"] == 0
     pl.close()
 
 

@@ -6,10 +6,10 @@ sys.path.insert(0, ".")
 from scsommerclock_b200 import engine, synth
 
 def oracle(codes, S, FP, FN):
-    x1 = ((codes == 1) | (codes == 2)).astype(np.int64)
-    x0 = (codes == 0).astype(np.int64)
-    C1 = x1 @ S.T.astype(np.int64)
-    C0 = x0 @ S.T.astype(np.int64)
+    x1 = ((codes == 1) | (codes == 2)).astype(np.float32)
+    x0 = (codes == 0).astype(np.float32)
+    C1 = (x1 @ S.T.astype(np.float32)).astype(np.int64)      # exact: counts < 2^24
+    C0 = (x0 @ S.T.astype(np.float32)).astype(np.int64)
     a1 = np.log1p(-FN) - np.log(FP)
     a0 = np.log(FN) - np.log1p(-FP)
     L = a1 * C1 + a0 * C0
@@ -25,12 +25,18 @@ def main():
     tree = synth.coalescent_tree(n_cells, rng)
     S = tree.clade_matrix()
     FN, FP, MS = 0.1, 0.01, 0.15
+    stress = "--stress" in sys.argv
+    if stress:       # dense random clade rows and genotypes: large counts in both planes
+        S = (rng.random(S.shape) < 0.9).astype(np.uint8); S[-1] = 0
     ctx = engine.Context(0)
     print("ctx sm", ctx.sm_count, flush=True)
     bits, words = engine.pack_clades(S)
     if not perf:
         br = synth.throw_mutations(tree, n_snv, rng)
         codes = synth.observe(tree, br, FN, FP, MS, rng)
+        if stress:
+            codes = rng.choice([0, 1, 2, 3], size=codes.shape, p=[0.5, 0.3, 0.15, 0.05]).astype(np.uint8)
+            codes[0] = 0; codes[1] = 1
         packed, pitch = engine.pack_genotypes(codes)
         pl = engine.Placement(ctx, n_snv, n_cells, S.shape[0])
         print(pl.info(), flush=True)
