@@ -327,11 +327,13 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES, "peak_source": pk_kind + " cuBLAS bf16, sustained (kernel timed inside a long step)",
-                         "kernel": "scs_place_kernel (tcgen05 kind::i8), avg of pass 1 and pass 2 launches",
+                         "kernel": "scs_place_kernel (%s), avg of pass 1 and pass 2 launches" % (
+                             "tcgen05 kind::f8f6f4, one radix-packed e5m2 plane" if plan.info()["mode"] == 1 else "tcgen05 kind::i8, two u8 planes"),
                          "algorithmic_flop_per_launch": flop, "ms_per_launch": t_gemm,
                          "pass1_ms": float(g[:, 0].mean()), "merge_ms": float(g[:, 1].mean()), "pass2_ms": float(g[:, 2].mean()),
                          "reduce_ms": float(g[:, 3].mean()),
-                         "executed_tensor_TOPs": 2 * achieved, "note": "each launch executes two exact 0/1 integer GEMMs (mutated / wild-type planes) per algorithmic contraction"},
+                         "executed_tensor_TOPs": achieved * (1 if plan.info()["mode"] == 1 else 2),
+                         "note": "radix mode: one exact FP8 GEMM per contraction (counts packed as C1 + 4096*C0); planes mode: two exact u8 GEMMs"},
             "pt_tests": {"per_step": len(W_MAXS), "LR": [float(v) for v in out[:, 0]], "p_value": [float(v) for v in out[:, 3]],
                          "newton_iterations": [int(v) for v in out[:, 6]], "status": [int(v) for v in out[:, 7]]},
             "clocks": sampler.summary() if sampler else None,

@@ -354,22 +354,21 @@ __global__ void scs_count_status_kernel(const uint8_t* __restrict__ status, int6
 // get_gt_tree's reductions (run_PT_test.py:350-358) on the packed matrix:
 // row_keep[i] = any active cell of SNV i carries code 1 or 2 (sum(axis=1) > 0 with
 // the outgroup column dropped); missing[c] = number of kept SNVs where cell c is NaN.
-__global__ void scs_row_keep_kernel(const uint8_t* __restrict__ gt, int64_t pitch, int64_t n_rows, int n_cols,
-                                    const uint8_t* __restrict__ col_active, int filter_rows, uint8_t* __restrict__ row_keep) {
+__global__ void scs_row_keep_kernel(const uint8_t* __restrict__ gt, int64_t pitch, int64_t n_rows, int n_words,
+                                    const uint32_t* __restrict__ active_mask, int filter_rows, uint8_t* __restrict__ row_keep) {
+    // one warp per row, 16 cells (one 32-bit word of codes) per lane and step.  A cell holds
+    // 1 or 2 exactly when its two code bits differ; active_mask has bit 2k of word j set when
+    // cell 16j+k takes part in the filter.
     const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= n_rows) return;
-    int any = 0;
-    const int nb = (n_cols + 3) / 4;
-    for (int b = lane; b < nb; b += 32) {
-        const uint32_t v = gt[row * pitch + b];
-        for (int k = 0; k < 4; ++k) {
-            const int c = b * 4 + k;
-            const uint32_t code = (v >> (2 * k)) & 3u;
-            if (c < n_cols && col_active[c] && (code == 1u || code == 2u)) any = 1;
-        }
+    uint32_t any = 0;
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(gt + row * pitch);
+    for (int j = lane; j < n_words; j += 32) {
+        const uint32_t v = r[j];
+        any |= ((v ^ (v >> 1)) & 0x55555555u) & active_mask[j];
     }
-    any = __any_sync(0xffffffffu, any);
+    any = __any_sync(0xffffffffu, any != 0);
     if (lane == 0) row_keep[row] = filter_rows ? uint8_t(any) : uint8_t(1);
 }
 
@@ -570,20 +569,26 @@ int scs_gt_reduce(scs_ctx* ctx, const uint8_t* d_gt, int64_t pitch_bytes, int64_
                   int32_t filter_rows, uint8_t* d_row_keep, int64_t* n_kept, double* missing_frac) {
     if (!ctx || !d_gt || !col_active || !d_row_keep || !n_kept || !missing_frac) return set_error(SCS_ERR_ARG, "null argument");
     SCS_CUDA(cudaSetDevice(ctx->device));
-    uint8_t* d_act = nullptr;
+    if ((pitch_bytes & 3) || pitch_bytes * 4 < n_cells) return set_error(SCS_ERR_ARG, "packed genotype pitch %lld must be a multiple of 4 and cover %d cells", (long long)pitch_bytes, n_cells);
+    uint32_t* d_act = nullptr;
     unsigned int* d_miss = nullptr;
     long long* d_flag = nullptr;
     int rc = SCS_OK;
     std::vector<unsigned int> miss(n_cells);
     do {
-        if (cudaMalloc(&d_act, n_cells) != cudaSuccess || cudaMalloc(&d_miss, size_t(n_cells) * 4) != cudaSuccess) {
+        if (cudaMalloc(&d_act, size_t(n_cells / 16 + 1) * 4) != cudaSuccess || cudaMalloc(&d_miss, size_t(n_cells) * 4) != cudaSuccess) {
             rc = set_error(SCS_ERR_OOM, "device allocation failed");
             break;
         }
-        cudaMemcpy(d_act, col_active, n_cells, cudaMemcpyHostToDevice);
+        // active cells as a mask over the low bit of every 2-bit code
+        const int n_words = (n_cells + 15) / 16;
+        std::vector<uint32_t> amask(n_words, 0u);
+        for (int c = 0; c < n_cells; ++c)
+            if (col_active[c]) amask[c >> 4] |= 1u << (2 * (c & 15));
+        cudaMemcpy(d_act, amask.data(), size_t(n_words) * 4, cudaMemcpyHostToDevice);
         cudaMemset(d_miss, 0, size_t(n_cells) * 4);
         if (n_snv > 0) {
-            scs_row_keep_kernel<<<unsigned((n_snv * 32 + 127) / 128), 128>>>(d_gt, pitch_bytes, n_snv, n_cells, d_act, filter_rows, d_row_keep);
+            scs_row_keep_kernel<<<unsigned((n_snv * 32 + 127) / 128), 128>>>(d_gt, pitch_bytes, n_snv, n_words, d_act, filter_rows, d_row_keep);
             const int nb = (n_cells + 3) / 4;
             dim3 grid((nb + 127) / 128, unsigned(std::min<int64_t>(1024, std::max<int64_t>(1, n_snv / 256))));
             scs_missing_count_kernel<<<grid, 128>>>(d_gt, pitch_bytes, n_snv, n_cells, d_row_keep, d_miss);

@@ -25,7 +25,8 @@
 
 namespace scs {
 
-constexpr int LRT_THREADS = 128;
+constexpr int LRT_MAX_THREADS = 512;   // CTA size: 128 for small trees, up to 512 for 10k-cell trees
+#define LRT_THREADS (int(blockDim.x))
 constexpr double LRT_LMIN = 1e-6;           // LAMBDA_MIN, run_PT_test.py:21
 constexpr double LRT_MU = 0.1 * 1.024e-7;   // 0.1 * 0.2^10, see above
 constexpr int LRT_MAX_ITER = 200;
@@ -54,7 +55,7 @@ __device__ __forceinline__ double block_reduce(double v, double* sh, bool is_min
     if (lane == 0) sh[warp] = v;
     __syncthreads();
     double out = sh[0];
-    for (int i = 1; i < LRT_THREADS / 32; ++i) out = is_min ? fmin(out, sh[i]) : out + sh[i];
+    for (int i = 1; i < (LRT_THREADS >> 5); ++i) out = is_min ? fmin(out, sh[i]) : out + sh[i];
     return out;
 }
 
@@ -92,11 +93,11 @@ __device__ double gamma_q(double a, double x) {
 }
 
 // out[p*8 ..] = {LR, dof, on_bound, p_value, ll_H0, ll_H1, newton iterations, status}
-__global__ void __launch_bounds__(LRT_THREADS)
+__global__ void __launch_bounds__(LRT_MAX_THREADS)
 scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ Ysrc, const int* __restrict__ gather,
                double* __restrict__ Yall, const double* __restrict__ wall, const int* __restrict__ child_all, LrtWork ws,
                double* __restrict__ out, double* __restrict__ x_out) {
-    __shared__ double sh[LRT_THREADS / 32];
+    __shared__ double sh[LRT_MAX_THREADS / 32];
     __shared__ double s_bcast[4];
     __shared__ int s_nlev;
     const LrtProblem pb = probs[blockIdx.x];
@@ -384,6 +385,7 @@ struct LrtPlanImpl {
     size_t src_len = 0;
     LrtWork ws;
     long long launches = 0;
+    int threads = 128;
 };
 
 int scs_lrt_plan_create(scs_ctx* ctx, int32_t n_prob, const int64_t* br_off, const int32_t* child_int, scs_lrt_plan** out) {
@@ -393,7 +395,7 @@ int scs_lrt_plan_create(scs_ctx* ctx, int32_t n_prob, const int64_t* br_off, con
     const int64_t total_br = br_off[n_prob];
     if (total_br > (int64_t(1) << 30)) return set_error(SCS_ERR_ARG, "batch too large: split it");
     std::vector<LrtProblem> probs(n_prob);
-    int64_t node_off = 0;
+    int64_t node_off = 0, max_nb = 0;
     for (int p = 0; p < n_prob; ++p) {
         const int64_t nb = br_off[p + 1] - br_off[p];
         if (nb < 2 || (nb & 1)) return set_error(SCS_ERR_ARG, "problem %d has %lld branches; a binary tree has an even number >= 2", p, (long long)nb);
@@ -401,6 +403,7 @@ int scs_lrt_plan_create(scs_ctx* ctx, int32_t n_prob, const int64_t* br_off, con
             const int c = child_int[br_off[p] + k];
             if (c >= int(k / 2) || c < -1) return set_error(SCS_ERR_ARG, "problem %d branch %lld: child node %d is not below its parent %lld in post-order", p, (long long)k, c, (long long)(k / 2));
         }
+        max_nb = std::max<int64_t>(max_nb, nb);
         probs[p].br_off = int(br_off[p]);
         probs[p].n_br = int(nb);
         probs[p].node_off = int(node_off);
@@ -411,6 +414,7 @@ int scs_lrt_plan_create(scs_ctx* ctx, int32_t n_prob, const int64_t* br_off, con
     pl->n_prob = n_prob;
     pl->nbr = size_t(total_br);
     pl->nnode = size_t(node_off);
+    pl->threads = max_nb >= 8192 ? 512 : (max_nb >= 2048 ? 256 : 128);
     const size_t nbr = pl->nbr, nnode = pl->nnode;
     const size_t dbl = 8 * nbr /*Ysrc Y w l g d dl x*/ + 7 * nnode + size_t(n_prob) * 8;
     const size_t ints = 2 * nbr /*child gather*/ + 4 * nnode;
@@ -491,7 +495,7 @@ int scs_lrt_plan_run(scs_lrt_plan* h, const double* d_Y, double* d_out, double* 
     if (!pl || !d_Y) return set_error(SCS_ERR_ARG, "null argument");
     if (!pl->have_w) return set_error(SCS_ERR_ARG, "scs_lrt_plan_set_weights has not been called");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    scs_lrt_kernel<<<pl->n_prob, LRT_THREADS, 0, st>>>(pl->d_probs, d_Y, pl->have_gather ? pl->d_gather : nullptr, pl->dY, pl->dw,
+    scs_lrt_kernel<<<pl->n_prob, pl->threads, 0, st>>>(pl->d_probs, d_Y, pl->have_gather ? pl->d_gather : nullptr, pl->dY, pl->dw,
                                                         pl->d_child, pl->ws, d_out ? d_out : pl->d_out, d_x ? d_x : pl->d_x);
     pl->launches++;
     SCS_CUDA(cudaGetLastError());

@@ -134,27 +134,42 @@ __device__ __forceinline__ void load_counts(uint32_t taddr, uint32_t use0, int n
 #pragma unroll
         for (int i = 0; i < 32; ++i) f0[i] = count_to_float(raw[i]);
     } else {
+        // first chunk initialises, further chunks (cells beyond 3968) accumulate
+        ptx::tmem_ld_x32(taddr + (use0 & 3) * BLOCK_N, raw);
+        ptx::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f1[i] = f0[i] = 0.f;
+        for (int i = 0; i < 32; ++i) {
+            const float v = __uint_as_float(raw[i]);                   // C1 + 4096 * C0, exact
+            const float hi = truncf(v * (1.0f / 4096.0f));
+            f0[i] = hi;
+            f1[i] = fmaf(-4096.0f, hi, v);
+        }
+#pragma unroll 1
+        for (int c = 1; c < nchunk; ++c) {
+            ptx::tmem_ld_x32(taddr + ((use0 + c) & 3) * BLOCK_N, raw);
+            ptx::tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < RADIX_MAX_CHUNKS; ++c) {
-            if (c < nchunk) {
-                ptx::tmem_ld_x32(taddr + ((use0 + c) & 3) * BLOCK_N, raw);
-                ptx::tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float v = __uint_as_float(raw[i]);           // C1 + 4096 * C0, exact
-                    const float hi = truncf(v * (1.0f / 4096.0f));
-                    f0[i] += hi;
-                    f1[i] += fmaf(-4096.0f, hi, v);
-                }
+            for (int i = 0; i < 32; ++i) {
+                const float v = __uint_as_float(raw[i]);
+                const float hi = truncf(v * (1.0f / 4096.0f));
+                f0[i] += hi;
+                f1[i] += fmaf(-4096.0f, hi, v);
             }
         }
     }
 }
 
+// 2^x for x <= ~20 or very negative (flushes to 0): one MUFU, no range fix-up.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// 320 threads x 200 registers = 64,000 of the SM's 65,536: one CTA per SM (shared memory
+// already enforces that), no spills in the 64-accumulator pass-2 epilogue.
 template <int PASS, int MODE>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __maxnreg__(200)
 scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x0,
                  const __grid_constant__ CUtensorMap tm_s, const PlaceParams p) {
     using Cfg = ModeCfg<MODE>;
@@ -329,31 +344,51 @@ scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constan
                         }
                     }
                 } else if (PASS == PASS_STATS) {
-                    float best = -INFINITY, b1 = 0.f, b0 = 0.f;
-#pragma unroll
+                    // One sweep over the 64 columns, 32 at a time, with a running reference column
+                    // (b1, b0): the best column of a group replaces it when it beats it by more than
+                    // 2^16 (then the running sum is rescaled by the exactly formed difference).
+                    float refv = -INFINITY, b1 = 0.f, b0 = 0.f, sum = 0.f;
+#pragma unroll 1
                     for (int ch = 0; ch < 2; ++ch) {
+                        if (ch * 32 >= n_valid) break;
                         load_counts<MODE>(taddr + ch * 32, use0, p.nchunk, f1, f0);
+                        const int nv = n_valid - ch * 32;      // >= 32 except in the last column tile
+                        float cm = -INFINITY, c1 = 0.f, c0 = 0.f;
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             const float v = fmaf(p.a1f, f1[i], p.a0f * f0[i]);
-                            const bool take = (ch * 32 + i < n_valid) && (v > best);
-                            best = take ? v : best;
-                            b1 = take ? f1[i] : b1;
-                            b0 = take ? f0[i] : b0;
+                            const bool take = (i < nv) && (v > cm);
+                            cm = take ? v : cm;
+                            c1 = take ? f1[i] : c1;
+                            c0 = take ? f0[i] : c0;
                         }
-                    }
-                    float sum = 0.f;
+                        if (cm > refv + 16.0f) {
+                            if (refv != -INFINITY) {
+                                const float e1 = b1 - c1, e0 = b0 - c0;
+                                sum *= ex2_approx(fmaf(p.a1h, e1, p.a0h * e0) + fmaf(p.a1l, e1, p.a0l * e0));
+                            }
+                            b1 = c1;
+                            b0 = c0;
+                            refv = cm;
+                        }
+                        if (nv >= 32) {
 #pragma unroll
-                    for (int ch = 0; ch < 2; ++ch) {
-                        load_counts<MODE>(taddr + ch * 32, use0, p.nchunk, f1, f0);
+                            for (int i = 0; i < 32; ++i) {
+                                const float e1 = f1[i] - b1;
+                                const float e0 = f0[i] - b0;
+                                const float s = fmaf(p.a1h, e1, p.a0h * e0);   // exact operands, one rounding
+                                const float lo = fmaf(p.a1l, e1, p.a0l * e0);
+                                sum += ex2_approx(s + lo);
+                            }
+                        } else {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float e1 = f1[i] - b1;
-                            const float e0 = f0[i] - b0;
-                            const float s = fmaf(p.a1h, e1, p.a0h * e0);   // exact operands, one rounding
-                            const float lo = fmaf(p.a1l, e1, p.a0l * e0);
-                            const float e = exp2f(s + lo);
-                            sum += (ch * 32 + i < n_valid) ? e : 0.f;
+                            for (int i = 0; i < 32; ++i) {
+                                const float e1 = f1[i] - b1;
+                                const float e0 = f0[i] - b0;
+                                const float s = fmaf(p.a1h, e1, p.a0h * e0);
+                                const float lo = fmaf(p.a1l, e1, p.a0l * e0);
+                                sum += (i < nv) ? ex2_approx(s + lo) : 0.f;
+                            }
                         }
                     }
                     const uint32_t pk = uint32_t(b1) | (uint32_t(b0) << 16);
@@ -362,8 +397,7 @@ scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constan
                     const uint2 rr = p.rowref[row];
                     const float r1f = float(rr.x & 0xFFFFu);
                     const float r0f = float(rr.x >> 16);
-                    const float L = __uint_as_float(rr.y);
-                    const bool rowvalid = row < p.M;
+                    const float L = __uint_as_float(rr.y);     // +inf for padded / dropped rows: 2^(-inf) = 0
 #pragma unroll
                     for (int ch = 0; ch < 2; ++ch) {
                         load_counts<MODE>(taddr + ch * 32, use0, p.nchunk, f1, f0);
@@ -374,8 +408,7 @@ scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constan
                             const float s = fmaf(p.a1h, e1, p.a0h * e0);
                             const float tl = fmaf(p.a0l, e0, -L);
                             const float lo = fmaf(p.a1l, e1, tl);
-                            const float e = exp2f(s + lo);
-                            colacc[ch * 32 + i] += rowvalid ? e : 0.f;
+                            colacc[ch * 32 + i] += ex2_approx(s + lo);
                         }
                     }
                 }
@@ -419,30 +452,31 @@ scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constan
 
 // ------------------------------------------------------- operand expansion
 // 2-bit genotype codes (0 wild type, 1 het, 2 hom, 3 missing; 4 cells per byte,
-// cell c in bits [2*(c%4), +2)) -> two 0/1 byte planes, K-major, zero padded.
-__global__ void scs_expand_genotypes_kernel(const uint8_t* __restrict__ gt, int64_t gt_pitch, int M, int n_cells,
+// cell c in bits [2*(c%4), +2)) -> 0/1 byte plane(s), K-major, zero padded.  One thread
+// turns 16 cells (one 32-bit word of codes) into one 16-byte store per plane.
+__global__ void scs_expand_genotypes_kernel(const uint8_t* __restrict__ gt, int64_t gt_pitch, int64_t M, int n_cells,
                                             uint8_t* __restrict__ x1, uint8_t* __restrict__ x0, int K_pad, int radix) {
-    const int kq = blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 cells
-    const int row = blockIdx.y;
-    if (kq * 4 >= K_pad || row >= M) return;
-    uint32_t o1 = 0, o0 = 0;
-    if (kq * 4 < n_cells) {
-        const uint32_t b = gt[size_t(row) * gt_pitch + kq];
+    const int kq = blockIdx.x * blockDim.x + threadIdx.x;  // group of 16 cells
+    if (kq * 16 >= K_pad) return;
+    for (int64_t row = blockIdx.y; row < M; row += gridDim.y) {
+        uint32_t w = 0;
+        if (kq * 4 < gt_pitch && kq * 16 < n_cells) w = *reinterpret_cast<const uint32_t*>(gt + row * gt_pitch + kq * 4);
+        uint32_t o1[4] = {0, 0, 0, 0}, o0[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t code = (b >> (2 * i)) & 3u;
-            const bool in = kq * 4 + i < n_cells;
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t code = (w >> (2 * i)) & 3u;
+            const bool in = kq * 16 + i < n_cells;
             const bool mut = in && (code == 1u || code == 2u), wt = in && code == 0u;
             if (radix) {
-                o1 |= uint32_t(mut ? E5M2_ONE : (wt ? E5M2_4096 : 0)) << (8 * i);   // one e5m2 plane: 1 / 4096 / 0
+                o1[i >> 2] |= uint32_t(mut ? E5M2_ONE : (wt ? E5M2_4096 : 0)) << (8 * (i & 3));   // one e5m2 plane: 1 / 4096 / 0
             } else {
-                o1 |= uint32_t(mut) << (8 * i);
-                o0 |= uint32_t(wt) << (8 * i);
+                o1[i >> 2] |= uint32_t(mut) << (8 * (i & 3));
+                o0[i >> 2] |= uint32_t(wt) << (8 * (i & 3));
             }
         }
+        *reinterpret_cast<uint4*>(x1 + row * K_pad + kq * 16) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+        if (!radix) *reinterpret_cast<uint4*>(x0 + row * K_pad + kq * 16) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
     }
-    *reinterpret_cast<uint32_t*>(x1 + size_t(row) * K_pad + kq * 4) = o1;
-    if (!radix) *reinterpret_cast<uint32_t*>(x0 + size_t(row) * K_pad + kq * 4) = o0;
 }
 
 // clade bit mask [N][words] (bit c%32 of word c/32 set when cell c is below the
@@ -723,22 +757,11 @@ int scs_placement_set_genotypes(scs_placement* h, const uint8_t* d_gt, int64_t p
     if (!pl || !d_gt) return set_error(SCS_ERR_ARG, "null argument");
     if (pitch_bytes < (pl->n_cells + 3) / 4) return set_error(SCS_ERR_ARG, "genotype row pitch %lld is smaller than ceil(n_cells/4)", (long long)pitch_bytes);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    dim3 block(128), grid((pl->K_pad / 4 + 127) / 128, unsigned(pl->n_snv));
-    if (pl->n_snv > 65535) {
-        // grid.y is limited to 65535: walk the rows in slabs
-        for (int64_t r0 = 0; r0 < pl->n_snv; r0 += 65535) {
-            const int rows = int(std::min<int64_t>(65535, pl->n_snv - r0));
-            grid.y = rows;
-            scs_expand_genotypes_kernel<<<grid, block, 0, st>>>(d_gt + r0 * pitch_bytes, pitch_bytes, rows, pl->n_cells,
-                                                                 pl->x1 + size_t(r0) * pl->K_pad, pl->x0 + size_t(r0) * pl->K_pad, pl->K_pad,
-                                                                 pl->mode == MODE_RADIX);
-            pl->launches++;
-        }
-    } else {
-        scs_expand_genotypes_kernel<<<grid, block, 0, st>>>(d_gt, pitch_bytes, int(pl->n_snv), pl->n_cells, pl->x1, pl->x0, pl->K_pad,
-                                                             pl->mode == MODE_RADIX);
-        pl->launches++;
-    }
+    if ((pitch_bytes & 3) || (reinterpret_cast<uintptr_t>(d_gt) & 3)) return set_error(SCS_ERR_ARG, "packed genotype rows must be 4-byte aligned (pitch %lld)", (long long)pitch_bytes);
+    dim3 block(128), grid((pl->K_pad / 16 + 127) / 128, unsigned(std::min<int64_t>(pl->n_snv, 16384)));
+    scs_expand_genotypes_kernel<<<grid, block, 0, st>>>(d_gt, pitch_bytes, pl->n_snv, pl->n_cells, pl->x1, pl->x0, pl->K_pad,
+                                                         pl->mode == MODE_RADIX);
+    pl->launches++;
     if (d_row_keep) {
         SCS_CUDA(cudaMemcpyAsync(pl->row_keep, d_row_keep, size_t(pl->n_snv), cudaMemcpyDeviceToDevice, st));
         pl->have_row_keep = true;
