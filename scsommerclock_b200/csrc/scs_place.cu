@@ -166,10 +166,10 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
-// 320 threads x 200 registers = 64,000 of the SM's 65,536: one CTA per SM (shared memory
-// already enforces that), no spills in the 64-accumulator pass-2 epilogue.
+// 10 warps are allocated as 12 (warp slots come in fours), which caps the kernel at
+// 65536 / 384 = 168 registers per thread; the 64-accumulator pass-2 epilogue spills a few.
 template <int PASS, int MODE>
-__global__ void __maxnreg__(200)
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x0,
                  const __grid_constant__ CUtensorMap tm_s, const PlaceParams p) {
     using Cfg = ModeCfg<MODE>;
