@@ -33,7 +33,8 @@ FN_TRUE, FP_TRUE, MS_TRUE = 0.10, 0.01, 0.15
 METRIC = "snv_branch_placements_per_s"
 # dram__bytes_read.sum + dram__bytes_write.sum of one scs_place_kernel launch at the default
 # workload, from the ncu --set full capture under profiles/ (None until a capture exists)
-NCU_TRAFFIC_BYTES = None
+# (profiles/r01_ncu_place_radix_summary.txt: 308.2 GB read + 2.5 GB written, pass 1, radix mode)
+NCU_TRAFFIC_BYTES = 310.7e9
 
 
 def parse():
@@ -326,7 +327,8 @@ def main():
             "e2e": e2e,
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES, "peak_source": pk_kind + " cuBLAS bf16, sustained (kernel timed inside a long step)",
+                         "traffic": NCU_TRAFFIC_BYTES if (n_cells == 10000 and n_snv == 1000000 and plan.info()["mode"] == 1) else None,
+                         "peak_source": pk_kind + " cuBLAS bf16, sustained (kernel timed inside a long step)",
                          "kernel": "scs_place_kernel (%s), avg of pass 1 and pass 2 launches" % (
                              "tcgen05 kind::f8f6f4, one radix-packed e5m2 plane" if plan.info()["mode"] == 1 else "tcgen05 kind::i8, two u8 planes"),
                          "algorithmic_flop_per_launch": flop, "ms_per_launch": t_gemm,
@@ -343,6 +345,9 @@ def main():
             line["cpu_baseline"] = cpu_port_baseline(tree_s, np.ascontiguousarray(S), n_cells, args.cpu_seconds)
         print(json.dumps(line), flush=True)
     sharding.barrier()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
