@@ -115,7 +115,8 @@ const void* scs_placement_device_result(scs_placement* plan);
 int scs_placement_last_times(scs_placement* plan, float* ms);
 /* info[0..9] = M_pad, N_pad, K_pad, tasks, run_len, superblock_width, grid,
  * kernel launches so far, runs, dynamic smem bytes, operand mode (0 = two u8
- * planes / kind::i8, 1 = one radix-packed e5m2 plane / kind::f8f6f4), K chunks */
+ * planes / kind::i8, 1 = one radix-packed e5m2 plane / kind::f8f6f4), K chunks,
+ * 1 when the 2-CTA (cta_group::2) kernel is used */
 int scs_placement_info(scs_placement* plan, int64_t* info, int32_t n);
 /* Parity aid for small problems: counts[i][b][0/1] = number of cells of clade b
  * observed mutated / observed wild type for SNV i (exact integers). */

@@ -85,6 +85,7 @@ struct PlaceParams {
     int run_len, num_runs, sb_width, num_tasks;
     int l2_hints;              // 1: clade tiles evict-last, genotype tiles evict-first
     int nchunk;                // radix mode: K chunks (accumulators) per tile
+    int num_row_pairs, run_len2, num_runs2, num_tasks2;   // 2-CTA kernel: schedule in row-block pairs
     float a1h, a1l, a0h, a0l;  // log2-unit constants, split so that a?h * count is exact
     float a1f, a0f;            // plain fp32 copies, used only to rank columns
     uint2* stats;              // pass 1 out: [num_col_tiles*2][M_pad] {ref counts, sum}
@@ -164,6 +165,116 @@ __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+
+// ---- epilogue building blocks shared by the 1-CTA and the 2-CTA kernels -------------
+// One tile (this thread's row, its 64-column half) from TMEM.
+template <int PASS, int MODE>
+__device__ __forceinline__ void epilogue_tile(const PlaceParams& p, uint32_t taddr, uint32_t use0, int row, int j, int hh,
+                                              int col0, int n_valid, float (&colacc)[64]) {
+    float f1[32], f0[32];
+    if (PASS == PASS_DUMP) {
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            load_counts<MODE>(taddr + ch * 32, use0, p.nchunk, f1, f0);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const size_t o = (size_t(row) * p.N_pad + col0 + ch * 32 + i) * 2;
+                p.dump[o] = int(f1[i]);
+                p.dump[o + 1] = int(f0[i]);
+            }
+        }
+    } else if (PASS == PASS_STATS) {
+        // One sweep over the 64 columns, 32 at a time, with a running reference column
+        // (b1, b0): the best column of a group replaces it when it beats it by more than
+        // 2^16 (then the running sum is rescaled by the exactly formed difference).
+        float refv = -INFINITY, b1 = 0.f, b0 = 0.f, sum = 0.f;
+#pragma unroll 1
+        for (int ch = 0; ch < 2; ++ch) {
+            if (ch * 32 >= n_valid) break;
+            load_counts<MODE>(taddr + ch * 32, use0, p.nchunk, f1, f0);
+            const int nv = n_valid - ch * 32;      // >= 32 except in the last column tile
+            float cm = -INFINITY, c1 = 0.f, c0 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float v = fmaf(p.a1f, f1[i], p.a0f * f0[i]);
+                const bool take = (i < nv) && (v > cm);
+                cm = take ? v : cm;
+                c1 = take ? f1[i] : c1;
+                c0 = take ? f0[i] : c0;
+            }
+            if (cm > refv + 16.0f) {
+                if (refv != -INFINITY) {
+                    const float e1 = b1 - c1, e0 = b0 - c0;
+                    sum *= ex2_approx(fmaf(p.a1h, e1, p.a0h * e0) + fmaf(p.a1l, e1, p.a0l * e0));
+                }
+                b1 = c1;
+                b0 = c0;
+                refv = cm;
+            }
+            if (nv >= 32) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float e1 = f1[i] - b1;
+                    const float e0 = f0[i] - b0;
+                    const float sdiff = fmaf(p.a1h, e1, p.a0h * e0);   // exact operands, one rounding
+                    const float lo = fmaf(p.a1l, e1, p.a0l * e0);
+                    sum += ex2_approx(sdiff + lo);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float e1 = f1[i] - b1;
+                    const float e0 = f0[i] - b0;
+                    const float sdiff = fmaf(p.a1h, e1, p.a0h * e0);
+                    const float lo = fmaf(p.a1l, e1, p.a0l * e0);
+                    sum += (i < nv) ? ex2_approx(sdiff + lo) : 0.f;
+                }
+            }
+        }
+        const uint32_t pk = uint32_t(b1) | (uint32_t(b0) << 16);
+        p.stats[size_t(j * 2 + hh) * p.M_pad + row] = make_uint2(pk, __float_as_uint(sum));
+    } else {
+        const uint2 rr = p.rowref[row];
+        const float r1f = float(rr.x & 0xFFFFu);
+        const float r0f = float(rr.x >> 16);
+        const float L = __uint_as_float(rr.y);     // +inf for padded / dropped rows: 2^(-inf) = 0
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            load_counts<MODE>(taddr + ch * 32, use0, p.nchunk, f1, f0);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float e1 = f1[i] - r1f;
+                const float e0 = f0[i] - r0f;
+                const float sdiff = fmaf(p.a1h, e1, p.a0h * e0);
+                const float tl = fmaf(p.a0l, e0, -L);
+                const float lo = fmaf(p.a1l, e1, tl);
+                colacc[ch * 32 + i] += ex2_approx(sdiff + lo);
+            }
+        }
+    }
+}
+
+// End of a run (pass 2): rows -> one number per column: lanes, then the four lane quarters.
+__device__ __forceinline__ void epilogue_flush_columns(const PlaceParams& p, float* red, const float (&colacc)[64], int q, int hh,
+                                                       int lane, int run, int j) {
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+        float v = colacc[i];
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        if (lane == (i & 31)) red[q * BLOCK_N + hh * 64 + i] = v;
+    }
+    asm volatile("bar.sync 1, %0;\n" ::"n"(NUM_EPI_WARPS * 32) : "memory");
+    const int et = threadIdx.x - 64;
+    if (et < BLOCK_N) {
+        const float v = ((red[et] + red[BLOCK_N + et]) + red[2 * BLOCK_N + et]) + red[3 * BLOCK_N + et];
+        p.colpart[size_t(run) * p.N_pad + j * BLOCK_N + et] = v;
+    }
+    asm volatile("bar.sync 1, %0;\n" ::"n"(NUM_EPI_WARPS * 32) : "memory");
 }
 
 // 10 warps are allocated as 12 (warp slots come in fours), which caps the kernel at
@@ -331,114 +442,14 @@ scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constan
                 const int row = r * BLOCK_M + q * 32 + lane;
                 const uint32_t use0 = tile_n * spt;
                 const uint32_t taddr = tmem_base + lane_base + hh * 64;
-                float f1[32], f0[32];
-                if (PASS == PASS_DUMP) {
-#pragma unroll
-                    for (int ch = 0; ch < 2; ++ch) {
-                        load_counts<MODE>(taddr + ch * 32, use0, p.nchunk, f1, f0);
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const size_t o = (size_t(row) * p.N_pad + col0 + ch * 32 + i) * 2;
-                            p.dump[o] = int(f1[i]);
-                            p.dump[o + 1] = int(f0[i]);
-                        }
-                    }
-                } else if (PASS == PASS_STATS) {
-                    // One sweep over the 64 columns, 32 at a time, with a running reference column
-                    // (b1, b0): the best column of a group replaces it when it beats it by more than
-                    // 2^16 (then the running sum is rescaled by the exactly formed difference).
-                    float refv = -INFINITY, b1 = 0.f, b0 = 0.f, sum = 0.f;
-#pragma unroll 1
-                    for (int ch = 0; ch < 2; ++ch) {
-                        if (ch * 32 >= n_valid) break;
-                        load_counts<MODE>(taddr + ch * 32, use0, p.nchunk, f1, f0);
-                        const int nv = n_valid - ch * 32;      // >= 32 except in the last column tile
-                        float cm = -INFINITY, c1 = 0.f, c0 = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float v = fmaf(p.a1f, f1[i], p.a0f * f0[i]);
-                            const bool take = (i < nv) && (v > cm);
-                            cm = take ? v : cm;
-                            c1 = take ? f1[i] : c1;
-                            c0 = take ? f0[i] : c0;
-                        }
-                        if (cm > refv + 16.0f) {
-                            if (refv != -INFINITY) {
-                                const float e1 = b1 - c1, e0 = b0 - c0;
-                                sum *= ex2_approx(fmaf(p.a1h, e1, p.a0h * e0) + fmaf(p.a1l, e1, p.a0l * e0));
-                            }
-                            b1 = c1;
-                            b0 = c0;
-                            refv = cm;
-                        }
-                        if (nv >= 32) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const float e1 = f1[i] - b1;
-                                const float e0 = f0[i] - b0;
-                                const float s = fmaf(p.a1h, e1, p.a0h * e0);   // exact operands, one rounding
-                                const float lo = fmaf(p.a1l, e1, p.a0l * e0);
-                                sum += ex2_approx(s + lo);
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const float e1 = f1[i] - b1;
-                                const float e0 = f0[i] - b0;
-                                const float s = fmaf(p.a1h, e1, p.a0h * e0);
-                                const float lo = fmaf(p.a1l, e1, p.a0l * e0);
-                                sum += (i < nv) ? ex2_approx(s + lo) : 0.f;
-                            }
-                        }
-                    }
-                    const uint32_t pk = uint32_t(b1) | (uint32_t(b0) << 16);
-                    p.stats[size_t(j * 2 + hh) * p.M_pad + row] = make_uint2(pk, __float_as_uint(sum));
-                } else {
-                    const uint2 rr = p.rowref[row];
-                    const float r1f = float(rr.x & 0xFFFFu);
-                    const float r0f = float(rr.x >> 16);
-                    const float L = __uint_as_float(rr.y);     // +inf for padded / dropped rows: 2^(-inf) = 0
-#pragma unroll
-                    for (int ch = 0; ch < 2; ++ch) {
-                        load_counts<MODE>(taddr + ch * 32, use0, p.nchunk, f1, f0);
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float e1 = f1[i] - r1f;
-                            const float e0 = f0[i] - r0f;
-                            const float s = fmaf(p.a1h, e1, p.a0h * e0);
-                            const float tl = fmaf(p.a0l, e0, -L);
-                            const float lo = fmaf(p.a1l, e1, tl);
-                            colacc[ch * 32 + i] += ex2_approx(s + lo);
-                        }
-                    }
-                }
+                epilogue_tile<PASS, MODE>(p, taddr, use0, row, j, hh, col0, n_valid, colacc);
                 // this tile's slots are drained: hand them back to the MMA warp
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0)
                     for (int c = 0; c < spt; ++c) ptx::mbar_arrive(&sempty_bar[(use0 + c) & 3]);
             }
-            if (PASS == PASS_COLSUM) {
-                // rows -> one number per column: lanes, then the four lane quarters
-#pragma unroll
-                for (int i = 0; i < 64; ++i) {
-                    float v = colacc[i];
-                    v += __shfl_xor_sync(0xffffffffu, v, 16);
-                    v += __shfl_xor_sync(0xffffffffu, v, 8);
-                    v += __shfl_xor_sync(0xffffffffu, v, 4);
-                    v += __shfl_xor_sync(0xffffffffu, v, 2);
-                    v += __shfl_xor_sync(0xffffffffu, v, 1);
-                    if (lane == (i & 31)) red[q * BLOCK_N + hh * 64 + i] = v;
-                }
-                asm volatile("bar.sync 1, %0;\n" ::"n"(NUM_EPI_WARPS * 32) : "memory");
-                const int et = threadIdx.x - 64;
-                if (et < BLOCK_N) {
-                    const float v = ((red[et] + red[BLOCK_N + et]) + red[2 * BLOCK_N + et]) + red[3 * BLOCK_N + et];
-                    const int run = r0 / p.run_len;
-                    p.colpart[size_t(run) * p.N_pad + j * BLOCK_N + et] = v;
-                }
-                asm volatile("bar.sync 1, %0;\n" ::"n"(NUM_EPI_WARPS * 32) : "memory");
-            }
+            if (PASS == PASS_COLSUM) epilogue_flush_columns(p, red, colacc, q, hh, lane, r0 / p.run_len, j);
         }
     }
 
@@ -447,6 +458,190 @@ scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constan
     if (warp_idx == 1) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------- 2-CTA kernel
+// Radix mode on CTA pairs (cluster of 2, tcgen05 cta_group::2): one MMA covers M = 256 SNV
+// rows (128 from each CTA's shared memory) x N = 128 clade rows, of which each CTA stages only
+// its half (64 rows).  Per 64-cycle MMA an SM now reads 4 KB (A) + 2 KB (B) of shared memory
+// instead of 8 KB, and pulls 24 KB instead of 32 KB per K block from L2: the 1-CTA kernel sits
+// at 68 % tensor-pipe utilisation with the shared-memory operand port saturated
+// (profiles/r01_ncu_place_radix_summary.txt).
+// Protocol: every CTA has a TMA producer (its own A rows + its B half), both signal the LEADER's
+// full barrier; only the leader issues MMAs and multicasts the commits (stage free, tile done)
+// to both CTAs; both CTAs' epilogue warps release TMEM slots on the leader's barrier.
+constexpr int K2_STAGES = 8;
+constexpr int K2_STAGE_BYTES = TILE_BYTES + TILE_BYTES / 2;   // A 16 KB + half of B 8 KB
+constexpr int K2_SMEM_TOTAL = K2_STAGES * K2_STAGE_BYTES + SMEM_BARRIER_BYTES + SMEM_RED_BYTES + 1024;
+constexpr uint32_t IDESC_E5M2_2SM = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BLOCK_N >> 3) << 17) | (uint32_t(256 >> 4) << 24);
+
+__host__ __device__ inline void decode_task2(const PlaceParams& p, int t, int& j, int& q0, int& q1) {
+    const int per_sb = p.num_runs2 * p.sb_width;
+    const int nsb_full = p.num_col_tiles / p.sb_width;
+    int sb = t / per_sb;
+    int w = p.sb_width;
+    if (sb >= nsb_full) {
+        sb = nsb_full;
+        w = p.num_col_tiles - nsb_full * p.sb_width;
+    }
+    const int rem = t - sb * per_sb;
+    const int run = rem / w;
+    j = sb * p.sb_width + (rem - run * w);
+    q0 = run * p.run_len2;
+    q1 = min(q0 + p.run_len2, p.num_row_pairs);
+}
+
+template <int PASS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+scs_place_kernel2(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_s64, const PlaceParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + K2_STAGES * K2_STAGE_BYTES);
+    uint64_t* full_bar = bars;                      // [8] used in the leader only
+    uint64_t* empty_bar = bars + K2_STAGES;         // [8] each CTA, one multicast commit per phase
+    uint64_t* tfull_bar = bars + 2 * K2_STAGES;     // [4] each CTA
+    uint64_t* sempty_bar = bars + 2 * K2_STAGES + 4;  // [4] leader only, both CTAs' epilogues arrive
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * K2_STAGES + 8);
+    float* red = reinterpret_cast<float*>(smem + K2_STAGES * K2_STAGE_BYTES + SMEM_BARRIER_BYTES);
+
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1;
+    const int num_clusters = gridDim.x >> 1;
+
+    if (warp_idx == 0 && ptx::elect_one()) {
+        ptx::prefetch_tmap(&tm_x);
+        ptx::prefetch_tmap(&tm_s64);
+        for (int s = 0; s < K2_STAGES; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 4; ++a) {
+            ptx::mbar_init(&tfull_bar[a], 1);
+            ptx::mbar_init(&sempty_bar[a], 2 * NUM_EPI_WARPS);
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp_idx == 1) {
+        ptx::tmem_alloc_2sm(tmem_ptr_smem, TMEM_COLS);
+        ptx::tmem_relinquish_2sm();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp_idx == 0) {
+        // ============ TMA producer (one lane, in BOTH CTAs) ============
+        if (ptx::elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint64_t pol_x = p.l2_hints ? ptx::L2_EVICT_FIRST : ptx::L2_EVICT_NORMAL;
+            const uint64_t pol_s = p.l2_hints ? ptx::L2_EVICT_LAST : ptx::L2_EVICT_NORMAL;
+            for (int t = cluster_id; t < p.num_tasks2; t += num_clusters) {
+                int j, q0, q1;
+                decode_task2(p, t, j, q0, q1);
+                for (int q = q0; q < q1; ++q) {
+                    const int rb = 2 * q + int(rank);
+                    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* st = smem + stage * K2_STAGE_BYTES;
+                        if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * K2_STAGE_BYTES);   // both CTAs' bytes
+                        const uint32_t lead_full = ptx::mapa_u32(&full_bar[stage], 0);
+                        ptx::tma_load_2d_2sm(&tm_x, lead_full, st, kb * BLOCK_K, rb * BLOCK_M, pol_x);
+                        ptx::tma_load_2d_2sm(&tm_s64, lead_full, st + TILE_BYTES, kb * BLOCK_K, j * BLOCK_N + int(rank) * 64, pol_s);
+                        if (++stage == K2_STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp_idx == 1) {
+        // ============ MMA issuer (one lane of the LEADER CTA) ============
+        if (rank == 0 && ptx::elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const int spt = p.nchunk;
+            uint32_t tile_n = 0;
+            for (int t = cluster_id; t < p.num_tasks2; t += num_clusters) {
+                int j, q0, q1;
+                decode_task2(p, t, j, q0, q1);
+                for (int q = q0; q < q1; ++q, ++tile_n) {
+                    const uint32_t use0 = tile_n * spt;
+                    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                        const int chunk = kb / RADIX_KB_PER_CHUNK;
+                        const int kin = kb - chunk * RADIX_KB_PER_CHUNK;
+                        if (kin == 0) {
+                            ptx::mbar_wait(&sempty_bar[(use0 + chunk) & 3], (((use0 + chunk) >> 2) & 1) ^ 1);
+                            ptx::tc_fence_after();
+                        }
+                        ptx::mbar_wait(&full_bar[stage], phase);
+                        ptx::tc_fence_after();
+                        const uint32_t st = ptx::smem_u32(smem + stage * K2_STAGE_BYTES);
+                        const uint64_t dx = ptx::make_kmajor_sw128_desc(st);
+                        const uint64_t ds = ptx::make_kmajor_sw128_desc(st + TILE_BYTES);
+                        const uint32_t d = tmem_base + (((use0 + chunk) & 3) * BLOCK_N);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                            const uint64_t koff = uint64_t(k * (UMMA_K >> 4));
+                            ptx::mma_f8_ss_2sm(d, dx + koff, ds + koff, IDESC_E5M2_2SM, (kin | k) != 0);
+                        }
+                        ptx::mma_commit_2sm(&empty_bar[stage], 3);
+                        if (++stage == K2_STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    ptx::mma_commit_2sm(&tfull_bar[tile_n & 3], 3);
+                }
+            }
+        }
+    } else {
+        // ============ epilogue warps (both CTAs, own 128 rows each) ============
+        const int ew = warp_idx - 2;
+        const int q4 = warp_idx & 3;
+        const int hh = ew >> 2;
+        const uint32_t lane_base = uint32_t(q4 * 32) << 16;
+        const int spt = p.nchunk;
+        uint32_t tile_n = 0;
+        for (int t = cluster_id; t < p.num_tasks2; t += num_clusters) {
+            int j, q0, q1;
+            decode_task2(p, t, j, q0, q1);
+            const int col0 = j * BLOCK_N + hh * 64;
+            const int n_valid = max(0, min(64, p.N - col0));
+            float colacc[64];
+            if (PASS == PASS_COLSUM) {
+#pragma unroll
+                for (int i = 0; i < 64; ++i) colacc[i] = 0.f;
+            }
+            for (int q = q0; q < q1; ++q, ++tile_n) {
+                ptx::mbar_wait(&tfull_bar[tile_n & 3], (tile_n >> 2) & 1);
+                ptx::tc_fence_after();
+                const int row = (2 * q + int(rank)) * BLOCK_M + q4 * 32 + lane;
+                const uint32_t use0 = tile_n * spt;
+                const uint32_t taddr = tmem_base + lane_base + hh * 64;
+                epilogue_tile<PASS, MODE_RADIX>(p, taddr, use0, row, j, hh, col0, n_valid, colacc);
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0)
+                    for (int c = 0; c < spt; ++c) ptx::mbar_arrive_cluster(ptx::mapa_u32(&sempty_bar[(use0 + c) & 3], 0));
+            }
+            if (PASS == PASS_COLSUM) epilogue_flush_columns(p, red, colacc, q4, hh, lane, (q0 / p.run_len2) * 2 + int(rank), j);
+        }
+    }
+
+    // both CTAs must be done with TMEM, shared memory and each other's barriers before either leaves
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();
+    if (warp_idx == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc_2sm(tmem_base, TMEM_COLS);
     }
 }
 
@@ -584,7 +779,13 @@ static void launch_place(int mode, int grid, cudaStream_t st, const CUtensorMap&
 }
 
 template <int PASS>
+static void launch_place2(int grid2, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b64, const PlaceParams& p) {
+    scs_place_kernel2<PASS><<<grid2, NUM_THREADS, K2_SMEM_TOTAL, st>>>(a, b64, p);
+}
+
+template <int PASS>
 static void set_place_smem() {
+    cudaFuncSetAttribute(scs_place_kernel2<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_TOTAL);
     cudaFuncSetAttribute(scs_place_kernel<PASS, MODE_PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModeCfg<MODE_PLANES>::SMEM_TOTAL);
     cudaFuncSetAttribute(scs_place_kernel<PASS, MODE_RADIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModeCfg<MODE_RADIX>::SMEM_TOTAL);
 }
@@ -611,6 +812,10 @@ struct Placement {
     size_t stage_mask_bytes = 0;
     long long launches = 0;
     int mode = MODE_PLANES;
+    bool pair = false;            // radix mode on CTA pairs (scs_place_kernel2)
+    int grid2 = 0;
+    int colpart_rows = 0;
+    CUtensorMap tm_s64;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // brackets of the four kernels of run()
     bool timed = false;
 };
@@ -646,7 +851,7 @@ int scs_placement_create(scs_ctx* ctx, int64_t n_snv, int32_t n_cells, int32_t n
     pl->n_snv = n_snv;
     pl->n_cells = n_cells;
     pl->n_rows = n_rows;
-    pl->M_pad = round_up(n_snv, BLOCK_M);
+    pl->M_pad = round_up(n_snv, 2 * BLOCK_M);     // row-block pairs for the 2-CTA kernel
     pl->N_pad = round_up(n_rows, BLOCK_N);
     pl->K_pad = round_up(n_cells, BLOCK_K);
     const size_t plane = size_t(pl->M_pad) * pl->K_pad;
@@ -692,6 +897,15 @@ int scs_placement_create(scs_ctx* ctx, int64_t n_snv, int32_t n_cells, int32_t n
     p.num_runs = (p.num_row_blocks + run_len - 1) / run_len;
     p.num_tasks = p.num_runs * p.num_col_tiles;
     pl->grid = std::min(ctx->sm_count, p.num_tasks);
+    // 2-CTA schedule: the same tasks, in units of row-block pairs
+    p.num_row_pairs = p.num_row_blocks / 2;
+    p.run_len2 = std::max(1, run_len / 2);
+    p.num_runs2 = (p.num_row_pairs + p.run_len2 - 1) / p.run_len2;
+    p.num_tasks2 = p.num_runs2 * p.num_col_tiles;
+    pl->grid2 = std::min(ctx->sm_count & ~1, 2 * p.num_tasks2);
+    pl->pair = pl->mode == MODE_RADIX;
+    if (const char* e = getenv("SCS_PLACE_PAIR")) pl->pair = pl->pair && atoi(e) != 0;
+    pl->colpart_rows = std::max(p.num_runs, 2 * p.num_runs2);
 
     int rc = SCS_OK;
     do {
@@ -699,7 +913,7 @@ int scs_placement_create(scs_ctx* ctx, int64_t n_snv, int32_t n_cells, int32_t n
             cudaMalloc(&pl->s, sbytes) != cudaSuccess ||
             cudaMalloc(&pl->stats, size_t(p.num_col_tiles) * 2 * pl->M_pad * sizeof(uint2)) != cudaSuccess ||
             cudaMalloc(&pl->rowref, size_t(pl->M_pad) * sizeof(uint2)) != cudaSuccess ||
-            cudaMalloc(&pl->colpart, size_t(p.num_runs) * pl->N_pad * sizeof(float)) != cudaSuccess ||
+            cudaMalloc(&pl->colpart, size_t(pl->colpart_rows) * pl->N_pad * sizeof(float)) != cudaSuccess ||
             cudaMalloc(&pl->y, size_t(pl->N_pad) * sizeof(double)) != cudaSuccess ||
             cudaMalloc(&pl->row_keep, size_t(pl->M_pad)) != cudaSuccess) {
             rc = set_error(SCS_ERR_OOM, "device allocation failed for placement plan (%s)", cudaGetErrorString(cudaGetLastError()));
@@ -714,6 +928,7 @@ int scs_placement_create(scs_ctx* ctx, int64_t n_snv, int32_t n_cells, int32_t n
         if ((rc = make_u8_tmap(&pl->tm_x1, pl->x1, pl->M_pad, pl->K_pad, BLOCK_M)) != SCS_OK) break;
         if ((rc = make_u8_tmap(&pl->tm_x0, pl->x0, pl->M_pad, pl->K_pad, BLOCK_M)) != SCS_OK) break;
         if ((rc = make_u8_tmap(&pl->tm_s, pl->s, pl->N_pad, pl->K_pad, BLOCK_N)) != SCS_OK) break;
+        if ((rc = make_u8_tmap(&pl->tm_s64, pl->s, pl->N_pad, pl->K_pad, BLOCK_N / 2)) != SCS_OK) break;
         set_place_smem<PASS_DUMP>();
         set_place_smem<PASS_STATS>();
         set_place_smem<PASS_COLSUM>();
@@ -853,15 +1068,17 @@ int scs_placement_run(scs_placement* h, double FP, double FN, double* d_soft_wei
     fill_constants(pl, FP, FN, &a1, &a0);
     const PlaceParams& p = pl->prm;
     cudaEventRecord(pl->ev[0], st);
-    launch_place<PASS_STATS>(pl->mode, pl->grid, st, pl->tm_x1, pl->tm_x0, pl->tm_s, p);
+    if (pl->pair) launch_place2<PASS_STATS>(pl->grid2, st, pl->tm_x1, pl->tm_s64, p);
+    else launch_place<PASS_STATS>(pl->mode, pl->grid, st, pl->tm_x1, pl->tm_x0, pl->tm_s, p);
     cudaEventRecord(pl->ev[1], st);
     scs_merge_stats_kernel<<<(p.M_pad + 255) / 256, 256, 0, st>>>(pl->stats, p.num_col_tiles * 2, p.M, p.M_pad,
                                                                   pl->have_row_keep ? pl->row_keep : nullptr, a1, a0, pl->rowref);
     cudaEventRecord(pl->ev[2], st);
-    launch_place<PASS_COLSUM>(pl->mode, pl->grid, st, pl->tm_x1, pl->tm_x0, pl->tm_s, p);
+    if (pl->pair) launch_place2<PASS_COLSUM>(pl->grid2, st, pl->tm_x1, pl->tm_s64, p);
+    else launch_place<PASS_COLSUM>(pl->mode, pl->grid, st, pl->tm_x1, pl->tm_x0, pl->tm_s, p);
     cudaEventRecord(pl->ev[3], st);
     double* y = d_soft_weights ? d_soft_weights : pl->y;
-    scs_reduce_colpart_kernel<<<(p.N + 255) / 256, 256, 0, st>>>(pl->colpart, p.num_runs, p.N, p.N_pad, y);
+    scs_reduce_colpart_kernel<<<(p.N + 255) / 256, 256, 0, st>>>(pl->colpart, pl->pair ? 2 * p.num_runs2 : p.num_runs, p.N, p.N_pad, y);
     cudaEventRecord(pl->ev[4], st);
     pl->timed = true;
     pl->launches += 4;
@@ -891,7 +1108,8 @@ int scs_placement_debug_counts(scs_placement* h, int32_t* counts_host, void* str
     if (!pl->dump && cudaMalloc(&pl->dump, n * sizeof(int)) != cudaSuccess) return set_error(SCS_ERR_OOM, "debug dump allocation failed");
     PlaceParams p = pl->prm;
     p.dump = pl->dump;
-    launch_place<PASS_DUMP>(pl->mode, pl->grid, st, pl->tm_x1, pl->tm_x0, pl->tm_s, p);
+    if (pl->pair) launch_place2<PASS_DUMP>(pl->grid2, st, pl->tm_x1, pl->tm_s64, p);
+    else launch_place<PASS_DUMP>(pl->mode, pl->grid, st, pl->tm_x1, pl->tm_x0, pl->tm_s, p);
     pl->launches++;
     SCS_CUDA(cudaGetLastError());
     std::vector<int> tmp(n);
@@ -905,9 +1123,10 @@ int scs_placement_debug_counts(scs_placement* h, int32_t* counts_host, void* str
 int scs_placement_info(scs_placement* h, int64_t* info, int32_t n) {
     Placement* pl = reinterpret_cast<Placement*>(h);
     if (!pl || !info) return set_error(SCS_ERR_ARG, "null argument");
-    const int64_t v[12] = {pl->M_pad, pl->N_pad, pl->K_pad, pl->prm.num_tasks, pl->prm.run_len, pl->prm.sb_width, pl->grid, pl->launches, pl->prm.num_runs,
-                           pl->mode == MODE_RADIX ? ModeCfg<MODE_RADIX>::SMEM_TOTAL : ModeCfg<MODE_PLANES>::SMEM_TOTAL, pl->mode, pl->prm.nchunk};
-    for (int i = 0; i < n && i < 12; ++i) info[i] = v[i];
+    const int64_t v[13] = {pl->M_pad, pl->N_pad, pl->K_pad, pl->prm.num_tasks, pl->prm.run_len, pl->prm.sb_width, pl->pair ? pl->grid2 : pl->grid, pl->launches, pl->prm.num_runs,
+                           pl->pair ? K2_SMEM_TOTAL : (pl->mode == MODE_RADIX ? ModeCfg<MODE_RADIX>::SMEM_TOTAL : ModeCfg<MODE_PLANES>::SMEM_TOTAL),
+                           pl->mode, pl->prm.nchunk, pl->pair ? 1 : 0};
+    for (int i = 0; i < n && i < 13; ++i) info[i] = v[i];
     return SCS_OK;
 }
 

@@ -124,10 +124,10 @@ class Placement:
             pass
 
     def info(self):
-        v = (C.c_int64 * 12)()
-        check(lib().scs_placement_info(self._h, v, 12))
+        v = (C.c_int64 * 13)()
+        check(lib().scs_placement_info(self._h, v, 13))
         keys = ("M_pad", "N_pad", "K_pad", "tasks", "run_len", "superblock_width", "grid", "launches", "runs", "smem_bytes",
-                "mode", "k_chunks")
+                "mode", "k_chunks", "cta_pair")
         return dict(zip(keys, (int(x) for x in v)))
 
     # host buffers (numpy)
