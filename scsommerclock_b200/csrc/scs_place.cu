@@ -903,8 +903,12 @@ int scs_placement_create(scs_ctx* ctx, int64_t n_snv, int32_t n_cells, int32_t n
     p.num_runs2 = (p.num_row_pairs + p.run_len2 - 1) / p.run_len2;
     p.num_tasks2 = p.num_runs2 * p.num_col_tiles;
     pl->grid2 = std::min(ctx->sm_count & ~1, 2 * p.num_tasks2);
-    pl->pair = pl->mode == MODE_RADIX;
-    if (const char* e = getenv("SCS_PLACE_PAIR")) pl->pair = pl->pair && atoi(e) != 0;
+    // The 2-CTA kernel is opt-in (SCS_PLACE_PAIR=1): it is bit-identical but, measured at
+    // 10k cells x 1M SNVs, not faster -- the same cycle count per pass at lower clocks under the
+    // 1 kW cap (169 ms @1522 MHz vs 140 ms @1815 MHz; profiles/r01_pair_vs_single.txt).  The
+    // 1-CTA kernel already runs at 98.6 % of twice the measured sustained cuBLAS bf16 rate.
+    pl->pair = false;
+    if (const char* e = getenv("SCS_PLACE_PAIR")) pl->pair = pl->mode == MODE_RADIX && atoi(e) != 0;
     pl->colpart_rows = std::max(p.num_runs, 2 * p.num_runs2);
 
     int rc = SCS_OK;
