@@ -91,6 +91,12 @@ int scs_gt_reduce(scs_ctx* ctx, const uint8_t* d_gt, int64_t pitch_bytes, int64_
  * A plan owns the device-resident operands and scratch for one (n_snv, n_cells,
  * n_rows) shape and can be re-run with new genotypes / clades / error rates. */
 int scs_placement_create(scs_ctx* ctx, int64_t n_snv, int32_t n_cells, int32_t n_rows, scs_placement** out);
+/* A batch of independent datasets ("groups": simulation replicates, each with its own
+ * SNVs and its own tree over the same number of cells) in one plan and one launch per
+ * pass.  Genotypes and row_keep are the groups' rows concatenated in group order, clade
+ * masks are [n_groups * n_rows][pitch_words], results are [n_groups][n_rows]. */
+int scs_placement_create_batch(scs_ctx* ctx, int32_t n_groups, const int64_t* n_snv, int32_t n_cells, int32_t n_rows,
+                               scs_placement** out);
 int scs_placement_destroy(scs_placement* plan);
 /* d_gt: packed 2-bit genotypes [n_snv][pitch_bytes]; d_row_keep: optional
  * [n_snv] bytes, 0 drops the SNV (the reference's `muts_red.sum(axis=1) > 0`
@@ -106,6 +112,8 @@ int scs_placement_set_clades_host(scs_placement* plan, const uint32_t* bits, int
 /* Asynchronous on `stream`.  d_soft_weights: [n_rows] doubles on the device, or
  * NULL to leave the result in the plan (scs_placement_device_result). */
 int scs_placement_run(scs_placement* plan, double FP, double FN, double* d_soft_weights, void* stream);
+/* One (FP, FN) pair per group. */
+int scs_placement_run_batch(scs_placement* plan, const double* FP, const double* FN, double* d_soft_weights, void* stream);
 /* Same, then copies [n_rows] doubles to host memory and synchronises. */
 int scs_placement_run_host(scs_placement* plan, double FP, double FN, double* soft_weights, void* stream);
 const void* scs_placement_device_result(scs_placement* plan);
@@ -116,7 +124,7 @@ int scs_placement_last_times(scs_placement* plan, float* ms);
 /* info[0..9] = M_pad, N_pad, K_pad, tasks, run_len, superblock_width, grid,
  * kernel launches so far, runs, dynamic smem bytes, operand mode (0 = two u8
  * planes / kind::i8, 1 = one radix-packed e5m2 plane / kind::f8f6f4), K chunks,
- * 1 when the 2-CTA (cta_group::2) kernel is used */
+ * 1 when the 2-CTA (cta_group::2) kernel is used, groups */
 int scs_placement_info(scs_placement* plan, int64_t* info, int32_t n);
 /* Parity aid for small problems: counts[i][b][0/1] = number of cells of clade b
  * observed mutated / observed wild type for SNV i (exact integers). */

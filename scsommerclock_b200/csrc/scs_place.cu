@@ -77,41 +77,39 @@ constexpr uint32_t IDESC_E5M2 = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(B
 
 enum { PASS_DUMP = 0, PASS_STATS = 1, PASS_COLSUM = 2 };
 
+// One task = one column tile against a run of row blocks of the same group (dataset).
+struct TaskEntry {
+    int j;          // global column tile
+    int r0, r1;     // global row blocks [r0, r1)
+    int jl;         // column tile index inside its group (indexes the pass-1 partials)
+    int run_local;  // run index inside its group (indexes the pass-2 partials)
+    int nvalid;     // valid clade rows in this tile (1..128)
+    int group;
+    int pad;
+};
+// Per-group (per-dataset) error-model constants, log2 units (see fill_constants).
+struct GroupConst {
+    float a1h, a1l, a0h, a0l;  // split so that a?h * (count difference) is exact
+    float a1f, a0f;            // plain fp32 copies, used only to rank columns
+    float pad0, pad1;
+};
+
 struct PlaceParams {
-    int M, N;            // valid SNV rows / valid clade rows
-    int M_pad, N_pad;    // padded to BLOCK_M / BLOCK_N
+    int M, N;            // single-group problems: valid SNV rows / valid clade rows (2-CTA kernel)
+    int M_pad, N_pad;    // padded totals over all groups
     int num_k_blocks;
     int num_row_blocks, num_col_tiles;
     int run_len, num_runs, sb_width, num_tasks;
     int l2_hints;              // 1: clade tiles evict-last, genotype tiles evict-first
     int nchunk;                // radix mode: K chunks (accumulators) per tile
     int num_row_pairs, run_len2, num_runs2, num_tasks2;   // 2-CTA kernel: schedule in row-block pairs
-    float a1h, a1l, a0h, a0l;  // log2-unit constants, split so that a?h * count is exact
-    float a1f, a0f;            // plain fp32 copies, used only to rank columns
+    const TaskEntry* tasks;    // [num_tasks], the 1-CTA kernel's schedule
+    const GroupConst* gconst;  // [groups]
     uint2* stats;              // pass 1 out: [num_col_tiles*2][M_pad] {ref counts, sum}
     const uint2* rowref;       // pass 2 in : [M_pad] {ref counts, log2 sum}
     float* colpart;            // pass 2 out: [num_runs][N_pad]
     int* dump;                 // debug     : [M_pad][N_pad][2] raw counts
 };
-
-__host__ __device__ inline void decode_task(const PlaceParams& p, int t, int& j, int& r0, int& r1) {
-    // Tasks are ordered super-block (a group of sb_width column tiles whose slab of
-    // S stays L2 resident) -> run of row blocks -> column tile, so that CTAs that
-    // run concurrently share both the genotype rows and the clade slab in L2.
-    const int per_sb = p.num_runs * p.sb_width;
-    const int nsb_full = p.num_col_tiles / p.sb_width;
-    int sb = t / per_sb;
-    int w = p.sb_width;
-    if (sb >= nsb_full) {
-        sb = nsb_full;
-        w = p.num_col_tiles - nsb_full * p.sb_width;
-    }
-    const int rem = t - sb * per_sb;
-    const int run = rem / w;
-    j = sb * p.sb_width + (rem - run * w);
-    r0 = run * p.run_len;
-    r1 = min(r0 + p.run_len, p.num_row_blocks);
-}
 
 __device__ __forceinline__ float count_to_float(uint32_t c) {
     // exact for 0 <= c < 2^23: plant the integer in the mantissa of 2^23
@@ -170,8 +168,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // ---- epilogue building blocks shared by the 1-CTA and the 2-CTA kernels -------------
 // One tile (this thread's row, its 64-column half) from TMEM.
 template <int PASS, int MODE>
-__device__ __forceinline__ void epilogue_tile(const PlaceParams& p, uint32_t taddr, uint32_t use0, int row, int j, int hh,
-                                              int col0, int n_valid, float (&colacc)[64]) {
+__device__ __forceinline__ void epilogue_tile(const PlaceParams& p, const GroupConst& gc, uint32_t taddr, uint32_t use0, int row,
+                                              int jl, int hh, int col0, int n_valid, float (&colacc)[64]) {
     float f1[32], f0[32];
     if (PASS == PASS_DUMP) {
 #pragma unroll
@@ -197,7 +195,7 @@ __device__ __forceinline__ void epilogue_tile(const PlaceParams& p, uint32_t tad
             float cm = -INFINITY, c1 = 0.f, c0 = 0.f;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                const float v = fmaf(p.a1f, f1[i], p.a0f * f0[i]);
+                const float v = fmaf(gc.a1f, f1[i], gc.a0f * f0[i]);
                 const bool take = (i < nv) && (v > cm);
                 cm = take ? v : cm;
                 c1 = take ? f1[i] : c1;
@@ -206,7 +204,7 @@ __device__ __forceinline__ void epilogue_tile(const PlaceParams& p, uint32_t tad
             if (cm > refv + 16.0f) {
                 if (refv != -INFINITY) {
                     const float e1 = b1 - c1, e0 = b0 - c0;
-                    sum *= ex2_approx(fmaf(p.a1h, e1, p.a0h * e0) + fmaf(p.a1l, e1, p.a0l * e0));
+                    sum *= ex2_approx(fmaf(gc.a1h, e1, gc.a0h * e0) + fmaf(gc.a1l, e1, gc.a0l * e0));
                 }
                 b1 = c1;
                 b0 = c0;
@@ -217,8 +215,8 @@ __device__ __forceinline__ void epilogue_tile(const PlaceParams& p, uint32_t tad
                 for (int i = 0; i < 32; ++i) {
                     const float e1 = f1[i] - b1;
                     const float e0 = f0[i] - b0;
-                    const float sdiff = fmaf(p.a1h, e1, p.a0h * e0);   // exact operands, one rounding
-                    const float lo = fmaf(p.a1l, e1, p.a0l * e0);
+                    const float sdiff = fmaf(gc.a1h, e1, gc.a0h * e0);   // exact operands, one rounding
+                    const float lo = fmaf(gc.a1l, e1, gc.a0l * e0);
                     sum += ex2_approx(sdiff + lo);
                 }
             } else {
@@ -226,14 +224,14 @@ __device__ __forceinline__ void epilogue_tile(const PlaceParams& p, uint32_t tad
                 for (int i = 0; i < 32; ++i) {
                     const float e1 = f1[i] - b1;
                     const float e0 = f0[i] - b0;
-                    const float sdiff = fmaf(p.a1h, e1, p.a0h * e0);
-                    const float lo = fmaf(p.a1l, e1, p.a0l * e0);
+                    const float sdiff = fmaf(gc.a1h, e1, gc.a0h * e0);
+                    const float lo = fmaf(gc.a1l, e1, gc.a0l * e0);
                     sum += (i < nv) ? ex2_approx(sdiff + lo) : 0.f;
                 }
             }
         }
         const uint32_t pk = uint32_t(b1) | (uint32_t(b0) << 16);
-        p.stats[size_t(j * 2 + hh) * p.M_pad + row] = make_uint2(pk, __float_as_uint(sum));
+        p.stats[size_t(jl * 2 + hh) * p.M_pad + row] = make_uint2(pk, __float_as_uint(sum));
     } else {
         const uint2 rr = p.rowref[row];
         const float r1f = float(rr.x & 0xFFFFu);
@@ -246,9 +244,9 @@ __device__ __forceinline__ void epilogue_tile(const PlaceParams& p, uint32_t tad
             for (int i = 0; i < 32; ++i) {
                 const float e1 = f1[i] - r1f;
                 const float e0 = f0[i] - r0f;
-                const float sdiff = fmaf(p.a1h, e1, p.a0h * e0);
-                const float tl = fmaf(p.a0l, e0, -L);
-                const float lo = fmaf(p.a1l, e1, tl);
+                const float sdiff = fmaf(gc.a1h, e1, gc.a0h * e0);
+                const float tl = fmaf(gc.a0l, e0, -L);
+                const float lo = fmaf(gc.a1l, e1, tl);
                 colacc[ch * 32 + i] += ex2_approx(sdiff + lo);
             }
         }
@@ -335,8 +333,7 @@ scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constan
             const uint64_t pol_x = p.l2_hints ? ptx::L2_EVICT_FIRST : ptx::L2_EVICT_NORMAL;
             const uint64_t pol_s = p.l2_hints ? ptx::L2_EVICT_LAST : ptx::L2_EVICT_NORMAL;
             for (int t = blockIdx.x; t < p.num_tasks; t += gridDim.x) {
-                int j, r0, r1;
-                decode_task(p, t, j, r0, r1);
+                const int j = p.tasks[t].j, r0 = p.tasks[t].r0, r1 = p.tasks[t].r1;
                 for (int r = r0; r < r1; ++r) {
                     for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -364,8 +361,7 @@ scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constan
             const int spt = MODE == MODE_PLANES ? 2 : p.nchunk;   // slots per tile
             uint32_t tile_n = 0;                                   // tiles issued by this CTA
             for (int t = blockIdx.x; t < p.num_tasks; t += gridDim.x) {
-                int j, r0, r1;
-                decode_task(p, t, j, r0, r1);
+                const int r0 = p.tasks[t].r0, r1 = p.tasks[t].r1;
                 for (int r = r0; r < r1; ++r, ++tile_n) {
                     const uint32_t use0 = tile_n * spt;            // running slot-use counter
                     if (MODE == MODE_PLANES) {
@@ -427,10 +423,11 @@ scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constan
         const int spt = MODE == MODE_PLANES ? 2 : p.nchunk;
         uint32_t tile_n = 0;
         for (int t = blockIdx.x; t < p.num_tasks; t += gridDim.x) {
-            int j, r0, r1;
-            decode_task(p, t, j, r0, r1);
+            const TaskEntry te = p.tasks[t];
+            const GroupConst gc = p.gconst[te.group];
+            const int j = te.j, r0 = te.r0, r1 = te.r1;
             const int col0 = j * BLOCK_N + hh * 64;
-            const int n_valid = max(0, min(64, p.N - col0));
+            const int n_valid = max(0, min(64, te.nvalid - hh * 64));
             float colacc[64];
             if (PASS == PASS_COLSUM) {
 #pragma unroll
@@ -442,14 +439,14 @@ scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constan
                 const int row = r * BLOCK_M + q * 32 + lane;
                 const uint32_t use0 = tile_n * spt;
                 const uint32_t taddr = tmem_base + lane_base + hh * 64;
-                epilogue_tile<PASS, MODE>(p, taddr, use0, row, j, hh, col0, n_valid, colacc);
+                epilogue_tile<PASS, MODE>(p, gc, taddr, use0, row, te.jl, hh, col0, n_valid, colacc);
                 // this tile's slots are drained: hand them back to the MMA warp
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0)
                     for (int c = 0; c < spt; ++c) ptx::mbar_arrive(&sempty_bar[(use0 + c) & 3]);
             }
-            if (PASS == PASS_COLSUM) epilogue_flush_columns(p, red, colacc, q, hh, lane, r0 / p.run_len, j);
+            if (PASS == PASS_COLSUM) epilogue_flush_columns(p, red, colacc, q, hh, lane, te.run_local, j);
         }
     }
 
@@ -612,6 +609,7 @@ scs_place_kernel2(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         for (int t = cluster_id; t < p.num_tasks2; t += num_clusters) {
             int j, q0, q1;
             decode_task2(p, t, j, q0, q1);
+            const GroupConst gc = p.gconst[0];          // the 2-CTA kernel handles single-group plans only
             const int col0 = j * BLOCK_N + hh * 64;
             const int n_valid = max(0, min(64, p.N - col0));
             float colacc[64];
@@ -625,7 +623,7 @@ scs_place_kernel2(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 const int row = (2 * q + int(rank)) * BLOCK_M + q4 * 32 + lane;
                 const uint32_t use0 = tile_n * spt;
                 const uint32_t taddr = tmem_base + lane_base + hh * 64;
-                epilogue_tile<PASS, MODE_RADIX>(p, taddr, use0, row, j, hh, col0, n_valid, colacc);
+                epilogue_tile<PASS, MODE_RADIX>(p, gc, taddr, use0, row, j, hh, col0, n_valid, colacc);
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0)
@@ -646,16 +644,30 @@ scs_place_kernel2(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 }
 
 // ------------------------------------------------------- operand expansion
+// Row geometry of a (possibly multi-group) plan: every group's SNVs are padded to whole
+// 256-row units in the operand planes; group_of_unit[u] says whose rows unit u holds.
+struct RowMap {
+    const int* group_of_unit;       // [M_pad / 256]
+    const long long* group_row0;    // [G] first padded (operand) row of the group
+    const long long* group_src0;    // [G] first row of the group in the caller's packed matrix
+    const int* group_nsnv;          // [G]
+};
+
 // 2-bit genotype codes (0 wild type, 1 het, 2 hom, 3 missing; 4 cells per byte,
 // cell c in bits [2*(c%4), +2)) -> 0/1 byte plane(s), K-major, zero padded.  One thread
-// turns 16 cells (one 32-bit word of codes) into one 16-byte store per plane.
-__global__ void scs_expand_genotypes_kernel(const uint8_t* __restrict__ gt, int64_t gt_pitch, int64_t M, int n_cells,
+// turns 16 cells (one 32-bit word of codes) into one 16-byte store per plane.  Padding rows
+// of the planes are never written (they were zeroed when the plan was created).
+__global__ void scs_expand_genotypes_kernel(const uint8_t* __restrict__ gt, int64_t gt_pitch, int64_t M_pad, int n_cells, RowMap rm,
                                             uint8_t* __restrict__ x1, uint8_t* __restrict__ x0, int K_pad, int radix) {
     const int kq = blockIdx.x * blockDim.x + threadIdx.x;  // group of 16 cells
     if (kq * 16 >= K_pad) return;
-    for (int64_t row = blockIdx.y; row < M; row += gridDim.y) {
+    for (int64_t row = blockIdx.y; row < M_pad; row += gridDim.y) {
+        const int g = rm.group_of_unit[row >> 8];
+        const int64_t local = row - rm.group_row0[g];
+        if (local >= rm.group_nsnv[g]) continue;
+        const int64_t src = rm.group_src0[g] + local;
         uint32_t w = 0;
-        if (kq * 4 < gt_pitch && kq * 16 < n_cells) w = *reinterpret_cast<const uint32_t*>(gt + row * gt_pitch + kq * 4);
+        if (kq * 4 < gt_pitch && kq * 16 < n_cells) w = *reinterpret_cast<const uint32_t*>(gt + src * gt_pitch + kq * 4);
         uint32_t o1[4] = {0, 0, 0, 0}, o0[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -674,37 +686,43 @@ __global__ void scs_expand_genotypes_kernel(const uint8_t* __restrict__ gt, int6
     }
 }
 
-// clade bit mask [N][words] (bit c%32 of word c/32 set when cell c is below the
-// node) -> 0/1 byte matrix, K-major, zero padded.
-__global__ void scs_expand_clades_kernel(const uint32_t* __restrict__ bits, int64_t pitch_words, int N, int n_cells,
-                                         uint8_t* __restrict__ s, int K_pad, uint32_t one) {
+// clade bit masks [G * n_rows][words] (bit c%32 of word c/32 set when cell c is below the
+// node) -> 0/1 byte matrix, K-major; group g's rows start at operand row g * N_pad1.
+__global__ void scs_expand_clades_kernel(const uint32_t* __restrict__ bits, int64_t pitch_words, int64_t total_rows, int n_rows,
+                                         int N_pad1, int n_cells, uint8_t* __restrict__ s, int K_pad, uint32_t one) {
     const int kq = blockIdx.x * blockDim.x + threadIdx.x;
-    const int row = blockIdx.y;
-    if (kq * 4 >= K_pad || row >= N) return;
-    uint32_t o = 0;
-    if (kq * 4 < n_cells) {
-        const uint32_t w = bits[size_t(row) * pitch_words + (kq >> 3)] >> ((kq & 7) * 4);
+    if (kq * 4 >= K_pad) return;
+    for (int64_t src = blockIdx.y; src < total_rows; src += gridDim.y) {
+        const int64_t g = src / n_rows;
+        const int64_t row = g * N_pad1 + (src - g * n_rows);
+        uint32_t o = 0;
+        if (kq * 4 < n_cells) {
+            const uint32_t w = bits[src * pitch_words + (kq >> 3)] >> ((kq & 7) * 4);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const bool in = kq * 4 + i < n_cells;
-            o |= ((in && ((w >> i) & 1u)) ? one : 0u) << (8 * i);
+            for (int i = 0; i < 4; ++i) {
+                const bool in = kq * 4 + i < n_cells;
+                o |= ((in && ((w >> i) & 1u)) ? one : 0u) << (8 * i);
+            }
         }
+        *reinterpret_cast<uint32_t*>(s + row * K_pad + kq * 4) = o;
     }
-    *reinterpret_cast<uint32_t*>(s + size_t(row) * K_pad + kq * 4) = o;
 }
 
 // ------------------------------------------------------------ small kernels
 // Merge the per-(row, half tile) partials of pass 1 into one record per SNV:
 // the reference counts of the globally best column and log2 sum_b 2^(logit-ref).
-__global__ void scs_merge_stats_kernel(const uint2* __restrict__ stats, int num_parts, int M, int M_pad,
-                                       const uint8_t* __restrict__ row_keep, double a1, double a0,
+__global__ void scs_merge_stats_kernel(const uint2* __restrict__ stats, int num_parts, int64_t M_pad, RowMap rm,
+                                       const uint8_t* __restrict__ row_keep, const double2* __restrict__ gconst_d,
                                        uint2* __restrict__ rowref) {
-    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (row >= M_pad) return;
-    if (row >= M || (row_keep != nullptr && row_keep[row] == 0)) {
+    const int g = rm.group_of_unit[row >> 8];
+    const int64_t local = row - rm.group_row0[g];
+    if (local >= rm.group_nsnv[g] || (row_keep != nullptr && row_keep[rm.group_src0[g] + local] == 0)) {
         rowref[row] = make_uint2(0u, __float_as_uint(INFINITY));  // 2^(x - inf) = 0: row contributes nothing
         return;
     }
+    const double a1 = gconst_d[g].x, a0 = gconst_d[g].y;
     double best = -1e300;
     uint32_t best_pk = 0;
     for (int s = 0; s < num_parts; ++s) {
@@ -729,14 +747,17 @@ __global__ void scs_merge_stats_kernel(const uint2* __restrict__ stats, int num_
     rowref[row] = make_uint2(best_pk, __float_as_uint(float(log2(total))));
 }
 
-// Y[b] = sum over runs of the per-run column partials, in a fixed order, in fp64.
-__global__ void scs_reduce_colpart_kernel(const float* __restrict__ colpart, int num_runs, int N, int N_pad,
-                                          double* __restrict__ y) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= N) return;
+// Y[g][b] = sum over the group's runs of the per-run column partials, fixed order, fp64.
+__global__ void scs_reduce_colpart_kernel(const float* __restrict__ colpart, const int* __restrict__ group_runs, int64_t total_rows,
+                                          int n_rows, int N_pad1, int64_t N_pad, double* __restrict__ y) {
+    const int64_t o = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;   // index into the compact [G][n_rows] output
+    if (o >= total_rows) return;
+    const int64_t g = o / n_rows;
+    const int64_t col = g * N_pad1 + (o - g * n_rows);
+    const int runs = group_runs[g];
     double acc = 0.0;
-    for (int r = 0; r < num_runs; ++r) acc += double(colpart[size_t(r) * N_pad + b]);
-    y[b] = acc;
+    for (int r = 0; r < runs; ++r) acc += double(colpart[size_t(r) * N_pad + col]);
+    y[o] = acc;
 }
 
 // ---------------------------------------------------------------- host side
@@ -792,9 +813,22 @@ static void set_place_smem() {
 
 struct Placement {
     scs_ctx* ctx = nullptr;
-    int64_t n_snv = 0;
-    int n_cells = 0, n_rows = 0;
-    int M_pad = 0, N_pad = 0, K_pad = 0;
+    int n_groups = 1;
+    int64_t n_snv = 0;            // total over groups
+    int n_cells = 0, n_rows = 0;  // per group
+    int64_t M_pad = 0, N_pad = 0;
+    int K_pad = 0, N_pad1 = 0;
+    std::vector<int64_t> g_nsnv, g_row0, g_src0;
+    std::vector<int> g_runs;
+    // device tables
+    int* d_group_of_unit = nullptr;
+    long long *d_group_row0 = nullptr, *d_group_src0 = nullptr;
+    int *d_group_nsnv = nullptr, *d_group_runs = nullptr;
+    TaskEntry* d_tasks = nullptr;
+    GroupConst* d_gconst = nullptr;
+    double2* d_gconst_d = nullptr;
+    RowMap rowmap;
+    int num_parts = 0;
     uint8_t *x1 = nullptr, *x0 = nullptr, *s = nullptr;
     uint8_t* row_keep = nullptr;  // optional, device
     bool have_row_keep = false;
@@ -841,27 +875,44 @@ using namespace scs;
 extern "C" {
 
 int scs_placement_create(scs_ctx* ctx, int64_t n_snv, int32_t n_cells, int32_t n_rows, scs_placement** out) {
-    if (!ctx || !out) return set_error(SCS_ERR_ARG, "null argument");
-    if (n_snv <= 0 || n_cells <= 0 || n_rows <= 0) return set_error(SCS_ERR_ARG, "empty problem (n_snv=%lld n_cells=%d n_rows=%d)", (long long)n_snv, n_cells, n_rows);
+    return scs_placement_create_batch(ctx, 1, &n_snv, n_cells, n_rows, out);
+}
+
+int scs_placement_create_batch(scs_ctx* ctx, int32_t n_groups, const int64_t* n_snv_g, int32_t n_cells, int32_t n_rows,
+                               scs_placement** out) {
+    if (!ctx || !out || !n_snv_g) return set_error(SCS_ERR_ARG, "null argument");
+    if (n_groups <= 0 || n_cells <= 0 || n_rows <= 0) return set_error(SCS_ERR_ARG, "empty problem (groups=%d n_cells=%d n_rows=%d)", n_groups, n_cells, n_rows);
     if (n_cells > 65535) return set_error(SCS_ERR_ARG, "n_cells %d exceeds the 16-bit count packing (65535)", n_cells);
-    if (n_snv > (int64_t(1) << 30)) return set_error(SCS_ERR_ARG, "n_snv too large for one placement plan; shard by SNV rows");
+    int64_t total = 0, m_pad = 0;
+    for (int g = 0; g < n_groups; ++g) {
+        if (n_snv_g[g] <= 0) return set_error(SCS_ERR_ARG, "group %d has no SNVs", g);
+        total += n_snv_g[g];
+        m_pad += (n_snv_g[g] + 2 * BLOCK_M - 1) / (2 * BLOCK_M) * (2 * BLOCK_M);
+    }
+    if (m_pad > (int64_t(1) << 30)) return set_error(SCS_ERR_ARG, "too many SNV rows for one placement plan; shard by SNV rows / replicates");
     SCS_CUDA(cudaSetDevice(ctx->device));
     Placement* pl = new Placement();
     pl->ctx = ctx;
-    pl->n_snv = n_snv;
+    pl->n_groups = n_groups;
+    pl->n_snv = total;
     pl->n_cells = n_cells;
     pl->n_rows = n_rows;
-    pl->M_pad = round_up(n_snv, 2 * BLOCK_M);     // row-block pairs for the 2-CTA kernel
-    pl->N_pad = round_up(n_rows, BLOCK_N);
+    pl->M_pad = m_pad;                               // every group padded to row-block pairs (2-CTA kernel)
+    pl->N_pad1 = round_up(n_rows, BLOCK_N);
+    pl->N_pad = int64_t(pl->N_pad1) * n_groups;
     pl->K_pad = round_up(n_cells, BLOCK_K);
+    if (pl->N_pad > (int64_t(1) << 30)) {
+        delete pl;
+        return set_error(SCS_ERR_ARG, "too many clade rows for one placement plan");
+    }
     const size_t plane = size_t(pl->M_pad) * pl->K_pad;
     const size_t sbytes = size_t(pl->N_pad) * pl->K_pad;
     PlaceParams& p = pl->prm;
     memset(&p, 0, sizeof(p));
-    p.M = int(n_snv);
+    p.M = int(n_snv_g[0]);
     p.N = n_rows;
-    p.M_pad = pl->M_pad;
-    p.N_pad = pl->N_pad;
+    p.M_pad = int(pl->M_pad);
+    p.N_pad = int(pl->N_pad);
     p.num_k_blocks = pl->K_pad / BLOCK_K;
     // Operand mode: radix packing halves the tensor work but needs K <= 4 chunks of 3968 cells.
     {
@@ -874,8 +925,10 @@ int scs_placement_create(scs_ctx* ctx, int64_t n_snv, int32_t n_cells, int32_t n
         pl->mode = mode;
         p.nchunk = mode == MODE_RADIX ? nchunk : 1;
     }
-    p.num_row_blocks = pl->M_pad / BLOCK_M;
-    p.num_col_tiles = pl->N_pad / BLOCK_N;
+    p.num_row_blocks = int(pl->M_pad / BLOCK_M);
+    p.num_col_tiles = int(pl->N_pad / BLOCK_N);
+    const int ct1 = pl->N_pad1 / BLOCK_N;           // column tiles per group
+    pl->num_parts = 2 * ct1;
     // Super-block: the w column tiles whose clade slab the concurrently running CTAs share.
     // With sm_count CTAs in flight the live L2 footprint is  w * slab + (sm_count / w) * 2 planes
     // * rows, smallest near w ~ sqrt(sm_count).  B200's L2 is two ~63 MB halves that replicate
@@ -885,19 +938,57 @@ int scs_placement_create(scs_ctx* ctx, int64_t n_snv, int32_t n_cells, int32_t n
     const size_t slab = size_t(BLOCK_N) * pl->K_pad;
     int sbw = std::max(1, int(std::lround(std::sqrt(double(ctx->sm_count)))));
     if (const char* e = getenv("SCS_SLAB_MB")) sbw = int(std::max<size_t>(1, (size_t(std::max(1, atoi(e))) << 20) / slab));
-    p.sb_width = std::min(sbw, p.num_col_tiles);
+    p.sb_width = std::min(sbw, ct1);
     p.l2_hints = 1;
     if (const char* e = getenv("SCS_L2_HINTS")) p.l2_hints = atoi(e) != 0;
     // Runs: long enough to amortise the end-of-run column reduction, short enough
     // that every SM gets several tasks.
     int run_len = 32;
     if (const char* e = getenv("SCS_RUN_LEN")) run_len = std::max(1, atoi(e));
-    while (run_len > 1 && (int64_t(p.num_row_blocks + run_len - 1) / run_len) * p.num_col_tiles < 4 * ctx->sm_count) run_len >>= 1;
+    while (run_len > 1 && (int64_t(p.num_row_blocks + run_len - 1) / run_len) * ct1 < 4 * ctx->sm_count) run_len >>= 1;
     p.run_len = run_len;
-    p.num_runs = (p.num_row_blocks + run_len - 1) / run_len;
-    p.num_tasks = p.num_runs * p.num_col_tiles;
+
+    // ---- the task table: group -> super-block -> run -> column tile
+    std::vector<TaskEntry> tasks;
+    std::vector<int> unit_group(size_t(pl->M_pad / (2 * BLOCK_M)));
+    pl->g_nsnv.assign(n_snv_g, n_snv_g + n_groups);
+    pl->g_row0.resize(n_groups);
+    pl->g_src0.resize(n_groups);
+    pl->g_runs.resize(n_groups);
+    int64_t row0 = 0, src0 = 0;
+    int max_runs = 0;
+    for (int g = 0; g < n_groups; ++g) {
+        const int64_t rows_pad = (n_snv_g[g] + 2 * BLOCK_M - 1) / (2 * BLOCK_M) * (2 * BLOCK_M);
+        pl->g_row0[g] = row0;
+        pl->g_src0[g] = src0;
+        for (int64_t u = row0 / (2 * BLOCK_M); u < (row0 + rows_pad) / (2 * BLOCK_M); ++u) unit_group[size_t(u)] = g;
+        const int rb0 = int(row0 / BLOCK_M), rbn = int(rows_pad / BLOCK_M);
+        const int runs = (rbn + run_len - 1) / run_len;
+        pl->g_runs[g] = runs;
+        max_runs = std::max(max_runs, runs);
+        for (int sb0 = 0; sb0 < ct1; sb0 += p.sb_width) {
+            const int w = std::min(p.sb_width, ct1 - sb0);
+            for (int run = 0; run < runs; ++run)
+                for (int jj = 0; jj < w; ++jj) {
+                    TaskEntry te;
+                    te.jl = sb0 + jj;
+                    te.j = g * ct1 + te.jl;
+                    te.r0 = rb0 + run * run_len;
+                    te.r1 = rb0 + std::min(rbn, (run + 1) * run_len);
+                    te.run_local = run;
+                    te.nvalid = std::max(0, std::min(BLOCK_N, n_rows - te.jl * BLOCK_N));
+                    te.group = g;
+                    te.pad = 0;
+                    tasks.push_back(te);
+                }
+        }
+        row0 += rows_pad;
+        src0 += n_snv_g[g];
+    }
+    p.num_runs = max_runs;
+    p.num_tasks = int(tasks.size());
     pl->grid = std::min(ctx->sm_count, p.num_tasks);
-    // 2-CTA schedule: the same tasks, in units of row-block pairs
+    // 2-CTA schedule (single-group plans only): the same tasks, in units of row-block pairs
     p.num_row_pairs = p.num_row_blocks / 2;
     p.run_len2 = std::max(1, run_len / 2);
     p.num_runs2 = (p.num_row_pairs + p.run_len2 - 1) / p.run_len2;
@@ -908,29 +999,56 @@ int scs_placement_create(scs_ctx* ctx, int64_t n_snv, int32_t n_cells, int32_t n
     // 1 kW cap (169 ms @1522 MHz vs 140 ms @1815 MHz; profiles/r01_pair_vs_single.txt).  The
     // 1-CTA kernel already runs at 98.6 % of twice the measured sustained cuBLAS bf16 rate.
     pl->pair = false;
-    if (const char* e = getenv("SCS_PLACE_PAIR")) pl->pair = pl->mode == MODE_RADIX && atoi(e) != 0;
-    pl->colpart_rows = std::max(p.num_runs, 2 * p.num_runs2);
+    if (const char* e = getenv("SCS_PLACE_PAIR")) pl->pair = pl->mode == MODE_RADIX && n_groups == 1 && atoi(e) != 0;
+    pl->colpart_rows = std::max(max_runs, 2 * p.num_runs2 * (n_groups == 1 ? 1 : 0));
 
     int rc = SCS_OK;
     do {
-        if (cudaMalloc(&pl->x1, plane) != cudaSuccess || cudaMalloc(&pl->x0, plane) != cudaSuccess ||
+        std::vector<long long> row0v(pl->g_row0.begin(), pl->g_row0.end()), src0v(pl->g_src0.begin(), pl->g_src0.end());
+        std::vector<int> nsnvv(n_groups);
+        for (int g = 0; g < n_groups; ++g) nsnvv[g] = int(n_snv_g[g]);
+        if (cudaMalloc(&pl->x1, plane) != cudaSuccess || (pl->mode == MODE_PLANES && cudaMalloc(&pl->x0, plane) != cudaSuccess) ||
             cudaMalloc(&pl->s, sbytes) != cudaSuccess ||
-            cudaMalloc(&pl->stats, size_t(p.num_col_tiles) * 2 * pl->M_pad * sizeof(uint2)) != cudaSuccess ||
+            cudaMalloc(&pl->stats, size_t(pl->num_parts) * pl->M_pad * sizeof(uint2)) != cudaSuccess ||
             cudaMalloc(&pl->rowref, size_t(pl->M_pad) * sizeof(uint2)) != cudaSuccess ||
             cudaMalloc(&pl->colpart, size_t(pl->colpart_rows) * pl->N_pad * sizeof(float)) != cudaSuccess ||
-            cudaMalloc(&pl->y, size_t(pl->N_pad) * sizeof(double)) != cudaSuccess ||
-            cudaMalloc(&pl->row_keep, size_t(pl->M_pad)) != cudaSuccess) {
+            cudaMalloc(&pl->y, size_t(n_groups) * n_rows * sizeof(double)) != cudaSuccess ||
+            cudaMalloc(&pl->row_keep, size_t(total)) != cudaSuccess ||
+            cudaMalloc(&pl->d_group_of_unit, unit_group.size() * sizeof(int)) != cudaSuccess ||
+            cudaMalloc(&pl->d_group_row0, size_t(n_groups) * sizeof(long long)) != cudaSuccess ||
+            cudaMalloc(&pl->d_group_src0, size_t(n_groups) * sizeof(long long)) != cudaSuccess ||
+            cudaMalloc(&pl->d_group_nsnv, size_t(n_groups) * sizeof(int)) != cudaSuccess ||
+            cudaMalloc(&pl->d_group_runs, size_t(n_groups) * sizeof(int)) != cudaSuccess ||
+            cudaMalloc(&pl->d_tasks, tasks.size() * sizeof(TaskEntry)) != cudaSuccess ||
+            cudaMalloc(&pl->d_gconst, size_t(n_groups) * sizeof(GroupConst)) != cudaSuccess ||
+            cudaMalloc(&pl->d_gconst_d, size_t(n_groups) * sizeof(double2)) != cudaSuccess) {
             rc = set_error(SCS_ERR_OOM, "device allocation failed for placement plan (%s)", cudaGetErrorString(cudaGetLastError()));
             break;
         }
         cudaMemset(pl->x1, 0, plane);
-        cudaMemset(pl->x0, 0, plane);
+        if (pl->x0) cudaMemset(pl->x0, 0, plane);
         cudaMemset(pl->s, 0, sbytes);
+        cudaMemcpy(pl->d_group_of_unit, unit_group.data(), unit_group.size() * sizeof(int), cudaMemcpyHostToDevice);
+        cudaMemcpy(pl->d_group_row0, row0v.data(), size_t(n_groups) * sizeof(long long), cudaMemcpyHostToDevice);
+        cudaMemcpy(pl->d_group_src0, src0v.data(), size_t(n_groups) * sizeof(long long), cudaMemcpyHostToDevice);
+        cudaMemcpy(pl->d_group_nsnv, nsnvv.data(), size_t(n_groups) * sizeof(int), cudaMemcpyHostToDevice);
+        cudaMemcpy(pl->d_group_runs, pl->g_runs.data(), size_t(n_groups) * sizeof(int), cudaMemcpyHostToDevice);
+        cudaMemcpy(pl->d_tasks, tasks.data(), tasks.size() * sizeof(TaskEntry), cudaMemcpyHostToDevice);
+        pl->rowmap.group_of_unit = pl->d_group_of_unit;
+        pl->rowmap.group_row0 = pl->d_group_row0;
+        pl->rowmap.group_src0 = pl->d_group_src0;
+        pl->rowmap.group_nsnv = pl->d_group_nsnv;
         p.stats = pl->stats;
         p.rowref = pl->rowref;
         p.colpart = pl->colpart;
+        p.tasks = pl->d_tasks;
+        p.gconst = pl->d_gconst;
         if ((rc = make_u8_tmap(&pl->tm_x1, pl->x1, pl->M_pad, pl->K_pad, BLOCK_M)) != SCS_OK) break;
-        if ((rc = make_u8_tmap(&pl->tm_x0, pl->x0, pl->M_pad, pl->K_pad, BLOCK_M)) != SCS_OK) break;
+        if (pl->x0) {
+            if ((rc = make_u8_tmap(&pl->tm_x0, pl->x0, pl->M_pad, pl->K_pad, BLOCK_M)) != SCS_OK) break;
+        } else {
+            pl->tm_x0 = pl->tm_x1;
+        }
         if ((rc = make_u8_tmap(&pl->tm_s, pl->s, pl->N_pad, pl->K_pad, BLOCK_N)) != SCS_OK) break;
         if ((rc = make_u8_tmap(&pl->tm_s64, pl->s, pl->N_pad, pl->K_pad, BLOCK_N / 2)) != SCS_OK) break;
         set_place_smem<PASS_DUMP>();
@@ -965,6 +1083,14 @@ int scs_placement_destroy(scs_placement* h) {
     cudaFree(pl->dump);
     cudaFree(pl->stage_gt);
     cudaFree(pl->stage_mask);
+    cudaFree(pl->d_group_of_unit);
+    cudaFree(pl->d_group_row0);
+    cudaFree(pl->d_group_src0);
+    cudaFree(pl->d_group_nsnv);
+    cudaFree(pl->d_group_runs);
+    cudaFree(pl->d_tasks);
+    cudaFree(pl->d_gconst);
+    cudaFree(pl->d_gconst_d);
     for (int i = 0; i < 5; ++i)
         if (pl->ev[i]) cudaEventDestroy(pl->ev[i]);
     delete pl;
@@ -977,8 +1103,8 @@ int scs_placement_set_genotypes(scs_placement* h, const uint8_t* d_gt, int64_t p
     if (pitch_bytes < (pl->n_cells + 3) / 4) return set_error(SCS_ERR_ARG, "genotype row pitch %lld is smaller than ceil(n_cells/4)", (long long)pitch_bytes);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if ((pitch_bytes & 3) || (reinterpret_cast<uintptr_t>(d_gt) & 3)) return set_error(SCS_ERR_ARG, "packed genotype rows must be 4-byte aligned (pitch %lld)", (long long)pitch_bytes);
-    dim3 block(128), grid((pl->K_pad / 16 + 127) / 128, unsigned(std::min<int64_t>(pl->n_snv, 16384)));
-    scs_expand_genotypes_kernel<<<grid, block, 0, st>>>(d_gt, pitch_bytes, pl->n_snv, pl->n_cells, pl->x1, pl->x0, pl->K_pad,
+    dim3 block(128), grid((pl->K_pad / 16 + 127) / 128, unsigned(std::min<int64_t>(pl->M_pad, 16384)));
+    scs_expand_genotypes_kernel<<<grid, block, 0, st>>>(d_gt, pitch_bytes, pl->M_pad, pl->n_cells, pl->rowmap, pl->x1, pl->x0, pl->K_pad,
                                                          pl->mode == MODE_RADIX);
     pl->launches++;
     if (d_row_keep) {
@@ -996,14 +1122,11 @@ int scs_placement_set_clades(scs_placement* h, const uint32_t* d_bits, int64_t p
     if (!pl || !d_bits) return set_error(SCS_ERR_ARG, "null argument");
     if (pitch_words < (pl->n_cells + 31) / 32) return set_error(SCS_ERR_ARG, "clade mask pitch %lld is smaller than ceil(n_cells/32)", (long long)pitch_words);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    dim3 block(128), grid((pl->K_pad / 4 + 127) / 128, 1);
-    for (int r0 = 0; r0 < pl->n_rows; r0 += 65535) {
-        const int rows = std::min(65535, pl->n_rows - r0);
-        grid.y = rows;
-        scs_expand_clades_kernel<<<grid, block, 0, st>>>(d_bits + size_t(r0) * pitch_words, pitch_words, rows, pl->n_cells,
-                                                          pl->s + size_t(r0) * pl->K_pad, pl->K_pad, pl->mode == MODE_RADIX ? uint32_t(E5M2_ONE) : 1u);
-        pl->launches++;
-    }
+    const int64_t total_rows = int64_t(pl->n_groups) * pl->n_rows;
+    dim3 block(128), grid((pl->K_pad / 4 + 127) / 128, unsigned(std::min<int64_t>(total_rows, 32768)));
+    scs_expand_clades_kernel<<<grid, block, 0, st>>>(d_bits, pitch_words, total_rows, pl->n_rows, pl->N_pad1, pl->n_cells, pl->s, pl->K_pad,
+                                                      pl->mode == MODE_RADIX ? uint32_t(E5M2_ONE) : 1u);
+    pl->launches++;
     SCS_CUDA(cudaGetLastError());
     return SCS_OK;
 }
@@ -1033,7 +1156,7 @@ int scs_placement_set_clades_host(scs_placement* h, const uint32_t* bits, int64_
     Placement* pl = reinterpret_cast<Placement*>(h);
     if (!pl || !bits) return set_error(SCS_ERR_ARG, "null argument");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const size_t bytes = size_t(pl->n_rows) * pitch_words * 4;
+    const size_t bytes = size_t(pl->n_groups) * pl->n_rows * pitch_words * 4;
     if (bytes > pl->stage_mask_bytes) {
         cudaFree(pl->stage_mask);
         pl->stage_mask = nullptr;
@@ -1045,49 +1168,71 @@ int scs_placement_set_clades_host(scs_placement* h, const uint32_t* bits, int64_
     return scs_placement_set_clades(h, pl->stage_mask, pitch_words, stream);
 }
 
-static void fill_constants(Placement* pl, double FP, double FN, double* a1_out, double* a0_out) {
+static void make_constants(int n_cells, double FP, double FN, GroupConst* gc, double2* gd) {
     const double LOG2E = 1.4426950408889634074;
     const double a1 = (log1p(-FN) - log(FP)) * LOG2E;   // log2((1-FN)/FP)
     const double a0 = (log(FN) - log1p(-FP)) * LOG2E;   // log2(FN/(1-FP))
     int cbits = 1;
-    while ((1 << cbits) <= pl->n_cells) ++cbits;         // counts and their differences fit cbits (+sign)
+    while ((1 << cbits) <= n_cells) ++cbits;             // counts and their differences fit cbits (+sign)
     const int hbits = std::max(4, 24 - cbits);
-    PlaceParams& p = pl->prm;
-    p.a1h = round_to_bits(a1, hbits);
-    p.a0h = round_to_bits(a0, hbits);
-    p.a1l = float(a1 - double(p.a1h));
-    p.a0l = float(a0 - double(p.a0h));
-    p.a1f = float(a1);
-    p.a0f = float(a0);
-    *a1_out = a1;
-    *a0_out = a0;
+    gc->a1h = round_to_bits(a1, hbits);
+    gc->a0h = round_to_bits(a0, hbits);
+    gc->a1l = float(a1 - double(gc->a1h));
+    gc->a0l = float(a0 - double(gc->a0h));
+    gc->a1f = float(a1);
+    gc->a0f = float(a0);
+    gc->pad0 = gc->pad1 = 0.f;
+    gd->x = a1;
+    gd->y = a0;
 }
 
-int scs_placement_run(scs_placement* h, double FP, double FN, double* d_soft_weights, void* stream) {
+// FP / FN: one value per group (per dataset).
+int scs_placement_run_batch(scs_placement* h, const double* FP, const double* FN, double* d_soft_weights, void* stream) {
     Placement* pl = reinterpret_cast<Placement*>(h);
-    if (!pl) return set_error(SCS_ERR_ARG, "null plan");
-    if (!(FP > 0.0 && FP < 1.0 && FN > 0.0 && FN < 1.0)) return set_error(SCS_ERR_ARG, "error rates must lie in (0,1): FP=%g FN=%g", FP, FN);
+    if (!pl || !FP || !FN) return set_error(SCS_ERR_ARG, "null argument");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    double a1, a0;
-    fill_constants(pl, FP, FN, &a1, &a0);
+    std::vector<GroupConst> gc(pl->n_groups);
+    std::vector<double2> gd(pl->n_groups);
+    for (int g = 0; g < pl->n_groups; ++g) {
+        if (!(FP[g] > 0.0 && FP[g] < 1.0 && FN[g] > 0.0 && FN[g] < 1.0))
+            return set_error(SCS_ERR_ARG, "error rates must lie in (0,1): group %d FP=%g FN=%g", g, FP[g], FN[g]);
+        make_constants(pl->n_cells, FP[g], FN[g], &gc[g], &gd[g]);
+    }
+    SCS_CUDA(cudaMemcpyAsync(pl->d_gconst, gc.data(), gc.size() * sizeof(GroupConst), cudaMemcpyHostToDevice, st));
+    SCS_CUDA(cudaMemcpyAsync(pl->d_gconst_d, gd.data(), gd.size() * sizeof(double2), cudaMemcpyHostToDevice, st));
     const PlaceParams& p = pl->prm;
     cudaEventRecord(pl->ev[0], st);
     if (pl->pair) launch_place2<PASS_STATS>(pl->grid2, st, pl->tm_x1, pl->tm_s64, p);
     else launch_place<PASS_STATS>(pl->mode, pl->grid, st, pl->tm_x1, pl->tm_x0, pl->tm_s, p);
     cudaEventRecord(pl->ev[1], st);
-    scs_merge_stats_kernel<<<(p.M_pad + 255) / 256, 256, 0, st>>>(pl->stats, p.num_col_tiles * 2, p.M, p.M_pad,
-                                                                  pl->have_row_keep ? pl->row_keep : nullptr, a1, a0, pl->rowref);
+    scs_merge_stats_kernel<<<unsigned((pl->M_pad + 255) / 256), 256, 0, st>>>(pl->stats, pl->num_parts, pl->M_pad, pl->rowmap,
+                                                                              pl->have_row_keep ? pl->row_keep : nullptr, pl->d_gconst_d,
+                                                                              pl->rowref);
     cudaEventRecord(pl->ev[2], st);
     if (pl->pair) launch_place2<PASS_COLSUM>(pl->grid2, st, pl->tm_x1, pl->tm_s64, p);
     else launch_place<PASS_COLSUM>(pl->mode, pl->grid, st, pl->tm_x1, pl->tm_x0, pl->tm_s, p);
     cudaEventRecord(pl->ev[3], st);
     double* y = d_soft_weights ? d_soft_weights : pl->y;
-    scs_reduce_colpart_kernel<<<(p.N + 255) / 256, 256, 0, st>>>(pl->colpart, pl->pair ? 2 * p.num_runs2 : p.num_runs, p.N, p.N_pad, y);
+    const int64_t total_rows = int64_t(pl->n_groups) * pl->n_rows;
+    if (pl->pair) {
+        // the pair kernel writes 2 * num_runs2 partial rows of the single group
+        const int runs2 = 2 * p.num_runs2;
+        cudaMemcpyAsync(pl->d_group_runs, &runs2, sizeof(int), cudaMemcpyHostToDevice, st);
+    }
+    scs_reduce_colpart_kernel<<<unsigned((total_rows + 255) / 256), 256, 0, st>>>(pl->colpart, pl->d_group_runs, total_rows, pl->n_rows,
+                                                                                  pl->N_pad1, pl->N_pad, y);
     cudaEventRecord(pl->ev[4], st);
     pl->timed = true;
     pl->launches += 4;
     SCS_CUDA(cudaGetLastError());
     return SCS_OK;
+}
+
+int scs_placement_run(scs_placement* h, double FP, double FN, double* d_soft_weights, void* stream) {
+    Placement* pl = reinterpret_cast<Placement*>(h);
+    if (!pl) return set_error(SCS_ERR_ARG, "null plan");
+    std::vector<double> fp(pl->n_groups, FP), fn(pl->n_groups, FN);
+    return scs_placement_run_batch(h, fp.data(), fn.data(), d_soft_weights, stream);
 }
 
 int scs_placement_run_host(scs_placement* h, double FP, double FN, double* soft_weights, void* stream) {
@@ -1096,7 +1241,7 @@ int scs_placement_run_host(scs_placement* h, double FP, double FN, double* soft_
     int rc = scs_placement_run(h, FP, FN, nullptr, stream);
     if (rc != SCS_OK) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    SCS_CUDA(cudaMemcpyAsync(soft_weights, pl->y, size_t(pl->n_rows) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SCS_CUDA(cudaMemcpyAsync(soft_weights, pl->y, size_t(pl->n_groups) * pl->n_rows * sizeof(double), cudaMemcpyDeviceToHost, st));
     SCS_CUDA(cudaStreamSynchronize(st));
     return SCS_OK;
 }
@@ -1106,7 +1251,12 @@ int scs_placement_run_host(scs_placement* h, double FP, double FN, double* soft_
 int scs_placement_debug_counts(scs_placement* h, int32_t* counts_host, void* stream) {
     Placement* pl = reinterpret_cast<Placement*>(h);
     if (!pl || !counts_host) return set_error(SCS_ERR_ARG, "null argument");
+    if (pl->n_groups != 1) return set_error(SCS_ERR_ARG, "the debug count dump is for single-group plans");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    std::vector<GroupConst> gc(1);
+    std::vector<double2> gd(1);
+    make_constants(pl->n_cells, 0.01, 0.1, &gc[0], &gd[0]);     // the dump pass reads no constants; keep the table defined
+    SCS_CUDA(cudaMemcpyAsync(pl->d_gconst, gc.data(), sizeof(GroupConst), cudaMemcpyHostToDevice, st));
     const size_t n = size_t(pl->M_pad) * pl->N_pad * 2;
     if (n > (size_t(1) << 28)) return set_error(SCS_ERR_ARG, "debug count dump is limited to small problems");
     if (!pl->dump && cudaMalloc(&pl->dump, n * sizeof(int)) != cudaSuccess) return set_error(SCS_ERR_OOM, "debug dump allocation failed");
@@ -1127,10 +1277,10 @@ int scs_placement_debug_counts(scs_placement* h, int32_t* counts_host, void* str
 int scs_placement_info(scs_placement* h, int64_t* info, int32_t n) {
     Placement* pl = reinterpret_cast<Placement*>(h);
     if (!pl || !info) return set_error(SCS_ERR_ARG, "null argument");
-    const int64_t v[13] = {pl->M_pad, pl->N_pad, pl->K_pad, pl->prm.num_tasks, pl->prm.run_len, pl->prm.sb_width, pl->pair ? pl->grid2 : pl->grid, pl->launches, pl->prm.num_runs,
+    const int64_t v[14] = {pl->M_pad, pl->N_pad, pl->K_pad, pl->prm.num_tasks, pl->prm.run_len, pl->prm.sb_width, pl->pair ? pl->grid2 : pl->grid, pl->launches, pl->prm.num_runs,
                            pl->pair ? K2_SMEM_TOTAL : (pl->mode == MODE_RADIX ? ModeCfg<MODE_RADIX>::SMEM_TOTAL : ModeCfg<MODE_PLANES>::SMEM_TOTAL),
-                           pl->mode, pl->prm.nchunk, pl->pair ? 1 : 0};
-    for (int i = 0; i < n && i < 13; ++i) info[i] = v[i];
+                           pl->mode, pl->prm.nchunk, pl->pair ? 1 : 0, pl->n_groups};
+    for (int i = 0; i < n && i < 14; ++i) info[i] = v[i];
     return SCS_OK;
 }
 

@@ -106,10 +106,14 @@ class Placement:
     """Device-resident placement plan (scs_placement) for one problem shape."""
 
     def __init__(self, ctx, n_snv, n_cells, n_rows):
+        """``n_snv``: an int (one dataset) or a sequence (a batch of datasets -- simulation
+        replicates -- over the same number of cells, placed block-diagonally in one launch)."""
         self.ctx = ctx
-        self.n_snv, self.n_cells, self.n_rows = int(n_snv), int(n_cells), int(n_rows)
+        self.group_snvs = np.atleast_1d(np.asarray(n_snv, dtype=np.int64)).copy()
+        self.n_groups = int(self.group_snvs.size)
+        self.n_snv, self.n_cells, self.n_rows = int(self.group_snvs.sum()), int(n_cells), int(n_rows)
         h = C.c_void_p()
-        check(lib().scs_placement_create(ctx._h, self.n_snv, self.n_cells, self.n_rows, C.byref(h)))
+        check(lib().scs_placement_create_batch(ctx._h, self.n_groups, ptr(self.group_snvs), self.n_cells, self.n_rows, C.byref(h)))
         self._h = h
 
     def close(self):
@@ -124,10 +128,10 @@ class Placement:
             pass
 
     def info(self):
-        v = (C.c_int64 * 13)()
-        check(lib().scs_placement_info(self._h, v, 13))
+        v = (C.c_int64 * 14)()
+        check(lib().scs_placement_info(self._h, v, 14))
         keys = ("M_pad", "N_pad", "K_pad", "tasks", "run_len", "superblock_width", "grid", "launches", "runs", "smem_bytes",
-                "mode", "k_chunks", "cta_pair")
+                "mode", "k_chunks", "cta_pair", "groups")
         return dict(zip(keys, (int(x) for x in v)))
 
     # host buffers (numpy)
@@ -141,7 +145,7 @@ class Placement:
 
     def set_clades_host(self, bits, words, stream=None):
         bits = np.ascontiguousarray(bits, dtype=np.uint32)
-        assert bits.shape == (self.n_rows, words)
+        assert bits.shape == (self.n_groups * self.n_rows, words)
         check(lib().scs_placement_set_clades_host(self._h, ptr(bits), int(words), _stream_handle(stream)))
 
     # device buffers (torch tensors or raw addresses)
@@ -151,14 +155,26 @@ class Placement:
     def set_clades(self, d_bits, words, stream=None):
         check(lib().scs_placement_set_clades(self._h, _dev_ptr(d_bits), int(words), _stream_handle(stream)))
 
+    def _rates(self, FP, FN):
+        fp = np.ascontiguousarray(np.broadcast_to(np.asarray(FP, dtype=np.float64), (self.n_groups,)))
+        fn = np.ascontiguousarray(np.broadcast_to(np.asarray(FN, dtype=np.float64), (self.n_groups,)))
+        return fp, fn
+
     def run(self, FP, FN, d_out=None, stream=None):
-        """Asynchronous; result in ``d_out`` (device, float64[n_rows]) or in the plan."""
-        check(lib().scs_placement_run(self._h, float(FP), float(FN), _dev_ptr(d_out), _stream_handle(stream)))
+        """Asynchronous; result in ``d_out`` (device, float64[n_groups * n_rows]) or in the plan.
+        ``FP`` / ``FN``: scalars or one value per group."""
+        fp, fn = self._rates(FP, FN)
+        check(lib().scs_placement_run_batch(self._h, ptr(fp), ptr(fn), _dev_ptr(d_out), _stream_handle(stream)))
 
     def run_host(self, FP, FN, stream=None):
-        out = np.empty(self.n_rows, dtype=np.float64)
-        check(lib().scs_placement_run_host(self._h, float(FP), float(FN), ptr(out), _stream_handle(stream)))
-        return out
+        out = np.empty(self.n_groups * self.n_rows, dtype=np.float64)
+        if self.n_groups == 1:
+            check(lib().scs_placement_run_host(self._h, float(np.ravel(FP)[0]), float(np.ravel(FN)[0]), ptr(out), _stream_handle(stream)))
+            return out
+        import torch
+        d = torch.empty(out.size, dtype=torch.float64, device=torch.device("cuda", self.ctx.device))
+        self.run(FP, FN, d, stream=stream)
+        return d.cpu().numpy().reshape(self.n_groups, self.n_rows)
 
     def last_times(self):
         """Device ms of (GEMM pass 1, merge, GEMM pass 2, reduce) of the last run."""

@@ -119,6 +119,44 @@ def test_radix_mode_falls_back_beyond_four_chunks(ctx, monkeypatch):
     pl.close()
 
 
+def test_batched_replicates_match_individual_plans(ctx):
+    """A batch of replicate datasets (own SNVs, own tree, own error rates) placed in one launch
+    per pass gives, group by group, the numbers of the single-dataset plans and of the oracle."""
+    n_cells = 37
+    rng = np.random.default_rng(21)
+    snvs = [300, 1, 129, 1000, 255, 256, 257]
+    rates = [(0.01, 0.1), (0.02, 0.2), (1e-6, 1e-6), (0.05, 0.3), (0.01, 0.1), (0.001, 0.05), (0.03, 0.15)]
+    codes_l, S_l, keep_l = [], [], []
+    for m in snvs:
+        tree = synth.coalescent_tree(n_cells, rng)
+        S_l.append(tree.clade_matrix())
+        c = synth.observe(tree, synth.throw_mutations(tree, m, rng), 0.1, 0.01, 0.2, rng)
+        codes_l.append(c)
+        k = (c == 1).any(axis=1).astype(np.uint8)
+        k[:1] = 1
+        keep_l.append(k)
+    n_rows = S_l[0].shape[0]
+    packed, pitch = engine.pack_genotypes(np.vstack(codes_l))
+    bits, words = engine.pack_clades(np.vstack(S_l))
+    pl = engine.Placement(ctx, snvs, n_cells, n_rows)
+    assert pl.info()["groups"] == len(snvs)
+    pl.set_genotypes_host(packed, pitch, np.concatenate(keep_l))
+    pl.set_clades_host(bits, words)
+    FP = np.array([r[0] for r in rates])
+    FN = np.array([r[1] for r in rates])
+    got = pl.run_host(FP, FN)
+    assert got.shape == (len(snvs), n_rows)
+    for g, m in enumerate(snvs):
+        muts = np.where(codes_l[g] == 3, np.nan, codes_l[g].astype(float))[keep_l[g].astype(bool)]
+        want = O.map_mutations_gt(muts, S_l[g].astype(float), FP[g], FN[g])
+        assert_soft_close(got[g], want)
+        pk, pt = engine.pack_genotypes(codes_l[g])
+        bg, wg = engine.pack_clades(S_l[g])
+        single = engine.map_mutations(ctx, pk, pt, bg, wg, n_cells, FP[g], FN[g], keep_l[g])
+        np.testing.assert_allclose(got[g], single, rtol=0, atol=1e-9 * max(1.0, np.abs(single).max()))
+    pl.close()
+
+
 def test_row_keep_and_extreme_rates(ctx):
     codes, S = make_problem(900, 120, seed=5)
     packed, pitch = engine.pack_genotypes(codes)
