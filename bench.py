@@ -48,6 +48,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--replicates", type=int, default=256,
+                    help="replicate-sweep leg (BASELINE configs[4] shape: 100 cells x 10k SNVs each); 0 disables it")
+    ap.add_argument("--rep-cells", type=int, default=100)
+    ap.add_argument("--rep-snvs", type=int, default=10000)
     return ap.parse_args()
 
 
@@ -175,6 +179,106 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------- replicate-sweep leg
+def replicate_sweep(ctx, dev, rank, world, R, n_cells, n_snv, steps, warmup):
+    """BASELINE configs[4]: many independent (VCF, tree) pairs, sharded over ranks with no
+    communication.  This rank's R replicates are placed block-diagonally in ONE launch per
+    GEMM pass (scs_placement_create_batch) and all R x 10 clock tests are solved in ONE LRT
+    launch.  Timed (CUDA events): row filter + operand expansion + both passes + LRT + result
+    read-back.  Host-side tree bookkeeping (Newick, branch order) is setup, outside the timing;
+    min(R, 32) distinct random trees are cycled over the replicates."""
+    import torch
+    from scsommerclock_b200 import engine, run_PT_test as P, synth
+    n_trees = min(R, 32)
+    names = ["tumcell%05d" % (i + 1) for i in range(n_cells)]
+    columns = names + ["healthycell"]
+    active = np.array([c != "healthycell" for c in columns], dtype=np.uint8)
+    tmp = tempfile.mkdtemp(prefix="scs_rep_")
+    trees, bits_l, childs, gathers = [], [], [], []
+    FP, FN = FP_TRUE, FN_TRUE / 2
+    words = None
+    for k in range(n_trees):
+        ts = make_tree(n_cells, seed=777 + 1000 * rank + k)
+        tf = os.path.join(tmp, "rep%d.newick" % k)
+        with open(tf, "w") as f:
+            f.write(ts.newick(names, "healthycell", scale=0.05))
+        tree, outg, _, _ = P.read_tree(tf, np.array(columns))
+        bits, words, nodes = P._clade_bits(tree, columns, active)
+        # branch order from the topology alone (soft weights all equal -> the reference's tie order)
+        st = {"soft": np.ones(bits.shape[0]), "columns": columns, "bits": bits, "words": words, "weights": {}}
+        P._apply_placement(tree, st)
+        MS_i = {c: MS_TRUE for c in names}
+        per_w_weights = []
+        name_row = {n.name: i for i, n in enumerate(nodes)}
+        for w_max in W_MAXS:
+            P.add_br_weights(tree, FP, FN, MS_i, w_max, _state=st)
+            Y, constr, init, wn, cols = P.get_model_data(tree)
+            per_w_weights.append(wn[:, 0].copy())
+        trees.append((ts, bits, constr.child_int, np.array([name_row[c] for c in cols], dtype=np.int32), per_w_weights))
+    n_rows = trees[0][1].shape[0]
+    n_cols = len(columns)
+    # genotypes of all replicates, concatenated, generated on the device
+    packs = []
+    for r in range(R):
+        ts = trees[r % n_trees][0]
+        lo = torch.as_tensor(ts.lo[:-1], device=dev)
+        hi = torch.as_tensor(ts.hi[:-1], device=dev)
+        rate = torch.as_tensor(ts.branch_len[:-1], device=dev, dtype=torch.float32)
+        pk, pitch, _ = synth.observe_packed_torch(lo, hi, torch.as_tensor(ts.leaf_rank), n_snv, FN_TRUE, FP_TRUE, MS_TRUE, dev,
+                                                  seed=5000 + 100000 * rank + r, rate=rate, extra_cols=1, chunk=n_snv)
+        packs.append(pk)
+    packed = torch.cat(packs, dim=0).contiguous()
+    del packs
+    all_bits = np.concatenate([trees[r % n_trees][1] for r in range(R)], axis=0)
+    plan = engine.Placement(ctx, [n_snv] * R, n_cols, n_rows)
+    plan.set_clades_host(all_bits, words)
+    row_keep = torch.empty(R * n_snv, dtype=torch.uint8, device=dev)
+    y_dev = torch.zeros(R * n_rows, dtype=torch.float64, device=dev)
+    ch_l, w_l, g_l = [], [], []
+    for r in range(R):
+        _, _, child_int, gather, pw = trees[r % n_trees]
+        for wi in range(len(W_MAXS)):
+            ch_l.append(child_int)
+            w_l.append(pw[wi])
+            g_l.append(gather + r * n_rows)
+    lrt = engine.LrtPlan(ctx, ch_l)
+    lrt.set_weights(w_l)
+    lrt.set_gather(np.concatenate(g_l), R * n_rows)
+    out = torch.zeros((R * len(W_MAXS), 8), dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        engine.gt_reduce(ctx, packed, pitch, R * n_snv, n_cols, active, True, row_keep)
+        plan.set_genotypes(packed, pitch, row_keep, stream=stream)
+        plan.run(FP, FN, y_dev, stream=stream)
+        lrt.run(y_dev, out, stream=stream)
+        return out.cpu()
+
+    for _ in range(max(1, warmup)):
+        res = step()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    gemm = []
+    e0.record()
+    for _ in range(steps):
+        res = step()
+        gemm.append(plan.last_times())
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    from scsommerclock_b200 import sharding
+    ms = sharding.max_over_ranks(ms, dev)
+    g = np.array(gemm)
+    r_np = res.numpy()
+    ok = int((r_np[:, 7] == 0).sum())
+    return {"replicates_per_gpu": R, "cells": n_cells, "snvs": n_snv, "w_max_per_replicate": len(W_MAXS), "distinct_trees": n_trees,
+            "ms_per_step": ms, "pt_tests_per_s": R * len(W_MAXS) * world / (ms / 1e3),
+            "placements_per_s": float(R) * n_snv * n_rows * world / (ms / 1e3),
+            "pass1_ms": float(g[:, 0].mean()), "pass2_ms": float(g[:, 2].mean()), "lrt_converged": ok, "lrt_problems": int(r_np.shape[0]),
+            "median_newton_iterations": float(np.median(r_np[:, 6])), "tiling": plan.info()}
+
+
 # ------------------------------------------------------------------ GPU arm
 def main():
     args = parse()
@@ -297,6 +401,7 @@ def main():
 
     sampler = ClockSampler(local) if rank == 0 else None
     ms_total, gemm_times, res, launches = timed(step, args.steps, args.warmup, sampler)
+    plan_info = plan.info()
     ms_step = ms_total / args.steps
     placements = float(n_snv) * n_rows * world
     value = placements / (ms_step / 1e3)
@@ -307,6 +412,14 @@ def main():
         e2e = {"value": placements / (ms_e2e / args.steps / 1e3), "unit": "placements/s",
                "h2d_bytes_per_step": int(packed.numel()) * world, "d2h_bytes_per_step": int(lrt_out.numel() * 8 + n_cols * 4 + 8) * world,
                "ms_per_step": ms_e2e / args.steps}
+
+    rep = None
+    if args.replicates > 0:
+        del pinned
+        plan.close()
+        del packed
+        torch.cuda.empty_cache()
+        rep = replicate_sweep(ctx, dev, rank, world, args.replicates, args.rep_cells, args.rep_snvs, max(2, args.steps), 1)
 
     if rank == 0:
         g = np.array(gemm_times)                         # [steps][pass1, merge, pass2, reduce]
@@ -322,23 +435,24 @@ def main():
             "config": {"workload": "coalescent %d cells x %d SNVs per GPU (BASELINE configs[3]), SNV rows sharded, one all-reduce of the branch weights, LRT for 10 w_max"
                                    % (n_cells, n_snv),
                        "cells": n_cells, "snvs_per_gpu": n_snv, "clade_rows": n_rows, "w_max": W_MAXS, "FN": FN_TRUE, "FP": FP_TRUE, "missing": MS_TRUE,
-                       "l2": "inputs larger than L2 (operand planes %.1f GB per GPU)" % (2.0 * plan.info()["M_pad"] * plan.info()["K_pad"] / 1e9),
-                       "tiling": plan.info()},
+                       "l2": "inputs larger than L2 (operand plane(s) %.1f GB per GPU)" % ((1 if plan_info["mode"] == 1 else 2) * float(plan_info["M_pad"]) * plan_info["K_pad"] / 1e9),
+                       "tiling": plan_info},
             "e2e": e2e,
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES if (n_cells == 10000 and n_snv == 1000000 and plan.info()["mode"] == 1) else None,
+                         "traffic": NCU_TRAFFIC_BYTES if (n_cells == 10000 and n_snv == 1000000 and plan_info["mode"] == 1) else None,
                          "peak_source": pk_kind + " cuBLAS bf16, sustained (kernel timed inside a long step)",
                          "kernel": "scs_place_kernel (%s), avg of pass 1 and pass 2 launches" % (
-                             "tcgen05 kind::f8f6f4, one radix-packed e5m2 plane" if plan.info()["mode"] == 1 else "tcgen05 kind::i8, two u8 planes"),
+                             "tcgen05 kind::f8f6f4, one radix-packed e5m2 plane" if plan_info["mode"] == 1 else "tcgen05 kind::i8, two u8 planes"),
                          "algorithmic_flop_per_launch": flop, "ms_per_launch": t_gemm,
                          "pass1_ms": float(g[:, 0].mean()), "merge_ms": float(g[:, 1].mean()), "pass2_ms": float(g[:, 2].mean()),
                          "reduce_ms": float(g[:, 3].mean()),
-                         "executed_tensor_TOPs": achieved * (1 if plan.info()["mode"] == 1 else 2),
+                         "executed_tensor_TOPs": achieved * (1 if plan_info["mode"] == 1 else 2),
                          "note": "radix mode: one exact FP8 GEMM per contraction (counts packed as C1 + 4096*C0); planes mode: two exact u8 GEMMs"},
             "pt_tests": {"per_step": len(W_MAXS), "LR": [float(v) for v in out[:, 0]], "p_value": [float(v) for v in out[:, 3]],
                          "newton_iterations": [int(v) for v in out[:, 6]], "status": [int(v) for v in out[:, 7]]},
             "clocks": sampler.summary() if sampler else None,
+            "replicate_sweep": rep,
         }
         if world == 1 and not args.no_cpu_baseline:
             S = engine.unpack_clades(bits, n_cols)[:, :n_cells].astype(np.uint8)
