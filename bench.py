@@ -247,16 +247,25 @@ def replicate_sweep(ctx, dev, rank, world, R, n_cells, n_snv, steps, warmup):
     out = torch.zeros((R * len(W_MAXS), 8), dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream()
 
-    def step():
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+
+    def step(mark=False):
+        if mark: ev[0].record()
         engine.gt_reduce(ctx, packed, pitch, R * n_snv, n_cols, active, True, row_keep)
+        if mark: ev[1].record()
         plan.set_genotypes(packed, pitch, row_keep, stream=stream)
+        if mark: ev[2].record()
         plan.run(FP, FN, y_dev, stream=stream)
+        if mark: ev[3].record()
         lrt.run(y_dev, out, stream=stream)
+        if mark: ev[4].record()
         return out.cpu()
 
     for _ in range(max(1, warmup)):
         res = step()
+    step(mark=True)
     torch.cuda.synchronize()
+    stage_ms = {k: ev[i].elapsed_time(ev[i + 1]) for i, k in enumerate(["row_filter", "expand", "placement", "lrt"])}
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     gemm = []
@@ -275,7 +284,8 @@ def replicate_sweep(ctx, dev, rank, world, R, n_cells, n_snv, steps, warmup):
     return {"replicates_per_gpu": R, "cells": n_cells, "snvs": n_snv, "w_max_per_replicate": len(W_MAXS), "distinct_trees": n_trees,
             "ms_per_step": ms, "pt_tests_per_s": R * len(W_MAXS) * world / (ms / 1e3),
             "placements_per_s": float(R) * n_snv * n_rows * world / (ms / 1e3),
-            "pass1_ms": float(g[:, 0].mean()), "pass2_ms": float(g[:, 2].mean()), "lrt_converged": ok, "lrt_problems": int(r_np.shape[0]),
+            "pass1_ms": float(g[:, 0].mean()), "pass2_ms": float(g[:, 2].mean()), "merge_ms": float(g[:, 1].mean()),
+            "stage_ms": stage_ms, "lrt_converged": ok, "lrt_problems": int(r_np.shape[0]),
             "median_newton_iterations": float(np.median(r_np[:, 6])), "tiling": plan.info()}
 
 

@@ -354,22 +354,25 @@ __global__ void scs_count_status_kernel(const uint8_t* __restrict__ status, int6
 // get_gt_tree's reductions (run_PT_test.py:350-358) on the packed matrix:
 // row_keep[i] = any active cell of SNV i carries code 1 or 2 (sum(axis=1) > 0 with
 // the outgroup column dropped); missing[c] = number of kept SNVs where cell c is NaN.
-__global__ void scs_row_keep_kernel(const uint8_t* __restrict__ gt, int64_t pitch, int64_t n_rows, int n_words,
+__global__ void scs_row_keep_kernel(const uint8_t* __restrict__ gt, int64_t pitch, int64_t n_rows, int n_words, int lanes_per_row,
                                     const uint32_t* __restrict__ active_mask, int filter_rows, uint8_t* __restrict__ row_keep) {
-    // one warp per row, 16 cells (one 32-bit word of codes) per lane and step.  A cell holds
-    // 1 or 2 exactly when its two code bits differ; active_mask has bit 2k of word j set when
-    // cell 16j+k takes part in the filter.
-    const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (row >= n_rows) return;
+    // `lanes_per_row` (a power of two <= 32) lanes share a row, 16 cells (one 32-bit word of
+    // codes) per lane and step: a full warp for wide matrices, several rows per warp for narrow
+    // ones.  A cell holds 1 or 2 exactly when its two code bits differ; active_mask has bit 2k of
+    // word j set when cell 16j+k takes part in the filter.
+    const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t row = t / lanes_per_row;
+    const int sub = int(t - row * lanes_per_row);
     uint32_t any = 0;
-    const uint32_t* r = reinterpret_cast<const uint32_t*>(gt + row * pitch);
-    for (int j = lane; j < n_words; j += 32) {
-        const uint32_t v = r[j];
-        any |= ((v ^ (v >> 1)) & 0x55555555u) & active_mask[j];
+    if (row < n_rows) {
+        const uint32_t* r = reinterpret_cast<const uint32_t*>(gt + row * pitch);
+        for (int j = sub; j < n_words; j += lanes_per_row) {
+            const uint32_t v = r[j];
+            any |= ((v ^ (v >> 1)) & 0x55555555u) & active_mask[j];
+        }
     }
-    any = __any_sync(0xffffffffu, any != 0);
-    if (lane == 0) row_keep[row] = filter_rows ? uint8_t(any) : uint8_t(1);
+    for (int o = lanes_per_row >> 1; o > 0; o >>= 1) any |= __shfl_xor_sync(0xffffffffu, any, o);
+    if (row < n_rows && sub == 0) row_keep[row] = filter_rows ? uint8_t(any != 0) : uint8_t(1);
 }
 
 __global__ void scs_missing_count_kernel(const uint8_t* __restrict__ gt, int64_t pitch, int64_t n_rows, int n_cols,
@@ -390,6 +393,35 @@ __global__ void scs_missing_count_kernel(const uint8_t* __restrict__ gt, int64_t
 #pragma unroll
     for (int k = 0; k < 4; ++k)
         if (b * 4 + k < n_cols && c[k]) atomicAdd(&missing[b * 4 + k], c[k]);
+}
+
+// Narrow matrices (<= 512 cells): `lanes_per_row` lanes share a row, one 32-bit word (16 cells)
+// each; 16 register counters per lane, reduced over the warp's row slots, one atomic per cell.
+__global__ void scs_missing_count_narrow_kernel(const uint8_t* __restrict__ gt, int64_t pitch, int64_t n_rows, int n_words,
+                                                int lanes_per_row, int n_cols, const uint8_t* __restrict__ row_keep,
+                                                unsigned int* __restrict__ missing) {
+    const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t nslots = int64_t(gridDim.x) * blockDim.x / lanes_per_row;
+    const int sub = int(t % lanes_per_row);
+    unsigned int c[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) c[k] = 0;
+    if (sub < n_words) {
+        for (int64_t row = t / lanes_per_row; row < n_rows; row += nslots) {
+            if (!row_keep[row]) continue;
+            const uint32_t v = reinterpret_cast<const uint32_t*>(gt + row * pitch)[sub];
+            const uint32_t m = v & (v >> 1) & 0x55555555u;      // code 3 = both bits set
+#pragma unroll
+            for (int k = 0; k < 16; ++k) c[k] += (m >> (2 * k)) & 1u;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        unsigned int v = c[k];
+        for (int o = 16; o >= lanes_per_row; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        const int cell = sub * 16 + k;
+        if ((threadIdx.x & 31) < lanes_per_row && sub < n_words && cell < n_cols && v) atomicAdd(&missing[cell], v);
+    }
 }
 
 struct Vcf {
@@ -588,10 +620,16 @@ int scs_gt_reduce(scs_ctx* ctx, const uint8_t* d_gt, int64_t pitch_bytes, int64_
         cudaMemcpy(d_act, amask.data(), size_t(n_words) * 4, cudaMemcpyHostToDevice);
         cudaMemset(d_miss, 0, size_t(n_cells) * 4);
         if (n_snv > 0) {
-            scs_row_keep_kernel<<<unsigned((n_snv * 32 + 127) / 128), 128>>>(d_gt, pitch_bytes, n_snv, n_words, d_act, filter_rows, d_row_keep);
-            const int nb = (n_cells + 3) / 4;
-            dim3 grid((nb + 127) / 128, unsigned(std::min<int64_t>(1024, std::max<int64_t>(1, n_snv / 256))));
-            scs_missing_count_kernel<<<grid, 128>>>(d_gt, pitch_bytes, n_snv, n_cells, d_row_keep, d_miss);
+            int lanes = 1;
+            while (lanes < 32 && lanes < n_words) lanes <<= 1;
+            scs_row_keep_kernel<<<unsigned((n_snv * lanes + 255) / 256), 256>>>(d_gt, pitch_bytes, n_snv, n_words, lanes, d_act, filter_rows, d_row_keep);
+            if (n_words <= 32) {
+                scs_missing_count_narrow_kernel<<<unsigned(ctx->sm_count * 8), 256>>>(d_gt, pitch_bytes, n_snv, n_words, lanes, n_cells, d_row_keep, d_miss);
+            } else {
+                const int nb = (n_cells + 3) / 4;
+                dim3 grid((nb + 127) / 128, unsigned(std::min<int64_t>(1024, std::max<int64_t>(1, n_snv / 256))));
+                scs_missing_count_kernel<<<grid, 128>>>(d_gt, pitch_bytes, n_snv, n_cells, d_row_keep, d_miss);
+            }
         }
         long long kept = thrust::reduce(thrust::device, thrust::device_ptr<const uint8_t>(d_row_keep), thrust::device_ptr<const uint8_t>(d_row_keep) + n_snv, 0ll);
         cudaError_t e = cudaMemcpy(miss.data(), d_miss, size_t(n_cells) * 4, cudaMemcpyDeviceToHost);

@@ -659,9 +659,12 @@ struct RowMap {
 // of the planes are never written (they were zeroed when the plan was created).
 __global__ void scs_expand_genotypes_kernel(const uint8_t* __restrict__ gt, int64_t gt_pitch, int64_t M_pad, int n_cells, RowMap rm,
                                             uint8_t* __restrict__ x1, uint8_t* __restrict__ x0, int K_pad, int radix) {
-    const int kq = blockIdx.x * blockDim.x + threadIdx.x;  // group of 16 cells
-    if (kq * 16 >= K_pad) return;
-    for (int64_t row = blockIdx.y; row < M_pad; row += gridDim.y) {
+    // flattened (row, 16-cell group) index, so narrow matrices (100 cells) keep every thread busy
+    const int kq_per_row = K_pad / 16;
+    const int64_t total = M_pad * kq_per_row;
+    for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t row = idx / kq_per_row;
+        const int kq = int(idx - row * kq_per_row);
         const int g = rm.group_of_unit[row >> 8];
         const int64_t local = row - rm.group_row0[g];
         if (local >= rm.group_nsnv[g]) continue;
@@ -1103,7 +1106,9 @@ int scs_placement_set_genotypes(scs_placement* h, const uint8_t* d_gt, int64_t p
     if (pitch_bytes < (pl->n_cells + 3) / 4) return set_error(SCS_ERR_ARG, "genotype row pitch %lld is smaller than ceil(n_cells/4)", (long long)pitch_bytes);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if ((pitch_bytes & 3) || (reinterpret_cast<uintptr_t>(d_gt) & 3)) return set_error(SCS_ERR_ARG, "packed genotype rows must be 4-byte aligned (pitch %lld)", (long long)pitch_bytes);
-    dim3 block(128), grid((pl->K_pad / 16 + 127) / 128, unsigned(std::min<int64_t>(pl->M_pad, 16384)));
+    const int64_t work = pl->M_pad * (pl->K_pad / 16);
+    const unsigned grid = unsigned(std::min<int64_t>((work + 255) / 256, int64_t(pl->ctx->sm_count) * 64));
+    const unsigned block = 256;
     scs_expand_genotypes_kernel<<<grid, block, 0, st>>>(d_gt, pitch_bytes, pl->M_pad, pl->n_cells, pl->rowmap, pl->x1, pl->x0, pl->K_pad,
                                                          pl->mode == MODE_RADIX);
     pl->launches++;
