@@ -96,22 +96,58 @@ __device__ double gamma_q(double a, double x) {
 __global__ void __launch_bounds__(LRT_MAX_THREADS)
 scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ Ysrc, const int* __restrict__ gather,
                double* __restrict__ Yall, const double* __restrict__ wall, const int* __restrict__ child_all, LrtWork ws,
-               double* __restrict__ out, double* __restrict__ x_out) {
+               double* __restrict__ out, double* __restrict__ x_out, int smem_mode) {
     __shared__ double sh[LRT_MAX_THREADS / 32];
     __shared__ double s_bcast[4];
     __shared__ int s_nlev;
     const LrtProblem pb = probs[blockIdx.x];
     const int nb = pb.n_br, m1 = nb / 2, tid = threadIdx.x;
+    extern __shared__ double lrt_dyn[];
+    double *Y, *l, *g, *d, *dl, *h, *Hd, *e, *D, *r, *x, *G;
+    const double* w;
+    const int* child;
+    int *up, *order, *level, *levoff;
+    if (smem_mode) {
+        // small trees: the whole working set (a few KB) lives in shared memory
+        double* q = lrt_dyn;
+        Y = q; q += nb;
+        double* wq = q; q += nb;
+        l = q; q += nb;
+        g = q; q += nb;
+        d = q; q += nb;
+        dl = q; q += nb;
+        const int mn = m1 + 2;
+        h = q; q += mn;
+        Hd = q; q += mn;
+        e = q; q += mn;
+        D = q; q += mn;
+        r = q; q += mn;
+        x = q; q += mn;
+        G = q; q += mn;
+        int* iq = reinterpret_cast<int*>(q);
+        int* cq = iq; iq += nb;
+        up = iq; iq += mn;
+        order = iq; iq += mn;
+        level = iq; iq += mn;
+        levoff = iq;
+        for (int k = tid; k < nb; k += LRT_THREADS) {
+            wq[k] = wall[pb.br_off + k];
+            cq[k] = child_all[pb.br_off + k];
+        }
+        w = wq;
+        child = cq;
+    } else {
+        Y = Yall + pb.br_off;
+        w = wall + pb.br_off;
+        child = child_all + pb.br_off;
+        l = ws.l + pb.br_off; g = ws.g + pb.br_off; d = ws.d + pb.br_off; dl = ws.dl + pb.br_off;
+        h = ws.h + pb.node_off; Hd = ws.Hd + pb.node_off; e = ws.e + pb.node_off; D = ws.D + pb.node_off;
+        r = ws.r + pb.node_off; x = ws.x + pb.node_off; G = ws.G + pb.node_off;
+        up = ws.up + pb.node_off; order = ws.order + pb.node_off; level = ws.level + pb.node_off; levoff = ws.levoff + pb.node_off;
+    }
     // counts in branch order: straight copy, or a gather from per-node soft weights
-    double* Y = Yall + pb.br_off;
     for (int k = tid; k < nb; k += LRT_THREADS) Y[k] = gather ? Ysrc[gather[pb.br_off + k]] : Ysrc[pb.br_off + k];
     __syncthreads();
-    const double* w = wall + pb.br_off;
-    const int* child = child_all + pb.br_off;
-    double *l = ws.l + pb.br_off, *g = ws.g + pb.br_off, *d = ws.d + pb.br_off, *dl = ws.dl + pb.br_off;
-    double *h = ws.h + pb.node_off, *Hd = ws.Hd + pb.node_off, *e = ws.e + pb.node_off, *D = ws.D + pb.node_off;
-    double *r = ws.r + pb.node_off, *x = ws.x + pb.node_off, *G = ws.G + pb.node_off;
-    int *up = ws.up + pb.node_off, *order = ws.order + pb.node_off, *level = ws.level + pb.node_off, *levoff = ws.levoff + pb.node_off;
     double* res = out + size_t(blockIdx.x) * 8;
 
     // ---- sums, scale factor (run_PT_test.py:639-643)
@@ -390,6 +426,7 @@ struct LrtPlanImpl {
     LrtWork ws;
     long long launches = 0;
     int threads = 128;
+    int smem_bytes = 0;    // > 0: per-CTA working set in shared memory (small trees)
 };
 
 int scs_lrt_plan_create(scs_ctx* ctx, int32_t n_prob, const int64_t* br_off, const int32_t* child_int, scs_lrt_plan** out) {
@@ -418,7 +455,11 @@ int scs_lrt_plan_create(scs_ctx* ctx, int32_t n_prob, const int64_t* br_off, con
     pl->n_prob = n_prob;
     pl->nbr = size_t(total_br);
     pl->nnode = size_t(node_off);
-    pl->threads = max_nb >= 8192 ? 512 : (max_nb >= 2048 ? 256 : 128);
+    pl->threads = max_nb >= 8192 ? 512 : (max_nb >= 2048 ? 256 : (max_nb > 256 ? 128 : 64));
+    if (max_nb <= 1024) {
+        const size_t mn = size_t(max_nb / 2 + 2);
+        pl->smem_bytes = int((6 * size_t(max_nb) + 7 * mn) * sizeof(double) + (size_t(max_nb) + 4 * mn) * sizeof(int));
+    }
     const size_t nbr = pl->nbr, nnode = pl->nnode;
     const size_t dbl = 8 * nbr /*Ysrc Y w l g d dl x*/ + 7 * nnode + size_t(n_prob) * 8;
     const size_t ints = 2 * nbr /*child gather*/ + 4 * nnode;
@@ -499,8 +540,10 @@ int scs_lrt_plan_run(scs_lrt_plan* h, const double* d_Y, double* d_out, double* 
     if (!pl || !d_Y) return set_error(SCS_ERR_ARG, "null argument");
     if (!pl->have_w) return set_error(SCS_ERR_ARG, "scs_lrt_plan_set_weights has not been called");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    scs_lrt_kernel<<<pl->n_prob, pl->threads, 0, st>>>(pl->d_probs, d_Y, pl->have_gather ? pl->d_gather : nullptr, pl->dY, pl->dw,
-                                                        pl->d_child, pl->ws, d_out ? d_out : pl->d_out, d_x ? d_x : pl->d_x);
+    if (pl->smem_bytes > 48 * 1024) cudaFuncSetAttribute(scs_lrt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->smem_bytes);
+    scs_lrt_kernel<<<pl->n_prob, pl->threads, pl->smem_bytes, st>>>(pl->d_probs, d_Y, pl->have_gather ? pl->d_gather : nullptr, pl->dY, pl->dw,
+                                                                    pl->d_child, pl->ws, d_out ? d_out : pl->d_out, d_x ? d_x : pl->d_x,
+                                                                    pl->smem_bytes > 0);
     pl->launches++;
     SCS_CUDA(cudaGetLastError());
     return SCS_OK;
