@@ -234,6 +234,7 @@ scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ 
 
     const double mu = LRT_MU;
     int it = 0, status = 1;
+    double f0 = 0.0;      // barrier objective at the current iterate (carried over from the line search)
     for (; it < LRT_MAX_ITER; ++it) {
         // branch lengths, barrier gradient and curvature
         double f0p = 0.0;
@@ -244,9 +245,9 @@ scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ 
             l[k] = lk;
             g[k] = w[k] * (1.0 - Y[k] / lk) / sf - mu / a + mu / b;
             d[k] = w[k] * Y[k] / (lk * lk * sf) + mu / (a * a) + mu / (b * b);
-            f0p += w[k] * (lk - Y[k] * log(lk)) / sf - mu * (log(a) + log(b));
+            if (it == 0) f0p += w[k] * (lk - Y[k] * log(lk)) / sf - mu * log(a * b);
         }
-        const double f0 = block_reduce(f0p, sh, false);
+        if (it == 0) f0 = block_reduce(f0p, sh, false);
         for (int i = tid; i < m1; i += LRT_THREADS) {
             const int u = up[i];
             G[i] = g[2 * i] + g[2 * i + 1] - (u >= 0 ? g[u] : 0.0);
@@ -300,15 +301,15 @@ scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ 
             break;
         }
         // backtracking (Armijo) on the barrier objective
-        double a = amax;
+        double a = amax, f1 = f0;
         bool ok = false;
         for (int bt = 0; bt < 60; ++bt) {
             double fp = 0.0;
             for (int k = tid; k < nb; k += LRT_THREADS) {
                 const double lk = l[k] + a * dl[k];
-                fp += w[k] * (lk - Y[k] * log(lk)) / sf - mu * (log(lk - LRT_LMIN) + log(U - lk));
+                fp += w[k] * (lk - Y[k] * log(lk)) / sf - mu * log((lk - LRT_LMIN) * (U - lk));
             }
-            const double f1 = block_reduce(fp, sh, false);
+            f1 = block_reduce(fp, sh, false);
             if (f1 <= f0 - 1e-4 * a * dec) {
                 ok = true;
                 break;
@@ -327,6 +328,7 @@ scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ 
             ++it;
             break;
         }
+        f0 = f1;
     }
 
     // ---- statistic and p-value (run_PT_test.py:683-695)

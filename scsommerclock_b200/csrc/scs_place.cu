@@ -239,7 +239,6 @@ __device__ __forceinline__ void epilogue_tile(const PlaceParams& p, const GroupC
         const float L = __uint_as_float(rr.y);     // +inf for padded / dropped rows: 2^(-inf) = 0
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
-            if (ch * 32 >= n_valid) continue;      // padding columns of the last tile: nothing to add
             load_counts<MODE>(taddr + ch * 32, use0, p.nchunk, f1, f0);
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
