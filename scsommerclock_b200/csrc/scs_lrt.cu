@@ -300,10 +300,21 @@ scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ 
             status = 3;   // NaN in the Newton system
             break;
         }
+        // Newton converges quadratically: once the decrement (~ twice the distance to the optimum
+        // of the scaled objective) is below 1e-12 the step about to be taken leaves ~1e-24, far
+        // under the rounding level of the objective, so take it and stop -- no line search, whose
+        // Armijo test could only compare rounding noise there.
+        if (dec <= 1e-12 * fmax(1.0, fabs(f0))) {
+            for (int i = tid; i < m1; i += LRT_THREADS) h[i] += amax * x[i];
+            __syncthreads();
+            status = 0;
+            ++it;
+            break;
+        }
         // backtracking (Armijo) on the barrier objective
         double a = amax, f1 = f0;
         bool ok = false;
-        for (int bt = 0; bt < 60; ++bt) {
+        for (int bt = 0; bt < 40; ++bt) {
             double fp = 0.0;
             for (int k = tid; k < nb; k += LRT_THREADS) {
                 const double lk = l[k] + a * dl[k];
@@ -319,11 +330,7 @@ scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ 
         if (ok)
             for (int i = tid; i < m1; i += LRT_THREADS) h[i] += a * x[i];
         __syncthreads();
-        // Converged when the Newton decrement (~ twice the distance to the optimum of the scaled
-        // objective) is at the rounding level of the objective itself, or when no step decreases
-        // it any more.  (A looser "decrement < 1e-16 at full step" rule let rare problems idle at
-        // 1e-15 until the iteration cap -- one straggler CTA then dominated a batch of thousands.)
-        if (!ok || dec <= 1e-14 * fmax(1.0, fabs(f0))) {
+        if (!ok) {          // no step decreases the objective any more: at the numerical optimum
             status = 0;
             ++it;
             break;
