@@ -265,6 +265,70 @@ def test_vcf_decode_bit_exact(ctx, name):
     assert muts._dec.n_noalt == want["skipped"][0] and muts._dec.n_filtered == want["skipped"][1]
 
 
+def _synthetic_vcf_text(n_cells, n_lines, seed):
+    """CellCoal-style records (GT:DP:RC:GQ:TG, multi-allelic ALT, mixed FILTERs) built in memory."""
+    rng = np.random.default_rng(seed)
+    tree = synth.coalescent_tree(n_cells, rng)
+    codes = synth.observe(tree, synth.throw_mutations(tree, n_lines, rng), 0.1, 0.01, 0.15, rng)
+    names = ["cell%04d" % (i + 1) for i in range(n_cells)] + ["outgcell"]
+    out = ["##fileformat=VCFv4.3", "##source=synthetic",
+           "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(names)]
+    bases = "ACGT"
+    for i in range(n_lines):
+        ref = bases[rng.integers(4)]
+        alts = [b for b in bases if b != ref]
+        a = 1 + int(rng.integers(3))
+        a2 = 1 + (a % 3)
+        recs = []
+        for c in codes[i]:
+            if c == 3:
+                recs.append(".|.:4:4,0,0,0:8:0|0")
+            elif c == 0:
+                recs.append("0|0:12:12,0,0,0:10:0|0")
+            else:
+                alt = a2 if rng.random() < 0.03 else a                 # a few calls of a second alt allele
+                gt = "%d|%d" % (alt, alt) if rng.random() < 0.1 else "0|%d" % alt
+                recs.append(gt + ":9:4,0,5,0:33:0|%d" % a)
+        recs.append("0|0:20:20,0,0,0:10:0|0")
+        u = rng.random()
+        flt = "PASS" if u > 0.15 else ("wildtype" if u < 0.05 else ("s50" if u < 0.1 else "singleton"))
+        out.append("1\t%d\tsnv%06d\t%s\t%s\t.\t%s\tAA=%s;NS=%d\tGT:DP:RC:GQ:TG\t%s"
+                   % (1 + 3 * i, i, ref, ",".join(alts), flt, ref, n_cells, "\t".join(recs)))
+    return "\n".join(out) + "\n"
+
+
+@pytest.mark.parametrize("n_cells,n_lines", [(60, 1500), (333, 400), (1, 50)])
+def test_vcf_decode_bit_exact_on_generated_files(ctx, tmp_path, n_cells, n_lines):
+    p = tmp_path / "gen.vcf"
+    p.write_text(_synthetic_vcf_text(n_cells, n_lines, seed=n_cells + n_lines))
+    for excl, incl in (("", ""), ("tumcell000[1-3]", ""), ("", "(tumcell00[0-2].)|healthycell")):
+        want = O.get_mut_df(str(p), excl, incl)
+        if len(want["samples"]) == 0:
+            continue
+        muts, _, _ = P.get_mut_df(str(p), excl, incl, ctx=ctx)
+        wc = np.where(np.isnan(want["muts"]), 3, np.nan_to_num(want["muts"])).astype(np.uint8)
+        assert list(muts.columns) == list(want["samples"])
+        assert np.array_equal(muts.codes, wc)
+        assert muts.index == want["pos"]
+        assert [muts._dec.n_noalt, muts._dec.n_filtered] == want["skipped"]
+
+
+def test_empty_inputs_fail_cleanly(ctx, tmp_path):
+    head = "##fileformat=VCFv4.3\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tcell1\toutgcell\n"
+    p = tmp_path / "none_kept.vcf"
+    p.write_text(head + "1\t5\t.\tA\tC\t.\tLowQual\t.\tGT\t0|1\t0|0\n")
+    m, _, _ = P.get_mut_df(str(p), "", "", ctx=ctx)
+    assert m.shape == (0, 2) and m.codes.shape == (0, 2)
+    with pytest.raises(engine._cabi.ScsError):
+        engine.Placement(ctx, 0, 2, 4)                       # nothing to place
+    with pytest.raises(engine._cabi.ScsError):
+        engine.Placement(ctx, 10, 70000, 4)                  # beyond the 16-bit count packing
+    pl = engine.Placement(ctx, 3, 2, 4)
+    with pytest.raises(engine._cabi.ScsError):
+        pl.run_host(0.0, 0.1)                                # error rates must lie in (0, 1)
+    pl.close()
+
+
 def test_vcf_decode_rejects_malformed_input(ctx, tmp_path):
     good = ("##fileformat=VCFv4.3\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tcell1\tcell2\toutgcell\n"
             "1\t10\t.\tA\tC\t.\tPASS\t.\tGT:DP\t0|1:3\t0|0:4\t0|0:2\n")
