@@ -33,8 +33,8 @@ FN_TRUE, FP_TRUE, MS_TRUE = 0.10, 0.01, 0.15
 METRIC = "snv_branch_placements_per_s"
 # dram__bytes_read.sum + dram__bytes_write.sum of one scs_place_kernel launch at the default
 # workload, from the ncu --set full capture under profiles/ (None until a capture exists)
-# (profiles/r01_ncu_place_radix_summary.txt: 308.2 GB read + 2.5 GB written, pass 1, radix mode)
-NCU_TRAFFIC_BYTES = 310.7e9
+# (profiles/r01_ncu_place_radix_summary.txt: 279.9 GB read + 2.5 GB written, pass 1, radix mode)
+NCU_TRAFFIC_BYTES = 282.4e9
 
 
 def parse():
@@ -372,14 +372,21 @@ def main():
         return lrt_out.cpu()             # the step's result, read back to the host
 
     pinned = None
+    streamer = None
     if not args.no_e2e:
         pinned = torch.empty(packed.shape, dtype=torch.uint8, pin_memory=True)
         pinned.copy_(packed)
         torch.cuda.synchronize()
+        # host-buffer path: the packed matrix is streamed from pinned host memory in SNV-row chunks
+        # (H2D of chunk c+1 under the GEMMs of chunk c), see engine.StreamingPlacement
+        streamer = engine.StreamingPlacement(ctx, n_snv, n_cols, n_rows, n_chunks=8)
+        streamer.set_clades_host(bits, words)
 
     def step_e2e():
-        packed.copy_(pinned, non_blocking=True)      # H2D of this step's input from pinned host memory
-        return step()
+        streamer.run(pinned, pitch, active, True, FP, FN, y_dev)
+        sharding.allreduce_soft_weights(y_dev)
+        lrt.run(y_dev, lrt_out, stream=stream)
+        return lrt_out.cpu()
 
     def timed(fn, steps, warmup, sampler=None):
         for _ in range(warmup):
@@ -418,14 +425,16 @@ def main():
 
     e2e = None
     if not args.no_e2e:
+        y_ref = y_dev.clone()
         ms_e2e, _, _, _ = timed(step_e2e, args.steps, min(args.warmup, 1))
+        e2e_dev = float((y_dev - y_ref).abs().max() / y_ref.abs().max())     # streamed == resident, to summation order
         e2e = {"value": placements / (ms_e2e / args.steps / 1e3), "unit": "placements/s",
                "h2d_bytes_per_step": int(packed.numel()) * world, "d2h_bytes_per_step": int(lrt_out.numel() * 8 + n_cols * 4 + 8) * world,
-               "ms_per_step": ms_e2e / args.steps}
+               "ms_per_step": ms_e2e / args.steps, "chunks": streamer.n_chunks, "max_rel_dev_vs_resident": e2e_dev}
 
     rep = None
     if args.replicates > 0:
-        del pinned
+        del pinned, streamer
         plan.close()
         del packed
         torch.cuda.empty_cache()

@@ -332,3 +332,71 @@ class LrtPlan:
             self.close()
         except Exception:
             pass
+
+
+class StreamingPlacement:
+    """Placement of a host-resident packed genotype matrix in SNV-row chunks.
+
+    The soft branch weights are additive over SNV rows, so a dataset that sits in (pinned)
+    host memory is walked in chunks: the H2D copy of chunk c+1 runs on a side stream while
+    chunk c goes through row filter -> operand expansion -> both GEMM passes on the compute
+    stream.  One chunk-sized plan is reused, device memory stays bounded by the chunk size,
+    and the copy disappears behind the GEMMs.  Returns the same numbers a single plan gives
+    (to summation order)."""
+
+    def __init__(self, ctx, n_snv, n_cells, n_rows, n_chunks=8):
+        import torch
+        self.ctx, self.n_snv, self.n_cells, self.n_rows = ctx, int(n_snv), int(n_cells), int(n_rows)
+        rows = (self.n_snv + n_chunks - 1) // n_chunks
+        self.chunk_rows = max(256, (rows + 255) // 256 * 256)
+        self.n_chunks = (self.n_snv + self.chunk_rows - 1) // self.chunk_rows
+        self.plan = Placement(ctx, self.chunk_rows, n_cells, n_rows)
+        self.dev = torch.device("cuda", ctx.device)
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self._bufs = None
+        self.y_chunk = torch.zeros(n_rows, dtype=torch.float64, device=self.dev)
+        self.keep = torch.zeros(self.chunk_rows, dtype=torch.uint8, device=self.dev)
+
+    def set_clades_host(self, bits, words):
+        self.plan.set_clades_host(bits, words)
+
+    def run(self, host_packed, pitch, col_active, filter_rows, FP, FN, y_dev):
+        """``host_packed``: torch uint8 [n_snv, pitch] in pinned host memory.  Accumulates the soft
+        weights into ``y_dev`` (zeroed here) and returns (kept SNVs, per-cell missing fraction)."""
+        import torch
+        cur = torch.cuda.current_stream(self.dev)
+        if self._bufs is None or self._bufs[0].shape[1] != pitch:
+            self._bufs = [torch.empty((self.chunk_rows, pitch), dtype=torch.uint8, device=self.dev) for _ in range(2)]
+            self._ready = [torch.cuda.Event() for _ in range(2)]
+            self._free = [torch.cuda.Event() for _ in range(2)]
+            for e in self._free:
+                e.record(cur)
+        y_dev.zero_()
+        n_kept_total, miss_sum = 0, np.zeros(len(col_active))
+
+        def enqueue_copy(c):
+            b = c & 1
+            r0 = c * self.chunk_rows
+            r1 = min(self.n_snv, r0 + self.chunk_rows)
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(self._free[b])          # the previous user of this buffer is done
+                self._bufs[b][: r1 - r0].copy_(host_packed[r0:r1], non_blocking=True)
+                self._ready[b].record(self.copy_stream)
+            return r1 - r0
+
+        rows_c = enqueue_copy(0)
+        for c in range(self.n_chunks):
+            b = c & 1
+            rows_next = enqueue_copy(c + 1) if c + 1 < self.n_chunks else 0
+            cur.wait_event(self._ready[b])
+            if rows_c < self.chunk_rows:
+                self.keep.zero_()                                    # tail rows of a short last chunk: dropped
+            n_kept, miss = gt_reduce(self.ctx, self._bufs[b], pitch, rows_c, len(col_active), col_active, filter_rows, self.keep)
+            self.plan.set_genotypes(self._bufs[b], pitch, self.keep, stream=cur)
+            self.plan.run(FP, FN, self.y_chunk, stream=cur)
+            y_dev.add_(self.y_chunk)
+            self._free[b].record(cur)
+            n_kept_total += n_kept
+            miss_sum += miss * n_kept
+            rows_c = rows_next
+        return n_kept_total, (miss_sum / max(n_kept_total, 1))

@@ -157,6 +157,39 @@ def test_batched_replicates_match_individual_plans(ctx):
     pl.close()
 
 
+def test_streaming_placement_equals_resident_plan(ctx):
+    """Host-resident matrix walked in row chunks (H2D of chunk c+1 under the GEMMs of chunk c):
+    same soft weights, kept-SNV count and missing rates as one device-resident plan."""
+    import torch
+    n_cells, n_snv = 150, 5000
+    codes, S = make_problem(n_snv, n_cells, seed=77)
+    codes = np.concatenate([codes, np.zeros((n_snv, 1), dtype=np.uint8)], axis=1)      # an outgroup column
+    S = np.concatenate([S, np.zeros((S.shape[0], 1), dtype=np.uint8)], axis=1)
+    active = np.ones(n_cells + 1, dtype=np.uint8)
+    active[-1] = 0
+    packed, pitch = engine.pack_genotypes(codes)
+    bits, words = engine.pack_clades(S)
+    dev = torch.device("cuda", ctx.device)
+    d = torch.as_tensor(packed, device=dev)
+    keep = torch.empty(n_snv, dtype=torch.uint8, device=dev)
+    n_kept, miss = engine.gt_reduce(ctx, d, pitch, n_snv, n_cells + 1, active, True, keep)
+    pl = engine.Placement(ctx, n_snv, n_cells + 1, S.shape[0])
+    pl.set_clades_host(bits, words)
+    pl.set_genotypes(d, pitch, keep)
+    want = pl.run_host(0.01, 0.1)
+    st = engine.StreamingPlacement(ctx, n_snv, n_cells + 1, S.shape[0], n_chunks=7)
+    assert st.n_chunks >= 6
+    st.set_clades_host(bits, words)
+    y = torch.zeros(S.shape[0], dtype=torch.float64, device=dev)
+    pinned = torch.as_tensor(packed).pin_memory()
+    for _ in range(2):                                           # buffers are reused across calls
+        got_kept, got_miss = st.run(pinned, pitch, active, True, 0.01, 0.1, y)
+        torch.cuda.synchronize()
+        assert got_kept == n_kept
+        np.testing.assert_allclose(got_miss, miss, rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(y.cpu().numpy(), want, rtol=1e-6, atol=1e-6)
+
+
 def test_row_keep_and_extreme_rates(ctx):
     codes, S = make_problem(900, 120, seed=5)
     packed, pitch = engine.pack_genotypes(codes)
@@ -297,7 +330,7 @@ def _synthetic_vcf_text(n_cells, n_lines, seed):
     return "\n".join(out) + "\n"
 
 
-@pytest.mark.parametrize("n_cells,n_lines", [(60, 1500), (333, 400), (1, 50)])
+@pytest.mark.parametrize("n_cells,n_lines", [(60, 1500), (333, 400), (2, 50)])
 def test_vcf_decode_bit_exact_on_generated_files(ctx, tmp_path, n_cells, n_lines):
     p = tmp_path / "gen.vcf"
     p.write_text(_synthetic_vcf_text(n_cells, n_lines, seed=n_cells + n_lines))
