@@ -15,6 +15,20 @@ int set_error(int code, const char* fmt, ...) {
 }
 }  // namespace scs
 
+namespace scs {
+void* ctx_scratch(scs_ctx* ctx, size_t bytes) {
+    if (bytes > ctx->scratch_bytes) {
+        if (ctx->scratch) cudaFree(ctx->scratch);
+        ctx->scratch = nullptr;
+        ctx->scratch_bytes = 0;
+        const size_t want = (bytes + 4095) / 4096 * 4096 * 2;
+        if (cudaMalloc(&ctx->scratch, want) != cudaSuccess) return nullptr;
+        ctx->scratch_bytes = want;
+    }
+    return ctx->scratch;
+}
+}  // namespace scs
+
 using namespace scs;
 
 extern "C" {
@@ -46,6 +60,7 @@ int scs_ctx_create(int32_t device, scs_ctx** out) {
 }
 
 int scs_ctx_destroy(scs_ctx* ctx) {
+    if (ctx && ctx->scratch) cudaFree(ctx->scratch);
     delete ctx;
     return SCS_OK;
 }

@@ -355,7 +355,8 @@ __global__ void scs_count_status_kernel(const uint8_t* __restrict__ status, int6
 // row_keep[i] = any active cell of SNV i carries code 1 or 2 (sum(axis=1) > 0 with
 // the outgroup column dropped); missing[c] = number of kept SNVs where cell c is NaN.
 __global__ void scs_row_keep_kernel(const uint8_t* __restrict__ gt, int64_t pitch, int64_t n_rows, int n_words, int lanes_per_row,
-                                    const uint32_t* __restrict__ active_mask, int filter_rows, uint8_t* __restrict__ row_keep) {
+                                    const uint32_t* __restrict__ active_mask, int filter_rows, uint8_t* __restrict__ row_keep,
+                                    unsigned long long* __restrict__ n_kept) {
     // `lanes_per_row` (a power of two <= 32) lanes share a row, 16 cells (one 32-bit word of
     // codes) per lane and step: a full warp for wide matrices, several rows per warp for narrow
     // ones.  A cell holds 1 or 2 exactly when its two code bits differ; active_mask has bit 2k of
@@ -372,7 +373,10 @@ __global__ void scs_row_keep_kernel(const uint8_t* __restrict__ gt, int64_t pitc
         }
     }
     for (int o = lanes_per_row >> 1; o > 0; o >>= 1) any |= __shfl_xor_sync(0xffffffffu, any, o);
-    if (row < n_rows && sub == 0) row_keep[row] = filter_rows ? uint8_t(any != 0) : uint8_t(1);
+    const bool kept = row < n_rows && sub == 0 && (!filter_rows || any != 0);
+    if (row < n_rows && sub == 0) row_keep[row] = uint8_t(kept);
+    const unsigned int votes = __popc(__ballot_sync(0xffffffffu, kept));
+    if ((threadIdx.x & 31) == 0 && votes) atomicAdd(n_kept, (unsigned long long)votes);      // integer: order-independent
 }
 
 __global__ void scs_missing_count_kernel(const uint8_t* __restrict__ gt, int64_t pitch, int64_t n_rows, int n_cols,
@@ -600,50 +604,43 @@ int scs_vcf_copy(scs_vcf* h, uint8_t* packed, int64_t* pos) {
 int scs_gt_reduce(scs_ctx* ctx, const uint8_t* d_gt, int64_t pitch_bytes, int64_t n_snv, int32_t n_cells, const uint8_t* col_active,
                   int32_t filter_rows, uint8_t* d_row_keep, int64_t* n_kept, double* missing_frac) {
     if (!ctx || !d_gt || !col_active || !d_row_keep || !n_kept || !missing_frac) return set_error(SCS_ERR_ARG, "null argument");
-    SCS_CUDA(cudaSetDevice(ctx->device));
     if ((pitch_bytes & 3) || pitch_bytes * 4 < n_cells) return set_error(SCS_ERR_ARG, "packed genotype pitch %lld must be a multiple of 4 and cover %d cells", (long long)pitch_bytes, n_cells);
-    uint32_t* d_act = nullptr;
-    unsigned int* d_miss = nullptr;
-    long long* d_flag = nullptr;
-    int rc = SCS_OK;
+    SCS_CUDA(cudaSetDevice(ctx->device));
+    // scratch layout: [kept counter (8 B, padded to 16)] [active mask words] [missing counters]
+    const int n_words = (n_cells + 15) / 16;
+    const size_t off_mask = 16, off_miss = off_mask + size_t(n_words + 3) / 4 * 16;
+    const size_t bytes = off_miss + size_t(n_cells) * 4;
+    uint8_t* sc = static_cast<uint8_t*>(ctx_scratch(ctx, bytes));
+    if (!sc) return set_error(SCS_ERR_OOM, "device scratch allocation failed");
+    unsigned long long* d_kept = reinterpret_cast<unsigned long long*>(sc);
+    uint32_t* d_act = reinterpret_cast<uint32_t*>(sc + off_mask);
+    unsigned int* d_miss = reinterpret_cast<unsigned int*>(sc + off_miss);
+    // active cells as a mask over the low bit of every 2-bit code
+    std::vector<uint32_t> amask(n_words, 0u);
+    for (int c = 0; c < n_cells; ++c)
+        if (col_active[c]) amask[c >> 4] |= 1u << (2 * (c & 15));
+    SCS_CUDA(cudaMemsetAsync(sc, 0, bytes, 0));
+    SCS_CUDA(cudaMemcpyAsync(d_act, amask.data(), size_t(n_words) * 4, cudaMemcpyHostToDevice, 0));
+    if (n_snv > 0) {
+        int lanes = 1;
+        while (lanes < 32 && lanes < n_words) lanes <<= 1;
+        scs_row_keep_kernel<<<unsigned((n_snv * lanes + 255) / 256), 256>>>(d_gt, pitch_bytes, n_snv, n_words, lanes, d_act, filter_rows, d_row_keep, d_kept);
+        if (n_words <= 32) {
+            scs_missing_count_narrow_kernel<<<unsigned(ctx->sm_count * 8), 256>>>(d_gt, pitch_bytes, n_snv, n_words, lanes, n_cells, d_row_keep, d_miss);
+        } else {
+            const int nb = (n_cells + 3) / 4;
+            dim3 grid((nb + 127) / 128, unsigned(std::min<int64_t>(1024, std::max<int64_t>(1, n_snv / 256))));
+            scs_missing_count_kernel<<<grid, 128>>>(d_gt, pitch_bytes, n_snv, n_cells, d_row_keep, d_miss);
+        }
+    }
+    SCS_CUDA(cudaGetLastError());
     std::vector<unsigned int> miss(n_cells);
-    do {
-        if (cudaMalloc(&d_act, size_t(n_cells / 16 + 1) * 4) != cudaSuccess || cudaMalloc(&d_miss, size_t(n_cells) * 4) != cudaSuccess) {
-            rc = set_error(SCS_ERR_OOM, "device allocation failed");
-            break;
-        }
-        // active cells as a mask over the low bit of every 2-bit code
-        const int n_words = (n_cells + 15) / 16;
-        std::vector<uint32_t> amask(n_words, 0u);
-        for (int c = 0; c < n_cells; ++c)
-            if (col_active[c]) amask[c >> 4] |= 1u << (2 * (c & 15));
-        cudaMemcpy(d_act, amask.data(), size_t(n_words) * 4, cudaMemcpyHostToDevice);
-        cudaMemset(d_miss, 0, size_t(n_cells) * 4);
-        if (n_snv > 0) {
-            int lanes = 1;
-            while (lanes < 32 && lanes < n_words) lanes <<= 1;
-            scs_row_keep_kernel<<<unsigned((n_snv * lanes + 255) / 256), 256>>>(d_gt, pitch_bytes, n_snv, n_words, lanes, d_act, filter_rows, d_row_keep);
-            if (n_words <= 32) {
-                scs_missing_count_narrow_kernel<<<unsigned(ctx->sm_count * 8), 256>>>(d_gt, pitch_bytes, n_snv, n_words, lanes, n_cells, d_row_keep, d_miss);
-            } else {
-                const int nb = (n_cells + 3) / 4;
-                dim3 grid((nb + 127) / 128, unsigned(std::min<int64_t>(1024, std::max<int64_t>(1, n_snv / 256))));
-                scs_missing_count_kernel<<<grid, 128>>>(d_gt, pitch_bytes, n_snv, n_cells, d_row_keep, d_miss);
-            }
-        }
-        long long kept = thrust::reduce(thrust::device, thrust::device_ptr<const uint8_t>(d_row_keep), thrust::device_ptr<const uint8_t>(d_row_keep) + n_snv, 0ll);
-        cudaError_t e = cudaMemcpy(miss.data(), d_miss, size_t(n_cells) * 4, cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) {
-            rc = set_error(SCS_ERR_CUDA, "genotype reduction failed: %s", cudaGetErrorString(e));
-            break;
-        }
-        *n_kept = kept;
-        for (int c = 0; c < n_cells; ++c) missing_frac[c] = kept > 0 ? double(miss[c]) / double(kept) : 0.0;
-    } while (0);
-    cudaFree(d_act);
-    cudaFree(d_miss);
-    cudaFree(d_flag);
-    return rc;
+    unsigned long long kept = 0;
+    SCS_CUDA(cudaMemcpy(&kept, d_kept, sizeof(kept), cudaMemcpyDeviceToHost));
+    SCS_CUDA(cudaMemcpy(miss.data(), d_miss, size_t(n_cells) * 4, cudaMemcpyDeviceToHost));
+    *n_kept = int64_t(kept);
+    for (int c = 0; c < n_cells; ++c) missing_frac[c] = kept > 0 ? double(miss[c]) / double(kept) : 0.0;
+    return SCS_OK;
 }
 
 }  // extern "C"

@@ -12,7 +12,16 @@ struct scs_ctx {
     int cc_major, cc_minor;
     size_t total_mem;
     int l2_bytes;
+    // small device scratch reused by the reduction entry points (no cudaMalloc/cudaFree -- and so no
+    // device-wide synchronisation -- on the per-chunk path of StreamingPlacement)
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
 };
+
+namespace scs {
+// Device scratch of at least `bytes` owned by the context (grown, never shrunk); nullptr on failure.
+void* ctx_scratch(scs_ctx* ctx, size_t bytes);
+}  // namespace scs
 
 namespace scs {
 // Records a printf-style message for scs_last_error() and returns `code`.
