@@ -129,6 +129,9 @@ int scs_placement_info(scs_placement* plan, int64_t* info, int32_t n);
 /* Parity aid for small problems: counts[i][b][0/1] = number of cells of clade b
  * observed mutated / observed wild type for SNV i (exact integers). */
 int scs_placement_debug_counts(scs_placement* plan, int32_t* counts, void* stream);
+/* Analysis aid: pass-1 partials ([2 * column tiles][M_pad] of {u32 ref counts, f32 sum}) and merged
+ * per-SNV records ([M_pad] of {u32 ref counts, f32 log2 sum}) of the last run; either may be NULL. */
+int scs_placement_debug_stats(scs_placement* plan, void* stats, void* rowref);
 
 /* One-shot host call mirroring map_mutations_gt's signature: host buffers in,
  * soft_weights[n_rows] out (H2D copy, both GEMM passes, D2H copy). */

@@ -358,7 +358,7 @@ scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ 
         const double df = dof - double(k);
         if (df > 0.0) {
             double pv = gamma_q(0.5 * df, 0.5 * LR);
-            pv = fmin(fmax(pv, 1e-100), 1.0);
+            if (on_bound > 0) pv = fmin(fmax(pv, 1e-100), 1.0);   // the reference clips only inside the mixture (:690 vs :695)
             // weights relative to the central binomial coefficient keep everything finite
             const double lw = lg_n - lgamma(double(k) + 1.0) - lgamma(double(on_bound - k) + 1.0) - double(on_bound) * 0.6931471805599453;
             const double wk = exp(lw);

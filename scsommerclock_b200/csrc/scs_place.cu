@@ -1279,6 +1279,17 @@ int scs_placement_debug_counts(scs_placement* h, int32_t* counts_host, void* str
     return SCS_OK;
 }
 
+// Analysis aid: the pass-1 partials ([parts][M_pad] {ref counts, sum}) and the merged per-SNV
+// records ([M_pad] {ref counts, log2 sum}) of the last run, copied to the host.
+int scs_placement_debug_stats(scs_placement* h, void* stats_host, void* rowref_host) {
+    Placement* pl = reinterpret_cast<Placement*>(h);
+    if (!pl) return set_error(SCS_ERR_ARG, "null argument");
+    SCS_CUDA(cudaDeviceSynchronize());
+    if (stats_host) SCS_CUDA(cudaMemcpy(stats_host, pl->stats, size_t(pl->num_parts) * pl->M_pad * sizeof(uint2), cudaMemcpyDeviceToHost));
+    if (rowref_host) SCS_CUDA(cudaMemcpy(rowref_host, pl->rowref, size_t(pl->M_pad) * sizeof(uint2), cudaMemcpyDeviceToHost));
+    return SCS_OK;
+}
+
 int scs_placement_info(scs_placement* h, int64_t* info, int32_t n) {
     Placement* pl = reinterpret_cast<Placement*>(h);
     if (!pl || !info) return set_error(SCS_ERR_ARG, "null argument");

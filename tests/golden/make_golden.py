@@ -266,6 +266,14 @@ def main():
     v, t = make_synthetic("syn_c", 9, 150, 13, FN=0.05, FP=0.02, MS=0.05, quirks=False, tree_suffix=".newick")
     run_case(ref, "syn_c", v, t, [1000], exclude="tumcell000[12]")
     run_case(ref, "syn_c_incl", v, t, [300], include="(tumcell000[1-7])|healthycell")
+    if "--skip-large" not in sys.argv:
+        # example_data-sized synthetic pairs (30 cells + outgroup, ~4000 SNVs, default w_max list),
+        # one simulated under the clock and one with a 5x rate in a subtree, like the reference's examples
+        v, t = make_synthetic("syn_d_clock", 30, 4000, 21, FN=0.1, FP=0.005, MS=0.1, quirks=True, log_rates=("0.005000", "0.200000"))
+        run_case(ref, "syn_d_clock", v, t, default_w)
+        v, t = make_synthetic("syn_d_noclock", 30, 4000, 22, FN=0.1, FP=0.005, MS=0.1, quirks=False, log_rates=("0.005000", "0.200000"),
+                              rate_mult_clade=5.0)
+        run_case(ref, "syn_d_noclock", v, t, default_w)
     print("golden fixtures written to", HERE)
 
 

@@ -21,7 +21,7 @@ from scsommerclock_b200 import engine, run_PT_test as P, synth
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["example_clock", "example_noclock", "syn_a", "syn_b", "syn_c", "syn_c_incl"]
+CASES = ["example_clock", "example_noclock", "syn_a", "syn_b", "syn_c", "syn_c_incl", "syn_d_clock", "syn_d_noclock"]
 SYN = [c for c in CASES if c.startswith("syn")]
 Y_TOL = 2e-5
 
@@ -421,7 +421,7 @@ def test_lrt_on_golden_model_data(ctx, name):
         assert dof == int(g["dof"][k])
         assert on_bound == int(g["on_bound"][k])
         assert abs(LR - g["LR"][k]) <= 1e-4 * max(1.0, abs(g["LR"][k]))
-        assert abs(p_val - g["p_val"][k]) <= 2e-3 * g["p_val"][k]
+        assert abs(p_val - g["p_val"][k]) <= 2e-3 * g["p_val"][k] + 1e-300      # far tails underflow to 0 in both
         assert int(p_val < 0.05) == int(g["hyp"][k])                     # identical clock / no-clock decision
         x = np.array([v[0] for v in opt])
         assert np.abs(g["constr"][k] @ x).max() < 1e-8                    # the fit is exactly ultrametric
@@ -481,7 +481,7 @@ def test_run_poisson_tree_test_tsv(ctx, name, tmp_path):
     for i in range(3, len(rc), 4):
         assert abs(float(rc[i]) - float(gc[i])) <= 1e-4 * max(1.0, abs(float(rc[i]))) + 6e-4   # 3 printed decimals
         assert rc[i + 1] == gc[i + 1]                                    # dof
-        assert abs(float(rc[i + 2]) - float(gc[i + 2])) <= 2e-3 * float(rc[i + 2])
+        assert abs(float(rc[i + 2]) - float(gc[i + 2])) <= 2e-3 * float(rc[i + 2]) + 1e-300
         assert rc[i + 3] == gc[i + 3]                                    # H0 / H1
 
 

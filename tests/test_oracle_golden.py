@@ -8,8 +8,8 @@ import pytest
 from conftest import case_inputs, golden_path
 from oracle import pt_oracle as O
 
-CASES = ["example_clock", "example_noclock", "syn_a", "syn_b", "syn_c", "syn_c_incl"]
-SYN = [c for c in CASES if c.startswith("syn")]
+CASES = ["example_clock", "example_noclock", "syn_a", "syn_b", "syn_c", "syn_c_incl", "syn_d_clock", "syn_d_noclock"]
+SYN = [c for c in CASES if c.startswith("syn") and not c.startswith("syn_d")]
 
 
 def load(name):
@@ -76,7 +76,7 @@ def test_model_data_and_lrt(name):
         pytest.skip("reference example_data not present on this machine")
     mut = _mut_from_golden(g)
     ws = list(g["w_maxs"])
-    if name.startswith("example"):
+    if name.startswith("example") or name.startswith("syn_d"):
         ws = ws[:1] + ws[-1:]           # the SciPy solve takes seconds per w
     for w in ws:
         k = list(g["w_maxs"]).index(w)
