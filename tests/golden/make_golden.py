@@ -266,6 +266,34 @@ def main():
     v, t = make_synthetic("syn_c", 9, 150, 13, FN=0.05, FP=0.02, MS=0.05, quirks=False, tree_suffix=".newick")
     run_case(ref, "syn_c", v, t, [1000], exclude="tumcell000[12]")
     run_case(ref, "syn_c_incl", v, t, [300], include="(tumcell000[1-7])|healthycell")
+    # tree leaves that are not in the VCF: the reference deletes them (:311-313), collapsing their
+    # parents.  (The opposite mismatch -- a VCF sample missing from the tree -- makes the reference
+    # itself fail with a KeyError at :437 as soon as one of the padding rows of S wins an SNV.)
+    v, t = make_synthetic("syn_e", 10, 160, 14, FN=0.1, FP=0.01, MS=0.1, quirks=False)
+    from scsommerclock_b200.tree import Tree as _T
+    tt = _T(open(t).read().strip(), format=1)
+    leaves = tt.get_leaves()
+    for k, (host, nm) in enumerate(((leaves[2], "cell0098"), (leaves[7], "cell0099"))):
+        # graft an extra leaf next to an existing one: (host) -> (host, extra)
+        up = host.up
+        pos = up.children.index(host)
+        joint = _T()
+        joint.dist = host.dist / 2
+        host.dist = host.dist / 2
+        up.children[pos] = joint
+        joint.up = up
+        joint.children = [host, _T(name=nm, dist=0.02)] if k == 0 else [_T(name=nm, dist=0.02), host]
+        for ch in joint.children:
+            ch.up = joint
+    t2 = t.replace("syn_e", "syn_e_mismatch")
+    def _nw(node):
+        if node.children:
+            return "(" + ",".join(_nw(c) for c in node.children) + "):%.6f" % node.dist
+        return "%s:%.6f" % (node.name, node.dist)
+    with open(t2, "w") as f:
+        f.write("(" + ",".join(_nw(c) for c in tt.children) + ");\n")
+    os.remove(t)
+    run_case(ref, "syn_e_mismatch", v, t2, [500])
     if "--skip-large" not in sys.argv:
         # example_data-sized synthetic pairs (30 cells + outgroup, ~4000 SNVs, default w_max list),
         # one simulated under the clock and one with a 5x rate in a subtree, like the reference's examples

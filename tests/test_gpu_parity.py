@@ -21,7 +21,7 @@ from scsommerclock_b200 import engine, run_PT_test as P, synth
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["example_clock", "example_noclock", "syn_a", "syn_b", "syn_c", "syn_c_incl", "syn_d_clock", "syn_d_noclock"]
+CASES = ["example_clock", "example_noclock", "syn_a", "syn_b", "syn_c", "syn_c_incl", "syn_d_clock", "syn_d_noclock", "syn_e_mismatch"]
 SYN = [c for c in CASES if c.startswith("syn")]
 Y_TOL = 2e-5
 

@@ -12,7 +12,7 @@ from oracle import pt_oracle as O
 from scsommerclock_b200 import engine, run_PT_test as P, synth
 from scsommerclock_b200.tree import NewickError, Tree
 
-CASES = ["example_clock", "example_noclock", "syn_a", "syn_b", "syn_c", "syn_c_incl", "syn_d_clock", "syn_d_noclock"]
+CASES = ["example_clock", "example_noclock", "syn_a", "syn_b", "syn_c", "syn_c_incl", "syn_d_clock", "syn_d_noclock", "syn_e_mismatch"]
 
 
 def load(name):

@@ -8,7 +8,7 @@ import pytest
 from conftest import case_inputs, golden_path
 from oracle import pt_oracle as O
 
-CASES = ["example_clock", "example_noclock", "syn_a", "syn_b", "syn_c", "syn_c_incl", "syn_d_clock", "syn_d_noclock"]
+CASES = ["example_clock", "example_noclock", "syn_a", "syn_b", "syn_c", "syn_c_incl", "syn_d_clock", "syn_d_noclock", "syn_e_mismatch"]
 SYN = [c for c in CASES if c.startswith("syn") and not c.startswith("syn_d")]
 
 
