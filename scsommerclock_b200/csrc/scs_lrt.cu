@@ -98,7 +98,6 @@ scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ 
                double* __restrict__ Yall, const double* __restrict__ wall, const int* __restrict__ child_all, LrtWork ws,
                double* __restrict__ out, double* __restrict__ x_out, int smem_mode) {
     __shared__ double sh[LRT_MAX_THREADS / 32];
-    __shared__ double s_bcast[4];
     __shared__ int s_nlev;
     const LrtProblem pb = probs[blockIdx.x];
     const int nb = pb.n_br, m1 = nb / 2, tid = threadIdx.x;
@@ -177,60 +176,88 @@ scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ 
         return;
     }
 
-    // ---- topology: up-branch of every internal node, levels, level order (thread 0)
-    for (int i = tid; i < m1; i += LRT_THREADS) up[i] = -1;
+    // ---- topology: up-branch of every internal node, levels, level order.  All of it in parallel:
+    // with 10,000-leaf trees the obvious thread-0 loops were 5 of the kernel's 7 ms.
+    __shared__ int s_changed;
+    for (int i = tid; i < m1; i += LRT_THREADS) {
+        up[i] = -1;
+        level[i] = 0;
+    }
     __syncthreads();
     for (int k = tid; k < nb; k += LRT_THREADS)
         if (child[k] >= 0) up[child[k]] = k;
-    if (tid == 0) {
-        // children precede parents (post-order), so one ascending sweep gives the levels
-        int nlev = 0;
-        for (int i = 0; i < m1; ++i) {
+    // level = 1 + max(level of internal children): relax until nothing changes (<= depth + 1 sweeps;
+    // children have smaller indices, and a sweep may already see this sweep's updates -- harmless)
+    for (int sweep = 0; sweep <= m1; ++sweep) {
+        __syncthreads();
+        if (tid == 0) s_changed = 0;
+        __syncthreads();
+        int ch = 0;
+        for (int i = tid; i < m1; i += LRT_THREADS) {
             int lv = 0;
             const int c0 = child[2 * i], c1 = child[2 * i + 1];
             if (c0 >= 0) lv = max(lv, level[c0] + 1);
             if (c1 >= 0) lv = max(lv, level[c1] + 1);
-            level[i] = lv;
-            nlev = max(nlev, lv + 1);
+            if (lv != level[i]) {
+                level[i] = lv;
+                ch = 1;
+            }
         }
-        // counting sort by level: levoff[q] = first slot of level q in `order`
-        for (int q = 0; q <= nlev; ++q) levoff[q] = 0;
-        for (int i = 0; i < m1; ++i) levoff[level[i] + 1]++;
-        for (int q = 0; q < nlev; ++q) levoff[q + 1] += levoff[q];
-        for (int i = 0; i < m1; ++i) order[levoff[level[i]]++] = i;
-        for (int q = nlev; q > 0; --q) levoff[q] = levoff[q - 1];
-        levoff[0] = 0;
+        if (ch) s_changed = 1;
+        __syncthreads();
+        if (!s_changed) break;
+    }
+    // counting sort by level: levoff[q] = first slot of level q in `order` (order inside a level is
+    // irrelevant: the nodes of a level are independent)
+    for (int q = tid; q <= m1 + 1; q += LRT_THREADS) levoff[q] = 0;
+    __syncthreads();
+    for (int i = tid; i < m1; i += LRT_THREADS) atomicAdd(&levoff[level[i] + 1], 1);
+    __syncthreads();
+    if (tid == 0) {
+        int nlev = 0;
+        for (int q = 0; q < m1; ++q) {
+            if (levoff[q + 1] == 0) break;
+            levoff[q + 1] += levoff[q];
+            nlev = q + 1;
+        }
         s_nlev = nlev;
     }
     __syncthreads();
     const int nlev = s_nlev;
-
-    // ---- strictly feasible start: heights from the counts themselves
-    if (tid == 0) {
-        const double dmin = 1e-3;
-        double lmax = 0.0;
-        for (int i = 0; i < m1; ++i) {
-            double hv = 0.0;
-            for (int s = 0; s < 2; ++s) {
-                const int k = 2 * i + s;
-                const double hc = child[k] >= 0 ? h[child[k]] : 0.0;
-                hv = fmax(hv, hc + fmax(Y[k], dmin));
-            }
-            h[i] = hv;
-        }
-        for (int k = 0; k < nb; ++k) {
-            const double hc = child[k] >= 0 ? h[child[k]] : 0.0;
-            lmax = fmax(lmax, h[k >> 1] - hc);
-        }
-        s_bcast[0] = lmax >= 0.9 * U ? 0.9 * U / lmax : 1.0;
-    }
+    // scatter with per-level cursors kept in `order`'s tail-free companion: reuse G (doubles, unused yet) as ints
+    int* cursor = reinterpret_cast<int*>(G);
+    for (int q = tid; q < nlev; q += LRT_THREADS) cursor[q] = levoff[q];
     __syncthreads();
+    for (int i = tid; i < m1; i += LRT_THREADS) order[atomicAdd(&cursor[level[i]], 1)] = i;
+    __syncthreads();
+
+    // ---- strictly feasible start: heights from the counts themselves, level by level
     {
-        const double sc = s_bcast[0];
+        const double dmin = 1e-3;
+        for (int q = 0; q < nlev; ++q) {
+            for (int s = levoff[q] + tid; s < levoff[q + 1]; s += LRT_THREADS) {
+                const int i = order[s];
+                double hv = 0.0;
+                for (int c = 0; c < 2; ++c) {
+                    const int k = 2 * i + c;
+                    const double hc = child[k] >= 0 ? h[child[k]] : 0.0;
+                    hv = fmax(hv, hc + fmax(Y[k], dmin));
+                }
+                h[i] = hv;
+            }
+            __syncthreads();
+        }
+        double lmaxp = 0.0;
+        for (int k = tid; k < nb; k += LRT_THREADS) {
+            const double hc = child[k] >= 0 ? h[child[k]] : 0.0;
+            lmaxp = fmax(lmaxp, h[k >> 1] - hc);
+        }
+        const double lmax = -block_reduce(-lmaxp, sh, true);
+        const double sc = lmax >= 0.9 * U ? 0.9 * U / lmax : 1.0;
         if (sc != 1.0)
             for (int i = tid; i < m1; i += LRT_THREADS) h[i] *= sc;
+        __syncthreads();
     }
-    __syncthreads();
 
     const double mu = LRT_MU;
     int it = 0, status = 1;
