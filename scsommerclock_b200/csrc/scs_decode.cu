@@ -365,7 +365,7 @@ __global__ void scs_row_keep_kernel(const uint8_t* __restrict__ gt, int64_t pitc
     const int64_t row = t / lanes_per_row;
     const int sub = int(t - row * lanes_per_row);
     uint32_t any = 0;
-    if (row < n_rows) {
+    if (row < n_rows) {   // (no early return: every thread reaches the block-wide count below)
         const uint32_t* r = reinterpret_cast<const uint32_t*>(gt + row * pitch);
         for (int j = sub; j < n_words; j += lanes_per_row) {
             const uint32_t v = r[j];
@@ -375,8 +375,8 @@ __global__ void scs_row_keep_kernel(const uint8_t* __restrict__ gt, int64_t pitc
     for (int o = lanes_per_row >> 1; o > 0; o >>= 1) any |= __shfl_xor_sync(0xffffffffu, any, o);
     const bool kept = row < n_rows && sub == 0 && (!filter_rows || any != 0);
     if (row < n_rows && sub == 0) row_keep[row] = uint8_t(kept);
-    const unsigned int votes = __popc(__ballot_sync(0xffffffffu, kept));
-    if ((threadIdx.x & 31) == 0 && votes) atomicAdd(n_kept, (unsigned long long)votes);      // integer: order-independent
+    const int votes = __syncthreads_count(kept);                                            // one atomic per block
+    if (threadIdx.x == 0 && votes) atomicAdd(n_kept, (unsigned long long)votes);             // integer: order-independent
 }
 
 __global__ void scs_missing_count_kernel(const uint8_t* __restrict__ gt, int64_t pitch, int64_t n_rows, int n_cols,
