@@ -657,35 +657,48 @@ struct RowMap {
 // cell c in bits [2*(c%4), +2)) -> 0/1 byte plane(s), K-major, zero padded.  One thread
 // turns 16 cells (one 32-bit word of codes) into one 16-byte store per plane.  Padding rows
 // of the planes are never written (they were zeroed when the plan was created).
+__device__ __forceinline__ void expand_16_cells(const uint8_t* __restrict__ gt, int64_t gt_pitch, int n_cells, const RowMap& rm,
+                                                uint8_t* __restrict__ x1, uint8_t* __restrict__ x0, int K_pad, int radix, int64_t row,
+                                                int kq) {
+    const int g = rm.group_of_unit[row >> 8];
+    const int64_t local = row - rm.group_row0[g];
+    if (local >= rm.group_nsnv[g]) return;
+    const int64_t src = rm.group_src0[g] + local;
+    uint32_t w = 0;
+    if (kq * 4 < gt_pitch && kq * 16 < n_cells) w = *reinterpret_cast<const uint32_t*>(gt + src * gt_pitch + kq * 4);
+    uint32_t o1[4] = {0, 0, 0, 0}, o0[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const uint32_t code = (w >> (2 * i)) & 3u;
+        const bool in = kq * 16 + i < n_cells;
+        const bool mut = in && (code == 1u || code == 2u), wt = in && code == 0u;
+        if (radix) {
+            o1[i >> 2] |= uint32_t(mut ? E5M2_ONE : (wt ? E5M2_4096 : 0)) << (8 * (i & 3));   // one e5m2 plane: 1 / 4096 / 0
+        } else {
+            o1[i >> 2] |= uint32_t(mut) << (8 * (i & 3));
+            o0[i >> 2] |= uint32_t(wt) << (8 * (i & 3));
+        }
+    }
+    *reinterpret_cast<uint4*>(x1 + row * K_pad + kq * 16) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+    if (!radix) *reinterpret_cast<uint4*>(x0 + row * K_pad + kq * 16) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
+}
+
+// Wide matrices: blockIdx.y walks the rows, threads cover the 16-cell groups of a row.
 __global__ void scs_expand_genotypes_kernel(const uint8_t* __restrict__ gt, int64_t gt_pitch, int64_t M_pad, int n_cells, RowMap rm,
                                             uint8_t* __restrict__ x1, uint8_t* __restrict__ x0, int K_pad, int radix) {
-    // flattened (row, 16-cell group) index, so narrow matrices (100 cells) keep every thread busy
-    const int kq_per_row = K_pad / 16;
-    const int64_t total = M_pad * kq_per_row;
-    for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
-        const int64_t row = idx / kq_per_row;
-        const int kq = int(idx - row * kq_per_row);
-        const int g = rm.group_of_unit[row >> 8];
-        const int64_t local = row - rm.group_row0[g];
-        if (local >= rm.group_nsnv[g]) continue;
-        const int64_t src = rm.group_src0[g] + local;
-        uint32_t w = 0;
-        if (kq * 4 < gt_pitch && kq * 16 < n_cells) w = *reinterpret_cast<const uint32_t*>(gt + src * gt_pitch + kq * 4);
-        uint32_t o1[4] = {0, 0, 0, 0}, o0[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const uint32_t code = (w >> (2 * i)) & 3u;
-            const bool in = kq * 16 + i < n_cells;
-            const bool mut = in && (code == 1u || code == 2u), wt = in && code == 0u;
-            if (radix) {
-                o1[i >> 2] |= uint32_t(mut ? E5M2_ONE : (wt ? E5M2_4096 : 0)) << (8 * (i & 3));   // one e5m2 plane: 1 / 4096 / 0
-            } else {
-                o1[i >> 2] |= uint32_t(mut) << (8 * (i & 3));
-                o0[i >> 2] |= uint32_t(wt) << (8 * (i & 3));
-            }
-        }
-        *reinterpret_cast<uint4*>(x1 + row * K_pad + kq * 16) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
-        if (!radix) *reinterpret_cast<uint4*>(x0 + row * K_pad + kq * 16) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
+    const int kq = blockIdx.x * blockDim.x + threadIdx.x;
+    if (kq * 16 >= K_pad) return;
+    for (int64_t row = blockIdx.y; row < M_pad; row += gridDim.y) expand_16_cells(gt, gt_pitch, n_cells, rm, x1, x0, K_pad, radix, row, kq);
+}
+
+// Narrow matrices (replicate batches, ~100 cells): flattened (row, group) index so that every thread works.
+__global__ void scs_expand_genotypes_flat_kernel(const uint8_t* __restrict__ gt, int64_t gt_pitch, int64_t M_pad, int n_cells, RowMap rm,
+                                                 uint8_t* __restrict__ x1, uint8_t* __restrict__ x0, int K_pad, int radix) {
+    const uint32_t kq_per_row = uint32_t(K_pad / 16);
+    const uint32_t total = uint32_t(M_pad) * kq_per_row;            // the host guarantees this fits 32 bits
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const uint32_t row = idx / kq_per_row;
+        expand_16_cells(gt, gt_pitch, n_cells, rm, x1, x0, K_pad, radix, int64_t(row), int(idx - row * kq_per_row));
     }
 }
 
@@ -1107,10 +1120,15 @@ int scs_placement_set_genotypes(scs_placement* h, const uint8_t* d_gt, int64_t p
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if ((pitch_bytes & 3) || (reinterpret_cast<uintptr_t>(d_gt) & 3)) return set_error(SCS_ERR_ARG, "packed genotype rows must be 4-byte aligned (pitch %lld)", (long long)pitch_bytes);
     const int64_t work = pl->M_pad * (pl->K_pad / 16);
-    const unsigned grid = unsigned(std::min<int64_t>((work + 255) / 256, int64_t(pl->ctx->sm_count) * 64));
-    const unsigned block = 256;
-    scs_expand_genotypes_kernel<<<grid, block, 0, st>>>(d_gt, pitch_bytes, pl->M_pad, pl->n_cells, pl->rowmap, pl->x1, pl->x0, pl->K_pad,
-                                                         pl->mode == MODE_RADIX);
+    if (pl->K_pad / 16 < 64 && work < (int64_t(1) << 31)) {
+        const unsigned grid = unsigned(std::min<int64_t>((work + 255) / 256, int64_t(pl->ctx->sm_count) * 64));
+        scs_expand_genotypes_flat_kernel<<<grid, 256, 0, st>>>(d_gt, pitch_bytes, pl->M_pad, pl->n_cells, pl->rowmap, pl->x1, pl->x0,
+                                                               pl->K_pad, pl->mode == MODE_RADIX);
+    } else {
+        dim3 block(128), grid((pl->K_pad / 16 + 127) / 128, unsigned(std::min<int64_t>(pl->M_pad, 32768)));
+        scs_expand_genotypes_kernel<<<grid, block, 0, st>>>(d_gt, pitch_bytes, pl->M_pad, pl->n_cells, pl->rowmap, pl->x1, pl->x0, pl->K_pad,
+                                                             pl->mode == MODE_RADIX);
+    }
     pl->launches++;
     if (d_row_keep) {
         SCS_CUDA(cudaMemcpyAsync(pl->row_keep, d_row_keep, size_t(pl->n_snv), cudaMemcpyDeviceToDevice, st));
