@@ -152,9 +152,10 @@ def reference_arm(args):
     tree = make_tree(args.cells)
     S = tree.clade_matrix().astype(np.float64)
     n_rows = S.shape[0]
-    # a bounded sample: a few SNVs per step (each costs ~8 passes over a 2n x n float64 matrix)
-    per_snv = 2.0e-8 * n_rows * args.cells * 1.0
-    n_sample = int(max(1, min(64, round(12.0 / max(per_snv, 1e-3)))))
+    # a bounded sample: a few SNVs per step (each costs ~8 passes over a 2n x n float64 matrix), sized so
+    # that the whole --steps/--warmup run stays around two minutes whatever K and W the caller asks for
+    per_snv = 2.4e-8 * n_rows * args.cells * 1.0
+    n_sample = int(max(1, min(64, round(120.0 / (args.steps + args.warmup) / max(per_snv, 1e-3)))))
     codes = cpu_sample_inputs(tree, args.cells, n_sample * (args.steps + args.warmup))
     muts = np.where(codes == 3, np.nan, codes.astype(float))
     times = []
@@ -450,7 +451,8 @@ def main():
         out = res.numpy()
         line = {
             "metric": METRIC, "value": value, "unit": "placements/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp8_e5m2 operands holding exact integer counts, f32 accumulate (epilogue f32, LRT f64)" if plan_info["mode"] == 1 else "u8 operands, s32 accumulate (epilogue f32, LRT f64)",
             "data": "synthetic",
             "config": {"workload": "coalescent %d cells x %d SNVs per GPU (BASELINE configs[3]), SNV rows sharded, one all-reduce of the branch weights, LRT for 10 w_max"
                                    % (n_cells, n_snv),

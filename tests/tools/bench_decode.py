@@ -1,7 +1,7 @@
 """VCF decode (scs_vcf_decode) parity at a larger size and throughput.  Run on the GPU box."""
 import os, sys, time, tempfile
 import numpy as np
-sys.path.insert(0, ".")
+sys.path.insert(0, ".")  # run from the repo root: python tests/tools/bench_decode.py
 from oracle import pt_oracle as O
 from scsommerclock_b200 import engine, run_PT_test as P, synth
 
