@@ -79,6 +79,17 @@ class GenotypeMatrix:
         c[c == engine._cabi.GT_MISSING] = np.nan
         return c
 
+    def device_tensor(self):
+        """Zero-copy torch view (uint8 [n_snv, pitch]) of the packed matrix in device memory."""
+        import torch
+
+        class _View:
+            pass
+        v = _View()
+        n, pitch = self._dec.n_kept, self._dec.pitch
+        v.__cuda_array_interface__ = {"shape": (n, pitch), "typestr": "|u1", "data": (self._dec.device_ptr(), False), "version": 2}
+        return torch.as_tensor(v, device=torch.device("cuda", self.ctx.device))
+
     def to_dataframe(self):
         import pandas as pd
         return pd.DataFrame(self.values, index=pd.MultiIndex.from_tuples(self.index), columns=self.columns)
@@ -361,13 +372,7 @@ def get_gt_tree(tree_file, call_data, w_max, FN_fix=None, FP_fix=None):
     muts = call_data[0]
     ctx = muts.ctx
     tree, outg, FP, FN = read_tree(tree_file, muts.columns)
-    if FP_fix and FN_fix:
-        FP = max(FP_fix, LAMBDA_MIN)
-        FN = max(FN_fix, LAMBDA_MIN)
-    else:
-        FP = max(FP, LAMBDA_MIN)
-        FN /= 2
-        FN = max(FN, LAMBDA_MIN)
+    FP, FN = _error_rates(FP, FN, FN_fix, FP_fix)
     key = (os.path.abspath(tree_file), FP, FN)
     st = muts._cache.get(key)
     if st is None:
@@ -579,6 +584,84 @@ def run_poisson_tree_test(vcf_file, tree_file, out_file, w_maxs, exclude, includ
     with open(out_file, "w") as f_out:
         f_out.write(f"{header_str}\n{model_str}")
     print("Running successful\n")
+
+
+def _error_rates(FP, FN, FN_fix, FP_fix):
+    """run_PT_test.py:341-347."""
+    if FP_fix and FN_fix:
+        return max(FP_fix, LAMBDA_MIN), max(FN_fix, LAMBDA_MIN)
+    return max(FP, LAMBDA_MIN), max(FN / 2, LAMBDA_MIN)
+
+
+def run_poisson_tree_test_batch(vcf_files, tree_files, out_files, w_maxs, exclude="", include="", FN_in=None, FP_in=None,
+                                ctx=None, shard=True):
+    """Many independent (VCF, tree) pairs -- a simulation sweep (BASELINE configs[4]).  Same TSV per
+    pair as run_poisson_tree_test.  Under torchrun the pairs are dealt to the ranks (no
+    communication); on each rank pairs of equal shape are placed block-diagonally in ONE launch
+    per GEMM pass (scs_placement_create_batch) and all (pair, w_max) clock tests are solved in ONE
+    LRT launch.  Returns the list of (pair index, [(LR, dof, on_bound, p), ...]) this rank handled."""
+    import torch
+    from . import sharding
+    ctx = ctx or get_context()
+    rank, world, _ = sharding.env_world()
+    mine = sharding.replicate_shard(len(vcf_files), rank, world) if shard else list(range(len(vcf_files)))
+    dev = torch.device("cuda", ctx.device)
+    items = []
+    for i in mine:
+        muts = get_mut_df(vcf_files[i], exclude, include, ctx=ctx)[0]
+        tree, outg, FP, FN = read_tree(tree_files[i], muts.columns)
+        FP, FN = _error_rates(FP, FN, FN_in, FP_in)
+        columns = list(muts.columns)
+        active = np.array([c != outg for c in columns], dtype=np.uint8)
+        n_snv, n_cols = muts.shape
+        if n_snv == 0:
+            raise ValueError("%s: no SNV passes the filters" % vcf_files[i])
+        d_gt = muts.device_tensor()
+        keep = torch.empty(n_snv, dtype=torch.uint8, device=dev)
+        n_kept, miss = engine.gt_reduce(ctx, d_gt, muts._dec.pitch, n_snv, n_cols, active, outg in columns, keep)
+        MS_i = {c: float(np.clip(miss[k], LAMBDA_MIN, 1 - FN - 0.2)) for k, c in enumerate(columns) if active[k]}
+        bits, words, nodes = _clade_bits(tree, columns, active)
+        items.append(dict(i=i, muts=muts, tree=tree, FP=FP, FN=FN, columns=columns, d_gt=d_gt, keep=keep, n_kept=n_kept, MS_i=MS_i,
+                          bits=bits, words=words, n_cols=n_cols, n_rows=bits.shape[0], pitch=muts._dec.pitch))
+    # ---- placement: one batched plan per (cells, clade rows) shape
+    shapes = {}
+    for it in items:
+        shapes.setdefault((it["n_cols"], it["n_rows"], it["pitch"]), []).append(it)
+    for (n_cols, n_rows, pitch), grp in shapes.items():
+        plan = engine.Placement(ctx, [g["muts"].shape[0] for g in grp], n_cols, n_rows)
+        plan.set_genotypes(torch.cat([g["d_gt"] for g in grp], dim=0).contiguous(), pitch, torch.cat([g["keep"] for g in grp]).contiguous())
+        plan.set_clades_host(np.concatenate([g["bits"] for g in grp], axis=0), grp[0]["words"])
+        soft = np.atleast_2d(plan.run_host(np.array([g["FP"] for g in grp]), np.array([g["FN"] for g in grp])).reshape(len(grp), n_rows))
+        plan.close()
+        for g, sw in zip(grp, soft):
+            g["st"] = {"soft": sw, "MS_i": g["MS_i"], "n_muts": g["n_kept"], "bits": g["bits"], "words": g["words"],
+                       "columns": g["columns"], "weights": {}}
+    # ---- LRT: every (pair, w_max) in one launch
+    problems = []
+    for it in items:
+        _apply_placement(it["tree"], it["st"])
+        for w_max in w_maxs:
+            add_br_weights(it["tree"], it["FP"], it["FN"], it["MS_i"], w_max, _state=it["st"])
+            Y, constr, init, weights_norm, constr_cols = get_model_data(it["tree"])
+            problems.append((Y, constr, weights_norm[:, 0].copy()))
+    results = get_LRT_poisson_batch(problems, ctx=ctx) if problems else []
+    out = []
+    w_cols = ["-2logLR", "dof", "p-value", "hypothesis"]
+    for k, it in enumerate(items):
+        header_str = "muts\tFN\tFP"
+        model_str = ""
+        res_i = []
+        for w_max, r in zip(w_maxs, results[k * len(w_maxs):(k + 1) * len(w_maxs)]):
+            LR, dof, on_bound, p_val = r[0], r[1], r[2], r[3]
+            hyp = int(p_val < 0.05)
+            header_str += "\t" + "\t".join([f"{c}_{w_max:.0f}" for c in w_cols])
+            model_str += f"\t{LR:0>5.3f}\t{dof}\t{p_val}\tH{hyp}"
+            res_i.append((LR, dof, on_bound, p_val))
+        model_str = f"{it['n_kept']}\t{it['FN']:.4f}\t{it['FP']:.4f}{model_str}"
+        with open(out_files[it["i"]], "w") as f_out:
+            f_out.write(f"{header_str}\n{model_str}")
+        out.append((it["i"], res_i))
+    return out
 
 
 def parse_args(argv=None):

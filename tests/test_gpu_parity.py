@@ -485,6 +485,31 @@ def test_run_poisson_tree_test_tsv(ctx, name, tmp_path):
         assert rc[i + 3] == gc[i + 3]                                    # H0 / H1
 
 
+def test_run_poisson_tree_test_batch(ctx, tmp_path):
+    """A sweep of (VCF, tree) pairs through the batched path: the two example-sized pairs share a
+    shape and go through ONE placement launch per pass; every TSV matches the reference's."""
+    names = ["syn_d_clock", "syn_a", "syn_d_noclock", "syn_e_mismatch"]
+    gs = [load(n) for n in names]
+    vcfs, trees = zip(*[case_inputs(g)[:2] for g in gs])
+    outs = [str(tmp_path / (n + ".tsv")) for n in names]
+    w = [100.0, 500.0, 1000.0]
+    res = P.run_poisson_tree_test_batch(list(vcfs), list(trees), outs, w, ctx=ctx)
+    assert [r[0] for r in res] == [0, 1, 2, 3]
+    for g, out in zip(gs, outs):
+        got = open(out).read().split("\n")[1].split("\t")
+        ref = str(g["tsv"]).split("\n")[1].split("\t")
+        assert got[:3] == ref[:3]
+        gw = list(g["w_maxs"])
+        for j, wm in enumerate(w):
+            if wm not in gw:
+                continue
+            k = gw.index(wm)
+            LR, dof, p, hyp = float(got[3 + 4 * j]), got[4 + 4 * j], float(got[5 + 4 * j]), got[6 + 4 * j]
+            assert abs(LR - g["LR"][k]) <= 1e-4 * max(1.0, abs(g["LR"][k])) + 6e-4
+            assert dof == str(int(g["dof"][k])) and hyp == "H%d" % int(g["hyp"][k])
+            assert abs(p - g["p_val"][k]) <= 2e-3 * g["p_val"][k] + 1e-300
+
+
 def test_cli_entry_point(ctx, tmp_path):
     g = load("syn_a")
     vcf, tree_file, meta = case_inputs(g)
