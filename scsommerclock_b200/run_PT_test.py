@@ -242,9 +242,51 @@ def get_mut_df(vcf_file, exclude_pat, include_pat, filter=True, ctx=None):
     include_id = [sample_names[i] for i in include_idx]
     if not include_idx:
         raise ValueError("no sample left after -excl/-incl")
+    sharded = False
+    if _row_sharding_active():
+        # one large dataset on several GPUs: every rank decodes and places its own block of record
+        # lines; the branch weights are all-reduced later
+        text = _shard_record_lines(text)
+        sharded = True
     dec = engine.DecodedVcf(ctx, text, len(sample_names), include_idx)
     muts = GenotypeMatrix(ctx, dec, include_id)
+    muts.row_sharded = sharded
     return muts, None, None
+
+
+def _row_sharding_active():
+    """True under torchrun with an initialised process group (and SCS_SHARD_ROWS != 0)."""
+    if os.environ.get("SCS_SHARD_ROWS", "1") == "0":
+        return False
+    try:
+        import torch.distributed as dist
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    except Exception:
+        return False
+
+
+def _shard_record_lines(text):
+    """This rank's share of the VCF: the header block plus a contiguous block of record lines
+    (cut at line boundaries, sizes balanced by bytes)."""
+    import torch.distributed as dist
+    from . import sharding
+    rank, world = dist.get_rank(), dist.get_world_size()
+    pos, n = 0, len(text)
+    while pos < n and (text[pos:pos + 1] == b"#" or text[pos:text.find(b"\n", pos) if text.find(b"\n", pos) >= 0 else n].strip() == b""):
+        nl = text.find(b"\n", pos)
+        pos = n if nl < 0 else nl + 1
+    body0 = pos
+    lo, hi = sharding.shard_range(n - body0, rank, world)
+
+    def snap(off):                    # first line start at or after body0 + off
+        if off <= 0:
+            return body0
+        if body0 + off >= n:
+            return n
+        nl = text.find(b"\n", body0 + off - 1)
+        return n if nl < 0 else nl + 1
+
+    return text[:body0] + text[snap(lo):snap(hi)]
 
 
 # -------------------------------------------------------------------- tree
@@ -394,14 +436,33 @@ def _place_on_tree(ctx, muts, tree, outg, FP, FN):
     row_keep = torch.empty(max(n_snv, 1), dtype=torch.uint8, device=dev)
     d_gt = muts._dec.device_ptr()
     n_kept, miss = engine.gt_reduce(ctx, d_gt, muts._dec.pitch, n_snv, n_cols, active, has_outg, row_keep)   # :350-357
+    sharded = getattr(muts, "row_sharded", False)
+    if sharded:
+        from . import sharding
+        t = torch.tensor(np.concatenate([[float(n_kept)], miss * n_kept]), dtype=torch.float64, device=dev)
+        sharding.allreduce_soft_weights(t)                 # kept SNVs and per-cell missing counts over all ranks
+        n_kept = int(round(t[0].item()))
+        miss = (t[1:] / max(n_kept, 1)).cpu().numpy()
     FN_cap = 1 - FN - 0.2
     MS_i = {c: float(np.clip(miss[i], LAMBDA_MIN, FN_cap)) for i, c in enumerate(columns) if active[i]}        # :358
     bits, words, nodes = _clade_bits(tree, columns, active)
-    plan = engine.Placement(ctx, n_snv, n_cols, bits.shape[0])
-    plan.set_genotypes(d_gt, muts._dec.pitch, row_keep)
-    plan.set_clades_host(bits, words)
-    soft = plan.run_host(FP, FN)
-    plan.close()
+    if sharded:
+        y = torch.zeros(bits.shape[0], dtype=torch.float64, device=dev)
+        if n_snv > 0:
+            plan = engine.Placement(ctx, n_snv, n_cols, bits.shape[0])
+            plan.set_genotypes(d_gt, muts._dec.pitch, row_keep)
+            plan.set_clades_host(bits, words)
+            plan.run(FP, FN, y)
+            torch.cuda.synchronize(dev)
+            plan.close()
+        sharding.allreduce_soft_weights(y)                 # the path's one exchange: 2n doubles
+        soft = y.cpu().numpy()
+    else:
+        plan = engine.Placement(ctx, n_snv, n_cols, bits.shape[0])
+        plan.set_genotypes(d_gt, muts._dec.pitch, row_keep)
+        plan.set_clades_host(bits, words)
+        soft = plan.run_host(FP, FN)
+        plan.close()
     return {"soft": soft, "MS_i": MS_i, "n_muts": n_kept, "bits": bits, "words": words, "columns": columns,
             "weights": {}}
 
@@ -581,8 +642,9 @@ def run_poisson_tree_test(vcf_file, tree_file, out_file, w_maxs, exclude, includ
         header_str += "\t" + "\t".join([f"{i}_{w_max:.0f}" for i in w_cols])
         model_str += f"\t{LR:0>5.3f}\t{dof}\t{p_val}\tH{hyp}"
     model_str = f"{M.shape[0]}\t{FN:.4f}\t{FP:.4f}{model_str}"
-    with open(out_file, "w") as f_out:
-        f_out.write(f"{header_str}\n{model_str}")
+    if not getattr(call_data[0], "row_sharded", False) or int(os.environ.get("RANK", "0")) == 0:
+        with open(out_file, "w") as f_out:
+            f_out.write(f"{header_str}\n{model_str}")
     print("Running successful\n")
 
 
@@ -688,6 +750,10 @@ def main(argv=None):
     args = parse_args(argv)
     if not args.output:
         args.output = args.vcf + ".poissonTree_LRT.tsv"
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # launched with torchrun: one process per GPU, SNV rows sharded over the ranks
+        from . import sharding
+        sharding.init_distributed()
     run_poisson_tree_test(vcf_file=args.vcf, tree_file=args.tree, out_file=args.output, w_maxs=args.w_max,
                           exclude=args.exclude, include=args.include, FN_in=args.FN_rate, FP_in=args.FP_rate)
 

@@ -131,3 +131,26 @@ def test_synthetic_tree_is_a_laminar_family():
         assert (S[v] == (S[a] | S[b])).all() and not (S[a] & S[b]).any()
     nw = t.newick(["c%d" % i for i in range(37)], "outg")
     assert len(Tree(nw, format=1)) == 38
+
+
+def test_vcf_record_lines_are_sharded_at_line_boundaries():
+    """Row sharding of one large VCF over ranks: every rank gets the header block plus a contiguous
+    block of whole record lines, and the blocks tile the body."""
+    import unittest.mock as mock
+    import torch.distributed as dist
+    head = b"##fileformat=VCFv4.3\n#CHROM\tPOS\tID\n\n"
+    text = head + b"".join(b"1\t%d\tsnv%06d\tpayload %s\n" % (i, i, b"x" * (i % 17)) for i in range(1, 700))
+    for world in (1, 2, 3, 8):
+        got = []
+        for rank in range(world):
+            with mock.patch.object(dist, "get_rank", return_value=rank), mock.patch.object(dist, "get_world_size", return_value=world):
+                got.append(P._shard_record_lines(text))
+        assert all(g.startswith(head) and g.endswith(b"\n") for g in got)
+        assert b"".join(g[len(head):] for g in got) == text[len(head):]
+    # more ranks than lines: some ranks get an empty body, nothing is lost
+    tiny = head + b"1\t5\tsnv\n"
+    got = []
+    for rank in range(4):
+        with mock.patch.object(dist, "get_rank", return_value=rank), mock.patch.object(dist, "get_world_size", return_value=4):
+            got.append(P._shard_record_lines(tiny)[len(head):])
+    assert b"".join(got) == b"1\t5\tsnv\n"
