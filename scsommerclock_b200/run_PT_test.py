@@ -756,6 +756,10 @@ def main(argv=None):
         sharding.init_distributed()
     run_poisson_tree_test(vcf_file=args.vcf, tree_file=args.tree, out_file=args.output, w_maxs=args.w_max,
                           exclude=args.exclude, include=args.include, FN_in=args.FN_rate, FP_in=args.FP_rate)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":
