@@ -466,6 +466,8 @@ def main():
                          "peak_source": pk_kind + " cuBLAS bf16, sustained (kernel timed inside a long step)",
                          "kernel": "scs_place_kernel (%s), avg of pass 1 and pass 2 launches" % (
                              "tcgen05 kind::f8f6f4, one radix-packed e5m2 plane" if plan_info["mode"] == 1 else "tcgen05 kind::i8, two u8 planes"),
+                         "peak_8bit_equiv": 2 * peak, "frac_8bit_equiv": achieved / (2 * peak),
+                         "why_frac_exceeds_1": "MEASURED_PEAKS.json holds a bf16 figure only; this GEMM runs 8-bit operands (FP8 e5m2 / u8), whose tensor rate is twice bf16: against 2 x the measured bf16 rate the kernel sits at frac_8bit_equiv",
                          "algorithmic_flop_per_launch": flop, "ms_per_launch": t_gemm,
                          "pass1_ms": float(g[:, 0].mean()), "merge_ms": float(g[:, 1].mean()), "pass2_ms": float(g[:, 2].mean()),
                          "reduce_ms": float(g[:, 3].mean()),

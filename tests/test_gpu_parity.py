@@ -82,10 +82,11 @@ def test_counts_bit_exact_and_soft_weights(ctx, monkeypatch, mode, n_snv, n_cell
 
 
 @pytest.mark.parametrize("mode", ["radix", "planes"])
-@pytest.mark.parametrize("n_snv,n_cells", [(300, 3968), (260, 4100), (140, 8100), (130, 10000)])
+@pytest.mark.parametrize("n_snv,n_cells", [(300, 3968), (260, 4100), (140, 8100), (130, 10000), (130, 12500), (129, 15872)])
 def test_counts_bit_exact_dense_many_cells(ctx, monkeypatch, mode, n_snv, n_cells):
     """Worst case for the radix packing: dense random clade rows and genotypes put both
-    counts of every K chunk (3968 cells) near their maximum; 1, 2 and 3 chunks."""
+    counts of every K chunk (3968 cells) near their maximum; 1, 2, 3 and 4 chunks (with 4 chunks
+    a tile fills the whole TMEM slot pool and the epilogue no longer overlaps the next tile)."""
     monkeypatch.setenv("SCS_PLACE_MODE", mode)
     rng = np.random.default_rng(n_cells)
     n_rows = 256 if n_cells > 5000 else 384
@@ -114,8 +115,21 @@ def test_counts_bit_exact_dense_many_cells(ctx, monkeypatch, mode, n_snv, n_cell
 
 def test_radix_mode_falls_back_beyond_four_chunks(ctx, monkeypatch):
     monkeypatch.setenv("SCS_PLACE_MODE", "radix")
-    pl = engine.Placement(ctx, 128, 16000, 64)         # 125 K blocks = 5 chunks: exact u8 planes instead
+    n_cells, n_snv, n_rows = 16000, 140, 64            # 125 K blocks = 5 chunks: exact u8 planes instead
+    pl = engine.Placement(ctx, n_snv, n_cells, n_rows)
     assert pl.info()["mode"] == 0
+    rng = np.random.default_rng(3)
+    S = (rng.random((n_rows, n_cells)) < 0.7).astype(np.uint8)
+    S[-1] = 0
+    codes = rng.choice([0, 1, 3], size=(n_snv, n_cells), p=[0.6, 0.3, 0.1]).astype(np.uint8)
+    packed, pitch = engine.pack_genotypes(codes)
+    bits, words = engine.pack_clades(S)
+    pl.set_genotypes_host(packed, pitch)
+    pl.set_clades_host(bits, words)
+    cnt = pl.debug_counts()
+    C1 = ((codes == 1).astype(np.float32) @ S.T.astype(np.float32)).astype(np.int64)
+    C0 = ((codes == 0).astype(np.float32) @ S.T.astype(np.float32)).astype(np.int64)
+    assert np.array_equal(cnt[:, :, 0], C1) and np.array_equal(cnt[:, :, 1], C0)
     pl.close()
 
 
