@@ -279,6 +279,46 @@ def test_placement_properties_at_scale(ctx):
     assert np.array_equal(pl.run_host(0.01, 0.1), y)
 
 
+def test_placement_properties_at_full_baseline_size(ctx):
+    """BASELINE configs[3] at full size (10,000 cells x 1,000,000 SNVs, ~16 GB of device memory): the
+    oracle cannot run here, so check what must hold at any size -- one unit of mass per kept SNV,
+    non-negative weights, bitwise run-to-run reproducibility, and additivity over SNV rows (the two
+    halves, placed by a separate plan, add up to the whole)."""
+    import torch
+    if ctx.total_mem_mib < 60000:
+        pytest.skip("needs a GPU with >= 60 GB")
+    n_cells, n_snv = 10000, 1000000
+    rng = np.random.default_rng(1234)
+    tree = synth.coalescent_tree(n_cells, rng)
+    S = tree.clade_matrix()
+    bits, words = engine.pack_clades(S)
+    dev = torch.device("cuda", ctx.device)
+    lo = torch.as_tensor(tree.lo[:-1], device=dev)
+    hi = torch.as_tensor(tree.hi[:-1], device=dev)
+    rate = torch.as_tensor(tree.branch_len[:-1], device=dev, dtype=torch.float32)
+    packed, pitch, keep = synth.observe_packed_torch(lo, hi, torch.as_tensor(tree.leaf_rank), n_snv, 0.1, 0.01, 0.15, dev,
+                                                      seed=11, rate=rate)
+    n_kept = int(keep.sum())
+    pl = engine.Placement(ctx, n_snv, n_cells, S.shape[0])
+    assert pl.info()["mode"] == 1 and pl.info()["k_chunks"] == 3
+    pl.set_clades_host(bits, words)
+    pl.set_genotypes(packed, pitch, keep)
+    y = pl.run_host(0.01, 0.05)
+    assert (y >= 0).all()
+    assert abs(y.sum() - n_kept) <= 2e-6 * n_kept
+    assert np.array_equal(pl.run_host(0.01, 0.05), y)
+    pl.close()
+    half = n_snv // 2
+    ph = engine.Placement(ctx, half, n_cells, S.shape[0])
+    ph.set_clades_host(bits, words)
+    ph.set_genotypes(packed[:half], pitch, keep[:half])
+    ya = ph.run_host(0.01, 0.05)
+    ph.set_genotypes(packed[half:], pitch, keep[half:])
+    yb = ph.run_host(0.01, 0.05)
+    ph.close()
+    np.testing.assert_allclose(ya + yb, y, rtol=2e-5, atol=2e-5)
+
+
 @pytest.mark.parametrize("name", CASES)
 def test_placement_on_golden_cases(ctx, name):
     g = load(name)
