@@ -379,24 +379,46 @@ __global__ void scs_row_keep_kernel(const uint8_t* __restrict__ gt, int64_t pitc
     if (threadIdx.x == 0 && votes) atomicAdd(n_kept, (unsigned long long)votes);             // integer: order-independent
 }
 
-__global__ void scs_missing_count_kernel(const uint8_t* __restrict__ gt, int64_t pitch, int64_t n_rows, int n_cols,
+__global__ void scs_missing_count_kernel(const uint8_t* __restrict__ gt, int64_t pitch, int64_t n_rows, int n_cols, int n_words,
                                          const uint8_t* __restrict__ row_keep, unsigned int* __restrict__ missing) {
-    // block = 128 byte-columns x a slab of rows; per-thread counters, one atomic per cell at the end
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    const int nb = (n_cols + 3) / 4;
-    if (b >= nb) return;
+    // Wide matrices: a thread owns one 32-bit word column (16 cells) over a slab of rows; loads are
+    // coalesced across the warp.  "Missing" (code 3) is both bits set.  The 16 counters are kept as
+    // four words of four byte-wide SWAR counters, flushed to 32-bit registers every 255 kept rows, so
+    // the loop is ~12 integer ops per 4 bytes and the kernel stays HBM bound.
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_words) return;
     const int64_t slab = (n_rows + gridDim.y - 1) / gridDim.y;
     const int64_t r0 = int64_t(blockIdx.y) * slab, r1 = min(n_rows, r0 + slab);
-    unsigned int c[4] = {0, 0, 0, 0};
+    unsigned int total[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) total[k] = 0;
+    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    int pending = 0;
+    auto flush = [&]() {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {      // byte b of accumulator q holds cell 4*b + q
+            total[4 * b + 0] += (a0 >> (8 * b)) & 0xFFu;
+            total[4 * b + 1] += (a1 >> (8 * b)) & 0xFFu;
+            total[4 * b + 2] += (a2 >> (8 * b)) & 0xFFu;
+            total[4 * b + 3] += (a3 >> (8 * b)) & 0xFFu;
+        }
+        a0 = a1 = a2 = a3 = 0;
+        pending = 0;
+    };
     for (int64_t r = r0; r < r1; ++r) {
         if (!row_keep[r]) continue;
-        const uint32_t v = gt[r * pitch + b];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) c[k] += ((v >> (2 * k)) & 3u) == 3u;
+        const uint32_t v = reinterpret_cast<const uint32_t*>(gt + r * pitch)[j];
+        const uint32_t m = v & (v >> 1);    // bit 2k set <=> cell k missing
+        a0 += m & 0x01010101u;
+        a1 += (m >> 2) & 0x01010101u;
+        a2 += (m >> 4) & 0x01010101u;
+        a3 += (m >> 6) & 0x01010101u;
+        if (++pending == 255) flush();
     }
+    flush();
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-        if (b * 4 + k < n_cols && c[k]) atomicAdd(&missing[b * 4 + k], c[k]);
+    for (int k = 0; k < 16; ++k)
+        if (j * 16 + k < n_cols && total[k]) atomicAdd(&missing[j * 16 + k], total[k]);
 }
 
 // Narrow matrices (<= 512 cells): `lanes_per_row` lanes share a row, one 32-bit word (16 cells)
@@ -628,9 +650,8 @@ int scs_gt_reduce(scs_ctx* ctx, const uint8_t* d_gt, int64_t pitch_bytes, int64_
         if (n_words <= 32) {
             scs_missing_count_narrow_kernel<<<unsigned(ctx->sm_count * 8), 256>>>(d_gt, pitch_bytes, n_snv, n_words, lanes, n_cells, d_row_keep, d_miss);
         } else {
-            const int nb = (n_cells + 3) / 4;
-            dim3 grid((nb + 127) / 128, unsigned(std::min<int64_t>(1024, std::max<int64_t>(1, n_snv / 256))));
-            scs_missing_count_kernel<<<grid, 128>>>(d_gt, pitch_bytes, n_snv, n_cells, d_row_keep, d_miss);
+            dim3 grid((n_words + 127) / 128, unsigned(std::min<int64_t>(2048, std::max<int64_t>(1, n_snv / 512))));
+            scs_missing_count_kernel<<<grid, 128>>>(d_gt, pitch_bytes, n_snv, n_cells, n_words, d_row_keep, d_miss);
         }
     }
     SCS_CUDA(cudaGetLastError());

@@ -666,17 +666,29 @@ __device__ __forceinline__ void expand_16_cells(const uint8_t* __restrict__ gt, 
     const int64_t src = rm.group_src0[g] + local;
     uint32_t w = 0;
     if (kq * 4 < gt_pitch && kq * 16 < n_cells) w = *reinterpret_cast<const uint32_t*>(gt + src * gt_pitch + kq * 4);
-    uint32_t o1[4] = {0, 0, 0, 0}, o0[4] = {0, 0, 0, 0};
+    const int left = n_cells - kq * 16;                 // cells of this group that exist (may be <= 0 or >= 16)
+    if (left < 16) w &= left <= 0 ? 0u : ((1u << (2 * left)) - 1u);      // trailing codes read as 0 ...
+    uint32_t o1[4], o0[4];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const uint32_t code = (w >> (2 * i)) & 3u;
-        const bool in = kq * 16 + i < n_cells;
-        const bool mut = in && (code == 1u || code == 2u), wt = in && code == 0u;
+    for (int q = 0; q < 4; ++q) {
+        // spread the four 2-bit codes of byte q into the low bits of four bytes
+        uint32_t x = (w >> (8 * q)) & 0xFFu;
+        x = (x | (x << 12)) & 0x000F000Fu;
+        x = (x | (x << 6)) & 0x03030303u;
+        const uint32_t lo = x & 0x01010101u, hi = (x >> 1) & 0x01010101u;
+        uint32_t mut = lo ^ hi;                          // code 1 or 2
+        uint32_t wt = (lo | hi) ^ 0x01010101u;           // code 0
+        if (left < 16) {                                 // ... so mask them out of the wild-type plane
+            const int rem = left - 4 * q;
+            const uint32_t valid = rem >= 4 ? 0x01010101u : (rem <= 0 ? 0u : (0x01010101u >> (8 * (4 - rem))));
+            wt &= valid;
+        }
         if (radix) {
-            o1[i >> 2] |= uint32_t(mut ? E5M2_ONE : (wt ? E5M2_4096 : 0)) << (8 * (i & 3));   // one e5m2 plane: 1 / 4096 / 0
+            o1[q] = mut * uint32_t(E5M2_ONE) + wt * uint32_t(E5M2_4096);   // byte fields: 1.0 / 4096.0 / 0, no carries
+            o0[q] = 0;
         } else {
-            o1[i >> 2] |= uint32_t(mut) << (8 * (i & 3));
-            o0[i >> 2] |= uint32_t(wt) << (8 * (i & 3));
+            o1[q] = mut;
+            o0[q] = wt;
         }
     }
     *reinterpret_cast<uint4*>(x1 + row * K_pad + kq * 16) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
