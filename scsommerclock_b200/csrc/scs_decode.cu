@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(DEC_THREADS) scs_decode_lines_kernel(const Dec
     __shared__ int s_cnt[DEC_THREADS];
     __shared__ int s_hist[10];
     __shared__ int s_sum_het, s_sum_hom, s_any_true, s_err;
-    __shared__ int s_gt_idx, s_tg_idx, s_filter_ok, s_ab_alt, s_mode, s_nsub;
+    __shared__ int s_gt_idx, s_tg_idx, s_filter_ok, s_ab_alt, s_mode;
     const int tid = threadIdx.x;
     for (int64_t line = blockIdx.x; line < p.n_lines; line += gridDim.x) {
         int64_t s = p.line_start[line], e = p.line_start[line + 1];
@@ -166,7 +166,6 @@ __global__ void __launch_bounds__(DEC_THREADS) scs_decode_lines_kernel(const Dec
                         tok = i + 1;
                     }
                 }
-                s_nsub = idx;
                 if (s_gt_idx < 0) s_err = PERR_NOGT;
             }
         }
