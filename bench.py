@@ -97,10 +97,12 @@ class ClockSampler(threading.Thread):
     def summary(self):
         sm, reasons, mx = [], set(), None
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        power = []
         for r in self.rows:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
+                power.append(float(r[2]))
             except Exception:
                 continue
             for k, nm in enumerate(names):
@@ -109,7 +111,8 @@ class ClockSampler(threading.Thread):
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": mx, "reasons": [], "samples": 0}
         busy = sorted(sm)[len(sm) // 2:]        # upper half: samples taken under load
-        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "power_w": float(np.median(sorted(power)[len(power) // 2:])) if power else None}
 
 
 # ----------------------------------------------------------------- CPU arms
@@ -444,6 +447,11 @@ def main():
 
     if rank == 0:
         g = np.array(gemm_times)                         # [steps][pass1, merge, pass2, reduce]
+        fp8_yard = None                                  # sustained cuBLASLt FP8 GEMM measured on this pool (tools/measure_fp8_peak.py)
+        try:
+            fp8_yard = json.load(open(os.path.join(REPO, "profiles", "r01_fp8_yardstick.json")))["fp8_scaled_mm_8192"]["sustained_tflops"]
+        except Exception:
+            pass
         t_gemm = float(np.mean(np.concatenate([g[:, 0], g[:, 2]])))      # average launch of the dominant kernel
         flop = 2.0 * n_snv * n_rows * n_cols                             # algorithmic: SNV x cells x clade rows, 2 flop per MAC
         achieved = flop / (t_gemm / 1e3) / 1e12
@@ -467,6 +475,7 @@ def main():
                          "kernel": "scs_place_kernel (%s), avg of pass 1 and pass 2 launches" % (
                              "tcgen05 kind::f8f6f4, one radix-packed e5m2 plane" if plan_info["mode"] == 1 else "tcgen05 kind::i8, two u8 planes"),
                          "peak_8bit_equiv": 2 * peak, "frac_8bit_equiv": achieved / (2 * peak),
+                         "fp8_cublaslt_sustained_tflops": fp8_yard, "frac_vs_fp8_cublaslt_sustained": (achieved / fp8_yard) if fp8_yard else None,
                          "why_frac_exceeds_1": "MEASURED_PEAKS.json holds a bf16 figure only; this GEMM runs 8-bit operands (FP8 e5m2 / u8), whose tensor rate is twice bf16: against 2 x the measured bf16 rate the kernel sits at frac_8bit_equiv",
                          "algorithmic_flop_per_launch": flop, "ms_per_launch": t_gemm,
                          "pass1_ms": float(g[:, 0].mean()), "merge_ms": float(g[:, 1].mean()), "pass2_ms": float(g[:, 2].mean()),
