@@ -136,12 +136,19 @@ __device__ __forceinline__ void load_counts(uint32_t taddr, uint32_t use0, int n
         // first chunk initialises, further chunks (cells beyond 3968) accumulate
         ptx::tmem_ld_x32(taddr + (use0 & 3) * BLOCK_N, raw);
         ptx::tmem_ld_wait();
+        const float2 inv = make_float2(1.0f / 4096.0f, 1.0f / 4096.0f), m4096 = make_float2(-4096.0f, -4096.0f);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const float v = __uint_as_float(raw[i]);                   // C1 + 4096 * C0, exact
-            const float hi = truncf(v * (1.0f / 4096.0f));
-            f0[i] = hi;
-            f1[i] = fmaf(-4096.0f, hi, v);
+        for (int i = 0; i < 32; i += 2) {
+            // two columns per instruction (sm_100 packed fp32): v = C1 + 4096 * C0, exact
+            const float2 v = make_float2(__uint_as_float(raw[i]), __uint_as_float(raw[i + 1]));
+            float2 hi = __fmul2_rn(v, inv);
+            hi.x = truncf(hi.x);
+            hi.y = truncf(hi.y);
+            const float2 lo = __ffma2_rn(m4096, hi, v);
+            f0[i] = hi.x;
+            f0[i + 1] = hi.y;
+            f1[i] = lo.x;
+            f1[i + 1] = lo.y;
         }
 #pragma unroll 1
         for (int c = 1; c < nchunk; ++c) {
@@ -211,14 +218,20 @@ __device__ __forceinline__ void epilogue_tile(const PlaceParams& p, const GroupC
                 refv = cm;
             }
             if (nv >= 32) {
+                const float2 nb1 = make_float2(-b1, -b1), nb0 = make_float2(-b0, -b0);
+                const float2 a1h2 = make_float2(gc.a1h, gc.a1h), a0h2 = make_float2(gc.a0h, gc.a0h);
+                const float2 a1l2 = make_float2(gc.a1l, gc.a1l), a0l2 = make_float2(gc.a0l, gc.a0l);
+                float2 sum2 = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float e1 = f1[i] - b1;
-                    const float e0 = f0[i] - b0;
-                    const float sdiff = fmaf(gc.a1h, e1, gc.a0h * e0);   // exact operands, one rounding
-                    const float lo = fmaf(gc.a1l, e1, gc.a0l * e0);
-                    sum += ex2_approx(sdiff + lo);
+                for (int i = 0; i < 32; i += 2) {
+                    const float2 e1 = __fadd2_rn(make_float2(f1[i], f1[i + 1]), nb1);
+                    const float2 e0 = __fadd2_rn(make_float2(f0[i], f0[i + 1]), nb0);
+                    const float2 sdiff = __ffma2_rn(a1h2, e1, __fmul2_rn(a0h2, e0));   // exact operands, one rounding
+                    const float2 lo = __ffma2_rn(a1l2, e1, __fmul2_rn(a0l2, e0));
+                    const float2 x = __fadd2_rn(sdiff, lo);
+                    sum2 = __fadd2_rn(sum2, make_float2(ex2_approx(x.x), ex2_approx(x.y)));
                 }
+                sum += sum2.x + sum2.y;
             } else {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
@@ -240,14 +253,21 @@ __device__ __forceinline__ void epilogue_tile(const PlaceParams& p, const GroupC
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
             load_counts<MODE>(taddr + ch * 32, use0, p.nchunk, f1, f0);
+            const float2 nr1 = make_float2(-r1f, -r1f), nr0 = make_float2(-r0f, -r0f), nL = make_float2(-L, -L);
+            const float2 a1h2 = make_float2(gc.a1h, gc.a1h), a0h2 = make_float2(gc.a0h, gc.a0h);
+            const float2 a1l2 = make_float2(gc.a1l, gc.a1l), a0l2 = make_float2(gc.a0l, gc.a0l);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float e1 = f1[i] - r1f;
-                const float e0 = f0[i] - r0f;
-                const float sdiff = fmaf(gc.a1h, e1, gc.a0h * e0);
-                const float tl = fmaf(gc.a0l, e0, -L);
-                const float lo = fmaf(gc.a1l, e1, tl);
-                colacc[ch * 32 + i] += ex2_approx(sdiff + lo);
+            for (int i = 0; i < 32; i += 2) {
+                const float2 e1 = __fadd2_rn(make_float2(f1[i], f1[i + 1]), nr1);
+                const float2 e0 = __fadd2_rn(make_float2(f0[i], f0[i + 1]), nr0);
+                const float2 sdiff = __ffma2_rn(a1h2, e1, __fmul2_rn(a0h2, e0));
+                const float2 tl = __ffma2_rn(a0l2, e0, nL);
+                const float2 lo = __ffma2_rn(a1l2, e1, tl);
+                const float2 x = __fadd2_rn(sdiff, lo);
+                const float2 acc = __fadd2_rn(make_float2(colacc[ch * 32 + i], colacc[ch * 32 + i + 1]),
+                                              make_float2(ex2_approx(x.x), ex2_approx(x.y)));
+                colacc[ch * 32 + i] = acc.x;
+                colacc[ch * 32 + i + 1] = acc.y;
             }
         }
     }
