@@ -19,6 +19,7 @@
 // the internal node below branch k, or -1 for a leaf.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "scs_internal.h"
@@ -39,24 +40,55 @@ struct LrtProblem {
 
 struct LrtWork {
     // per branch
-    double *l, *g, *d, *dl;
+    double *l, *g, *d, *dl, *wq;
     // per internal node
     double *h, *Hd, *e, *D, *r, *x, *G;
     int *up, *order, *level, *levoff;
 };
 
-__device__ __forceinline__ double block_reduce(double v, double* sh, bool is_min) {
+// Thread group of one problem: a whole CTA (WARP = false; big trees) or a single warp
+// (WARP = true; small trees, where CTA barriers were a quarter of the stall samples).
+template <bool WARP>
+__device__ __forceinline__ void grp_sync() {
+    if (WARP) __syncwarp();
+    else __syncthreads();
+}
+
+template <bool WARP>
+__device__ __forceinline__ int grp_any(int pred) {
+    if (WARP) return __any_sync(0xffffffffu, pred);
+    return __syncthreads_or(pred);
+}
+
+// two reductions in one pass: a is summed, b is summed (B_MIN = false) or minimised (B_MIN = true)
+template <bool WARP, bool B_MIN>
+__device__ __forceinline__ void grp_reduce2(double& a, double& b, double* sh) {
     for (int o = 16; o > 0; o >>= 1) {
-        const double t = __shfl_xor_sync(0xffffffffu, v, o);
-        v = is_min ? fmin(v, t) : v + t;
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        const double t = __shfl_xor_sync(0xffffffffu, b, o);
+        b = B_MIN ? fmin(b, t) : b + t;
     }
+    if (WARP) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __syncthreads();
-    if (lane == 0) sh[warp] = v;
+    if (lane == 0) {
+        sh[2 * warp] = a;
+        sh[2 * warp + 1] = b;
+    }
     __syncthreads();
-    double out = sh[0];
-    for (int i = 1; i < (LRT_THREADS >> 5); ++i) out = is_min ? fmin(out, sh[i]) : out + sh[i];
-    return out;
+    a = sh[0];
+    b = sh[1];
+    for (int i = 1; i < (LRT_THREADS >> 5); ++i) {
+        a += sh[2 * i];
+        b = B_MIN ? fmin(b, sh[2 * i + 1]) : b + sh[2 * i + 1];
+    }
+}
+
+template <bool WARP>
+__device__ __forceinline__ double grp_sum(double v, double* sh) {
+    double z = 0.0;
+    grp_reduce2<WARP, false>(v, z, sh);
+    return v;
 }
 
 // Regularised upper incomplete gamma Q(a, x) = chi2.sf(2x, 2a): power series of
@@ -93,24 +125,26 @@ __device__ double gamma_q(double a, double x) {
 }
 
 // out[p*8 ..] = {LR, dof, on_bound, p_value, ll_H0, ll_H1, newton iterations, status}
-__global__ void __launch_bounds__(LRT_MAX_THREADS)
+template <bool WARP>
+__global__ void __launch_bounds__(WARP ? 32 : LRT_MAX_THREADS)
 scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ Ysrc, const int* __restrict__ gather,
                double* __restrict__ Yall, const double* __restrict__ wall, const int* __restrict__ child_all, LrtWork ws,
                double* __restrict__ out, double* __restrict__ x_out, int smem_mode) {
-    __shared__ double sh[LRT_MAX_THREADS / 32];
+    __shared__ double sh[WARP ? 2 : 2 * (LRT_MAX_THREADS / 32)];
     __shared__ int s_nlev;
     const LrtProblem pb = probs[blockIdx.x];
     const int nb = pb.n_br, m1 = nb / 2, tid = threadIdx.x;
     extern __shared__ double lrt_dyn[];
-    double *Y, *l, *g, *d, *dl, *h, *Hd, *e, *D, *r, *x, *G;
-    const double* w;
+    // Y: counts, later w*Y/scale_fac; wq: w/scale_fac; D holds 1/pivot
+    double *Y, *wq, *l, *g, *d, *dl, *h, *Hd, *e, *D, *r, *x, *G;
+    const double* wraw;
     const int* child;
     int *up, *order, *level, *levoff;
     if (smem_mode) {
         // small trees: the whole working set (a few KB) lives in shared memory
         double* q = lrt_dyn;
         Y = q; q += nb;
-        double* wq = q; q += nb;
+        wq = q; q += nb;
         l = q; q += nb;
         g = q; q += nb;
         d = q; q += nb;
@@ -133,11 +167,12 @@ scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ 
             wq[k] = wall[pb.br_off + k];
             cq[k] = child_all[pb.br_off + k];
         }
-        w = wq;
+        wraw = wq;
         child = cq;
     } else {
         Y = Yall + pb.br_off;
-        w = wall + pb.br_off;
+        wraw = wall + pb.br_off;
+        wq = ws.wq + pb.br_off;
         child = child_all + pb.br_off;
         l = ws.l + pb.br_off; g = ws.g + pb.br_off; d = ws.d + pb.br_off; dl = ws.dl + pb.br_off;
         h = ws.h + pb.node_off; Hd = ws.Hd + pb.node_off; e = ws.e + pb.node_off; D = ws.D + pb.node_off;
@@ -146,20 +181,19 @@ scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ 
     }
     // counts in branch order: straight copy, or a gather from per-node soft weights
     for (int k = tid; k < nb; k += LRT_THREADS) Y[k] = gather ? Ysrc[gather[pb.br_off + k]] : Ysrc[pb.br_off + k];
-    __syncthreads();
+    grp_sync<WARP>();
     double* res = out + size_t(blockIdx.x) * 8;
 
     // ---- sums, scale factor (run_PT_test.py:639-643)
-    double sY = 0.0, sH1 = 0.0, sW = 0.0;
+    double U = 0.0, ll_H1 = 0.0, wsum = 0.0, zero = 0.0;
     for (int k = tid; k < nb; k += LRT_THREADS) {
         const double y = Y[k];
-        sY += y;
-        sH1 += (y * log(y > 0.0 ? y : 1.0) - y) * w[k];
-        sW += w[k];
+        U += y;
+        ll_H1 += (y * log(y > 0.0 ? y : 1.0) - y) * wraw[k];
+        wsum += wraw[k];
     }
-    const double U = block_reduce(sY, sh, false);
-    const double ll_H1 = block_reduce(sH1, sh, false);
-    const double wsum = block_reduce(sW, sh, false);
+    grp_reduce2<WARP, false>(U, ll_H1, sh);
+    grp_reduce2<WARP, false>(wsum, zero, sh);
     double sf = 0.0;
     {
         const double steps[6] = {10000.0, 1000.0, 100.0, 10.0, 1.0, 0.1};
@@ -178,20 +212,16 @@ scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ 
 
     // ---- topology: up-branch of every internal node, levels, level order.  All of it in parallel:
     // with 10,000-leaf trees the obvious thread-0 loops were 5 of the kernel's 7 ms.
-    __shared__ int s_changed;
     for (int i = tid; i < m1; i += LRT_THREADS) {
         up[i] = -1;
         level[i] = 0;
     }
-    __syncthreads();
+    grp_sync<WARP>();
     for (int k = tid; k < nb; k += LRT_THREADS)
         if (child[k] >= 0) up[child[k]] = k;
     // level = 1 + max(level of internal children): relax until nothing changes (<= depth + 1 sweeps;
     // children have smaller indices, and a sweep may already see this sweep's updates -- harmless)
     for (int sweep = 0; sweep <= m1; ++sweep) {
-        __syncthreads();
-        if (tid == 0) s_changed = 0;
-        __syncthreads();
         int ch = 0;
         for (int i = tid; i < m1; i += LRT_THREADS) {
             int lv = 0;
@@ -203,33 +233,31 @@ scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ 
                 ch = 1;
             }
         }
-        if (ch) s_changed = 1;
-        __syncthreads();
-        if (!s_changed) break;
+        if (!grp_any<WARP>(ch)) break;   // also the barrier between sweeps
     }
     // counting sort by level: levoff[q] = first slot of level q in `order` (order inside a level is
     // irrelevant: the nodes of a level are independent)
     for (int q = tid; q <= m1 + 1; q += LRT_THREADS) levoff[q] = 0;
-    __syncthreads();
+    grp_sync<WARP>();
     for (int i = tid; i < m1; i += LRT_THREADS) atomicAdd(&levoff[level[i] + 1], 1);
-    __syncthreads();
+    grp_sync<WARP>();
+    int nlev = 0;
     if (tid == 0) {
-        int nlev = 0;
         for (int q = 0; q < m1; ++q) {
             if (levoff[q + 1] == 0) break;
             levoff[q + 1] += levoff[q];
             nlev = q + 1;
         }
-        s_nlev = nlev;
+        if (!WARP) s_nlev = nlev;
     }
-    __syncthreads();
-    const int nlev = s_nlev;
-    // scatter with per-level cursors kept in `order`'s tail-free companion: reuse G (doubles, unused yet) as ints
+    grp_sync<WARP>();
+    nlev = WARP ? __shfl_sync(0xffffffffu, nlev, 0) : s_nlev;
+    // scatter with per-level cursors: reuse G (doubles, unused yet) as ints
     int* cursor = reinterpret_cast<int*>(G);
     for (int q = tid; q < nlev; q += LRT_THREADS) cursor[q] = levoff[q];
-    __syncthreads();
+    grp_sync<WARP>();
     for (int i = tid; i < m1; i += LRT_THREADS) order[atomicAdd(&cursor[level[i]], 1)] = i;
-    __syncthreads();
+    grp_sync<WARP>();
 
     // ---- strictly feasible start: heights from the counts themselves, level by level
     {
@@ -245,18 +273,27 @@ scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ 
                 }
                 h[i] = hv;
             }
-            __syncthreads();
+            grp_sync<WARP>();
         }
-        double lmaxp = 0.0;
+        double lmaxp = 0.0, z = 0.0;
         for (int k = tid; k < nb; k += LRT_THREADS) {
             const double hc = child[k] >= 0 ? h[child[k]] : 0.0;
             lmaxp = fmax(lmaxp, h[k >> 1] - hc);
         }
-        const double lmax = -block_reduce(-lmaxp, sh, true);
+        lmaxp = -lmaxp;
+        grp_reduce2<WARP, true>(z, lmaxp, sh);
+        const double lmax = -lmaxp;
         const double sc = lmax >= 0.9 * U ? 0.9 * U / lmax : 1.0;
         if (sc != 1.0)
             for (int i = tid; i < m1; i += LRT_THREADS) h[i] *= sc;
-        __syncthreads();
+        // from here on the objective only needs w/scale_fac and w*Y/scale_fac
+        const double isf = 1.0 / sf;
+        for (int k = tid; k < nb; k += LRT_THREADS) {
+            const double wk = wraw[k] * isf;
+            wq[k] = wk;
+            Y[k] = wk * Y[k];
+        }
+        grp_sync<WARP>();
     }
 
     const double mu = LRT_MU;
@@ -269,20 +306,23 @@ scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ 
             const double hc = child[k] >= 0 ? h[child[k]] : 0.0;
             const double lk = h[k >> 1] - hc;
             const double a = lk - LRT_LMIN, b = U - lk;
+            const double il = 1.0 / lk, ia = 1.0 / a, ib = 1.0 / b;
+            const double wy = Y[k];
             l[k] = lk;
-            g[k] = w[k] * (1.0 - Y[k] / lk) / sf - mu / a + mu / b;
-            d[k] = w[k] * Y[k] / (lk * lk * sf) + mu / (a * a) + mu / (b * b);
-            if (it == 0) f0p += w[k] * (lk - Y[k] * log(lk)) / sf - mu * log(a * b);
+            g[k] = wq[k] - wy * il + mu * (ib - ia);
+            d[k] = wy * il * il + mu * (ia * ia + ib * ib);
+            if (it == 0) f0p += wq[k] * lk - wy * log(lk) - mu * log(a * b);
         }
-        if (it == 0) f0 = block_reduce(f0p, sh, false);
+        if (it == 0) f0 = grp_sum<WARP>(f0p, sh);
+        else grp_sync<WARP>();
         for (int i = tid; i < m1; i += LRT_THREADS) {
             const int u = up[i];
             G[i] = g[2 * i] + g[2 * i + 1] - (u >= 0 ? g[u] : 0.0);
             Hd[i] = d[2 * i] + d[2 * i + 1] + (u >= 0 ? d[u] : 0.0);
             e[i] = u >= 0 ? d[u] : 0.0;
         }
-        __syncthreads();
-        // leaf-to-root elimination, level by level
+        grp_sync<WARP>();
+        // leaf-to-root elimination, level by level (D holds the reciprocal pivots)
         for (int q = 0; q < nlev; ++q) {
             const int a0 = levoff[q], a1 = levoff[q + 1];
             for (int s = a0 + tid; s < a1; s += LRT_THREADS) {
@@ -291,15 +331,15 @@ scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ 
                 for (int c = 0; c < 2; ++c) {
                     const int j = child[2 * i + c];
                     if (j >= 0) {
-                        const double t = e[j] / D[j];
+                        const double t = e[j] * D[j];
                         Dv -= e[j] * t;
                         rv += t * r[j];
                     }
                 }
-                D[i] = Dv;
+                D[i] = 1.0 / Dv;
                 r[i] = rv;
             }
-            __syncthreads();
+            grp_sync<WARP>();
         }
         // root-to-leaf back substitution
         for (int q = nlev - 1; q >= 0; --q) {
@@ -307,22 +347,23 @@ scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ 
             for (int s = a0 + tid; s < a1; s += LRT_THREADS) {
                 const int i = order[s];
                 const int u = up[i];
-                x[i] = u >= 0 ? (r[i] + e[i] * x[u >> 1]) / D[i] : r[i] / D[i];
+                x[i] = (u >= 0 ? r[i] + e[i] * x[u >> 1] : r[i]) * D[i];
             }
-            __syncthreads();
+            grp_sync<WARP>();
         }
         // Newton decrement and the largest step that stays strictly inside the bounds
-        double decp = 0.0, amaxp = 1.0;
-        for (int i = tid; i < m1; i += LRT_THREADS) decp -= G[i] * x[i];
+        double dec = 0.0, amax = 1.0;
+        for (int i = tid; i < m1; i += LRT_THREADS) dec -= G[i] * x[i];
         for (int k = tid; k < nb; k += LRT_THREADS) {
             const double xc = child[k] >= 0 ? x[child[k]] : 0.0;
             const double dk = x[k >> 1] - xc;
             dl[k] = dk;
-            if (dk < 0.0) amaxp = fmin(amaxp, 0.99 * (l[k] - LRT_LMIN) / -dk);
-            if (dk > 0.0) amaxp = fmin(amaxp, 0.99 * (U - l[k]) / dk);
+            if (dk != 0.0) {
+                const double room = dk < 0.0 ? l[k] - LRT_LMIN : U - l[k];
+                amax = fmin(amax, 0.99 * room / fabs(dk));
+            }
         }
-        const double dec = block_reduce(decp, sh, false);
-        const double amax = block_reduce(amaxp, sh, true);
+        grp_reduce2<WARP, true>(dec, amax, sh);
         if (!(dec == dec)) {
             status = 3;   // NaN in the Newton system
             break;
@@ -333,7 +374,7 @@ scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ 
         // Armijo test could only compare rounding noise there.
         if (dec <= 1e-12 * fmax(1.0, fabs(f0))) {
             for (int i = tid; i < m1; i += LRT_THREADS) h[i] += amax * x[i];
-            __syncthreads();
+            grp_sync<WARP>();
             status = 0;
             ++it;
             break;
@@ -345,9 +386,9 @@ scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ 
             double fp = 0.0;
             for (int k = tid; k < nb; k += LRT_THREADS) {
                 const double lk = l[k] + a * dl[k];
-                fp += w[k] * (lk - Y[k] * log(lk)) / sf - mu * log((lk - LRT_LMIN) * (U - lk));
+                fp += wq[k] * lk - Y[k] * log(lk) - mu * log((lk - LRT_LMIN) * (U - lk));
             }
-            f1 = block_reduce(fp, sh, false);
+            f1 = grp_sum<WARP>(fp, sh);
             if (f1 <= f0 - 1e-4 * a * dec) {
                 ok = true;
                 break;
@@ -356,7 +397,7 @@ scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ 
         }
         if (ok)
             for (int i = tid; i < m1; i += LRT_THREADS) h[i] += a * x[i];
-        __syncthreads();
+        grp_sync<WARP>();
         if (!ok) {          // no step decreases the objective any more: at the numerical optimum
             status = 0;
             ++it;
@@ -365,17 +406,18 @@ scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ 
         f0 = f1;
     }
 
-    // ---- statistic and p-value (run_PT_test.py:683-695)
-    double sH0 = 0.0, sOB = 0.0;
+    // ---- statistic and p-value (run_PT_test.py:683-695), from the unscaled counts and weights
+    double ll_H0 = 0.0, sOB = 0.0;
     for (int k = tid; k < nb; k += LRT_THREADS) {
         const double hc = child[k] >= 0 ? h[child[k]] : 0.0;
         const double lk = h[k >> 1] - hc;
-        sH0 += (Y[k] * log(lk) - lk) * w[k];
+        const double y = gather ? Ysrc[gather[pb.br_off + k]] : Ysrc[pb.br_off + k];
+        ll_H0 += (y * log(lk) - lk) * wall[pb.br_off + k];
         sOB += (lk <= 1e-3) ? 1.0 : 0.0;
         if (x_out) x_out[pb.br_off + k] = lk;
     }
-    const double ll_H0 = block_reduce(sH0, sh, false);
-    const int on_bound = int(block_reduce(sOB, sh, false) + 0.5);
+    grp_reduce2<WARP, false>(ll_H0, sOB, sh);
+    const int on_bound = int(sOB + 0.5);
     const double LR = -2.0 * (ll_H0 - ll_H1);
     const double dof = rint(wsum - double(m1));
     // mixture over the number of parameters on the bound, binomial weights, in log space
@@ -393,8 +435,7 @@ scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ 
             den += wk;
         }
     }
-    num = block_reduce(num, sh, false);
-    den = block_reduce(den, sh, false);
+    grp_reduce2<WARP, false>(num, den, sh);
     if (tid == 0) {
         res[0] = LR;
         res[1] = dof;
@@ -463,6 +504,7 @@ struct LrtPlanImpl {
     long long launches = 0;
     int threads = 128;
     int smem_bytes = 0;    // > 0: per-CTA working set in shared memory (small trees)
+    bool warp_mode = false;   // one warp per problem (trees up to 256 leaves)
 };
 
 int scs_lrt_plan_create(scs_ctx* ctx, int32_t n_prob, const int64_t* br_off, const int32_t* child_int, scs_lrt_plan** out) {
@@ -492,12 +534,16 @@ int scs_lrt_plan_create(scs_ctx* ctx, int32_t n_prob, const int64_t* br_off, con
     pl->nbr = size_t(total_br);
     pl->nnode = size_t(node_off);
     pl->threads = max_nb >= 8192 ? 512 : (max_nb >= 2048 ? 256 : (max_nb > 256 ? 128 : 64));
+    // small trees: one warp per problem -- no CTA barriers in the level sweeps, shuffle-only reductions
+    pl->warp_mode = max_nb <= 512;
+    if (const char* ev = getenv("SCS_LRT_WARP")) pl->warp_mode = atoi(ev) != 0 && max_nb <= 1024;
+    if (pl->warp_mode) pl->threads = 32;
     if (max_nb <= 1024) {
         const size_t mn = size_t(max_nb / 2 + 2);
         pl->smem_bytes = int((6 * size_t(max_nb) + 7 * mn) * sizeof(double) + (size_t(max_nb) + 4 * mn) * sizeof(int));
     }
     const size_t nbr = pl->nbr, nnode = pl->nnode;
-    const size_t dbl = 8 * nbr /*Ysrc Y w l g d dl x*/ + 7 * nnode + size_t(n_prob) * 8;
+    const size_t dbl = 9 * nbr /*Ysrc Y w l g d dl x wq*/ + 7 * nnode + size_t(n_prob) * 8;
     const size_t ints = 2 * nbr /*child gather*/ + 4 * nnode;
     if (cudaMalloc(&pl->d_buf, dbl * sizeof(double)) != cudaSuccess || cudaMalloc(&pl->i_buf, ints * sizeof(int)) != cudaSuccess ||
         cudaMalloc(&pl->d_probs, size_t(n_prob) * sizeof(LrtProblem)) != cudaSuccess) {
@@ -513,6 +559,7 @@ int scs_lrt_plan_create(scs_ctx* ctx, int32_t n_prob, const int64_t* br_off, con
     pl->ws.d = q; q += nbr;
     pl->ws.dl = q; q += nbr;
     pl->d_x = q; q += nbr;
+    pl->ws.wq = q; q += nbr;
     pl->ws.h = q; q += nnode;
     pl->ws.Hd = q; q += nnode;
     pl->ws.e = q; q += nnode;
@@ -576,10 +623,17 @@ int scs_lrt_plan_run(scs_lrt_plan* h, const double* d_Y, double* d_out, double* 
     if (!pl || !d_Y) return set_error(SCS_ERR_ARG, "null argument");
     if (!pl->have_w) return set_error(SCS_ERR_ARG, "scs_lrt_plan_set_weights has not been called");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (pl->smem_bytes > 48 * 1024) cudaFuncSetAttribute(scs_lrt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->smem_bytes);
-    scs_lrt_kernel<<<pl->n_prob, pl->threads, pl->smem_bytes, st>>>(pl->d_probs, d_Y, pl->have_gather ? pl->d_gather : nullptr, pl->dY, pl->dw,
-                                                                    pl->d_child, pl->ws, d_out ? d_out : pl->d_out, d_x ? d_x : pl->d_x,
-                                                                    pl->smem_bytes > 0);
+    auto launch = [&](auto kern) {
+        if (pl->smem_bytes > 0) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->smem_bytes);
+            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        }
+        kern<<<pl->n_prob, pl->threads, pl->smem_bytes, st>>>(pl->d_probs, d_Y, pl->have_gather ? pl->d_gather : nullptr, pl->dY, pl->dw,
+                                                              pl->d_child, pl->ws, d_out ? d_out : pl->d_out, d_x ? d_x : pl->d_x,
+                                                              pl->smem_bytes > 0);
+    };
+    if (pl->warp_mode) launch(scs_lrt_kernel<true>);
+    else launch(scs_lrt_kernel<false>);
     pl->launches++;
     SCS_CUDA(cudaGetLastError());
     return SCS_OK;
