@@ -361,8 +361,9 @@ __global__ void scs_row_keep_kernel(const uint8_t* __restrict__ gt, int64_t pitc
     // ones.  A cell holds 1 or 2 exactly when its two code bits differ; active_mask has bit 2k of
     // word j set when cell 16j+k takes part in the filter.
     const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    const int64_t row = t / lanes_per_row;
-    const int sub = int(t - row * lanes_per_row);
+    const int shift = 31 - __clz(lanes_per_row);
+    const int64_t row = t >> shift;
+    const int sub = int(t) & (lanes_per_row - 1);
     uint32_t any = 0;
     if (row < n_rows) {   // (no early return: every thread reaches the block-wide count below)
         const uint32_t* r = reinterpret_cast<const uint32_t*>(gt + row * pitch);
@@ -420,33 +421,86 @@ __global__ void scs_missing_count_kernel(const uint8_t* __restrict__ gt, int64_t
         if (j * 16 + k < n_cols && total[k]) atomicAdd(&missing[j * 16 + k], total[k]);
 }
 
-// Narrow matrices (<= 512 cells): `lanes_per_row` lanes share a row, one 32-bit word (16 cells)
-// each; 16 register counters per lane, reduced over the warp's row slots, one atomic per cell.
-__global__ void scs_missing_count_narrow_kernel(const uint8_t* __restrict__ gt, int64_t pitch, int64_t n_rows, int n_words,
-                                                int lanes_per_row, int n_cols, const uint8_t* __restrict__ row_keep,
-                                                unsigned int* __restrict__ missing) {
-    const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    const int64_t nslots = int64_t(gridDim.x) * blockDim.x / lanes_per_row;
-    const int sub = int(t % lanes_per_row);
-    unsigned int c[16];
+// Narrow matrices (<= 512 cells, replicate batches): row filter AND missing counts in one pass over the
+// matrix.  2^lane_shift lanes share a row, one 32-bit word (16 cells) each; the lanes of a row OR their
+// "mutated" bits with shuffles, lane 0 of the row writes row_keep, and every lane adds the missing
+// (code 3) bits of a kept row to sixteen byte-wide SWAR counters (flushed before they can wrap).  Eight
+// independent rows per lane are in flight per iteration; loop bounds are warp-uniform so that every
+// lane reaches the shuffles.
+__global__ void __launch_bounds__(256, 4)
+scs_gt_reduce_narrow_kernel(const uint8_t* __restrict__ gt, int64_t pitch, int64_t n_rows, int n_words, int lane_shift, int n_cols,
+                            const uint32_t* __restrict__ active_mask, int filter_rows, uint8_t* __restrict__ row_keep,
+                            unsigned long long* __restrict__ n_kept, unsigned int* __restrict__ missing) {
+    constexpr int UNROLL = 8;
+    __shared__ unsigned int s_miss[512];
+    __shared__ unsigned int s_kept;
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_miss[i] = 0;
+    if (threadIdx.x == 0) s_kept = 0;
+    __syncthreads();
+    const int lanes = 1 << lane_shift;
+    const int sub = threadIdx.x & (lanes - 1);
+    const int64_t gtid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t nslots = (int64_t(gridDim.x) * blockDim.x) >> lane_shift;
+    const int64_t wslot = (gtid & ~int64_t(31)) >> lane_shift;       // first row slot of this warp
+    const int64_t my = (gtid >> lane_shift) - wslot;                 // this lane's slot inside the warp
+    const bool has = sub < n_words;
+    const uint32_t am = has ? active_mask[sub] : 0u;
+    unsigned int total[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) c[k] = 0;
-    if (sub < n_words) {
-        for (int64_t row = t / lanes_per_row; row < n_rows; row += nslots) {
-            if (!row_keep[row]) continue;
-            const uint32_t v = reinterpret_cast<const uint32_t*>(gt + row * pitch)[sub];
-            const uint32_t m = v & (v >> 1) & 0x55555555u;      // code 3 = both bits set
+    for (int k = 0; k < 16; ++k) total[k] = 0;
+    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    int pending = 0;
+    unsigned int kept_cnt = 0;
+    auto flush = [&]() {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) c[k] += (m >> (2 * k)) & 1u;
+        for (int b = 0; b < 4; ++b) {      // byte b of accumulator q holds cell 4*b + q
+            total[4 * b + 0] += (a0 >> (8 * b)) & 0xFFu;
+            total[4 * b + 1] += (a1 >> (8 * b)) & 0xFFu;
+            total[4 * b + 2] += (a2 >> (8 * b)) & 0xFFu;
+            total[4 * b + 3] += (a3 >> (8 * b)) & 0xFFu;
         }
+        a0 = a1 = a2 = a3 = 0;
+        pending = 0;
+    };
+    for (int64_t base = wslot; base < n_rows; base += nslots * UNROLL) {
+        uint32_t v[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t r = base + my + u * nslots;
+            v[u] = (has && r < n_rows) ? reinterpret_cast<const uint32_t*>(gt + r * pitch)[sub] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t r = base + my + u * nslots;
+            uint32_t any = ((v[u] ^ (v[u] >> 1)) & 0x55555555u) & am;   // a cell holds 1 or 2 exactly when its two bits differ
+            for (int o = lanes >> 1; o > 0; o >>= 1) any |= __shfl_xor_sync(0xffffffffu, any, o);
+            const bool kept = r < n_rows && (!filter_rows || any != 0);
+            if (sub == 0 && r < n_rows) {
+                row_keep[r] = uint8_t(kept);
+                kept_cnt += kept;
+            }
+            const uint32_t m = kept ? (v[u] & (v[u] >> 1)) : 0u;        // bit 2k set <=> cell k missing
+            a0 += m & 0x01010101u;
+            a1 += (m >> 2) & 0x01010101u;
+            a2 += (m >> 4) & 0x01010101u;
+            a3 += (m >> 6) & 0x01010101u;
+        }
+        pending += UNROLL;
+        if (pending > 255 - UNROLL) flush();
     }
+    flush();
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        unsigned int v = c[k];
-        for (int o = 16; o >= lanes_per_row; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        const int cell = sub * 16 + k;
-        if ((threadIdx.x & 31) < lanes_per_row && sub < n_words && cell < n_cols && v) atomicAdd(&missing[cell], v);
+        unsigned int c = total[k];
+        for (int o = 16; o >= lanes; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if ((threadIdx.x & 31) < lanes && has && c) atomicAdd(&s_miss[sub * 16 + k], c);
     }
+    for (int o = 16; o > 0; o >>= 1) kept_cnt += __shfl_xor_sync(0xffffffffu, kept_cnt, o);
+    if ((threadIdx.x & 31) == 0 && kept_cnt) atomicAdd(&s_kept, kept_cnt);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_words * 16; i += blockDim.x)
+        if (i < n_cols && s_miss[i]) atomicAdd(&missing[i], s_miss[i]);
+    if (threadIdx.x == 0 && s_kept) atomicAdd(n_kept, (unsigned long long)s_kept);     // integers: order-independent
 }
 
 struct Vcf {
@@ -643,12 +697,14 @@ int scs_gt_reduce(scs_ctx* ctx, const uint8_t* d_gt, int64_t pitch_bytes, int64_
     SCS_CUDA(cudaMemsetAsync(sc, 0, bytes, 0));
     SCS_CUDA(cudaMemcpyAsync(d_act, amask.data(), size_t(n_words) * 4, cudaMemcpyHostToDevice, 0));
     if (n_snv > 0) {
-        int lanes = 1;
-        while (lanes < 32 && lanes < n_words) lanes <<= 1;
-        scs_row_keep_kernel<<<unsigned((n_snv * lanes + 255) / 256), 256>>>(d_gt, pitch_bytes, n_snv, n_words, lanes, d_act, filter_rows, d_row_keep, d_kept);
         if (n_words <= 32) {
-            scs_missing_count_narrow_kernel<<<unsigned(ctx->sm_count * 8), 256>>>(d_gt, pitch_bytes, n_snv, n_words, lanes, n_cells, d_row_keep, d_miss);
+            int shift = 0;
+            while ((1 << shift) < n_words) ++shift;
+            const int64_t want = (n_snv * (int64_t(1) << shift) + 255) / 256;
+            const unsigned grid = unsigned(std::min<int64_t>(std::max<int64_t>(want, 1), int64_t(ctx->sm_count) * 4));
+            scs_gt_reduce_narrow_kernel<<<grid, 256>>>(d_gt, pitch_bytes, n_snv, n_words, shift, n_cells, d_act, filter_rows, d_row_keep, d_kept, d_miss);
         } else {
+            scs_row_keep_kernel<<<unsigned((n_snv * 32 + 255) / 256), 256>>>(d_gt, pitch_bytes, n_snv, n_words, 32, d_act, filter_rows, d_row_keep, d_kept);
             dim3 grid((n_words + 127) / 128, unsigned(std::min<int64_t>(2048, std::max<int64_t>(1, n_snv / 512))));
             scs_missing_count_kernel<<<grid, 128>>>(d_gt, pitch_bytes, n_snv, n_cells, n_words, d_row_keep, d_miss);
         }

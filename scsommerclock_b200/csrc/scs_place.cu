@@ -117,9 +117,12 @@ __device__ __forceinline__ float count_to_float(uint32_t c) {
 }
 
 // 32 consecutive columns of this thread's row: number of clade cells observed mutated (f1)
-// and observed wild type (f0), as exact integer-valued floats.
+// and observed wild type (f0, times F0_SCALE<MODE>), as exact integer-valued floats.
 // `taddr` = TMEM base + lane quarter + column offset inside a slot; `use0` = the tile's first
 // slot-use number (slot of accumulator c is (use0 + c) & 3, at column 128 * slot).
+template <int MODE>
+constexpr float F0_SCALE = MODE == MODE_RADIX ? 4096.0f : 1.0f;   // radix mode leaves C0 multiplied by its radix
+
 template <int MODE>
 __device__ __forceinline__ void load_counts(uint32_t taddr, uint32_t use0, int nchunk, float (&f1)[32], float (&f0)[32]) {
     uint32_t raw[32];
@@ -133,18 +136,19 @@ __device__ __forceinline__ void load_counts(uint32_t taddr, uint32_t use0, int n
 #pragma unroll
         for (int i = 0; i < 32; ++i) f0[i] = count_to_float(raw[i]);
     } else {
-        // first chunk initialises, further chunks (cells beyond 3968) accumulate
+        // first chunk initialises, further chunks (cells beyond 3968) accumulate.
+        // v = C1 + 4096 * C0 < 2^24 is split on the FMA pipe (FRND shares the quarter-rate pipe with
+        // ex2 and was half of its load): adding 1.5 * 2^35 with round-toward-zero drops the bits
+        // below 4096 (ulp there is 2^12), so t - magic = 4096 * C0 and v - that = C1, all exact.
         ptx::tmem_ld_x32(taddr + (use0 & 3) * BLOCK_N, raw);
         ptx::tmem_ld_wait();
-        const float2 inv = make_float2(1.0f / 4096.0f, 1.0f / 4096.0f), m4096 = make_float2(-4096.0f, -4096.0f);
+        const float2 magic = make_float2(51539607552.0f, 51539607552.0f), nmagic = make_float2(-51539607552.0f, -51539607552.0f);
+        const float2 neg1 = make_float2(-1.0f, -1.0f);
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-            // two columns per instruction (sm_100 packed fp32): v = C1 + 4096 * C0, exact
             const float2 v = make_float2(__uint_as_float(raw[i]), __uint_as_float(raw[i + 1]));
-            float2 hi = __fmul2_rn(v, inv);
-            hi.x = truncf(hi.x);
-            hi.y = truncf(hi.y);
-            const float2 lo = __ffma2_rn(m4096, hi, v);
+            const float2 hi = __fadd2_rn(__fadd2_rz(v, magic), nmagic);     // 4096 * C0
+            const float2 lo = __ffma2_rn(neg1, hi, v);                      // C1
             f0[i] = hi.x;
             f0[i + 1] = hi.y;
             f1[i] = lo.x;
@@ -155,11 +159,14 @@ __device__ __forceinline__ void load_counts(uint32_t taddr, uint32_t use0, int n
             ptx::tmem_ld_x32(taddr + ((use0 + c) & 3) * BLOCK_N, raw);
             ptx::tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float v = __uint_as_float(raw[i]);
-                const float hi = truncf(v * (1.0f / 4096.0f));
-                f0[i] += hi;
-                f1[i] += fmaf(-4096.0f, hi, v);
+            for (int i = 0; i < 32; i += 2) {
+                const float2 v = make_float2(__uint_as_float(raw[i]), __uint_as_float(raw[i + 1]));
+                const float2 hi = __fadd2_rn(__fadd2_rz(v, magic), nmagic);
+                const float2 lo = __ffma2_rn(neg1, hi, v);
+                f0[i] += hi.x;
+                f0[i + 1] += hi.y;
+                f1[i] += lo.x;
+                f1[i + 1] += lo.y;
             }
         }
     }
@@ -178,6 +185,9 @@ template <int PASS, int MODE>
 __device__ __forceinline__ void epilogue_tile(const PlaceParams& p, const GroupConst& gc, uint32_t taddr, uint32_t use0, int row,
                                               int jl, int hh, int col0, int n_valid, float (&colacc)[64]) {
     float f1[32], f0[32];
+    // wild-type counts arrive scaled by a power of two: fold it into their constants (exact)
+    constexpr float F0S = F0_SCALE<MODE>, F0I = 1.0f / F0_SCALE<MODE>;
+    const float a0h = gc.a0h * F0I, a0l = gc.a0l * F0I, a0f = gc.a0f * F0I;
     if (PASS == PASS_DUMP) {
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
@@ -186,7 +196,7 @@ __device__ __forceinline__ void epilogue_tile(const PlaceParams& p, const GroupC
             for (int i = 0; i < 32; ++i) {
                 const size_t o = (size_t(row) * p.N_pad + col0 + ch * 32 + i) * 2;
                 p.dump[o] = int(f1[i]);
-                p.dump[o + 1] = int(f0[i]);
+                p.dump[o + 1] = int(f0[i] * F0I);
             }
         }
     } else if (PASS == PASS_STATS) {
@@ -202,7 +212,7 @@ __device__ __forceinline__ void epilogue_tile(const PlaceParams& p, const GroupC
             float cm = -INFINITY, c1 = 0.f, c0 = 0.f;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                const float v = fmaf(gc.a1f, f1[i], gc.a0f * f0[i]);
+                const float v = fmaf(gc.a1f, f1[i], a0f * f0[i]);
                 const bool take = (i < nv) && (v > cm);
                 cm = take ? v : cm;
                 c1 = take ? f1[i] : c1;
@@ -211,7 +221,7 @@ __device__ __forceinline__ void epilogue_tile(const PlaceParams& p, const GroupC
             if (cm > refv + 16.0f) {
                 if (refv != -INFINITY) {
                     const float e1 = b1 - c1, e0 = b0 - c0;
-                    sum *= ex2_approx(fmaf(gc.a1h, e1, gc.a0h * e0) + fmaf(gc.a1l, e1, gc.a0l * e0));
+                    sum *= ex2_approx(fmaf(gc.a1h, e1, a0h * e0) + fmaf(gc.a1l, e1, a0l * e0));
                 }
                 b1 = c1;
                 b0 = c0;
@@ -219,8 +229,8 @@ __device__ __forceinline__ void epilogue_tile(const PlaceParams& p, const GroupC
             }
             if (nv >= 32) {
                 const float2 nb1 = make_float2(-b1, -b1), nb0 = make_float2(-b0, -b0);
-                const float2 a1h2 = make_float2(gc.a1h, gc.a1h), a0h2 = make_float2(gc.a0h, gc.a0h);
-                const float2 a1l2 = make_float2(gc.a1l, gc.a1l), a0l2 = make_float2(gc.a0l, gc.a0l);
+                const float2 a1h2 = make_float2(gc.a1h, gc.a1h), a0h2 = make_float2(a0h, a0h);
+                const float2 a1l2 = make_float2(gc.a1l, gc.a1l), a0l2 = make_float2(a0l, a0l);
                 float2 sum2 = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
@@ -237,25 +247,25 @@ __device__ __forceinline__ void epilogue_tile(const PlaceParams& p, const GroupC
                 for (int i = 0; i < 32; ++i) {
                     const float e1 = f1[i] - b1;
                     const float e0 = f0[i] - b0;
-                    const float sdiff = fmaf(gc.a1h, e1, gc.a0h * e0);
-                    const float lo = fmaf(gc.a1l, e1, gc.a0l * e0);
+                    const float sdiff = fmaf(gc.a1h, e1, a0h * e0);
+                    const float lo = fmaf(gc.a1l, e1, a0l * e0);
                     sum += (i < nv) ? ex2_approx(sdiff + lo) : 0.f;
                 }
             }
         }
-        const uint32_t pk = uint32_t(b1) | (uint32_t(b0) << 16);
+        const uint32_t pk = uint32_t(b1) | (uint32_t(b0 * F0I) << 16);
         p.stats[size_t(jl * 2 + hh) * p.M_pad + row] = make_uint2(pk, __float_as_uint(sum));
     } else {
         const uint2 rr = p.rowref[row];
         const float r1f = float(rr.x & 0xFFFFu);
-        const float r0f = float(rr.x >> 16);
+        const float r0f = float(rr.x >> 16) * F0S;
         const float L = __uint_as_float(rr.y);     // +inf for padded / dropped rows: 2^(-inf) = 0
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
             load_counts<MODE>(taddr + ch * 32, use0, p.nchunk, f1, f0);
             const float2 nr1 = make_float2(-r1f, -r1f), nr0 = make_float2(-r0f, -r0f), nL = make_float2(-L, -L);
-            const float2 a1h2 = make_float2(gc.a1h, gc.a1h), a0h2 = make_float2(gc.a0h, gc.a0h);
-            const float2 a1l2 = make_float2(gc.a1l, gc.a1l), a0l2 = make_float2(gc.a0l, gc.a0l);
+            const float2 a1h2 = make_float2(gc.a1h, gc.a1h), a0h2 = make_float2(a0h, a0h);
+            const float2 a1l2 = make_float2(gc.a1l, gc.a1l), a0l2 = make_float2(a0l, a0l);
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
                 const float2 e1 = __fadd2_rn(make_float2(f1[i], f1[i + 1]), nr1);

@@ -57,15 +57,36 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// try_wait with a suspend-time hint: the thread may sleep in hardware until the phase completes or
+// the hint (ns) runs out, instead of burning issue slots that the epilogue warps need.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0;
+}
 // Bounded wait: a protocol bug must surface as a launch failure (trap), never
-// as a hung GPU.  ~4e9 cycles is seconds of wall clock, far beyond any tile.
+// as a hung GPU.  The clock is read once per 256 polls (reading it on every poll was 15 % of
+// the small-tree kernels' instructions); the limit is seconds of wall clock, far beyond any tile.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {
-            printf("scs: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-            __trap();
+    long long t0 = 0;
+    uint32_t polls = 0;
+    while (!mbar_try_wait_hint(bar, parity, 100000u)) {
+        if ((++polls & 0xFFu) == 0) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000LL) {
+                printf("scs: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+                __trap();
+            }
         }
     }
 }
