@@ -283,6 +283,195 @@ __device__ __forceinline__ void epilogue_tile(const PlaceParams& p, const GroupC
     }
 }
 
+// ---- radix mode, one K chunk (<= 3968 cells): the same epilogue, software pipelined ------
+// With short K the tensor work is negligible and the epilogue warps (two per scheduler) are
+// latency bound, so every TMEM load is issued before the arithmetic on the previous one.
+constexpr int STATS_W = 32;   // columns per TMEM load in the pipelined pass-1 epilogue
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[16]) { ptx::tmem_ld_x16(taddr, r); }
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[32]) { ptx::tmem_ld_x32(taddr, r); }
+__device__ __forceinline__ void tmem_wait_cols(uint32_t (&r)[16]) { ptx::tmem_ld_wait16(r); }
+__device__ __forceinline__ void tmem_wait_cols(uint32_t (&r)[32]) { ptx::tmem_ld_wait32(r); }
+
+template <int W>
+__device__ __forceinline__ void decode_cols(const uint32_t (&raw)[W], float (&f1)[W], float (&f0)[W]) {
+    const float2 magic = make_float2(51539607552.0f, 51539607552.0f), nmagic = make_float2(-51539607552.0f, -51539607552.0f);
+    const float2 neg1 = make_float2(-1.0f, -1.0f);
+#pragma unroll
+    for (int i = 0; i < W; i += 2) {
+        const float2 v = make_float2(__uint_as_float(raw[i]), __uint_as_float(raw[i + 1]));
+        const float2 hi = __fadd2_rn(__fadd2_rz(v, magic), nmagic);     // 4096 * C0 (see load_counts)
+        const float2 lo = __ffma2_rn(neg1, hi, v);                      // C1
+        f0[i] = hi.x;
+        f0[i + 1] = hi.y;
+        f1[i] = lo.x;
+        f1[i + 1] = lo.y;
+    }
+}
+
+struct StatsState {
+    float refv, b1, b0, sum;   // running reference column (rank value, counts) and sum relative to it
+};
+
+// pass 1, W (16 or 32) columns: same running-reference rule as epilogue_tile<PASS_STATS>
+template <int W>
+__device__ __forceinline__ void stats_cols(const GroupConst& gc, float a0h, float a0l, float a0f, const uint32_t (&raw)[W], int nv,
+                                           StatsState& st) {
+    float f1[W], f0[W];
+    decode_cols<W>(raw, f1, f0);
+    // Best column by rank value a1*C1 + a0*C0 (plain fp32: it only ranks).  The column index rides
+    // in the low mantissa bits of the key, so one max tree yields both the value and the position,
+    // and the winner's packed counts are picked from `raw` by a select tree -- a third fewer
+    // instructions than carrying (value, C1, C0) through W compare/selects.
+    constexpr uint32_t IDX_MASK = W - 1;
+    float key[W];
+    {
+        const float2 a1f2 = make_float2(gc.a1f, gc.a1f), a0f2 = make_float2(a0f, a0f);
+#pragma unroll
+        for (int i = 0; i < W; i += 2) {
+            const float2 v = __ffma2_rn(a1f2, make_float2(f1[i], f1[i + 1]), __fmul2_rn(a0f2, make_float2(f0[i], f0[i + 1])));
+            key[i] = __uint_as_float((__float_as_uint(v.x) & ~IDX_MASK) | uint32_t(i));
+            key[i + 1] = __uint_as_float((__float_as_uint(v.y) & ~IDX_MASK) | uint32_t(i + 1));
+        }
+        if (nv < W) {
+#pragma unroll
+            for (int i = 0; i < W; ++i)
+                if (i >= nv) key[i] = -3.0e38f;
+        }
+    }
+#pragma unroll
+    for (int n = W / 2; n >= 1; n >>= 1) {
+#pragma unroll
+        for (int i = 0; i < n; ++i) key[i] = fmaxf(key[2 * i], key[2 * i + 1]);
+    }
+    const float cm = key[0];
+    if (cm > st.refv + 16.0f) {
+        const uint32_t idx = __float_as_uint(cm) & IDX_MASK;
+        uint32_t sel[W];
+#pragma unroll
+        for (int i = 0; i < W; ++i) sel[i] = raw[i];
+#pragma unroll
+        for (int n = W / 2, bit = 1; n >= 1; n >>= 1, bit <<= 1) {
+            const bool pb = (idx & uint32_t(bit)) != 0;
+#pragma unroll
+            for (int i = 0; i < n; ++i) sel[i] = pb ? sel[2 * i + 1] : sel[2 * i];
+        }
+        const float vsel = __uint_as_float(sel[0]);
+        const float c0 = __fadd_rn(__fadd_rz(vsel, 51539607552.0f), -51539607552.0f);   // 4096 * C0
+        const float c1 = vsel - c0;
+        if (st.refv != -INFINITY) {
+            const float e1 = st.b1 - c1, e0 = st.b0 - c0;
+            st.sum *= ex2_approx(fmaf(gc.a1h, e1, a0h * e0) + fmaf(gc.a1l, e1, a0l * e0));
+        }
+        st.b1 = c1;
+        st.b0 = c0;
+        st.refv = cm;
+    }
+    if (nv >= W) {
+        const float2 nb1 = make_float2(-st.b1, -st.b1), nb0 = make_float2(-st.b0, -st.b0);
+        const float2 a1h2 = make_float2(gc.a1h, gc.a1h), a0h2 = make_float2(a0h, a0h);
+        const float2 a1l2 = make_float2(gc.a1l, gc.a1l), a0l2 = make_float2(a0l, a0l);
+        float2 sum2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < W; i += 2) {
+            const float2 e1 = __fadd2_rn(make_float2(f1[i], f1[i + 1]), nb1);
+            const float2 e0 = __fadd2_rn(make_float2(f0[i], f0[i + 1]), nb0);
+            const float2 sdiff = __ffma2_rn(a1h2, e1, __fmul2_rn(a0h2, e0));   // exact operands, one rounding
+            const float2 lo = __ffma2_rn(a1l2, e1, __fmul2_rn(a0l2, e0));
+            const float2 x = __fadd2_rn(sdiff, lo);
+            sum2 = __fadd2_rn(sum2, make_float2(ex2_approx(x.x), ex2_approx(x.y)));
+        }
+        st.sum += sum2.x + sum2.y;
+    } else {
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+            const float e1 = f1[i] - st.b1;
+            const float e0 = f0[i] - st.b0;
+            const float sdiff = fmaf(gc.a1h, e1, a0h * e0);
+            const float lo = fmaf(gc.a1l, e1, a0l * e0);
+            st.sum += (i < nv) ? ex2_approx(sdiff + lo) : 0.f;
+        }
+    }
+}
+
+// pass 2, 16 columns starting at accumulator OFF
+template <int OFF>
+__device__ __forceinline__ void colsum16(const GroupConst& gc, float a0h, float a0l, const uint32_t (&raw)[16], float r1f, float r0f,
+                                         float L, float (&colacc)[64]) {
+    float f1[16], f0[16];
+    decode_cols<16>(raw, f1, f0);
+    const float2 nr1 = make_float2(-r1f, -r1f), nr0 = make_float2(-r0f, -r0f), nL = make_float2(-L, -L);
+    const float2 a1h2 = make_float2(gc.a1h, gc.a1h), a0h2 = make_float2(a0h, a0h);
+    const float2 a1l2 = make_float2(gc.a1l, gc.a1l), a0l2 = make_float2(a0l, a0l);
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+        const float2 e1 = __fadd2_rn(make_float2(f1[i], f1[i + 1]), nr1);
+        const float2 e0 = __fadd2_rn(make_float2(f0[i], f0[i + 1]), nr0);
+        const float2 sdiff = __ffma2_rn(a1h2, e1, __fmul2_rn(a0h2, e0));
+        const float2 tl = __ffma2_rn(a0l2, e0, nL);
+        const float2 lo = __ffma2_rn(a1l2, e1, tl);
+        const float2 x = __fadd2_rn(sdiff, lo);
+        const float2 acc = __fadd2_rn(make_float2(colacc[OFF + i], colacc[OFF + i + 1]), make_float2(ex2_approx(x.x), ex2_approx(x.y)));
+        colacc[OFF + i] = acc.x;
+        colacc[OFF + i + 1] = acc.y;
+    }
+}
+
+// `taddr` = TMEM address of this thread's row, this warp's 64-column half, in the tile's slot
+template <int PASS>
+__device__ __forceinline__ void epilogue_tile_r1(const PlaceParams& p, const GroupConst& gc, uint32_t taddr, int row, int jl, int hh,
+                                                 int n_valid, float (&colacc)[64]) {
+    constexpr float F0S = 4096.0f, F0I = 1.0f / 4096.0f;
+    const float a0h = gc.a0h * F0I, a0l = gc.a0l * F0I, a0f = gc.a0f * F0I;
+    if (n_valid <= 0) {                    // (uniform over the warp) nothing to do in this half
+        if (PASS == PASS_STATS) p.stats[size_t(jl * 2 + hh) * p.M_pad + row] = make_uint2(0u, 0u);
+        return;
+    }
+    if (PASS == PASS_STATS) {
+        constexpr int W = STATS_W;
+        uint32_t wa[W], wb[W];
+        StatsState st = {-INFINITY, 0.f, 0.f, 0.f};
+        tmem_ld_cols(taddr, wa);
+#pragma unroll
+        for (int c = 0; c < 64 / W; c += 2) {
+            tmem_wait_cols(wa);
+            if (n_valid > (c + 1) * W) tmem_ld_cols(taddr + (c + 1) * W, wb);
+            stats_cols<W>(gc, a0h, a0l, a0f, wa, n_valid - c * W, st);
+            if (n_valid > (c + 1) * W) {
+                tmem_wait_cols(wb);
+                if ((c + 2) * W < 64 && n_valid > (c + 2) * W) tmem_ld_cols(taddr + (c + 2) * W, wa);
+                stats_cols<W>(gc, a0h, a0l, a0f, wb, n_valid - (c + 1) * W, st);
+            }
+            if (n_valid <= (c + 2) * W) break;
+        }
+        const uint32_t pk = uint32_t(st.b1) | (uint32_t(st.b0 * F0I) << 16);
+        p.stats[size_t(jl * 2 + hh) * p.M_pad + row] = make_uint2(pk, __float_as_uint(st.sum));
+    } else {
+        const uint2 rr = p.rowref[row];
+        const float r1f = float(rr.x & 0xFFFFu);
+        const float r0f = float(rr.x >> 16) * F0S;
+        const float L = __uint_as_float(rr.y);     // +inf for padded / dropped rows: 2^(-inf) = 0
+        uint32_t ra[16], rb[16];
+        ptx::tmem_ld_x16(taddr, ra);
+        ptx::tmem_ld_wait16(ra);
+        if (n_valid > 16) ptx::tmem_ld_x16(taddr + 16, rb);
+        colsum16<0>(gc, a0h, a0l, ra, r1f, r0f, L, colacc);
+        if (n_valid > 16) {
+            ptx::tmem_ld_wait16(rb);
+            if (n_valid > 32) ptx::tmem_ld_x16(taddr + 32, ra);
+            colsum16<16>(gc, a0h, a0l, rb, r1f, r0f, L, colacc);
+        }
+        if (n_valid > 32) {
+            ptx::tmem_ld_wait16(ra);
+            if (n_valid > 48) ptx::tmem_ld_x16(taddr + 48, rb);
+            colsum16<32>(gc, a0h, a0l, ra, r1f, r0f, L, colacc);
+        }
+        if (n_valid > 48) {
+            ptx::tmem_ld_wait16(rb);
+            colsum16<48>(gc, a0h, a0l, rb, r1f, r0f, L, colacc);
+        }
+    }
+}
+
 // End of a run (pass 2): rows -> one number per column: lanes, then the four lane quarters.
 __device__ __forceinline__ void epilogue_flush_columns(const PlaceParams& p, float* red, const float (&colacc)[64], int q, int hh,
                                                        int lane, int run, int j) {
@@ -307,7 +496,7 @@ __device__ __forceinline__ void epilogue_flush_columns(const PlaceParams& p, flo
 
 // 10 warps are allocated as 12 (warp slots come in fours), which caps the kernel at
 // 65536 / 384 = 168 registers per thread; the 64-accumulator pass-2 epilogue spills a few.
-template <int PASS, int MODE>
+template <int PASS, int MODE, int R1 = 0>   // R1: radix mode with one K chunk -> pipelined epilogue
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x0,
                  const __grid_constant__ CUtensorMap tm_s, const PlaceParams p) {
@@ -469,7 +658,10 @@ scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constan
                 const int row = r * BLOCK_M + q * 32 + lane;
                 const uint32_t use0 = tile_n * spt;
                 const uint32_t taddr = tmem_base + lane_base + hh * 64;
-                epilogue_tile<PASS, MODE>(p, gc, taddr, use0, row, te.jl, hh, col0, n_valid, colacc);
+                if (R1)
+                    epilogue_tile_r1<PASS>(p, gc, taddr + (use0 & 3) * BLOCK_N, row, te.jl, hh, n_valid, colacc);
+                else
+                    epilogue_tile<PASS, MODE>(p, gc, taddr, use0, row, te.jl, hh, col0, n_valid, colacc);
                 // this tile's slots are drained: hand them back to the MMA warp
                 ptx::tc_fence_before();
                 __syncwarp();
@@ -851,7 +1043,9 @@ static int make_u8_tmap(CUtensorMap* tm, void* base, uint64_t rows, uint64_t k_p
 template <int PASS>
 static void launch_place(int mode, int grid, cudaStream_t st, const CUtensorMap& a1, const CUtensorMap& a0, const CUtensorMap& b,
                          const PlaceParams& p) {
-    if (mode == MODE_RADIX)
+    if (mode == MODE_RADIX && p.nchunk == 1 && PASS != PASS_DUMP)
+        scs_place_kernel<PASS, MODE_RADIX, (PASS != PASS_DUMP)><<<grid, NUM_THREADS, ModeCfg<MODE_RADIX>::SMEM_TOTAL, st>>>(a1, a0, b, p);
+    else if (mode == MODE_RADIX)
         scs_place_kernel<PASS, MODE_RADIX><<<grid, NUM_THREADS, ModeCfg<MODE_RADIX>::SMEM_TOTAL, st>>>(a1, a0, b, p);
     else
         scs_place_kernel<PASS, MODE_PLANES><<<grid, NUM_THREADS, ModeCfg<MODE_PLANES>::SMEM_TOTAL, st>>>(a1, a0, b, p);
@@ -867,6 +1061,9 @@ static void set_place_smem() {
     cudaFuncSetAttribute(scs_place_kernel2<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_TOTAL);
     cudaFuncSetAttribute(scs_place_kernel<PASS, MODE_PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModeCfg<MODE_PLANES>::SMEM_TOTAL);
     cudaFuncSetAttribute(scs_place_kernel<PASS, MODE_RADIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModeCfg<MODE_RADIX>::SMEM_TOTAL);
+    if (PASS != PASS_DUMP)
+        cudaFuncSetAttribute(scs_place_kernel<PASS, MODE_RADIX, (PASS != PASS_DUMP)>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             ModeCfg<MODE_RADIX>::SMEM_TOTAL);
 }
 
 struct Placement {
