@@ -183,7 +183,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // One tile (this thread's row, its 64-column half) from TMEM.
 template <int PASS, int MODE>
 __device__ __forceinline__ void epilogue_tile(const PlaceParams& p, const GroupConst& gc, uint32_t taddr, uint32_t use0, int row,
-                                              int jl, int hh, int col0, int n_valid, float (&colacc)[64]) {
+                                              int jl, int hh, int col0, int n_valid, float (&colacc)[64], uint2 rr) {
     float f1[32], f0[32];
     // wild-type counts arrive scaled by a power of two: fold it into their constants (exact)
     constexpr float F0S = F0_SCALE<MODE>, F0I = 1.0f / F0_SCALE<MODE>;
@@ -256,7 +256,7 @@ __device__ __forceinline__ void epilogue_tile(const PlaceParams& p, const GroupC
         const uint32_t pk = uint32_t(b1) | (uint32_t(b0 * F0I) << 16);
         p.stats[size_t(jl * 2 + hh) * p.M_pad + row] = make_uint2(pk, __float_as_uint(sum));
     } else {
-        const uint2 rr = p.rowref[row];
+        // rr = rowref[row], loaded by the caller one tile ahead
         const float r1f = float(rr.x & 0xFFFFu);
         const float r0f = float(rr.x >> 16) * F0S;
         const float L = __uint_as_float(rr.y);     // +inf for padded / dropped rows: 2^(-inf) = 0
@@ -419,7 +419,7 @@ __device__ __forceinline__ void colsum16(const GroupConst& gc, float a0h, float 
 // `taddr` = TMEM address of this thread's row, this warp's 64-column half, in the tile's slot
 template <int PASS>
 __device__ __forceinline__ void epilogue_tile_r1(const PlaceParams& p, const GroupConst& gc, uint32_t taddr, int row, int jl, int hh,
-                                                 int n_valid, float (&colacc)[64]) {
+                                                 int n_valid, float (&colacc)[64], uint2 rr) {
     constexpr float F0S = 4096.0f, F0I = 1.0f / 4096.0f;
     const float a0h = gc.a0h * F0I, a0l = gc.a0l * F0I, a0f = gc.a0f * F0I;
     if (n_valid <= 0) {                    // (uniform over the warp) nothing to do in this half
@@ -446,7 +446,6 @@ __device__ __forceinline__ void epilogue_tile_r1(const PlaceParams& p, const Gro
         const uint32_t pk = uint32_t(st.b1) | (uint32_t(st.b0 * F0I) << 16);
         p.stats[size_t(jl * 2 + hh) * p.M_pad + row] = make_uint2(pk, __float_as_uint(st.sum));
     } else {
-        const uint2 rr = p.rowref[row];
         const float r1f = float(rr.x & 0xFFFFu);
         const float r0f = float(rr.x >> 16) * F0S;
         const float L = __uint_as_float(rr.y);     // +inf for padded / dropped rows: 2^(-inf) = 0
@@ -641,9 +640,20 @@ scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constan
         const uint32_t lane_base = uint32_t(q * 32) << 16;
         const int spt = MODE == MODE_PLANES ? 2 : p.nchunk;
         uint32_t tile_n = 0;
+        // task entry and its group's constants are fetched one task ahead (two dependent loads)
+        TaskEntry te_next = {};
+        GroupConst gc_next = {};
+        if (R1 && int(blockIdx.x) < p.num_tasks) {      // (short tasks only: long-K kernels are short of registers)
+            te_next = p.tasks[blockIdx.x];
+            gc_next = p.gconst[te_next.group];
+        }
         for (int t = blockIdx.x; t < p.num_tasks; t += gridDim.x) {
-            const TaskEntry te = p.tasks[t];
-            const GroupConst gc = p.gconst[te.group];
+            const TaskEntry te = R1 ? te_next : p.tasks[t];
+            const GroupConst gc = R1 ? gc_next : p.gconst[te.group];
+            if (R1 && t + int(gridDim.x) < p.num_tasks) {
+                te_next = p.tasks[t + gridDim.x];
+                gc_next = p.gconst[te_next.group];
+            }
             const int j = te.j, r0 = te.r0, r1 = te.r1;
             const int col0 = j * BLOCK_N + hh * 64;
             const int n_valid = max(0, min(64, te.nvalid - hh * 64));
@@ -652,16 +662,21 @@ scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constan
 #pragma unroll
                 for (int i = 0; i < 64; ++i) colacc[i] = 0.f;
             }
+            // pass 2 needs rowref[row]: fetched one tile ahead so that the DRAM latency hides behind a tile
+            uint2 rr = make_uint2(0u, 0u), rr_next = make_uint2(0u, 0u);
+            if (PASS == PASS_COLSUM) rr = p.rowref[r0 * BLOCK_M + q * 32 + lane];
             for (int r = r0; r < r1; ++r, ++tile_n) {
+                const int row = r * BLOCK_M + q * 32 + lane;
+                if (PASS == PASS_COLSUM && r + 1 < r1) rr_next = p.rowref[row + BLOCK_M];
                 ptx::mbar_wait(&tfull_bar[tile_n & 3], (tile_n >> 2) & 1);
                 ptx::tc_fence_after();
-                const int row = r * BLOCK_M + q * 32 + lane;
                 const uint32_t use0 = tile_n * spt;
                 const uint32_t taddr = tmem_base + lane_base + hh * 64;
                 if (R1)
-                    epilogue_tile_r1<PASS>(p, gc, taddr + (use0 & 3) * BLOCK_N, row, te.jl, hh, n_valid, colacc);
+                    epilogue_tile_r1<PASS>(p, gc, taddr + (use0 & 3) * BLOCK_N, row, te.jl, hh, n_valid, colacc, rr);
                 else
-                    epilogue_tile<PASS, MODE>(p, gc, taddr, use0, row, te.jl, hh, col0, n_valid, colacc);
+                    epilogue_tile<PASS, MODE>(p, gc, taddr, use0, row, te.jl, hh, col0, n_valid, colacc, rr);
+                rr = rr_next;
                 // this tile's slots are drained: hand them back to the MMA warp
                 ptx::tc_fence_before();
                 __syncwarp();
@@ -845,7 +860,8 @@ scs_place_kernel2(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 const int row = (2 * q + int(rank)) * BLOCK_M + q4 * 32 + lane;
                 const uint32_t use0 = tile_n * spt;
                 const uint32_t taddr = tmem_base + lane_base + hh * 64;
-                epilogue_tile<PASS, MODE_RADIX>(p, gc, taddr, use0, row, j, hh, col0, n_valid, colacc);
+                epilogue_tile<PASS, MODE_RADIX>(p, gc, taddr, use0, row, j, hh, col0, n_valid, colacc,
+                                                PASS == PASS_COLSUM ? p.rowref[row] : make_uint2(0u, 0u));
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0)
