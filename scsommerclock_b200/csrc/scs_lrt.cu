@@ -141,28 +141,30 @@ scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ 
     const int* child;
     int *up, *order, *level, *levoff;
     if (smem_mode) {
-        // small trees: the whole working set (a few KB) lives in shared memory
+        // small trees: the whole working set (a few KB) lives in shared memory.  Arrays whose
+        // lifetimes do not overlap share storage (more resident problems per SM): g is dead once
+        // the node gradient is formed and dl is written after the solve; d is dead once Hd/e are
+        // formed and the pivots D and right-hand sides r are written after that; level is only
+        // needed to build the level order, x only during the Newton solve.
         double* q = lrt_dyn;
         Y = q; q += nb;
         wq = q; q += nb;
         l = q; q += nb;
-        g = q; q += nb;
-        d = q; q += nb;
-        dl = q; q += nb;
+        g = dl = q; q += nb;
         const int mn = m1 + 2;
+        d = D = q; q += mn;      // d[0..nb) spans D and r (2 * mn >= nb)
+        r = q; q += mn;
         h = q; q += mn;
         Hd = q; q += mn;
         e = q; q += mn;
-        D = q; q += mn;
-        r = q; q += mn;
         x = q; q += mn;
         G = q; q += mn;
         int* iq = reinterpret_cast<int*>(q);
         int* cq = iq; iq += nb;
         up = iq; iq += mn;
         order = iq; iq += mn;
-        level = iq; iq += mn;
         levoff = iq;
+        level = reinterpret_cast<int*>(x);
         for (int k = tid; k < nb; k += LRT_THREADS) {
             wq[k] = wall[pb.br_off + k];
             cq[k] = child_all[pb.br_off + k];
@@ -540,7 +542,7 @@ int scs_lrt_plan_create(scs_ctx* ctx, int32_t n_prob, const int64_t* br_off, con
     if (pl->warp_mode) pl->threads = 32;
     if (max_nb <= 1024) {
         const size_t mn = size_t(max_nb / 2 + 2);
-        pl->smem_bytes = int((6 * size_t(max_nb) + 7 * mn) * sizeof(double) + (size_t(max_nb) + 4 * mn) * sizeof(int));
+        pl->smem_bytes = int((4 * size_t(max_nb) + 7 * mn) * sizeof(double) + (size_t(max_nb) + 3 * mn) * sizeof(int));
     }
     const size_t nbr = pl->nbr, nnode = pl->nnode;
     const size_t dbl = 9 * nbr /*Ysrc Y w l g d dl x wq*/ + 7 * nnode + size_t(n_prob) * 8;
