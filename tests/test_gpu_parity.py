@@ -81,6 +81,29 @@ def test_counts_bit_exact_and_soft_weights(ctx, monkeypatch, mode, n_snv, n_cell
     pl.close()
 
 
+def test_every_partial_column_tile_width(ctx):
+    """The single-K-chunk radix epilogue reads a tile in pipelined 16/32-column loads and skips
+    what lies beyond the last valid clade row: cover every boundary of the last column tile."""
+    rng = np.random.default_rng(99)
+    n_snv, n_cells = 300, 40
+    codes = rng.choice([0, 1, 2, 3], size=(n_snv, n_cells), p=[0.6, 0.2, 0.1, 0.1]).astype(np.uint8)
+    packed, pitch = engine.pack_genotypes(codes)
+    muts = np.where(codes == 3, np.nan, codes.astype(float))
+    for n_rows in [1, 2, 15, 16, 17, 31, 32, 33, 47, 48, 49, 63, 64, 65, 79, 80, 81, 95, 96, 97, 111, 112, 113, 127, 128, 129, 161, 193, 255]:
+        S = (rng.random((n_rows, n_cells)) < 0.3).astype(np.uint8)
+        S[-1] = 0
+        bits, words = engine.pack_clades(S)
+        pl = engine.Placement(ctx, n_snv, n_cells, n_rows)
+        assert pl.info()["mode"] == 1 and pl.info()["k_chunks"] == 1
+        pl.set_genotypes_host(packed, pitch)
+        pl.set_clades_host(bits, words)
+        C1, C0 = oracle_counts(codes, S)
+        cnt = pl.debug_counts()
+        assert np.array_equal(cnt[:, :, 0], C1) and np.array_equal(cnt[:, :, 1], C0), n_rows
+        assert_soft_close(pl.run_host(0.02, 0.2), O.map_mutations_gt(muts, S.astype(float), 0.02, 0.2))
+        pl.close()
+
+
 @pytest.mark.parametrize("mode", ["radix", "planes"])
 @pytest.mark.parametrize("n_snv,n_cells", [(300, 3968), (260, 4100), (140, 8100), (130, 10000), (130, 12500), (129, 15872)])
 def test_counts_bit_exact_dense_many_cells(ctx, monkeypatch, mode, n_snv, n_cells):
@@ -433,24 +456,58 @@ def test_vcf_decode_rejects_malformed_input(ctx, tmp_path):
             P.get_mut_df(str(q), "", "", ctx=ctx)
 
 
-def test_gt_reduce_matches_numpy(ctx):
+@pytest.mark.parametrize("n_snv,n_cells", [(5000, 77), (1, 1), (333, 16), (4097, 17), (10000, 100), (2500, 250), (1500, 512),
+                                            (1200, 513), (900, 1000)])
+def test_gt_reduce_matches_numpy(ctx, n_snv, n_cells):
+    """Row filter + per-cell missing rates (run_PT_test.py:350-358): the fused narrow kernel
+    (<= 512 cells) and the wide pair of kernels."""
     import torch
-    rng = np.random.default_rng(8)
-    codes = rng.choice([0, 0, 0, 1, 2, 3], size=(5000, 77)).astype(np.uint8)
+    rng = np.random.default_rng(8 + n_cells)
+    codes = rng.choice([0, 0, 0, 1, 2, 3], size=(n_snv, n_cells)).astype(np.uint8)
     codes[::9] = np.where(codes[::9] == 3, 3, 0)
     packed, pitch = engine.pack_genotypes(codes)
-    active = np.ones(77, dtype=np.uint8)
-    active[[3, 76]] = 0
+    active = np.ones(n_cells, dtype=np.uint8)
+    if n_cells > 4:
+        active[[3, n_cells - 1]] = 0
     dev = torch.device("cuda", ctx.device)
     d = torch.as_tensor(packed, device=dev)
-    keep = torch.empty(5000, dtype=torch.uint8, device=dev)
-    n_kept, miss = engine.gt_reduce(ctx, d, pitch, 5000, 77, active, True, keep)
+    keep = torch.empty(n_snv, dtype=torch.uint8, device=dev)
+    n_kept, miss = engine.gt_reduce(ctx, d, pitch, n_snv, n_cells, active, True, keep)
     want_keep = (((codes == 1) | (codes == 2)) & active.astype(bool)[None, :]).any(axis=1)
     assert np.array_equal(keep.cpu().numpy().astype(bool), want_keep) and n_kept == want_keep.sum()
-    np.testing.assert_array_equal(miss, (codes[want_keep] == 3).mean(axis=0))
-    n_all, miss_all = engine.gt_reduce(ctx, d, pitch, 5000, 77, active, False, keep)
-    assert n_all == 5000
+    if want_keep.any():
+        np.testing.assert_array_equal(miss, (codes[want_keep] == 3).mean(axis=0))
+    n_all, miss_all = engine.gt_reduce(ctx, d, pitch, n_snv, n_cells, active, False, keep)
+    assert n_all == n_snv
     np.testing.assert_array_equal(miss_all, (codes == 3).mean(axis=0))
+
+
+def test_gt_reduce_many_rows_per_lane(ctx):
+    """Enough rows that every lane of the fused narrow kernel flushes its byte-wide counters
+    (> 255 rows per lane): random packed bytes on the device, checked with torch integer ops."""
+    import torch
+    dev = torch.device("cuda", ctx.device)
+    n_snv, n_cells, pitch = 45_000_000, 16, 16
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    d = torch.zeros((n_snv, pitch), dtype=torch.uint8, device=dev)
+    d[:, :4] = torch.randint(0, 256, (n_snv, 4), dtype=torch.uint8, device=dev, generator=g)
+    d[::3, :4] &= 0xF0           # rows with fewer mutated cells, some with none at all
+    d[::7, :4] = 0xCC            # only missing / wild type: dropped by the filter
+    active = np.ones(n_cells, dtype=np.uint8)
+    active[5] = 0
+    keep = torch.empty(n_snv, dtype=torch.uint8, device=dev)
+    n_kept, miss = engine.gt_reduce(ctx, d, pitch, n_snv, n_cells, active, True, keep)
+    want_keep = torch.zeros(n_snv, dtype=torch.bool, device=dev)
+    is3 = []
+    for c in range(n_cells):
+        code = (d[:, c // 4] >> (2 * (c % 4))) & 3
+        if active[c]:
+            want_keep |= (code == 1) | (code == 2)
+        is3.append(code == 3)
+    assert torch.equal(keep.bool(), want_keep) and n_kept == int(want_keep.sum())
+    want_miss = np.array([int((m & want_keep).sum()) for m in is3]) / n_kept
+    np.testing.assert_array_equal(miss, want_miss)
 
 
 # ------------------------------------------------------ weights and the LRT
