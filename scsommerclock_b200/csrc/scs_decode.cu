@@ -379,16 +379,23 @@ __global__ void scs_row_keep_kernel(const uint8_t* __restrict__ gt, int64_t pitc
     if (threadIdx.x == 0 && votes) atomicAdd(n_kept, (unsigned long long)votes);             // integer: order-independent
 }
 
-__global__ void scs_missing_count_kernel(const uint8_t* __restrict__ gt, int64_t pitch, int64_t n_rows, int n_cols, int n_words,
-                                         const uint8_t* __restrict__ row_keep, unsigned int* __restrict__ missing) {
+constexpr int MISS_REPL = 8;   // copies of the per-cell counters (spreads same-address atomics), summed on the host
+
+__global__ void __launch_bounds__(256)
+scs_missing_count_kernel(const uint8_t* __restrict__ gt, int64_t pitch, int64_t n_rows, int n_cols, int n_words,
+                         const uint8_t* __restrict__ row_keep, unsigned int* __restrict__ missing) {
     // Wide matrices: a thread owns one 32-bit word column (16 cells) over a slab of rows; loads are
-    // coalesced across the warp.  "Missing" (code 3) is both bits set.  The 16 counters are kept as
-    // four words of four byte-wide SWAR counters, flushed to 32-bit registers every 255 kept rows, so
-    // the loop is ~12 integer ops per 4 bytes and the kernel stays HBM bound.
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_words) return;
-    const int64_t slab = (n_rows + gridDim.y - 1) / gridDim.y;
-    const int64_t r0 = int64_t(blockIdx.y) * slab, r1 = min(n_rows, r0 + slab);
+    // coalesced across the warp and eight rows are in flight per thread (a dropped row's word is
+    // loaded and masked rather than skipped, which keeps the loads independent).  "Missing"
+    // (code 3) is both bits set.  The 16 counters are four words of byte-wide SWAR counters,
+    // flushed to 32-bit registers before they can wrap.  Block = 64 word columns x 4 row slabs,
+    // combined in shared memory: one atomic per cell and block, on one of MISS_REPL counter copies.
+    constexpr int UNROLL = 8;
+    __shared__ unsigned int part[3][64 * 16];
+    const int j = blockIdx.x * 64 + threadIdx.x;
+    const int64_t n_slabs = int64_t(gridDim.y) * 4;
+    const int64_t slab = (n_rows + n_slabs - 1) / n_slabs;
+    const int64_t r0 = (int64_t(blockIdx.y) * 4 + threadIdx.y) * slab, r1 = min(n_rows, r0 + slab);
     unsigned int total[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) total[k] = 0;
@@ -405,20 +412,42 @@ __global__ void scs_missing_count_kernel(const uint8_t* __restrict__ gt, int64_t
         a0 = a1 = a2 = a3 = 0;
         pending = 0;
     };
-    for (int64_t r = r0; r < r1; ++r) {
-        if (!row_keep[r]) continue;
-        const uint32_t v = reinterpret_cast<const uint32_t*>(gt + r * pitch)[j];
-        const uint32_t m = v & (v >> 1);    // bit 2k set <=> cell k missing
-        a0 += m & 0x01010101u;
-        a1 += (m >> 2) & 0x01010101u;
-        a2 += (m >> 4) & 0x01010101u;
-        a3 += (m >> 6) & 0x01010101u;
-        if (++pending == 255) flush();
-    }
-    flush();
+    if (j < n_words) {
+        for (int64_t r = r0; r < r1; r += UNROLL) {
+            uint32_t v[UNROLL];
+            bool keep[UNROLL];
 #pragma unroll
-    for (int k = 0; k < 16; ++k)
-        if (j * 16 + k < n_cols && total[k]) atomicAdd(&missing[j * 16 + k], total[k]);
+            for (int u = 0; u < UNROLL; ++u) {
+                const bool in = r + u < r1;
+                keep[u] = in && row_keep[in ? r + u : r] != 0;
+                v[u] = in ? reinterpret_cast<const uint32_t*>(gt + (r + u) * pitch)[j] : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const uint32_t m = keep[u] ? (v[u] & (v[u] >> 1)) : 0u;    // bit 2k set <=> cell k missing
+                a0 += m & 0x01010101u;
+                a1 += (m >> 2) & 0x01010101u;
+                a2 += (m >> 4) & 0x01010101u;
+                a3 += (m >> 6) & 0x01010101u;
+            }
+            pending += UNROLL;
+            if (pending > 255 - UNROLL) flush();
+        }
+        flush();
+    }
+    if (threadIdx.y > 0) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) part[threadIdx.y - 1][k * 64 + threadIdx.x] = total[k];
+    }
+    __syncthreads();
+    if (threadIdx.y == 0 && j < n_words) {
+        unsigned int* dst = missing + size_t(blockIdx.y % MISS_REPL) * n_cols;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const unsigned int t = total[k] + part[0][k * 64 + threadIdx.x] + part[1][k * 64 + threadIdx.x] + part[2][k * 64 + threadIdx.x];
+            if (j * 16 + k < n_cols && t) atomicAdd(&dst[j * 16 + k], t);
+        }
+    }
 }
 
 // Narrow matrices (<= 512 cells, replicate batches): row filter AND missing counts in one pass over the
@@ -684,7 +713,7 @@ int scs_gt_reduce(scs_ctx* ctx, const uint8_t* d_gt, int64_t pitch_bytes, int64_
     // scratch layout: [kept counter (8 B, padded to 16)] [active mask words] [missing counters]
     const int n_words = (n_cells + 15) / 16;
     const size_t off_mask = 16, off_miss = off_mask + size_t(n_words + 3) / 4 * 16;
-    const size_t bytes = off_miss + size_t(n_cells) * 4;
+    const size_t bytes = off_miss + size_t(n_cells) * 4 * MISS_REPL;
     uint8_t* sc = static_cast<uint8_t*>(ctx_scratch(ctx, bytes));
     if (!sc) return set_error(SCS_ERR_OOM, "device scratch allocation failed");
     unsigned long long* d_kept = reinterpret_cast<unsigned long long*>(sc);
@@ -705,17 +734,24 @@ int scs_gt_reduce(scs_ctx* ctx, const uint8_t* d_gt, int64_t pitch_bytes, int64_
             scs_gt_reduce_narrow_kernel<<<grid, 256>>>(d_gt, pitch_bytes, n_snv, n_words, shift, n_cells, d_act, filter_rows, d_row_keep, d_kept, d_miss);
         } else {
             scs_row_keep_kernel<<<unsigned((n_snv * 32 + 255) / 256), 256>>>(d_gt, pitch_bytes, n_snv, n_words, 32, d_act, filter_rows, d_row_keep, d_kept);
-            dim3 grid((n_words + 127) / 128, unsigned(std::min<int64_t>(2048, std::max<int64_t>(1, n_snv / 512))));
-            scs_missing_count_kernel<<<grid, 128>>>(d_gt, pitch_bytes, n_snv, n_cells, n_words, d_row_keep, d_miss);
+            // ~4 blocks of 64 x 4 threads per SM, at least 32 rows per thread
+            const unsigned gx = unsigned((n_words + 63) / 64);
+            const int64_t gy = std::max<int64_t>(1, std::min<int64_t>((n_snv + 127) / 128, (int64_t(ctx->sm_count) * 4 + gx - 1) / gx));
+            dim3 grid(gx, unsigned(std::min<int64_t>(gy, 65535))), block(64, 4);
+            scs_missing_count_kernel<<<grid, block>>>(d_gt, pitch_bytes, n_snv, n_cells, n_words, d_row_keep, d_miss);
         }
     }
     SCS_CUDA(cudaGetLastError());
-    std::vector<unsigned int> miss(n_cells);
+    std::vector<unsigned int> miss(size_t(n_cells) * MISS_REPL);
     unsigned long long kept = 0;
     SCS_CUDA(cudaMemcpy(&kept, d_kept, sizeof(kept), cudaMemcpyDeviceToHost));
-    SCS_CUDA(cudaMemcpy(miss.data(), d_miss, size_t(n_cells) * 4, cudaMemcpyDeviceToHost));
+    SCS_CUDA(cudaMemcpy(miss.data(), d_miss, miss.size() * 4, cudaMemcpyDeviceToHost));
     *n_kept = int64_t(kept);
-    for (int c = 0; c < n_cells; ++c) missing_frac[c] = kept > 0 ? double(miss[c]) / double(kept) : 0.0;
+    for (int c = 0; c < n_cells; ++c) {
+        unsigned long long m = 0;
+        for (int rep = 0; rep < MISS_REPL; ++rep) m += miss[size_t(rep) * n_cells + c];
+        missing_frac[c] = kept > 0 ? double(m) / double(kept) : 0.0;
+    }
     return SCS_OK;
 }
 

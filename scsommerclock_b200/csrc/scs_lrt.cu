@@ -540,7 +540,9 @@ int scs_lrt_plan_create(scs_ctx* ctx, int32_t n_prob, const int64_t* br_off, con
     pl->warp_mode = max_nb <= 512;
     if (const char* ev = getenv("SCS_LRT_WARP")) pl->warp_mode = atoi(ev) != 0 && max_nb <= 1024;
     if (pl->warp_mode) pl->threads = 32;
-    if (max_nb <= 1024) {
+    // the per-problem working set lives in shared memory while it fits one SM (~3,000 branches);
+    // beyond 1024 branches only a handful of CTAs are resident anyway
+    if (max_nb <= 3000) {
         const size_t mn = size_t(max_nb / 2 + 2);
         pl->smem_bytes = int((4 * size_t(max_nb) + 7 * mn) * sizeof(double) + (size_t(max_nb) + 3 * mn) * sizeof(int));
     }
