@@ -49,8 +49,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--replicates", type=int, default=256,
-                    help="replicate-sweep leg (BASELINE configs[4] shape: 100 cells x 10k SNVs each); 0 disables it")
+    ap.add_argument("--replicates", type=int, default=1250,
+                    help="replicate-sweep leg, replicates per GPU and step (BASELINE configs[4]: 10,000 pairs of 100 cells x 10k SNVs "
+                         "over 8 GPUs = 1250 per GPU); 0 disables it")
     ap.add_argument("--rep-cells", type=int, default=100)
     ap.add_argument("--rep-snvs", type=int, default=10000)
     return ap.parse_args()

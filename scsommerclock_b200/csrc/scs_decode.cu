@@ -381,21 +381,24 @@ __global__ void scs_row_keep_kernel(const uint8_t* __restrict__ gt, int64_t pitc
 
 constexpr int MISS_REPL = 8;   // copies of the per-cell counters (spreads same-address atomics), summed on the host
 
-__global__ void __launch_bounds__(256)
+constexpr int MISS_SLABS = 8;   // row slabs per block of the wide missing-count kernel
+
+__global__ void __launch_bounds__(64 * MISS_SLABS)
 scs_missing_count_kernel(const uint8_t* __restrict__ gt, int64_t pitch, int64_t n_rows, int n_cols, int n_words,
                          const uint8_t* __restrict__ row_keep, unsigned int* __restrict__ missing) {
     // Wide matrices: a thread owns one 32-bit word column (16 cells) over a slab of rows; loads are
     // coalesced across the warp and eight rows are in flight per thread (a dropped row's word is
     // loaded and masked rather than skipped, which keeps the loads independent).  "Missing"
     // (code 3) is both bits set.  The 16 counters are four words of byte-wide SWAR counters,
-    // flushed to 32-bit registers before they can wrap.  Block = 64 word columns x 4 row slabs,
-    // combined in shared memory: one atomic per cell and block, on one of MISS_REPL counter copies.
+    // flushed to 32-bit registers before they can wrap.  Block = 64 word columns x MISS_SLABS row
+    // slabs, combined in shared memory: one atomic per cell and block (atomic throughput, not HBM,
+    // bounded the first version), on one of MISS_REPL counter copies.
     constexpr int UNROLL = 8;
-    __shared__ unsigned int part[3][64 * 16];
+    __shared__ unsigned int part[MISS_SLABS - 1][64 * 16];
     const int j = blockIdx.x * 64 + threadIdx.x;
-    const int64_t n_slabs = int64_t(gridDim.y) * 4;
+    const int64_t n_slabs = int64_t(gridDim.y) * MISS_SLABS;
     const int64_t slab = (n_rows + n_slabs - 1) / n_slabs;
-    const int64_t r0 = (int64_t(blockIdx.y) * 4 + threadIdx.y) * slab, r1 = min(n_rows, r0 + slab);
+    const int64_t r0 = (int64_t(blockIdx.y) * MISS_SLABS + threadIdx.y) * slab, r1 = min(n_rows, r0 + slab);
     unsigned int total[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) total[k] = 0;
@@ -412,26 +415,30 @@ scs_missing_count_kernel(const uint8_t* __restrict__ gt, int64_t pitch, int64_t 
         a0 = a1 = a2 = a3 = 0;
         pending = 0;
     };
+    auto add = [&](uint32_t v, bool keep) {
+        const uint32_t m = keep ? (v & (v >> 1)) : 0u;    // bit 2k set <=> cell k missing
+        a0 += m & 0x01010101u;
+        a1 += (m >> 2) & 0x01010101u;
+        a2 += (m >> 4) & 0x01010101u;
+        a3 += (m >> 6) & 0x01010101u;
+    };
     if (j < n_words) {
-        for (int64_t r = r0; r < r1; r += UNROLL) {
+        int64_t r = r0;
+        for (; r + UNROLL <= r1; r += UNROLL) {      // full batches: plain loads, all issued before the first use
             uint32_t v[UNROLL];
-            bool keep[UNROLL];
+            uint8_t keep[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
-                const bool in = r + u < r1;
-                keep[u] = in && row_keep[in ? r + u : r] != 0;
-                v[u] = in ? reinterpret_cast<const uint32_t*>(gt + (r + u) * pitch)[j] : 0u;
+                v[u] = __ldg(reinterpret_cast<const uint32_t*>(gt + (r + u) * pitch) + j);
+                keep[u] = __ldg(row_keep + r + u);
             }
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const uint32_t m = keep[u] ? (v[u] & (v[u] >> 1)) : 0u;    // bit 2k set <=> cell k missing
-                a0 += m & 0x01010101u;
-                a1 += (m >> 2) & 0x01010101u;
-                a2 += (m >> 4) & 0x01010101u;
-                a3 += (m >> 6) & 0x01010101u;
-            }
+            for (int u = 0; u < UNROLL; ++u) add(v[u], keep[u] != 0);
             pending += UNROLL;
             if (pending > 255 - UNROLL) flush();
+        }
+        for (; r < r1; ++r) {                         // (< UNROLL rows: cannot overflow the byte counters)
+            add(__ldg(reinterpret_cast<const uint32_t*>(gt + r * pitch) + j), row_keep[r] != 0);
         }
         flush();
     }
@@ -444,7 +451,9 @@ scs_missing_count_kernel(const uint8_t* __restrict__ gt, int64_t pitch, int64_t 
         unsigned int* dst = missing + size_t(blockIdx.y % MISS_REPL) * n_cols;
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            const unsigned int t = total[k] + part[0][k * 64 + threadIdx.x] + part[1][k * 64 + threadIdx.x] + part[2][k * 64 + threadIdx.x];
+            unsigned int t = total[k];
+#pragma unroll
+            for (int y = 0; y < MISS_SLABS - 1; ++y) t += part[y][k * 64 + threadIdx.x];
             if (j * 16 + k < n_cols && t) atomicAdd(&dst[j * 16 + k], t);
         }
     }
@@ -491,24 +500,33 @@ scs_gt_reduce_narrow_kernel(const uint8_t* __restrict__ gt, int64_t pitch, int64
         a0 = a1 = a2 = a3 = 0;
         pending = 0;
     };
+    const int subc = min(sub, n_words - 1);                            // lanes beyond the row re-read its last word, masked below
+    const int rows_per_warp = 32 >> lane_shift;
     for (int64_t base = wslot; base < n_rows; base += nslots * UNROLL) {
         uint32_t v[UNROLL];
+        if (base + rows_per_warp - 1 + (UNROLL - 1) * nslots < n_rows) {   // (warp-uniform) whole batch inside: plain loads
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const int64_t r = base + my + u * nslots;
-            v[u] = (has && r < n_rows) ? reinterpret_cast<const uint32_t*>(gt + r * pitch)[sub] : 0u;
+            for (int u = 0; u < UNROLL; ++u)
+                v[u] = __ldg(reinterpret_cast<const uint32_t*>(gt + (base + my + u * nslots) * pitch) + subc);
+        } else {
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int64_t r = base + my + u * nslots;
+                v[u] = r < n_rows ? __ldg(reinterpret_cast<const uint32_t*>(gt + r * pitch) + subc) : 0u;
+            }
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const int64_t r = base + my + u * nslots;
-            uint32_t any = ((v[u] ^ (v[u] >> 1)) & 0x55555555u) & am;   // a cell holds 1 or 2 exactly when its two bits differ
+            const uint32_t w = has ? v[u] : 0u;
+            uint32_t any = ((w ^ (w >> 1)) & 0x55555555u) & am;      // a cell holds 1 or 2 exactly when its two bits differ
             for (int o = lanes >> 1; o > 0; o >>= 1) any |= __shfl_xor_sync(0xffffffffu, any, o);
             const bool kept = r < n_rows && (!filter_rows || any != 0);
             if (sub == 0 && r < n_rows) {
                 row_keep[r] = uint8_t(kept);
                 kept_cnt += kept;
             }
-            const uint32_t m = kept ? (v[u] & (v[u] >> 1)) : 0u;        // bit 2k set <=> cell k missing
+            const uint32_t m = kept ? (w & (w >> 1)) : 0u;           // bit 2k set <=> cell k missing
             a0 += m & 0x01010101u;
             a1 += (m >> 2) & 0x01010101u;
             a2 += (m >> 4) & 0x01010101u;
@@ -734,10 +752,11 @@ int scs_gt_reduce(scs_ctx* ctx, const uint8_t* d_gt, int64_t pitch_bytes, int64_
             scs_gt_reduce_narrow_kernel<<<grid, 256>>>(d_gt, pitch_bytes, n_snv, n_words, shift, n_cells, d_act, filter_rows, d_row_keep, d_kept, d_miss);
         } else {
             scs_row_keep_kernel<<<unsigned((n_snv * 32 + 255) / 256), 256>>>(d_gt, pitch_bytes, n_snv, n_words, 32, d_act, filter_rows, d_row_keep, d_kept);
-            // ~4 blocks of 64 x 4 threads per SM, at least 32 rows per thread
+            // 32..256 rows per thread: at least ~2 blocks per SM on small inputs, few atomics on big ones
             const unsigned gx = unsigned((n_words + 63) / 64);
-            const int64_t gy = std::max<int64_t>(1, std::min<int64_t>((n_snv + 127) / 128, (int64_t(ctx->sm_count) * 4 + gx - 1) / gx));
-            dim3 grid(gx, unsigned(std::min<int64_t>(gy, 65535))), block(64, 4);
+            const int64_t per_thread = std::max<int64_t>(32, std::min<int64_t>(256, n_snv / (int64_t(ctx->sm_count) * 2 * MISS_SLABS)));
+            const int64_t gy = std::max<int64_t>(1, (n_snv + per_thread * MISS_SLABS - 1) / (per_thread * MISS_SLABS));
+            dim3 grid(gx, unsigned(std::min<int64_t>(gy, 65535))), block(64, MISS_SLABS);
             scs_missing_count_kernel<<<grid, block>>>(d_gt, pitch_bytes, n_snv, n_cells, n_words, d_row_keep, d_miss);
         }
     }
