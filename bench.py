@@ -25,6 +25,10 @@ import time
 
 import numpy as np
 
+# stdout carries exactly one JSON line: if the environment turns NCCL's debug output on (it goes to
+# stdout by default, e.g. the version banner), send it to stderr instead
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
