@@ -119,12 +119,15 @@ int scs_placement_run_host(scs_placement* plan, double FP, double FN, double* so
 const void* scs_placement_device_result(scs_placement* plan);
 /* Device durations (CUDA events on the launching stream) of the four kernels of the
  * last scs_placement_run: ms[0] GEMM pass 1 (row statistics), ms[1] merge, ms[2]
- * GEMM pass 2 (column sums), ms[3] reduction.  Waits for that run to finish. */
+ * pass 2 (column sums: second GEMM pass or count-cache sweep), ms[3] reduction.  Waits for
+ * that run to finish. */
 int scs_placement_last_times(scs_placement* plan, float* ms);
 /* info[0..9] = M_pad, N_pad, K_pad, tasks, run_len, superblock_width, grid,
  * kernel launches so far, runs, dynamic smem bytes, operand mode (0 = two u8
  * planes / kind::i8, 1 = one radix-packed e5m2 plane / kind::f8f6f4), K chunks,
- * 1 when the 2-CTA (cta_group::2) kernel is used, groups */
+ * 1 when the 2-CTA (cta_group::2) kernel is used, groups, pass-2 mode (0 not run yet,
+ * 1 second GEMM pass, 2 sweep over the packed integer counts that pass 1 cached in HBM --
+ * chosen per plan, see SCS_PLACE_PASS2 in DESIGN.md) */
 int scs_placement_info(scs_placement* plan, int64_t* info, int32_t n);
 /* Parity aid for small problems: counts[i][b][0/1] = number of cells of clade b
  * observed mutated / observed wild type for SNV i (exact integers). */

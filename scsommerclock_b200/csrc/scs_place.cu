@@ -109,6 +109,7 @@ struct PlaceParams {
     const uint2* rowref;       // pass 2 in : [M_pad] {ref counts, log2 sum}
     float* colpart;            // pass 2 out: [num_runs][N_pad]
     int* dump;                 // debug     : [M_pad][N_pad][2] raw counts
+    uint32_t* cache;           // pass 1 out (optional): [row block][column tile][128][128] packed counts C1 | C0 << 16 (see scs_colsum_cached_kernel)
 };
 
 __device__ __forceinline__ float count_to_float(uint32_t c) {
@@ -208,6 +209,21 @@ __device__ __forceinline__ void epilogue_tile(const PlaceParams& p, const GroupC
         for (int ch = 0; ch < 2; ++ch) {
             if (ch * 32 >= n_valid) break;
             load_counts<MODE>(taddr + ch * 32, use0, p.nchunk, f1, f0);
+            if (p.cache != nullptr) {
+                // count cache: both counts of the 32 columns as C1 | C0 << 16 (exact: counts < 2^16),
+                // taken from the mantissas of count + 2^23; one 128-byte line per thread
+                // (tile-major layout, 64 KB per 128 x 128 tile: row-major rows are 80 KB apart at 10k cells,
+                // and 148 CTAs scattering 16-byte pieces over such rows cost pass 1 a sixth of its speed)
+                uint32_t* dst = p.cache + ((size_t(row >> 7) * (p.N_pad >> 7) + (col0 >> 7)) * BLOCK_M + (row & 127)) * BLOCK_N + (col0 & 127) + ch * 32;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        w[k] = __byte_perm(__float_as_uint(f1[i + k] + 8388608.0f), __float_as_uint(fmaf(f0[i + k], F0I, 8388608.0f)), 0x5410);
+                    __stcs(reinterpret_cast<uint4*>(dst + i), make_uint4(w[0], w[1], w[2], w[3]));   // streaming: keep the operand slabs in L2
+                }
+            }
             const int nv = n_valid - ch * 32;      // >= 32 except in the last column tile
             float cm = -INFINITY, c1 = 0.f, c0 = 0.f;
 #pragma unroll
@@ -979,13 +995,14 @@ __global__ void scs_expand_clades_kernel(const uint32_t* __restrict__ bits, int6
 // the reference counts of the globally best column and log2 sum_b 2^(logit-ref).
 __global__ void scs_merge_stats_kernel(const uint2* __restrict__ stats, int num_parts, int64_t M_pad, RowMap rm,
                                        const uint8_t* __restrict__ row_keep, const double2* __restrict__ gconst_d,
-                                       uint2* __restrict__ rowref) {
+                                       uint2* __restrict__ rowref, float4* __restrict__ rowref_f) {
     const int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (row >= M_pad) return;
     const int g = rm.group_of_unit[row >> 8];
     const int64_t local = row - rm.group_row0[g];
     if (local >= rm.group_nsnv[g] || (row_keep != nullptr && row_keep[rm.group_src0[g] + local] == 0)) {
         rowref[row] = make_uint2(0u, __float_as_uint(INFINITY));  // 2^(x - inf) = 0: row contributes nothing
+        if (rowref_f) rowref_f[row] = make_float4(-8388608.0f, -8388608.0f, -INFINITY, 0.f);
         return;
     }
     const double a1 = gconst_d[g].x, a0 = gconst_d[g].y;
@@ -1011,6 +1028,79 @@ __global__ void scs_merge_stats_kernel(const uint2* __restrict__ stats, int num_
         }
     }
     rowref[row] = make_uint2(best_pk, __float_as_uint(float(log2(total))));
+    // the same record for the cached pass 2: reference counts offset by 2^23, negated (see scs_colsum_cached_kernel)
+    if (rowref_f) rowref_f[row] = make_float4(-(8388608.0f + float(best_pk & 0xFFFFu)), -(8388608.0f + float(best_pk >> 16)), -float(log2(total)), 0.f);
+}
+
+// Pass 2 from the count cache (single-group plans with long K): the tensor work of a second GEMM
+// pass costs 2*K flops per (SNV, clade row) -- 140 ms at 10k cells -- while reading the 4-byte packed
+// counts back costs 4 bytes, so beyond ~2,000 cells the HBM round trip of the *counts* (not of the
+// floating-point SNV x branch matrix: the softmax terms are still formed on the fly, with the same
+// arithmetic on exact integer differences as the GEMM epilogue) is several times cheaper.
+// The cache is tile-major ([row block][column tile][128 rows][128 columns], 64 KB per tile); block = one
+// column tile over one run of row blocks.  A warp reads one whole 512-byte cache row per load (lane =
+// four adjacent clade columns, 16 bytes), the four warps take rows r, r+1, r+2, r+3, four loads in
+// flight per thread (64 bytes: ~64 KB per SM at full occupancy, enough to cover the HBM latency);
+// the arithmetic is the packed fp32x2 form of the GEMM epilogue's.  rowref_f holds the NEGATED
+// record {-(2^23 + R1), -(2^23 + R0), -log2 sum}, the same address for a whole warp (one broadcast).
+// Partial column sums land in colpart[run][col] like the GEMM pass 2.
+__global__ void __launch_bounds__(BLOCK_N)
+scs_colsum_cached_kernel(const uint32_t* __restrict__ cache, const float4* __restrict__ rowref_f, const GroupConst* __restrict__ gconst,
+                         int num_row_blocks, int64_t N_pad, int n_cols, int run_len, float* __restrict__ colpart) {
+    constexpr int UNROLL = 4;
+    __shared__ float red[4][BLOCK_N];
+    const int j = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const GroupConst gc = gconst[0];
+    const int rb0 = blockIdx.y * run_len, rb1 = min(num_row_blocks, rb0 + run_len);
+    const int64_t ct = N_pad / BLOCK_N;
+    const float2 a1h2 = make_float2(gc.a1h, gc.a1h), a0h2 = make_float2(gc.a0h, gc.a0h);
+    const float2 a1l2 = make_float2(gc.a1l, gc.a1l), a0l2 = make_float2(gc.a0l, gc.a0l);
+    float2 acc[UNROLL][2];      // one accumulator pair per load slot: short fp32 chains
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) acc[u][0] = acc[u][1] = make_float2(0.f, 0.f);
+    for (int rb = rb0; rb < rb1; ++rb) {
+        const uint4* src = reinterpret_cast<const uint4*>(cache + (size_t(rb) * ct + j) * (BLOCK_M * BLOCK_N)) + w * (BLOCK_N / 4) + lane;
+        const float4* ref = rowref_f + size_t(rb) * BLOCK_M + w;
+#pragma unroll 2
+        for (int r = 0; r < BLOCK_M; r += 4 * UNROLL) {
+            uint4 v[UNROLL];
+            float4 rr[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                v[u] = __ldcs(src + (r + 4 * u) * (BLOCK_N / 4));     // read once
+                rr[u] = __ldg(ref + r + 4 * u);
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const float2 n1 = make_float2(rr[u].x, rr[u].x), n0 = make_float2(rr[u].y, rr[u].y), nL = make_float2(rr[u].z, rr[u].z);
+                const uint32_t q[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    // count + 2^23 as a float straight from the bits; the reference already carries the 2^23
+                    const float2 e1 = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(q[2 * h], 0x4B000000u, 0x7610)),
+                                                             __uint_as_float(__byte_perm(q[2 * h + 1], 0x4B000000u, 0x7610))), n1);
+                    const float2 e0 = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(q[2 * h], 0x4B000000u, 0x7632)),
+                                                             __uint_as_float(__byte_perm(q[2 * h + 1], 0x4B000000u, 0x7632))), n0);
+                    const float2 sdiff = __ffma2_rn(a1h2, e1, __fmul2_rn(a0h2, e0));   // exact operands, one rounding
+                    const float2 lo = __ffma2_rn(a1l2, e1, __ffma2_rn(a0l2, e0, nL));
+                    const float2 x = __fadd2_rn(sdiff, lo);
+                    acc[u][h] = __fadd2_rn(acc[u][h], make_float2(ex2_approx(x.x), ex2_approx(x.y)));
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const float2 t = __fadd2_rn(__fadd2_rn(acc[0][h], acc[1][h]), __fadd2_rn(acc[2][h], acc[3][h]));
+        red[w][4 * lane + 2 * h] = t.x;
+        red[w][4 * lane + 2 * h + 1] = t.y;
+    }
+    __syncthreads();
+    // columns beyond the last clade row of the last tile were never written by pass 1: their sums are
+    // whatever the buffer held and are dropped here
+    const int col = j * BLOCK_N + threadIdx.x;
+    const float total = (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
+    colpart[size_t(blockIdx.y) * N_pad + col] = col < n_cols ? total : 0.f;
 }
 
 // Y[g][b] = sum over the group's runs of the per-run column partials, fixed order, fp64.
@@ -1059,7 +1149,7 @@ static int make_u8_tmap(CUtensorMap* tm, void* base, uint64_t rows, uint64_t k_p
 template <int PASS>
 static void launch_place(int mode, int grid, cudaStream_t st, const CUtensorMap& a1, const CUtensorMap& a0, const CUtensorMap& b,
                          const PlaceParams& p) {
-    if (mode == MODE_RADIX && p.nchunk == 1 && PASS != PASS_DUMP)
+    if (mode == MODE_RADIX && p.nchunk == 1 && PASS != PASS_DUMP && p.cache == nullptr)
         scs_place_kernel<PASS, MODE_RADIX, (PASS != PASS_DUMP)><<<grid, NUM_THREADS, ModeCfg<MODE_RADIX>::SMEM_TOTAL, st>>>(a1, a0, b, p);
     else if (mode == MODE_RADIX)
         scs_place_kernel<PASS, MODE_RADIX><<<grid, NUM_THREADS, ModeCfg<MODE_RADIX>::SMEM_TOTAL, st>>>(a1, a0, b, p);
@@ -1105,6 +1195,9 @@ struct Placement {
     bool have_row_keep = false;
     uint2* stats = nullptr;
     uint2* rowref = nullptr;
+    float4* rowref_f = nullptr;   // cached pass 2 only
+    uint32_t* cache = nullptr;    // [M_pad][N_pad] packed counts, allocated on first use
+    int pass2_mode = 0;           // 0 undecided, 1 recompute (second GEMM pass), 2 count cache
     float* colpart = nullptr;
     double* y = nullptr;
     int* dump = nullptr;
@@ -1348,6 +1441,8 @@ int scs_placement_destroy(scs_placement* h) {
     cudaFree(pl->s);
     cudaFree(pl->stats);
     cudaFree(pl->rowref);
+    cudaFree(pl->rowref_f);
+    cudaFree(pl->cache);
     cudaFree(pl->colpart);
     cudaFree(pl->y);
     cudaFree(pl->row_keep);
@@ -1464,6 +1559,36 @@ static void make_constants(int n_cells, double FP, double FN, GroupConst* gc, do
     gd->y = a0;
 }
 
+// How the softmax column sums (pass 2) are formed.  "recompute": a second GEMM pass, nothing but
+// 16 bytes per SNV kept between the passes.  "cache": pass 1 also writes the packed integer counts
+// (4 bytes per SNV x clade row) and pass 2 is an HBM-bound sweep over them -- cheaper than the tensor
+// work once K exceeds ~2,000 cells (measured at 10k cells: ~15 ms instead of 140 ms), at the price of
+// M_pad * N_pad * 4 bytes of HBM (80 GB for 1M SNVs x 20k clade rows; callers with less memory to
+// spare walk the SNV rows in chunks, engine.StreamingPlacement).  SCS_PLACE_PASS2 = recompute | cache
+// overrides; the default takes the cache when the plan is a single dataset with K >= 2560 cells and
+// the buffer fits the free device memory with 4 GB to spare, else recomputes.
+static void choose_pass2_mode(Placement* pl) {
+    pl->pass2_mode = 1;
+    const char* e = getenv("SCS_PLACE_PASS2");
+    if (e && !strcmp(e, "recompute")) return;
+    const bool forced = e && !strcmp(e, "cache");
+    if (pl->n_groups != 1 || pl->pair) return;
+    if (!forced && pl->K_pad < 2560) return;
+    const size_t bytes = size_t(pl->M_pad) * size_t(pl->N_pad) * sizeof(uint32_t);
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < bytes + (size_t(4) << 30)) return;
+    if (cudaMalloc(&pl->cache, bytes) != cudaSuccess || cudaMalloc(&pl->rowref_f, size_t(pl->M_pad) * sizeof(float4)) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(pl->cache);
+        cudaFree(pl->rowref_f);
+        pl->cache = nullptr;
+        pl->rowref_f = nullptr;
+        return;
+    }
+    pl->prm.cache = pl->cache;
+    pl->pass2_mode = 2;
+}
+
 // FP / FN: one value per group (per dataset).
 int scs_placement_run_batch(scs_placement* h, const double* FP, const double* FN, double* d_soft_weights, void* stream) {
     Placement* pl = reinterpret_cast<Placement*>(h);
@@ -1478,17 +1603,26 @@ int scs_placement_run_batch(scs_placement* h, const double* FP, const double* FN
     }
     SCS_CUDA(cudaMemcpyAsync(pl->d_gconst, gc.data(), gc.size() * sizeof(GroupConst), cudaMemcpyHostToDevice, st));
     SCS_CUDA(cudaMemcpyAsync(pl->d_gconst_d, gd.data(), gd.size() * sizeof(double2), cudaMemcpyHostToDevice, st));
+    if (pl->pass2_mode == 0) choose_pass2_mode(pl);
     const PlaceParams& p = pl->prm;
+    const bool cached = pl->pass2_mode == 2;
     cudaEventRecord(pl->ev[0], st);
     if (pl->pair) launch_place2<PASS_STATS>(pl->grid2, st, pl->tm_x1, pl->tm_s64, p);
     else launch_place<PASS_STATS>(pl->mode, pl->grid, st, pl->tm_x1, pl->tm_x0, pl->tm_s, p);
     cudaEventRecord(pl->ev[1], st);
     scs_merge_stats_kernel<<<unsigned((pl->M_pad + 255) / 256), 256, 0, st>>>(pl->stats, pl->num_parts, pl->M_pad, pl->rowmap,
                                                                               pl->have_row_keep ? pl->row_keep : nullptr, pl->d_gconst_d,
-                                                                              pl->rowref);
+                                                                              pl->rowref, cached ? pl->rowref_f : nullptr);
     cudaEventRecord(pl->ev[2], st);
-    if (pl->pair) launch_place2<PASS_COLSUM>(pl->grid2, st, pl->tm_x1, pl->tm_s64, p);
-    else launch_place<PASS_COLSUM>(pl->mode, pl->grid, st, pl->tm_x1, pl->tm_x0, pl->tm_s, p);
+    if (cached) {
+        dim3 grid(unsigned((pl->n_rows + BLOCK_N - 1) / BLOCK_N), unsigned(p.num_runs));
+        scs_colsum_cached_kernel<<<grid, BLOCK_N, 0, st>>>(pl->cache, pl->rowref_f, pl->d_gconst, p.num_row_blocks, pl->N_pad, pl->n_rows,
+                                                           p.run_len, pl->colpart);
+    } else if (pl->pair) {
+        launch_place2<PASS_COLSUM>(pl->grid2, st, pl->tm_x1, pl->tm_s64, p);
+    } else {
+        launch_place<PASS_COLSUM>(pl->mode, pl->grid, st, pl->tm_x1, pl->tm_x0, pl->tm_s, p);
+    }
     cudaEventRecord(pl->ev[3], st);
     double* y = d_soft_weights ? d_soft_weights : pl->y;
     const int64_t total_rows = int64_t(pl->n_groups) * pl->n_rows;
@@ -1566,10 +1700,10 @@ int scs_placement_debug_stats(scs_placement* h, void* stats_host, void* rowref_h
 int scs_placement_info(scs_placement* h, int64_t* info, int32_t n) {
     Placement* pl = reinterpret_cast<Placement*>(h);
     if (!pl || !info) return set_error(SCS_ERR_ARG, "null argument");
-    const int64_t v[14] = {pl->M_pad, pl->N_pad, pl->K_pad, pl->prm.num_tasks, pl->prm.run_len, pl->prm.sb_width, pl->pair ? pl->grid2 : pl->grid, pl->launches, pl->prm.num_runs,
+    const int64_t v[15] = {pl->M_pad, pl->N_pad, pl->K_pad, pl->prm.num_tasks, pl->prm.run_len, pl->prm.sb_width, pl->pair ? pl->grid2 : pl->grid, pl->launches, pl->prm.num_runs,
                            pl->pair ? K2_SMEM_TOTAL : (pl->mode == MODE_RADIX ? ModeCfg<MODE_RADIX>::SMEM_TOTAL : ModeCfg<MODE_PLANES>::SMEM_TOTAL),
-                           pl->mode, pl->prm.nchunk, pl->pair ? 1 : 0, pl->n_groups};
-    for (int i = 0; i < n && i < 14; ++i) info[i] = v[i];
+                           pl->mode, pl->prm.nchunk, pl->pair ? 1 : 0, pl->n_groups, pl->pass2_mode};
+    for (int i = 0; i < n && i < 15; ++i) info[i] = v[i];
     return SCS_OK;
 }
 

@@ -128,10 +128,10 @@ class Placement:
             pass
 
     def info(self):
-        v = (C.c_int64 * 14)()
-        check(lib().scs_placement_info(self._h, v, 14))
+        v = (C.c_int64 * 15)()
+        check(lib().scs_placement_info(self._h, v, 15))
         keys = ("M_pad", "N_pad", "K_pad", "tasks", "run_len", "superblock_width", "grid", "launches", "runs", "smem_bytes",
-                "mode", "k_chunks", "cta_pair", "groups")
+                "mode", "k_chunks", "cta_pair", "groups", "pass2_mode")
         return dict(zip(keys, (int(x) for x in v)))
 
     # host buffers (numpy)

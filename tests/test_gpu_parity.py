@@ -104,13 +104,15 @@ def test_every_partial_column_tile_width(ctx):
         pl.close()
 
 
+@pytest.mark.parametrize("pass2", ["recompute", "cache"])
 @pytest.mark.parametrize("mode", ["radix", "planes"])
 @pytest.mark.parametrize("n_snv,n_cells", [(300, 3968), (260, 4100), (140, 8100), (130, 10000), (130, 12500), (129, 15872)])
-def test_counts_bit_exact_dense_many_cells(ctx, monkeypatch, mode, n_snv, n_cells):
+def test_counts_bit_exact_dense_many_cells(ctx, monkeypatch, mode, pass2, n_snv, n_cells):
     """Worst case for the radix packing: dense random clade rows and genotypes put both
     counts of every K chunk (3968 cells) near their maximum; 1, 2, 3 and 4 chunks (with 4 chunks
     a tile fills the whole TMEM slot pool and the epilogue no longer overlaps the next tile)."""
     monkeypatch.setenv("SCS_PLACE_MODE", mode)
+    monkeypatch.setenv("SCS_PLACE_PASS2", pass2)     # second GEMM pass / sweep over the cached integer counts
     rng = np.random.default_rng(n_cells)
     n_rows = 256 if n_cells > 5000 else 384
     S = (rng.random((n_rows, n_cells)) < 0.9).astype(np.uint8)
@@ -133,7 +135,40 @@ def test_counts_bit_exact_dense_many_cells(ctx, monkeypatch, mode, n_snv, n_cell
     assert np.array_equal(cnt[:, :, 0], C1) and np.array_equal(cnt[:, :, 1], C0)
     muts = np.where(codes == 3, np.nan, codes.astype(float))
     assert_soft_close(pl.run_host(0.01, 0.1), O.map_mutations_gt(muts, S.astype(float), 0.01, 0.1))
+    assert pl.info()["pass2_mode"] == (2 if pass2 == "cache" else 1)
     pl.close()
+
+
+@pytest.mark.parametrize("n_snv,n_cells,n_rows", [(1000, 200, 400), (5000, 2600, 700), (300, 70, 1)])
+def test_count_cache_pass2_matches_recompute(ctx, monkeypatch, n_snv, n_cells, n_rows):
+    """Pass 2 from the cached integer counts (default for one dataset with >= 2560 cells) against
+    the second GEMM pass: same soft weights, with row filter, ragged tiles and several runs."""
+    rng = np.random.default_rng(n_cells)
+    S = (rng.random((n_rows, n_cells)) < 0.2).astype(np.uint8)
+    S[-1] = 0
+    codes = rng.choice([0, 1, 2, 3], size=(n_snv, n_cells), p=[0.7, 0.12, 0.08, 0.1]).astype(np.uint8)
+    keep = (rng.random(n_snv) < 0.8).astype(np.uint8)
+    packed, pitch = engine.pack_genotypes(codes)
+    bits, words = engine.pack_clades(S)
+    got = {}
+    for pass2 in ("recompute", "cache", None):
+        if pass2 is None:
+            monkeypatch.delenv("SCS_PLACE_PASS2")
+        else:
+            monkeypatch.setenv("SCS_PLACE_PASS2", pass2)
+        monkeypatch.setenv("SCS_RUN_LEN", "4")          # several runs of row blocks even at this size
+        pl = engine.Placement(ctx, n_snv, n_cells, n_rows)
+        pl.set_genotypes_host(packed, pitch, keep)
+        pl.set_clades_host(bits, words)
+        got[pass2] = pl.run_host(0.01, 0.1)
+        want_mode = {"recompute": 1, "cache": 2, None: 2 if n_cells >= 2560 else 1}[pass2]
+        assert pl.info()["pass2_mode"] == want_mode
+        pl.close()
+    muts = np.where(codes == 3, np.nan, codes.astype(float))[keep.astype(bool)]
+    want = O.map_mutations_gt(muts, S.astype(float), 0.01, 0.1)
+    for v in got.values():
+        assert_soft_close(v, want)
+    np.testing.assert_allclose(got["cache"], got["recompute"], rtol=2e-6, atol=1e-9)
 
 
 def test_radix_mode_falls_back_beyond_four_chunks(ctx, monkeypatch):
