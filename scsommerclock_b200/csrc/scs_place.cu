@@ -67,7 +67,10 @@ struct ModeCfg {
     static constexpr int NUM_STAGES = MODE == MODE_PLANES ? 4 : 6;
     static constexpr int STAGE_BYTES = (A_TILES + 1) * TILE_BYTES;
     static constexpr int SMEM_TOTAL = NUM_STAGES * STAGE_BYTES + SMEM_BARRIER_BYTES + SMEM_RED_BYTES + 1024;
+    // pass 1 with the count cache: 8 x 4 KB staging buffers (one per epilogue warp) in place of `red`
+    static constexpr int SMEM_CACHE = NUM_STAGES * STAGE_BYTES + SMEM_BARRIER_BYTES + NUM_EPI_WARPS * 4096 + 1024;
 };
+static_assert(ModeCfg<0>::SMEM_CACHE <= 232448 && ModeCfg<1>::SMEM_CACHE <= 232448, "count-cache staging does not fit 227 KB");
 
 // Instruction descriptors (bit layout of the tcgen05 instruction descriptor): D format at
 // [4,6) (1 = f32, 2 = s32), A format [7,10), B format [10,13), both K-major (bits 15, 16 = 0),
@@ -109,7 +112,7 @@ struct PlaceParams {
     const uint2* rowref;       // pass 2 in : [M_pad] {ref counts, log2 sum}
     float* colpart;            // pass 2 out: [num_runs][N_pad]
     int* dump;                 // debug     : [M_pad][N_pad][2] raw counts
-    uint32_t* cache;           // pass 1 out (optional): [row block][column tile][128][128] packed counts C1 | C0 << 16 (see scs_colsum_cached_kernel)
+    uint32_t* cache;           // pass 1 out (optional): packed counts C1 | C0 << 16, 64 KB per (row block, column tile) (see cache_store_and_stats)
 };
 
 __device__ __forceinline__ float count_to_float(uint32_t c) {
@@ -180,6 +183,58 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+// Pass 1, 32 columns of one row: running reference column (refv = its rank value, b1/b0 = its counts)
+// and sum of 2^(logit - logit_ref) relative to it.  The best column of the group replaces the
+// reference when it beats it by more than 2^16 (then the running sum is rescaled by the exactly
+// formed difference).  f0 carries the wild-type counts times a power of two that a0h/a0l/a0f undo.
+__device__ __forceinline__ void stats_cols32(const GroupConst& gc, float a0h, float a0l, float a0f, const float (&f1)[32],
+                                             const float (&f0)[32], int nv, float& refv, float& b1, float& b0, float& sum) {
+    // nv >= 32 except in the last column tile
+    float cm = -INFINITY, c1 = 0.f, c0 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const float v = fmaf(gc.a1f, f1[i], a0f * f0[i]);
+        const bool take = (i < nv) && (v > cm);
+        cm = take ? v : cm;
+        c1 = take ? f1[i] : c1;
+        c0 = take ? f0[i] : c0;
+    }
+    if (cm > refv + 16.0f) {
+        if (refv != -INFINITY) {
+            const float e1 = b1 - c1, e0 = b0 - c0;
+            sum *= ex2_approx(fmaf(gc.a1h, e1, a0h * e0) + fmaf(gc.a1l, e1, a0l * e0));
+        }
+        b1 = c1;
+        b0 = c0;
+        refv = cm;
+    }
+    if (nv >= 32) {
+        const float2 nb1 = make_float2(-b1, -b1), nb0 = make_float2(-b0, -b0);
+        const float2 a1h2 = make_float2(gc.a1h, gc.a1h), a0h2 = make_float2(a0h, a0h);
+        const float2 a1l2 = make_float2(gc.a1l, gc.a1l), a0l2 = make_float2(a0l, a0l);
+        float2 sum2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+            const float2 e1 = __fadd2_rn(make_float2(f1[i], f1[i + 1]), nb1);
+            const float2 e0 = __fadd2_rn(make_float2(f0[i], f0[i + 1]), nb0);
+            const float2 sdiff = __ffma2_rn(a1h2, e1, __fmul2_rn(a0h2, e0));   // exact operands, one rounding
+            const float2 lo = __ffma2_rn(a1l2, e1, __fmul2_rn(a0l2, e0));
+            const float2 x = __fadd2_rn(sdiff, lo);
+            sum2 = __fadd2_rn(sum2, make_float2(ex2_approx(x.x), ex2_approx(x.y)));
+        }
+        sum += sum2.x + sum2.y;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const float e1 = f1[i] - b1;
+            const float e0 = f0[i] - b0;
+            const float sdiff = fmaf(gc.a1h, e1, a0h * e0);
+            const float lo = fmaf(gc.a1l, e1, a0l * e0);
+            sum += (i < nv) ? ex2_approx(sdiff + lo) : 0.f;
+        }
+    }
+}
+
 // ---- epilogue building blocks shared by the 1-CTA and the 2-CTA kernels -------------
 // One tile (this thread's row, its 64-column half) from TMEM.
 template <int PASS, int MODE>
@@ -209,65 +264,7 @@ __device__ __forceinline__ void epilogue_tile(const PlaceParams& p, const GroupC
         for (int ch = 0; ch < 2; ++ch) {
             if (ch * 32 >= n_valid) break;
             load_counts<MODE>(taddr + ch * 32, use0, p.nchunk, f1, f0);
-            if (p.cache != nullptr) {
-                // count cache: both counts of the 32 columns as C1 | C0 << 16 (exact: counts < 2^16),
-                // taken from the mantissas of count + 2^23; one 128-byte line per thread
-                // (tile-major layout, 64 KB per 128 x 128 tile: row-major rows are 80 KB apart at 10k cells,
-                // and 148 CTAs scattering 16-byte pieces over such rows cost pass 1 a sixth of its speed)
-                uint32_t* dst = p.cache + ((size_t(row >> 7) * (p.N_pad >> 7) + (col0 >> 7)) * BLOCK_M + (row & 127)) * BLOCK_N + (col0 & 127) + ch * 32;
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    uint32_t w[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        w[k] = __byte_perm(__float_as_uint(f1[i + k] + 8388608.0f), __float_as_uint(fmaf(f0[i + k], F0I, 8388608.0f)), 0x5410);
-                    __stcs(reinterpret_cast<uint4*>(dst + i), make_uint4(w[0], w[1], w[2], w[3]));   // streaming: keep the operand slabs in L2
-                }
-            }
-            const int nv = n_valid - ch * 32;      // >= 32 except in the last column tile
-            float cm = -INFINITY, c1 = 0.f, c0 = 0.f;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float v = fmaf(gc.a1f, f1[i], a0f * f0[i]);
-                const bool take = (i < nv) && (v > cm);
-                cm = take ? v : cm;
-                c1 = take ? f1[i] : c1;
-                c0 = take ? f0[i] : c0;
-            }
-            if (cm > refv + 16.0f) {
-                if (refv != -INFINITY) {
-                    const float e1 = b1 - c1, e0 = b0 - c0;
-                    sum *= ex2_approx(fmaf(gc.a1h, e1, a0h * e0) + fmaf(gc.a1l, e1, a0l * e0));
-                }
-                b1 = c1;
-                b0 = c0;
-                refv = cm;
-            }
-            if (nv >= 32) {
-                const float2 nb1 = make_float2(-b1, -b1), nb0 = make_float2(-b0, -b0);
-                const float2 a1h2 = make_float2(gc.a1h, gc.a1h), a0h2 = make_float2(a0h, a0h);
-                const float2 a1l2 = make_float2(gc.a1l, gc.a1l), a0l2 = make_float2(a0l, a0l);
-                float2 sum2 = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const float2 e1 = __fadd2_rn(make_float2(f1[i], f1[i + 1]), nb1);
-                    const float2 e0 = __fadd2_rn(make_float2(f0[i], f0[i + 1]), nb0);
-                    const float2 sdiff = __ffma2_rn(a1h2, e1, __fmul2_rn(a0h2, e0));   // exact operands, one rounding
-                    const float2 lo = __ffma2_rn(a1l2, e1, __fmul2_rn(a0l2, e0));
-                    const float2 x = __fadd2_rn(sdiff, lo);
-                    sum2 = __fadd2_rn(sum2, make_float2(ex2_approx(x.x), ex2_approx(x.y)));
-                }
-                sum += sum2.x + sum2.y;
-            } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float e1 = f1[i] - b1;
-                    const float e0 = f0[i] - b0;
-                    const float sdiff = fmaf(gc.a1h, e1, a0h * e0);
-                    const float lo = fmaf(gc.a1l, e1, a0l * e0);
-                    sum += (i < nv) ? ex2_approx(sdiff + lo) : 0.f;
-                }
-            }
+            stats_cols32(gc, a0h, a0l, a0f, f1, f0, n_valid - ch * 32, refv, b1, b0, sum);
         }
         const uint32_t pk = uint32_t(b1) | (uint32_t(b0 * F0I) << 16);
         p.stats[size_t(jl * 2 + hh) * p.M_pad + row] = make_uint2(pk, __float_as_uint(sum));
@@ -297,6 +294,60 @@ __device__ __forceinline__ void epilogue_tile(const PlaceParams& p, const GroupC
             }
         }
     }
+}
+
+// ---- pass 1 with the count cache (scs_place_kernel<PASS_STATS, MODE, 2>) -----------------------
+// Same sweep as epilogue_tile<PASS_STATS>; in addition every 32-column group of counts is packed as
+// C1 | C0 << 16 (two mantissa plants and one byte permute per entry) and written to the cache through
+// shared memory by the bulk-copy engine: direct 16-byte stores from a warp whose lanes own different
+// rows touch 32 lines per instruction and half-fill every sector (measured: +17 % cycles on pass 1,
+// against +9 % this way).  ncu shows the MMA warp never waiting for a TMEM slot or for operands in
+// either variant: what the extra work costs is tensor-pipe duty under the power cap, so the epilogue
+// adds as few instructions as it can.
+// Cache layout: [row block][column tile][lane quarter q][column half hh][ch][32 rows][32 words], i.e.
+// one contiguous 4 KB sub-block per (epilogue warp, 32-column group); inside a row the eight 16-byte
+// chunks are XOR-swizzled with (row & 7) so that the shared-memory staging stores are conflict free.
+constexpr int CACHE_SUB_WORDS = 32 * 32;
+
+template <int MODE>
+__device__ __forceinline__ void epilogue_tile_cache(const PlaceParams& p, const GroupConst& gc, uint32_t taddr, uint32_t use0, int row,
+                                                    int jl, int j, int q, int hh, int lane, int n_valid, uint8_t* stage) {
+    constexpr float F0I = 1.0f / F0_SCALE<MODE>;
+    const float a0h = gc.a0h * F0I, a0l = gc.a0l * F0I, a0f = gc.a0f * F0I;
+    uint32_t* tile = p.cache + (size_t(row >> 7) * (p.N_pad >> 7) + j) * (BLOCK_M * BLOCK_N);
+    const uint32_t st_row = ptx::smem_u32(stage) + lane * 128;
+    const float2 two23 = make_float2(8388608.0f, 8388608.0f), inv = make_float2(F0I, F0I);
+    float refv = -INFINITY, b1 = 0.f, b0 = 0.f, sum = 0.f;
+    float f1[32], f0[32];
+#pragma unroll 1
+    for (int ch = 0; ch < 2; ++ch) {
+        // (column groups beyond the last clade row hold zero counts -- the operand is zero padded -- and are
+        // cached like the rest; the sweep over the cache drops their sums)
+        load_counts<MODE>(taddr + ch * 32, use0, p.nchunk, f1, f0);
+        if (lane == 0) ptx::bulk_wait_read0();     // the copy engine is done reading this warp's staging buffer
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 4; k += 2) {
+                const float2 m1 = __fadd2_rn(make_float2(f1[4 * c + k], f1[4 * c + k + 1]), two23);          // C1 + 2^23
+                const float2 m0 = __ffma2_rn(make_float2(f0[4 * c + k], f0[4 * c + k + 1]), inv, two23);     // C0 + 2^23
+                w[k] = __byte_perm(__float_as_uint(m1.x), __float_as_uint(m0.x), 0x5410);
+                w[k + 1] = __byte_perm(__float_as_uint(m1.y), __float_as_uint(m0.y), 0x5410);
+            }
+            ptx::st_shared_v4(st_row + ((c ^ (lane & 7)) << 4), w[0], w[1], w[2], w[3]);
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            // streaming: the counts are read back once, after the whole pass -- keep the operand slabs in L2
+            ptx::bulk_store_hint(tile + ((q * 2 + hh) * 2 + ch) * CACHE_SUB_WORDS, stage, CACHE_SUB_WORDS * 4, ptx::L2_EVICT_FIRST);
+            ptx::bulk_commit();
+        }
+        if (ch * 32 < n_valid) stats_cols32(gc, a0h, a0l, a0f, f1, f0, n_valid - ch * 32, refv, b1, b0, sum);
+    }
+    p.stats[size_t(jl * 2 + hh) * p.M_pad + row] = make_uint2(uint32_t(b1) | (uint32_t(b0 * F0I) << 16), __float_as_uint(sum));
 }
 
 // ---- radix mode, one K chunk (<= 3968 cells): the same epilogue, software pipelined ------
@@ -511,7 +562,7 @@ __device__ __forceinline__ void epilogue_flush_columns(const PlaceParams& p, flo
 
 // 10 warps are allocated as 12 (warp slots come in fours), which caps the kernel at
 // 65536 / 384 = 168 registers per thread; the 64-accumulator pass-2 epilogue spills a few.
-template <int PASS, int MODE, int R1 = 0>   // R1: radix mode with one K chunk -> pipelined epilogue
+template <int PASS, int MODE, int R1 = 0>   // R1 = 1: radix mode with one K chunk -> pipelined epilogue; R1 = 2: pass 1 that also fills the count cache
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x0,
                  const __grid_constant__ CUtensorMap tm_s, const PlaceParams p) {
@@ -659,14 +710,14 @@ scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constan
         // task entry and its group's constants are fetched one task ahead (two dependent loads)
         TaskEntry te_next = {};
         GroupConst gc_next = {};
-        if (R1 && int(blockIdx.x) < p.num_tasks) {      // (short tasks only: long-K kernels are short of registers)
+        if (R1 == 1 && int(blockIdx.x) < p.num_tasks) {      // (short tasks only: long-K kernels are short of registers)
             te_next = p.tasks[blockIdx.x];
             gc_next = p.gconst[te_next.group];
         }
         for (int t = blockIdx.x; t < p.num_tasks; t += gridDim.x) {
-            const TaskEntry te = R1 ? te_next : p.tasks[t];
-            const GroupConst gc = R1 ? gc_next : p.gconst[te.group];
-            if (R1 && t + int(gridDim.x) < p.num_tasks) {
+            const TaskEntry te = R1 == 1 ? te_next : p.tasks[t];
+            const GroupConst gc = R1 == 1 ? gc_next : p.gconst[te.group];
+            if (R1 == 1 && t + int(gridDim.x) < p.num_tasks) {
                 te_next = p.tasks[t + gridDim.x];
                 gc_next = p.gconst[te_next.group];
             }
@@ -688,7 +739,9 @@ scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constan
                 ptx::tc_fence_after();
                 const uint32_t use0 = tile_n * spt;
                 const uint32_t taddr = tmem_base + lane_base + hh * 64;
-                if (R1)
+                if (R1 == 2)
+                    epilogue_tile_cache<MODE>(p, gc, taddr, use0, row, te.jl, j, q, hh, lane, n_valid, reinterpret_cast<uint8_t*>(red) + ew * (CACHE_SUB_WORDS * 4));
+                else if (R1 == 1)
                     epilogue_tile_r1<PASS>(p, gc, taddr + (use0 & 3) * BLOCK_N, row, te.jl, hh, n_valid, colacc, rr);
                 else
                     epilogue_tile<PASS, MODE>(p, gc, taddr, use0, row, te.jl, hh, col0, n_valid, colacc, rr);
@@ -701,6 +754,7 @@ scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constan
             }
             if (PASS == PASS_COLSUM) epilogue_flush_columns(p, red, colacc, q, hh, lane, te.run_local, j);
         }
+        if (R1 == 2 && lane == 0) ptx::bulk_wait0();   // the staging buffers must outlive the copies
     }
 
     ptx::tc_fence_before();
@@ -1037,50 +1091,56 @@ __global__ void scs_merge_stats_kernel(const uint2* __restrict__ stats, int num_
 // counts back costs 4 bytes, so beyond ~2,000 cells the HBM round trip of the *counts* (not of the
 // floating-point SNV x branch matrix: the softmax terms are still formed on the fly, with the same
 // arithmetic on exact integer differences as the GEMM epilogue) is several times cheaper.
-// The cache is tile-major ([row block][column tile][128 rows][128 columns], 64 KB per tile); block = one
-// column tile over one run of row blocks.  A warp reads one whole 512-byte cache row per load (lane =
-// four adjacent clade columns, 16 bytes), the four warps take rows r, r+1, r+2, r+3, four loads in
-// flight per thread (64 bytes: ~64 KB per SM at full occupancy, enough to cover the HBM latency);
-// the arithmetic is the packed fp32x2 form of the GEMM epilogue's.  rowref_f holds the NEGATED
-// record {-(2^23 + R1), -(2^23 + R0), -log2 sum}, the same address for a whole warp (one broadcast).
-// Partial column sums land in colpart[run][col] like the GEMM pass 2.
+// Cache layout (written by scs_place_kernel<PASS_STATS, MODE, 2>): 64 KB per tile as 16 contiguous 4 KB
+// sub-blocks [lane quarter q][32-column group cs][32 rows][8 x 16 bytes], the 16-byte chunks of a row
+// XOR-swizzled with (row & 7).  Block = one column tile over one run of row blocks; warp w takes the
+// 32-column group cs = w and walks the four sub-blocks of every tile.  One load instruction covers
+// four whole rows (512 contiguous bytes): lane = (row offset lane >> 3, logical chunk lane & 7), so a
+// lane keeps the same four clade columns throughout; four loads in flight per thread (64 bytes: ~64 KB
+// per SM at full occupancy).  The arithmetic is the packed fp32x2 form of the GEMM epilogue's;
+// rowref_f holds the NEGATED record {-(2^23 + R1), -(2^23 + R0), -log2 sum}.  Partial column sums land
+// in colpart[run][col] like the GEMM pass 2.
 __global__ void __launch_bounds__(BLOCK_N)
 scs_colsum_cached_kernel(const uint32_t* __restrict__ cache, const float4* __restrict__ rowref_f, const GroupConst* __restrict__ gconst,
                          int num_row_blocks, int64_t N_pad, int n_cols, int run_len, float* __restrict__ colpart) {
     constexpr int UNROLL = 4;
-    __shared__ float red[4][BLOCK_N];
     const int j = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int rsub = lane >> 3, chunk = lane & 7;
     const GroupConst gc = gconst[0];
     const int rb0 = blockIdx.y * run_len, rb1 = min(num_row_blocks, rb0 + run_len);
     const int64_t ct = N_pad / BLOCK_N;
     const float2 a1h2 = make_float2(gc.a1h, gc.a1h), a0h2 = make_float2(gc.a0h, gc.a0h);
     const float2 a1l2 = make_float2(gc.a1l, gc.a1l), a0l2 = make_float2(gc.a0l, gc.a0l);
+    // row k * 4 + rsub of a sub-block: (row & 7) = (k & 1) * 4 + rsub; offsets in uint4 units
+    const int off_even = rsub * 8 + (chunk ^ rsub), off_odd = rsub * 8 + (chunk ^ (4 + rsub));
     float2 acc[UNROLL][2];      // one accumulator pair per load slot: short fp32 chains
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) acc[u][0] = acc[u][1] = make_float2(0.f, 0.f);
     for (int rb = rb0; rb < rb1; ++rb) {
-        const uint4* src = reinterpret_cast<const uint4*>(cache + (size_t(rb) * ct + j) * (BLOCK_M * BLOCK_N)) + w * (BLOCK_N / 4) + lane;
-        const float4* ref = rowref_f + size_t(rb) * BLOCK_M + w;
-#pragma unroll 2
-        for (int r = 0; r < BLOCK_M; r += 4 * UNROLL) {
+        const uint4* tile = reinterpret_cast<const uint4*>(cache + (size_t(rb) * ct + j) * (BLOCK_M * BLOCK_N));
+#pragma unroll 1
+        for (int qh = 0; qh < 8; ++qh) {          // sub-block q = qh >> 1, its rows 16 * (qh & 1) .. + 15
+            const int q = qh >> 1, k0 = (qh & 1) * 4;
+            const uint4* src = tile + (q * 4 + w) * (CACHE_SUB_WORDS / 4) + k0 * 32;
+            const float4* ref = rowref_f + size_t(rb) * BLOCK_M + q * 32 + k0 * 4 + rsub;
             uint4 v[UNROLL];
             float4 rr[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
-                v[u] = __ldcs(src + (r + 4 * u) * (BLOCK_N / 4));     // read once
-                rr[u] = __ldg(ref + r + 4 * u);
+                v[u] = __ldcs(src + u * 32 + ((u & 1) ? off_odd : off_even));     // read once
+                rr[u] = __ldg(ref + 4 * u);
             }
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 const float2 n1 = make_float2(rr[u].x, rr[u].x), n0 = make_float2(rr[u].y, rr[u].y), nL = make_float2(rr[u].z, rr[u].z);
-                const uint32_t q[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                const uint32_t qv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     // count + 2^23 as a float straight from the bits; the reference already carries the 2^23
-                    const float2 e1 = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(q[2 * h], 0x4B000000u, 0x7610)),
-                                                             __uint_as_float(__byte_perm(q[2 * h + 1], 0x4B000000u, 0x7610))), n1);
-                    const float2 e0 = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(q[2 * h], 0x4B000000u, 0x7632)),
-                                                             __uint_as_float(__byte_perm(q[2 * h + 1], 0x4B000000u, 0x7632))), n0);
+                    const float2 e1 = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(qv[2 * h], 0x4B000000u, 0x7610)),
+                                                             __uint_as_float(__byte_perm(qv[2 * h + 1], 0x4B000000u, 0x7610))), n1);
+                    const float2 e0 = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(qv[2 * h], 0x4B000000u, 0x7632)),
+                                                             __uint_as_float(__byte_perm(qv[2 * h + 1], 0x4B000000u, 0x7632))), n0);
                     const float2 sdiff = __ffma2_rn(a1h2, e1, __fmul2_rn(a0h2, e0));   // exact operands, one rounding
                     const float2 lo = __ffma2_rn(a1l2, e1, __ffma2_rn(a0l2, e0, nL));
                     const float2 x = __fadd2_rn(sdiff, lo);
@@ -1089,18 +1149,25 @@ scs_colsum_cached_kernel(const uint32_t* __restrict__ cache, const float4* __res
             }
         }
     }
+    float out[4];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const float2 t = __fadd2_rn(__fadd2_rn(acc[0][h], acc[1][h]), __fadd2_rn(acc[2][h], acc[3][h]));
-        red[w][4 * lane + 2 * h] = t.x;
-        red[w][4 * lane + 2 * h + 1] = t.y;
+        out[2 * h] = t.x;
+        out[2 * h + 1] = t.y;
     }
-    __syncthreads();
-    // columns beyond the last clade row of the last tile were never written by pass 1: their sums are
-    // whatever the buffer held and are dropped here
-    const int col = j * BLOCK_N + threadIdx.x;
-    const float total = (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
-    colpart[size_t(blockIdx.y) * N_pad + col] = col < n_cols ? total : 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {     // the four row offsets of a load sit in lanes 8 apart
+        out[i] += __shfl_xor_sync(0xffffffffu, out[i], 8);
+        out[i] += __shfl_xor_sync(0xffffffffu, out[i], 16);
+    }
+    if (rsub == 0) {
+        const int col = j * BLOCK_N + w * 32 + chunk * 4;
+        // clade rows beyond the last valid one (zero rows of the padded operand) carry no weight
+#pragma unroll
+        for (int i = 0; i < 4; ++i) out[i] = col + i < n_cols ? out[i] : 0.f;
+        *reinterpret_cast<float4*>(colpart + size_t(blockIdx.y) * N_pad + col) = make_float4(out[0], out[1], out[2], out[3]);
+    }
 }
 
 // Y[g][b] = sum over the group's runs of the per-run column partials, fixed order, fp64.
@@ -1149,7 +1216,14 @@ static int make_u8_tmap(CUtensorMap* tm, void* base, uint64_t rows, uint64_t k_p
 template <int PASS>
 static void launch_place(int mode, int grid, cudaStream_t st, const CUtensorMap& a1, const CUtensorMap& a0, const CUtensorMap& b,
                          const PlaceParams& p) {
-    if (mode == MODE_RADIX && p.nchunk == 1 && PASS != PASS_DUMP && p.cache == nullptr)
+    if (PASS == PASS_STATS && p.cache != nullptr) {
+        // pass 1 that also fills the count cache: same pipeline, 32 KB of staging buffers in place of `red`
+        constexpr int R = PASS == PASS_STATS ? 2 : 0;
+        if (mode == MODE_RADIX)
+            scs_place_kernel<PASS, MODE_RADIX, R><<<grid, NUM_THREADS, ModeCfg<MODE_RADIX>::SMEM_CACHE, st>>>(a1, a0, b, p);
+        else
+            scs_place_kernel<PASS, MODE_PLANES, R><<<grid, NUM_THREADS, ModeCfg<MODE_PLANES>::SMEM_CACHE, st>>>(a1, a0, b, p);
+    } else if (mode == MODE_RADIX && p.nchunk == 1 && PASS != PASS_DUMP)
         scs_place_kernel<PASS, MODE_RADIX, (PASS != PASS_DUMP)><<<grid, NUM_THREADS, ModeCfg<MODE_RADIX>::SMEM_TOTAL, st>>>(a1, a0, b, p);
     else if (mode == MODE_RADIX)
         scs_place_kernel<PASS, MODE_RADIX><<<grid, NUM_THREADS, ModeCfg<MODE_RADIX>::SMEM_TOTAL, st>>>(a1, a0, b, p);
@@ -1167,6 +1241,12 @@ static void set_place_smem() {
     cudaFuncSetAttribute(scs_place_kernel2<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_TOTAL);
     cudaFuncSetAttribute(scs_place_kernel<PASS, MODE_PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModeCfg<MODE_PLANES>::SMEM_TOTAL);
     cudaFuncSetAttribute(scs_place_kernel<PASS, MODE_RADIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModeCfg<MODE_RADIX>::SMEM_TOTAL);
+    if (PASS == PASS_STATS) {
+        cudaFuncSetAttribute(scs_place_kernel<PASS, MODE_RADIX, PASS == PASS_STATS ? 2 : 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             ModeCfg<MODE_RADIX>::SMEM_CACHE);
+        cudaFuncSetAttribute(scs_place_kernel<PASS, MODE_PLANES, PASS == PASS_STATS ? 2 : 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             ModeCfg<MODE_PLANES>::SMEM_CACHE);
+    }
     if (PASS != PASS_DUMP)
         cudaFuncSetAttribute(scs_place_kernel<PASS, MODE_RADIX, (PASS != PASS_DUMP)>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              ModeCfg<MODE_RADIX>::SMEM_TOTAL);

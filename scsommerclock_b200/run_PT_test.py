@@ -588,6 +588,30 @@ def get_model_data(tree, pseudo_mut=0, true_data=False):
     return Y, constr, init, weights_norm, np.array(constr_cols)
 
 
+def _branch_order(tree):
+    """The w_max-independent part of get_model_data (:553-611): the branches in the order the
+    reference numbers them and, per branch, the index of the internal node it leads to (-1 for a
+    leaf) -- all the LRT kernel needs besides Y and the weights.  Used by the sweep driver so
+    that a tree is walked once, not once per w_max."""
+    int_nodes = [i for i in tree.iter_descendants("postorder") if not i.is_leaf()]
+    int_index = {id(n): i for i, n in enumerate(int_nodes)}
+    order = []
+    for int_node in int_nodes:
+        if len(int_node.children) != 2:
+            raise ValueError("the PT test needs a binary tree")
+        a, b = int_node.children
+        ta, tb = a.is_leaf(), b.is_leaf()
+        if ta == tb:
+            if not ta and b.mut_no_soft < a.mut_no_soft:      # two internal children: fewer mutations first (stable)
+                a, b = b, a
+        elif tb:                                              # one leaf: the leaf first
+            a, b = b, a
+        order.append(a)
+        order.append(b)
+    child_int = np.array([-1 if n.is_leaf() else int_index[id(n)] for n in order], dtype=np.int32)
+    return order, child_int
+
+
 def get_LRT_poisson(Y, constr, init, weights=np.array([]), alg="trust-constr"):
     """run_PT_test.py:638-700 on the GPU (``alg`` is accepted for signature
     compatibility; the solver is the barrier-Newton kernel, see csrc/scs_lrt.cu).
@@ -698,15 +722,36 @@ def run_poisson_tree_test_batch(vcf_files, tree_files, out_files, w_maxs, exclud
         for g, sw in zip(grp, soft):
             g["st"] = {"soft": sw, "MS_i": g["MS_i"], "n_muts": g["n_kept"], "bits": g["bits"], "words": g["words"],
                        "columns": g["columns"], "weights": {}}
-    # ---- LRT: every (pair, w_max) in one launch
-    problems = []
+    # ---- LRT: every (pair, w_max) in one launch.  Per pair the tree is walked once (branch order and
+    # topology do not depend on w_max) and the branch weights of all w_max come from one call.
+    Ys, ws, chs = [], [], []
     for it in items:
-        _apply_placement(it["tree"], it["st"])
-        for w_max in w_maxs:
-            add_br_weights(it["tree"], it["FP"], it["FN"], it["MS_i"], w_max, _state=it["st"])
-            Y, constr, init, weights_norm, constr_cols = get_model_data(it["tree"])
-            problems.append((Y, constr, weights_norm[:, 0].copy()))
-    results = get_LRT_poisson_batch(problems, ctx=ctx) if problems else []
+        tree = it["tree"]
+        _apply_placement(tree, it["st"])
+        nodes = list(tree.iter_descendants())
+        if len(nodes) != 2 * len(tree) - 1:
+            raise ValueError("the PT test needs a binary tree: %d leaves but %d nodes" % (len(tree), len(nodes)))
+        leaves = set(l.name for l in tree.get_leaves())
+        rate = np.array([float(it["MS_i"][c]) if c in leaves else -1.0 for c in it["columns"]])
+        _, wn, _ = engine.branch_weights(ctx, it["bits"][:len(nodes)], it["words"], len(it["columns"]), rate, it["FP"], it["FN"],
+                                         list(w_maxs))
+        order, child_int = _branch_order(tree)
+        row_of = {id(n): k for k, n in enumerate(nodes)}
+        rows = np.array([row_of[id(n)] for n in order], dtype=np.int64)
+        Y = np.asarray(it["st"]["soft"], dtype=np.float64)[rows]
+        for wi in range(len(w_maxs)):
+            Ys.append(Y)
+            ws.append(wn[wi][rows])
+            chs.append(child_int)
+    results = []
+    if Ys:
+        lrt_out, _ = engine.lrt_poisson_batch(ctx, Ys, ws, chs, want_x=False)
+        for LR, dof, on_bound, p_val, _h0, _h1, _it, status in lrt_out:
+            if status != 0 or not np.isfinite(LR):
+                print("\nFAILED POISSON OPTIMIZATION\n")
+                results.append((np.nan, np.nan, np.nan, np.nan))
+            else:
+                results.append((float(LR), int(dof), int(on_bound), float(p_val)))
     out = []
     w_cols = ["-2logLR", "dof", "p-value", "hypothesis"]
     for k, it in enumerate(items):

@@ -105,6 +105,10 @@ def test_get_model_data_matches_golden(name):
         assert np.array_equal(back.child_int, constr.child_int)
         assert np.array_equal(back.toarray(), g["constr"][k])
         np.testing.assert_allclose(constr @ init, g["constr"][k] @ init, atol=1e-9)
+        # the sweep driver's w_max-independent walk gives the same branch order and topology
+        order, child_int = P._branch_order(r["tree"])
+        assert [n.name for n in order] == list(cols)
+        assert np.array_equal(child_int, constr.child_int)
 
 
 def test_packing_round_trips():
