@@ -105,10 +105,28 @@ int scs_placement_set_genotypes(scs_placement* plan, const uint8_t* d_gt, int64_
                                 const uint8_t* d_row_keep, void* stream);
 int scs_placement_set_genotypes_host(scs_placement* plan, const uint8_t* gt, int64_t pitch_bytes,
                                      const uint8_t* row_keep, void* stream);
+/* Same as scs_placement_set_genotypes without the plan taking a copy where it does not need one:
+ * on the interval path (see scs_placement_set_clades) the kernel reads the caller's packed
+ * matrix directly, so `d_gt` must stay alive and unchanged until the run that uses it has
+ * finished.  Call it after the clades are set; on the GEMM path it builds the operand planes
+ * like scs_placement_set_genotypes. */
+int scs_placement_bind_genotypes(scs_placement* plan, const uint8_t* d_gt, int64_t pitch_bytes,
+                                 const uint8_t* d_row_keep, void* stream);
 /* d_bits: clade membership bit mask [n_rows][pitch_words] of uint32, bit c%32 of
- * word c/32 set when cell c descends from the node (S, run_PT_test.py:389-397). */
+ * word c/32 set when cell c descends from the node (S, run_PT_test.py:389-397).
+ * The masks also decide HOW the counts S x genotypes are formed: the clades of a tree are a
+ * laminar family, so in a depth-first order of the cells every row is one interval and both
+ * counts of a (SNV, clade) pair are a difference of per-SNV prefix counts -- the "interval
+ * path" (csrc/scs_place_interval.cuh), used for single-dataset plans whenever the masks pass
+ * that test.  Any other 0/1 matrix, and every replicate batch, goes through the tcgen05 GEMM.
+ * SCS_PLACE_ALGO=gemm forces the GEMM. */
 int scs_placement_set_clades(scs_placement* plan, const uint32_t* d_bits, int64_t pitch_words, void* stream);
 int scs_placement_set_clades_host(scs_placement* plan, const uint32_t* bits, int64_t pitch_words, void* stream);
+/* Host-only helper (no device work): *laminar = 1 when the masks are a laminar family, and then
+ * perm[k] (optional, [n_cells]) = cell at depth-first position k and lohi[r] (optional, [n_rows]) =
+ * lo | hi << 16, the interval of positions row r covers (lo = hi = 0 for an empty row). */
+int scs_clade_intervals(const uint32_t* bits, int64_t pitch_words, int32_t n_rows, int32_t n_cells, uint16_t* perm,
+                        uint32_t* lohi, int32_t* laminar);
 /* Asynchronous on `stream`.  d_soft_weights: [n_rows] doubles on the device, or
  * NULL to leave the result in the plan (scs_placement_device_result). */
 int scs_placement_run(scs_placement* plan, double FP, double FN, double* d_soft_weights, void* stream);
@@ -119,15 +137,18 @@ int scs_placement_run_host(scs_placement* plan, double FP, double FN, double* so
 const void* scs_placement_device_result(scs_placement* plan);
 /* Device durations (CUDA events on the launching stream) of the four kernels of the
  * last scs_placement_run: ms[0] GEMM pass 1 (row statistics), ms[1] merge, ms[2]
- * pass 2 (column sums: second GEMM pass or count-cache sweep), ms[3] reduction.  Waits for
- * that run to finish. */
+ * pass 2 (column sums: second GEMM pass or count-cache sweep), ms[3] reduction; on the
+ * interval path ms[0] is the one placement kernel and ms[1], ms[2] are zero.  Waits for that
+ * run to finish. */
 int scs_placement_last_times(scs_placement* plan, float* ms);
 /* info[0..9] = M_pad, N_pad, K_pad, tasks, run_len, superblock_width, grid,
  * kernel launches so far, runs, dynamic smem bytes, operand mode (0 = two u8
  * planes / kind::i8, 1 = one radix-packed e5m2 plane / kind::f8f6f4), K chunks,
  * 1 when the 2-CTA (cta_group::2) kernel is used, groups, pass-2 mode (0 not run yet,
  * 1 second GEMM pass, 2 sweep over the packed integer counts that pass 1 cached in HBM --
- * chosen per plan, see SCS_PLACE_PASS2 in DESIGN.md) */
+ * chosen per plan, see SCS_PLACE_PASS2 in DESIGN.md), algorithm (0 no clades yet, 1 GEMM,
+ * 2 interval path), and for the interval path its grid, threads per CTA, dynamic smem bytes
+ * and number of row runs */
 int scs_placement_info(scs_placement* plan, int64_t* info, int32_t n);
 /* Parity aid for small problems: counts[i][b][0/1] = number of cells of clade b
  * observed mutated / observed wild type for SNV i (exact integers). */

@@ -35,6 +35,8 @@ _SIGNATURES = {
     "scs_placement_destroy": (C.c_int, [C.c_void_p]),
     "scs_placement_set_genotypes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "scs_placement_set_genotypes_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "scs_clade_intervals": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scs_placement_bind_genotypes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "scs_placement_set_clades": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "scs_placement_set_clades_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "scs_placement_run": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),

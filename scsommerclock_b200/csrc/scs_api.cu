@@ -78,8 +78,8 @@ int scs_map_mutations(scs_ctx* ctx, const uint8_t* gt, int64_t pitch_bytes, cons
     scs_placement* pl = nullptr;
     int rc = scs_placement_create(ctx, n_snv, n_cells, n_rows, &pl);
     if (rc != SCS_OK) return rc;
-    rc = scs_placement_set_genotypes_host(pl, gt, pitch_bytes, row_keep, nullptr);
-    if (rc == SCS_OK) rc = scs_placement_set_clades_host(pl, clade_bits, pitch_words, nullptr);
+    rc = scs_placement_set_clades_host(pl, clade_bits, pitch_words, nullptr);      // first: the masks decide the algorithm
+    if (rc == SCS_OK) rc = scs_placement_set_genotypes_host(pl, gt, pitch_bytes, row_keep, nullptr);
     if (rc == SCS_OK) rc = scs_placement_run_host(pl, FP, FN, soft_weights, nullptr);
     scs_placement_destroy(pl);
     return rc;

@@ -1183,6 +1183,10 @@ __global__ void scs_reduce_colpart_kernel(const float* __restrict__ colpart, con
     y[o] = acc;
 }
 
+}  // namespace scs
+#include "scs_place_interval.cuh"
+namespace scs {
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1296,6 +1300,20 @@ struct Placement {
     CUtensorMap tm_s64;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // brackets of the four kernels of run()
     bool timed = false;
+    // ---- interval path (scs_place_interval.cuh): chosen by set_clades when the masks are a laminar family
+    int algo = 0;                  // 0 undecided (no clades yet), 1 GEMM, 2 interval
+    bool operands_valid = false;   // the GEMM operand plane(s) hold the current genotypes
+    uint8_t* gt_own = nullptr;     // plan-owned copy of the packed genotypes (set_genotypes)
+    size_t gt_own_bytes = 0;
+    const uint8_t* gt_src = nullptr;   // what the interval kernel reads: gt_own or the caller's bound buffer
+    int64_t gt_pitch = 0;
+    uint16_t* d_perm = nullptr;
+    uint32_t* d_lohi = nullptr;
+    float* ipart = nullptr;
+    size_t ipart_bytes = 0;
+    int iv_threads = 0, iv_grid = 0, iv_rows_per_run = 0, iv_runs = 0;
+    bool iv_dcache = false, iv_perm_smem = false;
+    size_t iv_smem = 0;
 };
 
 // Radix packing is the default wherever it applies (<= 15,872 cells); its integer exactness is
@@ -1523,6 +1541,10 @@ int scs_placement_destroy(scs_placement* h) {
     cudaFree(pl->rowref);
     cudaFree(pl->rowref_f);
     cudaFree(pl->cache);
+    cudaFree(pl->gt_own);
+    cudaFree(pl->d_perm);
+    cudaFree(pl->d_lohi);
+    cudaFree(pl->ipart);
     cudaFree(pl->colpart);
     cudaFree(pl->y);
     cudaFree(pl->row_keep);
@@ -1543,12 +1565,8 @@ int scs_placement_destroy(scs_placement* h) {
     return SCS_OK;
 }
 
-int scs_placement_set_genotypes(scs_placement* h, const uint8_t* d_gt, int64_t pitch_bytes, const uint8_t* d_row_keep, void* stream) {
-    Placement* pl = reinterpret_cast<Placement*>(h);
-    if (!pl || !d_gt) return set_error(SCS_ERR_ARG, "null argument");
-    if (pitch_bytes < (pl->n_cells + 3) / 4) return set_error(SCS_ERR_ARG, "genotype row pitch %lld is smaller than ceil(n_cells/4)", (long long)pitch_bytes);
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if ((pitch_bytes & 3) || (reinterpret_cast<uintptr_t>(d_gt) & 3)) return set_error(SCS_ERR_ARG, "packed genotype rows must be 4-byte aligned (pitch %lld)", (long long)pitch_bytes);
+// GEMM operand plane(s) from the packed matrix
+static int expand_operands(Placement* pl, const uint8_t* d_gt, int64_t pitch_bytes, cudaStream_t st) {
     const int64_t work = pl->M_pad * (pl->K_pad / 16);
     if (pl->K_pad / 16 < 64 && work < (int64_t(1) << 31)) {
         const unsigned grid = unsigned(std::min<int64_t>((work + 255) / 256, int64_t(pl->ctx->sm_count) * 64));
@@ -1560,6 +1578,47 @@ int scs_placement_set_genotypes(scs_placement* h, const uint8_t* d_gt, int64_t p
                                                              pl->mode == MODE_RADIX);
     }
     pl->launches++;
+    pl->operands_valid = true;
+    SCS_CUDA(cudaGetLastError());
+    return SCS_OK;
+}
+
+static int set_genotypes_impl(Placement* pl, const uint8_t* d_gt, int64_t pitch_bytes, const uint8_t* d_row_keep, cudaStream_t st, bool bind) {
+    if (!pl || !d_gt) return set_error(SCS_ERR_ARG, "null argument");
+    if (pitch_bytes < (pl->n_cells + 3) / 4) return set_error(SCS_ERR_ARG, "genotype row pitch %lld is smaller than ceil(n_cells/4)", (long long)pitch_bytes);
+    if ((pitch_bytes & 3) || (reinterpret_cast<uintptr_t>(d_gt) & 3)) return set_error(SCS_ERR_ARG, "packed genotype rows must be 4-byte aligned (pitch %lld)", (long long)pitch_bytes);
+    pl->operands_valid = false;
+    pl->gt_src = nullptr;
+    // GEMM path (or clades not seen yet): the operand plane(s)
+    if (pl->algo != 2) {
+        int rc = expand_operands(pl, d_gt, pitch_bytes, st);
+        if (rc != SCS_OK) return rc;
+    }
+    // interval path (or clades not seen yet): the packed matrix itself -- bound (the caller keeps the buffer
+    // alive and unchanged until the run has finished) or copied into the plan
+    if (pl->algo != 1 && pl->n_groups == 1) {
+        if (bind && (pl->algo == 2 || d_gt == pl->stage_gt)) {      // (the staging buffer of set_genotypes_host is the plan's own)
+            pl->gt_src = d_gt;
+        } else {
+            const size_t bytes = size_t(pl->n_snv) * size_t(pitch_bytes);
+            if (bytes > pl->gt_own_bytes) {
+                cudaFree(pl->gt_own);
+                pl->gt_own = nullptr;
+                pl->gt_own_bytes = 0;
+                if (cudaMalloc(&pl->gt_own, bytes) != cudaSuccess) {
+                    cudaGetLastError();
+                    if (pl->algo == 2) return set_error(SCS_ERR_OOM, "device allocation of %zu bytes for the packed genotypes failed", bytes);
+                } else {
+                    pl->gt_own_bytes = bytes;
+                }
+            }
+            if (pl->gt_own) {
+                SCS_CUDA(cudaMemcpyAsync(pl->gt_own, d_gt, bytes, cudaMemcpyDeviceToDevice, st));
+                pl->gt_src = pl->gt_own;
+            }
+        }
+        pl->gt_pitch = pitch_bytes;
+    }
     if (d_row_keep) {
         SCS_CUDA(cudaMemcpyAsync(pl->row_keep, d_row_keep, size_t(pl->n_snv), cudaMemcpyDeviceToDevice, st));
         pl->have_row_keep = true;
@@ -1567,6 +1626,97 @@ int scs_placement_set_genotypes(scs_placement* h, const uint8_t* d_gt, int64_t p
         pl->have_row_keep = false;
     }
     SCS_CUDA(cudaGetLastError());
+    return SCS_OK;
+}
+
+// Host-only: the cell order and the intervals the interval path would use for these masks.
+int scs_clade_intervals(const uint32_t* bits, int64_t pitch_words, int32_t n_rows, int32_t n_cells, uint16_t* perm, uint32_t* lohi,
+                        int32_t* laminar) {
+    if (!bits || !laminar || n_rows <= 0 || n_cells <= 0 || n_cells > 65535 || pitch_words < (n_cells + 31) / 32)
+        return set_error(SCS_ERR_ARG, "bad argument");
+    std::vector<uint16_t> pv;
+    std::vector<uint32_t> lv;
+    *laminar = clade_intervals(bits, pitch_words, n_rows, n_cells, pv, lv) ? 1 : 0;
+    if (*laminar) {
+        if (perm) memcpy(perm, pv.data(), pv.size() * sizeof(uint16_t));
+        if (lohi) memcpy(lohi, lv.data(), lv.size() * sizeof(uint32_t));
+    }
+    return SCS_OK;
+}
+
+int scs_placement_set_genotypes(scs_placement* h, const uint8_t* d_gt, int64_t pitch_bytes, const uint8_t* d_row_keep, void* stream) {
+    return set_genotypes_impl(reinterpret_cast<Placement*>(h), d_gt, pitch_bytes, d_row_keep, reinterpret_cast<cudaStream_t>(stream), false);
+}
+
+int scs_placement_bind_genotypes(scs_placement* h, const uint8_t* d_gt, int64_t pitch_bytes, const uint8_t* d_row_keep, void* stream) {
+    return set_genotypes_impl(reinterpret_cast<Placement*>(h), d_gt, pitch_bytes, d_row_keep, reinterpret_cast<cudaStream_t>(stream), true);
+}
+
+// Decide the algorithm for these clade masks (host copy `bits`): interval path when they are a laminar
+// family, the plan is a single dataset and the working set fits shared memory; SCS_PLACE_ALGO = gemm |
+// interval | auto overrides ("interval" still falls back when the masks are not laminar).
+static int choose_algo(Placement* pl, const uint32_t* bits, int64_t pitch_words, cudaStream_t st) {
+    pl->algo = 1;
+    const char* e = getenv("SCS_PLACE_ALGO");
+    if (e && !strcmp(e, "gemm")) return SCS_OK;
+    if (pl->n_groups != 1) return SCS_OK;
+    // shared-memory working set: prefix counts + accumulators always; the per-row count cache and the
+    // cell order when they fit
+    bool dcache = true, perm_smem = true;
+    size_t smem = interval_smem_bytes(pl->n_cells, pl->n_rows, dcache, perm_smem);
+    if (smem > 227 * 1024) {
+        perm_smem = false;
+        smem = interval_smem_bytes(pl->n_cells, pl->n_rows, dcache, perm_smem);
+    }
+    if (smem > 227 * 1024) {
+        dcache = false;
+        perm_smem = true;
+        smem = interval_smem_bytes(pl->n_cells, pl->n_rows, dcache, perm_smem);
+    }
+    if (smem > 227 * 1024) {
+        perm_smem = false;
+        smem = interval_smem_bytes(pl->n_cells, pl->n_rows, dcache, perm_smem);
+    }
+    if (smem > 227 * 1024) return SCS_OK;
+    std::vector<uint16_t> perm;
+    std::vector<uint32_t> lohi;
+    if (!clade_intervals(bits, pitch_words, pl->n_rows, pl->n_cells, perm, lohi)) return SCS_OK;
+    if (!pl->d_perm && cudaMalloc(&pl->d_perm, size_t(pl->n_cells) * sizeof(uint16_t)) != cudaSuccess) return set_error(SCS_ERR_OOM, "device allocation failed");
+    if (!pl->d_lohi && cudaMalloc(&pl->d_lohi, size_t(pl->n_rows) * sizeof(uint32_t)) != cudaSuccess) return set_error(SCS_ERR_OOM, "device allocation failed");
+    SCS_CUDA(cudaMemcpyAsync(pl->d_perm, perm.data(), perm.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+    SCS_CUDA(cudaMemcpyAsync(pl->d_lohi, lohi.data(), lohi.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    SCS_CUDA(cudaStreamSynchronize(st));          // perm / lohi are stack-local
+    pl->iv_dcache = dcache;
+    pl->iv_perm_smem = perm_smem;
+    pl->iv_smem = smem;
+    pl->iv_threads = pl->n_rows >= 4096 ? 1024 : (pl->n_rows >= 1024 ? 512 : 256);
+    if (const char* t = getenv("SCS_IV_THREADS")) pl->iv_threads = std::max(32, std::min(1024, atoi(t) / 32 * 32));
+    int per_sm = 1;
+    if (dcache) {
+        cudaFuncSetAttribute(scs_place_interval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scs_place_interval_kernel<true>, pl->iv_threads, smem);
+    } else {
+        cudaFuncSetAttribute(scs_place_interval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scs_place_interval_kernel<false>, pl->iv_threads, smem);
+    }
+    per_sm = std::max(1, per_sm);
+    const int64_t slots = int64_t(pl->ctx->sm_count) * per_sm;
+    // runs: short fp32 accumulation chains (<= 256 rows) and at least ~4 runs per resident CTA
+    int rpr = int(std::min<int64_t>(256, std::max<int64_t>(16, (pl->n_snv + 4 * slots - 1) / (4 * slots))));
+    if (const char* t = getenv("SCS_IV_ROWS_PER_RUN")) rpr = std::max(1, atoi(t));
+    pl->iv_rows_per_run = rpr;
+    pl->iv_runs = int((pl->n_snv + rpr - 1) / rpr);
+    pl->iv_grid = int(std::min<int64_t>(pl->iv_runs, slots));
+    const size_t pbytes = size_t(pl->iv_runs) * pl->n_rows * sizeof(float);
+    if (pbytes > pl->ipart_bytes) {
+        cudaFree(pl->ipart);
+        pl->ipart = nullptr;
+        pl->ipart_bytes = 0;
+        if (cudaMalloc(&pl->ipart, pbytes) != cudaSuccess) return set_error(SCS_ERR_OOM, "device allocation of %zu bytes failed", pbytes);
+        pl->ipart_bytes = pbytes;
+    }
+    SCS_CUDA(cudaGetLastError());
+    pl->algo = 2;
     return SCS_OK;
 }
 
@@ -1581,6 +1731,18 @@ int scs_placement_set_clades(scs_placement* h, const uint32_t* d_bits, int64_t p
                                                       pl->mode == MODE_RADIX ? uint32_t(E5M2_ONE) : 1u);
     pl->launches++;
     SCS_CUDA(cudaGetLastError());
+    if (pl->n_groups == 1) {
+        // which algorithm these masks allow is decided on a host copy (tree-shaped masks -> interval path)
+        std::vector<uint32_t> hb(size_t(pl->n_rows) * size_t(pitch_words));
+        SCS_CUDA(cudaMemcpyAsync(hb.data(), d_bits, hb.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        SCS_CUDA(cudaStreamSynchronize(st));
+        const int prev = pl->algo;
+        int rc = choose_algo(pl, hb.data(), pitch_words, st);
+        if (rc != SCS_OK) return rc;
+        if (prev == 2 && pl->algo == 1) pl->operands_valid = false;   // genotypes were set for the interval path only
+    } else {
+        pl->algo = 1;
+    }
     return SCS_OK;
 }
 
@@ -1602,7 +1764,7 @@ int scs_placement_set_genotypes_host(scs_placement* h, const uint8_t* gt, int64_
         d_keep = pl->stage_gt + size_t(pl->n_snv) * pitch_bytes;
         SCS_CUDA(cudaMemcpyAsync(d_keep, row_keep, size_t(pl->n_snv), cudaMemcpyHostToDevice, st));
     }
-    return scs_placement_set_genotypes(h, pl->stage_gt, pitch_bytes, d_keep, stream);
+    return set_genotypes_impl(pl, pl->stage_gt, pitch_bytes, d_keep, st, true);
 }
 
 int scs_placement_set_clades_host(scs_placement* h, const uint32_t* bits, int64_t pitch_words, void* stream) {
@@ -1683,6 +1845,44 @@ int scs_placement_run_batch(scs_placement* h, const double* FP, const double* FN
     }
     SCS_CUDA(cudaMemcpyAsync(pl->d_gconst, gc.data(), gc.size() * sizeof(GroupConst), cudaMemcpyHostToDevice, st));
     SCS_CUDA(cudaMemcpyAsync(pl->d_gconst_d, gd.data(), gd.size() * sizeof(double2), cudaMemcpyHostToDevice, st));
+    if (pl->algo == 0) return set_error(SCS_ERR_ARG, "scs_placement_run before scs_placement_set_clades");
+    if (pl->algo == 2) {
+        if (!pl->gt_src) return set_error(SCS_ERR_ARG, "scs_placement_run before scs_placement_set_genotypes");
+        IntervalParams ip;
+        ip.gt = pl->gt_src;
+        ip.pitch = pl->gt_pitch;
+        ip.n_snv = pl->n_snv;
+        ip.n_cells = pl->n_cells;
+        ip.n_nodes = pl->n_rows;
+        ip.row_words = (pl->n_cells + 15) / 16;
+        ip.perm = pl->d_perm;
+        ip.lohi = pl->d_lohi;
+        ip.row_keep = pl->have_row_keep ? pl->row_keep : nullptr;
+        ip.gconst = pl->d_gconst;
+        ip.part = pl->ipart;
+        ip.rows_per_run = pl->iv_rows_per_run;
+        ip.num_runs = pl->iv_runs;
+        ip.perm_smem = pl->iv_perm_smem ? 1 : 0;
+        double* y = d_soft_weights ? d_soft_weights : pl->y;
+        cudaEventRecord(pl->ev[0], st);
+        if (pl->iv_dcache) scs_place_interval_kernel<true><<<pl->iv_grid, pl->iv_threads, pl->iv_smem, st>>>(ip);
+        else scs_place_interval_kernel<false><<<pl->iv_grid, pl->iv_threads, pl->iv_smem, st>>>(ip);
+        cudaEventRecord(pl->ev[1], st);
+        cudaEventRecord(pl->ev[2], st);
+        cudaEventRecord(pl->ev[3], st);
+        scs_reduce_interval_kernel<<<unsigned((pl->n_rows + 255) / 256), 256, 0, st>>>(pl->ipart, pl->iv_runs, pl->n_rows, y);
+        cudaEventRecord(pl->ev[4], st);
+        pl->timed = true;
+        pl->launches += 2;
+        SCS_CUDA(cudaGetLastError());
+        return SCS_OK;
+    }
+    if (!pl->operands_valid) {
+        // the masks changed from tree-shaped to general after the genotypes were set: build the operands now
+        if (!pl->gt_src) return set_error(SCS_ERR_ARG, "scs_placement_run before scs_placement_set_genotypes");
+        int rc = expand_operands(pl, pl->gt_src, pl->gt_pitch, st);
+        if (rc != SCS_OK) return rc;
+    }
     if (pl->pass2_mode == 0) choose_pass2_mode(pl);
     const PlaceParams& p = pl->prm;
     const bool cached = pl->pass2_mode == 2;
@@ -1752,6 +1952,11 @@ int scs_placement_debug_counts(scs_placement* h, int32_t* counts_host, void* str
     const size_t n = size_t(pl->M_pad) * pl->N_pad * 2;
     if (n > (size_t(1) << 28)) return set_error(SCS_ERR_ARG, "debug count dump is limited to small problems");
     if (!pl->dump && cudaMalloc(&pl->dump, n * sizeof(int)) != cudaSuccess) return set_error(SCS_ERR_OOM, "debug dump allocation failed");
+    if (!pl->operands_valid) {       // the plan runs the interval path: the GEMM operands were never built
+        if (!pl->gt_src) return set_error(SCS_ERR_ARG, "set the genotypes before asking for the count dump");
+        int rc = expand_operands(pl, pl->gt_src, pl->gt_pitch, st);
+        if (rc != SCS_OK) return rc;
+    }
     PlaceParams p = pl->prm;
     p.dump = pl->dump;
     if (pl->pair) launch_place2<PASS_DUMP>(pl->grid2, st, pl->tm_x1, pl->tm_s64, p);
@@ -1780,10 +1985,11 @@ int scs_placement_debug_stats(scs_placement* h, void* stats_host, void* rowref_h
 int scs_placement_info(scs_placement* h, int64_t* info, int32_t n) {
     Placement* pl = reinterpret_cast<Placement*>(h);
     if (!pl || !info) return set_error(SCS_ERR_ARG, "null argument");
-    const int64_t v[15] = {pl->M_pad, pl->N_pad, pl->K_pad, pl->prm.num_tasks, pl->prm.run_len, pl->prm.sb_width, pl->pair ? pl->grid2 : pl->grid, pl->launches, pl->prm.num_runs,
+    const int64_t v[20] = {pl->M_pad, pl->N_pad, pl->K_pad, pl->prm.num_tasks, pl->prm.run_len, pl->prm.sb_width, pl->pair ? pl->grid2 : pl->grid, pl->launches, pl->prm.num_runs,
                            pl->pair ? K2_SMEM_TOTAL : (pl->mode == MODE_RADIX ? ModeCfg<MODE_RADIX>::SMEM_TOTAL : ModeCfg<MODE_PLANES>::SMEM_TOTAL),
-                           pl->mode, pl->prm.nchunk, pl->pair ? 1 : 0, pl->n_groups, pl->pass2_mode};
-    for (int i = 0; i < n && i < 15; ++i) info[i] = v[i];
+                           pl->mode, pl->prm.nchunk, pl->pair ? 1 : 0, pl->n_groups, pl->pass2_mode,
+                           pl->algo, pl->iv_grid, pl->iv_threads, int64_t(pl->iv_smem), pl->iv_runs};
+    for (int i = 0; i < n && i < 20; ++i) info[i] = v[i];
     return SCS_OK;
 }
 

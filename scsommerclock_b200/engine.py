@@ -62,6 +62,17 @@ def unpack_clades(bits, n_cells):
 
 
 # ------------------------------------------------------------------ handles
+def clade_intervals(bits, n_cells):
+    """scs_clade_intervals (host only): (laminar, perm [n_cells] uint16, lo [n_rows], hi [n_rows])."""
+    bits = np.ascontiguousarray(bits, dtype=np.uint32)
+    n_rows, words = bits.shape
+    perm = np.zeros(n_cells, dtype=np.uint16)
+    lohi = np.zeros(n_rows, dtype=np.uint32)
+    lam = C.c_int32()
+    check(lib().scs_clade_intervals(ptr(bits), int(words), int(n_rows), int(n_cells), ptr(perm), ptr(lohi), C.byref(lam)))
+    return bool(lam.value), perm, (lohi & 0xFFFF).astype(np.int64), (lohi >> 16).astype(np.int64)
+
+
 def _stream_handle(stream):
     if stream is None:
         return None
@@ -128,10 +139,11 @@ class Placement:
             pass
 
     def info(self):
-        v = (C.c_int64 * 15)()
-        check(lib().scs_placement_info(self._h, v, 15))
+        v = (C.c_int64 * 20)()
+        check(lib().scs_placement_info(self._h, v, 20))
         keys = ("M_pad", "N_pad", "K_pad", "tasks", "run_len", "superblock_width", "grid", "launches", "runs", "smem_bytes",
-                "mode", "k_chunks", "cta_pair", "groups", "pass2_mode")
+                "mode", "k_chunks", "cta_pair", "groups", "pass2_mode", "algo", "interval_grid", "interval_threads",
+                "interval_smem_bytes", "interval_runs")
         return dict(zip(keys, (int(x) for x in v)))
 
     # host buffers (numpy)
@@ -151,6 +163,11 @@ class Placement:
     # device buffers (torch tensors or raw addresses)
     def set_genotypes(self, d_packed, pitch, d_row_keep=None, stream=None):
         check(lib().scs_placement_set_genotypes(self._h, _dev_ptr(d_packed), int(pitch), _dev_ptr(d_row_keep), _stream_handle(stream)))
+
+    def bind_genotypes(self, d_packed, pitch, d_row_keep=None, stream=None):
+        """set_genotypes without a copy on the interval path: ``d_packed`` must stay alive and
+        unchanged until the run that uses it has finished (call after the clades are set)."""
+        check(lib().scs_placement_bind_genotypes(self._h, _dev_ptr(d_packed), int(pitch), _dev_ptr(d_row_keep), _stream_handle(stream)))
 
     def set_clades(self, d_bits, words, stream=None):
         check(lib().scs_placement_set_clades(self._h, _dev_ptr(d_bits), int(words), _stream_handle(stream)))
@@ -392,7 +409,7 @@ class StreamingPlacement:
             if rows_c < self.chunk_rows:
                 self.keep.zero_()                                    # tail rows of a short last chunk: dropped
             n_kept, miss = gt_reduce(self.ctx, self._bufs[b], pitch, rows_c, len(col_active), col_active, filter_rows, self.keep)
-            self.plan.set_genotypes(self._bufs[b], pitch, self.keep, stream=cur)
+            self.plan.bind_genotypes(self._bufs[b], pitch, self.keep, stream=cur)     # the buffer outlives the run (_free[b])
             self.plan.run(FP, FN, self.y_chunk, stream=cur)
             y_dev.add_(self.y_chunk)
             self._free[b].record(cur)

@@ -450,8 +450,8 @@ def _place_on_tree(ctx, muts, tree, outg, FP, FN):
         y = torch.zeros(bits.shape[0], dtype=torch.float64, device=dev)
         if n_snv > 0:
             plan = engine.Placement(ctx, n_snv, n_cols, bits.shape[0])
-            plan.set_genotypes(d_gt, muts._dec.pitch, row_keep)
             plan.set_clades_host(bits, words)
+            plan.bind_genotypes(d_gt, muts._dec.pitch, row_keep)     # the decoded matrix outlives the run
             plan.run(FP, FN, y)
             torch.cuda.synchronize(dev)
             plan.close()
@@ -459,8 +459,8 @@ def _place_on_tree(ctx, muts, tree, outg, FP, FN):
         soft = y.cpu().numpy()
     else:
         plan = engine.Placement(ctx, n_snv, n_cols, bits.shape[0])
-        plan.set_genotypes(d_gt, muts._dec.pitch, row_keep)
         plan.set_clades_host(bits, words)
+        plan.bind_genotypes(d_gt, muts._dec.pitch, row_keep)         # the decoded matrix outlives the run
         soft = plan.run_host(FP, FN)
         plan.close()
     return {"soft": soft, "MS_i": MS_i, "n_muts": n_kept, "bits": bits, "words": words, "columns": columns,

@@ -60,6 +60,7 @@ def assert_soft_close(got, want):
                                             (2000, 300), (700, 513)])
 def test_counts_bit_exact_and_soft_weights(ctx, monkeypatch, mode, n_snv, n_cells):
     monkeypatch.setenv("SCS_PLACE_MODE", mode)      # one e5m2 radix plane (kind::f8f6f4) / two u8 planes (kind::i8)
+    monkeypatch.setenv("SCS_PLACE_ALGO", "gemm")    # tree-shaped masks would otherwise take the interval path (tested below)
     codes, S = make_problem(n_snv, n_cells, seed=n_snv * 7 + n_cells)
     FP, FN = 0.01, 0.1
     packed, pitch = engine.pack_genotypes(codes)
@@ -169,6 +170,114 @@ def test_count_cache_pass2_matches_recompute(ctx, monkeypatch, n_snv, n_cells, n
     for v in got.values():
         assert_soft_close(v, want)
     np.testing.assert_allclose(got["cache"], got["recompute"], rtol=2e-6, atol=1e-9)
+
+
+# ------------------------------------------------------------ interval path
+def shuffled_problem(n_snv, n_cells, seed):
+    """make_problem with the cell columns shuffled, so that the depth-first order is not the column order."""
+    codes, S = make_problem(n_snv, n_cells, seed)
+    perm = np.random.default_rng(seed + 1).permutation(n_cells)
+    return np.ascontiguousarray(codes[:, perm]), np.ascontiguousarray(S[:, perm])
+
+
+@pytest.mark.parametrize("n_snv,n_cells", [(1, 2), (127, 3), (300, 50), (1000, 200), (700, 513), (400, 1100), (150, 4200), (60, 10000),
+                                            (40, 12500)])
+def test_interval_path_matches_oracle_and_gemm(ctx, monkeypatch, n_snv, n_cells):
+    """Tree-shaped clade masks: counts as differences of per-SNV prefix counts (no GEMM).  Same soft
+    weights as the oracle (where it finishes in seconds) and as the tcgen05 GEMM on the same inputs;
+    256 / 512 / 1024 threads per CTA, with and without the count cache in shared memory (12,500 cells)."""
+    codes, S = shuffled_problem(n_snv, n_cells, seed=n_snv + 3 * n_cells)
+    keep = np.ones(n_snv, dtype=np.uint8)
+    if n_snv > 4:
+        keep[::5] = 0
+    packed, pitch = engine.pack_genotypes(codes)
+    bits, words = engine.pack_clades(S)
+    got = {}
+    for algo in ("auto", "gemm"):
+        monkeypatch.setenv("SCS_PLACE_ALGO", algo)
+        pl = engine.Placement(ctx, n_snv, n_cells, S.shape[0])
+        pl.set_clades_host(bits, words)
+        pl.set_genotypes_host(packed, pitch, keep)
+        got[algo] = pl.run_host(0.01, 0.1)
+        assert pl.info()["algo"] == (2 if algo == "auto" else 1)
+        if algo == "auto":
+            assert np.array_equal(pl.run_host(0.01, 0.1), got[algo])          # fixed reduction order
+            if n_cells <= 1100:
+                cnt = pl.debug_counts()                                      # builds the GEMM operands on demand
+                C1, C0 = oracle_counts(codes, S)
+                assert np.array_equal(cnt[:, :, 0], C1) and np.array_equal(cnt[:, :, 1], C0)
+        pl.close()
+    assert_soft_close(got["auto"], got["gemm"])
+    np.testing.assert_allclose(got["auto"], got["gemm"], rtol=5e-6, atol=1e-7)
+    if n_cells <= 513:
+        muts = np.where(codes == 3, np.nan, codes.astype(float))[keep.astype(bool)]
+        assert_soft_close(got["auto"], O.map_mutations_gt(muts, S.astype(float), 0.01, 0.1))
+
+
+@pytest.mark.parametrize("threads,rows_per_run", [(32, 1), (64, 3), (96, 7), (1024, 256)])
+def test_interval_path_block_shapes_and_run_lengths(ctx, monkeypatch, threads, rows_per_run):
+    """One warp per CTA up to 32 warps (most of them without a clade row), runs of 1..256 SNV rows, rows
+    dropped by the filter, extreme error rates."""
+    n_snv, n_cells = 333, 300
+    codes, S = shuffled_problem(n_snv, n_cells, seed=threads)
+    codes[7] = 3                       # nothing observed: uniform over the rows of S
+    codes[8] = 1                       # everything mutated
+    codes[9] = 0
+    keep = (np.arange(n_snv) % 4 != 1).astype(np.uint8)
+    monkeypatch.setenv("SCS_IV_THREADS", str(threads))
+    monkeypatch.setenv("SCS_IV_ROWS_PER_RUN", str(rows_per_run))
+    packed, pitch = engine.pack_genotypes(codes)
+    bits, words = engine.pack_clades(S)
+    pl = engine.Placement(ctx, n_snv, n_cells, S.shape[0])
+    pl.set_clades_host(bits, words)
+    pl.set_genotypes_host(packed, pitch, keep)
+    info = pl.info()
+    assert info["algo"] == 2 and info["interval_threads"] == threads
+    muts = np.where(codes == 3, np.nan, codes.astype(float))[keep.astype(bool)]
+    for FP, FN in [(0.01, 0.1), (1e-6, 1e-6), (0.2, 0.4)]:
+        assert_soft_close(pl.run_host(FP, FN), O.map_mutations_gt(muts, S.astype(float), FP, FN))
+    pl.close()
+
+
+def test_interval_path_needs_tree_shaped_masks_and_shared_memory(ctx):
+    """Masks that are not a laminar family, replicate batches and trees whose working set exceeds
+    shared memory go through the GEMM."""
+    rng = np.random.default_rng(3)
+    codes, S = make_problem(50, 40, seed=1)
+    S2 = S.copy()
+    S2[3] = 0
+    S2[3, [0, 39]] = 1
+    S2[4] = 0
+    S2[4, [39, 20]] = 1                 # overlaps row 3 without nesting
+    packed, pitch = engine.pack_genotypes(codes)
+    for mat, want_algo in ((S, 2), (S2, 1)):
+        bits, words = engine.pack_clades(mat)
+        pl = engine.Placement(ctx, 50, 40, mat.shape[0])
+        pl.set_genotypes_host(packed, pitch)             # genotypes first, clades second: either order works
+        pl.set_clades_host(bits, words)
+        assert pl.info()["algo"] == want_algo
+        muts = np.where(codes == 3, np.nan, codes.astype(float))
+        assert_soft_close(pl.run_host(0.01, 0.1), O.map_mutations_gt(muts, mat.astype(float), 0.01, 0.1))
+        # the same plan, other masks: tree-shaped -> general and back
+        other = S2 if mat is S else S
+        bits2, _ = engine.pack_clades(other)
+        pl.set_clades_host(bits2, words)
+        assert pl.info()["algo"] == (1 if want_algo == 2 else 2)
+        assert_soft_close(pl.run_host(0.01, 0.1), O.map_mutations_gt(muts, other.astype(float), 0.01, 0.1))
+        pl.close()
+    bits, words = engine.pack_clades(S)
+    pb = engine.Placement(ctx, [50, 50], 40, S.shape[0])
+    pb.set_clades_host(np.concatenate([bits, bits], axis=0), words)
+    assert pb.info()["algo"] == 1
+    pb.close()
+    n_cells = 20000                                       # prefix counts + accumulators > 227 KB of shared memory
+    tree = synth.coalescent_tree(n_cells, rng)
+    Sb = tree.clade_matrix()
+    bits, words = engine.pack_clades(Sb)
+    pl = engine.Placement(ctx, 16, n_cells, Sb.shape[0])
+    pl.set_clades_host(bits, words)
+    assert pl.info()["algo"] == 1
+    pl.close()
 
 
 def test_radix_mode_falls_back_beyond_four_chunks(ctx, monkeypatch):

@@ -158,3 +158,34 @@ def test_vcf_record_lines_are_sharded_at_line_boundaries():
         with mock.patch.object(dist, "get_rank", return_value=rank), mock.patch.object(dist, "get_world_size", return_value=4):
             got.append(P._shard_record_lines(tiny)[len(head):])
     assert b"".join(got) == b"1\t5\tsnv\n"
+
+
+def test_clade_intervals_of_tree_masks_and_of_general_masks():
+    """The interval path's host analysis: tree-shaped masks (any cell order, empty and duplicate
+    rows included) are recognised and every row is exactly its interval in the returned order;
+    a matrix that is not a laminar family is rejected."""
+    from scsommerclock_b200 import synth
+    rng = np.random.default_rng(5)
+    for n in (2, 3, 33, 100, 257):
+        ts = synth.coalescent_tree(n, rng)
+        cols = rng.permutation(n + 1)                       # leaf rank -> column (one extra column: the outgroup, in no clade)
+        S = np.zeros((2 * n + 1, n + 1), dtype=np.uint8)    # all tree nodes, one duplicate row, one empty row
+        inv = np.zeros(n, dtype=np.int64)
+        inv[ts.leaf_rank] = np.arange(n)                    # depth-first rank -> cell
+        for b in range(2 * n - 1):
+            S[b, cols[inv[ts.lo[b]:ts.hi[b]]]] = 1
+        S[2 * n - 1] = S[0]
+        bits, words = engine.pack_clades(S)
+        ok, perm, lo, hi = engine.clade_intervals(bits, n + 1)
+        assert ok
+        assert sorted(perm.tolist()) == list(range(n + 1))
+        for b in range(S.shape[0]):
+            members = np.zeros(n + 1, dtype=np.uint8)
+            members[perm[lo[b]:hi[b]]] = 1
+            assert np.array_equal(members, S[b]), (n, b)
+    S = np.array([[1, 1, 0, 0], [0, 1, 1, 0], [0, 0, 1, 1]], dtype=np.uint8)      # overlapping, not nested
+    bits, words = engine.pack_clades(S)
+    assert not engine.clade_intervals(bits, 4)[0]
+    S = (rng.random((40, 70)) < 0.3).astype(np.uint8)
+    bits, words = engine.pack_clades(S)
+    assert not engine.clade_intervals(bits, 70)[0]

@@ -1,4 +1,4 @@
-"""Pass 2 from the count cache against the second GEMM pass on the bench's own data path
+"""The three placement variants (GEMM with a second pass, GEMM with the count cache, interval path) on the bench's own data path
 (coalescent tree, device-generated genotypes, row filter), at bench sizes:
 python tools/check_pass2_modes.py [cells] [snvs ...]
 Prints per size the kernel times of both modes, the number of non-finite / mismatching clade rows
@@ -41,11 +41,12 @@ for n_snv in sizes:
     row_keep = torch.empty(n_snv, dtype=torch.uint8, device=dev)
     engine.gt_reduce(ctx, packed, pitch, n_snv, n_cols, active, True, row_keep)
     res = {}
-    for mode in ("recompute", "cache"):
-        os.environ["SCS_PLACE_PASS2"] = mode
+    for mode in ("recompute", "cache", "interval"):
+        os.environ["SCS_PLACE_PASS2"] = "cache" if mode == "interval" else mode
+        os.environ["SCS_PLACE_ALGO"] = "auto" if mode == "interval" else "gemm"
         pl = engine.Placement(ctx, n_snv, n_cols, n_rows)
         pl.set_clades_host(bits, words)
-        pl.set_genotypes(packed, pitch, row_keep, stream=stream)
+        pl.bind_genotypes(packed, pitch, row_keep, stream=stream)
         y = torch.zeros(n_rows, dtype=torch.float64, device=dev)
         for _ in range(3):
             pl.run(bench.FP_TRUE, bench.FN_TRUE / 2, y, stream=stream)
@@ -53,23 +54,25 @@ for n_snv in sizes:
         t = pl.last_times()
         info = pl.info()
         res[mode] = y.cpu().numpy()
-        print("cells %d snvs %d %-9s pass1 %.2f merge %.2f pass2 %.2f reduce %.3f ms  pass2_mode %d runs %d run_len %d free %.1f GB" % (
-            n_cells, n_snv, mode, t[0], t[1], t[2], t[3], info["pass2_mode"], info["runs"], info["run_len"],
-            torch.cuda.mem_get_info()[0] / 1e9), flush=True)
+        print("cells %d snvs %d %-9s pass1 %.2f merge %.2f pass2 %.2f reduce %.3f ms  algo %d pass2_mode %d runs %d run_len %d free %.1f GB  interval grid %d x %d thr, %d B smem, %d runs" % (
+            n_cells, n_snv, mode, t[0], t[1], t[2], t[3], info["algo"], info["pass2_mode"], info["runs"], info["run_len"],
+            torch.cuda.mem_get_info()[0] / 1e9, info["interval_grid"], info["interval_threads"], info["interval_smem_bytes"],
+            info["interval_runs"]), flush=True)
         pl.close()
-    a, b = res["recompute"], res["cache"]
-    nf = ~np.isfinite(b)
-    rel = np.abs(a - b) / np.maximum(1.0, np.abs(a))
-    rel[nf] = np.inf
-    wrong = np.nonzero(rel > 2e-5)[0]
-    print("  kept %d  sum recompute %.6f cache %.6f  non-finite(recompute) %d non-finite(cache) %d  rows off %d  max rel %.3g" % (
-        int(row_keep.sum().item()), a[np.isfinite(a)].sum(), b[~nf].sum(), int((~np.isfinite(a)).sum()), int(nf.sum()), wrong.size,
-        float(rel[~nf].max()) if (~nf).any() else -1), flush=True)
-    if wrong.size:
-        bad += 1
-        tiles, cnt = np.unique(wrong // 128, return_counts=True)
-        print("  off rows by column tile:", dict(zip(tiles.tolist()[:20], cnt.tolist()[:20])), " first rows", wrong[:10].tolist(),
-              " values", a[wrong[:5]].tolist(), b[wrong[:5]].tolist(), flush=True)
+    for other in ("cache", "interval"):
+        a, b = res["recompute"], res[other]
+        nf = ~np.isfinite(b)
+        rel = np.abs(a - b) / np.maximum(1.0, np.abs(a))
+        rel[nf] = np.inf
+        wrong = np.nonzero(rel > 2e-5)[0]
+        print("  %-8s vs recompute: kept %d  sum recompute %.6f %s %.6f  non-finite %d / %d  rows off %d  max rel %.3g" % (
+            other, int(row_keep.sum().item()), a[np.isfinite(a)].sum(), other, b[~nf].sum(), int((~np.isfinite(a)).sum()), int(nf.sum()),
+            wrong.size, float(rel[~nf].max()) if (~nf).any() else -1), flush=True)
+        if wrong.size:
+            bad += 1
+            tiles, cnt = np.unique(wrong // 128, return_counts=True)
+            print("  off rows by column tile:", dict(zip(tiles.tolist()[:20], cnt.tolist()[:20])), " first rows", wrong[:10].tolist(),
+                  " values", a[wrong[:5]].tolist(), b[wrong[:5]].tolist(), flush=True)
     del packed, row_keep
     torch.cuda.empty_cache()
 sys.exit(1 if bad else 0)
