@@ -147,8 +147,9 @@ int scs_placement_last_times(scs_placement* plan, float* ms);
  * 1 when the 2-CTA (cta_group::2) kernel is used, groups, pass-2 mode (0 not run yet,
  * 1 second GEMM pass, 2 sweep over the packed integer counts that pass 1 cached in HBM --
  * chosen per plan, see SCS_PLACE_PASS2 in DESIGN.md), algorithm (0 no clades yet, 1 GEMM,
- * 2 interval path), and for the interval path its grid, threads per CTA, dynamic smem bytes
- * and number of row runs */
+ * 2 interval path), and for the interval path its grid, threads per CTA, dynamic smem bytes,
+ * number of row runs and kernel variant (3: leaves outside the sweeps + count cache in shared
+ * memory, 1: every row through the sweeps -- trees too large for the cache) */
 int scs_placement_info(scs_placement* plan, int64_t* info, int32_t n);
 /* Parity aid for small problems: counts[i][b][0/1] = number of cells of clade b
  * observed mutated / observed wild type for SNV i (exact integers). */

@@ -1309,6 +1309,9 @@ struct Placement {
     int64_t gt_pitch = 0;
     uint16_t* d_perm = nullptr;
     uint32_t* d_lohi = nullptr;
+    int* d_slot_row = nullptr;     // clade row of every accumulator slot (-1: none)
+    uint4* d_off4 = nullptr;       // variant 3: byte offsets into the prefix counts, per pair of rows
+    int iv_slots = 0, iv_variant = 0, iv_nodes = 0, iv_leaf_pos = 0, iv_stride = 0, iv_entries = 0;
     float* ipart = nullptr;
     size_t ipart_bytes = 0;
     int iv_threads = 0, iv_grid = 0, iv_rows_per_run = 0, iv_runs = 0;
@@ -1544,6 +1547,8 @@ int scs_placement_destroy(scs_placement* h) {
     cudaFree(pl->gt_own);
     cudaFree(pl->d_perm);
     cudaFree(pl->d_lohi);
+    cudaFree(pl->d_slot_row);
+    cudaFree(pl->d_off4);
     cudaFree(pl->ipart);
     cudaFree(pl->colpart);
     cudaFree(pl->y);
@@ -1660,45 +1665,113 @@ static int choose_algo(Placement* pl, const uint32_t* bits, int64_t pitch_words,
     const char* e = getenv("SCS_PLACE_ALGO");
     if (e && !strcmp(e, "gemm")) return SCS_OK;
     if (pl->n_groups != 1) return SCS_OK;
-    // shared-memory working set: prefix counts + accumulators always; the per-row count cache and the
-    // cell order when they fit
-    bool dcache = true, perm_smem = true;
-    size_t smem = interval_smem_bytes(pl->n_cells, pl->n_rows, dcache, perm_smem);
-    if (smem > 227 * 1024) {
-        perm_smem = false;
-        smem = interval_smem_bytes(pl->n_cells, pl->n_rows, dcache, perm_smem);
-    }
-    if (smem > 227 * 1024) {
-        dcache = false;
-        perm_smem = true;
-        smem = interval_smem_bytes(pl->n_cells, pl->n_rows, dcache, perm_smem);
-    }
-    if (smem > 227 * 1024) {
-        perm_smem = false;
-        smem = interval_smem_bytes(pl->n_cells, pl->n_rows, dcache, perm_smem);
-    }
-    if (smem > 227 * 1024) return SCS_OK;
+    const size_t SMEM_MAX = 227 * 1024;
+    // cheapest test first: does even the smallest working set (prefix counts + accumulators) fit shared memory?
+    if (interval_smem_bytes(pl->n_cells, pl->n_rows, false, false) > SMEM_MAX) return SCS_OK;
     std::vector<uint16_t> perm;
     std::vector<uint32_t> lohi;
     if (!clade_intervals(bits, pitch_words, pl->n_rows, pl->n_cells, perm, lohi)) return SCS_OK;
-    if (!pl->d_perm && cudaMalloc(&pl->d_perm, size_t(pl->n_cells) * sizeof(uint16_t)) != cudaSuccess) return set_error(SCS_ERR_OOM, "device allocation failed");
-    if (!pl->d_lohi && cudaMalloc(&pl->d_lohi, size_t(pl->n_rows) * sizeof(uint32_t)) != cudaSuccess) return set_error(SCS_ERR_OOM, "device allocation failed");
-    SCS_CUDA(cudaMemcpyAsync(pl->d_perm, perm.data(), perm.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
-    SCS_CUDA(cudaMemcpyAsync(pl->d_lohi, lohi.data(), lohi.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    SCS_CUDA(cudaStreamSynchronize(st));          // perm / lohi are stack-local
-    pl->iv_dcache = dcache;
-    pl->iv_perm_smem = perm_smem;
-    pl->iv_smem = smem;
-    pl->iv_threads = pl->n_rows >= 4096 ? 1024 : (pl->n_rows >= 1024 ? 512 : 256);
-    if (const char* t = getenv("SCS_IV_THREADS")) pl->iv_threads = std::max(32, std::min(1024, atoi(t) / 32 * 32));
-    int per_sm = 1;
-    if (dcache) {
-        cudaFuncSetAttribute(scs_place_interval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scs_place_interval_kernel<true>, pl->iv_threads, smem);
-    } else {
-        cudaFuncSetAttribute(scs_place_interval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scs_place_interval_kernel<false>, pl->iv_threads, smem);
+    const int n_cells = pl->n_cells, n_rows = pl->n_rows;
+    const int n_cells_even = (n_cells + 1) & ~1;
+    int threads = n_rows >= 4096 ? 1024 : (n_rows >= 1024 ? 512 : 256);
+    if (const char* t = getenv("SCS_IV_THREADS")) threads = std::max(32, std::min(1024, atoi(t) / 32 * 32));
+
+    // ---- variant 3 (leaves out of the sweeps, count cache in shared memory) when it fits
+    std::vector<int> leaf_row_of_pos(size_t(n_cells), -1), general;
+    for (int r = 0; r < n_rows; ++r) {
+        const int lo = int(lohi[size_t(r)] & 0xFFFFu), hi = int(lohi[size_t(r)] >> 16);
+        if (hi - lo == 1 && leaf_row_of_pos[size_t(lo)] < 0) leaf_row_of_pos[size_t(lo)] = r;
+        else general.push_back(r);
     }
+    // the sweeps walk the rows sorted by (lo, hi): neighbouring lanes then look up neighbouring prefix counts
+    // instead of 32 random shared-memory banks
+    auto by_interval = [&](int a, int b) {
+        const uint32_t la = lohi[size_t(a)] & 0xFFFFu, lb = lohi[size_t(b)] & 0xFFFFu;
+        return la != lb ? la < lb : (lohi[size_t(a)] >> 16) < (lohi[size_t(b)] >> 16);
+    };
+    std::stable_sort(general.begin(), general.end(), by_interval);
+    const int n_gen = int(general.size()), n_slots3 = (n_gen + 1) & ~1;
+    int threads3 = threads;
+    while (threads3 < 1024 && (((n_cells + threads3 - 1) / threads3) | 1) > 15) threads3 *= 2;
+    const bool v3 = n_cells < 32768 && interval3_smem_bytes(n_cells, n_slots3) <= SMEM_MAX && (((n_cells + threads3 - 1) / threads3) | 1) <= 15 &&
+                    !(e && !strcmp(e, "interval1"));
+    std::vector<int> slot_row;
+    size_t smem = 0;
+    int per_sm = 1;
+    if (v3) {
+        threads = threads3;
+        std::vector<uint4> off4(size_t(n_slots3 / 2), make_uint4(0u, 0u, 0u, 0u));
+        for (int sidx = 0; sidx < n_gen; ++sidx) {
+            const uint32_t lh = lohi[size_t(general[size_t(sidx)])];
+            uint4& o = off4[size_t(sidx >> 1)];
+            if (sidx & 1) {
+                o.z = (lh & 0xFFFFu) * 4u;
+                o.w = (lh >> 16) * 4u;
+            } else {
+                o.x = (lh & 0xFFFFu) * 4u;
+                o.y = (lh >> 16) * 4u;
+            }
+        }
+        int n_leaf_pos = 0;
+        for (int k = 0; k < n_cells; ++k)
+            if (leaf_row_of_pos[size_t(k)] >= 0) {
+                perm[size_t(k)] |= 0x8000u;
+                ++n_leaf_pos;
+            }
+        slot_row.assign(size_t(n_slots3 + n_cells_even), -1);
+        for (int sidx = 0; sidx < n_gen; ++sidx) slot_row[size_t(sidx)] = general[size_t(sidx)];
+        for (int k = 0; k < n_cells; ++k) slot_row[size_t(n_slots3 + k)] = leaf_row_of_pos[size_t(k)];
+        cudaFree(pl->d_off4);
+        pl->d_off4 = nullptr;
+        if (cudaMalloc(&pl->d_off4, std::max<size_t>(1, off4.size()) * sizeof(uint4)) != cudaSuccess) return set_error(SCS_ERR_OOM, "device allocation failed");
+        SCS_CUDA(cudaMemcpyAsync(pl->d_off4, off4.data(), off4.size() * sizeof(uint4), cudaMemcpyHostToDevice, st));
+        SCS_CUDA(cudaStreamSynchronize(st));
+        pl->iv_variant = 3;
+        pl->iv_nodes = n_gen;
+        pl->iv_slots = n_slots3;
+        pl->iv_leaf_pos = n_leaf_pos;
+        pl->iv_stride = n_slots3 + n_cells_even;
+        smem = interval3_smem_bytes(n_cells, n_slots3);
+        cudaFuncSetAttribute(scs_place_interval3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scs_place_interval3_kernel, threads, smem);
+    } else {
+        // ---- variant 1: every row through the sweeps, counts recomputed in the second sweep
+        std::vector<int> all(size_t(n_rows), 0);
+        std::iota(all.begin(), all.end(), 0);
+        std::stable_sort(all.begin(), all.end(), by_interval);
+        const int n_slots1 = (n_rows + 1) & ~1;
+        std::vector<uint32_t> lohi_sorted(size_t(n_slots1), 0u);
+        for (int sidx = 0; sidx < n_rows; ++sidx) lohi_sorted[size_t(sidx)] = lohi[size_t(all[size_t(sidx)])];
+        slot_row.assign(size_t(n_slots1), -1);
+        for (int sidx = 0; sidx < n_rows; ++sidx) slot_row[size_t(sidx)] = all[size_t(sidx)];
+        cudaFree(pl->d_lohi);
+        pl->d_lohi = nullptr;
+        if (cudaMalloc(&pl->d_lohi, size_t(n_slots1) * sizeof(uint32_t)) != cudaSuccess) return set_error(SCS_ERR_OOM, "device allocation failed");
+        SCS_CUDA(cudaMemcpyAsync(pl->d_lohi, lohi_sorted.data(), lohi_sorted.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        SCS_CUDA(cudaStreamSynchronize(st));
+        pl->iv_variant = 1;
+        pl->iv_nodes = n_rows;
+        pl->iv_slots = n_slots1;
+        pl->iv_leaf_pos = 0;
+        pl->iv_stride = n_slots1;
+        pl->iv_perm_smem = interval_smem_bytes(n_cells, n_rows, false, true) <= SMEM_MAX;
+        smem = interval_smem_bytes(n_cells, n_rows, false, pl->iv_perm_smem);
+        cudaFuncSetAttribute(scs_place_interval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scs_place_interval_kernel<false>, threads, smem);
+    }
+    cudaFree(pl->d_perm);
+    cudaFree(pl->d_slot_row);
+    pl->d_perm = nullptr;
+    pl->d_slot_row = nullptr;
+    if (cudaMalloc(&pl->d_perm, size_t(n_cells) * sizeof(uint16_t)) != cudaSuccess ||
+        cudaMalloc(&pl->d_slot_row, slot_row.size() * sizeof(int)) != cudaSuccess)
+        return set_error(SCS_ERR_OOM, "device allocation failed");
+    SCS_CUDA(cudaMemcpyAsync(pl->d_perm, perm.data(), perm.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+    SCS_CUDA(cudaMemcpyAsync(pl->d_slot_row, slot_row.data(), slot_row.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    SCS_CUDA(cudaStreamSynchronize(st));          // the host vectors are stack-local
+    pl->iv_entries = int(slot_row.size());
+    pl->iv_smem = smem;
+    pl->iv_threads = threads;
     per_sm = std::max(1, per_sm);
     const int64_t slots = int64_t(pl->ctx->sm_count) * per_sm;
     // runs: short fp32 accumulation chains (<= 256 rows) and at least ~4 runs per resident CTA
@@ -1707,7 +1780,7 @@ static int choose_algo(Placement* pl, const uint32_t* bits, int64_t pitch_words,
     pl->iv_rows_per_run = rpr;
     pl->iv_runs = int((pl->n_snv + rpr - 1) / rpr);
     pl->iv_grid = int(std::min<int64_t>(pl->iv_runs, slots));
-    const size_t pbytes = size_t(pl->iv_runs) * pl->n_rows * sizeof(float);
+    const size_t pbytes = size_t(pl->iv_runs) * size_t(pl->iv_stride) * sizeof(float);
     if (pbytes > pl->ipart_bytes) {
         cudaFree(pl->ipart);
         pl->ipart = nullptr;
@@ -1853,7 +1926,8 @@ int scs_placement_run_batch(scs_placement* h, const double* FP, const double* FN
         ip.pitch = pl->gt_pitch;
         ip.n_snv = pl->n_snv;
         ip.n_cells = pl->n_cells;
-        ip.n_nodes = pl->n_rows;
+        ip.n_nodes = pl->iv_nodes;
+        ip.n_slots = pl->iv_slots;
         ip.row_words = (pl->n_cells + 15) / 16;
         ip.perm = pl->d_perm;
         ip.lohi = pl->d_lohi;
@@ -1865,12 +1939,21 @@ int scs_placement_run_batch(scs_placement* h, const double* FP, const double* FN
         ip.perm_smem = pl->iv_perm_smem ? 1 : 0;
         double* y = d_soft_weights ? d_soft_weights : pl->y;
         cudaEventRecord(pl->ev[0], st);
-        if (pl->iv_dcache) scs_place_interval_kernel<true><<<pl->iv_grid, pl->iv_threads, pl->iv_smem, st>>>(ip);
-        else scs_place_interval_kernel<false><<<pl->iv_grid, pl->iv_threads, pl->iv_smem, st>>>(ip);
+        if (pl->iv_variant == 3) {
+            Interval3Params q;
+            q.b = ip;
+            q.off4 = pl->d_off4;
+            q.n_leaf_pos = pl->iv_leaf_pos;
+            q.part_stride = pl->iv_stride;
+            scs_place_interval3_kernel<<<pl->iv_grid, pl->iv_threads, pl->iv_smem, st>>>(q);
+        } else {
+            scs_place_interval_kernel<false><<<pl->iv_grid, pl->iv_threads, pl->iv_smem, st>>>(ip);
+        }
         cudaEventRecord(pl->ev[1], st);
         cudaEventRecord(pl->ev[2], st);
         cudaEventRecord(pl->ev[3], st);
-        scs_reduce_interval_kernel<<<unsigned((pl->n_rows + 255) / 256), 256, 0, st>>>(pl->ipart, pl->iv_runs, pl->n_rows, y);
+        scs_reduce_interval_kernel<<<unsigned((pl->iv_entries + 255) / 256), 256, 0, st>>>(pl->ipart, pl->iv_runs, pl->iv_entries, pl->iv_stride,
+                                                                                         pl->d_slot_row, y);
         cudaEventRecord(pl->ev[4], st);
         pl->timed = true;
         pl->launches += 2;
@@ -1985,11 +2068,11 @@ int scs_placement_debug_stats(scs_placement* h, void* stats_host, void* rowref_h
 int scs_placement_info(scs_placement* h, int64_t* info, int32_t n) {
     Placement* pl = reinterpret_cast<Placement*>(h);
     if (!pl || !info) return set_error(SCS_ERR_ARG, "null argument");
-    const int64_t v[20] = {pl->M_pad, pl->N_pad, pl->K_pad, pl->prm.num_tasks, pl->prm.run_len, pl->prm.sb_width, pl->pair ? pl->grid2 : pl->grid, pl->launches, pl->prm.num_runs,
+    const int64_t v[21] = {pl->M_pad, pl->N_pad, pl->K_pad, pl->prm.num_tasks, pl->prm.run_len, pl->prm.sb_width, pl->pair ? pl->grid2 : pl->grid, pl->launches, pl->prm.num_runs,
                            pl->pair ? K2_SMEM_TOTAL : (pl->mode == MODE_RADIX ? ModeCfg<MODE_RADIX>::SMEM_TOTAL : ModeCfg<MODE_PLANES>::SMEM_TOTAL),
                            pl->mode, pl->prm.nchunk, pl->pair ? 1 : 0, pl->n_groups, pl->pass2_mode,
-                           pl->algo, pl->iv_grid, pl->iv_threads, int64_t(pl->iv_smem), pl->iv_runs};
-    for (int i = 0; i < n && i < 20; ++i) info[i] = v[i];
+                           pl->algo, pl->iv_grid, pl->iv_threads, int64_t(pl->iv_smem), pl->iv_runs, pl->iv_variant};
+    for (int i = 0; i < n && i < 21; ++i) info[i] = v[i];
     return SCS_OK;
 }
 

@@ -43,10 +43,12 @@ struct IntervalParams {
     int n_cells, n_nodes;
     int row_words;             // 32-bit words of a row that hold cells: ceil(n_cells / 16)
     const uint16_t* perm;      // [n_cells] column of the cell at depth-first position k
-    const uint32_t* lohi;      // [n_nodes] lo | hi << 16 (positions, hi exclusive; lo = hi for an empty row)
+    const uint32_t* lohi;      // [n_slots] lo | hi << 16 (positions, hi exclusive; lo = hi for an empty row), the clade rows
+                               // sorted by (lo, hi) so that neighbouring lanes look up neighbouring prefix counts
+    int n_slots;               // n_nodes rounded up to even (slot n_nodes, if any, is padding and carries no weight)
     const uint8_t* row_keep;   // optional [n_snv]
     const GroupConst* gconst;
-    float* part;               // [num_runs][n_nodes]
+    float* part;               // [num_runs][n_slots], in sorted clade-row order
     int rows_per_run, num_runs;
     int perm_smem;             // 1: the cell order is staged in shared memory (it fits), 0: read from global / L2
 };
@@ -56,7 +58,8 @@ constexpr int IV_SCRATCH_WORDS = 5 * 32;
 __host__ __device__ inline int iv_p_words(int n_cells) { return (n_cells + 1 + 3) & ~3; }
 
 static inline size_t interval_smem_bytes(int n_cells, int n_nodes, bool dcache, bool perm_smem) {
-    return 4 * (size_t(iv_p_words(n_cells)) + size_t(n_nodes) * (dcache ? 2 : 1) + 2 * size_t((n_cells + 15) / 16) + IV_SCRATCH_WORDS +
+    const size_t n_slots = size_t(n_nodes + 1) & ~size_t(1);
+    return 4 * (size_t(iv_p_words(n_cells)) + n_slots * (dcache ? 2 : 1) + 2 * size_t((n_cells + 15) / 16) + IV_SCRATCH_WORDS +
                 (perm_smem ? size_t((n_cells + 1) / 2) : 0));
 }
 
@@ -80,11 +83,11 @@ __global__ void __launch_bounds__(1024, 1) scs_place_interval_kernel(const Inter
     const int T = blockDim.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarp = T >> 5;
     uint32_t* P = iv_smem;
     float* acc = reinterpret_cast<float*>(P + iv_p_words(p.n_cells));
-    uint32_t* dc = reinterpret_cast<uint32_t*>(acc + p.n_nodes);
-    uint32_t* rowbuf = dc + (DCACHE ? p.n_nodes : 0);
+    uint32_t* dc = reinterpret_cast<uint32_t*>(acc + p.n_slots);
+    uint32_t* rowbuf = dc + (DCACHE ? p.n_slots : 0);
     uint32_t* scr = rowbuf + 2 * p.row_words;      // [0,32) scan totals, [32,64) rank values, [64,96) / [96,128) reference counts, [128,160) sums
     const GroupConst gc = p.gconst[0];
-    const int E = (p.n_cells + T - 1) / T;         // depth-first positions per thread (contiguous)
+    const int E = ((p.n_cells + T - 1) / T) | 1;   // depth-first positions per thread (contiguous; odd: the P[k + 1] stores of a warp spread over all banks)
     const int k0 = min(t * E, p.n_cells), k1 = min(k0 + E, p.n_cells);
     // Nothing row-independent is fetched from global memory inside the row loop: with one CTA per SM in
     // lockstep between barriers, every exposed L2 round trip (~0.5 us) would be a tenth of a row's time.
@@ -228,25 +231,279 @@ __global__ void __launch_bounds__(1024, 1) scs_place_interval_kernel(const Inter
             }
         }
         asm volatile("cp.async.wait_all;\n" ::: "memory");
-        float* out = p.part + size_t(run) * p.n_nodes;
+        float* out = p.part + size_t(run) * p.n_slots;
         for (int b = t; b < p.n_nodes; b += T) out[b] = acc[b];
     }
 }
 
-// y[b] = sum over the runs of part[run][b], fixed order, fp64
-__global__ void scs_reduce_interval_kernel(const float* __restrict__ part, int num_runs, int n_nodes, double* __restrict__ y) {
+// ---- the main variant: per-row count cache in shared memory (whenever it fits: up to ~14,000 cells with
+// all 2n clade rows), packed fp32x2 arithmetic, and the single-cell rows (the leaves: half of a tree's
+// clade rows) taken out of the sweeps:
+//   * a leaf's counts are its cell's genotype, so a row has only THREE distinct leaf terms (mutated /
+//     wild type / missing).  They are evaluated once per SNV; their share of the row sum is
+//     n_mut t_mut + n_wt t_wt + n_miss t_miss from the leaf totals, and each leaf's accumulator gets
+//     its term from the 2-bit codes the scan kept in a register -- ~10 instructions per (SNV, leaf);
+//   * the other rows (internal nodes, empty rows, duplicates), sorted by (lo, hi), go through three
+//     sweeps over PAIRS of rows:
+//       sweep 1  counts d = P[hi] - P[lo] -> cache; best column of the row by rank value (no exponentials)
+//       sweep 2  t = 2^(logit - logit_best) from exact integer differences -> cache (in place); row sum
+//       sweep 3  accumulators += t / sum
+//     ~55 instructions per (SNV, row), one ex2.
+// Tables: perm[k] = column of depth-first position k, bit 15 set when the position has a leaf row
+// (n_cells < 32768 here); off4[pair] = byte offsets into P (lo0, hi0, lo1, hi1) * 4.
+struct Interval3Params {
+    IntervalParams b;          // n_nodes / n_slots / lohi describe the NON-leaf rows here; part rows hold
+                               // [n_slots non-leaf accumulators][n_cells_even leaf accumulators by position]
+    const uint4* off4;         // [n_slots / 2]
+    int n_leaf_pos;            // positions that have a leaf row
+    int part_stride;           // n_slots + n_cells rounded up to even
+};
+
+__device__ __forceinline__ float2 iv_lo16(uint32_t a, uint32_t b) {      // (2^23 + low half of a, 2^23 + low half of b)
+    return make_float2(__uint_as_float(__byte_perm(a, 0x4B000000u, 0x7610)), __uint_as_float(__byte_perm(b, 0x4B000000u, 0x7610)));
+}
+__device__ __forceinline__ float2 iv_hi16(uint32_t a, uint32_t b) {
+    return make_float2(__uint_as_float(__byte_perm(a, 0x4B000000u, 0x7632)), __uint_as_float(__byte_perm(b, 0x4B000000u, 0x7632)));
+}
+__device__ __forceinline__ uint32_t iv_lds_off(const uint32_t* base, uint32_t byte_off) {
+    return *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(base) + byte_off);
+}
+
+constexpr int IV3_SCRATCH_WORDS = 6 * 32;
+
+static inline size_t interval3_smem_bytes(int n_cells, int n_slots) {
+    // P | non-leaf accumulators | count / term cache | leaf accumulators | two row buffers | scratch | perm
+    return 4 * (size_t(iv_p_words(n_cells)) + 2 * size_t(n_slots) + (size_t(n_cells + 1) & ~size_t(1)) + 2 * size_t((n_cells + 15) / 16) +
+                IV3_SCRATCH_WORDS + size_t((n_cells + 1) / 2));
+}
+
+__global__ void __launch_bounds__(1024, 1) scs_place_interval3_kernel(const Interval3Params q) {
+    const IntervalParams& p = q.b;
+    extern __shared__ uint32_t iv_smem[];
+    const int T = blockDim.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarp = T >> 5;
+    const int n_cells_even = (p.n_cells + 1) & ~1;
+    uint32_t* P = iv_smem;
+    float2* acc2 = reinterpret_cast<float2*>(P + iv_p_words(p.n_cells));           // 16-byte aligned: iv_p_words is a multiple of 4
+    uint2* dc2 = reinterpret_cast<uint2*>(reinterpret_cast<float*>(acc2) + p.n_slots);
+    float* accL = reinterpret_cast<float*>(reinterpret_cast<uint32_t*>(dc2) + p.n_slots);
+    uint32_t* rowbuf = reinterpret_cast<uint32_t*>(accL + n_cells_even);
+    uint32_t* scr = rowbuf + 2 * p.row_words;      // [0,32) scan totals, [32,64) rank values, [64,96) their counts, [128,160) sums, [160,192) leaf totals
+    uint16_t* perm = reinterpret_cast<uint16_t*>(scr + IV3_SCRATCH_WORDS);
+    const GroupConst gc = p.gconst[0];
+    const int E = ((p.n_cells + T - 1) / T) | 1;   // <= 15 (host): the 2-bit codes of a thread's positions fit one register
+    const int k0 = min(t * E, p.n_cells), k1 = min(k0 + E, p.n_cells);
+    const int n_pairs = p.n_slots >> 1;
+    const int j_pad = (p.n_nodes & 1) ? n_pairs - 1 : -1;         // the pair whose second slot is padding
+    for (int k = t; k < p.n_cells; k += T) perm[k] = p.perm[k];   // (visible after the first barrier of the row loop)
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    const uint4 of_first0 = t < n_pairs ? q.off4[t] : zero4, of_first1 = t + T < n_pairs ? q.off4[t + T] : zero4;
+    const float2 a1f2 = make_float2(gc.a1f, gc.a1f), a0f2 = make_float2(gc.a0f, gc.a0f);
+    const float2 a1h2 = make_float2(gc.a1h, gc.a1h), a0h2 = make_float2(gc.a0h, gc.a0h);
+    const float2 a1l2 = make_float2(gc.a1l, gc.a1l), a0l2 = make_float2(gc.a0l, gc.a0l);
+    const float2 n23 = make_float2(-8388608.0f, -8388608.0f);
+
+    for (int run = blockIdx.x; run < p.num_runs; run += gridDim.x) {
+        for (int j = t; j < n_pairs; j += T) acc2[j] = make_float2(0.f, 0.f);
+        for (int k = k0; k < k1; ++k) accL[k] = 0.f;
+        const long long r0 = (long long)run * p.rows_per_run;
+        const long long r1 = r0 + p.rows_per_run < p.n_snv ? r0 + p.rows_per_run : p.n_snv;
+        int buf = 0;
+        iv_issue_row(p, r0, rowbuf, t, T);
+        uint32_t keep_next = p.row_keep != nullptr ? p.row_keep[r0] : 1u;
+        for (long long r = r0; r < r1; ++r, buf ^= 1) {
+            asm volatile("cp.async.wait_all;\n" ::: "memory");
+            __syncthreads();
+            const uint32_t keep = keep_next;
+            if (r + 1 < r1) {
+                iv_issue_row(p, r + 1, rowbuf + (buf ^ 1) * p.row_words, t, T);
+                if (p.row_keep != nullptr) keep_next = p.row_keep[r + 1];
+            }
+            if (keep == 0u) continue;
+
+            // ---- prefix counts in depth-first order; the thread keeps its positions' codes (0 wild type, 1 mutated,
+            // 3 missing or no leaf row) and the totals over positions that have a leaf row
+            const uint8_t* rb8 = reinterpret_cast<const uint8_t*>(rowbuf + buf * p.row_words);
+            uint32_t run_sum = 0u, leaf_sum = 0u, codes = 0u;
+            for (int k = k0; k < k1; ++k) {
+                const uint32_t pc = perm[k];
+                const uint32_t col = pc & 0x7FFFu;
+                const uint32_t code = (uint32_t(rb8[col >> 2]) >> ((col & 3) * 2)) & 3u;
+                const uint32_t inc = code == 3u ? 0u : (code == 0u ? 0x10000u : 1u);
+                run_sum += inc;
+                P[k + 1] = run_sum;
+                const bool leaf = (pc & 0x8000u) != 0u;
+                leaf_sum += leaf ? inc : 0u;
+                // per-leaf selector: 0 wild type, 1 mutated, 2 missing, 3 no leaf row at this position
+                const uint32_t sel = leaf ? (code == 3u ? 2u : (code == 0u ? 0u : 1u)) : 3u;
+                codes |= sel << (2 * (k - k0));
+            }
+            uint32_t incl = run_sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) leaf_sum += __shfl_xor_sync(0xffffffffu, leaf_sum, o);
+            if (lane == 31) {
+                scr[warp] = incl;
+                scr[160 + warp] = leaf_sum;
+            }
+            __syncthreads();
+            const uint32_t wt = lane < nwarp ? scr[lane] : 0u;
+            uint32_t winc = wt, ltot = lane < nwarp ? scr[160 + lane] : 0u;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += v;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ltot += __shfl_xor_sync(0xffffffffu, ltot, o);
+            const uint32_t base = __shfl_sync(0xffffffffu, winc - wt, warp) + incl - run_sum;
+            for (int k = k0; k < k1; ++k) P[k + 1] += base;
+            if (t == 0) P[0] = 0u;
+            __syncthreads();
+            const float n_mut = float(ltot & 0xFFFFu), n_wt = float(ltot >> 16), n_miss = float(q.n_leaf_pos) - n_mut - n_wt;
+
+            // ---- sweep 1: counts into the cache, best column by rank value
+            float bv = -INFINITY;
+            uint32_t bd = 0u;
+            {
+                uint4 of = of_first0, of_n1 = of_first1;
+                for (int j = t; j < n_pairs; j += T) {
+                    const uint4 of_n2 = j + 2 * T < n_pairs ? q.off4[j + 2 * T] : zero4;
+                    const uint32_t d0 = iv_lds_off(P, of.y) - iv_lds_off(P, of.x);      // both counts at once (no borrow: P is monotone in each half)
+                    const uint32_t d1 = iv_lds_off(P, of.w) - iv_lds_off(P, of.z);
+                    of = of_n1;
+                    of_n1 = of_n2;
+                    dc2[j] = make_uint2(d0, d1);
+                    const float2 c1 = __fadd2_rn(iv_lo16(d0, d1), n23), c0 = __fadd2_rn(iv_hi16(d0, d1), n23);
+                    float2 v = __ffma2_rn(a1f2, c1, __fmul2_rn(a0f2, c0));
+                    if (j == j_pad) v.y = -INFINITY;
+                    if (v.x > bv) {          // (first maximum in this thread's fixed order)
+                        bv = v.x;
+                        bd = d0;
+                    }
+                    if (v.y > bv) {
+                        bv = v.y;
+                        bd = d1;
+                    }
+                }
+            }
+            // across threads: ties go to the larger packed counts -- a total order, so the result is the same
+            // for every reduction shape
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const uint32_t od = __shfl_xor_sync(0xffffffffu, bd, o);
+                if (ov > bv || (ov == bv && od > bd)) {
+                    bv = ov;
+                    bd = od;
+                }
+            }
+            if (lane == 0) {
+                scr[32 + warp] = __float_as_uint(bv);
+                scr[64 + warp] = bd;
+            }
+            __syncthreads();
+            bv = lane < nwarp ? __uint_as_float(scr[32 + lane]) : -INFINITY;
+            bd = lane < nwarp ? scr[64 + lane] : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const uint32_t od = __shfl_xor_sync(0xffffffffu, bd, o);
+                if (ov > bv || (ov == bv && od > bd)) {
+                    bv = ov;
+                    bd = od;
+                }
+            }
+            // the three leaf columns compete too: mutated (C1, C0) = (1, 0), wild type (0, 1), missing (0, 0)
+            if (n_mut > 0.f && (gc.a1f > bv || (gc.a1f == bv && 1u > bd))) {
+                bv = gc.a1f;
+                bd = 1u;
+            }
+            if (n_wt > 0.f && (gc.a0f > bv || (gc.a0f == bv && 0x10000u > bd))) {
+                bv = gc.a0f;
+                bd = 0x10000u;
+            }
+            if (n_miss > 0.f && 0.f > bv) {
+                bv = 0.f;
+                bd = 0u;
+            }
+            // reference counts: e = count - reference is an exact integer difference
+            const float rf1 = float(bd & 0xFFFFu), rf0 = float(bd >> 16);
+            const float2 nb1_2 = make_float2(-(8388608.0f + rf1), -(8388608.0f + rf1)), nb0_2 = make_float2(-(8388608.0f + rf0), -(8388608.0f + rf0));
+            // the three leaf terms and their share of the row sum
+            float t_leaf[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float e1 = (c == 1 ? 1.f : 0.f) - rf1, e0 = (c == 0 ? 1.f : 0.f) - rf0;
+                t_leaf[c] = ex2_approx(fmaf(gc.a1h, e1, gc.a0h * e0) + fmaf(gc.a1l, e1, gc.a0l * e0));
+            }
+            const float leaf_total = fmaf(n_mut, t_leaf[1], fmaf(n_wt, t_leaf[0], n_miss * t_leaf[2]));
+
+            // ---- sweep 2: terms relative to the best column, in place; row sum
+            float2 s2 = make_float2(0.f, 0.f);
+            for (int j = t; j < n_pairs; j += T) {
+                const uint2 d = dc2[j];
+                const float2 e1 = __fadd2_rn(iv_lo16(d.x, d.y), nb1_2), e0 = __fadd2_rn(iv_hi16(d.x, d.y), nb0_2);
+                const float2 sdiff = __ffma2_rn(a1h2, e1, __fmul2_rn(a0h2, e0));      // exact operands, one rounding
+                const float2 lo = __ffma2_rn(a1l2, e1, __fmul2_rn(a0l2, e0));
+                const float2 x = __fadd2_rn(sdiff, lo);
+                float2 tt = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+                if (j == j_pad) tt.y = 0.f;
+                s2 = __fadd2_rn(s2, tt);
+                dc2[j] = make_uint2(__float_as_uint(tt.x), __float_as_uint(tt.y));
+            }
+            float sum = s2.x + s2.y;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (lane == 0) scr[128 + warp] = __float_as_uint(sum);
+            __syncthreads();
+            float total = lane < nwarp ? __uint_as_float(scr[128 + lane]) : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+            const float inv = 1.0f / (total + leaf_total);        // >= 1: the best column's own term
+            const float2 inv2 = make_float2(inv, inv);
+
+            // ---- sweep 3: normalised terms into the accumulators (each owned by one thread)
+            for (int j = t; j < n_pairs; j += T) {
+                const uint2 tb = dc2[j];
+                acc2[j] = __ffma2_rn(make_float2(__uint_as_float(tb.x), __uint_as_float(tb.y)), inv2, acc2[j]);
+            }
+            const float w_wt = t_leaf[0] * inv, w_mut = t_leaf[1] * inv, w_miss = t_leaf[2] * inv;
+            uint32_t cc = codes;
+            for (int k = k0; k < k1; ++k, cc >>= 2) {
+                const uint32_t sel = cc & 3u;
+                const float w = sel == 0u ? w_wt : (sel == 1u ? w_mut : (sel == 2u ? w_miss : 0.f));
+                accL[k] += w;
+            }
+        }
+        asm volatile("cp.async.wait_all;\n" ::: "memory");
+        float* out = p.part + size_t(run) * q.part_stride;
+        for (int j = t; j < n_pairs; j += T) reinterpret_cast<float2*>(out)[j] = acc2[j];
+        for (int k = k0; k < k1; ++k) out[p.n_slots + k] = accL[k];
+    }
+}
+
+// y[row of slot s] = sum over the runs of part[run][s], fixed order, fp64 (slots without a row -- padding,
+// positions without a leaf row -- are skipped)
+__global__ void scs_reduce_interval_kernel(const float* __restrict__ part, int num_runs, int n_entries, int stride,
+                                           const int* __restrict__ row_of_slot, double* __restrict__ y) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= n_nodes) return;
+    if (b >= n_entries) return;
+    const int row = row_of_slot[b];
+    if (row < 0) return;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     int r = 0;
     for (; r + 3 < num_runs; r += 4) {
-        a0 += double(part[size_t(r) * n_nodes + b]);
-        a1 += double(part[size_t(r + 1) * n_nodes + b]);
-        a2 += double(part[size_t(r + 2) * n_nodes + b]);
-        a3 += double(part[size_t(r + 3) * n_nodes + b]);
+        a0 += double(part[size_t(r) * stride + b]);
+        a1 += double(part[size_t(r + 1) * stride + b]);
+        a2 += double(part[size_t(r + 2) * stride + b]);
+        a3 += double(part[size_t(r + 3) * stride + b]);
     }
-    for (; r < num_runs; ++r) a0 += double(part[size_t(r) * n_nodes + b]);
-    y[b] = (a0 + a1) + (a2 + a3);
+    for (; r < num_runs; ++r) a0 += double(part[size_t(r) * stride + b]);
+    y[row] = (a0 + a1) + (a2 + a3);
 }
 
 // ---- host: is the clade matrix a laminar family, and in which cell order is every row an interval?

@@ -139,11 +139,11 @@ class Placement:
             pass
 
     def info(self):
-        v = (C.c_int64 * 20)()
-        check(lib().scs_placement_info(self._h, v, 20))
+        v = (C.c_int64 * 21)()
+        check(lib().scs_placement_info(self._h, v, 21))
         keys = ("M_pad", "N_pad", "K_pad", "tasks", "run_len", "superblock_width", "grid", "launches", "runs", "smem_bytes",
                 "mode", "k_chunks", "cta_pair", "groups", "pass2_mode", "algo", "interval_grid", "interval_threads",
-                "interval_smem_bytes", "interval_runs")
+                "interval_smem_bytes", "interval_runs", "interval_variant")
         return dict(zip(keys, (int(x) for x in v)))
 
     # host buffers (numpy)

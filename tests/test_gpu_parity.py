@@ -214,12 +214,18 @@ def test_interval_path_matches_oracle_and_gemm(ctx, monkeypatch, n_snv, n_cells)
         assert_soft_close(got["auto"], O.map_mutations_gt(muts, S.astype(float), 0.01, 0.1))
 
 
+@pytest.mark.parametrize("variant", [3, 1])
 @pytest.mark.parametrize("threads,rows_per_run", [(32, 1), (64, 3), (96, 7), (1024, 256)])
-def test_interval_path_block_shapes_and_run_lengths(ctx, monkeypatch, threads, rows_per_run):
+def test_interval_path_block_shapes_and_run_lengths(ctx, monkeypatch, threads, rows_per_run, variant):
     """One warp per CTA up to 32 warps (most of them without a clade row), runs of 1..256 SNV rows, rows
-    dropped by the filter, extreme error rates."""
+    dropped by the filter, extreme error rates; both kernel variants (3: leaves outside the sweeps and
+    counts cached in shared memory, 1: every row through the sweeps -- what very large trees get).
+    The masks also hold an empty row, a duplicate of a leaf row and a duplicate of an internal row."""
     n_snv, n_cells = 333, 300
     codes, S = shuffled_problem(n_snv, n_cells, seed=threads)
+    S = np.concatenate([S, S[5:6], S[n_cells + 3:n_cells + 4], S[0:1]], axis=0)
+    if variant == 1:
+        monkeypatch.setenv("SCS_PLACE_ALGO", "interval1")
     codes[7] = 3                       # nothing observed: uniform over the rows of S
     codes[8] = 1                       # everything mutated
     codes[9] = 0
@@ -232,7 +238,8 @@ def test_interval_path_block_shapes_and_run_lengths(ctx, monkeypatch, threads, r
     pl.set_clades_host(bits, words)
     pl.set_genotypes_host(packed, pitch, keep)
     info = pl.info()
-    assert info["algo"] == 2 and info["interval_threads"] == threads
+    assert info["algo"] == 2 and info["interval_variant"] == variant
+    assert info["interval_threads"] == threads
     muts = np.where(codes == 3, np.nan, codes.astype(float))[keep.astype(bool)]
     for FP, FN in [(0.01, 0.1), (1e-6, 1e-6), (0.2, 0.4)]:
         assert_soft_close(pl.run_host(FP, FN), O.map_mutations_gt(muts, S.astype(float), FP, FN))
