@@ -9,10 +9,13 @@ Workload (BASELINE.json configs[3]): 10,000 cells x 1,000,000 SNVs PER GPU, SNV
 rows sharded over ranks (weak scaling), one all-reduce of the 2n branch weights,
 then the clock LRT for the ten default w_max values.  One "step" is one pass of
 the hot path over the resident packed genotype matrix:
-    row filter + missing rates (scs_gt_reduce) -> operand planes -> GEMM pass 1 ->
-    merge -> GEMM pass 2 -> reduce -> [all-reduce] -> LRT batch -> result to host.
-`value` times that with CUDA events, inputs already in HBM; `e2e` adds the H2D copy
-of the packed matrix from pinned host memory every step.  Prints ONE JSON line.
+    row filter + missing rates (scs_gt_reduce) -> placement -> [all-reduce] -> LRT batch -> result to host,
+where the placement of a tree-shaped clade matrix is ONE kernel (interval path: per-SNV prefix
+counts in shared memory, counts of a clade = one difference) and that of a general 0/1 matrix
+(or with --algo gemm) is operand planes -> tcgen05 GEMM pass 1 -> merge -> pass 2 -> reduce.
+`value` times the step with CUDA events, inputs already in HBM; `e2e` adds the H2D copy of the
+packed matrix from pinned host memory every step; `gemm_path` is the same workload through the
+GEMM, measured in the same run.  Prints ONE JSON line.
 """
 import argparse
 import json
@@ -40,6 +43,11 @@ METRIC = "snv_branch_placements_per_s"
 # (profiles/r01_ncu_place_radix_summary.txt: 287.1 GB read + 2.5 GB written, pass 1, radix mode;
 # earlier captures of the same kernel read 280-310 GB -- it depends on how the L2 halves fill)
 NCU_TRAFFIC_BYTES = 289.6e9
+# pass 1 that also fills the count cache (profiles/r01_ncu_place_cache_summary.txt, 250k-SNV capture x 4:
+# 230 GB read + 83 GB written) and the interval kernel (profiles/r01_ncu_interval_summary.txt: the packed
+# genotypes once + per-run partials)
+NCU_TRAFFIC_BYTES_CACHE = 313e9
+NCU_TRAFFIC_BYTES_INTERVAL = 2.79e9
 
 
 def parse():
@@ -53,6 +61,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--algo", default="auto", choices=["auto", "gemm"],
+                    help="auto: tree-shaped clade masks take the interval path (prefix counts, no GEMM); gemm: force the tcgen05 GEMM")
+    ap.add_argument("--no-gemm-leg", action="store_true", help="skip the extra GEMM-path measurement of the same workload")
     ap.add_argument("--replicates", type=int, default=1250,
                     help="replicate-sweep leg, replicates per GPU and step (BASELINE configs[4]: 10,000 pairs of 100 cells x 10k SNVs "
                          "over 8 GPUs = 1250 per GPU); 0 disables it")
@@ -337,6 +348,7 @@ def main():
     torch.cuda.synchronize()
     FP, FN = FP_TRUE, FN_TRUE / 2        # what get_gt_tree would pass for a CellPhy log with these rates
 
+    os.environ["SCS_PLACE_ALGO"] = args.algo
     plan = engine.Placement(ctx, n_snv, n_cols, n_rows)
     plan.set_clades_host(bits, words)
     row_keep = torch.empty(n_snv, dtype=torch.uint8, device=dev)
@@ -345,7 +357,7 @@ def main():
 
     def place_step():
         n_kept, miss = engine.gt_reduce(ctx, packed, pitch, n_snv, n_cols, active, True, row_keep)
-        plan.set_genotypes(packed, pitch, row_keep, stream=stream)
+        plan.bind_genotypes(packed, pitch, row_keep, stream=stream)     # GEMM path: builds the operand plane(s); interval path: no copy
         plan.run(FP, FN, y_dev, stream=stream)
         sharding.allreduce_soft_weights(y_dev)
         return n_kept, miss
@@ -398,7 +410,8 @@ def main():
         lrt.run(y_dev, lrt_out, stream=stream)
         return lrt_out.cpu()
 
-    def timed(fn, steps, warmup, sampler=None):
+    def timed(fn, steps, warmup, sampler=None, pl=None):
+        pl = pl or plan
         for _ in range(warmup):
             fn()
         torch.cuda.synchronize()
@@ -406,14 +419,14 @@ def main():
         torch.cuda.synchronize()
         if sampler:
             sampler.start()
-        l0 = plan.info()["launches"]
+        l0 = pl.info()["launches"]
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         gemm = []
         e0.record()
         for _ in range(steps):
             res = fn()
-            gemm.append(plan.last_times())
+            gemm.append(pl.last_times())
         e1.record()
         torch.cuda.synchronize()
         sharding.barrier()
@@ -423,7 +436,7 @@ def main():
         ms = e0.elapsed_time(e1)
         # this library's kernels inside the timed region: plan launches (operand expansion, two GEMM
         # passes, merge, reduce) + 2 per step in scs_gt_reduce + 1 LRT kernel per step
-        n_launch = plan.info()["launches"] - l0 + 3 * steps
+        n_launch = pl.info()["launches"] - l0 + 3 * steps
         return sharding.max_over_ranks(ms, dev), gemm, res, n_launch
 
     sampler = ClockSampler(local) if rank == 0 else None
@@ -442,6 +455,30 @@ def main():
                "h2d_bytes_per_step": int(packed.numel()) * world, "d2h_bytes_per_step": int(lrt_out.numel() * 8 + n_cols * 4 + 8) * world,
                "ms_per_step": ms_e2e / args.steps, "chunks": streamer.n_chunks, "max_rel_dev_vs_resident": e2e_dev}
 
+    # ---- the same workload through the tcgen05 GEMM (north_star's formulation), when the headline ran the interval path
+    gemm_leg = None
+    if plan_info["algo"] == 2 and not args.no_gemm_leg:
+        os.environ["SCS_PLACE_ALGO"] = "gemm"
+        plan_g = engine.Placement(ctx, n_snv, n_cols, n_rows)
+        plan_g.set_clades_host(bits, words)
+        os.environ["SCS_PLACE_ALGO"] = args.algo
+        y_g = torch.zeros_like(y_dev)
+        y_iv = y_dev.clone()
+
+        def step_gemm():
+            engine.gt_reduce(ctx, packed, pitch, n_snv, n_cols, active, True, row_keep)
+            plan_g.bind_genotypes(packed, pitch, row_keep, stream=stream)
+            plan_g.run(FP, FN, y_g, stream=stream)
+            sharding.allreduce_soft_weights(y_g)
+            lrt.run(y_g, lrt_out, stream=stream)
+            return lrt_out.cpu()
+
+        ms_g, g_times, _, _ = timed(step_gemm, 2, 1, pl=plan_g)
+        gemm_leg = {"ms_per_step": ms_g / 2, "value": placements / (ms_g / 2 / 1e3), "times": np.array(g_times), "info": plan_g.info(),
+                    "max_rel_dev_vs_interval": float((y_g - y_iv).abs().max() / y_iv.abs().max())}
+        plan_g.close()
+        del plan_g, y_g, y_iv
+
     rep = None
     if args.replicates > 0:
         del pinned, streamer
@@ -457,41 +494,77 @@ def main():
             fp8_yard = json.load(open(os.path.join(REPO, "profiles", "r01_fp8_yardstick.json")))["fp8_scaled_mm_8192"]["sustained_tflops"]
         except Exception:
             pass
-        cached = plan_info.get("pass2_mode") == 2                        # pass 2 = sweep over the cached integer counts, not a GEMM
-        t_gemm = float(np.mean(g[:, 0] if cached else np.concatenate([g[:, 0], g[:, 2]])))   # average launch of the dominant kernel
-        flop = 2.0 * n_snv * n_rows * n_cols                             # algorithmic: SNV x cells x clade rows, 2 flop per MAC
-        achieved = flop / (t_gemm / 1e3) / 1e12
         peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
+        full_size = n_cells == 10000 and n_snv == 1000000
+
+        def gemm_roofline(g, info):
+            cached = info.get("pass2_mode") == 2                             # pass 2 = sweep over the cached integer counts, not a GEMM
+            t_gemm = float(np.mean(g[:, 0] if cached else np.concatenate([g[:, 0], g[:, 2]])))   # average launch of the dominant kernel
+            flop = 2.0 * n_snv * n_rows * n_cols                             # algorithmic: SNV x cells x clade rows, 2 flop per MAC
+            achieved = flop / (t_gemm / 1e3) / 1e12
+            return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "traffic": (NCU_TRAFFIC_BYTES_CACHE if cached else NCU_TRAFFIC_BYTES) if (full_size and info["mode"] == 1) else None,
+                    "peak_source": pk_kind + " cuBLAS bf16, sustained (kernel timed inside a long step)",
+                    "kernel": "scs_place_kernel (%s), %s" % (
+                        "tcgen05 kind::f8f6f4, one radix-packed e5m2 plane" if info["mode"] == 1 else "tcgen05 kind::i8, two u8 planes",
+                        "pass 1 launches (pass 2 sweeps the cached integer counts: HBM bound, see pass2_*)" if cached else "avg of pass 1 and pass 2 launches"),
+                    "peak_8bit_equiv": 2 * peak, "frac_8bit_equiv": achieved / (2 * peak),
+                    "fp8_cublaslt_sustained_tflops": fp8_yard, "frac_vs_fp8_cublaslt_sustained": (achieved / fp8_yard) if fp8_yard else None,
+                    "why_frac_exceeds_1": "MEASURED_PEAKS.json holds a bf16 figure only; this GEMM runs 8-bit operands (FP8 e5m2 / u8), whose tensor rate is twice bf16: against 2 x the measured bf16 rate the kernel sits at frac_8bit_equiv",
+                    "algorithmic_flop_per_launch": flop, "ms_per_launch": t_gemm,
+                    "pass1_ms": float(g[:, 0].mean()), "merge_ms": float(g[:, 1].mean()), "pass2_ms": float(g[:, 2].mean()),
+                    "reduce_ms": float(g[:, 3].mean()),
+                    "pass2_kind": "count-cache sweep (scs_colsum_cached_kernel)" if cached else "second GEMM pass",
+                    "pass2_hbm_GBps": (4.0 * info["M_pad"] * n_rows / 1e9 / (float(g[:, 2].mean()) / 1e3)) if cached else None,
+                    "count_cache_GB": (4.0 * info["M_pad"] * info["N_pad"] / 1e9) if cached else 0.0,
+                    "executed_tensor_TOPs": achieved * (1 if info["mode"] == 1 else 2),
+                    "note": "radix mode: one exact FP8 GEMM per contraction (counts packed as C1 + 4096*C0); planes mode: two exact u8 GEMMs"}
+
+        if plan_info["algo"] == 2:
+            # interval path: the packed 2-bit genotypes are read once (2 bits per (SNV, cell)); nothing else touches HBM but
+            # the per-run partial sums.  The kernel is bound by instruction issue, not by HBM or the tensor pipe -- of the
+            # two rooflines the contract names, HBM is the one its only off-chip traffic belongs to.
+            t_k = float(g[:, 0].mean())
+            alg_bytes = float(n_snv) * pitch
+            hbm_peak = pk.get("hbm_gbs_sustained", pk.get("hbm_gbs"))
+            roofline = {"bound": "hbm", "achieved": alg_bytes / 1e9 / (t_k / 1e3), "peak": hbm_peak, "unit": "GB/s",
+                        "frac": alg_bytes / 1e9 / (t_k / 1e3) / hbm_peak,
+                        "traffic": NCU_TRAFFIC_BYTES_INTERVAL if full_size else None,
+                        "peak_source": pk_kind + " HBM copy bandwidth",
+                        "kernel": "scs_place_interval%s_kernel (prefix counts in shared memory, no GEMM)" % ("3" if plan_info["interval_variant"] == 3 else ""),
+                        "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": t_k, "reduce_ms": float(g[:, 3].mean()),
+                        "entries_per_s": float(n_snv) * n_rows / (t_k / 1e3),
+                        "actual_limiter": "instruction issue (ncu: issue slots 67 % busy, ALU pipe 52 %, 8 warps per scheduler, ~12 cycles between "
+                                          "a warp's instructions); HBM traffic is ~50 GB/s because the algorithm needs O(cells + clade rows) work "
+                                          "per SNV instead of the GEMM's O(cells x clade rows) -- see gemm_path for the tensor-pipe roofline of "
+                                          "the same workload through the tcgen05 GEMM",
+                        "smem_bytes": plan_info["interval_smem_bytes"], "threads": plan_info["interval_threads"], "grid": plan_info["interval_grid"]}
+        else:
+            roofline = gemm_roofline(g, plan_info)
+        gemm_path = None
+        if gemm_leg is not None:
+            gemm_path = {"ms_per_step": gemm_leg["ms_per_step"], "value": gemm_leg["value"], "unit": "placements/s", "steps": 2, "warmup": 1,
+                         "max_rel_dev_soft_weights_vs_interval": gemm_leg["max_rel_dev_vs_interval"],
+                         "roofline": gemm_roofline(gemm_leg["times"], gemm_leg["info"]), "tiling": gemm_leg["info"]}
         out = res.numpy()
         line = {
             "metric": METRIC, "value": value, "unit": "placements/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "fp8_e5m2 operands holding exact integer counts, f32 accumulate (epilogue f32, LRT f64)" if plan_info["mode"] == 1 else "u8 operands, s32 accumulate (epilogue f32, LRT f64)",
+            "dtype": ("u16 prefix counts (exact integers), f32 softmax terms on exact integer differences (LRT f64)" if plan_info["algo"] == 2 else
+                      "fp8_e5m2 operands holding exact integer counts, f32 accumulate (epilogue f32, LRT f64)" if plan_info["mode"] == 1 else
+                      "u8 operands, s32 accumulate (epilogue f32, LRT f64)"),
             "data": "synthetic",
             "config": {"workload": "coalescent %d cells x %d SNVs per GPU (BASELINE configs[3]), SNV rows sharded, one all-reduce of the branch weights, LRT for 10 w_max"
                                    % (n_cells, n_snv),
                        "cells": n_cells, "snvs_per_gpu": n_snv, "clade_rows": n_rows, "w_max": W_MAXS, "FN": FN_TRUE, "FP": FP_TRUE, "missing": MS_TRUE,
-                       "l2": "inputs larger than L2 (operand plane(s) %.1f GB per GPU)" % ((1 if plan_info["mode"] == 1 else 2) * float(plan_info["M_pad"]) * plan_info["K_pad"] / 1e9),
+                       "algorithm": "interval path (tree-shaped clade masks: counts = differences of per-SNV prefix counts)" if plan_info["algo"] == 2 else "tcgen05 GEMM",
+                       "l2": ("inputs larger than L2 (packed genotypes %.1f GB per GPU, read once per step)" % (float(n_snv) * pitch / 1e9)) if plan_info["algo"] == 2 else
+                             ("inputs larger than L2 (operand plane(s) %.1f GB per GPU)" % ((1 if plan_info["mode"] == 1 else 2) * float(plan_info["M_pad"]) * plan_info["K_pad"] / 1e9)),
                        "tiling": plan_info},
             "e2e": e2e,
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES if (n_cells == 10000 and n_snv == 1000000 and plan_info["mode"] == 1) else None,
-                         "peak_source": pk_kind + " cuBLAS bf16, sustained (kernel timed inside a long step)",
-                         "kernel": "scs_place_kernel (%s), %s" % (
-                             "tcgen05 kind::f8f6f4, one radix-packed e5m2 plane" if plan_info["mode"] == 1 else "tcgen05 kind::i8, two u8 planes",
-                             "pass 1 launches (pass 2 sweeps the cached integer counts: HBM bound, see pass2_*)" if cached else "avg of pass 1 and pass 2 launches"),
-                         "peak_8bit_equiv": 2 * peak, "frac_8bit_equiv": achieved / (2 * peak),
-                         "fp8_cublaslt_sustained_tflops": fp8_yard, "frac_vs_fp8_cublaslt_sustained": (achieved / fp8_yard) if fp8_yard else None,
-                         "why_frac_exceeds_1": "MEASURED_PEAKS.json holds a bf16 figure only; this GEMM runs 8-bit operands (FP8 e5m2 / u8), whose tensor rate is twice bf16: against 2 x the measured bf16 rate the kernel sits at frac_8bit_equiv",
-                         "algorithmic_flop_per_launch": flop, "ms_per_launch": t_gemm,
-                         "pass1_ms": float(g[:, 0].mean()), "merge_ms": float(g[:, 1].mean()), "pass2_ms": float(g[:, 2].mean()),
-                         "reduce_ms": float(g[:, 3].mean()),
-                         "pass2_kind": "count-cache sweep (scs_colsum_cached_kernel)" if cached else "second GEMM pass",
-                         "pass2_hbm_GBps": (4.0 * plan_info["M_pad"] * n_rows / 1e9 / (float(g[:, 2].mean()) / 1e3)) if cached else None,
-                         "count_cache_GB": (4.0 * plan_info["M_pad"] * plan_info["N_pad"] / 1e9) if cached else 0.0,
-                         "executed_tensor_TOPs": achieved * (1 if plan_info["mode"] == 1 else 2),
-                         "note": "radix mode: one exact FP8 GEMM per contraction (counts packed as C1 + 4096*C0); planes mode: two exact u8 GEMMs"},
+            "roofline": roofline,
+            "gemm_path": gemm_path,
             "pt_tests": {"per_step": len(W_MAXS), "LR": [float(v) for v in out[:, 0]], "p_value": [float(v) for v in out[:, 3]],
                          "newton_iterations": [int(v) for v in out[:, 6]], "status": [int(v) for v in out[:, 7]]},
             "clocks": sampler.summary() if sampler else None,
