@@ -1311,6 +1311,11 @@ struct Placement {
     uint32_t* d_lohi = nullptr;
     int* d_slot_row = nullptr;     // clade row of every accumulator slot (-1: none)
     uint4* d_off4 = nullptr;       // variant 3: byte offsets into the prefix counts, per pair of rows
+    uint32_t* d_leafmask = nullptr;   // variant 3: positions that have a leaf row, per word of a permuted genotype row
+    uint32_t* gt_perm = nullptr;   // variant 3: the genotype rows in depth-first cell order [n_snv][ceil(n_cells/16)]
+    size_t gt_perm_bytes = 0;
+    bool gt_perm_valid = false;
+    int iv_leaf_off = 0;
     int iv_slots = 0, iv_variant = 0, iv_nodes = 0, iv_leaf_pos = 0, iv_stride = 0, iv_entries = 0;
     float* ipart = nullptr;
     size_t ipart_bytes = 0;
@@ -1549,6 +1554,8 @@ int scs_placement_destroy(scs_placement* h) {
     cudaFree(pl->d_lohi);
     cudaFree(pl->d_slot_row);
     cudaFree(pl->d_off4);
+    cudaFree(pl->d_leafmask);
+    cudaFree(pl->gt_perm);
     cudaFree(pl->ipart);
     cudaFree(pl->colpart);
     cudaFree(pl->y);
@@ -1593,6 +1600,7 @@ static int set_genotypes_impl(Placement* pl, const uint8_t* d_gt, int64_t pitch_
     if (pitch_bytes < (pl->n_cells + 3) / 4) return set_error(SCS_ERR_ARG, "genotype row pitch %lld is smaller than ceil(n_cells/4)", (long long)pitch_bytes);
     if ((pitch_bytes & 3) || (reinterpret_cast<uintptr_t>(d_gt) & 3)) return set_error(SCS_ERR_ARG, "packed genotype rows must be 4-byte aligned (pitch %lld)", (long long)pitch_bytes);
     pl->operands_valid = false;
+    pl->gt_perm_valid = false;
     pl->gt_src = nullptr;
     // GEMM path (or clades not seen yet): the operand plane(s)
     if (pl->algo != 2) {
@@ -1662,6 +1670,7 @@ int scs_placement_bind_genotypes(scs_placement* h, const uint8_t* d_gt, int64_t 
 // interval | auto overrides ("interval" still falls back when the masks are not laminar).
 static int choose_algo(Placement* pl, const uint32_t* bits, int64_t pitch_words, cudaStream_t st) {
     pl->algo = 1;
+    pl->gt_perm_valid = false;      // (the cell order may change with the masks)
     const char* e = getenv("SCS_PLACE_ALGO");
     if (e && !strcmp(e, "gemm")) return SCS_OK;
     if (pl->n_groups != 1) return SCS_OK;
@@ -1672,7 +1681,6 @@ static int choose_algo(Placement* pl, const uint32_t* bits, int64_t pitch_words,
     std::vector<uint32_t> lohi;
     if (!clade_intervals(bits, pitch_words, pl->n_rows, pl->n_cells, perm, lohi)) return SCS_OK;
     const int n_cells = pl->n_cells, n_rows = pl->n_rows;
-    const int n_cells_even = (n_cells + 1) & ~1;
     int threads = n_rows >= 4096 ? 1024 : (n_rows >= 1024 ? 512 : 256);
     if (const char* t = getenv("SCS_IV_THREADS")) threads = std::max(32, std::min(1024, atoi(t) / 32 * 32));
 
@@ -1691,10 +1699,9 @@ static int choose_algo(Placement* pl, const uint32_t* bits, int64_t pitch_words,
     };
     std::stable_sort(general.begin(), general.end(), by_interval);
     const int n_gen = int(general.size()), n_slots3 = (n_gen + 1) & ~1;
-    int threads3 = threads;
-    while (threads3 < 1024 && (((n_cells + threads3 - 1) / threads3) | 1) > 15) threads3 *= 2;
-    const bool v3 = n_cells < 32768 && interval3_smem_bytes(n_cells, n_slots3) <= SMEM_MAX && (((n_cells + threads3 - 1) / threads3) | 1) <= 15 &&
-                    !(e && !strcmp(e, "interval1"));
+    const int rw = (n_cells + 15) / 16;                     // 32-bit words of a permuted row: one thread each
+    const int threads3 = std::max(threads, (rw + 31) / 32 * 32);
+    const bool v3 = threads3 <= 1024 && interval3_smem_bytes(n_cells, n_slots3) <= SMEM_MAX && !(e && !strcmp(e, "interval1"));
     std::vector<int> slot_row;
     size_t smem = 0;
     int per_sm = 1;
@@ -1713,24 +1720,32 @@ static int choose_algo(Placement* pl, const uint32_t* bits, int64_t pitch_words,
             }
         }
         int n_leaf_pos = 0;
+        std::vector<uint32_t> leafmask(size_t(rw), 0u);
         for (int k = 0; k < n_cells; ++k)
             if (leaf_row_of_pos[size_t(k)] >= 0) {
-                perm[size_t(k)] |= 0x8000u;
+                leafmask[size_t(k >> 4)] |= 1u << (2 * (k & 15));
                 ++n_leaf_pos;
             }
-        slot_row.assign(size_t(n_slots3 + n_cells_even), -1);
+        const int leaf_off = (n_slots3 + 3) & ~3;           // the leaf section of a partial row starts 16-byte aligned
+        slot_row.assign(size_t(leaf_off + 16 * rw), -1);
         for (int sidx = 0; sidx < n_gen; ++sidx) slot_row[size_t(sidx)] = general[size_t(sidx)];
-        for (int k = 0; k < n_cells; ++k) slot_row[size_t(n_slots3 + k)] = leaf_row_of_pos[size_t(k)];
+        for (int k = 0; k < n_cells; ++k) slot_row[size_t(leaf_off + k)] = leaf_row_of_pos[size_t(k)];
         cudaFree(pl->d_off4);
+        cudaFree(pl->d_leafmask);
         pl->d_off4 = nullptr;
-        if (cudaMalloc(&pl->d_off4, std::max<size_t>(1, off4.size()) * sizeof(uint4)) != cudaSuccess) return set_error(SCS_ERR_OOM, "device allocation failed");
+        pl->d_leafmask = nullptr;
+        if (cudaMalloc(&pl->d_off4, std::max<size_t>(1, off4.size()) * sizeof(uint4)) != cudaSuccess ||
+            cudaMalloc(&pl->d_leafmask, size_t(rw) * sizeof(uint32_t)) != cudaSuccess)
+            return set_error(SCS_ERR_OOM, "device allocation failed");
         SCS_CUDA(cudaMemcpyAsync(pl->d_off4, off4.data(), off4.size() * sizeof(uint4), cudaMemcpyHostToDevice, st));
+        SCS_CUDA(cudaMemcpyAsync(pl->d_leafmask, leafmask.data(), leafmask.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         SCS_CUDA(cudaStreamSynchronize(st));
         pl->iv_variant = 3;
         pl->iv_nodes = n_gen;
         pl->iv_slots = n_slots3;
         pl->iv_leaf_pos = n_leaf_pos;
-        pl->iv_stride = n_slots3 + n_cells_even;
+        pl->iv_stride = leaf_off + 16 * rw;
+        pl->iv_leaf_off = leaf_off;
         smem = interval3_smem_bytes(n_cells, n_slots3);
         cudaFuncSetAttribute(scs_place_interval3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scs_place_interval3_kernel, threads, smem);
@@ -1940,11 +1955,33 @@ int scs_placement_run_batch(scs_placement* h, const double* FP, const double* FN
         double* y = d_soft_weights ? d_soft_weights : pl->y;
         cudaEventRecord(pl->ev[0], st);
         if (pl->iv_variant == 3) {
+            const int rw = ip.row_words;
+            if (!pl->gt_perm_valid) {
+                // the rows in depth-first cell order (one streaming pass; the walk below then works on whole words)
+                const size_t bytes = size_t(pl->n_snv) * rw * sizeof(uint32_t);
+                if (bytes > pl->gt_perm_bytes) {
+                    cudaFree(pl->gt_perm);
+                    pl->gt_perm = nullptr;
+                    pl->gt_perm_bytes = 0;
+                    if (cudaMalloc(&pl->gt_perm, bytes) != cudaSuccess) return set_error(SCS_ERR_OOM, "device allocation of %zu bytes failed", bytes);
+                    pl->gt_perm_bytes = bytes;
+                }
+                const int pt = (rw + 31) / 32 * 32;
+                const unsigned pgrid = unsigned(std::min<int64_t>(pl->n_snv, int64_t(pl->ctx->sm_count) * std::max(1, 2048 / pt)));
+                scs_permute_cells_kernel<<<pgrid, pt, 2 * rw * sizeof(uint32_t), st>>>(pl->gt_src, pl->gt_pitch, pl->n_snv, pl->n_cells, rw, pl->d_perm,
+                                                                                   pl->gt_perm);
+                pl->gt_perm_valid = true;
+                pl->launches++;
+            }
             Interval3Params q;
+            ip.gt = reinterpret_cast<const uint8_t*>(pl->gt_perm);
+            ip.pitch = int64_t(rw) * 4;
             q.b = ip;
+            q.leafmask = pl->d_leafmask;
             q.off4 = pl->d_off4;
             q.n_leaf_pos = pl->iv_leaf_pos;
             q.part_stride = pl->iv_stride;
+            q.leaf_off = pl->iv_leaf_off;
             scs_place_interval3_kernel<<<pl->iv_grid, pl->iv_threads, pl->iv_smem, st>>>(q);
         } else {
             scs_place_interval_kernel<false><<<pl->iv_grid, pl->iv_threads, pl->iv_smem, st>>>(ip);

@@ -236,27 +236,31 @@ __global__ void __launch_bounds__(1024, 1) scs_place_interval_kernel(const Inter
     }
 }
 
-// ---- the main variant: per-row count cache in shared memory (whenever it fits: up to ~14,000 cells with
-// all 2n clade rows), packed fp32x2 arithmetic, and the single-cell rows (the leaves: half of a tree's
-// clade rows) taken out of the sweeps:
-//   * a leaf's counts are its cell's genotype, so a row has only THREE distinct leaf terms (mutated /
-//     wild type / missing).  They are evaluated once per SNV; their share of the row sum is
-//     n_mut t_mut + n_wt t_wt + n_miss t_miss from the leaf totals, and each leaf's accumulator gets
-//     its term from the 2-bit codes the scan kept in a register -- ~10 instructions per (SNV, leaf);
+// ---- the main variant (trees up to ~14,000 cells): the genotype rows are first rewritten in depth-first
+// cell order (scs_permute_cells_kernel, one streaming pass), so that a thread owns one 32-bit word = 16
+// consecutive positions and all per-position work is bit arithmetic on two masks (mutated / wild type):
+//   * prefix counts: block scan over the words' popcounts, then 16 unrolled adds and four 16-byte stores
+//     per thread (~4 instructions per position, against ~30 for gathering through the cell order);
+//   * single-cell rows (the leaves: half of a tree's clade rows) stay out of the sweeps.  A leaf's counts
+//     are its cell's genotype, so a row has only THREE distinct leaf terms (mutated / wild type /
+//     missing): they are evaluated once per SNV, their share of the row sum is n_mut t_mut + n_wt t_wt +
+//     n_miss t_miss from the leaf totals (popcounts under the leaf mask), and each leaf's accumulator
+//     gets its term by two selects on the mask bits (~6 instructions per (SNV, leaf));
 //   * the other rows (internal nodes, empty rows, duplicates), sorted by (lo, hi), go through three
-//     sweeps over PAIRS of rows:
+//     sweeps over PAIRS of rows in packed fp32x2 arithmetic:
 //       sweep 1  counts d = P[hi] - P[lo] -> cache; best column of the row by rank value (no exponentials)
 //       sweep 2  t = 2^(logit - logit_best) from exact integer differences -> cache (in place); row sum
 //       sweep 3  accumulators += t / sum
-//     ~55 instructions per (SNV, row), one ex2.
-// Tables: perm[k] = column of depth-first position k, bit 15 set when the position has a leaf row
-// (n_cells < 32768 here); off4[pair] = byte offsets into P (lo0, hi0, lo1, hi1) * 4.
+// off4[pair] = byte offsets into P (lo0, hi0, lo1, hi1) * 4; leafmask[w] has bit 2e set when position
+// 16w + e has a leaf row.
 struct Interval3Params {
-    IntervalParams b;          // n_nodes / n_slots / lohi describe the NON-leaf rows here; part rows hold
-                               // [n_slots non-leaf accumulators][n_cells_even leaf accumulators by position]
+    IntervalParams b;          // gt = the permuted matrix [n_snv][row_words] (pitch = 4 row_words); n_nodes / n_slots describe
+                               // the NON-leaf rows; part rows hold [n_slots non-leaf accumulators, padded to leaf_off][16 row_words leaf accumulators]
     const uint4* off4;         // [n_slots / 2]
+    const uint32_t* leafmask;  // [row_words]
     int n_leaf_pos;            // positions that have a leaf row
-    int part_stride;           // n_slots + n_cells rounded up to even
+    int part_stride;           // leaf_off + 16 row_words
+    int leaf_off;              // n_slots rounded up to a multiple of 4 (16-byte aligned leaf section)
 };
 
 __device__ __forceinline__ float2 iv_lo16(uint32_t a, uint32_t b) {      // (2^23 + low half of a, 2^23 + low half of b)
@@ -271,30 +275,63 @@ __device__ __forceinline__ uint32_t iv_lds_off(const uint32_t* base, uint32_t by
 
 constexpr int IV3_SCRATCH_WORDS = 6 * 32;
 
+// P[0] sits at word 3 so that P[16 w + 1], the first of a thread's sixteen prefix counts, is 16-byte aligned
+__host__ __device__ inline int iv3_p_words(int row_words) { return 4 + 16 * row_words; }
+
 static inline size_t interval3_smem_bytes(int n_cells, int n_slots) {
-    // P | non-leaf accumulators | count / term cache | leaf accumulators | two row buffers | scratch | perm
-    return 4 * (size_t(iv_p_words(n_cells)) + 2 * size_t(n_slots) + (size_t(n_cells + 1) & ~size_t(1)) + 2 * size_t((n_cells + 15) / 16) +
-                IV3_SCRATCH_WORDS + size_t((n_cells + 1) / 2));
+    const size_t rw = size_t((n_cells + 15) / 16);
+    // P | non-leaf accumulators | count / term cache | leaf accumulators | scratch
+    return 4 * (size_t(iv3_p_words(int(rw))) + 2 * size_t(n_slots) + 16 * rw + IV3_SCRATCH_WORDS);
+}
+
+// Rows rewritten in depth-first cell order: out[r][k] = code of cell perm[k] (positions beyond n_cells: 3 = missing).
+// One CTA per row at a time, thread = one output word; its sixteen source columns stay in registers.
+__global__ void scs_permute_cells_kernel(const uint8_t* __restrict__ gt, long long pitch, long long n_snv, int n_cells, int row_words,
+                                         const uint16_t* __restrict__ perm, uint32_t* __restrict__ out) {
+    extern __shared__ uint32_t pm_smem[];          // two row buffers
+    const int t = threadIdx.x;
+    uint32_t cols[8];
+#pragma unroll
+    for (int e = 0; e < 16; e += 2) {
+        const int k = 16 * t + e;
+        const uint32_t c0 = (t < row_words && k < n_cells) ? perm[k] : 0xFFFFu, c1 = (t < row_words && k + 1 < n_cells) ? perm[k + 1] : 0xFFFFu;
+        cols[e >> 1] = c0 | (c1 << 16);
+    }
+    int buf = 0;
+    for (long long r = blockIdx.x; r < n_snv; r += gridDim.x, buf ^= 1) {
+        uint32_t* rb = pm_smem + buf * row_words;
+        if (t < row_words) rb[t] = reinterpret_cast<const uint32_t*>(gt + size_t(r) * pitch)[t];
+        __syncthreads();           // (two buffers: the previous row's readers are at most one barrier behind)
+        if (t < row_words) {
+            const uint8_t* rb8 = reinterpret_cast<const uint8_t*>(rb);
+            uint32_t w = 0u;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const uint32_t col = (cols[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu;
+                const uint32_t code = col == 0xFFFFu ? 3u : ((uint32_t(rb8[col >> 2]) >> ((col & 3) * 2)) & 3u);
+                w |= code << (2 * e);
+            }
+            out[size_t(r) * row_words + t] = w;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(1024, 1) scs_place_interval3_kernel(const Interval3Params q) {
     const IntervalParams& p = q.b;
     extern __shared__ uint32_t iv_smem[];
     const int T = blockDim.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarp = T >> 5;
-    const int n_cells_even = (p.n_cells + 1) & ~1;
-    uint32_t* P = iv_smem;
-    float2* acc2 = reinterpret_cast<float2*>(P + iv_p_words(p.n_cells));           // 16-byte aligned: iv_p_words is a multiple of 4
+    const int rw = p.row_words;                    // <= T (host)
+    uint32_t* P = iv_smem + 3;
+    float2* acc2 = reinterpret_cast<float2*>(iv_smem + iv3_p_words(rw));           // 16-byte aligned
     uint2* dc2 = reinterpret_cast<uint2*>(reinterpret_cast<float*>(acc2) + p.n_slots);
-    float* accL = reinterpret_cast<float*>(reinterpret_cast<uint32_t*>(dc2) + p.n_slots);
-    uint32_t* rowbuf = reinterpret_cast<uint32_t*>(accL + n_cells_even);
-    uint32_t* scr = rowbuf + 2 * p.row_words;      // [0,32) scan totals, [32,64) rank values, [64,96) their counts, [128,160) sums, [160,192) leaf totals
-    uint16_t* perm = reinterpret_cast<uint16_t*>(scr + IV3_SCRATCH_WORDS);
+    float4* accL4 = reinterpret_cast<float4*>(reinterpret_cast<uint32_t*>(dc2) + p.n_slots);   // n_slots even: 8-byte aligned ...
+    uint32_t* scr = reinterpret_cast<uint32_t*>(accL4) + 16 * rw;      // [0,32) scan totals, [32,64) rank values, [64,96) their counts, [128,160) sums, [160,192) leaf totals
     const GroupConst gc = p.gconst[0];
-    const int E = ((p.n_cells + T - 1) / T) | 1;   // <= 15 (host): the 2-bit codes of a thread's positions fit one register
-    const int k0 = min(t * E, p.n_cells), k1 = min(k0 + E, p.n_cells);
+    const bool own = t < rw;                       // this thread owns word t = positions 16 t .. 16 t + 15
     const int n_pairs = p.n_slots >> 1;
     const int j_pad = (p.n_nodes & 1) ? n_pairs - 1 : -1;         // the pair whose second slot is padding
-    for (int k = t; k < p.n_cells; k += T) perm[k] = p.perm[k];   // (visible after the first barrier of the row loop)
+    const uint32_t lmask = own ? q.leafmask[t] : 0u;
+    const uint32_t* gw = reinterpret_cast<const uint32_t*>(p.gt);
     const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
     const uint4 of_first0 = t < n_pairs ? q.off4[t] : zero4, of_first1 = t + T < n_pairs ? q.off4[t + T] : zero4;
     const float2 a1f2 = make_float2(gc.a1f, gc.a1f), a0f2 = make_float2(gc.a0f, gc.a0f);
@@ -304,40 +341,28 @@ __global__ void __launch_bounds__(1024, 1) scs_place_interval3_kernel(const Inte
 
     for (int run = blockIdx.x; run < p.num_runs; run += gridDim.x) {
         for (int j = t; j < n_pairs; j += T) acc2[j] = make_float2(0.f, 0.f);
-        for (int k = k0; k < k1; ++k) accL[k] = 0.f;
+        if (own) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) accL4[4 * t + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         const long long r0 = (long long)run * p.rows_per_run;
         const long long r1 = r0 + p.rows_per_run < p.n_snv ? r0 + p.rows_per_run : p.n_snv;
-        int buf = 0;
-        iv_issue_row(p, r0, rowbuf, t, T);
+        // the row's word and its keep flag are fetched one row ahead, straight into registers
+        uint32_t w_next = own ? gw[size_t(r0) * rw + t] : 0xFFFFFFFFu;
         uint32_t keep_next = p.row_keep != nullptr ? p.row_keep[r0] : 1u;
-        for (long long r = r0; r < r1; ++r, buf ^= 1) {
-            asm volatile("cp.async.wait_all;\n" ::: "memory");
-            __syncthreads();
-            const uint32_t keep = keep_next;
+        for (long long r = r0; r < r1; ++r) {
+            const uint32_t w = w_next, keep = keep_next;
             if (r + 1 < r1) {
-                iv_issue_row(p, r + 1, rowbuf + (buf ^ 1) * p.row_words, t, T);
+                if (own) w_next = gw[size_t(r + 1) * rw + t];
                 if (p.row_keep != nullptr) keep_next = p.row_keep[r + 1];
             }
-            if (keep == 0u) continue;
+            if (keep == 0u) continue;              // (uniform over the block)
 
-            // ---- prefix counts in depth-first order; the thread keeps its positions' codes (0 wild type, 1 mutated,
-            // 3 missing or no leaf row) and the totals over positions that have a leaf row
-            const uint8_t* rb8 = reinterpret_cast<const uint8_t*>(rowbuf + buf * p.row_words);
-            uint32_t run_sum = 0u, leaf_sum = 0u, codes = 0u;
-            for (int k = k0; k < k1; ++k) {
-                const uint32_t pc = perm[k];
-                const uint32_t col = pc & 0x7FFFu;
-                const uint32_t code = (uint32_t(rb8[col >> 2]) >> ((col & 3) * 2)) & 3u;
-                const uint32_t inc = code == 3u ? 0u : (code == 0u ? 0x10000u : 1u);
-                run_sum += inc;
-                P[k + 1] = run_sum;
-                const bool leaf = (pc & 0x8000u) != 0u;
-                leaf_sum += leaf ? inc : 0u;
-                // per-leaf selector: 0 wild type, 1 mutated, 2 missing, 3 no leaf row at this position
-                const uint32_t sel = leaf ? (code == 3u ? 2u : (code == 0u ? 0u : 1u)) : 3u;
-                codes |= sel << (2 * (k - k0));
-            }
-            uint32_t incl = run_sum;
+            // ---- prefix counts: mutated = exactly one bit of the code set (1 het, 2 hom), wild type = none, 3 = missing
+            const uint32_t mm = (w ^ (w >> 1)) & 0x55555555u, wm = ~(w | (w >> 1)) & 0x55555555u;
+            const uint32_t tot = uint32_t(__popc(mm)) | (uint32_t(__popc(wm)) << 16);
+            uint32_t leaf_sum = uint32_t(__popc(mm & lmask)) | (uint32_t(__popc(wm & lmask)) << 16);
+            uint32_t incl = tot;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -345,6 +370,8 @@ __global__ void __launch_bounds__(1024, 1) scs_place_interval3_kernel(const Inte
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) leaf_sum += __shfl_xor_sync(0xffffffffu, leaf_sum, o);
+            // (no barrier needed here: whoever gets this far has passed the previous row's last barrier, which
+            // every thread reaches only after its last read of P, the cache and the scratch words written below)
             if (lane == 31) {
                 scr[warp] = incl;
                 scr[160 + warp] = leaf_sum;
@@ -359,8 +386,19 @@ __global__ void __launch_bounds__(1024, 1) scs_place_interval3_kernel(const Inte
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) ltot += __shfl_xor_sync(0xffffffffu, ltot, o);
-            const uint32_t base = __shfl_sync(0xffffffffu, winc - wt, warp) + incl - run_sum;
-            for (int k = k0; k < k1; ++k) P[k + 1] += base;
+            const uint32_t wbase = __shfl_sync(0xffffffffu, winc - wt, warp);                   // prefix before this warp
+            if (own) {
+                uint32_t run_sum = wbase + incl - tot;                                          // prefix before this word
+                uint32_t pv[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    run_sum += ((mm >> (2 * e)) & 1u) + (((wm >> (2 * e)) & 1u) << 16);
+                    pv[e] = run_sum;
+                }
+                uint4* dst = reinterpret_cast<uint4*>(P + 16 * t + 1);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dst[i] = make_uint4(pv[4 * i], pv[4 * i + 1], pv[4 * i + 2], pv[4 * i + 3]);
+            }
             if (t == 0) P[0] = 0u;
             __syncthreads();
             const float n_mut = float(ltot & 0xFFFFu), n_wt = float(ltot >> 16), n_miss = float(q.n_leaf_pos) - n_mut - n_wt;
@@ -471,18 +509,28 @@ __global__ void __launch_bounds__(1024, 1) scs_place_interval3_kernel(const Inte
                 const uint2 tb = dc2[j];
                 acc2[j] = __ffma2_rn(make_float2(__uint_as_float(tb.x), __uint_as_float(tb.y)), inv2, acc2[j]);
             }
-            const float w_wt = t_leaf[0] * inv, w_mut = t_leaf[1] * inv, w_miss = t_leaf[2] * inv;
-            uint32_t cc = codes;
-            for (int k = k0; k < k1; ++k, cc >>= 2) {
-                const uint32_t sel = cc & 3u;
-                const float w = sel == 0u ? w_wt : (sel == 1u ? w_mut : (sel == 2u ? w_miss : 0.f));
-                accL[k] += w;
+            if (own) {
+                // leaves: the term by the position's code (positions without a leaf row collect numbers nobody reads)
+                const float w_wt = t_leaf[0] * inv, w_mut = t_leaf[1] * inv, w_miss = t_leaf[2] * inv;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float4 a = accL4[4 * t + i];
+                    float* av = reinterpret_cast<float*>(&a);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int e = 4 * i + k;
+                        av[k] += ((mm >> (2 * e)) & 1u) ? w_mut : (((wm >> (2 * e)) & 1u) ? w_wt : w_miss);
+                    }
+                    accL4[4 * t + i] = a;
+                }
             }
         }
-        asm volatile("cp.async.wait_all;\n" ::: "memory");
         float* out = p.part + size_t(run) * q.part_stride;
         for (int j = t; j < n_pairs; j += T) reinterpret_cast<float2*>(out)[j] = acc2[j];
-        for (int k = k0; k < k1; ++k) out[p.n_slots + k] = accL[k];
+        if (own) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(out + q.leaf_off)[4 * t + i] = accL4[4 * t + i];
+        }
     }
 }
 
