@@ -298,9 +298,14 @@ __global__ void scs_permute_cells_kernel(const uint8_t* __restrict__ gt, long lo
         cols[e >> 1] = c0 | (c1 << 16);
     }
     int buf = 0;
+    // the next row's word is fetched while this row is gathered (nothing between a global load and its use but work)
+    uint32_t w_next = (t < row_words && blockIdx.x < n_snv) ? reinterpret_cast<const uint32_t*>(gt + size_t(blockIdx.x) * pitch)[t] : 0u;
     for (long long r = blockIdx.x; r < n_snv; r += gridDim.x, buf ^= 1) {
         uint32_t* rb = pm_smem + buf * row_words;
-        if (t < row_words) rb[t] = reinterpret_cast<const uint32_t*>(gt + size_t(r) * pitch)[t];
+        if (t < row_words) {
+            rb[t] = w_next;
+            if (r + gridDim.x < n_snv) w_next = reinterpret_cast<const uint32_t*>(gt + size_t(r + gridDim.x) * pitch)[t];
+        }
         __syncthreads();           // (two buffers: the previous row's readers are at most one barrier behind)
         if (t < row_words) {
             const uint8_t* rb8 = reinterpret_cast<const uint8_t*>(rb);
