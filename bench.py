@@ -61,6 +61,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="SNV-row chunks of the host-buffer (e2e) leg")
     ap.add_argument("--algo", default="auto", choices=["auto", "gemm"],
                     help="auto: tree-shaped clade masks take the interval path (prefix counts, no GEMM); gemm: force the tcgen05 GEMM")
     ap.add_argument("--no-gemm-leg", action="store_true", help="skip the extra GEMM-path measurement of the same workload")
@@ -407,7 +408,7 @@ def main():
         torch.cuda.synchronize()
         # host-buffer path: the packed matrix is streamed from pinned host memory in SNV-row chunks
         # (H2D of chunk c+1 under the GEMMs of chunk c), see engine.StreamingPlacement
-        streamer = engine.StreamingPlacement(ctx, n_snv, n_cols, n_rows, n_chunks=8)
+        streamer = engine.StreamingPlacement(ctx, n_snv, n_cols, n_rows, n_chunks=args.e2e_chunks)
         streamer.set_clades_host(bits, words)
 
     def step_e2e():
