@@ -1752,8 +1752,13 @@ static int choose_algo(Placement* pl, const uint32_t* bits, int64_t pitch_words,
         pl->iv_stride = leaf_off + 16 * rw;
         pl->iv_leaf_off = leaf_off;
         smem = interval3_smem_bytes(n_cells, n_slots3);
-        cudaFuncSetAttribute(scs_place_interval3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scs_place_interval3_kernel, threads, smem);
+        if (threads <= 640) {
+            cudaFuncSetAttribute(scs_place_interval3_kernel<640, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scs_place_interval3_kernel<640, 2>, threads, smem);
+        } else {
+            cudaFuncSetAttribute(scs_place_interval3_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scs_place_interval3_kernel<1024, 1>, threads, smem);
+        }
     } else {
         // ---- variant 1: every row through the sweeps, counts recomputed in the second sweep
         std::vector<int> all(size_t(n_rows), 0);
@@ -1987,7 +1992,8 @@ int scs_placement_run_batch(scs_placement* h, const double* FP, const double* FN
             q.n_leaf_pos = pl->iv_leaf_pos;
             q.part_stride = pl->iv_stride;
             q.leaf_off = pl->iv_leaf_off;
-            scs_place_interval3_kernel<<<pl->iv_grid, pl->iv_threads, pl->iv_smem, st>>>(q);
+            if (pl->iv_threads <= 640) scs_place_interval3_kernel<640, 2><<<pl->iv_grid, pl->iv_threads, pl->iv_smem, st>>>(q);
+            else scs_place_interval3_kernel<1024, 1><<<pl->iv_grid, pl->iv_threads, pl->iv_smem, st>>>(q);
         } else {
             scs_place_interval_kernel<false><<<pl->iv_grid, pl->iv_threads, pl->iv_smem, st>>>(ip);
         }

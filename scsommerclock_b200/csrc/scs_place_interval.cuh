@@ -321,7 +321,11 @@ __global__ void scs_permute_cells_kernel(const uint8_t* __restrict__ gt, long lo
     }
 }
 
-__global__ void __launch_bounds__(1024, 1) scs_place_interval3_kernel(const Interval3Params q) {
+// MAXT: largest CTA this instantiation is launched with (register budget); UNR: unroll factor of the three sweeps.
+// At 10k cells the CTA has 640 threads (one per word): 96 registers per thread are available, and two pairs of rows in
+// flight per thread hide more of the shared-memory / ex2 latency that bounds the sweeps.
+template <int MAXT, int UNR>
+__global__ void __launch_bounds__(MAXT, 1) scs_place_interval3_kernel(const Interval3Params q) {
     const IntervalParams& p = q.b;
     extern __shared__ uint32_t iv_smem[];
     const int T = blockDim.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarp = T >> 5;
@@ -413,6 +417,7 @@ __global__ void __launch_bounds__(1024, 1) scs_place_interval3_kernel(const Inte
             uint32_t bd = 0u;
             {
                 uint4 of = of_first0, of_n1 = of_first1;
+#pragma unroll(UNR)
                 for (int j = t; j < n_pairs; j += T) {
                     const uint4 of_n2 = j + 2 * T < n_pairs ? q.off4[j + 2 * T] : zero4;
                     const uint32_t d0 = iv_lds_off(P, of.y) - iv_lds_off(P, of.x);      // both counts at once (no borrow: P is monotone in each half)
@@ -487,6 +492,7 @@ __global__ void __launch_bounds__(1024, 1) scs_place_interval3_kernel(const Inte
 
             // ---- sweep 2: terms relative to the best column, in place; row sum
             float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll(UNR)
             for (int j = t; j < n_pairs; j += T) {
                 const uint2 d = dc2[j];
                 const float2 e1 = __fadd2_rn(iv_lo16(d.x, d.y), nb1_2), e0 = __fadd2_rn(iv_hi16(d.x, d.y), nb0_2);
@@ -510,6 +516,7 @@ __global__ void __launch_bounds__(1024, 1) scs_place_interval3_kernel(const Inte
             const float2 inv2 = make_float2(inv, inv);
 
             // ---- sweep 3: normalised terms into the accumulators (each owned by one thread)
+#pragma unroll(UNR)
             for (int j = t; j < n_pairs; j += T) {
                 const uint2 tb = dc2[j];
                 acc2[j] = __ffma2_rn(make_float2(__uint_as_float(tb.x), __uint_as_float(tb.y)), inv2, acc2[j]);
