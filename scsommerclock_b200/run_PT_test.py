@@ -185,6 +185,27 @@ def _read_text(vcf_file):
         return f.read()
 
 
+def _prefetch_texts(files, workers=None, window=None):
+    """Yield ``_read_text(f)`` for every file, in order, reading (and gunzipping -- zlib releases the GIL)
+    up to ``window`` files ahead on ``workers`` threads: a sweep over thousands of small VCFs is bound by
+    decompression on the host, not by the GPU."""
+    from concurrent.futures import ThreadPoolExecutor
+    files = list(files)
+    workers = workers or max(1, min(8, (os.cpu_count() or 2) - 1))
+    window = window or 2 * workers
+    if workers == 1 or len(files) <= 1:
+        for f in files:
+            yield _read_text(f)
+        return
+    with ThreadPoolExecutor(max_workers=workers) as ex:
+        futs, nxt = {}, 0
+        for i in range(len(files)):
+            while nxt < len(files) and nxt < i + window:
+                futs[nxt] = ex.submit(_read_text, files[nxt])
+                nxt += 1
+            yield futs.pop(i).result()
+
+
 def _header_samples(text):
     """Sample names from the (last) #CHROM line, renamed like run_PT_test.py:49-56."""
     sample_names = None
@@ -210,14 +231,15 @@ def _header_samples(text):
     return sample_names
 
 
-def get_mut_df(vcf_file, exclude_pat, include_pat, filter=True, ctx=None):
+def get_mut_df(vcf_file, exclude_pat, include_pat, filter=True, ctx=None, _text=None):
     """run_PT_test.py:27-207.  Returns ``(muts, true_muts, read_data)`` like the
     reference; ``muts`` is a device-resident GenotypeMatrix, the other two (true
-    genotypes and read counts, which the PT test never touches) are None."""
+    genotypes and read counts, which the PT test never touches) are None.
+    ``_text``: the file's decompressed bytes when the caller has read them already."""
     if not filter:
         raise NotImplementedError("filter=False is not on the PT-test path")
     ctx = ctx or get_context()
-    text = _read_text(vcf_file)
+    text = _text if _text is not None else _read_text(vcf_file)
     sample_names = _header_samples(text)
     exclude = []
     if exclude_pat != "":                                                       # :57-65
@@ -693,8 +715,8 @@ def run_poisson_tree_test_batch(vcf_files, tree_files, out_files, w_maxs, exclud
     mine = sharding.replicate_shard(len(vcf_files), rank, world) if shard else list(range(len(vcf_files)))
     dev = torch.device("cuda", ctx.device)
     items = []
-    for i in mine:
-        muts = get_mut_df(vcf_files[i], exclude, include, ctx=ctx)[0]
+    for i, text in zip(mine, _prefetch_texts([vcf_files[i] for i in mine])):    # files are read / gunzipped ahead on host threads
+        muts = get_mut_df(vcf_files[i], exclude, include, ctx=ctx, _text=text)[0]
         tree, outg, FP, FN = read_tree(tree_files[i], muts.columns)
         FP, FN = _error_rates(FP, FN, FN_in, FP_in)
         columns = list(muts.columns)

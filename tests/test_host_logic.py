@@ -189,3 +189,22 @@ def test_clade_intervals_of_tree_masks_and_of_general_masks():
     S = (rng.random((40, 70)) < 0.3).astype(np.uint8)
     bits, words = engine.pack_clades(S)
     assert not engine.clade_intervals(bits, 70)[0]
+
+
+def test_vcf_texts_are_prefetched_in_order(tmp_path):
+    """The sweep driver reads / gunzips VCFs ahead on host threads: same bytes, same order, any window."""
+    import gzip
+    files = []
+    for k in range(7):
+        body = ("##fileformat=VCFv4.2\n#CHROM\tPOS\n" + "".join("1\t%d\n" % (k * 100 + j) for j in range(50 * (k + 1)))).encode()
+        f = tmp_path / ("v%d.vcf%s" % (k, ".gz" if k % 2 else ""))
+        if k % 2:
+            with gzip.open(f, "wb") as fh:
+                fh.write(body)
+        else:
+            f.write_bytes(body)
+        files.append(str(f))
+    want = [P._read_text(f) for f in files]
+    for workers, window in [(1, None), (2, 1), (3, 2), (4, None), (8, 50)]:
+        assert list(P._prefetch_texts(files, workers=workers, window=window)) == want
+    assert list(P._prefetch_texts([])) == []
