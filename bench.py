@@ -48,6 +48,9 @@ NCU_TRAFFIC_BYTES = 289.6e9
 # the full size: 2.52 GB read = the permuted genotypes once, 0.30 GB of per-run partials written)
 NCU_TRAFFIC_BYTES_CACHE = 305.5e9
 NCU_TRAFFIC_BYTES_INTERVAL = 2.82e9
+# warp instructions the interval kernel executes per SNV at 10,001 columns x 20,000 clade rows
+# (smsp__inst_executed.sum of profiles/r01_ncu_interval_final_250k_summary.txt / 250,000 SNVs)
+NCU_INTERVAL_WARP_INST_PER_SNV = 5282607802.0 / 250000.0
 
 
 def parse():
@@ -531,7 +534,7 @@ def main():
             # interval path: the packed 2-bit genotypes are read once (2 bits per (SNV, cell)); nothing else touches HBM but
             # the per-run partial sums.  The kernel is bound by instruction issue, not by HBM or the tensor pipe -- of the
             # two rooflines the contract names, HBM is the one its only off-chip traffic belongs to.
-            t_k = float(g[:, 0].mean())
+            t_k = float(g[:, 2].mean())                                      # the placement kernel (g[:, 0]: the cell-order pass before it)
             alg_bytes = float(n_snv) * pitch
             hbm_peak = pk.get("hbm_gbs_sustained", pk.get("hbm_gbs"))
             roofline = {"bound": "hbm", "achieved": alg_bytes / 1e9 / (t_k / 1e3), "peak": hbm_peak, "unit": "GB/s",
@@ -539,13 +542,25 @@ def main():
                         "traffic": NCU_TRAFFIC_BYTES_INTERVAL if full_size else None,
                         "peak_source": pk_kind + " HBM copy bandwidth",
                         "kernel": "scs_place_interval%s_kernel (prefix counts in shared memory, no GEMM)" % ("3" if plan_info["interval_variant"] == 3 else ""),
-                        "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": t_k, "reduce_ms": float(g[:, 3].mean()),
+                        "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": t_k, "permute_ms": float(g[:, 0].mean()),
+                        "reduce_ms": float(g[:, 3].mean()),
                         "entries_per_s": float(n_snv) * n_rows / (t_k / 1e3),
                         "actual_limiter": "instruction issue (ncu: issue slots 67 % busy, ALU pipe 52 %, 8 warps per scheduler, ~12 cycles between "
                                           "a warp's instructions); HBM traffic is ~50 GB/s because the algorithm needs O(cells + clade rows) work "
                                           "per SNV instead of the GEMM's O(cells x clade rows) -- see gemm_path for the tensor-pipe roofline of "
                                           "the same workload through the tcgen05 GEMM",
                         "smem_bytes": plan_info["interval_smem_bytes"], "threads": plan_info["interval_threads"], "grid": plan_info["interval_grid"]}
+            if full_size:
+              try:
+                # the roofline that does bound it: issue slots (4 schedulers per SM, one warp instruction per cycle each)
+                sm_count = getattr(ctx, "sm_count", 148)
+                clk = ((sampler.summary().get("sm_mhz") if sampler else None) or pk.get("sm_max_mhz", 1965.0)) * 1e6
+                inst = NCU_INTERVAL_WARP_INST_PER_SNV * n_snv
+                roofline["issue_roofline"] = {"warp_instructions_per_launch": inst, "achieved_per_s": inst / (t_k / 1e3),
+                                              "peak_per_s": sm_count * 4 * clk, "frac": inst / (t_k / 1e3) / (sm_count * 4 * clk),
+                                              "note": "instruction count from the ncu capture of the same kernel (250k SNVs, scaled)"}
+              except Exception as exc:          # (an explanatory extra: never lose the line over it)
+                roofline["issue_roofline"] = {"error": repr(exc)}
         else:
             roofline = gemm_roofline(g, plan_info)
         gemm_path = None

@@ -117,9 +117,10 @@ int scs_placement_bind_genotypes(scs_placement* plan, const uint8_t* d_gt, int64
  * The masks also decide HOW the counts S x genotypes are formed: the clades of a tree are a
  * laminar family, so in a depth-first order of the cells every row is one interval and both
  * counts of a (SNV, clade) pair are a difference of per-SNV prefix counts -- the "interval
- * path" (csrc/scs_place_interval.cuh), used for single-dataset plans whenever the masks pass
- * that test.  Any other 0/1 matrix, and every replicate batch, goes through the tcgen05 GEMM.
- * SCS_PLACE_ALGO=gemm forces the GEMM. */
+ * path" (csrc/scs_place_interval.cuh), used for single-dataset plans of more than 3968 cells
+ * whose masks pass that test (below that the GEMM was measured faster).  Any other 0/1 matrix,
+ * and every replicate batch, goes through the tcgen05 GEMM.  SCS_PLACE_ALGO=gemm forces the GEMM,
+ * SCS_PLACE_ALGO=interval takes the interval path for tree-shaped masks at any size. */
 int scs_placement_set_clades(scs_placement* plan, const uint32_t* d_bits, int64_t pitch_words, void* stream);
 int scs_placement_set_clades_host(scs_placement* plan, const uint32_t* bits, int64_t pitch_words, void* stream);
 /* Host-only helper (no device work): *laminar = 1 when the masks are a laminar family, and then
@@ -138,8 +139,9 @@ const void* scs_placement_device_result(scs_placement* plan);
 /* Device durations (CUDA events on the launching stream) of the four kernels of the
  * last scs_placement_run: ms[0] GEMM pass 1 (row statistics), ms[1] merge, ms[2]
  * pass 2 (column sums: second GEMM pass or count-cache sweep), ms[3] reduction; on the
- * interval path ms[0] is the one placement kernel and ms[1], ms[2] are zero.  Waits for that
- * run to finish. */
+ * interval path ms[0] is the pass that rewrites the genotype rows in depth-first cell order
+ * (zero when they were still valid), ms[1] is zero, ms[2] the placement kernel.  Waits for
+ * that run to finish. */
 int scs_placement_last_times(scs_placement* plan, float* ms);
 /* info[0..9] = M_pad, N_pad, K_pad, tasks, run_len, superblock_width, grid,
  * kernel launches so far, runs, dynamic smem bytes, operand mode (0 = two u8

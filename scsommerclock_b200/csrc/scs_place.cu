@@ -1666,14 +1666,21 @@ int scs_placement_bind_genotypes(scs_placement* h, const uint8_t* d_gt, int64_t 
 }
 
 // Decide the algorithm for these clade masks (host copy `bits`): interval path when they are a laminar
-// family, the plan is a single dataset and the working set fits shared memory; SCS_PLACE_ALGO = gemm |
-// interval | auto overrides ("interval" still falls back when the masks are not laminar).
+// family, the plan is a single dataset of more than 3968 cells and the working set fits shared memory;
+// SCS_PLACE_ALGO = gemm | interval | auto overrides ("interval": whenever the masks are laminar, at any size).
 static int choose_algo(Placement* pl, const uint32_t* bits, int64_t pitch_words, cudaStream_t st) {
     pl->algo = 1;
     pl->gt_perm_valid = false;      // (the cell order may change with the masks)
     const char* e = getenv("SCS_PLACE_ALGO");
     if (e && !strcmp(e, "gemm")) return SCS_OK;
     if (pl->n_groups != 1) return SCS_OK;
+    // Where each algorithm wins was measured, not assumed (bench.py, same run): at 10,000 cells the interval path
+    // is 3.3x faster than the GEMM (51 against 170 ms per step), at 1,000 cells the GEMM -- one K chunk, epilogue
+    // bound, cost proportional to the clade rows like the interval path's but with a smaller constant -- is 1.9x
+    // faster (0.98 against 1.86 ms).  "auto" therefore takes the interval path from the GEMM's own regime change on
+    // (more than one K chunk: > 3968 cells); SCS_PLACE_ALGO=interval takes it for every tree-shaped matrix.
+    const bool forced = e && (!strcmp(e, "interval") || !strcmp(e, "interval1"));
+    if (!forced && pl->n_cells <= RADIX_KB_PER_CHUNK * BLOCK_K) return SCS_OK;
     const size_t SMEM_MAX = 227 * 1024;
     // cheapest test first: does even the smallest working set (prefix counts + accumulators) fit shared memory?
     if (interval_smem_bytes(pl->n_cells, pl->n_rows, false, false) > SMEM_MAX) return SCS_OK;
@@ -1983,6 +1990,8 @@ int scs_placement_run_batch(scs_placement* h, const double* FP, const double* FN
                 pl->gt_perm_valid = true;
                 pl->launches++;
             }
+            cudaEventRecord(pl->ev[1], st);      // ms[0] = the permutation pass (0 when the permuted rows were still valid)
+            cudaEventRecord(pl->ev[2], st);
             Interval3Params q;
             ip.gt = reinterpret_cast<const uint8_t*>(pl->gt_perm);
             ip.pitch = int64_t(rw) * 4;
@@ -1995,11 +2004,11 @@ int scs_placement_run_batch(scs_placement* h, const double* FP, const double* FN
             if (pl->iv_threads <= 640) scs_place_interval3_kernel<640, 2><<<pl->iv_grid, pl->iv_threads, pl->iv_smem, st>>>(q);
             else scs_place_interval3_kernel<1024, 1><<<pl->iv_grid, pl->iv_threads, pl->iv_smem, st>>>(q);
         } else {
+            cudaEventRecord(pl->ev[1], st);
+            cudaEventRecord(pl->ev[2], st);
             scs_place_interval_kernel<false><<<pl->iv_grid, pl->iv_threads, pl->iv_smem, st>>>(ip);
         }
-        cudaEventRecord(pl->ev[1], st);
-        cudaEventRecord(pl->ev[2], st);
-        cudaEventRecord(pl->ev[3], st);
+        cudaEventRecord(pl->ev[3], st);          // ms[2] = the placement kernel
         scs_reduce_interval_kernel<<<unsigned((pl->iv_entries + 255) / 256), 256, 0, st>>>(pl->ipart, pl->iv_runs, pl->iv_entries, pl->iv_stride,
                                                                                          pl->d_slot_row, y);
         cudaEventRecord(pl->ev[4], st);

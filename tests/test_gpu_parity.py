@@ -196,7 +196,8 @@ def test_interval_path_matches_oracle_and_gemm(ctx, monkeypatch, n_snv, n_cells)
     bits, words = engine.pack_clades(S)
     got = {}
     for algo in ("auto", "gemm"):
-        monkeypatch.setenv("SCS_PLACE_ALGO", algo)
+        # "auto" takes the interval path above 3968 cells (where it is faster), "interval" at any size
+        monkeypatch.setenv("SCS_PLACE_ALGO", algo if (algo == "gemm" or n_cells > 3968) else "interval")
         pl = engine.Placement(ctx, n_snv, n_cells, S.shape[0])
         pl.set_clades_host(bits, words)
         pl.set_genotypes_host(packed, pitch, keep)
@@ -226,8 +227,7 @@ def test_interval_path_block_shapes_and_run_lengths(ctx, monkeypatch, threads, r
     n_snv, n_cells = 333, 300
     codes, S = shuffled_problem(n_snv, n_cells, seed=threads)
     S = np.concatenate([S, S[5:6], S[n_cells + 3:n_cells + 4], S[0:1]], axis=0)
-    if variant == 1:
-        monkeypatch.setenv("SCS_PLACE_ALGO", "interval1")
+    monkeypatch.setenv("SCS_PLACE_ALGO", "interval1" if variant == 1 else "interval")
     codes[7] = 3                       # nothing observed: uniform over the rows of S
     codes[8] = 1                       # everything mutated
     codes[9] = 0
@@ -248,10 +248,18 @@ def test_interval_path_block_shapes_and_run_lengths(ctx, monkeypatch, threads, r
     pl.close()
 
 
-def test_interval_path_needs_tree_shaped_masks_and_shared_memory(ctx):
+def test_interval_path_needs_tree_shaped_masks_and_shared_memory(ctx, monkeypatch):
     """Masks that are not a laminar family, replicate batches and trees whose working set exceeds
-    shared memory go through the GEMM."""
+    shared memory go through the GEMM; so do, by default, trees of up to 3968 cells (the GEMM is
+    faster there) unless SCS_PLACE_ALGO=interval asks for the interval path."""
     rng = np.random.default_rng(3)
+    codes, S = make_problem(50, 40, seed=1)
+    bits, words = engine.pack_clades(S)
+    pl = engine.Placement(ctx, 50, 40, S.shape[0])
+    pl.set_clades_host(bits, words)
+    assert pl.info()["algo"] == 1                       # default: small tree -> GEMM
+    pl.close()
+    monkeypatch.setenv("SCS_PLACE_ALGO", "interval")
     codes, S = make_problem(50, 40, seed=1)
     S2 = S.copy()
     S2[3] = 0

@@ -54,7 +54,7 @@ for n_snv in sizes:
         t = pl.last_times()
         info = pl.info()
         res[mode] = y.cpu().numpy()
-        print("cells %d snvs %d %-9s pass1 %.2f merge %.2f pass2 %.2f reduce %.3f ms  algo %d pass2_mode %d runs %d run_len %d free %.1f GB  interval grid %d x %d thr, %d B smem, %d runs" % (
+        print("cells %d snvs %d %-9s pass1|permute %.2f merge %.2f pass2|interval %.2f reduce %.3f ms  algo %d pass2_mode %d runs %d run_len %d free %.1f GB  interval grid %d x %d thr, %d B smem, %d runs" % (
             n_cells, n_snv, mode, t[0], t[1], t[2], t[3], info["algo"], info["pass2_mode"], info["runs"], info["run_len"],
             torch.cuda.mem_get_info()[0] / 1e9, info["interval_grid"], info["interval_threads"], info["interval_smem_bytes"],
             info["interval_runs"]), flush=True)
