@@ -208,3 +208,59 @@ def test_vcf_texts_are_prefetched_in_order(tmp_path):
     for workers, window in [(1, None), (2, 1), (3, 2), (4, None), (8, 50)]:
         assert list(P._prefetch_texts(files, workers=workers, window=window)) == want
     assert list(P._prefetch_texts([])) == []
+
+
+def interval_counts(codes, S):
+    """CPU restatement of the interval path's integer arithmetic (csrc/scs_place_interval.cuh): the cell
+    order and the intervals come from the library's host analysis (scs_clade_intervals), the counts are
+    differences of per-SNV prefix counts in that order."""
+    bits, words = engine.pack_clades(S)
+    ok, perm, lo, hi = engine.clade_intervals(bits, S.shape[1])
+    assert ok
+    c = codes[:, perm]                                            # depth-first cell order
+    z = np.zeros((codes.shape[0], 1), dtype=np.int64)
+    p1 = np.concatenate([z, np.cumsum((c == 1) | (c == 2), axis=1)], axis=1)
+    p0 = np.concatenate([z, np.cumsum(c == 0, axis=1)], axis=1)
+    return p1[:, hi] - p1[:, lo], p0[:, hi] - p0[:, lo]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_interval_counts_equal_the_dense_contraction_on_golden_cases(name):
+    """run_PT_test.py:421-430 contracts the genotypes against S; for a tree's S the same integers are
+    prefix-count differences.  Checked here on the reference's own clade matrices (fixtures), cell by
+    cell, without a GPU; the soft weights built from those counts reproduce the recorded ones."""
+    g = load(name)
+    S = g["S"].astype(np.uint8)
+    codes = g["muts_codes"]
+    samples = list(g["samples"])
+    if codes.shape[1] != S.shape[1]:                              # the fixture's S has no outgroup column
+        keep_cols = [i for i, c in enumerate(samples) if c != "healthycell"]
+        codes = codes[:, keep_cols]
+    assert codes.shape[1] == S.shape[1]
+    C1, C0 = interval_counts(codes, S)
+    x1 = ((codes == 1) | (codes == 2)).astype(np.int64)
+    x0 = (codes == 0).astype(np.int64)
+    assert np.array_equal(C1, x1 @ S.T.astype(np.int64)) and np.array_equal(C0, x0 @ S.T.astype(np.int64))
+    # the softmax over clade rows of a1 C1 + a0 C0 is the reference's normalised placement (:368-383, :421-430)
+    FP, FN = float(g["FP"]), float(g["FN"])
+    a1, a0 = np.log((1 - FN) / FP), np.log(FN / (1 - FP))
+    keep = x1.any(axis=1) if "healthycell" in samples else np.ones(codes.shape[0], dtype=bool)
+    logit = a1 * C1[keep] + a0 * C0[keep]
+    M = np.exp(logit - logit.max(axis=1, keepdims=True))
+    soft = (M / M.sum(axis=1, keepdims=True)).sum(axis=0)
+    np.testing.assert_allclose(soft, g["soft"], rtol=1e-9, atol=1e-9)
+
+
+def test_interval_counts_on_random_trees_with_shuffled_columns():
+    from scsommerclock_b200 import synth
+    rng = np.random.default_rng(11)
+    for n in (2, 5, 64, 301):
+        tree = synth.coalescent_tree(n, rng)
+        S = tree.clade_matrix()
+        codes = synth.observe(tree, synth.throw_mutations(tree, 200, rng), 0.1, 0.01, 0.2, rng)
+        cols = rng.permutation(n)
+        S, codes = np.ascontiguousarray(S[:, cols]), np.ascontiguousarray(codes[:, cols])
+        C1, C0 = interval_counts(codes, S)
+        x1 = ((codes == 1) | (codes == 2)).astype(np.int64)
+        x0 = (codes == 0).astype(np.int64)
+        assert np.array_equal(C1, x1 @ S.T.astype(np.int64)) and np.array_equal(C0, x0 @ S.T.astype(np.int64))
