@@ -7,25 +7,23 @@
 //     (C1, C0)[i, b] = P_i[hi_b] - P_i[lo_b],
 // i.e. O(cells + clade rows) work per SNV instead of the O(cells x clade rows) contraction
 // (run_PT_test.py:421-430 evaluates the dense product; the numbers are the same integers).  At
-// 10k cells that is ~10,000x fewer operations than the GEMM, and the kernel is bound by instruction
-// issue (about 40 instructions per (SNV, clade row): two shared-memory lookups, the exact-difference
-// exponent of the GEMM epilogue, ex2, accumulate), not by the tensor pipe or HBM: the packed 2-bit
-// genotypes (2.5 GB at 10k x 1M) are read exactly once, nothing else touches HBM.
+// 10k cells that is ~10,000x fewer operations than the GEMM.  Nothing but the packed 2-bit
+// genotypes (2.5 GB at 10k x 1M, read once) and the per-run partial sums touches HBM; what bounds
+// the kernels is instruction issue and shared-memory latency, not the tensor pipe or HBM.
 //
-// One CTA walks SNV rows; per row it
-//   1. gathers the row's 2-bit codes in depth-first order and scans them into P (packed u32:
-//      mutated | wild type << 16, so one subtraction yields both counts),
-//   2. sweeps the clade rows once with a running reference column (same rule and the same
-//      arithmetic on exact integer differences as stats_cols32 in scs_place.cu), merges the
-//      per-thread (reference, sum) pairs over the block -> reference column and log2-sum of the row,
-//   3. sweeps the clade rows again and adds 2^(logit - logit_ref - log2sum) to per-clade-row
-//      accumulators in shared memory (each owned by one thread: no atomics).
-// Accumulators are flushed per run of rows to part[run][row]; a fixed-order fp64 reduction over the
-// runs gives the soft weights (short fp32 chains, deterministic).
+// Two kernels walk SNV rows, one CTA per run of rows, accumulators in shared memory (each owned by
+// one thread: no atomics), flushed per run to part[run][slot]; a fixed-order fp64 reduction over
+// the runs gives the soft weights (short fp32 chains, deterministic):
+//   scs_place_interval3_kernel  the main one (trees up to ~14,000 cells): rows rewritten in
+//       depth-first cell order first (scs_permute_cells_kernel), word-wise prefix counts, the
+//       leaves handled outside the sweeps, per-row count cache in shared memory -- see below;
+//   scs_place_interval_kernel   every clade row through two sweeps with a running reference column
+//       (same rule and arithmetic as stats_cols32 in scs_place.cu), cells gathered through the
+//       cell order, counts recomputed in the second sweep: for trees whose count cache does not
+//       fit shared memory.
 //
 // Whether a clade matrix is laminar is decided from the bit masks themselves (clade_intervals), so
-// the C ABI is unchanged: any caller that passes tree-shaped masks gets this path, anything else
-// goes through the GEMM.
+// the C ABI is unchanged; which plans take this path is decided in choose_algo (scs_place.cu).
 #pragma once
 
 #include <algorithm>
