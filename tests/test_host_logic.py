@@ -264,3 +264,55 @@ def test_interval_counts_on_random_trees_with_shuffled_columns():
         x1 = ((codes == 1) | (codes == 2)).astype(np.int64)
         x0 = (codes == 0).astype(np.int64)
         assert np.array_equal(C1, x1 @ S.T.astype(np.int64)) and np.array_equal(C0, x0 @ S.T.astype(np.int64))
+
+
+def test_clade_intervals_on_general_laminar_families():
+    """Any laminar family is accepted (multifurcating trees, duplicate and empty rows, cells in no clade),
+    a family with one crossing pair is rejected; accepted orders make every row exactly its interval --
+    which is all the interval path's integer arithmetic needs."""
+    rng = np.random.default_rng(2024)
+
+    def random_family(cells, out):
+        if len(cells) < 2:
+            return
+        k = int(rng.integers(2, min(5, len(cells)) + 1))              # arity 2..5
+        cuts = np.sort(rng.choice(np.arange(1, len(cells)), size=k - 1, replace=False))
+        for part in np.split(cells, cuts):
+            if rng.random() < 0.85:
+                out.append(part)
+            random_family(part, out)
+
+    def is_laminar(rows):
+        sets = [frozenset(np.nonzero(r)[0].tolist()) for r in rows]
+        return all(not (a & b) or a <= b or b <= a for i, a in enumerate(sets) for b in sets[i + 1:])
+
+    for n in (3, 17, 90):
+        for trial in range(6):
+            cells = rng.permutation(n)
+            fam = [cells[: n - 2]]                                   # the last two cells sit in no clade
+            random_family(cells[: n - 2], fam)
+            S = np.zeros((len(fam) + 2, n), dtype=np.uint8)
+            for r, part in enumerate(fam):
+                S[r, part] = 1
+            S[-2] = S[int(rng.integers(0, len(fam)))]                # a duplicate; the last row stays empty
+            S = S[rng.permutation(S.shape[0])]
+            assert is_laminar(S)
+            bits, words = engine.pack_clades(S)
+            ok, perm, lo, hi = engine.clade_intervals(bits, n)
+            assert ok, (n, trial)
+            for b in range(S.shape[0]):
+                members = np.zeros(n, dtype=np.uint8)
+                members[perm[lo[b]:hi[b]]] = 1
+                assert np.array_equal(members, S[b])
+            # one crossing pair: a row that takes one cell of each of two disjoint rows
+            big = [r for r in range(S.shape[0]) if S[r].sum() >= 2]
+            pairs = [(a, b) for a in big for b in big if a < b and not (S[a] & S[b]).any()]
+            if pairs:
+                a, b = pairs[int(rng.integers(0, len(pairs)))]
+                bad = np.zeros(n, dtype=np.uint8)
+                bad[np.nonzero(S[a])[0][0]] = 1
+                bad[np.nonzero(S[b])[0][0]] = 1
+                S2 = np.concatenate([S, bad[None, :]], axis=0)
+                assert not is_laminar(S2)
+                bits2, _ = engine.pack_clades(S2)
+                assert not engine.clade_intervals(bits2, n)[0]
