@@ -313,6 +313,61 @@ def map_mutations_gt_literal(muts_vals, S, FP, FN):
     return M.sum(axis=0), M
 
 
+def clade_intervals(S):
+    """Order of the cells in which every row of a tree-shaped (laminar) 0/1 matrix S is one interval.
+    Rows by decreasing size, cells sorted by their membership signature over those rows; returns
+    (perm, lo, hi) with row b == cells perm[lo[b]:hi[b]], or None when some row is not contiguous in
+    that order (S is then not a laminar family).  Independent NumPy restatement of the product's host
+    analysis (csrc/scs_place_interval.cuh: clade_intervals), used to check it and to give the tests an
+    oracle that finishes at 10,000 cells."""
+    S = np.asarray(S).astype(bool)
+    size = S.sum(axis=1)
+    order = np.argsort(-size, kind="stable")
+    order = order[size[order] > 0]
+    # lexsort: last key is the primary one -> feed the rows smallest first; descending on every key
+    perm = np.lexsort(tuple(~S[r] for r in order[::-1])) if order.size else np.arange(S.shape[1])
+    pos = np.empty(S.shape[1], dtype=np.int64)
+    pos[perm] = np.arange(S.shape[1])
+    lo = np.zeros(S.shape[0], dtype=np.int64)
+    hi = np.zeros(S.shape[0], dtype=np.int64)
+    for b in range(S.shape[0]):
+        if size[b] == 0:
+            continue
+        p = pos[S[b]]
+        lo[b], hi[b] = p.min(), p.max() + 1
+        if hi[b] - lo[b] != size[b]:
+            return None
+    return perm, lo, hi
+
+
+def map_mutations_gt_interval(muts_vals, S, FP, FN, chunk=2048):
+    """map_mutations_gt (run_PT_test.py:386-448) for a tree-shaped S without the dense products: the
+    terms of probs[i, b] that depend on b are log((1-FN)/FP) * C1[i, b] + log(FN/(1-FP)) * C0[i, b]
+    (C1 / C0: cells of clade b observed mutated / wild type; everything else cancels in the
+    normalisation :368-383), and for a laminar S both counts are differences of per-SNV prefix counts
+    in the cell order of clade_intervals.  float64 throughout; agrees with map_mutations_gt to
+    rounding (tests/test_oracle_golden.py) and runs at 10,000 cells x 20,000 rows in seconds."""
+    iv = clade_intervals(S)
+    if iv is None:
+        raise ValueError("S is not a laminar family")
+    perm, lo, hi = iv
+    a1 = np.log(1 - FN) - np.log(FP)
+    a0 = np.log(FN) - np.log(1 - FP)
+    soft = np.zeros(S.shape[0])
+    for s in range(0, muts_vals.shape[0], chunk):
+        v = muts_vals[s:s + chunk][:, perm]
+        obs = ~np.isnan(v)
+        mut = obs & (np.nan_to_num(v) != 0)
+        wt = obs & ~mut
+        z = np.zeros((v.shape[0], 1), dtype=np.int64)
+        p1 = np.concatenate([z, np.cumsum(mut, axis=1)], axis=1)
+        p0 = np.concatenate([z, np.cumsum(wt, axis=1)], axis=1)
+        logit = a1 * (p1[:, hi] - p1[:, lo]) + a0 * (p0[:, hi] - p0[:, lo])
+        M = np.exp(logit - logit.max(axis=1, keepdims=True))
+        soft += (M / M.sum(axis=1, keepdims=True)).sum(axis=0)
+    return soft
+
+
 # ----------------------------------------------------------------- weights
 def branch_weights(S_nodes_bool, l_TN, l_DO, w_max):
     """add_br_weights, run_PT_test.py:451-502 (per-cell MS branch).  S_nodes_bool

@@ -118,3 +118,40 @@ def test_pvalue_mixture_known_values():
     assert O.lrt_pvalue(30.0, 29, 1) == pytest.approx(want)
     # dof - k <= 0 terms are NaN in SciPy and get weight 0
     assert np.isfinite(O.lrt_pvalue(3.0, 2, 3))
+
+
+def test_interval_form_of_the_placement_oracle():
+    """The oracle's prefix-count form of map_mutations_gt (for tree-shaped S) against its dense form and
+    against the soft weights the reference recorded; its cell order against the product's host analysis."""
+    from scsommerclock_b200 import engine, synth
+    for name in CASES:
+        g = load(name)
+        S = g["S"].astype(float)
+        codes = g["muts_codes"]
+        samples = list(g["samples"])
+        if codes.shape[1] != S.shape[1]:
+            codes = codes[:, [i for i, c in enumerate(samples) if c != "healthycell"]]
+        muts = np.where(codes == 3, np.nan, codes.astype(float))
+        if "healthycell" in samples:
+            muts = muts[((codes == 1) | (codes == 2)).any(axis=1)]
+        FP, FN = float(g["FP"]), float(g["FN"])
+        got = O.map_mutations_gt_interval(muts, S, FP, FN)
+        np.testing.assert_allclose(got, g["soft"], rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(got, O.map_mutations_gt(muts, S, FP, FN), rtol=1e-9, atol=1e-9)
+    rng = np.random.default_rng(8)
+    for n in (2, 33, 300):
+        tree = synth.coalescent_tree(n, rng)
+        cols = rng.permutation(n)
+        S = np.ascontiguousarray(tree.clade_matrix()[:, cols])
+        codes = np.ascontiguousarray(synth.observe(tree, synth.throw_mutations(tree, 150, rng), 0.1, 0.01, 0.2, rng)[:, cols])
+        muts = np.where(codes == 3, np.nan, codes.astype(float))
+        np.testing.assert_allclose(O.map_mutations_gt_interval(muts, S.astype(float), 0.01, 0.1),
+                                   O.map_mutations_gt(muts, S.astype(float), 0.01, 0.1), rtol=1e-9, atol=1e-9)
+        perm, lo, hi = O.clade_intervals(S)
+        bits, words = engine.pack_clades(S)
+        ok, perm2, lo2, hi2 = engine.clade_intervals(bits, n)
+        assert ok
+        for b in range(S.shape[0]):                                   # both orders describe the same clades
+            assert set(perm[lo[b]:hi[b]].tolist()) == set(perm2[lo2[b]:hi2[b]].tolist()) == set(np.nonzero(S[b])[0].tolist())
+    bad = np.array([[1, 1, 0, 0], [0, 1, 1, 0]], dtype=float)
+    assert O.clade_intervals(bad) is None
