@@ -231,11 +231,14 @@ def _header_samples(text):
     return sample_names
 
 
-def get_mut_df(vcf_file, exclude_pat, include_pat, filter=True, ctx=None, _text=None):
+def get_mut_df(vcf_file, exclude_pat, include_pat, filter=True, ctx=None, _text=None, shard_rows=False):
     """run_PT_test.py:27-207.  Returns ``(muts, true_muts, read_data)`` like the
     reference; ``muts`` is a device-resident GenotypeMatrix, the other two (true
     genotypes and read counts, which the PT test never touches) are None.
-    ``_text``: the file's decompressed bytes when the caller has read them already."""
+    ``_text``: the file's decompressed bytes when the caller has read them already.
+    ``shard_rows``: opt-in, set by run_poisson_tree_test under torchrun only -- this rank decodes its own
+    block of record lines and the caller all-reduces what depends on all rows (kept SNVs, missing counts,
+    soft weights).  Replicate sweeps shard whole pairs instead and never set it."""
     if not filter:
         raise NotImplementedError("filter=False is not on the PT-test path")
     ctx = ctx or get_context()
@@ -265,7 +268,7 @@ def get_mut_df(vcf_file, exclude_pat, include_pat, filter=True, ctx=None, _text=
     if not include_idx:
         raise ValueError("no sample left after -excl/-incl")
     sharded = False
-    if _row_sharding_active():
+    if shard_rows and _row_sharding_active():
         # one large dataset on several GPUs: every rank decodes and places its own block of record
         # lines; the branch weights are all-reduced later
         text = _shard_record_lines(text)
@@ -676,7 +679,7 @@ def run_poisson_tree_test(vcf_file, tree_file, out_file, w_maxs, exclude, includ
     model_str = ""
     w_cols = ["-2logLR", "dof", "p-value", "hypothesis"]
     w_idx = 0
-    call_data = get_mut_df(vcf_file, exclude, include)
+    call_data = get_mut_df(vcf_file, exclude, include, shard_rows=_row_sharding_active())
     problems = []
     for w_max in w_maxs:
         tree, FP, FN, M = get_gt_tree(tree_file, call_data, w_max, FN_in, FP_in)
@@ -716,7 +719,7 @@ def run_poisson_tree_test_batch(vcf_files, tree_files, out_files, w_maxs, exclud
     dev = torch.device("cuda", ctx.device)
     items = []
     for i, text in zip(mine, _prefetch_texts([vcf_files[i] for i in mine])):    # files are read / gunzipped ahead on host threads
-        muts = get_mut_df(vcf_files[i], exclude, include, ctx=ctx, _text=text)[0]
+        muts = get_mut_df(vcf_files[i], exclude, include, ctx=ctx, _text=text, shard_rows=False)[0]   # whole pairs are sharded, not rows
         tree, outg, FP, FN = read_tree(tree_files[i], muts.columns)
         FP, FN = _error_rates(FP, FN, FN_in, FP_in)
         columns = list(muts.columns)

@@ -18,22 +18,12 @@ def golden_path(name):
 
 
 def case_inputs(g):
-    """(vcf, tree) paths of a golden case.  The reference's example_data is not in
-    this repo (it lives in /root/reference, absent on the GPU box); its inputs are
-    replaced there by the fixture's recorded genotype matrix."""
+    """(vcf, tree, meta) of a golden case.  Every input file -- the reference's own example_data included,
+    copied byte for byte by make_golden.py -- lives under tests/golden/data/, so the same tests run on the
+    GPU box, where /root/reference does not exist."""
     import json
     meta = json.loads(str(g["meta"]))
-    vcf, tree = meta["vcf"], meta["tree"]
-    if vcf.startswith("reference/"):
-        vcf_p, tree_p = os.path.join("/root", vcf), os.path.join("/root", tree)
-        if not os.path.exists(tree_p) and "tree_text" in g.files:
-            d = os.path.join(GOLDEN, "_tmp", meta["case"])
-            os.makedirs(d, exist_ok=True)
-            tree_p = os.path.join(d, str(g["tree_basename"]))
-            with open(tree_p, "w") as f:
-                f.write(str(g["tree_text"]))
-        return vcf_p, tree_p, meta
-    return os.path.join(REPO, vcf), os.path.join(REPO, tree), meta
+    return os.path.join(REPO, meta["vcf"]), os.path.join(REPO, meta["tree"]), meta
 
 
 @pytest.fixture(scope="session")

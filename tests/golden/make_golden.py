@@ -250,14 +250,171 @@ def make_synthetic(tag, n_cells, n_snv, seed, FN, FP, MS, with_tg=True, reads="R
     return vcf, tree_file
 
 
+def scite_newick(tree, n_cells):
+    """infSCITE-style Newick (run_PT_test.py:233-252): every node is an integer, leaves 0..n_cells-1 are the
+    tumour cells in VCF column order, n_cells is the outgroup, internal nodes carry the larger labels."""
+    counter = [n_cells + 1]
+
+    def rec(v):
+        if v < n_cells:
+            return str(v)
+        a, b = tree.left[v - n_cells], tree.right[v - n_cells]
+        body = "(%s,%s)" % (rec(a), rec(b))
+        lab = counter[0]
+        counter[0] += 1
+        return body + str(lab)
+
+    body = rec(2 * n_cells - 2)
+    return "(%s,%d)%d;" % (body, n_cells, counter[0])
+
+
+def make_scite_and_path_cases(ref):
+    """The two tree-file branches of read_tree the CellPhy cases do not reach: infSCITE trees (:233-280; integer
+    node labels, error rates from the .log or the .errors.csv next to the tree, FN doubled) and plain Newick files
+    whose error rates are parsed out of the file PATH (:281-294)."""
+    from scsommerclock_b200 import synth
+    d = os.path.join(HERE, "data")
+    n_cells, n_snv = 14, 300
+    v, t = make_synthetic("syn_f", n_cells, n_snv, 31, FN=0.15, FP=0.01, MS=0.1, quirks=False, tree_suffix=".plain.newick")
+    rng = np.random.default_rng(31)
+    tree = synth.coalescent_tree(n_cells, rng)          # the same tree make_synthetic drew (same seed, first draw)
+    os.remove(t)
+    # (1) infSCITE tree + .log holding "best value for beta:\\t..." (a literal backslash-t: that is what the reference's pattern matches)
+    t1 = os.path.join(d, "syn_f_ml0.newick")
+    with open(t1, "w") as f:
+        f.write(scite_newick(tree, n_cells) + "\n")
+    with open(os.path.join(d, "syn_f.log"), "w") as f:
+        f.write("infSCITE-style log (synthetic)\nbest value for beta:\\t0.0750\nbest value for alpha:\\t1.2e-2\n")
+    run_case(ref, "syn_f_scite_log", v, t1, [100, 1000])
+    # (2) infSCITE tree + .errors.csv, two trees in the file (everything after the first ';' is dropped, :237-238)
+    t2 = os.path.join(d, "syn_g_ml0.newick")
+    with open(t2, "w") as f:
+        f.write(scite_newick(tree, n_cells) + "\n" + scite_newick(tree, n_cells) + "\n")
+    with open(os.path.join(d, "syn_g.errors.csv"), "w") as f:
+        f.write("FP,FN\n0.02,0.06\n")
+    run_case(ref, "syn_g_scite_csv", v, t2, [400])
+    # (3) plain Newick, rates from the path (FN = 0.2 -> 0.1 after :346, FP = 0.01)
+    sub = os.path.join(d, "sim_WGA0.2-0-0.01")
+    os.makedirs(sub, exist_ok=True)
+    names = ["cell%04d" % (i + 1) for i in range(n_cells)]
+    t3 = os.path.join(sub, "syn_h.newick")
+    with open(t3, "w") as f:
+        f.write(tree.newick(names, "outgcell", scale=0.05) + "\n")
+    run_case(ref, "syn_h_path_rates", v, t3, [100, 1000])
+
+
+def make_lrt_sweep(ref, n_problems=240, seed=2024):
+    """Random clock-test problems solved by the reference's own get_LRT_poisson (:638-700, SciPy trust-constr),
+    set up by its own get_model_data (:518-635) on random trees of 3..60 leaves: clock-like and rate-shifted
+    counts, sparse counts (zero-count branches, many fitted lengths on the bound), non-integer soft counts,
+    weight vectors clipped at different w_max.  One npz: per problem Y, weights, constr (as child_int, the
+    tree form, checked here to reproduce the dense matrix), init and the reference's LR / dof / on_bound / p."""
+    import tempfile
+    from scsommerclock_b200 import synth
+    from scsommerclock_b200.run_PT_test import ClockConstraints
+    rng = np.random.default_rng(seed)
+    tmp = tempfile.mkdtemp(prefix="scs_lrt_")
+    recs = []
+    n_raise = 0
+    k = 0
+    while len(recs) < n_problems:
+        k += 1
+        n = int(rng.choice([3, 4, 5, 6, 8, 10, 14, 20, 30, 40, 50, 60]))
+        st = synth.coalescent_tree(n, rng)
+        names = ["tumcell%04d" % (i + 1) for i in range(n)]
+        tf = os.path.join(tmp, "t%d.newick" % k)
+        with open(tf, "w") as f:
+            f.write(st.newick(names, "healthycell", scale=0.05))
+        tree, _, _, _ = ref.read_tree(tf, np.array(names + ["healthycell"]))
+        nodes = list(tree.iter_descendants())
+        kind = ["clock", "shift", "sparse", "verysparse", "frac"][int(rng.integers(5))]
+        mu = {"clock": 400.0, "shift": 400.0, "sparse": 6.0, "verysparse": 1.5, "frac": 60.0}[kind] * n
+        w_max = float(rng.choice([50, 100, 400, 1000]))
+        # per node: expected count from the node's height difference in the synthetic tree (clade size identifies the node)
+        by_name = {}
+        inv = np.empty(n, dtype=np.int64)
+        inv[st.leaf_rank] = np.arange(n)
+        for v_ in range(2 * n - 2):
+            cells = sorted(names[c] for c in inv[st.lo[v_]:st.hi[v_]])
+            by_name["+".join(cells)] = v_
+        mult = np.ones(2 * n - 1)
+        if kind == "shift":
+            sizes = st.hi - st.lo
+            top = [v_ for v_ in np.argsort(-sizes) if sizes[v_] <= max(1, n // 2)][0]
+            inside = (st.lo >= st.lo[top]) & (st.hi <= st.hi[top])
+            mult[inside] = float(rng.choice([3.0, 5.0, 8.0]))
+        total_len = (st.branch_len[:-1] * mult[:-1]).sum()
+        p_ado = np.exp(rng.uniform(np.log(1e-6), np.log(0.5), size=len(nodes)))
+        raw = np.clip(1.0 / ((1 - p_ado) * p_ado), None, w_max)
+        for i, node in enumerate(nodes):
+            v_ = by_name.get(node.name)
+            lam = 0.0 if v_ is None else mu * st.branch_len[v_] * mult[v_] / total_len
+            y = float(rng.poisson(lam))
+            if kind == "frac" or rng.random() < 0.3:
+                y = y * float(rng.uniform(0.7, 1.3)) + float(rng.uniform(0, 0.4))
+            node.mut_no_soft = y
+        root_row = [i for i, node in enumerate(nodes) if node.name.count("+") == n - 1][0]
+        wsel = np.delete(raw, root_row)
+        wn = wsel.size * wsel / wsel.sum()
+        j = 0
+        for i, node in enumerate(nodes):
+            if i == root_row:
+                node.weights_norm = np.full(2, -1.0)
+            else:
+                node.weights_norm = np.array([wn[j], wn[j]])
+                j += 1
+        try:
+            Y, constr, init, weights_norm, cols = ref.get_model_data(tree)
+            LR, dof, on_bound, p_val, opt = ref.get_LRT_poisson(Y, constr, init, weights_norm[:, 0])[:5]
+        except (FloatingPointError, AssertionError, ZeroDivisionError) as exc:
+            n_raise += 1
+            continue
+        failed = isinstance(LR, float) and np.isnan(LR)
+        cc = ClockConstraints.from_dense(constr)
+        assert np.array_equal(cc.toarray(), constr)
+        w = weights_norm[:, 0]
+        ll_H1 = float(np.sum((Y * np.log(np.where(Y > 0, Y, 1)) - Y) * w))
+        x = np.full(Y.size, np.nan) if failed else np.array([v_[0] for v_ in opt])
+        recs.append(dict(Y=Y, w=w, child_int=cc.child_int, init=init, x=x, LR=np.nan if failed else LR, dof=-1 if failed else dof,
+                         on_bound=-1 if failed else on_bound, p_val=np.nan if failed else p_val, kind=kind, n=n, ll_H1=ll_H1))
+        print("  lrt %3d: n=%2d %-10s w_max=%4.0f ll_H1=%9.2f LR=%s dof=%s on_bound=%s p=%s" %
+              (len(recs), n, kind, w_max, ll_H1, recs[-1]["LR"], recs[-1]["dof"], recs[-1]["on_bound"], recs[-1]["p_val"]), flush=True)
+    off = np.zeros(len(recs) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([r["Y"].size for r in recs])
+    meta = dict(META, case="lrt_sweep", seed=seed, raised_and_skipped=n_raise,
+                note="problems where the reference itself raised under np.seterr(all='raise') are skipped; LR = NaN marks its failure tuple")
+    np.savez_compressed(os.path.join(HERE, "lrt_sweep.npz"), off=off, Y=np.concatenate([r["Y"] for r in recs]),
+                        w=np.concatenate([r["w"] for r in recs]), child_int=np.concatenate([r["child_int"] for r in recs]),
+                        init=np.concatenate([r["init"] for r in recs]), x=np.concatenate([r["x"] for r in recs]),
+                        LR=np.array([r["LR"] for r in recs]), dof=np.array([r["dof"] for r in recs]),
+                        on_bound=np.array([r["on_bound"] for r in recs]), p_val=np.array([r["p_val"] for r in recs]),
+                        kind=np.array([r["kind"] for r in recs]), n_leaves=np.array([r["n"] for r in recs]),
+                        ll_H1=np.array([r["ll_H1"] for r in recs]), meta=np.array(json.dumps(meta)))
+    shutil.rmtree(tmp, ignore_errors=True)
+
+
 def main():
     ref = load_reference()
+    if "--only-lrt-sweep" in sys.argv:
+        make_lrt_sweep(ref)
+        return
+    if "--only-scite" in sys.argv:
+        make_scite_and_path_cases(ref)
+        return
     ex = os.path.join(REF, "example_data")
     default_w = [100, 200, 300, 400, 500, 600, 700, 800, 900, 1000]
-    if "--skip-examples" not in sys.argv: run_case(ref, "example_clock", os.path.join(ex, "data_simulated_clock.vcf.gz"),
-             os.path.join(ex, "data_simulated_clock.raxml.bestTree"), default_w, rel_to="/root")
-    if "--skip-examples" not in sys.argv: run_case(ref, "example_noclock", os.path.join(ex, "data_simulated_noclock.vcf.gz"),
-             os.path.join(ex, "data_simulated_noclock.raxml.bestTree"), default_w, rel_to="/root")
+    if "--skip-examples" not in sys.argv:
+        # the reference's own example inputs travel with the fixtures (the GPU box has no /root/reference):
+        # byte-for-byte copies under tests/golden/data/, and the reference is run on the copies
+        d = os.path.join(HERE, "data")
+        os.makedirs(d, exist_ok=True)
+        for tag in ("clock", "noclock"):
+            for ext in (".vcf.gz", ".raxml.bestTree"):
+                shutil.copyfile(os.path.join(ex, "data_simulated_%s%s" % (tag, ext)), os.path.join(d, "data_simulated_%s%s" % (tag, ext)))
+            run_case(ref, "example_" + tag, os.path.join(d, "data_simulated_%s.vcf.gz" % tag),
+                     os.path.join(d, "data_simulated_%s.raxml.bestTree" % tag), default_w)
+    if "--only-examples" in sys.argv:
+        return
     v, t = make_synthetic("syn_a", 12, 240, 11, FN=0.12, FP=0.01, MS=0.1, log_rates=("0.010000", "0.240000"))
     run_case(ref, "syn_a", v, t, [100, 400, 1000])
     v, t = make_synthetic("syn_b", 20, 400, 12, FN=0.2, FP=0.005, MS=0.25, with_tg=False, reads="AD", chrom_prefix="chr",
@@ -302,6 +459,10 @@ def main():
         v, t = make_synthetic("syn_d_noclock", 30, 4000, 22, FN=0.1, FP=0.005, MS=0.1, quirks=False, log_rates=("0.005000", "0.200000"),
                               rate_mult_clade=5.0)
         run_case(ref, "syn_d_noclock", v, t, default_w)
+    if "--skip-scite" not in sys.argv:
+        make_scite_and_path_cases(ref)
+    if "--skip-lrt-sweep" not in sys.argv:
+        make_lrt_sweep(ref)
     print("golden fixtures written to", HERE)
 
 

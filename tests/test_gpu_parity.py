@@ -21,7 +21,8 @@ from scsommerclock_b200 import engine, run_PT_test as P, synth
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["example_clock", "example_noclock", "syn_a", "syn_b", "syn_c", "syn_c_incl", "syn_d_clock", "syn_d_noclock", "syn_e_mismatch"]
+CASES = ["example_clock", "example_noclock", "syn_a", "syn_b", "syn_c", "syn_c_incl", "syn_d_clock", "syn_d_noclock", "syn_e_mismatch",
+         "syn_f_scite_log", "syn_g_scite_csv", "syn_h_path_rates"]
 SYN = [c for c in CASES if c.startswith("syn")]
 Y_TOL = 2e-5
 
@@ -529,8 +530,6 @@ def test_placement_on_golden_cases(ctx, name):
 def test_vcf_decode_bit_exact(ctx, name):
     g = load(name)
     vcf, tree_file, meta = case_inputs(g)
-    if not os.path.exists(vcf):
-        pytest.skip("reference example_data not present on this machine")
     muts, _, _ = P.get_mut_df(vcf, meta["exclude"], meta["include"], ctx=ctx)
     assert list(muts.columns) == list(g["samples"])
     assert np.array_equal(muts.codes, g["muts_codes"])
@@ -743,8 +742,6 @@ def test_lrt_degenerate_input_reports_failure(ctx):
 def test_run_poisson_tree_test_tsv(ctx, name, tmp_path):
     g = load(name)
     vcf, tree_file, meta = case_inputs(g)
-    if not os.path.exists(vcf):
-        pytest.skip("reference example_data not present on this machine")
     out = tmp_path / "out.tsv"
     P.run_poisson_tree_test(vcf, tree_file, str(out), [float(w) for w in g["w_maxs"]], meta["exclude"], meta["include"],
                             meta["FN_in"], meta["FP_in"])
@@ -763,7 +760,8 @@ def test_run_poisson_tree_test_tsv(ctx, name, tmp_path):
 def test_run_poisson_tree_test_batch(ctx, tmp_path):
     """A sweep of (VCF, tree) pairs through the batched path: the two example-sized pairs share a
     shape and go through ONE placement launch per pass; every TSV matches the reference's."""
-    names = ["syn_d_clock", "syn_a", "syn_d_noclock", "syn_e_mismatch"]
+    names = ["syn_d_clock", "syn_a", "syn_d_noclock", "syn_e_mismatch",
+         "syn_f_scite_log", "syn_g_scite_csv", "syn_h_path_rates"]
     gs = [load(n) for n in names]
     vcfs, trees = zip(*[case_inputs(g)[:2] for g in gs])
     outs = [str(tmp_path / (n + ".tsv")) for n in names]

@@ -12,7 +12,8 @@ from oracle import pt_oracle as O
 from scsommerclock_b200 import engine, run_PT_test as P, synth
 from scsommerclock_b200.tree import NewickError, Tree
 
-CASES = ["example_clock", "example_noclock", "syn_a", "syn_b", "syn_c", "syn_c_incl", "syn_d_clock", "syn_d_noclock", "syn_e_mismatch"]
+CASES = ["example_clock", "example_noclock", "syn_a", "syn_b", "syn_c", "syn_c_incl", "syn_d_clock", "syn_d_noclock", "syn_e_mismatch",
+         "syn_f_scite_log", "syn_g_scite_csv", "syn_h_path_rates"]
 
 
 def load(name):
@@ -76,8 +77,6 @@ def test_set_outgroup_and_delete_child_order():
 def test_read_tree_and_clade_bits_match_golden(name):
     g = load(name)
     vcf, tree_file, meta = case_inputs(g)
-    if not os.path.exists(tree_file):
-        pytest.skip("reference example_data not present on this machine")
     tree, outg, FP, FN = P.read_tree(tree_file, g["samples"])
     assert [n.name for n in tree.iter_descendants()] == list(g["node_names"])
     columns = list(g["samples"])
@@ -91,8 +90,6 @@ def test_read_tree_and_clade_bits_match_golden(name):
 def test_get_model_data_matches_golden(name):
     g = load(name)
     vcf, tree_file, meta = case_inputs(g)
-    if not os.path.exists(tree_file):
-        pytest.skip("reference example_data not present on this machine")
     for k, w in enumerate(g["w_maxs"]):
         r = O.get_gt_tree(tree_file, _mut_from_golden(g), float(w), meta["FN_in"], meta["FP_in"])   # oracle fills the node attributes
         Y, constr, init, wn, cols = P.get_model_data(r["tree"])

@@ -8,7 +8,8 @@ import pytest
 from conftest import case_inputs, golden_path
 from oracle import pt_oracle as O
 
-CASES = ["example_clock", "example_noclock", "syn_a", "syn_b", "syn_c", "syn_c_incl", "syn_d_clock", "syn_d_noclock", "syn_e_mismatch"]
+CASES = ["example_clock", "example_noclock", "syn_a", "syn_b", "syn_c", "syn_c_incl", "syn_d_clock", "syn_d_noclock", "syn_e_mismatch",
+         "syn_f_scite_log", "syn_g_scite_csv", "syn_h_path_rates"]
 SYN = [c for c in CASES if c.startswith("syn") and not c.startswith("syn_d")]
 
 
@@ -24,8 +25,6 @@ def codes(muts):
 def test_get_mut_df_bit_exact(name):
     g = load(name)
     vcf, tree, meta = case_inputs(g)
-    if not os.path.exists(vcf):
-        pytest.skip("reference example_data not present on this machine")
     m = O.get_mut_df(vcf, meta["exclude"], meta["include"])
     assert list(m["samples"]) == list(g["samples"])
     assert np.array_equal(codes(m["muts"]), g["muts_codes"])
@@ -42,8 +41,6 @@ def _mut_from_golden(g):
 def test_tree_clades_and_placement(name):
     g = load(name)
     vcf, tree, meta = case_inputs(g)
-    if not os.path.exists(tree):
-        pytest.skip("reference example_data not present on this machine")
     r = O.get_gt_tree(tree, _mut_from_golden(g), float(g["w_maxs"][0]), meta["FN_in"], meta["FP_in"])
     assert r["FP"] == float(g["FP"]) and r["FN"] == float(g["FN"])
     assert list(r["columns"]) == list(g["red_cols"])
@@ -72,8 +69,6 @@ def test_placement_literal_loop_matches_vectorised(name):
 def test_model_data_and_lrt(name):
     g = load(name)
     vcf, tree, meta = case_inputs(g)
-    if not os.path.exists(tree):
-        pytest.skip("reference example_data not present on this machine")
     mut = _mut_from_golden(g)
     ws = list(g["w_maxs"])
     if name.startswith("example") or name.startswith("syn_d"):
