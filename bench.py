@@ -64,7 +64,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-chunks", type=int, default=8, help="SNV-row chunks of the host-buffer (e2e) leg")
+    ap.add_argument("--e2e-chunks", type=int, default=0, help="SNV-row chunks of the host-buffer (e2e) leg (0: sized from the matrix, ~96 MB per chunk)")
     ap.add_argument("--algo", default="auto", choices=["auto", "gemm"],
                     help="auto: tree-shaped clade masks take the interval path (prefix counts, no GEMM); gemm: force the tcgen05 GEMM")
     ap.add_argument("--no-gemm-leg", action="store_true", help="skip the extra GEMM-path measurement of the same workload")
@@ -366,14 +366,15 @@ def main():
     stream = torch.cuda.current_stream()
 
     def place_step():
-        n_kept, miss = engine.gt_reduce(ctx, packed, pitch, n_snv, n_cols, active, True, row_keep)
-        plan.bind_genotypes(packed, pitch, row_keep, stream=stream)     # GEMM path: builds the operand plane(s); interval path: no copy
+        # row filter + per-cell missing counts + (interval path) the cell-order pass: one read of the packed matrix, counters
+        # stay on the device; GEMM path: the two reduction kernels + the operand plane(s)
+        plan.prepare(packed, pitch, active, True, stream=stream)
         plan.run(FP, FN, y_dev, stream=stream)
         sharding.allreduce_soft_weights(y_dev)
-        return n_kept, miss
 
     # ---- one untimed pass fixes the LRT model (branch order, weights) for the timed steps
-    n_kept, miss = place_step()
+    place_step()
+    n_kept, miss = plan.prepare_result(stream=stream)
     torch.cuda.synchronize()
     soft = y_dev.cpu().numpy()
     if world > 1:
@@ -411,7 +412,7 @@ def main():
         torch.cuda.synchronize()
         # host-buffer path: the packed matrix is streamed from pinned host memory in SNV-row chunks
         # (H2D of chunk c+1 under the GEMMs of chunk c), see engine.StreamingPlacement
-        streamer = engine.StreamingPlacement(ctx, n_snv, n_cols, n_rows, n_chunks=args.e2e_chunks)
+        streamer = engine.StreamingPlacement(ctx, n_snv, n_cols, n_rows, n_chunks=args.e2e_chunks or None, pitch=pitch)
         streamer.set_clades_host(bits, words)
 
     def step_e2e():
@@ -444,9 +445,9 @@ def main():
         if sampler:
             sampler.stop_flag.set()
         ms = e0.elapsed_time(e1)
-        # this library's kernels inside the timed region: plan launches (operand expansion, two GEMM
-        # passes, merge, reduce) + 2 per step in scs_gt_reduce + 1 LRT kernel per step
-        n_launch = pl.info()["launches"] - l0 + 3 * steps
+        # this library's kernels inside the timed region: plan launches (pre-pass, placement, reduce / operand expansion,
+        # two GEMM passes, merge, reduce) + 1 LRT kernel per step
+        n_launch = pl.info()["launches"] - l0 + steps
         return sharding.max_over_ranks(ms, dev), gemm, res, n_launch
 
     sampler = ClockSampler(local) if rank == 0 else None
@@ -476,8 +477,7 @@ def main():
         y_iv = y_dev.clone()
 
         def step_gemm():
-            engine.gt_reduce(ctx, packed, pitch, n_snv, n_cols, active, True, row_keep)
-            plan_g.bind_genotypes(packed, pitch, row_keep, stream=stream)
+            plan_g.prepare(packed, pitch, active, True, stream=stream)
             plan_g.run(FP, FN, y_g, stream=stream)
             sharding.allreduce_soft_weights(y_g)
             lrt.run(y_g, lrt_out, stream=stream)

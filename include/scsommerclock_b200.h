@@ -78,10 +78,11 @@ int scs_vcf_copy(scs_vcf* vcf, uint8_t* packed, int64_t* pos);
 /* get_gt_tree's filters (run_PT_test.py:350-358) on a device-resident packed
  * matrix: d_row_keep[i] = 1 when SNV i has a call in an active cell (all ones when
  * filter_rows == 0: the reference only filters when the outgroup is a column);
- * missing_frac[c] = fraction of kept SNVs where cell c is missing. */
+ * missing_frac[c] = fraction of kept SNVs where cell c is missing.  Everything (scratch reset, kernels, the
+ * read-back) is ordered on `stream`, which is synchronised before the call returns. */
 int scs_gt_reduce(scs_ctx* ctx, const uint8_t* d_gt, int64_t pitch_bytes, int64_t n_snv, int32_t n_cells,
                   const uint8_t* col_active, int32_t filter_rows, uint8_t* d_row_keep, int64_t* n_kept,
-                  double* missing_frac);
+                  double* missing_frac, void* stream);
 
 /* ---------------------------------------------------------------- placement
  * map_mutations_gt (run_PT_test.py:386-448): for every SNV, the normalised
@@ -112,6 +113,19 @@ int scs_placement_set_genotypes_host(scs_placement* plan, const uint8_t* gt, int
  * like scs_placement_set_genotypes. */
 int scs_placement_bind_genotypes(scs_placement* plan, const uint8_t* d_gt, int64_t pitch_bytes,
                                  const uint8_t* d_row_keep, void* stream);
+/* get_gt_tree's filters (run_PT_test.py:350-358) and the plan's own genotype set-up in one call, for a plan whose
+ * clades are set: d_row_keep / n_kept / missing_frac as scs_gt_reduce computes them (col_active: host, [n_cells]
+ * bytes; filter_rows as there), kept in the plan, followed by what scs_placement_bind_genotypes would do.  On the
+ * interval path all of it is ONE pass over d_gt (row flags, per-cell missing counts and the rows rewritten in the
+ * plan's depth-first cell order come out of the same read); on the GEMM path it is the reduction kernels plus the
+ * operand planes.  Asynchronous on `stream`, no host synchronisation: the counters stay on the device until
+ * scs_placement_prepare_result.  accumulate != 0 adds to the counters of the previous prepare calls instead of
+ * starting from zero (a matrix walked in SNV-row chunks through one chunk-sized plan).  d_gt must stay alive and
+ * unchanged until the run that uses it has finished.  Plans holding several groups get the totals over all groups. */
+int scs_placement_prepare(scs_placement* plan, const uint8_t* d_gt, int64_t pitch_bytes, const uint8_t* col_active,
+                          int32_t filter_rows, int32_t accumulate, void* stream);
+/* Waits for `stream`, then: *n_kept = SNVs kept so far, missing_frac[c] = fraction of them where cell c is missing. */
+int scs_placement_prepare_result(scs_placement* plan, int64_t* n_kept, double* missing_frac, void* stream);
 /* d_bits: clade membership bit mask [n_rows][pitch_words] of uint32, bit c%32 of
  * word c/32 set when cell c descends from the node (S, run_PT_test.py:389-397).
  * The masks also decide HOW the counts S x genotypes are formed: the clades of a tree are a
@@ -182,8 +196,11 @@ int scs_branch_weights(scs_ctx* ctx, const uint32_t* clade_bits, int64_t pitch_w
  * [br_off[p], br_off[p+1]) of Y / w / child_int.  Branch k hangs below internal
  * node k/2 (get_model_data's order, run_PT_test.py:569-622); child_int[k] is the
  * internal node below it, or -1 for a leaf.  out[p][8] = {-2logLR, dof, on_bound,
- * p-value, ll_H0, ll_H1, Newton iterations, status (0 = converged)}; x_out
- * (optional, may be NULL) receives the fitted branch lengths. */
+ * p-value, ll_H0, ll_H1, Newton iterations, status}; x_out (optional, may be NULL) receives the fitted
+ * branch lengths.  status: 0 converged; 1 iteration limit; 2 degenerate input (the reference's scale_fac is 0 or
+ * there are no counts); 3 numerical breakdown of the Newton system; 4 ll_H1 < 0 -- the reference's scale_fac is
+ * negative there and its minimiser runs on a sign-flipped objective, so no meaningful value exists to reproduce.
+ * Every non-zero status comes with NaN in the first five fields (the reference's failure tuple, :678). */
 int scs_lrt_poisson_batch(scs_ctx* ctx, int32_t n_prob, const int64_t* br_off, const double* Y, const double* w,
                           const int32_t* child_int, double* out, double* x_out);
 /* The same batch as a reusable, device-resident plan (topology and workspace are

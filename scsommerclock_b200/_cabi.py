@@ -37,6 +37,8 @@ _SIGNATURES = {
     "scs_placement_set_genotypes_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "scs_clade_intervals": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scs_placement_bind_genotypes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "scs_placement_prepare": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "scs_placement_prepare_result": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p]),
     "scs_placement_set_clades": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "scs_placement_set_clades_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "scs_placement_run": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
@@ -54,7 +56,7 @@ _SIGNATURES = {
     "scs_vcf_device_genotypes": (C.c_void_p, [C.c_void_p]),
     "scs_vcf_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "scs_gt_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int32,
-                                C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
+                                C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p]),
     "scs_branch_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_double,
                                      C.c_double, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
     "scs_lrt_poisson_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

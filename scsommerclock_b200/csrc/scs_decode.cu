@@ -550,6 +550,68 @@ scs_gt_reduce_narrow_kernel(const uint8_t* __restrict__ gt, int64_t pitch, int64
     if (threadIdx.x == 0 && s_kept) atomicAdd(n_kept, (unsigned long long)s_kept);     // integers: order-independent
 }
 
+// ---- row filter + per-cell missing counts, split into an asynchronous launch and a fetch so that the placement
+// plan (scs_placement_prepare, scs_place.cu) can run them on its own counters without a host round trip per call.
+// scratch layout: [kept counter (8 B, padded to 16)] [active mask words] [missing counters x MISS_REPL]
+size_t gt_reduce_scratch_bytes(int n_cells) {
+    const int n_words = (n_cells + 15) / 16;
+    return 16 + size_t(n_words + 3) / 4 * 16 + size_t(n_cells) * 4 * MISS_REPL;
+}
+
+int gt_reduce_launch(scs_ctx* ctx, const uint8_t* d_gt, int64_t pitch_bytes, int64_t n_snv, int n_cells, const uint8_t* col_active,
+                     int filter_rows, uint8_t* d_row_keep, uint8_t* sc, bool accumulate, cudaStream_t st) {
+    const int n_words = (n_cells + 15) / 16;
+    const size_t off_mask = 16, off_miss = off_mask + size_t(n_words + 3) / 4 * 16;
+    const size_t bytes = gt_reduce_scratch_bytes(n_cells);
+    unsigned long long* d_kept = reinterpret_cast<unsigned long long*>(sc);
+    uint32_t* d_act = reinterpret_cast<uint32_t*>(sc + off_mask);
+    unsigned int* d_miss = reinterpret_cast<unsigned int*>(sc + off_miss);
+    if (!accumulate) {
+        // active cells as a mask over the low bit of every 2-bit code
+        std::vector<uint32_t> amask(n_words, 0u);
+        for (int c = 0; c < n_cells; ++c)
+            if (col_active[c]) amask[c >> 4] |= 1u << (2 * (c & 15));
+        SCS_CUDA(cudaMemsetAsync(sc, 0, bytes, st));
+        SCS_CUDA(cudaMemcpyAsync(d_act, amask.data(), size_t(n_words) * 4, cudaMemcpyHostToDevice, st));   // (pageable source: staged before the call returns)
+    }
+    if (n_snv > 0) {
+        if (n_words <= 32) {
+            int shift = 0;
+            while ((1 << shift) < n_words) ++shift;
+            const int64_t want = (n_snv * (int64_t(1) << shift) + 255) / 256;
+            const unsigned grid = unsigned(std::min<int64_t>(std::max<int64_t>(want, 1), int64_t(ctx->sm_count) * 4));
+            scs_gt_reduce_narrow_kernel<<<grid, 256, 0, st>>>(d_gt, pitch_bytes, n_snv, n_words, shift, n_cells, d_act, filter_rows, d_row_keep, d_kept, d_miss);
+        } else {
+            scs_row_keep_kernel<<<unsigned((n_snv * 32 + 255) / 256), 256, 0, st>>>(d_gt, pitch_bytes, n_snv, n_words, 32, d_act, filter_rows, d_row_keep, d_kept);
+            // 32..256 rows per thread: at least ~2 blocks per SM on small inputs, few atomics on big ones
+            const unsigned gx = unsigned((n_words + 63) / 64);
+            const int64_t per_thread = std::max<int64_t>(32, std::min<int64_t>(256, n_snv / (int64_t(ctx->sm_count) * 2 * MISS_SLABS)));
+            const int64_t gy = std::max<int64_t>(1, (n_snv + per_thread * MISS_SLABS - 1) / (per_thread * MISS_SLABS));
+            dim3 grid(gx, unsigned(std::min<int64_t>(gy, 65535))), block(64, MISS_SLABS);
+            scs_missing_count_kernel<<<grid, block, 0, st>>>(d_gt, pitch_bytes, n_snv, n_cells, n_words, d_row_keep, d_miss);
+        }
+    }
+    SCS_CUDA(cudaGetLastError());
+    return SCS_OK;
+}
+
+int gt_reduce_fetch(const uint8_t* sc, int n_cells, int64_t* n_kept, double* missing_frac, cudaStream_t st) {
+    const int n_words = (n_cells + 15) / 16;
+    const size_t off_miss = 16 + size_t(n_words + 3) / 4 * 16;
+    std::vector<unsigned int> miss(size_t(n_cells) * MISS_REPL);
+    unsigned long long kept = 0;
+    SCS_CUDA(cudaMemcpyAsync(&kept, sc, sizeof(kept), cudaMemcpyDeviceToHost, st));
+    SCS_CUDA(cudaMemcpyAsync(miss.data(), sc + off_miss, miss.size() * 4, cudaMemcpyDeviceToHost, st));
+    SCS_CUDA(cudaStreamSynchronize(st));
+    *n_kept = int64_t(kept);
+    for (int c = 0; c < n_cells; ++c) {
+        unsigned long long m = 0;
+        for (int rep = 0; rep < MISS_REPL; ++rep) m += miss[size_t(rep) * n_cells + c];
+        missing_frac[c] = kept > 0 ? double(m) / double(kept) : 0.0;
+    }
+    return SCS_OK;
+}
+
 struct Vcf {
     scs_ctx* ctx = nullptr;
     int64_t n_lines = 0, n_kept = 0, n_noalt = 0, n_filtered = 0;
@@ -724,54 +786,16 @@ int scs_vcf_copy(scs_vcf* h, uint8_t* packed, int64_t* pos) {
 }
 
 int scs_gt_reduce(scs_ctx* ctx, const uint8_t* d_gt, int64_t pitch_bytes, int64_t n_snv, int32_t n_cells, const uint8_t* col_active,
-                  int32_t filter_rows, uint8_t* d_row_keep, int64_t* n_kept, double* missing_frac) {
+                  int32_t filter_rows, uint8_t* d_row_keep, int64_t* n_kept, double* missing_frac, void* stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (!ctx || !d_gt || !col_active || !d_row_keep || !n_kept || !missing_frac) return set_error(SCS_ERR_ARG, "null argument");
     if ((pitch_bytes & 3) || pitch_bytes * 4 < n_cells) return set_error(SCS_ERR_ARG, "packed genotype pitch %lld must be a multiple of 4 and cover %d cells", (long long)pitch_bytes, n_cells);
     SCS_CUDA(cudaSetDevice(ctx->device));
-    // scratch layout: [kept counter (8 B, padded to 16)] [active mask words] [missing counters]
-    const int n_words = (n_cells + 15) / 16;
-    const size_t off_mask = 16, off_miss = off_mask + size_t(n_words + 3) / 4 * 16;
-    const size_t bytes = off_miss + size_t(n_cells) * 4 * MISS_REPL;
-    uint8_t* sc = static_cast<uint8_t*>(ctx_scratch(ctx, bytes));
+    uint8_t* sc = static_cast<uint8_t*>(ctx_scratch(ctx, gt_reduce_scratch_bytes(n_cells)));
     if (!sc) return set_error(SCS_ERR_OOM, "device scratch allocation failed");
-    unsigned long long* d_kept = reinterpret_cast<unsigned long long*>(sc);
-    uint32_t* d_act = reinterpret_cast<uint32_t*>(sc + off_mask);
-    unsigned int* d_miss = reinterpret_cast<unsigned int*>(sc + off_miss);
-    // active cells as a mask over the low bit of every 2-bit code
-    std::vector<uint32_t> amask(n_words, 0u);
-    for (int c = 0; c < n_cells; ++c)
-        if (col_active[c]) amask[c >> 4] |= 1u << (2 * (c & 15));
-    SCS_CUDA(cudaMemsetAsync(sc, 0, bytes, 0));
-    SCS_CUDA(cudaMemcpyAsync(d_act, amask.data(), size_t(n_words) * 4, cudaMemcpyHostToDevice, 0));
-    if (n_snv > 0) {
-        if (n_words <= 32) {
-            int shift = 0;
-            while ((1 << shift) < n_words) ++shift;
-            const int64_t want = (n_snv * (int64_t(1) << shift) + 255) / 256;
-            const unsigned grid = unsigned(std::min<int64_t>(std::max<int64_t>(want, 1), int64_t(ctx->sm_count) * 4));
-            scs_gt_reduce_narrow_kernel<<<grid, 256>>>(d_gt, pitch_bytes, n_snv, n_words, shift, n_cells, d_act, filter_rows, d_row_keep, d_kept, d_miss);
-        } else {
-            scs_row_keep_kernel<<<unsigned((n_snv * 32 + 255) / 256), 256>>>(d_gt, pitch_bytes, n_snv, n_words, 32, d_act, filter_rows, d_row_keep, d_kept);
-            // 32..256 rows per thread: at least ~2 blocks per SM on small inputs, few atomics on big ones
-            const unsigned gx = unsigned((n_words + 63) / 64);
-            const int64_t per_thread = std::max<int64_t>(32, std::min<int64_t>(256, n_snv / (int64_t(ctx->sm_count) * 2 * MISS_SLABS)));
-            const int64_t gy = std::max<int64_t>(1, (n_snv + per_thread * MISS_SLABS - 1) / (per_thread * MISS_SLABS));
-            dim3 grid(gx, unsigned(std::min<int64_t>(gy, 65535))), block(64, MISS_SLABS);
-            scs_missing_count_kernel<<<grid, block>>>(d_gt, pitch_bytes, n_snv, n_cells, n_words, d_row_keep, d_miss);
-        }
-    }
-    SCS_CUDA(cudaGetLastError());
-    std::vector<unsigned int> miss(size_t(n_cells) * MISS_REPL);
-    unsigned long long kept = 0;
-    SCS_CUDA(cudaMemcpy(&kept, d_kept, sizeof(kept), cudaMemcpyDeviceToHost));
-    SCS_CUDA(cudaMemcpy(miss.data(), d_miss, miss.size() * 4, cudaMemcpyDeviceToHost));
-    *n_kept = int64_t(kept);
-    for (int c = 0; c < n_cells; ++c) {
-        unsigned long long m = 0;
-        for (int rep = 0; rep < MISS_REPL; ++rep) m += miss[size_t(rep) * n_cells + c];
-        missing_frac[c] = kept > 0 ? double(m) / double(kept) : 0.0;
-    }
-    return SCS_OK;
+    int rc = gt_reduce_launch(ctx, d_gt, pitch_bytes, n_snv, n_cells, col_active, filter_rows, d_row_keep, sc, false, st);
+    if (rc != SCS_OK) return rc;
+    return gt_reduce_fetch(sc, n_cells, n_kept, missing_frac, st);
 }
 
 }  // extern "C"

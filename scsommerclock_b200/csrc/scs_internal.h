@@ -28,6 +28,15 @@ namespace scs {
 int set_error(int code, const char* fmt, ...);
 }  // namespace scs
 
+namespace scs {
+// Row filter + per-cell missing counts (scs_decode.cu) as an asynchronous launch on caller-owned counters plus a
+// fetch: what scs_gt_reduce does in one call, and what scs_placement_prepare falls back to on the GEMM path.
+size_t gt_reduce_scratch_bytes(int n_cells);
+int gt_reduce_launch(scs_ctx* ctx, const uint8_t* d_gt, int64_t pitch_bytes, int64_t n_snv, int n_cells, const uint8_t* col_active,
+                     int filter_rows, uint8_t* d_row_keep, uint8_t* scratch, bool accumulate, cudaStream_t st);
+int gt_reduce_fetch(const uint8_t* scratch, int n_cells, int64_t* n_kept, double* missing_frac, cudaStream_t st);
+}  // namespace scs
+
 #define SCS_CUDA(expr)                                                                         \
     do {                                                                                       \
         cudaError_t _e = (expr);                                                               \

@@ -211,6 +211,19 @@ scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ 
         }
         return;
     }
+    if (sf < 0.0) {
+        // ll_H1 < 0 (very sparse counts, most Y < e): the reference's scale_fac = (ll_H1 // 10000) * 10000 = -10000 flips
+        // the sign of its objective, so its "minimize" call MAXIMISES the negative log-likelihood and returns whatever
+        // vertex of the feasible polytope trust-constr stops at (LR in the hundreds or thousands for a 30-leaf tree,
+        // tests/golden/lrt_sweep.npz holds examples).  That number is an accident of the optimiser, not a statistic: it
+        // is reported as a failure with its own status instead of being imitated or silently "converged".
+        if (tid == 0) {
+            for (int i = 0; i < 7; ++i) res[i] = NAN;
+            res[5] = ll_H1;
+            res[7] = 4.0;
+        }
+        return;
+    }
 
     // ---- topology: up-branch of every internal node, levels, level order.  All of it in parallel:
     // with 10,000-leaf trees the obvious thread-0 loops were 5 of the kernel's 7 ms.
@@ -366,8 +379,8 @@ scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ 
             }
         }
         grp_reduce2<WARP, true>(dec, amax, sh);
-        if (!(dec == dec)) {
-            status = 3;   // NaN in the Newton system
+        if (!(dec == dec) || dec < -1e-9 * fmax(1.0, fabs(f0))) {
+            status = 3;   // NaN in the Newton system, or an ascent direction (the barrier objective is convex: cannot happen in exact arithmetic)
             break;
         }
         // Newton converges quadratically: once the decrement (~ twice the distance to the optimum

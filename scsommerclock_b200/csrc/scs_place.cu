@@ -1185,6 +1185,7 @@ __global__ void scs_reduce_colpart_kernel(const float* __restrict__ colpart, con
 
 }  // namespace scs
 #include "scs_place_interval.cuh"
+#include "scs_place_iv4.cuh"
 namespace scs {
 
 // ---------------------------------------------------------------- host side
@@ -1322,6 +1323,12 @@ struct Placement {
     int iv_threads = 0, iv_grid = 0, iv_rows_per_run = 0, iv_runs = 0;
     bool iv_dcache = false, iv_perm_smem = false;
     size_t iv_smem = 0;
+    int iv4_np = 0;                // variant 4 (scs_place_iv4.cuh): pairs of non-leaf rows per thread
+    // ---- scs_placement_prepare: row filter + missing counts (+ cell-order pass) with the counters kept on the device
+    std::vector<uint16_t> h_perm;  // host copy of the cell order (positions -> cells)
+    uint8_t* d_prep = nullptr;     // mode 1: [kept u64 | pad][active mask, rw words (16-byte padded)][missing per POSITION, 16 rw u32]
+    size_t d_prep_bytes = 0;       // mode 2: the scratch layout of gt_reduce_launch (scs_decode.cu)
+    int prep_mode = 0;             // 0: nothing prepared yet
 };
 
 // Radix packing is the default wherever it applies (<= 15,872 cells); its integer exactness is
@@ -1557,6 +1564,7 @@ int scs_placement_destroy(scs_placement* h) {
     cudaFree(pl->d_leafmask);
     cudaFree(pl->gt_perm);
     cudaFree(pl->ipart);
+    cudaFree(pl->d_prep);
     cudaFree(pl->colpart);
     cudaFree(pl->y);
     cudaFree(pl->row_keep);
@@ -1679,7 +1687,7 @@ static int choose_algo(Placement* pl, const uint32_t* bits, int64_t pitch_words,
     // bound, cost proportional to the clade rows like the interval path's but with a smaller constant -- is 1.9x
     // faster (0.98 against 1.86 ms).  "auto" therefore takes the interval path from the GEMM's own regime change on
     // (more than one K chunk: > 3968 cells); SCS_PLACE_ALGO=interval takes it for every tree-shaped matrix.
-    const bool forced = e && (!strcmp(e, "interval") || !strcmp(e, "interval1"));
+    const bool forced = e && (!strcmp(e, "interval") || !strcmp(e, "interval1") || !strcmp(e, "interval3"));
     if (!forced && pl->n_cells <= RADIX_KB_PER_CHUNK * BLOCK_K) return SCS_OK;
     const size_t SMEM_MAX = 227 * 1024;
     // cheapest test first: does even the smallest working set (prefix counts + accumulators) fit shared memory?
@@ -1758,13 +1766,34 @@ static int choose_algo(Placement* pl, const uint32_t* bits, int64_t pitch_words,
         pl->iv_leaf_pos = n_leaf_pos;
         pl->iv_stride = leaf_off + 16 * rw;
         pl->iv_leaf_off = leaf_off;
-        smem = interval3_smem_bytes(n_cells, n_slots3);
-        if (threads <= 640) {
-            cudaFuncSetAttribute(scs_place_interval3_kernel<640, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scs_place_interval3_kernel<640, 2>, threads, smem);
-        } else {
-            cudaFuncSetAttribute(scs_place_interval3_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scs_place_interval3_kernel<1024, 1>, threads, smem);
+        // variant 4 (scs_place_iv4.cuh: the same tables, every per-row quantity in registers) when the shape allows:
+        // one thread per word of a permuted row, at most 8 pairs of non-leaf rows per thread, at most 640 threads
+        pl->iv4_np = 0;
+        if (!(e && !strcmp(e, "interval3")) && n_slots3 >= 2) {
+            const int n_pairs = n_slots3 / 2;
+            int t4 = std::max(rw32, (((n_pairs + IV4_MAX_NP - 1) / IV4_MAX_NP) + 31) / 32 * 32);
+            if (const char* tt = getenv("SCS_IV_THREADS")) t4 = std::max(t4, std::min(1024, atoi(tt) / 32 * 32));
+            const int np = (n_pairs + t4 - 1) / t4;
+            if (t4 <= IV4_MAX_THREADS && np >= 1 && np <= IV4_MAX_NP && iv4_smem_bytes(rw, t4) <= SMEM_MAX) {
+                const int occ = iv4_occupancy(np, t4, iv4_smem_bytes(rw, t4));
+                if (occ > 0) {
+                    pl->iv4_np = np;
+                    threads = t4;
+                    smem = iv4_smem_bytes(rw, t4);
+                    per_sm = occ;
+                    pl->iv_variant = 4;
+                }
+            }
+        }
+        if (pl->iv4_np == 0) {
+            smem = interval3_smem_bytes(n_cells, n_slots3);
+            if (threads <= 640) {
+                cudaFuncSetAttribute(scs_place_interval3_kernel<640, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scs_place_interval3_kernel<640, 2>, threads, smem);
+            } else {
+                cudaFuncSetAttribute(scs_place_interval3_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scs_place_interval3_kernel<1024, 1>, threads, smem);
+            }
         }
     } else {
         // ---- variant 1: every row through the sweeps, counts recomputed in the second sweep
@@ -1798,6 +1827,8 @@ static int choose_algo(Placement* pl, const uint32_t* bits, int64_t pitch_words,
     if (cudaMalloc(&pl->d_perm, size_t(n_cells) * sizeof(uint16_t)) != cudaSuccess ||
         cudaMalloc(&pl->d_slot_row, slot_row.size() * sizeof(int)) != cudaSuccess)
         return set_error(SCS_ERR_OOM, "device allocation failed");
+    pl->h_perm = perm;
+    pl->prep_mode = 0;
     SCS_CUDA(cudaMemcpyAsync(pl->d_perm, perm.data(), perm.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
     SCS_CUDA(cudaMemcpyAsync(pl->d_slot_row, slot_row.data(), slot_row.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     SCS_CUDA(cudaStreamSynchronize(st));          // the host vectors are stack-local
@@ -1936,6 +1967,91 @@ static void choose_pass2_mode(Placement* pl) {
     pl->pass2_mode = 2;
 }
 
+// get_gt_tree's filters (run_PT_test.py:350-358) for a plan whose clades are set, asynchronous on `stream`, counters on
+// the device.  Interval path (variants 3 / 4): ONE kernel reads the caller's matrix once and produces the row flags, the
+// missing counts and the rows in depth-first cell order (scs_permute_reduce_kernel).  GEMM path / variant 1: the two
+// reduction kernels of scs_gt_reduce, then the operand planes.
+int scs_placement_prepare(scs_placement* h, const uint8_t* d_gt, int64_t pitch_bytes, const uint8_t* col_active, int32_t filter_rows,
+                          int32_t accumulate, void* stream) {
+    Placement* pl = reinterpret_cast<Placement*>(h);
+    if (!pl || !d_gt || !col_active) return set_error(SCS_ERR_ARG, "null argument");
+    if (pl->algo == 0) return set_error(SCS_ERR_ARG, "scs_placement_prepare before scs_placement_set_clades");
+    if (pitch_bytes < (pl->n_cells + 3) / 4) return set_error(SCS_ERR_ARG, "genotype row pitch %lld is smaller than ceil(n_cells/4)", (long long)pitch_bytes);
+    if ((pitch_bytes & 3) || (reinterpret_cast<uintptr_t>(d_gt) & 3)) return set_error(SCS_ERR_ARG, "packed genotype rows must be 4-byte aligned (pitch %lld)", (long long)pitch_bytes);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int n_cells = pl->n_cells, rw = (n_cells + 15) / 16;
+    const bool fused = pl->algo == 2 && pl->iv_variant >= 3;
+    const int mode = fused ? 1 : 2;
+    if (accumulate && pl->prep_mode != mode) return set_error(SCS_ERR_ARG, "scs_placement_prepare: nothing to accumulate onto");
+    const size_t off_mask = 16, off_miss = off_mask + size_t(rw + 3) / 4 * 16;
+    const size_t need = fused ? off_miss + size_t(16) * rw * sizeof(uint32_t) : gt_reduce_scratch_bytes(n_cells);
+    if (need > pl->d_prep_bytes) {
+        if (accumulate) return set_error(SCS_ERR_ARG, "scs_placement_prepare: counter buffer changed size while accumulating");
+        cudaFree(pl->d_prep);
+        pl->d_prep = nullptr;
+        pl->d_prep_bytes = 0;
+        if (cudaMalloc(&pl->d_prep, need) != cudaSuccess) return set_error(SCS_ERR_OOM, "device allocation of %zu bytes failed", need);
+        pl->d_prep_bytes = need;
+    }
+    pl->prep_mode = mode;
+    if (!fused) {
+        int rc = gt_reduce_launch(pl->ctx, d_gt, pitch_bytes, pl->n_snv, n_cells, col_active, filter_rows, pl->row_keep, pl->d_prep, accumulate != 0, st);
+        if (rc != SCS_OK) return rc;
+        pl->launches += rw <= 32 ? 1 : 2;
+        rc = set_genotypes_impl(pl, d_gt, pitch_bytes, nullptr, st, true);
+        pl->have_row_keep = true;
+        return rc;
+    }
+    if (!accumulate) {
+        std::vector<uint32_t> amask(size_t(rw), 0u);      // active cells (source column order): low bit of every 2-bit code
+        for (int c = 0; c < n_cells; ++c)
+            if (col_active[c]) amask[size_t(c >> 4)] |= 1u << (2 * (c & 15));
+        SCS_CUDA(cudaMemsetAsync(pl->d_prep, 0, need, st));
+        SCS_CUDA(cudaMemcpyAsync(pl->d_prep + off_mask, amask.data(), size_t(rw) * 4, cudaMemcpyHostToDevice, st));   // (pageable: staged before the call returns)
+    }
+    const size_t bytes = size_t(pl->n_snv) * rw * sizeof(uint32_t);
+    if (bytes > pl->gt_perm_bytes) {
+        cudaFree(pl->gt_perm);
+        pl->gt_perm = nullptr;
+        pl->gt_perm_bytes = 0;
+        if (cudaMalloc(&pl->gt_perm, bytes) != cudaSuccess) return set_error(SCS_ERR_OOM, "device allocation of %zu bytes failed", bytes);
+        pl->gt_perm_bytes = bytes;
+    }
+    const int pt = (rw + 31) / 32 * 32;
+    const unsigned pgrid = unsigned(std::min<int64_t>(pl->n_snv, int64_t(pl->ctx->sm_count) * std::max(1, 2048 / pt)));
+    scs_permute_reduce_kernel<<<pgrid, pt, 2 * rw * sizeof(uint32_t), st>>>(
+        d_gt, pitch_bytes, pl->n_snv, n_cells, rw, pl->d_perm, reinterpret_cast<const uint32_t*>(pl->d_prep + off_mask), filter_rows,
+        pl->gt_perm, pl->row_keep, reinterpret_cast<unsigned long long*>(pl->d_prep), reinterpret_cast<unsigned int*>(pl->d_prep + off_miss));
+    SCS_CUDA(cudaGetLastError());
+    pl->launches++;
+    pl->operands_valid = false;
+    pl->gt_src = d_gt;             // bound: a later switch to general clade masks builds the GEMM operands from it
+    pl->gt_pitch = pitch_bytes;
+    pl->gt_perm_valid = true;
+    pl->have_row_keep = true;
+    return SCS_OK;
+}
+
+// Waits for the prepare call(s) on `stream` and returns the kept-SNV count and, per cell (column), the fraction of kept
+// SNVs where the cell is missing.
+int scs_placement_prepare_result(scs_placement* h, int64_t* n_kept, double* missing_frac, void* stream) {
+    Placement* pl = reinterpret_cast<Placement*>(h);
+    if (!pl || !n_kept || !missing_frac) return set_error(SCS_ERR_ARG, "null argument");
+    if (pl->prep_mode == 0) return set_error(SCS_ERR_ARG, "scs_placement_prepare_result before scs_placement_prepare");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int n_cells = pl->n_cells, rw = (n_cells + 15) / 16;
+    if (pl->prep_mode == 2) return gt_reduce_fetch(pl->d_prep, n_cells, n_kept, missing_frac, st);
+    const size_t off_miss = 16 + size_t(rw + 3) / 4 * 16;
+    std::vector<unsigned int> miss(size_t(16) * rw);
+    unsigned long long kept = 0;
+    SCS_CUDA(cudaMemcpyAsync(&kept, pl->d_prep, sizeof(kept), cudaMemcpyDeviceToHost, st));
+    SCS_CUDA(cudaMemcpyAsync(miss.data(), pl->d_prep + off_miss, miss.size() * 4, cudaMemcpyDeviceToHost, st));
+    SCS_CUDA(cudaStreamSynchronize(st));
+    *n_kept = int64_t(kept);
+    for (int k = 0; k < n_cells; ++k) missing_frac[pl->h_perm[size_t(k)]] = kept > 0 ? double(miss[size_t(k)]) / double(kept) : 0.0;
+    return SCS_OK;
+}
+
 // FP / FN: one value per group (per dataset).
 int scs_placement_run_batch(scs_placement* h, const double* FP, const double* FN, double* d_soft_weights, void* stream) {
     Placement* pl = reinterpret_cast<Placement*>(h);
@@ -1971,7 +2087,7 @@ int scs_placement_run_batch(scs_placement* h, const double* FP, const double* FN
         ip.perm_smem = pl->iv_perm_smem ? 1 : 0;
         double* y = d_soft_weights ? d_soft_weights : pl->y;
         cudaEventRecord(pl->ev[0], st);
-        if (pl->iv_variant == 3) {
+        if (pl->iv_variant >= 3) {
             const int rw = ip.row_words;
             if (!pl->gt_perm_valid) {
                 // the rows in depth-first cell order (one streaming pass; the walk below then works on whole words)
@@ -2001,7 +2117,25 @@ int scs_placement_run_batch(scs_placement* h, const double* FP, const double* FN
             q.n_leaf_pos = pl->iv_leaf_pos;
             q.part_stride = pl->iv_stride;
             q.leaf_off = pl->iv_leaf_off;
-            if (pl->iv_threads <= 640) scs_place_interval3_kernel<640, 2><<<pl->iv_grid, pl->iv_threads, pl->iv_smem, st>>>(q);
+            if (pl->iv_variant == 4) {
+                Iv4Params q4;
+                q4.gt = pl->gt_perm;
+                q4.n_snv = pl->n_snv;
+                q4.rw = rw;
+                q4.n_pairs = pl->iv_slots / 2;
+                q4.pad_pair = (pl->iv_nodes & 1) ? pl->iv_slots / 2 - 1 : -1;
+                q4.off4 = pl->d_off4;
+                q4.leafmask = pl->d_leafmask;
+                q4.n_leaf_pos = pl->iv_leaf_pos;
+                q4.row_keep = ip.row_keep;
+                q4.gconst = pl->d_gconst;
+                q4.part = pl->ipart;
+                q4.part_stride = pl->iv_stride;
+                q4.leaf_off = pl->iv_leaf_off;
+                q4.rows_per_run = pl->iv_rows_per_run;
+                q4.num_runs = pl->iv_runs;
+                iv4_launch(pl->iv4_np, q4, pl->iv_grid, pl->iv_threads, pl->iv_smem, st);
+            } else if (pl->iv_threads <= 640) scs_place_interval3_kernel<640, 2><<<pl->iv_grid, pl->iv_threads, pl->iv_smem, st>>>(q);
             else scs_place_interval3_kernel<1024, 1><<<pl->iv_grid, pl->iv_threads, pl->iv_smem, st>>>(q);
         } else {
             cudaEventRecord(pl->ev[1], st);

@@ -319,6 +319,92 @@ __global__ void scs_permute_cells_kernel(const uint8_t* __restrict__ gt, long lo
     }
 }
 
+// The pre-pass of a plan on the interval path, fused: ONE read of the caller's packed matrix gives (1) the rows in
+// depth-first cell order (as scs_permute_cells_kernel), (2) the row filter of get_gt_tree (run_PT_test.py:352: an SNV
+// stays when an active -- non-outgroup -- cell carries a call) and (3) the per-cell missing counts over the kept rows
+// (:358), which used to be three passes over 2.5 GB.  The row's barrier doubles as the block-wide OR of "has a call";
+// missing counts are sixteen byte-wide SWAR counters per thread over its OUTPUT positions (flushed every 255 kept rows),
+// added to missing_pos[position] once per CTA; the host maps positions back to cells.
+__global__ void scs_permute_reduce_kernel(const uint8_t* __restrict__ gt, long long pitch, long long n_snv, int n_cells, int row_words,
+                                          const uint16_t* __restrict__ perm, const uint32_t* __restrict__ active_mask, int filter_rows,
+                                          uint32_t* __restrict__ out, uint8_t* __restrict__ row_keep,
+                                          unsigned long long* __restrict__ n_kept, unsigned int* __restrict__ missing_pos) {
+    extern __shared__ uint32_t pm_smem[];          // two row buffers
+    const int t = threadIdx.x;
+    const bool own = t < row_words;
+    uint32_t cols[8];
+    uint32_t valid = 0u;                           // bit 2e: output position 16 t + e is a cell
+#pragma unroll
+    for (int e = 0; e < 16; e += 2) {
+        const int k = 16 * t + e;
+        const uint32_t c0 = (own && k < n_cells) ? perm[k] : 0xFFFFu, c1 = (own && k + 1 < n_cells) ? perm[k + 1] : 0xFFFFu;
+        cols[e >> 1] = c0 | (c1 << 16);
+        if (own && k < n_cells) valid |= 1u << (2 * e);
+        if (own && k + 1 < n_cells) valid |= 1u << (2 * e + 2);
+    }
+    const uint32_t am = own ? active_mask[t] : 0u;
+    unsigned int total[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) total[k] = 0u;
+    uint32_t a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;
+    int pending = 0;
+    unsigned int kept_cnt = 0u;
+    auto flush = [&]() {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {              // byte b of accumulator q holds position 4 b + q
+            total[4 * b + 0] += (a0 >> (8 * b)) & 0xFFu;
+            total[4 * b + 1] += (a1 >> (8 * b)) & 0xFFu;
+            total[4 * b + 2] += (a2 >> (8 * b)) & 0xFFu;
+            total[4 * b + 3] += (a3 >> (8 * b)) & 0xFFu;
+        }
+        a0 = a1 = a2 = a3 = 0u;
+        pending = 0;
+    };
+    int buf = 0;
+    uint32_t w_next = (own && blockIdx.x < n_snv) ? reinterpret_cast<const uint32_t*>(gt + size_t(blockIdx.x) * pitch)[t] : 0u;
+    for (long long r = blockIdx.x; r < n_snv; r += gridDim.x, buf ^= 1) {
+        uint32_t* rb = pm_smem + buf * row_words;
+        const uint32_t ws = w_next;
+        if (own) {
+            rb[t] = ws;
+            if (r + gridDim.x < n_snv) w_next = reinterpret_cast<const uint32_t*>(gt + size_t(r + gridDim.x) * pitch)[t];
+        }
+        // a cell holds 1 or 2 exactly when its two bits differ (the mask keeps the low bit of the active cells only)
+        const int has_call = (((ws ^ (ws >> 1)) & am) != 0u) ? 1 : 0;
+        const int keep = __syncthreads_or(has_call) || !filter_rows;      // also the barrier between filling and gathering the row
+        if (own) {
+            const uint8_t* rb8 = reinterpret_cast<const uint8_t*>(rb);
+            uint32_t w = 0u;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const uint32_t col = (cols[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu;
+                const uint32_t code = col == 0xFFFFu ? 3u : ((uint32_t(rb8[col >> 2]) >> ((col & 3) * 2)) & 3u);
+                w |= code << (2 * e);
+            }
+            out[size_t(r) * row_words + t] = w;
+            if (keep) {
+                const uint32_t m = w & (w >> 1) & valid;          // bit 2e set <=> position e missing
+                a0 += m & 0x01010101u;
+                a1 += (m >> 2) & 0x01010101u;
+                a2 += (m >> 4) & 0x01010101u;
+                a3 += (m >> 6) & 0x01010101u;
+            }
+        }
+        if (keep) {                                               // (uniform over the block)
+            if (++pending == 255) flush();
+            ++kept_cnt;
+        }
+        if (t == 0) row_keep[r] = uint8_t(keep);
+    }
+    flush();
+    if (own) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            if (total[k]) atomicAdd(&missing_pos[16 * t + k], total[k]);
+    }
+    if (t == 0 && kept_cnt) atomicAdd(n_kept, (unsigned long long)kept_cnt);
+}
+
 // MAXT: largest CTA this instantiation is launched with (register budget); UNR: unroll factor of the three sweeps.
 // At 10k cells the CTA has 640 threads (one per word): 96 registers per thread are available, and two pairs of rows in
 // flight per thread hide more of the shared-memory / ex2 latency that bounds the sweeps.

@@ -1,0 +1,382 @@
+// scs_place_iv4.cuh -- the interval placement with everything per-clade-row in REGISTERS.
+//
+// Same algorithm and the same arithmetic as scs_place_interval3_kernel (scs_place_interval.cuh: rows in
+// depth-first cell order, word-wise prefix counts, counts of a clade = one difference of prefix counts,
+// leaves outside the sweeps, softmax terms from exact integer differences), restructured around what ncu
+// showed limits that kernel (profiles/r01_ncu_interval_final_250k_summary.txt: 21.1k warp instructions per
+// SNV, issue slots 45 % busy, short-scoreboard stalls on shared memory, four barriers per row):
+//
+//   * a thread OWNS its clade rows for the whole kernel: NP pairs of non-leaf rows per thread (pair
+//     j = t + i T, the same assignment the sweeps of variant 3 used).  Their prefix-count offsets, their
+//     counts / softmax terms of the current SNV and their accumulators live in registers -- no per-row
+//     reload of the offset table from L1/L2, no count cache and no accumulator traffic in shared memory;
+//     the sweeps are straight-line code over NP unrolled pairs with all their shared-memory loads
+//     (2 per row: P[hi], P[lo]) issued back to back;
+//   * the row loop is software pipelined over three rows so that ONE pair of barriers serves them all:
+//         phase 1:  E(r-1) accumulate   | C(r) counts + best column      | A(r+1) word popcounts, warp scan
+//         ---- barrier
+//         phase 2:  D(r) terms + row sum                                  | B(r+1) block scan, prefix counts
+//         ---- barrier
+//     (every hand-over through shared memory -- scan totals, P, best column, row sum -- is written in one
+//     phase and read in the next, each buffer has a single writer phase, so no double buffering);
+//   * shared memory shrinks to the prefix counts, the leaf accumulators and 160 words of scratch
+//     (82 KB at 10,000 cells instead of 160 KB).
+//
+// Shapes: one CTA of T threads per run of SNV rows, T = words of a permuted row rounded up to a warp
+// (<= 640: ~100 registers per thread), NP = ceil(pairs / T) <= 8.  Anything else (more than 10,240 cells,
+// more non-leaf rows than 16 T) keeps variant 3.  Small trees simply get small CTAs and several of
+// them per SM (1,000 cells: 64 threads), which is what makes this path the faster one below 3,968 cells too.
+#pragma once
+
+#include "scs_place_interval.cuh"
+
+namespace scs {
+
+struct Iv4Params {
+    const uint32_t* gt;        // rows in depth-first cell order [n_snv][rw], positions beyond n_cells = 3 (missing)
+    long long n_snv;
+    int rw;                    // 32-bit words of a row: ceil(n_cells / 16), <= blockDim.x
+    int n_pairs;               // pairs of non-leaf rows (sorted by (lo, hi)); ceil(n_pairs / blockDim.x) == NP
+    int pad_pair;              // the pair whose second slot is padding (odd number of rows), or -1
+    const uint4* off4;         // [n_pairs] byte offsets into P: (lo0, hi0, lo1, hi1) * 4
+    const uint32_t* leafmask;  // [rw] bit 2e set when position 16 w + e has a leaf row
+    int n_leaf_pos;
+    const uint8_t* row_keep;   // optional [n_snv]
+    const GroupConst* gconst;
+    float* part;               // [num_runs][part_stride]: non-leaf accumulators, then (at leaf_off) 16 rw leaf accumulators
+    int part_stride, leaf_off;
+    int rows_per_run, num_runs;
+};
+
+constexpr int IV4_SCRATCH_WORDS = 5 * 32;   // [0,32) scan totals, [32,64) leaf totals, [64,96) best rank value, [96,128) its counts, [128,160) row sums
+constexpr int IV4_MAX_THREADS = 640;
+constexpr int IV4_MAX_NP = 8;
+
+static inline size_t iv4_smem_bytes(int rw, int threads) {
+    return 4 * (size_t(iv3_p_words(rw)) + 16 * size_t(threads) + IV4_SCRATCH_WORDS);
+}
+
+template <int NP>
+__global__ void __launch_bounds__(IV4_MAX_THREADS, 1) scs_place_iv4_kernel(const Iv4Params q) {
+    extern __shared__ uint32_t iv_smem[];
+    const int T = blockDim.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarp = T >> 5;
+    const int rw = q.rw;
+    uint32_t* P = iv_smem + 3;                      // P[0] at word 3: P[16 t + 1], a thread's first prefix count, is 16-byte aligned
+    float4* accL = reinterpret_cast<float4*>(iv_smem + iv3_p_words(rw));     // [4][T]: positions 16 t + 4 i .. + 3 of thread t at [i][t]
+    uint32_t* scr = reinterpret_cast<uint32_t*>(accL + 4 * T);
+    const GroupConst gc = q.gconst[0];
+    const bool own = t < rw;                        // this thread owns word t = positions 16 t .. 16 t + 15
+    const uint32_t lmask = own ? q.leafmask[t] : 0u;
+    const uint32_t* gw = q.gt;
+
+    // this thread's clade rows: NP pairs, offsets packed lo | hi << 16 (bytes into P: < 64 KB)
+    uint32_t offx[NP], offy[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        const int j = t + i * T;
+        const uint4 o = j < q.n_pairs ? q.off4[j] : make_uint4(0u, 0u, 0u, 0u);
+        offx[i] = o.x | (o.y << 16);
+        offy[i] = o.z | (o.w << 16);
+    }
+    // only the last pair of a thread can be missing or half padding (NP = ceil(n_pairs / T))
+    const int j_last = t + (NP - 1) * T;
+    const bool valid_x = j_last < q.n_pairs, valid_y = valid_x && j_last != q.pad_pair;
+
+    const float2 a1f2 = make_float2(gc.a1f, gc.a1f), a0f2 = make_float2(gc.a0f, gc.a0f);
+    const float2 a1h2 = make_float2(gc.a1h, gc.a1h), a0h2 = make_float2(gc.a0h, gc.a0h);
+    const float2 a1l2 = make_float2(gc.a1l, gc.a1l), a0l2 = make_float2(gc.a0l, gc.a0l);
+    const float2 n23 = make_float2(-8388608.0f, -8388608.0f);
+    const float n_leaf = float(q.n_leaf_pos);
+
+    for (int run = blockIdx.x; run < q.num_runs; run += gridDim.x) {
+        float2 acc[NP];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) acc[i] = make_float2(0.f, 0.f);
+        if (own) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) accL[i * T + t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const long long r0 = (long long)run * q.rows_per_run;
+        const long long r1 = r0 + q.rows_per_run < q.n_snv ? r0 + q.rows_per_run : q.n_snv;
+
+        // ---- pipeline state: row "cur" is in stages C/D, "nxt" in A/B, "prev" in E
+        uint32_t w_cur = own ? gw[size_t(r0) * rw + t] : 0xFFFFFFFFu;
+        uint32_t keep_cur = q.row_keep != nullptr ? q.row_keep[r0] : 1u;
+        uint32_t w_nxt = 0xFFFFFFFFu, keep_nxt = 0u;
+        if (r0 + 1 < r1) {
+            if (own) w_nxt = gw[size_t(r0 + 1) * rw + t];
+            keep_nxt = q.row_keep != nullptr ? q.row_keep[r0 + 1] : 1u;
+        }
+        uint32_t w_prev = 0u, keep_prev = 0u;
+        uint32_t ltot_cur = 0u, ltot_nxt = 0u;      // leaf totals (mutated | wild type << 16) of the rows in C/D and A/B
+        uint32_t sc_incl = 0u, sc_tot = 0u;         // A -> B: this word's inclusive warp scan and its own popcounts
+        uint32_t dx[NP], dy[NP];                    // C -> D: packed counts; D -> E: softmax terms (float bits)
+        float tl_wt = 0.f, tl_mut = 0.f, tl_miss = 0.f, leaf_total = 0.f;      // D -> E: the three leaf terms and their share of the row sum
+
+        // stage A: popcounts of this word, inclusive scan over the warp, leaf totals; warp totals -> scratch
+        auto stage_a = [&](uint32_t w) {
+            const uint32_t mm = (w ^ (w >> 1)) & 0x55555555u, wm = ~(w | (w >> 1)) & 0x55555555u;
+            const uint32_t tot = uint32_t(__popc(mm)) | (uint32_t(__popc(wm)) << 16);
+            uint32_t leaf_sum = uint32_t(__popc(mm & lmask)) | (uint32_t(__popc(wm & lmask)) << 16);
+            uint32_t incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) leaf_sum += __shfl_xor_sync(0xffffffffu, leaf_sum, o);
+            if (lane == 31) {
+                scr[warp] = incl;
+                scr[32 + warp] = leaf_sum;
+            }
+            sc_incl = incl;
+            sc_tot = tot;
+        };
+        // stage B: scan of the warp totals, this word's sixteen prefix counts -> P; returns the row's leaf totals
+        auto stage_b = [&](uint32_t w) -> uint32_t {
+            const uint32_t mm = (w ^ (w >> 1)) & 0x55555555u, wm = ~(w | (w >> 1)) & 0x55555555u;
+            const uint32_t wt = lane < nwarp ? scr[lane] : 0u;
+            uint32_t winc = wt, ltot = lane < nwarp ? scr[32 + lane] : 0u;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += v;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ltot += __shfl_xor_sync(0xffffffffu, ltot, o);
+            const uint32_t wbase = __shfl_sync(0xffffffffu, winc - wt, warp);       // prefix before this warp
+            if (own) {
+                uint32_t run_sum = wbase + sc_incl - sc_tot;                         // prefix before this word
+                uint32_t pv[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    run_sum += ((mm >> (2 * e)) & 1u) + (((wm >> (2 * e)) & 1u) << 16);
+                    pv[e] = run_sum;
+                }
+                uint4* dst = reinterpret_cast<uint4*>(P + 16 * t + 1);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dst[i] = make_uint4(pv[4 * i], pv[4 * i + 1], pv[4 * i + 2], pv[4 * i + 3]);
+            }
+            if (t == 0) P[0] = 0u;
+            return ltot;
+        };
+        // stage E: normalised terms into the accumulators
+        auto stage_e = [&](uint32_t w) {
+            float total = lane < nwarp ? __uint_as_float(scr[128 + lane]) : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+            const float inv = 1.0f / (total + leaf_total);        // >= 1: the best column's own term
+            const float2 inv2 = make_float2(inv, inv);
+#pragma unroll
+            for (int i = 0; i < NP; ++i) acc[i] = __ffma2_rn(make_float2(__uint_as_float(dx[i]), __uint_as_float(dy[i])), inv2, acc[i]);
+            if (own) {
+                // leaves: the term by the position's code (positions without a leaf row collect numbers nobody reads)
+                const uint32_t mm = (w ^ (w >> 1)) & 0x55555555u, wm = ~(w | (w >> 1)) & 0x55555555u;
+                const float w_wt = tl_wt * inv, w_mut = tl_mut * inv, w_miss = tl_miss * inv;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float4 a = accL[i * T + t];
+                    float* av = reinterpret_cast<float*>(&a);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int e = 4 * i + k;
+                        av[k] += ((mm >> (2 * e)) & 1u) ? w_mut : (((wm >> (2 * e)) & 1u) ? w_wt : w_miss);
+                    }
+                    accL[i * T + t] = a;
+                }
+            }
+        };
+
+        if (keep_cur) stage_a(w_cur);
+        __syncthreads();
+        if (keep_cur) ltot_cur = stage_b(w_cur);
+        __syncthreads();
+
+        for (long long r = r0; r < r1; ++r) {
+            // ================= phase 1: E(r-1) | C(r) | A(r+1)
+            if (keep_prev) stage_e(w_prev);
+            if (keep_cur) {
+                // counts of this thread's rows: both counts of a row in one subtraction (no borrow: P is monotone in each half)
+                float bv = -INFINITY;
+                uint32_t bd = 0u;
+#pragma unroll
+                for (int i = 0; i < NP; ++i) {
+                    dx[i] = iv_lds_off(P, offx[i] >> 16) - iv_lds_off(P, offx[i] & 0xFFFFu);
+                    dy[i] = iv_lds_off(P, offy[i] >> 16) - iv_lds_off(P, offy[i] & 0xFFFFu);
+                }
+#pragma unroll
+                for (int i = 0; i < NP; ++i) {
+                    const float2 c1 = __fadd2_rn(iv_lo16(dx[i], dy[i]), n23), c0 = __fadd2_rn(iv_hi16(dx[i], dy[i]), n23);
+                    float2 v = __ffma2_rn(a1f2, c1, __fmul2_rn(a0f2, c0));
+                    if (i == NP - 1) {
+                        if (!valid_x) v.x = -INFINITY;
+                        if (!valid_y) v.y = -INFINITY;
+                    }
+                    if (v.x > bv) {          // (first maximum in this thread's fixed order)
+                        bv = v.x;
+                        bd = dx[i];
+                    }
+                    if (v.y > bv) {
+                        bv = v.y;
+                        bd = dy[i];
+                    }
+                }
+                // across threads: ties go to the larger packed counts -- a total order, so the result does not depend
+                // on the reduction shape
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                    const uint32_t od = __shfl_xor_sync(0xffffffffu, bd, o);
+                    if (ov > bv || (ov == bv && od > bd)) {
+                        bv = ov;
+                        bd = od;
+                    }
+                }
+                if (lane == 0) {
+                    scr[64 + warp] = __float_as_uint(bv);
+                    scr[96 + warp] = bd;
+                }
+            }
+            const bool has_next = r + 1 < r1;
+            uint32_t w_nn = 0xFFFFFFFFu, keep_nn = 0u;
+            if (r + 2 < r1) {                       // two rows ahead: consumed by stage A of the next iteration
+                if (own) w_nn = gw[size_t(r + 2) * rw + t];
+                keep_nn = q.row_keep != nullptr ? q.row_keep[r + 2] : 1u;
+            }
+            if (has_next && keep_nxt) stage_a(w_nxt);
+            __syncthreads();
+
+            // ================= phase 2: D(r) | B(r+1)
+            if (keep_cur) {
+                float bv = lane < nwarp ? __uint_as_float(scr[64 + lane]) : -INFINITY;
+                uint32_t bd = lane < nwarp ? scr[96 + lane] : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                    const uint32_t od = __shfl_xor_sync(0xffffffffu, bd, o);
+                    if (ov > bv || (ov == bv && od > bd)) {
+                        bv = ov;
+                        bd = od;
+                    }
+                }
+                // the three leaf columns compete too: mutated (C1, C0) = (1, 0), wild type (0, 1), missing (0, 0)
+                const float n_mut = float(ltot_cur & 0xFFFFu), n_wt = float(ltot_cur >> 16), n_miss = n_leaf - n_mut - n_wt;
+                if (n_mut > 0.f && (gc.a1f > bv || (gc.a1f == bv && 1u > bd))) {
+                    bv = gc.a1f;
+                    bd = 1u;
+                }
+                if (n_wt > 0.f && (gc.a0f > bv || (gc.a0f == bv && 0x10000u > bd))) {
+                    bv = gc.a0f;
+                    bd = 0x10000u;
+                }
+                if (n_miss > 0.f && 0.f > bv) {
+                    bv = 0.f;
+                    bd = 0u;
+                }
+                // reference counts: e = count - reference is an exact integer difference
+                const float rf1 = float(bd & 0xFFFFu), rf0 = float(bd >> 16);
+                const float2 nb1_2 = make_float2(-(8388608.0f + rf1), -(8388608.0f + rf1)), nb0_2 = make_float2(-(8388608.0f + rf0), -(8388608.0f + rf0));
+                {
+                    const float e1m = 1.f - rf1, e1z = -rf1, e0w = 1.f - rf0, e0z = -rf0;
+                    tl_wt = ex2_approx(fmaf(gc.a1h, e1z, gc.a0h * e0w) + fmaf(gc.a1l, e1z, gc.a0l * e0w));
+                    tl_mut = ex2_approx(fmaf(gc.a1h, e1m, gc.a0h * e0z) + fmaf(gc.a1l, e1m, gc.a0l * e0z));
+                    tl_miss = ex2_approx(fmaf(gc.a1h, e1z, gc.a0h * e0z) + fmaf(gc.a1l, e1z, gc.a0l * e0z));
+                }
+                leaf_total = fmaf(n_mut, tl_mut, fmaf(n_wt, tl_wt, n_miss * tl_miss));
+                // terms relative to the best column (in place of the counts), row sum
+                float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < NP; ++i) {
+                    const float2 e1 = __fadd2_rn(iv_lo16(dx[i], dy[i]), nb1_2), e0 = __fadd2_rn(iv_hi16(dx[i], dy[i]), nb0_2);
+                    const float2 sdiff = __ffma2_rn(a1h2, e1, __fmul2_rn(a0h2, e0));      // exact operands, one rounding
+                    const float2 lo = __ffma2_rn(a1l2, e1, __fmul2_rn(a0l2, e0));
+                    const float2 x = __fadd2_rn(sdiff, lo);
+                    float2 tt = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+                    if (i == NP - 1) {
+                        if (!valid_x) tt.x = 0.f;
+                        if (!valid_y) tt.y = 0.f;
+                    }
+                    s2 = __fadd2_rn(s2, tt);
+                    dx[i] = __float_as_uint(tt.x);
+                    dy[i] = __float_as_uint(tt.y);
+                }
+                float sum = s2.x + s2.y;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                if (lane == 0) scr[128 + warp] = __float_as_uint(sum);
+            }
+            if (has_next && keep_nxt) ltot_nxt = stage_b(w_nxt);
+            __syncthreads();
+
+            keep_prev = keep_cur;
+            w_prev = w_cur;
+            keep_cur = has_next ? keep_nxt : 0u;
+            w_cur = w_nxt;
+            ltot_cur = ltot_nxt;
+            keep_nxt = keep_nn;
+            w_nxt = w_nn;
+        }
+        if (keep_prev) stage_e(w_prev);
+
+        float* out = q.part + size_t(run) * q.part_stride;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            const int j = t + i * T;
+            if (j < q.n_pairs) reinterpret_cast<float2*>(out)[j] = acc[i];
+        }
+        if (own) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(out + q.leaf_off)[4 * t + i] = accL[i * T + t];
+        }
+    }
+}
+
+template <int NP>
+static void iv4_launch_np(const Iv4Params& q, int grid, int threads, size_t smem, cudaStream_t st) {
+    scs_place_iv4_kernel<NP><<<grid, threads, smem, st>>>(q);
+}
+
+// Resident CTAs per SM for this shape (0 when the shape is not supported); also raises the kernel's dynamic shared-memory limit.
+template <int NP>
+static int iv4_occupancy_np(int threads, size_t smem) {
+    int per_sm = 0;
+    if (cudaFuncSetAttribute(scs_place_iv4_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scs_place_iv4_kernel<NP>, threads, smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return per_sm;
+}
+
+static int iv4_occupancy(int np, int threads, size_t smem) {
+    switch (np) {
+        case 1: return iv4_occupancy_np<1>(threads, smem);
+        case 2: return iv4_occupancy_np<2>(threads, smem);
+        case 3: return iv4_occupancy_np<3>(threads, smem);
+        case 4: return iv4_occupancy_np<4>(threads, smem);
+        case 5: return iv4_occupancy_np<5>(threads, smem);
+        case 6: return iv4_occupancy_np<6>(threads, smem);
+        case 7: return iv4_occupancy_np<7>(threads, smem);
+        case 8: return iv4_occupancy_np<8>(threads, smem);
+    }
+    return 0;
+}
+
+static void iv4_launch(int np, const Iv4Params& q, int grid, int threads, size_t smem, cudaStream_t st) {
+    switch (np) {
+        case 1: iv4_launch_np<1>(q, grid, threads, smem, st); break;
+        case 2: iv4_launch_np<2>(q, grid, threads, smem, st); break;
+        case 3: iv4_launch_np<3>(q, grid, threads, smem, st); break;
+        case 4: iv4_launch_np<4>(q, grid, threads, smem, st); break;
+        case 5: iv4_launch_np<5>(q, grid, threads, smem, st); break;
+        case 6: iv4_launch_np<6>(q, grid, threads, smem, st); break;
+        case 7: iv4_launch_np<7>(q, grid, threads, smem, st); break;
+        case 8: iv4_launch_np<8>(q, grid, threads, smem, st); break;
+    }
+}
+
+}  // namespace scs

@@ -169,6 +169,22 @@ class Placement:
         unchanged until the run that uses it has finished (call after the clades are set)."""
         check(lib().scs_placement_bind_genotypes(self._h, _dev_ptr(d_packed), int(pitch), _dev_ptr(d_row_keep), _stream_handle(stream)))
 
+    def prepare(self, d_packed, pitch, col_active, filter_rows, accumulate=False, stream=None):
+        """scs_placement_prepare: row filter + per-cell missing counts + the plan's genotype set-up in one
+        asynchronous call (one pass over ``d_packed`` on the interval path).  ``d_packed`` must stay alive
+        and unchanged until the run has finished; the numbers come back through ``prepare_result``."""
+        col_active = np.ascontiguousarray(col_active, dtype=np.uint8)
+        assert col_active.shape == (self.n_cells,)
+        check(lib().scs_placement_prepare(self._h, _dev_ptr(d_packed), int(pitch), ptr(col_active), int(bool(filter_rows)),
+                                          int(bool(accumulate)), _stream_handle(stream)))
+
+    def prepare_result(self, stream=None):
+        """(kept SNVs, missing fraction per cell) of the prepare call(s) so far; waits for ``stream``."""
+        n_kept = C.c_int64()
+        miss = np.zeros(self.n_cells, dtype=np.float64)
+        check(lib().scs_placement_prepare_result(self._h, C.byref(n_kept), ptr(miss), _stream_handle(stream)))
+        return int(n_kept.value), miss
+
     def set_clades(self, d_bits, words, stream=None):
         check(lib().scs_placement_set_clades(self._h, _dev_ptr(d_bits), int(words), _stream_handle(stream)))
 
@@ -257,14 +273,18 @@ class DecodedVcf:
             pass
 
 
-def gt_reduce(ctx, d_gt, pitch, n_snv, n_cells, col_active, filter_rows, d_row_keep):
+def gt_reduce(ctx, d_gt, pitch, n_snv, n_cells, col_active, filter_rows, d_row_keep, stream=None):
     """scs_gt_reduce: fills the device buffer ``d_row_keep`` and returns
-    (n_kept, missing fraction per cell)."""
+    (n_kept, missing fraction per cell).  Ordered on ``stream`` (default: torch's current stream when the
+    buffers are torch tensors, else the legacy default stream)."""
+    if stream is None and hasattr(d_gt, "device"):
+        import torch
+        stream = torch.cuda.current_stream(d_gt.device)
     col_active = np.ascontiguousarray(col_active, dtype=np.uint8)
     n_kept = C.c_int64()
     miss = np.zeros(n_cells, dtype=np.float64)
     check(lib().scs_gt_reduce(ctx._h, _dev_ptr(d_gt), int(pitch), int(n_snv), int(n_cells), ptr(col_active),
-                              int(bool(filter_rows)), _dev_ptr(d_row_keep), C.byref(n_kept), ptr(miss)))
+                              int(bool(filter_rows)), _dev_ptr(d_row_keep), C.byref(n_kept), ptr(miss), _stream_handle(stream)))
     return int(n_kept.value), miss
 
 
@@ -356,26 +376,41 @@ class StreamingPlacement:
 
     The soft branch weights are additive over SNV rows, so a dataset that sits in (pinned)
     host memory is walked in chunks: the H2D copy of chunk c+1 runs on a side stream while
-    chunk c goes through row filter -> operand expansion -> both GEMM passes on the compute
-    stream.  One chunk-sized plan is reused, device memory stays bounded by the chunk size,
-    and the copy disappears behind the GEMMs.  Returns the same numbers a single plan gives
-    (to summation order)."""
+    chunk c goes through scs_placement_prepare (row filter, missing counts, cell-order pass: one
+    read of the chunk) and the placement kernel on the compute stream.  One chunk-sized plan is
+    reused (plus a smaller one for a short last chunk), device memory stays bounded by the chunk
+    size, nothing is read back per chunk -- the counters accumulate on the device -- and the copy
+    disappears behind the kernels.  Returns the same numbers a single plan gives (to summation order)."""
 
-    def __init__(self, ctx, n_snv, n_cells, n_rows, n_chunks=8):
+    CHUNK_BYTES = 96 << 20      # default chunk size: large enough for full-rate H2D copies, small enough that the first,
+                                # exposed copy is a few per cent of the step
+
+    def __init__(self, ctx, n_snv, n_cells, n_rows, n_chunks=None, pitch=None):
         import torch
         self.ctx, self.n_snv, self.n_cells, self.n_rows = ctx, int(n_snv), int(n_cells), int(n_rows)
+        if n_chunks is None:
+            pitch = pitch or ((n_cells + 3) // 4 + 15) // 16 * 16
+            n_chunks = int(max(1, min(64, (self.n_snv * pitch) // self.CHUNK_BYTES)))
         rows = (self.n_snv + n_chunks - 1) // n_chunks
-        self.chunk_rows = max(256, (rows + 255) // 256 * 256)
+        self.chunk_rows = min(self.n_snv, max(256, (rows + 255) // 256 * 256))
         self.n_chunks = (self.n_snv + self.chunk_rows - 1) // self.chunk_rows
+        self.tail_rows = self.n_snv - (self.n_chunks - 1) * self.chunk_rows
         self.plan = Placement(ctx, self.chunk_rows, n_cells, n_rows)
+        self.plan_tail = Placement(ctx, self.tail_rows, n_cells, n_rows) if self.tail_rows != self.chunk_rows else None
         self.dev = torch.device("cuda", ctx.device)
         self.copy_stream = torch.cuda.Stream(device=self.dev)
         self._bufs = None
         self.y_chunk = torch.zeros(n_rows, dtype=torch.float64, device=self.dev)
-        self.keep = torch.zeros(self.chunk_rows, dtype=torch.uint8, device=self.dev)
 
     def set_clades_host(self, bits, words):
         self.plan.set_clades_host(bits, words)
+        if self.plan_tail is not None:
+            self.plan_tail.set_clades_host(bits, words)
+
+    def close(self):
+        self.plan.close()
+        if self.plan_tail is not None:
+            self.plan_tail.close()
 
     def run(self, host_packed, pitch, col_active, filter_rows, FP, FN, y_dev):
         """``host_packed``: torch uint8 [n_snv, pitch] in pinned host memory.  Accumulates the soft
@@ -389,7 +424,6 @@ class StreamingPlacement:
             for e in self._free:
                 e.record(cur)
         y_dev.zero_()
-        n_kept_total, miss_sum = 0, np.zeros(len(col_active))
 
         def enqueue_copy(c):
             b = c & 1
@@ -399,21 +433,22 @@ class StreamingPlacement:
                 self.copy_stream.wait_event(self._free[b])          # the previous user of this buffer is done
                 self._bufs[b][: r1 - r0].copy_(host_packed[r0:r1], non_blocking=True)
                 self._ready[b].record(self.copy_stream)
-            return r1 - r0
 
-        rows_c = enqueue_copy(0)
+        enqueue_copy(0)
         for c in range(self.n_chunks):
             b = c & 1
-            rows_next = enqueue_copy(c + 1) if c + 1 < self.n_chunks else 0
+            if c + 1 < self.n_chunks:
+                enqueue_copy(c + 1)
             cur.wait_event(self._ready[b])
-            if rows_c < self.chunk_rows:
-                self.keep.zero_()                                    # tail rows of a short last chunk: dropped
-            n_kept, miss = gt_reduce(self.ctx, self._bufs[b], pitch, rows_c, len(col_active), col_active, filter_rows, self.keep)
-            self.plan.bind_genotypes(self._bufs[b], pitch, self.keep, stream=cur)     # the buffer outlives the run (_free[b])
-            self.plan.run(FP, FN, self.y_chunk, stream=cur)
+            tail = c == self.n_chunks - 1 and self.plan_tail is not None
+            plan = self.plan_tail if tail else self.plan
+            plan.prepare(self._bufs[b], pitch, col_active, filter_rows, accumulate=(c > 0 and not tail), stream=cur)   # the buffer outlives the run (_free[b])
+            plan.run(FP, FN, self.y_chunk, stream=cur)
             y_dev.add_(self.y_chunk)
             self._free[b].record(cur)
-            n_kept_total += n_kept
-            miss_sum += miss * n_kept
-            rows_c = rows_next
-        return n_kept_total, (miss_sum / max(n_kept_total, 1))
+        n_kept, miss = self.plan.prepare_result(stream=cur) if (self.plan_tail is None or self.n_chunks > 1) else (0, np.zeros(len(col_active)))
+        if self.plan_tail is not None:
+            k2, m2 = self.plan_tail.prepare_result(stream=cur)
+            miss = (miss * n_kept + m2 * k2) / max(n_kept + k2, 1)
+            n_kept += k2
+        return n_kept, miss

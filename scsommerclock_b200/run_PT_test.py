@@ -458,36 +458,31 @@ def _place_on_tree(ctx, muts, tree, outg, FP, FN):
     has_outg = outg in columns
     n_snv, n_cols = muts.shape
     dev = torch.device("cuda", ctx.device)
-    row_keep = torch.empty(max(n_snv, 1), dtype=torch.uint8, device=dev)
+    cur = torch.cuda.current_stream(dev)
     d_gt = muts._dec.device_ptr()
-    n_kept, miss = engine.gt_reduce(ctx, d_gt, muts._dec.pitch, n_snv, n_cols, active, has_outg, row_keep)   # :350-357
+    bits, words, nodes = _clade_bits(tree, columns, active)
     sharded = getattr(muts, "row_sharded", False)
+    y = torch.zeros(bits.shape[0], dtype=torch.float64, device=dev)
+    n_kept, miss = 0, np.zeros(n_cols)
+    if n_snv > 0 or not sharded:
+        # row filter + per-cell missing counts (:350-358) and the placement (:362): the decoded matrix is read once on the
+        # interval path (scs_placement_prepare), nothing comes back to the host before the soft weights do
+        plan = engine.Placement(ctx, n_snv, n_cols, bits.shape[0])
+        plan.set_clades_host(bits, words, stream=cur)
+        plan.prepare(d_gt, muts._dec.pitch, active, has_outg, stream=cur)     # the decoded matrix outlives the run
+        plan.run(FP, FN, y, stream=cur)
+        n_kept, miss = plan.prepare_result(stream=cur)
+        plan.close()
     if sharded:
         from . import sharding
-        t = torch.tensor(np.concatenate([[float(n_kept)], miss * n_kept]), dtype=torch.float64, device=dev)
-        sharding.allreduce_soft_weights(t)                 # kept SNVs and per-cell missing counts over all ranks
+        t = torch.cat([torch.tensor(np.concatenate([[float(n_kept)], miss * n_kept]), dtype=torch.float64, device=dev), y])
+        sharding.allreduce_soft_weights(t)                 # the path's one exchange: kept SNVs, per-cell missing counts, 2n soft weights
         n_kept = int(round(t[0].item()))
-        miss = (t[1:] / max(n_kept, 1)).cpu().numpy()
+        miss = (t[1:1 + n_cols] / max(n_kept, 1)).cpu().numpy()
+        y = t[1 + n_cols:]
+    soft = y.cpu().numpy()
     FN_cap = 1 - FN - 0.2
     MS_i = {c: float(np.clip(miss[i], LAMBDA_MIN, FN_cap)) for i, c in enumerate(columns) if active[i]}        # :358
-    bits, words, nodes = _clade_bits(tree, columns, active)
-    if sharded:
-        y = torch.zeros(bits.shape[0], dtype=torch.float64, device=dev)
-        if n_snv > 0:
-            plan = engine.Placement(ctx, n_snv, n_cols, bits.shape[0])
-            plan.set_clades_host(bits, words)
-            plan.bind_genotypes(d_gt, muts._dec.pitch, row_keep)     # the decoded matrix outlives the run
-            plan.run(FP, FN, y)
-            torch.cuda.synchronize(dev)
-            plan.close()
-        sharding.allreduce_soft_weights(y)                 # the path's one exchange: 2n doubles
-        soft = y.cpu().numpy()
-    else:
-        plan = engine.Placement(ctx, n_snv, n_cols, bits.shape[0])
-        plan.set_clades_host(bits, words)
-        plan.bind_genotypes(d_gt, muts._dec.pitch, row_keep)         # the decoded matrix outlives the run
-        soft = plan.run_host(FP, FN)
-        plan.close()
     return {"soft": soft, "MS_i": MS_i, "n_muts": n_kept, "bits": bits, "words": words, "columns": columns,
             "weights": {}}
 

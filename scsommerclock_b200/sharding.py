@@ -36,7 +36,8 @@ def init_distributed(backend=None):
         import torch.distributed as dist
         if not dist.is_initialized():
             if backend is None:
-                backend = "nccl" if torch.cuda.is_available() else "gloo"
+                # SCS_DIST_BACKEND=gloo lets several ranks share one GPU (NCCL refuses duplicate devices): used by the tests
+                backend = os.environ.get("SCS_DIST_BACKEND") or ("nccl" if torch.cuda.is_available() else "gloo")
             if backend == "nccl":
                 torch.cuda.set_device(local)
                 dist.init_process_group(backend=backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
@@ -49,7 +50,12 @@ def allreduce_soft_weights(y):
     """In-place sum of the branch-weight vector over ranks (a no-op on one rank)."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(y, op=dist.ReduceOp.SUM)
+        if y.is_cuda and dist.get_backend() == "gloo":
+            h = y.cpu()                      # gloo: stage through the host
+            dist.all_reduce(h, op=dist.ReduceOp.SUM)
+            y.copy_(h)
+        else:
+            dist.all_reduce(y, op=dist.ReduceOp.SUM)
     return y
 
 
@@ -57,7 +63,7 @@ def max_over_ranks(value, device=None):
     import torch
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+        t = torch.tensor([float(value)], dtype=torch.float64, device=None if dist.get_backend() == "gloo" else device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
     return float(value)
