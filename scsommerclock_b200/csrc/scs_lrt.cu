@@ -129,7 +129,7 @@ template <bool WARP>
 __global__ void __launch_bounds__(WARP ? 32 : LRT_MAX_THREADS)
 scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ Ysrc, const int* __restrict__ gather,
                double* __restrict__ Yall, const double* __restrict__ wall, const int* __restrict__ child_all, LrtWork ws,
-               double* __restrict__ out, double* __restrict__ x_out, int smem_mode) {
+               double* __restrict__ out, double* __restrict__ x_out, int smem_mode, double mu_in) {
     __shared__ double sh[WARP ? 2 : 2 * (LRT_MAX_THREADS / 32)];
     __shared__ int s_nlev;
     const LrtProblem pb = probs[blockIdx.x];
@@ -311,7 +311,7 @@ scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ 
         grp_sync<WARP>();
     }
 
-    const double mu = LRT_MU;
+    const double mu = mu_in;
     int it = 0, status = 1;
     double f0 = 0.0;      // barrier objective at the current iterate (carried over from the line search)
     for (; it < LRT_MAX_ITER; ++it) {
@@ -640,6 +640,8 @@ int scs_lrt_plan_run(scs_lrt_plan* h, const double* d_Y, double* d_out, double* 
     if (!pl || !d_Y) return set_error(SCS_ERR_ARG, "null argument");
     if (!pl->have_w) return set_error(SCS_ERR_ARG, "scs_lrt_plan_set_weights has not been called");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    double mu = LRT_MU;
+    if (const char* e = getenv("SCS_LRT_MU")) mu = atof(e) > 0.0 ? atof(e) : LRT_MU;      // analysis knob (tools/lrt_sweep_probe.py)
     auto launch = [&](auto kern) {
         if (pl->smem_bytes > 0) {
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->smem_bytes);
@@ -647,7 +649,7 @@ int scs_lrt_plan_run(scs_lrt_plan* h, const double* d_Y, double* d_out, double* 
         }
         kern<<<pl->n_prob, pl->threads, pl->smem_bytes, st>>>(pl->d_probs, d_Y, pl->have_gather ? pl->d_gather : nullptr, pl->dY, pl->dw,
                                                               pl->d_child, pl->ws, d_out ? d_out : pl->d_out, d_x ? d_x : pl->d_x,
-                                                              pl->smem_bytes > 0);
+                                                              pl->smem_bytes > 0, mu);
     };
     if (pl->warp_mode) launch(scs_lrt_kernel<true>);
     else launch(scs_lrt_kernel<false>);

@@ -1727,16 +1727,37 @@ static int choose_algo(Placement* pl, const uint32_t* bits, int64_t pitch_words,
     int per_sm = 1;
     if (v3) {
         threads = threads3;
-        std::vector<uint4> off4(size_t(n_slots3 / 2), make_uint4(0u, 0u, 0u, 0u));
+        // variant 4 (scs_place_iv4.cuh: the same tables, every per-row quantity in registers) when the shape allows:
+        // one thread per word of a permuted row, at most 8 pairs of non-leaf rows per thread, at most 640 threads
+        pl->iv4_np = 0;
+        int t4 = 0;
+        if (!(e && !strcmp(e, "interval3")) && n_slots3 >= 2) {
+            const int n_pairs = n_slots3 / 2;
+            t4 = std::max(rw32, (((n_pairs + IV4_MAX_NP - 1) / IV4_MAX_NP) + 31) / 32 * 32);
+            if (const char* tt = getenv("SCS_IV_THREADS")) t4 = std::max(t4, std::min(1024, atoi(tt) / 32 * 32));
+            const int np = (n_pairs + t4 - 1) / t4;
+            if (t4 <= IV4_MAX_THREADS && np >= 1 && np <= IV4_MAX_NP && iv4_smem_bytes(rw, t4) <= SMEM_MAX) {
+                const int occ = iv4_occupancy(np, t4, iv4_smem_bytes(rw, t4));
+                if (occ > 0) {
+                    pl->iv4_np = np;
+                    per_sm = occ;
+                }
+            }
+        }
+        const bool v4 = pl->iv4_np > 0;
+        // byte offset of prefix count P[k] in shared memory: variant 3 keeps P[0] at word 3; variant 4 keeps a zero word
+        // at byte 0 and swizzles the 16-byte chunks of P[1..] (iv4_p_offset) so that its stores are bank-conflict free
+        auto poff = [&](uint32_t k) -> uint32_t { return v4 ? iv4_p_offset(k) : k * 4u; };
+        std::vector<uint4> off4(size_t(n_slots3 / 2), make_uint4(poff(0), poff(0), poff(0), poff(0)));
         for (int sidx = 0; sidx < n_gen; ++sidx) {
             const uint32_t lh = lohi[size_t(general[size_t(sidx)])];
             uint4& o = off4[size_t(sidx >> 1)];
             if (sidx & 1) {
-                o.z = (lh & 0xFFFFu) * 4u;
-                o.w = (lh >> 16) * 4u;
+                o.z = poff(lh & 0xFFFFu);
+                o.w = poff(lh >> 16);
             } else {
-                o.x = (lh & 0xFFFFu) * 4u;
-                o.y = (lh >> 16) * 4u;
+                o.x = poff(lh & 0xFFFFu);
+                o.y = poff(lh >> 16);
             }
         }
         int n_leaf_pos = 0;
@@ -1766,24 +1787,10 @@ static int choose_algo(Placement* pl, const uint32_t* bits, int64_t pitch_words,
         pl->iv_leaf_pos = n_leaf_pos;
         pl->iv_stride = leaf_off + 16 * rw;
         pl->iv_leaf_off = leaf_off;
-        // variant 4 (scs_place_iv4.cuh: the same tables, every per-row quantity in registers) when the shape allows:
-        // one thread per word of a permuted row, at most 8 pairs of non-leaf rows per thread, at most 640 threads
-        pl->iv4_np = 0;
-        if (!(e && !strcmp(e, "interval3")) && n_slots3 >= 2) {
-            const int n_pairs = n_slots3 / 2;
-            int t4 = std::max(rw32, (((n_pairs + IV4_MAX_NP - 1) / IV4_MAX_NP) + 31) / 32 * 32);
-            if (const char* tt = getenv("SCS_IV_THREADS")) t4 = std::max(t4, std::min(1024, atoi(tt) / 32 * 32));
-            const int np = (n_pairs + t4 - 1) / t4;
-            if (t4 <= IV4_MAX_THREADS && np >= 1 && np <= IV4_MAX_NP && iv4_smem_bytes(rw, t4) <= SMEM_MAX) {
-                const int occ = iv4_occupancy(np, t4, iv4_smem_bytes(rw, t4));
-                if (occ > 0) {
-                    pl->iv4_np = np;
-                    threads = t4;
-                    smem = iv4_smem_bytes(rw, t4);
-                    per_sm = occ;
-                    pl->iv_variant = 4;
-                }
-            }
+        if (v4) {
+            threads = t4;
+            smem = iv4_smem_bytes(rw, t4);
+            pl->iv_variant = 4;
         }
         if (pl->iv4_np == 0) {
             smem = interval3_smem_bytes(n_cells, n_slots3);
@@ -2018,10 +2025,19 @@ int scs_placement_prepare(scs_placement* h, const uint8_t* d_gt, int64_t pitch_b
         pl->gt_perm_bytes = bytes;
     }
     const int pt = (rw + 31) / 32 * 32;
-    const unsigned pgrid = unsigned(std::min<int64_t>(pl->n_snv, int64_t(pl->ctx->sm_count) * std::max(1, 2048 / pt)));
-    scs_permute_reduce_kernel<<<pgrid, pt, 2 * rw * sizeof(uint32_t), st>>>(
-        d_gt, pitch_bytes, pl->n_snv, n_cells, rw, pl->d_perm, reinterpret_cast<const uint32_t*>(pl->d_prep + off_mask), filter_rows,
-        pl->gt_perm, pl->row_keep, reinterpret_cast<unsigned long long*>(pl->d_prep), reinterpret_cast<unsigned int*>(pl->d_prep + off_miss));
+    const char* pe = getenv("SCS_PREP_ROWS");          // 1: the one-row-per-step kernel (kept for comparison); default: four rows per step
+    if (pe && atoi(pe) == 1) {
+        const unsigned pgrid = unsigned(std::min<int64_t>(pl->n_snv, int64_t(pl->ctx->sm_count) * std::max(1, 2048 / pt)));
+        scs_permute_reduce_kernel<<<pgrid, pt, 2 * rw * sizeof(uint32_t), st>>>(
+            d_gt, pitch_bytes, pl->n_snv, n_cells, rw, pl->d_perm, reinterpret_cast<const uint32_t*>(pl->d_prep + off_mask), filter_rows,
+            pl->gt_perm, pl->row_keep, reinterpret_cast<unsigned long long*>(pl->d_prep), reinterpret_cast<unsigned int*>(pl->d_prep + off_miss));
+    } else {
+        const int64_t groups = (pl->n_snv + 3) / 4;
+        const unsigned pgrid = unsigned(std::min<int64_t>(groups, int64_t(pl->ctx->sm_count) * std::max(1, 2048 / pt)));
+        scs_permute_reduce4_kernel<<<pgrid, pt, 2 * (4 * rw + 4) * sizeof(uint32_t), st>>>(
+            d_gt, pitch_bytes, pl->n_snv, n_cells, rw, pl->d_perm, reinterpret_cast<const uint32_t*>(pl->d_prep + off_mask), filter_rows,
+            pl->gt_perm, pl->row_keep, reinterpret_cast<unsigned long long*>(pl->d_prep), reinterpret_cast<unsigned int*>(pl->d_prep + off_miss));
+    }
     SCS_CUDA(cudaGetLastError());
     pl->launches++;
     pl->operands_valid = false;

@@ -405,6 +405,136 @@ __global__ void scs_permute_reduce_kernel(const uint8_t* __restrict__ gt, long l
     if (t == 0 && kept_cnt) atomicAdd(n_kept, (unsigned long long)kept_cnt);
 }
 
+// The same pre-pass, FOUR rows per step.  ncu on the one-row kernel (profiles/r02_ncu_iv4_first_summary.txt): ALU pipe 72 %
+// busy, ~6 instructions and one 3.4-way bank-conflicted byte load per (row, cell).  The cell order is the same for every row,
+// so the rows of a group are staged byte-interleaved -- shared-memory word b holds source byte b of rows 4g .. 4g+3 (a 4 x 4
+// byte transpose in registers, one 16-byte store per thread) -- and ONE 32-bit load then serves a cell of all four rows; a
+// code is moved into its output word with two shifts (funnel shift: the two low bits of the shifted source enter at the top,
+// sixteen steps fill the word in order, no masking).  ~2.7 instructions and a quarter of a load per (row, cell).
+// Row flags of the four rows are OR-ed over the block through one shared word per group (three rotate, cleared two groups
+// ahead) in front of the group's single barrier.
+constexpr int PERM4_THREADS_MAX = 1024;
+__global__ void scs_permute_reduce4_kernel(const uint8_t* __restrict__ gt, long long pitch, long long n_snv, int n_cells, int row_words,
+                                           const uint16_t* __restrict__ perm, const uint32_t* __restrict__ active_mask, int filter_rows,
+                                           uint32_t* __restrict__ out, uint8_t* __restrict__ row_keep,
+                                           unsigned long long* __restrict__ n_kept, unsigned int* __restrict__ missing_pos) {
+    extern __shared__ uint32_t pm_smem[];          // two buffers of 4 row_words + 4 words (the last four: all ones = "missing" for padding)
+    __shared__ uint32_t s_flags[3];
+    const int t = threadIdx.x, lane = t & 31;
+    const bool own = t < row_words;
+    const int buf_words = 4 * row_words + 4;
+    // per output position: source word index (= source byte of the row) | shift << 16
+    uint32_t src[16];
+    uint32_t valid = 0u;                           // bit 2e: output position 16 t + e is a cell
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+        const int k = 16 * t + e;
+        if (own && k < n_cells) {
+            const uint32_t c = perm[k];
+            src[e] = (c >> 2) | ((2u * (c & 3u)) << 16);
+            valid |= 1u << (2 * e);
+        } else {
+            src[e] = uint32_t(4 * row_words);      // the all-ones word: code 3
+        }
+    }
+    const uint32_t am = own ? active_mask[t] : 0u;
+    unsigned int total[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) total[k] = 0u;
+    uint32_t a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;
+    int pending = 0;
+    unsigned int kept_cnt = 0u;
+    auto flush = [&]() {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {              // byte b of accumulator q holds position 4 b + q
+            total[4 * b + 0] += (a0 >> (8 * b)) & 0xFFu;
+            total[4 * b + 1] += (a1 >> (8 * b)) & 0xFFu;
+            total[4 * b + 2] += (a2 >> (8 * b)) & 0xFFu;
+            total[4 * b + 3] += (a3 >> (8 * b)) & 0xFFu;
+        }
+        a0 = a1 = a2 = a3 = 0u;
+        pending = 0;
+    };
+    if (t < 3) s_flags[t] = 0u;
+    if (t < 8) pm_smem[(t >> 2) * buf_words + 4 * row_words + (t & 3)] = 0xFFFFFFFFu;
+    __syncthreads();
+    const long long n_groups = (n_snv + 3) >> 2;
+    uint32_t wn[4];
+    auto load_group = [&](long long g) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const long long r = 4 * g + i;
+            wn[i] = (own && r < n_snv) ? reinterpret_cast<const uint32_t*>(gt + size_t(r) * pitch)[t] : 0xFFFFFFFFu;
+        }
+    };
+    if (blockIdx.x < n_groups) load_group(blockIdx.x);
+    int buf = 0, fb = 0;
+    for (long long g = blockIdx.x; g < n_groups; g += gridDim.x, buf ^= 1, fb = fb == 2 ? 0 : fb + 1) {
+        uint32_t* rb = pm_smem + buf * buf_words;
+        const uint32_t w0 = wn[0], w1 = wn[1], w2 = wn[2], w3 = wn[3];
+        if (g + gridDim.x < n_groups) load_group(g + gridDim.x);
+        uint32_t flags = 0u;
+        if (own) {
+            // 4 x 4 byte transpose: word k of the result holds byte k of the four rows
+            const uint32_t l01 = __byte_perm(w0, w1, 0x5140), h01 = __byte_perm(w0, w1, 0x7362);
+            const uint32_t l23 = __byte_perm(w2, w3, 0x5140), h23 = __byte_perm(w2, w3, 0x7362);
+            reinterpret_cast<uint4*>(rb)[t] = make_uint4(__byte_perm(l01, l23, 0x5410), __byte_perm(l01, l23, 0x7632),
+                                                         __byte_perm(h01, h23, 0x5410), __byte_perm(h01, h23, 0x7632));
+            // a cell holds 1 or 2 exactly when its two bits differ (the mask keeps the low bit of the active cells only)
+            flags = ((((w0 ^ (w0 >> 1)) & am) != 0u) ? 1u : 0u) | ((((w1 ^ (w1 >> 1)) & am) != 0u) ? 2u : 0u) |
+                    ((((w2 ^ (w2 >> 1)) & am) != 0u) ? 4u : 0u) | ((((w3 ^ (w3 >> 1)) & am) != 0u) ? 8u : 0u);
+        }
+        flags = __reduce_or_sync(0xffffffffu, flags);
+        if (lane == 0 && flags) atomicOr(&s_flags[fb], flags);
+        __syncthreads();           // the group is staged, its flags are complete
+        uint32_t keep4 = filter_rows ? s_flags[fb] : 0xFu;
+        if (t == 0) s_flags[fb == 0 ? 2 : fb - 1] = 0u;      // the word of group g + 2 (last read one group ago, next written after the next barrier)
+        if (own) {
+            uint32_t o0 = 0u, o1 = 0u, o2 = 0u, o3 = 0u;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const uint32_t y = rb[src[e] & 0xFFFFu] >> (src[e] >> 16);
+                o0 = __funnelshift_r(o0, y, 2);
+                o1 = __funnelshift_r(o1, y >> 8, 2);
+                o2 = __funnelshift_r(o2, y >> 16, 2);
+                o3 = __funnelshift_r(o3, y >> 24, 2);
+            }
+            const uint32_t ov[4] = {o0, o1, o2, o3};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const long long r = 4 * g + i;
+                if (r < n_snv) {
+                    out[size_t(r) * row_words + t] = ov[i];
+                    if ((keep4 >> i) & 1u) {
+                        const uint32_t m = ov[i] & (ov[i] >> 1) & valid;          // bit 2e set <=> position e missing
+                        a0 += m & 0x01010101u;
+                        a1 += (m >> 2) & 0x01010101u;
+                        a2 += (m >> 4) & 0x01010101u;
+                        a3 += (m >> 6) & 0x01010101u;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                             // (uniform over the block)
+            const long long r = 4 * g + i;
+            if (r < n_snv && ((keep4 >> i) & 1u)) {
+                ++pending;
+                ++kept_cnt;
+            }
+        }
+        if (pending > 250) flush();
+        if (t < 4 && 4 * g + t < n_snv) row_keep[4 * g + t] = uint8_t((keep4 >> t) & 1u);
+    }
+    flush();
+    if (own) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            if (total[k]) atomicAdd(&missing_pos[16 * t + k], total[k]);
+    }
+    if (t == 0 && kept_cnt) atomicAdd(n_kept, (unsigned long long)kept_cnt);
+}
+
 // MAXT: largest CTA this instantiation is launched with (register budget); UNR: unroll factor of the three sweeps.
 // At 10k cells the CTA has 640 threads (one per word): 96 registers per thread are available, and two pairs of rows in
 // flight per thread hide more of the shared-memory / ex2 latency that bounds the sweeps.

@@ -52,6 +52,23 @@ constexpr int IV4_SCRATCH_WORDS = 5 * 32;   // [0,32) scan totals, [32,64) leaf 
 constexpr int IV4_MAX_THREADS = 640;
 constexpr int IV4_MAX_NP = 8;
 
+// Shared-memory byte offset of prefix count P[k].  Word 0 holds P[0] = 0; P[1..] follows from word 4 in 16-byte chunks of
+// four counts, chunk c at physical chunk c ^ ((c >> 3) & 3): a thread writes the four chunks 4 t .. 4 t + 3 of its word with
+// 16-byte stores, and without the swizzle lanes t, t + 2, t + 4, t + 6 of a quarter warp would hit the same banks (64-byte
+// lane stride, 4-way conflict: ncu counted 3.5k shared-memory wavefronts per SNV against 1.8k ideal).  Readers never pay for
+// it: the offsets of a clade row are computed once on the host.
+__host__ __device__ inline uint32_t iv4_p_offset(uint32_t k) {
+    if (k == 0u) return 0u;
+    const uint32_t m = k - 1u, c = m >> 2;
+    return 4u * (4u + 4u * (c ^ ((c >> 3) & 3u)) + (m & 3u));
+}
+
+__device__ __forceinline__ float iv4_warp_max(float v) {
+    float m;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));
+    return m;
+}
+
 static inline size_t iv4_smem_bytes(int rw, int threads) {
     return 4 * (size_t(iv3_p_words(rw)) + 16 * size_t(threads) + IV4_SCRATCH_WORDS);
 }
@@ -61,13 +78,17 @@ __global__ void __launch_bounds__(IV4_MAX_THREADS, 1) scs_place_iv4_kernel(const
     extern __shared__ uint32_t iv_smem[];
     const int T = blockDim.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarp = T >> 5;
     const int rw = q.rw;
-    uint32_t* P = iv_smem + 3;                      // P[0] at word 3: P[16 t + 1], a thread's first prefix count, is 16-byte aligned
+    const uint32_t* P = iv_smem;                    // prefix counts at their swizzled byte offsets (iv4_p_offset); word 0 = P[0] = 0
     float4* accL = reinterpret_cast<float4*>(iv_smem + iv3_p_words(rw));     // [4][T]: positions 16 t + 4 i .. + 3 of thread t at [i][t]
     uint32_t* scr = reinterpret_cast<uint32_t*>(accL + 4 * T);
     const GroupConst gc = q.gconst[0];
     const bool own = t < rw;                        // this thread owns word t = positions 16 t .. 16 t + 15
     const uint32_t lmask = own ? q.leafmask[t] : 0u;
     const uint32_t* gw = q.gt;
+    if (t == 0) iv_smem[0] = 0u;                    // P[0]: never written again (visible after the first barrier)
+    // this thread's four 16-byte chunks of P: chunk 4 t + i sits at physical chunk 4 t + (i ^ ((t >> 1) & 3))
+    uint4* const pdst = reinterpret_cast<uint4*>(iv_smem + 4) + 4 * t;
+    const int psw = (t >> 1) & 3;
 
     // this thread's clade rows: NP pairs, offsets packed lo | hi << 16 (bytes into P: < 64 KB)
     uint32_t offx[NP], offy[NP];
@@ -124,8 +145,7 @@ __global__ void __launch_bounds__(IV4_MAX_THREADS, 1) scs_place_iv4_kernel(const
                 const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += v;
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) leaf_sum += __shfl_xor_sync(0xffffffffu, leaf_sum, o);
+            leaf_sum = __reduce_add_sync(0xffffffffu, leaf_sum);      // (both halves stay below 2^16: no carry between them)
             if (lane == 31) {
                 scr[warp] = incl;
                 scr[32 + warp] = leaf_sum;
@@ -136,16 +156,9 @@ __global__ void __launch_bounds__(IV4_MAX_THREADS, 1) scs_place_iv4_kernel(const
         // stage B: scan of the warp totals, this word's sixteen prefix counts -> P; returns the row's leaf totals
         auto stage_b = [&](uint32_t w) -> uint32_t {
             const uint32_t mm = (w ^ (w >> 1)) & 0x55555555u, wm = ~(w | (w >> 1)) & 0x55555555u;
-            const uint32_t wt = lane < nwarp ? scr[lane] : 0u;
-            uint32_t winc = wt, ltot = lane < nwarp ? scr[32 + lane] : 0u;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t v = __shfl_up_sync(0xffffffffu, winc, o);
-                if (lane >= o) winc += v;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) ltot += __shfl_xor_sync(0xffffffffu, ltot, o);
-            const uint32_t wbase = __shfl_sync(0xffffffffu, winc - wt, warp);       // prefix before this warp
+            // prefix before this warp and the row's leaf totals: one integer warp reduction each over the warp totals
+            const uint32_t wbase = __reduce_add_sync(0xffffffffu, lane < warp ? scr[lane] : 0u);
+            const uint32_t ltot = __reduce_add_sync(0xffffffffu, lane < nwarp ? scr[32 + lane] : 0u);
             if (own) {
                 uint32_t run_sum = wbase + sc_incl - sc_tot;                         // prefix before this word
                 uint32_t pv[16];
@@ -154,11 +167,9 @@ __global__ void __launch_bounds__(IV4_MAX_THREADS, 1) scs_place_iv4_kernel(const
                     run_sum += ((mm >> (2 * e)) & 1u) + (((wm >> (2 * e)) & 1u) << 16);
                     pv[e] = run_sum;
                 }
-                uint4* dst = reinterpret_cast<uint4*>(P + 16 * t + 1);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) dst[i] = make_uint4(pv[4 * i], pv[4 * i + 1], pv[4 * i + 2], pv[4 * i + 3]);
+                for (int i = 0; i < 4; ++i) pdst[i ^ psw] = make_uint4(pv[4 * i], pv[4 * i + 1], pv[4 * i + 2], pv[4 * i + 3]);
             }
-            if (t == 0) P[0] = 0u;
             return ltot;
         };
         // stage E: normalised terms into the accumulators
@@ -222,16 +233,12 @@ __global__ void __launch_bounds__(IV4_MAX_THREADS, 1) scs_place_iv4_kernel(const
                         bd = dy[i];
                     }
                 }
-                // across threads: ties go to the larger packed counts -- a total order, so the result does not depend
-                // on the reduction shape
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                    const uint32_t od = __shfl_xor_sync(0xffffffffu, bd, o);
-                    if (ov > bv || (ov == bv && od > bd)) {
-                        bv = ov;
-                        bd = od;
-                    }
+                // across threads: the largest rank value, ties to the larger packed counts -- a total order, so the result does
+                // not depend on the reduction shape (two warp-wide reductions: redux.sync.max.f32, then max over the tied counts)
+                {
+                    const float m = iv4_warp_max(bv);
+                    bd = __reduce_max_sync(0xffffffffu, bv == m ? bd : 0u);
+                    bv = m;
                 }
                 if (lane == 0) {
                     scr[64 + warp] = __float_as_uint(bv);
@@ -251,14 +258,10 @@ __global__ void __launch_bounds__(IV4_MAX_THREADS, 1) scs_place_iv4_kernel(const
             if (keep_cur) {
                 float bv = lane < nwarp ? __uint_as_float(scr[64 + lane]) : -INFINITY;
                 uint32_t bd = lane < nwarp ? scr[96 + lane] : 0u;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                    const uint32_t od = __shfl_xor_sync(0xffffffffu, bd, o);
-                    if (ov > bv || (ov == bv && od > bd)) {
-                        bv = ov;
-                        bd = od;
-                    }
+                {
+                    const float m = iv4_warp_max(bv);
+                    bd = __reduce_max_sync(0xffffffffu, bv == m ? bd : 0u);
+                    bv = m;
                 }
                 // the three leaf columns compete too: mutated (C1, C0) = (1, 0), wild type (0, 1), missing (0, 0)
                 const float n_mut = float(ltot_cur & 0xFFFFu), n_wt = float(ltot_cur >> 16), n_miss = n_leaf - n_mut - n_wt;
