@@ -48,7 +48,7 @@ struct Iv4Params {
     int rows_per_run, num_runs;
 };
 
-constexpr int IV4_SCRATCH_WORDS = 5 * 32;   // [0,32) scan totals, [32,64) leaf totals, [64,96) best rank value, [96,128) its counts, [128,160) row sums
+constexpr int IV4_SCRATCH_WORDS = 5 * 32;   // (at the start of shared memory) [0,32) scan totals, [32,64) leaf totals, [64,96) best rank value, [96,128) its counts, [128,160) row sums
 constexpr int IV4_MAX_THREADS = 640;
 constexpr int IV4_MAX_NP = 8;
 
@@ -76,18 +76,25 @@ static inline size_t iv4_smem_bytes(int rw, int threads) {
 template <int NP>
 __global__ void __launch_bounds__(IV4_MAX_THREADS, 1) scs_place_iv4_kernel(const Iv4Params q) {
     extern __shared__ uint32_t iv_smem[];
-    const int T = blockDim.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarp = T >> 5;
+    // thread index and CTA size are read ONCE (volatile: ptxas otherwise re-reads the special registers -- S2R, ~20 cycles --
+    // and re-derives lane / warp / shared-memory addresses all over the row loop instead of keeping them in registers)
+    int t, T;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
+    asm volatile("mov.u32 %0, %%ntid.x;" : "=r"(T));
+    const int lane = t & 31, warp = t >> 5, nwarp = T >> 5;
     const int rw = q.rw;
-    const uint32_t* P = iv_smem;                    // prefix counts at their swizzled byte offsets (iv4_p_offset); word 0 = P[0] = 0
-    float4* accL = reinterpret_cast<float4*>(iv_smem + iv3_p_words(rw));     // [4][T]: positions 16 t + 4 i .. + 3 of thread t at [i][t]
-    uint32_t* scr = reinterpret_cast<uint32_t*>(accL + 4 * T);
-    const GroupConst gc = q.gconst[0];
+    // shared memory: [scratch, 160 words][P[0] = 0 and padding, 4 words][P[1..], 16 rw words, swizzled][leaf accumulators, 16 T words]
+    // -- everything the row loop addresses without a thread-dependent index sits at a compile-time offset
+    uint32_t* const scr = iv_smem;
+    const uint32_t* const P = iv_smem + IV4_SCRATCH_WORDS;      // prefix counts at their swizzled byte offsets (iv4_p_offset); word 0 = P[0] = 0
     const bool own = t < rw;                        // this thread owns word t = positions 16 t .. 16 t + 15
+    float4* const accL = reinterpret_cast<float4*>(iv_smem + IV4_SCRATCH_WORDS + iv3_p_words(rw)) + t;     // [4][T]: positions 16 t + 4 i .. + 3 at [i][t]
+    const GroupConst gc = q.gconst[0];
     const uint32_t lmask = own ? q.leafmask[t] : 0u;
     const uint32_t* gw = q.gt;
-    if (t == 0) iv_smem[0] = 0u;                    // P[0]: never written again (visible after the first barrier)
+    if (t == 0) iv_smem[IV4_SCRATCH_WORDS] = 0u;    // P[0]: never written again (visible after the first barrier)
     // this thread's four 16-byte chunks of P: chunk 4 t + i sits at physical chunk 4 t + (i ^ ((t >> 1) & 3))
-    uint4* const pdst = reinterpret_cast<uint4*>(iv_smem + 4) + 4 * t;
+    uint4* const pdst = reinterpret_cast<uint4*>(iv_smem + IV4_SCRATCH_WORDS + 4) + 4 * t;
     const int psw = (t >> 1) & 3;
 
     // this thread's clade rows: NP pairs, offsets packed lo | hi << 16 (bytes into P: < 64 KB)
@@ -115,7 +122,7 @@ __global__ void __launch_bounds__(IV4_MAX_THREADS, 1) scs_place_iv4_kernel(const
         for (int i = 0; i < NP; ++i) acc[i] = make_float2(0.f, 0.f);
         if (own) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) accL[i * T + t] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < 4; ++i) accL[i * T] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         const long long r0 = (long long)run * q.rows_per_run;
         const long long r1 = r0 + q.rows_per_run < q.n_snv ? r0 + q.rows_per_run : q.n_snv;
@@ -160,12 +167,31 @@ __global__ void __launch_bounds__(IV4_MAX_THREADS, 1) scs_place_iv4_kernel(const
             const uint32_t wbase = __reduce_add_sync(0xffffffffu, lane < warp ? scr[lane] : 0u);
             const uint32_t ltot = __reduce_add_sync(0xffffffffu, lane < nwarp ? scr[32 + lane] : 0u);
             if (own) {
-                uint32_t run_sum = wbase + sc_incl - sc_tot;                         // prefix before this word
+                const uint32_t base = wbase + sc_incl - sc_tot;                      // prefix before this word
+                // the sixteen inclusive prefix counts of the word, four positions per 32-bit operation: plane bits of positions
+                // 4 q + r gathered into byte q (A_r), byte-wise running sums over r, and one multiply for the carry-in of the
+                // groups q' < q; PRMT then zips a mutated-count byte and a wild-type-count byte into the packed 16 + 16 format
+                // (selector nibbles 8 | q replicate the -- always clear -- sign bit of a count byte: zero bytes)
+                uint32_t pm[4], pw[4];
+                {
+                    const uint32_t a0 = mm & 0x01010101u, a1 = (mm >> 2) & 0x01010101u, a2 = (mm >> 4) & 0x01010101u, a3 = (mm >> 6) & 0x01010101u;
+                    const uint32_t s1 = a0 + a1, s2 = s1 + a2, s3 = s2 + a3, ex = s3 * 0x01010100u;
+                    pm[0] = ex + a0; pm[1] = ex + s1; pm[2] = ex + s2; pm[3] = ex + s3;
+                }
+                {
+                    const uint32_t a0 = wm & 0x01010101u, a1 = (wm >> 2) & 0x01010101u, a2 = (wm >> 4) & 0x01010101u, a3 = (wm >> 6) & 0x01010101u;
+                    const uint32_t s1 = a0 + a1, s2 = s1 + a2, s3 = s2 + a3, ex = s3 * 0x01010100u;
+                    pw[0] = ex + a0; pw[1] = ex + s1; pw[2] = ex + s2; pw[3] = ex + s3;
+                }
                 uint32_t pv[16];
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    run_sum += ((mm >> (2 * e)) & 1u) + (((wm >> (2 * e)) & 1u) << 16);
-                    pv[e] = run_sum;
+                for (int qq = 0; qq < 4; ++qq) {
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                        uint32_t z;
+                        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(z) : "r"(pm[rr]), "r"(pw[rr]), "r"(uint32_t(qq | ((8 | qq) << 4) | ((4 + qq) << 8) | ((8 | qq) << 12))));
+                        pv[4 * qq + rr] = base + z;
+                    }
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) pdst[i ^ psw] = make_uint4(pv[4 * i], pv[4 * i + 1], pv[4 * i + 2], pv[4 * i + 3]);
@@ -187,14 +213,16 @@ __global__ void __launch_bounds__(IV4_MAX_THREADS, 1) scs_place_iv4_kernel(const
                 const float w_wt = tl_wt * inv, w_mut = tl_mut * inv, w_miss = tl_miss * inv;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    float4 a = accL[i * T + t];
-                    float* av = reinterpret_cast<float*>(&a);
+                    float4 a = accL[i * T];
+                    float sel[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const int e = 4 * i + k;
-                        av[k] += ((mm >> (2 * e)) & 1u) ? w_mut : (((wm >> (2 * e)) & 1u) ? w_wt : w_miss);
+                        sel[k] = ((mm >> (2 * e)) & 1u) ? w_mut : (((wm >> (2 * e)) & 1u) ? w_wt : w_miss);
                     }
-                    accL[i * T + t] = a;
+                    const float2 lo2 = __fadd2_rn(make_float2(a.x, a.y), make_float2(sel[0], sel[1]));
+                    const float2 hi2 = __fadd2_rn(make_float2(a.z, a.w), make_float2(sel[2], sel[3]));
+                    accL[i * T] = make_float4(lo2.x, lo2.y, hi2.x, hi2.y);
                 }
             }
         };
@@ -216,6 +244,11 @@ __global__ void __launch_bounds__(IV4_MAX_THREADS, 1) scs_place_iv4_kernel(const
                     dx[i] = iv_lds_off(P, offx[i] >> 16) - iv_lds_off(P, offx[i] & 0xFFFFu);
                     dy[i] = iv_lds_off(P, offy[i] >> 16) - iv_lds_off(P, offy[i] & 0xFFFFu);
                 }
+                // best of this thread's rows: two interleaved chains (even / odd pairs) instead of one chain of 2 NP dependent
+                // compare/selects, merged at the end; on ties the earlier row wins (a later one must be strictly greater),
+                // which is what one sequential scan would give
+                float bv1 = -INFINITY;
+                uint32_t bd1 = 0u;
 #pragma unroll
                 for (int i = 0; i < NP; ++i) {
                     const float2 c1 = __fadd2_rn(iv_lo16(dx[i], dy[i]), n23), c0 = __fadd2_rn(iv_hi16(dx[i], dy[i]), n23);
@@ -224,14 +257,27 @@ __global__ void __launch_bounds__(IV4_MAX_THREADS, 1) scs_place_iv4_kernel(const
                         if (!valid_x) v.x = -INFINITY;
                         if (!valid_y) v.y = -INFINITY;
                     }
-                    if (v.x > bv) {          // (first maximum in this thread's fixed order)
-                        bv = v.x;
-                        bd = dx[i];
+                    const bool y_wins = v.y > v.x;
+                    const float pvv = y_wins ? v.y : v.x;
+                    const uint32_t pdd = y_wins ? dy[i] : dx[i];
+                    if (i & 1) {
+                        if (pvv > bv1) {
+                            bv1 = pvv;
+                            bd1 = pdd;
+                        }
+                    } else {
+                        if (pvv > bv) {
+                            bv = pvv;
+                            bd = pdd;
+                        }
                     }
-                    if (v.y > bv) {
-                        bv = v.y;
-                        bd = dy[i];
-                    }
+                }
+                // merge: chain 0 holds pairs 0, 2, .. and chain 1 pairs 1, 3, ..; the earlier ROW wins a tie.  Rows are not
+                // compared by index here: equal rank values with different counts are told apart below by the counts, and equal
+                // counts are the same number either way
+                if (bv1 > bv || (bv1 == bv && bd1 > bd)) {
+                    bv = bv1;
+                    bd = bd1;
                 }
                 // across threads: the largest rank value, ties to the larger packed counts -- a total order, so the result does
                 // not depend on the reduction shape (two warp-wide reductions: redux.sync.max.f32, then max over the tied counts)
@@ -330,7 +376,7 @@ __global__ void __launch_bounds__(IV4_MAX_THREADS, 1) scs_place_iv4_kernel(const
         }
         if (own) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(out + q.leaf_off)[4 * t + i] = accL[i * T + t];
+            for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(out + q.leaf_off)[4 * t + i] = accL[i * T];
         }
     }
 }
