@@ -205,47 +205,55 @@ def reference_arm(args):
 
 
 # ------------------------------------------------------- replicate-sweep leg
-def replicate_sweep(ctx, dev, rank, world, R, n_cells, n_snv, steps, warmup):
-    """BASELINE configs[4]: many independent (VCF, tree) pairs, sharded over ranks with no
-    communication.  This rank's R replicates are placed block-diagonally in ONE launch per
-    GEMM pass (scs_placement_create_batch) and all R x 10 clock tests are solved in ONE LRT
-    launch.  Timed (CUDA events): row filter + operand expansion + both passes + LRT + result
-    read-back.  Host-side tree bookkeeping (Newick, branch order) is setup, outside the timing;
-    min(R, 32) distinct random trees are cycled over the replicates."""
+def sweep_cpu_baseline(tree_s, names, codes, tmp, seconds):
+    """PT tests/s of the reference's per-(pair, w_max) loop body (run_PT_test.py:713-718: get_gt_tree -- placement and
+    branch weights --, get_model_data, get_LRT_poisson with SciPy trust-constr) as restated in oracle/pt_oracle.py, on ONE
+    replicate of the sweep's shape and as many w_max values as fit the time budget; single process like the reference."""
+    from oracle import pt_oracle as O
+    tf = os.path.join(tmp, "cpu_rep.raxml.bestTree")
+    with open(tf, "w") as f:
+        f.write(tree_s.newick(names[:-1], "healthycell", scale=0.05))
+    with open(os.path.join(tmp, "cpu_rep.raxml.log"), "w") as f:
+        f.write("SEQ_ERROR: %.6f,  ADO_RATE: %.6f\n" % (FP_TRUE, FN_TRUE))
+    muts = np.where(codes == 3, np.nan, codes.astype(float))
+    muts = np.concatenate([muts, np.zeros((muts.shape[0], 1))], axis=1)
+    mut = {"muts": muts, "samples": np.array(names)}
+    t0 = time.perf_counter()
+    done = 0
+    for w_max in W_MAXS:
+        r = O.get_gt_tree(tf, mut, w_max)
+        Y, constr, init, wn, cols = O.get_model_data(r["tree"])
+        with np.errstate(all="ignore"):
+            O.get_LRT_poisson(Y, constr, init, wn[:, 0])
+        done += 1
+        if time.perf_counter() - t0 > seconds:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": done / dt, "unit": "PT tests/s", "cores": 1, "kind": "port",
+            "sample": "%d (pair, w_max) tests of one replicate (%d cells x %d SNVs): placement + branch weights + model data + SciPy "
+                      "trust-constr LRT per w_max like run_PT_test.py:713-718, oracle/pt_oracle.py, %.1f s" % (done, len(names) - 1, codes.shape[0], dt)}
+
+
+def replicate_sweep(ctx, dev, rank, world, R, n_cells, n_snv, steps, warmup, n_sub=4, cpu_seconds=0.0):
+    """BASELINE configs[4]: many independent (VCF, tree) pairs, sharded over ranks with no communication.  Every replicate
+    has its OWN random tree and its own genotypes.  Two timings of engine.ReplicateSweep (CUDA events, max over ranks):
+      * device-resident: packed matrices in HBM, trees parsed beforehand; timed = upload of the clade masks / topology,
+        per-group row filters, operand expansion, both placement passes, branch weights + LRT branch order, all R x 10
+        clock tests in one launch, result read-back;
+      * e2e: packed matrices in pinned HOST memory + Newick TEXT -> TSV rows.  The batch is cut into n_sub sub-batches on
+        their own streams so that the native tree parsing (host threads) and the H2D copy of sub-batch k + 1 run under the
+        kernels of sub-batch k; the TSV lines are formatted natively (scs_format_pt_rows)."""
     import torch
-    from scsommerclock_b200 import engine, run_PT_test as P, synth
-    n_trees = min(R, 32)
+    from scsommerclock_b200 import engine, sharding, synth
     names = ["tumcell%05d" % (i + 1) for i in range(n_cells)]
     columns = names + ["healthycell"]
-    active = np.array([c != "healthycell" for c in columns], dtype=np.uint8)
     tmp = tempfile.mkdtemp(prefix="scs_rep_")
-    trees, bits_l, childs, gathers = [], [], [], []
     FP, FN = FP_TRUE, FN_TRUE / 2
-    words = None
-    for k in range(n_trees):
-        ts = make_tree(n_cells, seed=777 + 1000 * rank + k)
-        tf = os.path.join(tmp, "rep%d.newick" % k)
-        with open(tf, "w") as f:
-            f.write(ts.newick(names, "healthycell", scale=0.05))
-        tree, outg, _, _ = P.read_tree(tf, np.array(columns))
-        bits, words, nodes = P._clade_bits(tree, columns, active)
-        # branch order from the topology alone (soft weights all equal -> the reference's tie order)
-        st = {"soft": np.ones(bits.shape[0]), "columns": columns, "bits": bits, "words": words, "weights": {}}
-        P._apply_placement(tree, st)
-        MS_i = {c: MS_TRUE for c in names}
-        per_w_weights = []
-        name_row = {n.name: i for i, n in enumerate(nodes)}
-        for w_max in W_MAXS:
-            P.add_br_weights(tree, FP, FN, MS_i, w_max, _state=st)
-            Y, constr, init, wn, cols = P.get_model_data(tree)
-            per_w_weights.append(wn[:, 0].copy())
-        trees.append((ts, bits, constr.child_int, np.array([name_row[c] for c in cols], dtype=np.int32), per_w_weights))
-    n_rows = trees[0][1].shape[0]
-    n_cols = len(columns)
-    # genotypes of all replicates, concatenated, generated on the device
+    trees = [make_tree(n_cells, seed=777 + 100000 * rank + r) for r in range(R)]
+    newicks = [ts.newick(names, "healthycell", scale=0.05) for ts in trees]
     packs = []
-    for r in range(R):
-        ts = trees[r % n_trees][0]
+    pitch = None
+    for r, ts in enumerate(trees):
         lo = torch.as_tensor(ts.lo[:-1], device=dev)
         hi = torch.as_tensor(ts.hi[:-1], device=dev)
         rate = torch.as_tensor(ts.branch_len[:-1], device=dev, dtype=torch.float32)
@@ -254,64 +262,90 @@ def replicate_sweep(ctx, dev, rank, world, R, n_cells, n_snv, steps, warmup):
         packs.append(pk)
     packed = torch.cat(packs, dim=0).contiguous()
     del packs
-    all_bits = np.concatenate([trees[r % n_trees][1] for r in range(R)], axis=0)
-    plan = engine.Placement(ctx, [n_snv] * R, n_cols, n_rows)
-    plan.set_clades_host(all_bits, words)
-    row_keep = torch.empty(R * n_snv, dtype=torch.uint8, device=dev)
-    y_dev = torch.zeros(R * n_rows, dtype=torch.float64, device=dev)
-    ch_l, w_l, g_l = [], [], []
-    for r in range(R):
-        _, _, child_int, gather, pw = trees[r % n_trees]
-        for wi in range(len(W_MAXS)):
-            ch_l.append(child_int)
-            w_l.append(pw[wi])
-            g_l.append(gather + r * n_rows)
-    lrt = engine.LrtPlan(ctx, ch_l)
-    lrt.set_weights(w_l)
-    lrt.set_gather(np.concatenate(g_l), R * n_rows)
-    out = torch.zeros((R * len(W_MAXS), 8), dtype=torch.float64, device=dev)
-    stream = torch.cuda.current_stream()
+    sweep = engine.ReplicateSweep(ctx, [n_snv] * R, columns, W_MAXS)
+    assert sweep.pitch == pitch
+    t0 = time.perf_counter()
+    sweep.parse_trees(newicks)
+    parse_ms = 1e3 * (time.perf_counter() - t0)
 
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    def step():
+        sweep.enqueue(packed, FP, FN)
+        return sweep.results()
 
-    def step(mark=False):
-        if mark: ev[0].record()
-        engine.gt_reduce(ctx, packed, pitch, R * n_snv, n_cols, active, True, row_keep)
-        if mark: ev[1].record()
-        plan.set_genotypes(packed, pitch, row_keep, stream=stream)
-        if mark: ev[2].record()
-        plan.run(FP, FN, y_dev, stream=stream)
-        if mark: ev[3].record()
-        lrt.run(y_dev, out, stream=stream)
-        if mark: ev[4].record()
-        return out.cpu()
+    def timed(fn, n_steps, n_warm):
+        for _ in range(n_warm):
+            res = fn()
+        torch.cuda.synchronize()
+        sharding.barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_steps):
+            res = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return sharding.max_over_ranks(e0.elapsed_time(e1) / n_steps, dev), res
 
-    for _ in range(max(1, warmup)):
-        res = step()
-    step(mark=True)
+    ms, (out, n_kept, status) = timed(step, steps, max(1, warmup))
+    gemm = sweep.place.last_times()
+    ok = int((out[:, :, 7] == 0).sum())
+    ref_rows = sweep.rows()
+    result = {"replicates_per_gpu": R, "cells": n_cells, "snvs": n_snv, "w_max_per_replicate": len(W_MAXS), "distinct_trees": R,
+              "ms_per_step": ms, "pt_tests_per_s": R * len(W_MAXS) * world / (ms / 1e3),
+              "placements_per_s": float(R) * n_snv * sweep.n_rows * world / (ms / 1e3),
+              "pass1_ms": gemm[0], "merge_ms": gemm[1], "pass2_ms": gemm[2], "tree_parse_ms_untimed": parse_ms,
+              "lrt_converged": ok, "lrt_problems": int(out.shape[0] * out.shape[1]), "groups_flagged": int((status != 0).sum()),
+              "median_newton_iterations": float(np.median(out[:, :, 6])), "tiling": sweep.place.info()}
+    # ---- end to end: host matrices + Newick text -> TSV rows
+    pinned = torch.empty(packed.shape, dtype=torch.uint8, pin_memory=True)
+    pinned.copy_(packed)
     torch.cuda.synchronize()
-    stage_ms = {k: ev[i].elapsed_time(ev[i + 1]) for i, k in enumerate(["row_filter", "expand", "placement", "lrt"])}
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    gemm = []
-    e0.record()
-    for _ in range(steps):
-        res = step()
-        gemm.append(plan.last_times())
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
-    from scsommerclock_b200 import sharding
-    ms = sharding.max_over_ranks(ms, dev)
-    g = np.array(gemm)
-    r_np = res.numpy()
-    ok = int((r_np[:, 7] == 0).sum())
-    return {"replicates_per_gpu": R, "cells": n_cells, "snvs": n_snv, "w_max_per_replicate": len(W_MAXS), "distinct_trees": n_trees,
-            "ms_per_step": ms, "pt_tests_per_s": R * len(W_MAXS) * world / (ms / 1e3),
-            "placements_per_s": float(R) * n_snv * n_rows * world / (ms / 1e3),
-            "pass1_ms": float(g[:, 0].mean()), "pass2_ms": float(g[:, 2].mean()), "merge_ms": float(g[:, 1].mean()),
-            "stage_ms": stage_ms, "lrt_converged": ok, "lrt_problems": int(r_np.shape[0]),
-            "median_newton_iterations": float(np.median(r_np[:, 6])), "tiling": plan.info()}
+    n_sub = max(1, min(n_sub, R))
+    cuts = [R * k // n_sub for k in range(n_sub + 1)]
+    subs = [engine.ReplicateSweep(ctx, [n_snv] * (cuts[k + 1] - cuts[k]), columns, W_MAXS) for k in range(n_sub)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(n_sub)]
+    host_ms = []
+
+    def step_e2e():
+        t0 = time.perf_counter()
+        for k, sub in enumerate(subs):
+            sub.parse_trees(newicks[cuts[k]:cuts[k + 1]])
+            sub.enqueue(pinned[cuts[k] * n_snv:cuts[k + 1] * n_snv], FP, FN, stream=streams[k])
+        rows = []
+        for sub in subs:
+            rows.extend(sub.rows())
+        host_ms.append(1e3 * (time.perf_counter() - t0))
+        return rows
+
+    cur = torch.cuda.current_stream(dev)
+
+    def step_e2e_timed():
+        for st in streams:
+            st.wait_stream(cur)                       # the timing events are recorded on the current stream
+        rows = step_e2e()
+        for st in streams:
+            cur.wait_stream(st)
+        return rows
+
+    ms_e2e, rows = timed(step_e2e_timed, steps, 1)
+    result["e2e"] = {"value": R * len(W_MAXS) * world / (ms_e2e / 1e3), "unit": "PT tests/s", "ms_per_step": ms_e2e,
+                     "h2d_bytes_per_step": int(pinned.numel() + R * sweep.n_rows * (sweep.words + 2) * 4 + R * 16) * world,
+                     "d2h_bytes_per_step": int(R * len(W_MAXS) * 64 + R * 12) * world, "sub_batches": n_sub,
+                     "host_wall_ms_per_step": float(np.mean(host_ms[-steps:])),
+                     "input": "packed genotype matrices in pinned host memory + Newick text of %d distinct trees" % R,
+                     "output": "TSV model lines (scs_format_pt_rows)", "rows_equal_device_leg": bool(rows == ref_rows),
+                     "vs_device_resident": ms_e2e / ms}
+    if rank == 0 and cpu_seconds > 0:
+        codes = synth.observe(trees[0], synth.throw_mutations(trees[0], n_snv, np.random.default_rng(3)), FN_TRUE, FP_TRUE, MS_TRUE,
+                              np.random.default_rng(4))
+        try:
+            result["cpu_baseline"] = sweep_cpu_baseline(trees[0], columns, codes, tmp, cpu_seconds)
+        except Exception as exc:          # (a reported extra: never lose the line over it)
+            result["cpu_baseline"] = {"error": repr(exc)}
+    for sub in subs:
+        sub.close()
+    sweep.close()
+    return result
 
 
 # ------------------------------------------------------------------ GPU arm
@@ -495,7 +529,8 @@ def main():
         plan.close()
         del packed
         torch.cuda.empty_cache()
-        rep = replicate_sweep(ctx, dev, rank, world, args.replicates, args.rep_cells, args.rep_snvs, max(2, args.steps), 1)
+        rep = replicate_sweep(ctx, dev, rank, world, args.replicates, args.rep_cells, args.rep_snvs, max(2, args.steps), 1,
+                              cpu_seconds=(args.cpu_seconds if (world == 1 and not args.no_cpu_baseline) else 0.0))
 
     if rank == 0:
         g = np.array(gemm_times)                         # [steps][pass1, merge, pass2, reduce]

@@ -216,6 +216,48 @@ int scs_lrt_plan_run(scs_lrt_plan* plan, const double* d_Y, double* d_out, doubl
 int scs_lrt_plan_run_host(scs_lrt_plan* plan, const double* Y, double* out, double* x_out, void* stream);
 const void* scs_lrt_plan_device_result(scs_lrt_plan* plan);
 
+/* Placeholder-topology plan of n_prob problems with n_br branches each, and the device buffers a producer kernel
+ * (scs_sweep_model) fills in place of scs_lrt_plan_set_weights / set_gather / the topology upload. */
+int scs_lrt_plan_create_uniform(scs_ctx* ctx, int32_t n_prob, int32_t n_br, scs_lrt_plan** out);
+int scs_lrt_plan_device_inputs(scs_lrt_plan* plan, int64_t src_len, int32_t** d_child, int32_t** d_gather, double** d_w);
+
+/* ------------------------------------------------------------ replicate sweeps
+ * The reference runs run_poisson_tree_test (run_PT_test.py:703-728) once per (VCF, tree) pair; a simulation sweep is
+ * thousands of pairs over the same samples.  These entry points do the per-pair work of read_tree, add_br_weights and
+ * get_model_data for ALL pairs of a batch at once, so that a sweep costs a handful of calls instead of a Python loop.
+ *
+ * scs_tree_parse_batch (host only, `threads` host threads, 0 = as many as there are cores up to 16): read_tree
+ * (:210-222, :281-285, :296-313) for CellPhy / plain Newick texts -- clean-up, cell -> tumcell / outgcell -> healthycell
+ * renames, `[n]` tags dropped when strip_tags != 0 (CellPhy files), Newick parsing, re-rooting on `outgroup`, its
+ * removal, removal of leaves that are not samples -- and the rows of S (:389-397).  Texts and sample names are passed
+ * as one character buffer plus offsets ([n + 1] each).  Per tree t: bits[t][n_rows][pitch_words] = membership masks over
+ * the sample columns, one row per node of tree.iter_descendants() (level order), zero rows after them;
+ * children[t][n_rows][2] = rows of a node's two children (-1 -1: leaf or unused row); info[t][4] = {nodes, leaves, 0, 0}.
+ * SCS_ERR_PARSE names the first tree that is malformed, lacks the outgroup leaf or is not binary. */
+int scs_tree_parse_batch(int32_t n_trees, const char* text, const int64_t* text_off, int32_t strip_tags, int32_t n_samples,
+                         const char* sample_names, const int64_t* name_off, const char* outgroup, int32_t n_rows,
+                         int64_t pitch_words, uint32_t* bits, int32_t* children, int32_t* info, int32_t threads);
+/* scs_gt_reduce for a batch of datasets stacked in one device matrix (<= 512 cells): group g owns rows
+ * [d_group_row0[g], d_group_row0[g + 1]) (device array); d_n_kept[g] and d_missing[g][n_cells] (counts, not fractions)
+ * stay on the device.  max_rows: the largest group (sizes the grid).  Asynchronous on `stream`. */
+int scs_gt_reduce_groups(scs_ctx* ctx, const uint8_t* d_gt, int64_t pitch_bytes, int32_t n_groups, const int64_t* d_group_row0,
+                         int64_t max_rows, int32_t n_cells, const uint8_t* col_active, int32_t filter_rows, uint8_t* d_row_keep,
+                         uint64_t* d_n_kept, uint32_t* d_missing, void* stream);
+/* add_br_weights (:451-515) and get_model_data's branch order (:569-611) for every group, on the device, written into
+ * the inputs of `plan` (created with scs_lrt_plan_create_uniform(n_groups * n_w, n_br)): problem g * n_w + w is group g
+ * at w_max[w].  d_bits / d_children / d_info: device copies of scs_tree_parse_batch's outputs; d_n_kept / d_missing: from
+ * scs_gt_reduce_groups; d_soft: [n_groups][n_rows] soft weights of the batched placement; FP, FN: host, one per group;
+ * d_status[g] != 0 flags a group whose tree has no root row or not n_br / 2 + 1 leaves.  Asynchronous on `stream`. */
+int scs_sweep_model(scs_ctx* ctx, int32_t n_groups, int32_t n_rows, int32_t n_cells, int64_t pitch_words, const uint32_t* d_bits,
+                    const int32_t* d_children, const int32_t* d_info, const uint64_t* d_n_kept, const uint32_t* d_missing,
+                    const double* FP, const double* FN, const double* w_max, int32_t n_w, const double* d_soft, int32_t n_br,
+                    scs_lrt_plan* plan, int32_t* d_status, void* stream);
+/* The model line of the reference's TSV (:722-724) for every group, host only: "{muts}\t{FN:.4f}\t{FP:.4f}" and, per
+ * w_max, "\t{LR:0>5.3f}\t{dof}\t{p_val}\tH{hyp}" with Python's number formatting.  out: [n_groups][n_w][8] as
+ * scs_lrt_plan_run writes it.  Rows are written back to back into buf; row g is buf[row_off[g] .. row_off[g + 1]). */
+int scs_format_pt_rows(int32_t n_groups, int32_t n_w, const double* out, const int64_t* n_kept, const double* FN, const double* FP,
+                       char* buf, int64_t buf_len, int64_t* row_off);
+
 #ifdef __cplusplus
 }
 #endif

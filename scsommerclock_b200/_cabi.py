@@ -68,6 +68,16 @@ _SIGNATURES = {
     "scs_lrt_plan_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scs_lrt_plan_run_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scs_lrt_plan_device_result": (C.c_void_p, [C.c_void_p]),
+    "scs_lrt_plan_create_uniform": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "scs_lrt_plan_device_inputs": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "scs_tree_parse_batch": (C.c_int, [C.c_int32, C.c_char_p, C.c_void_p, C.c_int32, C.c_int32, C.c_char_p, C.c_void_p, C.c_char_p, C.c_int32,
+                                       C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "scs_gt_reduce_groups": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scs_sweep_model": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                  C.c_void_p]),
+    "scs_format_pt_rows": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -6,7 +6,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["scs_api.cu", "scs_place.cu", "scs_lrt.cu", "scs_decode.cu"]
+SOURCES = ["scs_api.cu", "scs_place.cu", "scs_lrt.cu", "scs_decode.cu", "scs_tree.cu", "scs_sweep.cu"]
 OUT = os.path.join(HERE, "libscs_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]

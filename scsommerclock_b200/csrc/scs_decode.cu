@@ -468,8 +468,18 @@ scs_missing_count_kernel(const uint8_t* __restrict__ gt, int64_t pitch, int64_t 
 __global__ void __launch_bounds__(256, 4)
 scs_gt_reduce_narrow_kernel(const uint8_t* __restrict__ gt, int64_t pitch, int64_t n_rows, int n_words, int lane_shift, int n_cols,
                             const uint32_t* __restrict__ active_mask, int filter_rows, uint8_t* __restrict__ row_keep,
-                            unsigned long long* __restrict__ n_kept, unsigned int* __restrict__ missing) {
+                            unsigned long long* __restrict__ n_kept, unsigned int* __restrict__ missing,
+                            const long long* __restrict__ group_row0 = nullptr) {
     constexpr int UNROLL = 8;
+    if (group_row0 != nullptr) {
+        // a batch of datasets (replicates), one per blockIdx.y: rows [group_row0[g], group_row0[g + 1]) with their own counters
+        const long long g0 = group_row0[blockIdx.y];
+        n_rows = group_row0[blockIdx.y + 1] - g0;
+        gt += g0 * pitch;
+        row_keep += g0;
+        n_kept += blockIdx.y;
+        missing += size_t(blockIdx.y) * n_cols;
+    }
     __shared__ unsigned int s_miss[512];
     __shared__ unsigned int s_kept;
     for (int i = threadIdx.x; i < 512; i += blockDim.x) s_miss[i] = 0;
@@ -609,6 +619,26 @@ int gt_reduce_fetch(const uint8_t* sc, int n_cells, int64_t* n_kept, double* mis
         for (int rep = 0; rep < MISS_REPL; ++rep) m += miss[size_t(rep) * n_cells + c];
         missing_frac[c] = kept > 0 ? double(m) / double(kept) : 0.0;
     }
+    return SCS_OK;
+}
+
+// Row filter + missing counts for a batch of datasets stacked in one matrix (replicate sweeps): per-group counters, all
+// outputs stay on the device.  d_group_row0: [n_groups + 1] row offsets on the device.  Narrow matrices only (<= 512 cells).
+int gt_reduce_groups_launch(scs_ctx* ctx, const uint8_t* d_gt, int64_t pitch_bytes, int n_groups, const long long* d_group_row0,
+                            int64_t max_rows, int n_cells, const uint32_t* d_active_mask, int filter_rows, uint8_t* d_row_keep,
+                            unsigned long long* d_n_kept, unsigned int* d_missing, cudaStream_t st) {
+    const int n_words = (n_cells + 15) / 16;
+    if (n_words > 32) return set_error(SCS_ERR_ARG, "grouped row filter: at most 512 cells per dataset (got %d)", n_cells);
+    int shift = 0;
+    while ((1 << shift) < n_words) ++shift;
+    SCS_CUDA(cudaMemsetAsync(d_n_kept, 0, size_t(n_groups) * sizeof(unsigned long long), st));
+    SCS_CUDA(cudaMemsetAsync(d_missing, 0, size_t(n_groups) * n_cells * sizeof(unsigned int), st));
+    const int64_t want = (max_rows * (int64_t(1) << shift) + 255) / 256;
+    const unsigned gx = unsigned(std::max<int64_t>(1, std::min<int64_t>(want, std::max<int64_t>(1, int64_t(ctx->sm_count) * 8 / std::max(1, n_groups)))));
+    dim3 grid(gx, unsigned(n_groups));
+    scs_gt_reduce_narrow_kernel<<<grid, 256, 0, st>>>(d_gt, pitch_bytes, 0, n_words, shift, n_cells, d_active_mask, filter_rows, d_row_keep, d_n_kept,
+                                                      d_missing, d_group_row0);
+    SCS_CUDA(cudaGetLastError());
     return SCS_OK;
 }
 

@@ -35,6 +35,9 @@ size_t gt_reduce_scratch_bytes(int n_cells);
 int gt_reduce_launch(scs_ctx* ctx, const uint8_t* d_gt, int64_t pitch_bytes, int64_t n_snv, int n_cells, const uint8_t* col_active,
                      int filter_rows, uint8_t* d_row_keep, uint8_t* scratch, bool accumulate, cudaStream_t st);
 int gt_reduce_fetch(const uint8_t* scratch, int n_cells, int64_t* n_kept, double* missing_frac, cudaStream_t st);
+int gt_reduce_groups_launch(scs_ctx* ctx, const uint8_t* d_gt, int64_t pitch_bytes, int n_groups, const long long* d_group_row0,
+                            int64_t max_rows, int n_cells, const uint32_t* d_active_mask, int filter_rows, uint8_t* d_row_keep,
+                            unsigned long long* d_n_kept, unsigned int* d_missing, cudaStream_t st);
 }  // namespace scs
 
 #define SCS_CUDA(expr)                                                                         \

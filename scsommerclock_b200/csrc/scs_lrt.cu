@@ -602,6 +602,34 @@ int scs_lrt_plan_create(scs_ctx* ctx, int32_t n_prob, const int64_t* br_off, con
     return SCS_OK;
 }
 
+// A plan of n_prob problems with n_br branches each whose topologies, gather indices and weights are produced ON THE DEVICE
+// (scs_sweep_model, scs_sweep.cu): created around a placeholder topology (a caterpillar tree) that is overwritten before the
+// first run.  The kernel's shape decisions (threads per problem, shared-memory working set) depend on n_br only.
+int scs_lrt_plan_create_uniform(scs_ctx* ctx, int32_t n_prob, int32_t n_br, scs_lrt_plan** out) {
+    if (!ctx || !out) return set_error(SCS_ERR_ARG, "null argument");
+    if (n_prob <= 0 || n_br < 2 || (n_br & 1)) return set_error(SCS_ERR_ARG, "bad LRT batch shape (problems=%d branches=%d)", n_prob, n_br);
+    std::vector<int64_t> off(size_t(n_prob) + 1);
+    for (int p = 0; p <= n_prob; ++p) off[size_t(p)] = int64_t(p) * n_br;
+    std::vector<int32_t> child(size_t(n_prob) * n_br, -1);
+    for (int p = 0; p < n_prob; ++p)
+        for (int i = 1; i < n_br / 2; ++i) child[size_t(p) * n_br + 2 * i + 1] = i - 1;
+    return scs_lrt_plan_create(ctx, n_prob, off.data(), child.data(), out);
+}
+
+// Device buffers a producer kernel fills instead of scs_lrt_plan_set_weights / set_gather / the topology upload:
+// child_int [n_br total], gather index [n_br total] into a source vector of src_len doubles, weights [n_br total].
+int scs_lrt_plan_device_inputs(scs_lrt_plan* h, int64_t src_len, int32_t** d_child, int32_t** d_gather, double** d_w) {
+    LrtPlanImpl* pl = reinterpret_cast<LrtPlanImpl*>(h);
+    if (!pl || !d_child || !d_gather || !d_w) return set_error(SCS_ERR_ARG, "null argument");
+    *d_child = pl->d_child;
+    *d_gather = pl->d_gather;
+    *d_w = pl->dw;
+    pl->have_gather = true;
+    pl->have_w = true;
+    pl->src_len = size_t(src_len);
+    return SCS_OK;
+}
+
 int scs_lrt_plan_destroy(scs_lrt_plan* h) {
     LrtPlanImpl* pl = reinterpret_cast<LrtPlanImpl*>(h);
     if (!pl) return SCS_OK;

@@ -452,3 +452,174 @@ class StreamingPlacement:
             miss = (miss * n_kept + m2 * k2) / max(n_kept + k2, 1)
             n_kept += k2
         return n_kept, miss
+
+
+# ------------------------------------------------------------------ replicate sweeps
+def _concat_strings(items):
+    """bytes buffer + int64 offsets [n + 1] of a list of str / bytes."""
+    bs = [s.encode() if isinstance(s, str) else bytes(s) for s in items]
+    off = np.zeros(len(bs) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(b) for b in bs])
+    return b"".join(bs), off
+
+
+def tree_parse_batch(newicks, sample_names, n_rows, strip_tags=False, outgroup="healthycell", threads=0):
+    """scs_tree_parse_batch (host only): read_tree + the clade rows for many Newick texts at once.
+    Returns (bits uint32 [n, n_rows, words], words, children int32 [n, n_rows, 2], info int32 [n, 4])."""
+    n = len(newicks)
+    text, off = _concat_strings(newicks)
+    names, noff = _concat_strings(sample_names)
+    words = (len(sample_names) + 31) // 32
+    bits = np.empty((n, n_rows, words), dtype=np.uint32)
+    children = np.empty((n, n_rows, 2), dtype=np.int32)
+    info = np.zeros((n, 4), dtype=np.int32)
+    check(lib().scs_tree_parse_batch(n, text, ptr(off), int(bool(strip_tags)), len(sample_names), names, ptr(noff), outgroup.encode(),
+                                     int(n_rows), int(words), ptr(bits), ptr(children), ptr(info), int(threads)))
+    return bits, words, children, info
+
+
+def format_pt_rows(out, n_kept, FN, FP):
+    """scs_format_pt_rows: the TSV model line of every replicate (list of str)."""
+    out = np.ascontiguousarray(out, dtype=np.float64)
+    n_groups, n_w = out.shape[0], out.shape[1]
+    n_kept = np.ascontiguousarray(n_kept, dtype=np.int64)
+    FN = np.ascontiguousarray(np.broadcast_to(np.asarray(FN, dtype=np.float64), (n_groups,)))
+    FP = np.ascontiguousarray(np.broadcast_to(np.asarray(FP, dtype=np.float64), (n_groups,)))
+    cap = n_groups * (40 + 64 * n_w)
+    buf = C.create_string_buffer(cap)
+    row_off = np.zeros(n_groups + 1, dtype=np.int64)
+    check(lib().scs_format_pt_rows(n_groups, n_w, ptr(out), ptr(n_kept), ptr(FN), ptr(FP), C.cast(buf, C.c_void_p), cap, ptr(row_off)))
+    raw = buf.raw
+    return [raw[row_off[g]:row_off[g + 1]].decode() for g in range(n_groups)]
+
+
+class ReplicateSweep:
+    """A batch of (genotype matrix, tree) pairs over the same sample columns -- a simulation sweep -- through the whole PT
+    test with a fixed number of calls, whatever the number of pairs:
+
+        host threads   scs_tree_parse_batch      read_tree + clade rows of every tree (native, ~30 us per 100-leaf tree)
+        device         scs_gt_reduce_groups      row filter + per-cell missing counts of every pair
+                       scs_placement_* (batch)   all pairs placed block-diagonally, one launch per pass
+                       scs_sweep_model           branch weights + LRT branch order of every pair, into the LRT plan
+                       scs_lrt_plan_run          all (pair, w_max) clock tests in one launch
+        host           scs_format_pt_rows        the TSV model lines
+
+    Nothing is read back between the upload of the matrices / masks and the download of the results.  Every tree must
+    hold all non-outgroup columns as leaves (the usual case); pairs whose tree does not are flagged in ``status`` and left
+    to the per-pair path."""
+
+    def __init__(self, ctx, group_snvs, columns, w_maxs, outgroup="healthycell"):
+        import torch
+        self.ctx = ctx
+        self.dev = torch.device("cuda", ctx.device)
+        self.group_snvs = np.ascontiguousarray(group_snvs, dtype=np.int64)
+        self.G = int(self.group_snvs.size)
+        self.columns = list(columns)
+        self.outgroup = outgroup
+        self.n_cols = len(self.columns)
+        self.active = np.array([c != outgroup for c in self.columns], dtype=np.uint8)
+        self.has_outg = outgroup in self.columns
+        n_active = int(self.active.sum())
+        if n_active < 2:
+            raise ValueError("a sweep needs at least two cells besides the outgroup")
+        self.n_rows = 2 * n_active                  # max(2 n - 1, nodes) + 1 with nodes = 2 n - 1 (:389, :397)
+        self.n_br = 2 * (n_active - 1)
+        self.w_maxs = np.ascontiguousarray(w_maxs, dtype=np.float64)
+        self.n_w = int(self.w_maxs.size)
+        self.words = (self.n_cols + 31) // 32
+        self.pitch = ((self.n_cols + 3) // 4 + 15) // 16 * 16
+        self.total = int(self.group_snvs.sum())
+        self.place = Placement(ctx, self.group_snvs, self.n_cols, self.n_rows)
+        h = C.c_void_p()
+        check(lib().scs_lrt_plan_create_uniform(ctx._h, self.G * self.n_w, self.n_br, C.byref(h)))
+        self._lrt = h
+        G, d = self.G, self.dev
+        row0 = np.zeros(G + 1, dtype=np.int64)
+        row0[1:] = np.cumsum(self.group_snvs)
+        self.d_row0 = torch.as_tensor(row0, device=d)
+        self.d_keep = torch.empty(max(self.total, 1), dtype=torch.uint8, device=d)
+        self.d_nkept = torch.zeros(G, dtype=torch.int64, device=d)
+        self.d_missing = torch.zeros((G, self.n_cols), dtype=torch.int32, device=d)
+        self.d_bits = torch.empty((G, self.n_rows, self.words), dtype=torch.int32, device=d)
+        self.d_children = torch.empty((G, self.n_rows, 2), dtype=torch.int32, device=d)
+        self.d_info = torch.empty((G, 4), dtype=torch.int32, device=d)
+        self.d_y = torch.zeros(G * self.n_rows, dtype=torch.float64, device=d)
+        self.d_out = torch.zeros((G * self.n_w, 8), dtype=torch.float64, device=d)
+        self.d_status = torch.zeros(G, dtype=torch.int32, device=d)
+        # pinned staging for the small host <-> device transfers (asynchronous copies need page-locked memory)
+        self.h_bits = torch.empty((G, self.n_rows, self.words), dtype=torch.int32, pin_memory=True)
+        self.h_children = torch.empty((G, self.n_rows, 2), dtype=torch.int32, pin_memory=True)
+        self.h_info = torch.empty((G, 4), dtype=torch.int32, pin_memory=True)
+        self.h_out = torch.empty((G * self.n_w, 8), dtype=torch.float64, pin_memory=True)
+        self.h_nkept = torch.empty(G, dtype=torch.int64, pin_memory=True)
+        self.h_status = torch.empty(G, dtype=torch.int32, pin_memory=True)
+        self.d_gt = None
+        self.done = torch.cuda.Event()
+
+    def close(self):
+        if self._lrt:
+            lib().scs_lrt_plan_destroy(self._lrt)
+            self._lrt = None
+        self.place.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def parse_trees(self, newicks, strip_tags=False, threads=0):
+        """Host part (no device work): trees -> masks / topology in the pinned staging buffers."""
+        n = len(newicks)
+        assert n == self.G
+        text, off = _concat_strings(newicks)
+        names, noff = _concat_strings(self.columns)
+        check(lib().scs_tree_parse_batch(n, text, ptr(off), int(bool(strip_tags)), self.n_cols, names, ptr(noff), self.outgroup.encode(),
+                                         self.n_rows, self.words, C.c_void_p(self.h_bits.data_ptr()), C.c_void_p(self.h_children.data_ptr()),
+                                         C.c_void_p(self.h_info.data_ptr()), int(threads)))
+
+    def enqueue(self, packed, FP, FN, stream=None):
+        """Device part, asynchronous on ``stream`` (default: torch's current stream): ``packed`` is a torch uint8
+        [sum(group_snvs), pitch] tensor on the device, or in pinned host memory (then it is copied first).  The trees
+        must have been parsed (``parse_trees``).  ``done`` is recorded at the end; ``results()`` waits for it."""
+        import torch
+        st = stream or torch.cuda.current_stream(self.dev)
+        FP = np.ascontiguousarray(np.broadcast_to(np.asarray(FP, dtype=np.float64), (self.G,)))
+        FN = np.ascontiguousarray(np.broadcast_to(np.asarray(FN, dtype=np.float64), (self.G,)))
+        self.FP, self.FN = FP, FN
+        with torch.cuda.stream(st):
+            if packed.is_cuda:
+                d_gt = packed
+            else:
+                if self.d_gt is None:
+                    self.d_gt = torch.empty((self.total, self.pitch), dtype=torch.uint8, device=self.dev)
+                self.d_gt.copy_(packed, non_blocking=True)
+                d_gt = self.d_gt
+            self.d_bits.copy_(self.h_bits, non_blocking=True)
+            self.d_children.copy_(self.h_children, non_blocking=True)
+            self.d_info.copy_(self.h_info, non_blocking=True)
+            sh = _stream_handle(st)
+            check(lib().scs_gt_reduce_groups(self.ctx._h, _dev_ptr(d_gt), int(self.pitch), self.G, _dev_ptr(self.d_row0), int(self.group_snvs.max()),
+                                             self.n_cols, ptr(self.active), int(self.has_outg), _dev_ptr(self.d_keep), _dev_ptr(self.d_nkept),
+                                             _dev_ptr(self.d_missing), sh))
+            self.place.set_clades(self.d_bits, self.words, stream=st)
+            self.place.set_genotypes(d_gt, self.pitch, self.d_keep, stream=st)
+            self.place.run(FP, FN, self.d_y, stream=st)
+            check(lib().scs_sweep_model(self.ctx._h, self.G, self.n_rows, self.n_cols, int(self.words), _dev_ptr(self.d_bits), _dev_ptr(self.d_children),
+                                        _dev_ptr(self.d_info), _dev_ptr(self.d_nkept), _dev_ptr(self.d_missing), ptr(FP), ptr(FN), ptr(self.w_maxs),
+                                        self.n_w, _dev_ptr(self.d_y), self.n_br, self._lrt, _dev_ptr(self.d_status), sh))
+            check(lib().scs_lrt_plan_run(self._lrt, _dev_ptr(self.d_y), _dev_ptr(self.d_out), None, sh))
+            self.h_out.copy_(self.d_out, non_blocking=True)
+            self.h_nkept.copy_(self.d_nkept, non_blocking=True)
+            self.h_status.copy_(self.d_status, non_blocking=True)
+            self.done.record(st)
+
+    def results(self):
+        """(out float64 [G, n_w, 8], n_kept int64 [G], status int32 [G]) of the last ``enqueue``."""
+        self.done.synchronize()
+        return self.h_out.numpy().reshape(self.G, self.n_w, 8), self.h_nkept.numpy(), self.h_status.numpy()
+
+    def rows(self):
+        """The TSV model line of every pair (``results`` formatted by scs_format_pt_rows)."""
+        out, n_kept, status = self.results()
+        return format_pt_rows(out, n_kept, self.FN, self.FP)

@@ -699,29 +699,111 @@ def _error_rates(FP, FN, FN_fix, FP_fix):
     return max(FP, LAMBDA_MIN), max(FN / 2, LAMBDA_MIN)
 
 
+def _tree_source(tree_file):
+    """The file-level part of read_tree (:210-231, :281-294) without building the tree: (kind, text, FP, FN) with kind
+    'cellphy' (``[n]`` tags are dropped), 'plain', or 'scite' (integer node labels: handled by read_tree only)."""
+    with open(tree_file, "r") as f:
+        tree_raw = f.read().strip()
+    cellphy_ends = (".raxml.bestTree", "raxml.mutationMapTree", "raxml.supportFBP", "raxml.supportTBE")
+    if tree_file.endswith(cellphy_ends) or "cellphy" in tree_file:
+        log_file = ".".join(tree_file.split(".")[:-1]) + ".log"
+        if os.path.exists(log_file):
+            with open(log_file, "r") as f:
+                log = f.read().strip()
+            FP = float(re.search(r"SEQ_ERROR: (0.\d+(e-\d+)?)", log).group(1))
+            FN = float(re.search(r"ADO_RATE: (0.\d+(e-\d+)?)", log).group(1))
+        else:
+            FP = FN = LAMBDA_MIN
+        return "cellphy", tree_raw, FP, FN
+    if tree_file.endswith("_ml0.newick") or "scite" in tree_file:
+        return "scite", tree_raw, None, None
+    try:
+        FP = float(re.search(r"WGA0[\.\d,]*-0[\.\d]*-(0[\.\d]*)", tree_file).group(1))
+        FN = float(re.search(r"WGA(0[\.\d]*)[,\.\d]*?-", tree_file).group(1))
+    except AttributeError:
+        FP = FN = LAMBDA_MIN
+    return "plain", tree_raw, FP, FN
+
+
+def _tsv_header(w_maxs):
+    w_cols = ["-2logLR", "dof", "p-value", "hypothesis"]
+    return "muts\tFN\tFP" + "".join("\t" + "\t".join([f"{c}_{w_max:.0f}" for c in w_cols]) for w_max in w_maxs)
+
+
 def run_poisson_tree_test_batch(vcf_files, tree_files, out_files, w_maxs, exclude="", include="", FN_in=None, FP_in=None,
                                 ctx=None, shard=True):
-    """Many independent (VCF, tree) pairs -- a simulation sweep (BASELINE configs[4]).  Same TSV per
-    pair as run_poisson_tree_test.  Under torchrun the pairs are dealt to the ranks (no
-    communication); on each rank pairs of equal shape are placed block-diagonally in ONE launch
-    per GEMM pass (scs_placement_create_batch) and all (pair, w_max) clock tests are solved in ONE
-    LRT launch.  Returns the list of (pair index, [(LR, dof, on_bound, p), ...]) this rank handled."""
+    """Many independent (VCF, tree) pairs -- a simulation sweep (BASELINE configs[4]).  Same TSV per pair as
+    run_poisson_tree_test.  Under torchrun the pairs are dealt to the ranks (no communication, no row sharding).  On each
+    rank the pairs that share their sample columns go through engine.ReplicateSweep: tree parsing on host threads in native
+    code, then ONE call each for the row filters, the placement (block-diagonal, one launch per pass), branch weights +
+    LRT branch order, and all (pair, w_max) clock tests -- no Python loop over pairs touches a tree or waits for the
+    device.  infSCITE trees, trees that lack some of the VCF's cells and matrices wider than 512 cells take the per-pair
+    path (``_run_pairs``).  Returns the list of (pair index, [(LR, dof, on_bound, p), ...]) this rank handled."""
     import torch
     from . import sharding
     ctx = ctx or get_context()
     rank, world, _ = sharding.env_world()
     mine = sharding.replicate_shard(len(vcf_files), rank, world) if shard else list(range(len(vcf_files)))
-    dev = torch.device("cuda", ctx.device)
-    items = []
+    w_maxs = [float(w) for w in w_maxs]
+    pairs = []
     for i, text in zip(mine, _prefetch_texts([vcf_files[i] for i in mine])):    # files are read / gunzipped ahead on host threads
         muts = get_mut_df(vcf_files[i], exclude, include, ctx=ctx, _text=text, shard_rows=False)[0]   # whole pairs are sharded, not rows
+        if muts.shape[0] == 0:
+            raise ValueError("%s: no SNV passes the filters" % vcf_files[i])
+        kind, raw, FP, FN = _tree_source(tree_files[i])
+        pairs.append(dict(i=i, muts=muts, kind=kind, raw=raw, FP=FP, FN=FN))
+    results = {}
+    slow = []
+    fast = {}
+    force_pairs = os.environ.get("SCS_SWEEP_PATH", "") == "pairs"      # (tests: the per-pair path on inputs the batched path would take)
+    for p in pairs:
+        if force_pairs or p["kind"] == "scite" or p["muts"].shape[1] > 512 or p["muts"].shape[1] < 3:
+            slow.append(p)
+        else:
+            fast.setdefault((tuple(p["muts"].columns), p["kind"]), []).append(p)
+    header = _tsv_header(w_maxs)
+    for (columns, kind), grp in fast.items():
+        rates = [_error_rates(p["FP"], p["FN"], FN_in, FP_in) for p in grp]
+        sweep = engine.ReplicateSweep(ctx, [p["muts"].shape[0] for p in grp], list(columns), w_maxs)
+        try:
+            sweep.parse_trees([p["raw"] for p in grp], strip_tags=(kind == "cellphy"))
+        except engine._cabi.ScsError:
+            slow.extend(grp)                      # let the per-pair path name the offending file
+            sweep.close()
+            continue
+        packed = torch.cat([p["muts"].device_tensor() for p in grp], dim=0) if len(grp) > 1 else grp[0]["muts"].device_tensor()
+        sweep.enqueue(packed.contiguous(), np.array([r[0] for r in rates]), np.array([r[1] for r in rates]))
+        out, n_kept, status = sweep.results()
+        rows = sweep.rows()
+        for k, p in enumerate(grp):
+            if status[k] != 0:
+                slow.append(p)                    # e.g. a tree that lacks some of the VCF's cells
+                continue
+            if (out[k, :, 7] != 0).any():
+                print("\nFAILED POISSON OPTIMIZATION\n")
+            with open(out_files[p["i"]], "w") as f_out:
+                f_out.write(f"{header}\n{rows[k]}")
+            results[p["i"]] = [(float(o[0]), int(o[1]), int(o[2]), float(o[3])) if o[7] == 0 and np.isfinite(o[0])
+                               else (np.nan, np.nan, np.nan, np.nan) for o in out[k]]
+        sweep.close()
+    if slow:
+        results.update(_run_pairs(ctx, slow, tree_files, out_files, w_maxs, FN_in, FP_in))
+    return [(p["i"], results[p["i"]]) for p in pairs]
+
+
+def _run_pairs(ctx, pairs, tree_files, out_files, w_maxs, FN_in, FP_in):
+    """The per-pair form of the sweep: every tree goes through read_tree and the host-side model set-up; pairs of equal
+    shape still share one placement launch per pass and all clock tests one LRT launch."""
+    import torch
+    dev = torch.device("cuda", ctx.device)
+    items = []
+    for p in pairs:
+        i, muts = p["i"], p["muts"]
         tree, outg, FP, FN = read_tree(tree_files[i], muts.columns)
         FP, FN = _error_rates(FP, FN, FN_in, FP_in)
         columns = list(muts.columns)
         active = np.array([c != outg for c in columns], dtype=np.uint8)
         n_snv, n_cols = muts.shape
-        if n_snv == 0:
-            raise ValueError("%s: no SNV passes the filters" % vcf_files[i])
         d_gt = muts.device_tensor()
         keep = torch.empty(n_snv, dtype=torch.uint8, device=dev)
         n_kept, miss = engine.gt_reduce(ctx, d_gt, muts._dec.pitch, n_snv, n_cols, active, outg in columns, keep)
@@ -772,22 +854,20 @@ def run_poisson_tree_test_batch(vcf_files, tree_files, out_files, w_maxs, exclud
                 results.append((np.nan, np.nan, np.nan, np.nan))
             else:
                 results.append((float(LR), int(dof), int(on_bound), float(p_val)))
-    out = []
-    w_cols = ["-2logLR", "dof", "p-value", "hypothesis"]
+    out = {}
+    header_str = _tsv_header(w_maxs)
     for k, it in enumerate(items):
-        header_str = "muts\tFN\tFP"
         model_str = ""
         res_i = []
         for w_max, r in zip(w_maxs, results[k * len(w_maxs):(k + 1) * len(w_maxs)]):
             LR, dof, on_bound, p_val = r[0], r[1], r[2], r[3]
             hyp = int(p_val < 0.05)
-            header_str += "\t" + "\t".join([f"{c}_{w_max:.0f}" for c in w_cols])
             model_str += f"\t{LR:0>5.3f}\t{dof}\t{p_val}\tH{hyp}"
             res_i.append((LR, dof, on_bound, p_val))
         model_str = f"{it['n_kept']}\t{it['FN']:.4f}\t{it['FP']:.4f}{model_str}"
         with open(out_files[it["i"]], "w") as f_out:
             f_out.write(f"{header_str}\n{model_str}")
-        out.append((it["i"], res_i))
+        out[it["i"]] = res_i
     return out
 
 

@@ -848,6 +848,54 @@ def test_run_poisson_tree_test_batch(ctx, tmp_path):
             assert abs(p - g["p_val"][k]) <= 2e-3 * g["p_val"][k] + 1e-300
 
 
+def test_replicate_sweep_equals_the_per_pair_path(ctx, tmp_path, monkeypatch):
+    """engine.ReplicateSweep (native tree parsing on host threads, per-group row filters, batched placement, branch
+    weights + LRT branch order on the device, one LRT launch, native TSV formatting) against the per-pair path
+    (read_tree / _clade_bits / get_model_data-style bookkeeping in Python per tree) on 24 distinct random trees with
+    their own genotypes and error rates: identical muts / FN / FP / dof / decisions, LR and p to 1e-9."""
+    import gzip
+    rng = np.random.default_rng(77)
+    n_cells, n_rep = 14, 24
+    names = ["cell%04d" % (i + 1) for i in range(n_cells)] + ["outgcell"]
+    vcfs, trees = [], []
+    for r in range(n_rep):
+        tree = synth.coalescent_tree(n_cells, rng)
+        n_snv = int(rng.integers(60, 140))
+        codes = synth.observe(tree, synth.throw_mutations(tree, n_snv, rng), 0.15, 0.01, 0.1, rng)
+        d = tmp_path / ("sim_WGA0.%d-0-0.0%d" % (1 + r % 3, 1 + r % 2))
+        d.mkdir(exist_ok=True)
+        vcf = d / ("rep%02d.vcf.gz" % r)
+        with gzip.open(vcf, "wt") as f:
+            f.write("##fileformat=VCFv4.3\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(names) + "\n")
+            for i in range(n_snv):
+                gts = [".|." if c == 3 else ("0|0" if c == 0 else "0|1") for c in codes[i]] + ["0|0"]
+                f.write("1\t%d\t.\tA\tC\t.\tPASS\t.\tGT\t%s\n" % (10 + i, "\t".join(gts)))
+        tf = d / ("rep%02d.newick" % r)
+        tf.write_text(tree.newick(names[:-1], names[-1], scale=0.05) + "\n")
+        vcfs.append(str(vcf))
+        trees.append(str(tf))
+    w = [100.0, 400.0, 1000.0]
+    outs_a = [str(tmp_path / ("a%02d.tsv" % r)) for r in range(n_rep)]
+    outs_b = [str(tmp_path / ("b%02d.tsv" % r)) for r in range(n_rep)]
+    res_a = P.run_poisson_tree_test_batch(vcfs, trees, outs_a, w, ctx=ctx)
+    monkeypatch.setenv("SCS_SWEEP_PATH", "pairs")
+    res_b = P.run_poisson_tree_test_batch(vcfs, trees, outs_b, w, ctx=ctx)
+    assert [r[0] for r in res_a] == list(range(n_rep)) == [r[0] for r in res_b]
+    n_fail = 0
+    for r in range(n_rep):
+        (ha, fa), (hb, fb) = _tsv_fields(outs_a[r]), _tsv_fields(outs_b[r])
+        assert ha == hb and fa[:3] == fb[:3], (r, fa[:3], fb[:3])
+        for k, (ra, rb) in enumerate(zip(res_a[r][1], res_b[r][1])):
+            if np.isnan(rb[0]):
+                assert np.isnan(ra[0])
+                n_fail += 1
+                continue
+            assert ra[1] == rb[1] and ra[2] == rb[2], (r, k, ra, rb)
+            assert abs(ra[0] - rb[0]) <= 1e-9 * max(1.0, abs(rb[0])) and abs(ra[3] - rb[3]) <= 1e-9 * rb[3] + 1e-300, (r, k, ra, rb)
+            assert fa[6 + 4 * k] == fb[6 + 4 * k]
+    assert n_fail <= n_rep
+
+
 def test_cli_entry_point(ctx, tmp_path):
     g = load("syn_a")
     vcf, tree_file, meta = case_inputs(g)

@@ -313,3 +313,81 @@ def test_clade_intervals_on_general_laminar_families():
                 assert not is_laminar(S2)
                 bits2, _ = engine.pack_clades(S2)
                 assert not engine.clade_intervals(bits2, n)[0]
+
+
+# ---------------------------------------------------------------- replicate sweeps: native host work
+def _python_tree_rows(tree_file, columns):
+    tree, outg, FP, FN = P.read_tree(tree_file, np.array(columns))
+    active = np.array([c != outg for c in columns], dtype=np.uint8)
+    bits, words, nodes = P._clade_bits(tree, columns, active)
+    idx = {id(n): i for i, n in enumerate(nodes)}
+    ch = np.full((bits.shape[0], 2), -1, dtype=np.int32)
+    for i, n in enumerate(nodes):
+        if n.children:
+            ch[i] = [idx[id(c)] for c in n.children]
+    return bits, ch, len(nodes), len(tree)
+
+
+@pytest.mark.parametrize("name", [c for c in CASES if "scite" not in c])
+def test_native_tree_parser_matches_read_tree_on_golden_trees(name):
+    """scs_tree_parse_batch (C++, host threads) against read_tree + _clade_bits (which the fixtures pin to the reference's
+    S): same rows, same child order, for the reference's example trees and every synthetic case."""
+    g = load(name)
+    vcf, tree_file, meta = case_inputs(g)
+    columns = list(g["samples"])
+    bits, ch, n_nodes, n_leaves = _python_tree_rows(tree_file, columns)
+    kind, raw, FP, FN = P._tree_source(tree_file)
+    b2, words, c2, info = engine.tree_parse_batch([raw], columns, bits.shape[0], strip_tags=(kind == "cellphy"))
+    assert np.array_equal(b2[0], bits) and np.array_equal(c2[0], ch) and tuple(info[0][:2]) == (n_nodes, n_leaves)
+    tree, outg, FP0, FN0 = P.read_tree(tree_file, np.array(columns))
+    assert (FP, FN) == (FP0, FN0)                       # the file-level rates of _tree_source are read_tree's
+
+
+def test_native_tree_parser_on_random_trees_with_missing_samples(tmp_path):
+    rng = np.random.default_rng(5)
+    n = 40
+    names = ["cell%04d" % (i + 1) for i in range(n)]
+    cols = [c for i, c in enumerate(["tumcell%04d" % (i + 1) for i in range(n)] + ["healthycell"]) if i not in (3, 17, 22)]
+    texts, want = [], []
+    for k in range(60):
+        st = synth.coalescent_tree(n, rng)
+        nw = st.newick(names, "outgcell", scale=0.05) + "\n"
+        tf = tmp_path / ("t%d.newick" % k)
+        tf.write_text(nw)
+        texts.append(nw)
+        want.append(_python_tree_rows(str(tf), cols))
+    n_rows = want[0][0].shape[0]
+    for threads in (1, 0):
+        bits, words, ch, info = engine.tree_parse_batch(texts, cols, n_rows, threads=threads)
+        for k in range(len(texts)):
+            assert np.array_equal(bits[k], want[k][0]) and np.array_equal(ch[k], want[k][1]) and tuple(info[k][:2]) == want[k][2:]
+    for bad in ["((a:1,b:1):1,c:1)", "((tumcell0001:1,,tumcell0002:1):1,healthycell:1);", "((tumcell0001:1,tumcell0002:1):1,tumcell0005:1);",
+                "((tumcell0001:1,tumcell0002:x):1,healthycell:1);", "((tumcell0001:1,tumcell0002:1,tumcell0005:1):1,healthycell:1);"]:
+        with pytest.raises(engine._cabi.ScsError):
+            engine.tree_parse_batch([texts[0], bad], cols, n_rows)
+
+
+def test_native_tsv_rows_match_python_formatting():
+    rng = np.random.default_rng(0)
+    vals = [0.0, 1.0, 0.5, 0.05, 0.0001, 0.0003, 9.999e-5, 1.5e-7, 1e-100, 3.3e-16, 0.6725292599860104, 0.049999999, 1e-5, 2.5e-5, 0.1,
+            0.30000000000000004, 5e-324, 1e-300] + list(10 ** rng.uniform(-20, 0, 300))
+    out = np.zeros((len(vals), 2, 8))
+    for i, v in enumerate(vals):
+        out[i, 0] = [rng.uniform(0, 200), 29, 1, v, 0, 0, 5, 0]
+        out[i, 1] = [rng.uniform(0, 2), 13, 0, min(1.0, v * 3), 0, 0, 5, 0]
+    out[3, 1, 7] = 1
+    out[3, 1, 0] = np.nan
+    nk = rng.integers(1, 100000, len(vals))
+    FN = rng.uniform(0, 0.5, len(vals))
+    FP = rng.uniform(0, 0.1, len(vals))
+    rows = engine.format_pt_rows(out, nk, FN, FP)
+    for i in range(len(vals)):
+        s = f"{nk[i]}\t{FN[i]:.4f}\t{FP[i]:.4f}"
+        for w in range(2):
+            LR, dof, ob, p, _, _, _, st = out[i, w]
+            if st != 0 or not np.isfinite(LR):
+                LR = dof = p = np.nan
+                s += f"\t{LR:0>5.3f}\t{dof}\t{p}\tH{int(p < 0.05)}"
+            else:
+                s += f"\t{LR:0>5.3f}\t{int(dof)}\t{float(p)}\tH{int(p < 0.05)}"
+        assert s == rows[i]
