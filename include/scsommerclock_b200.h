@@ -239,19 +239,23 @@ int scs_tree_parse_batch(int32_t n_trees, const char* text, const int64_t* text_
                          int64_t pitch_words, uint32_t* bits, int32_t* children, int32_t* info, int32_t threads);
 /* scs_gt_reduce for a batch of datasets stacked in one device matrix (<= 512 cells): group g owns rows
  * [d_group_row0[g], d_group_row0[g + 1]) (device array); d_n_kept[g] and d_missing[g][n_cells] (counts, not fractions)
- * stay on the device.  max_rows: the largest group (sizes the grid).  Asynchronous on `stream`. */
+ * stay on the device.  d_active_mask: device, ceil(n_cells / 16) words, bit 2 (c % 16) of word c / 16 set for every
+ * active (non-outgroup) cell c.  max_rows: the largest group (sizes the grid).  Asynchronous on `stream`. */
 int scs_gt_reduce_groups(scs_ctx* ctx, const uint8_t* d_gt, int64_t pitch_bytes, int32_t n_groups, const int64_t* d_group_row0,
-                         int64_t max_rows, int32_t n_cells, const uint8_t* col_active, int32_t filter_rows, uint8_t* d_row_keep,
+                         int64_t max_rows, int32_t n_cells, const uint32_t* d_active_mask, int32_t filter_rows, uint8_t* d_row_keep,
                          uint64_t* d_n_kept, uint32_t* d_missing, void* stream);
 /* add_br_weights (:451-515) and get_model_data's branch order (:569-611) for every group, on the device, written into
  * the inputs of `plan` (created with scs_lrt_plan_create_uniform(n_groups * n_w, n_br)): problem g * n_w + w is group g
  * at w_max[w].  d_bits / d_children / d_info: device copies of scs_tree_parse_batch's outputs; d_n_kept / d_missing: from
  * scs_gt_reduce_groups; d_soft: [n_groups][n_rows] soft weights of the batched placement; FP, FN: host, one per group;
- * d_status[g] != 0 flags a group whose tree has no root row or not n_br / 2 + 1 leaves.  Asynchronous on `stream`. */
+ * d_status[g] != 0 flags a group whose tree has no root row or not n_br / 2 + 1 leaves.  d_workspace: caller-owned
+ * device scratch of scs_sweep_model_workspace(n_groups, n_rows, n_w) bytes, 8-byte aligned (one per concurrent
+ * call).  Asynchronous on `stream`. */
+int64_t scs_sweep_model_workspace(int32_t n_groups, int32_t n_rows, int32_t n_w);
 int scs_sweep_model(scs_ctx* ctx, int32_t n_groups, int32_t n_rows, int32_t n_cells, int64_t pitch_words, const uint32_t* d_bits,
                     const int32_t* d_children, const int32_t* d_info, const uint64_t* d_n_kept, const uint32_t* d_missing,
                     const double* FP, const double* FN, const double* w_max, int32_t n_w, const double* d_soft, int32_t n_br,
-                    scs_lrt_plan* plan, int32_t* d_status, void* stream);
+                    scs_lrt_plan* plan, int32_t* d_status, void* d_workspace, void* stream);
 /* The model line of the reference's TSV (:722-724) for every group, host only: "{muts}\t{FN:.4f}\t{FP:.4f}" and, per
  * w_max, "\t{LR:0>5.3f}\t{dof}\t{p_val}\tH{hyp}" with Python's number formatting.  out: [n_groups][n_w][8] as
  * scs_lrt_plan_run writes it.  Rows are written back to back into buf; row g is buf[row_off[g] .. row_off[g + 1]). */

@@ -180,27 +180,6 @@ scs_sweep_branch_order_kernel(const int* __restrict__ children, int n_rows, cons
     }
 }
 
-struct SweepBuffers {
-    double* wn = nullptr;
-    int* scratch = nullptr;
-    int* status = nullptr;
-    double* consts = nullptr;      // FP[G], FN[G], w_max[n_w]
-    size_t wn_elems = 0, scratch_elems = 0, status_elems = 0, const_elems = 0;
-};
-
-static thread_local SweepBuffers g_sweep;      // grown, never shrunk: a sweep calls scs_sweep_model once per batch
-
-template <typename T>
-static bool grow(T** p, size_t* have, size_t want) {
-    if (want <= *have) return true;
-    cudaFree(*p);
-    *p = nullptr;
-    *have = 0;
-    if (cudaMalloc(p, want * sizeof(T)) != cudaSuccess) return false;
-    *have = want;
-    return true;
-}
-
 // float.__repr__: the shortest digits that round-trip, fixed notation for 1e-4 <= |v| < 1e16, else d.ddde-XX
 static std::string py_repr(double v) {
     if (std::isnan(v)) return "nan";
@@ -249,44 +228,44 @@ using namespace scs;
 extern "C" {
 
 int scs_gt_reduce_groups(scs_ctx* ctx, const uint8_t* d_gt, int64_t pitch_bytes, int32_t n_groups, const int64_t* d_group_row0,
-                         int64_t max_rows, int32_t n_cells, const uint8_t* col_active, int32_t filter_rows, uint8_t* d_row_keep,
+                         int64_t max_rows, int32_t n_cells, const uint32_t* d_active_mask, int32_t filter_rows, uint8_t* d_row_keep,
                          uint64_t* d_n_kept, uint32_t* d_missing, void* stream) {
-    if (!ctx || !d_gt || !d_group_row0 || !col_active || !d_row_keep || !d_n_kept || !d_missing) return set_error(SCS_ERR_ARG, "null argument");
+    if (!ctx || !d_gt || !d_group_row0 || !d_active_mask || !d_row_keep || !d_n_kept || !d_missing) return set_error(SCS_ERR_ARG, "null argument");
     if (n_groups <= 0 || n_cells <= 0 || (pitch_bytes & 3) || pitch_bytes * 4 < n_cells) return set_error(SCS_ERR_ARG, "bad shape");
     SCS_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const int n_words = (n_cells + 15) / 16;
-    uint32_t* d_act = static_cast<uint32_t*>(ctx_scratch(ctx, size_t(n_words) * 4));
-    if (!d_act) return set_error(SCS_ERR_OOM, "device scratch allocation failed");
-    std::vector<uint32_t> amask(size_t(n_words), 0u);
-    for (int c = 0; c < n_cells; ++c)
-        if (col_active[c]) amask[size_t(c >> 4)] |= 1u << (2 * (c & 15));
-    SCS_CUDA(cudaMemcpyAsync(d_act, amask.data(), size_t(n_words) * 4, cudaMemcpyHostToDevice, st));
     static_assert(sizeof(long long) == sizeof(int64_t) && sizeof(unsigned long long) == sizeof(uint64_t), "64-bit integer types");
-    return gt_reduce_groups_launch(ctx, d_gt, pitch_bytes, n_groups, reinterpret_cast<const long long*>(d_group_row0), max_rows, n_cells, d_act,
-                                   filter_rows, d_row_keep, reinterpret_cast<unsigned long long*>(d_n_kept), d_missing, st);
+    return gt_reduce_groups_launch(ctx, d_gt, pitch_bytes, n_groups, reinterpret_cast<const long long*>(d_group_row0), max_rows, n_cells,
+                                   d_active_mask, filter_rows, d_row_keep, reinterpret_cast<unsigned long long*>(d_n_kept), d_missing, st);
+}
+
+int64_t scs_sweep_model_workspace(int32_t n_groups, int32_t n_rows, int32_t n_w) {
+    // wn [G][n_w][n_rows] + constants [2 G + n_w] doubles, then [G][3 n_rows] ints (padded to a multiple of 8 bytes)
+    const int64_t dbl = int64_t(n_groups) * n_w * n_rows + 2 * int64_t(n_groups) + n_w;
+    const int64_t ints = int64_t(n_groups) * 3 * n_rows;
+    return dbl * 8 + (ints * 4 + 7) / 8 * 8;
 }
 
 int scs_sweep_model(scs_ctx* ctx, int32_t n_groups, int32_t n_rows, int32_t n_cells, int64_t pitch_words, const uint32_t* d_bits,
                     const int32_t* d_children, const int32_t* d_info, const uint64_t* d_n_kept, const uint32_t* d_missing,
                     const double* FP, const double* FN, const double* w_max, int32_t n_w, const double* d_soft, int32_t n_br,
-                    scs_lrt_plan* plan, int32_t* d_status, void* stream) {
-    if (!ctx || !d_bits || !d_children || !d_info || !d_n_kept || !d_missing || !FP || !FN || !w_max || !d_soft || !plan || !d_status)
+                    scs_lrt_plan* plan, int32_t* d_status, void* d_workspace, void* stream) {
+    if (!ctx || !d_bits || !d_children || !d_info || !d_n_kept || !d_missing || !FP || !FN || !w_max || !d_soft || !plan || !d_status || !d_workspace)
         return set_error(SCS_ERR_ARG, "null argument");
     if (n_groups <= 0 || n_rows <= 0 || n_cells <= 0 || n_w <= 0 || n_br < 2) return set_error(SCS_ERR_ARG, "bad shape");
+    if (reinterpret_cast<uintptr_t>(d_workspace) & 7) return set_error(SCS_ERR_ARG, "the workspace must be 8-byte aligned");
     SCS_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    SweepBuffers& b = g_sweep;
-    if (!grow(&b.wn, &b.wn_elems, size_t(n_groups) * n_w * n_rows) || !grow(&b.scratch, &b.scratch_elems, size_t(n_groups) * 3 * n_rows) ||
-        !grow(&b.consts, &b.const_elems, size_t(2) * n_groups + n_w))
-        return set_error(SCS_ERR_OOM, "device allocation failed for the sweep model");
+    double* d_wn = static_cast<double*>(d_workspace);
+    double* d_consts = d_wn + size_t(n_groups) * n_w * n_rows;
+    int* d_scratch = reinterpret_cast<int*>(d_consts + 2 * size_t(n_groups) + n_w);
     std::vector<double> consts(size_t(2) * n_groups + n_w);
     for (int g = 0; g < n_groups; ++g) {
         consts[size_t(g)] = FP[g];
         consts[size_t(n_groups) + g] = FN[g];
     }
     for (int w = 0; w < n_w; ++w) consts[size_t(2) * n_groups + w] = w_max[w];
-    SCS_CUDA(cudaMemcpyAsync(b.consts, consts.data(), consts.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    SCS_CUDA(cudaMemcpyAsync(d_consts, consts.data(), consts.size() * sizeof(double), cudaMemcpyHostToDevice, st));   // (pageable: staged before the call returns)
     int32_t *d_child = nullptr, *d_gather = nullptr;
     double* d_w = nullptr;
     int rc = scs_lrt_plan_device_inputs(plan, int64_t(n_groups) * n_rows, &d_child, &d_gather, &d_w);
@@ -294,9 +273,9 @@ int scs_sweep_model(scs_ctx* ctx, int32_t n_groups, int32_t n_rows, int32_t n_ce
     const size_t smem = (size_t(n_cells) + n_rows + SW_THREADS) * sizeof(double);
     if (smem > 48 * 1024) cudaFuncSetAttribute(scs_sweep_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     scs_sweep_weights_kernel<<<n_groups, SW_THREADS, smem, st>>>(d_bits, pitch_words, n_rows, n_cells, d_info,
-                                                                  reinterpret_cast<const unsigned long long*>(d_n_kept), d_missing, b.consts,
-                                                                  b.consts + n_groups, b.consts + 2 * size_t(n_groups), n_w, b.wn, d_status);
-    scs_sweep_branch_order_kernel<<<n_groups, 64, 0, st>>>(d_children, n_rows, d_info, d_soft, b.wn, n_w, n_br, d_child, d_gather, d_w, b.scratch,
+                                                                  reinterpret_cast<const unsigned long long*>(d_n_kept), d_missing, d_consts,
+                                                                  d_consts + n_groups, d_consts + 2 * size_t(n_groups), n_w, d_wn, d_status);
+    scs_sweep_branch_order_kernel<<<n_groups, 64, 0, st>>>(d_children, n_rows, d_info, d_soft, d_wn, n_w, n_br, d_child, d_gather, d_w, d_scratch,
                                                            d_status);
     SCS_CUDA(cudaGetLastError());
     return SCS_OK;

@@ -546,6 +546,12 @@ class ReplicateSweep:
         self.d_y = torch.zeros(G * self.n_rows, dtype=torch.float64, device=d)
         self.d_out = torch.zeros((G * self.n_w, 8), dtype=torch.float64, device=d)
         self.d_status = torch.zeros(G, dtype=torch.int32, device=d)
+        amask = np.zeros((self.n_cols + 15) // 16, dtype=np.uint32)
+        for c in range(self.n_cols):
+            if self.active[c]:
+                amask[c >> 4] |= np.uint32(1 << (2 * (c & 15)))
+        self.d_amask = torch.as_tensor(amask.view(np.int32), device=d)
+        self.d_work = torch.empty(int(lib().scs_sweep_model_workspace(G, self.n_rows, self.n_w)) // 8, dtype=torch.float64, device=d)
         # pinned staging for the small host <-> device transfers (asynchronous copies need page-locked memory)
         self.h_bits = torch.empty((G, self.n_rows, self.words), dtype=torch.int32, pin_memory=True)
         self.h_children = torch.empty((G, self.n_rows, 2), dtype=torch.int32, pin_memory=True)
@@ -600,14 +606,14 @@ class ReplicateSweep:
             self.d_info.copy_(self.h_info, non_blocking=True)
             sh = _stream_handle(st)
             check(lib().scs_gt_reduce_groups(self.ctx._h, _dev_ptr(d_gt), int(self.pitch), self.G, _dev_ptr(self.d_row0), int(self.group_snvs.max()),
-                                             self.n_cols, ptr(self.active), int(self.has_outg), _dev_ptr(self.d_keep), _dev_ptr(self.d_nkept),
+                                             self.n_cols, _dev_ptr(self.d_amask), int(self.has_outg), _dev_ptr(self.d_keep), _dev_ptr(self.d_nkept),
                                              _dev_ptr(self.d_missing), sh))
             self.place.set_clades(self.d_bits, self.words, stream=st)
             self.place.set_genotypes(d_gt, self.pitch, self.d_keep, stream=st)
             self.place.run(FP, FN, self.d_y, stream=st)
             check(lib().scs_sweep_model(self.ctx._h, self.G, self.n_rows, self.n_cols, int(self.words), _dev_ptr(self.d_bits), _dev_ptr(self.d_children),
                                         _dev_ptr(self.d_info), _dev_ptr(self.d_nkept), _dev_ptr(self.d_missing), ptr(FP), ptr(FN), ptr(self.w_maxs),
-                                        self.n_w, _dev_ptr(self.d_y), self.n_br, self._lrt, _dev_ptr(self.d_status), sh))
+                                        self.n_w, _dev_ptr(self.d_y), self.n_br, self._lrt, _dev_ptr(self.d_status), _dev_ptr(self.d_work), sh))
             check(lib().scs_lrt_plan_run(self._lrt, _dev_ptr(self.d_y), _dev_ptr(self.d_out), None, sh))
             self.h_out.copy_(self.d_out, non_blocking=True)
             self.h_nkept.copy_(self.d_nkept, non_blocking=True)
