@@ -5,8 +5,9 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...        (the reference's CPU algorithm, rank 0 only)
 
-Workload (BASELINE.json configs[3]): 10,000 cells x 1,000,000 SNVs PER GPU, SNV
-rows sharded over ranks (weak scaling), one all-reduce of the 2n branch weights,
+Workload (BASELINE.json configs[3]): ONE dataset of 10,000 cells x 1,000,000 SNVs, its
+SNV rows block-partitioned over the ranks (strong scaling; the 1M-SNVs-per-GPU variant
+is measured beside it as `weak_scaling`), one all-reduce of the 2n branch weights,
 then the clock LRT for the ten default w_max values.  One "step" is one pass of
 the hot path over the resident packed genotype matrix:
     row filter + missing rates (scs_gt_reduce) -> placement -> [all-reduce] -> LRT batch -> result to host,
@@ -38,20 +39,6 @@ sys.path.insert(0, REPO)
 W_MAXS = [100.0, 200.0, 300.0, 400.0, 500.0, 600.0, 700.0, 800.0, 900.0, 1000.0]
 FN_TRUE, FP_TRUE, MS_TRUE = 0.10, 0.01, 0.15
 METRIC = "snv_branch_placements_per_s"
-# dram__bytes_read.sum + dram__bytes_write.sum of one scs_place_kernel launch at the default
-# workload, from the ncu --set full capture under profiles/ (None until a capture exists)
-# (profiles/r01_ncu_place_radix_summary.txt: 287.1 GB read + 2.5 GB written, pass 1, radix mode;
-# earlier captures of the same kernel read 280-310 GB -- it depends on how the L2 halves fill)
-NCU_TRAFFIC_BYTES = 289.6e9
-# pass 1 that also fills the count cache (profiles/r01_ncu_place_cache_summary.txt, 250k-SNV capture x 4:
-# 222.8 GB read + 82.7 GB written) and the interval kernel (profiles/r01_ncu_interval_summary.txt, captured at
-# the full size: 2.52 GB read = the permuted genotypes once, 0.30 GB of per-run partials written)
-NCU_TRAFFIC_BYTES_CACHE = 305.5e9
-NCU_TRAFFIC_BYTES_INTERVAL = 2.82e9
-# warp instructions the interval kernel executes per SNV at 10,001 columns x 20,000 clade rows
-# (smsp__inst_executed.sum of profiles/r01_ncu_interval_final_250k_summary.txt / 250,000 SNVs)
-NCU_INTERVAL_WARP_INST_PER_SNV = 5282607802.0 / 250000.0
-
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -60,7 +47,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cells", type=int, default=10000)
-    ap.add_argument("--snvs", type=int, default=1000000, help="SNVs per GPU")
+    ap.add_argument("--snvs", type=int, default=1000000, help="SNVs of the dataset (block-partitioned over the GPUs)")
+    ap.add_argument("--no-weak-leg", action="store_true", help="N > 1: skip the extra weak-scaling measurement (--snvs rows on every rank)")
+    ap.add_argument("--no-small-leg", action="store_true", help="N = 1: skip the BASELINE configs[2] leg (1,000 cells x 100k SNVs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-e2e", action="store_true")
@@ -149,57 +138,101 @@ def cpu_port_baseline(tree, S, n_cells, seconds):
     from oracle import c_oracle
     cores = os.cpu_count() or 1
     n_rows = S.shape[0]
-    probe = max(cores, 8)
-    codes = cpu_sample_inputs(tree, n_cells, probe)
-    t0 = time.perf_counter()
-    c_oracle.place(codes, S, FP_TRUE, FN_TRUE, cores)
-    dt = time.perf_counter() - t0
-    n_sample = int(min(max(probe, seconds / max(dt / probe, 1e-9)), 200000))
-    n_sample = max(cores, n_sample // cores * cores)
-    codes = cpu_sample_inputs(tree, n_cells, n_sample)
-    t0 = time.perf_counter()
-    c_oracle.place(codes, S, FP_TRUE, FN_TRUE, cores)
-    dt = time.perf_counter() - t0
+    # grow the sample until one call takes at least ~2/3 of the budget (the first call also pays thread start-up and first touch)
+    n_sample = max(cores, 8)
+    while True:
+        codes = cpu_sample_inputs(tree, n_cells, n_sample)
+        t0 = time.perf_counter()
+        c_oracle.place(codes, S, FP_TRUE, FN_TRUE, cores)
+        dt = time.perf_counter() - t0
+        if dt >= 0.66 * seconds or n_sample >= 200000:
+            break
+        n_sample = int(min(200000, max(2 * n_sample, n_sample * 0.9 * seconds / max(dt, 1e-3)))) // cores * cores
     return {"value": n_sample * n_rows / dt, "unit": "placements/s", "cores": cores, "kind": "port",
             "sample": "%d SNVs x %d clade rows x %d cells of the same workload, oracle/place_oracle.c (OpenMP), %.1f s" % (n_sample, n_rows, n_cells, dt)}
 
 
 def reference_arm(args):
-    """The reference's own algorithm for the path -- map_mutations_gt's per-SNV NumPy
-    loop (run_PT_test.py:421-430), restated in oracle/pt_oracle.py because the Python
-    reference cannot travel to the GPU box -- on this box's host cores."""
+    """The reference's own CPU implementation of the path on this box's host cores, rank 0 only.
+
+    kind "reference": the UNMODIFIED reference module (oracle/_ref/run_PT_test.py, a byte-for-byte copy made by
+    oracle/ref_module.make() in the build container; ete3 served by the tree.py stand-in) -- its read_tree (:210-334) parses
+    the bench's Newick file, its map_mutations_gt (:386-448) is called on a pandas frame of a bounded sample of SNVs of
+    the bench's 10,000-cell workload.  map_mutations_gt rebuilds its 2n x n clade matrices on every call (the reference
+    calls it once per w_max); that fixed cost stays outside the timed steps and is reported separately, so `value` is the
+    marginal per-SNV rate -- the figure that extrapolates to 1M SNVs, and the one that flatters the reference.
+    kind "port" (only when oracle/_ref is missing): the same per-SNV loop as restated in oracle/pt_oracle.py."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import pt_oracle as O
-    tree = make_tree(args.cells)
-    S = tree.clade_matrix().astype(np.float64)
-    n_rows = S.shape[0]
-    # a bounded sample: a few SNVs per step (each costs ~8 passes over a 2n x n float64 matrix), sized so
-    # that the whole --steps/--warmup run stays around two minutes whatever K and W the caller asks for
+    from oracle import ref_module
+    tree_s = make_tree(args.cells)
+    n_rows = 2 * args.cells            # 2n - 1 clade rows of the n + 1 sample columns ... + the reference's extra "FP" row
     per_snv = 2.4e-8 * n_rows * args.cells * 1.0
     n_sample = int(max(1, min(64, round(120.0 / (args.steps + args.warmup) / max(per_snv, 1e-3)))))
-    codes = cpu_sample_inputs(tree, args.cells, n_sample * (args.steps + args.warmup))
-    muts = np.where(codes == 3, np.nan, codes.astype(float))
-    times = []
-    for it in range(args.warmup + args.steps):
-        chunk = muts[it * n_sample:(it + 1) * n_sample]
+    codes = cpu_sample_inputs(tree_s, args.cells, n_sample * (args.steps + args.warmup))
+    times = []      # (about two minutes of per-SNV work whatever K and W, plus the reference's one-off set-up)
+    if ref_module.available():
+        import pandas as pd
+        ref = ref_module.load()
+        names = ["tumcell%05d" % (i + 1) for i in range(args.cells)]
+        tmp = tempfile.mkdtemp(prefix="scs_ref_")
+        tree_file = os.path.join(tmp, "bench.newick")
+        with open(tree_file, "w") as f:
+            f.write(tree_s.newick(names, "healthycell", scale=0.05))
         t0 = time.perf_counter()
-        O.map_mutations_gt_literal(chunk, S, FP_TRUE, FN_TRUE)
-        dt = time.perf_counter() - t0
-        if it >= args.warmup:
-            times.append(dt)
+        tree, outg, _, _ = ref.read_tree(tree_file, np.array(names + ["healthycell"]))
+        t_tree = time.perf_counter() - t0
+        # one extra SNV closes the last step's interval
+        codes = np.concatenate([codes, cpu_sample_inputs(tree_s, args.cells, 1, seed=98)], axis=0)
+        muts = pd.DataFrame(np.where(codes == 3, np.nan, codes.astype(float)), columns=names)      # (the outgroup column is dropped before the call, :350)
+        # map_mutations_gt rebuilds its 2n x n clade matrices on every call (65 s at 10,000 cells), so the K + W steps are ONE
+        # call over (K + W) * n_sample SNVs; step boundaries are time stamps taken where its per-SNV loop enters
+        # _normalize_log_probs (:431) -- a stamp on a module attribute, the loop body itself is untouched.
+        stamps = []
+        inner = ref._normalize_log_probs
+
+        def stamped(*a, **k):
+            stamps.append(time.perf_counter())
+            return inner(*a, **k)
+
+        ref._normalize_log_probs = stamped
+        t0 = time.perf_counter()
+        M = ref.map_mutations_gt(tree, muts, FP_TRUE, FN_TRUE / 2)
+        t_setup = stamps[0] - t0
+        ref._normalize_log_probs = inner
+        n_rows = M.shape[1]
+        for it in range(args.warmup, args.warmup + args.steps):
+            times.append(stamps[(it + 1) * n_sample] - stamps[it * n_sample])
+        kind = "reference"
+        sample = ("%d SNV(s) per step: ONE call of the unmodified reference's map_mutations_gt (run_PT_test.py:386-448, oracle/_ref) over %d SNVs "
+                  "on its own read_tree (%.1f s, untimed), steps cut at its per-SNV loop's entry into _normalize_log_probs; the call's build of "
+                  "the %d x %d clade matrices (%.1f s, the reference repeats it per w_max) is outside the steps; single process (the loop is "
+                  "single-threaded NumPy and holds ~%.0f GB)"
+                  % (n_sample, len(muts), t_tree, n_rows, args.cells, t_setup, 6 * 8 * n_rows * args.cells / 1e9))
+    else:
+        from oracle import pt_oracle as O
+        S = tree_s.clade_matrix().astype(np.float64)
+        n_rows = S.shape[0]
+        muts = np.where(codes == 3, np.nan, codes.astype(float))
+        for it in range(args.warmup + args.steps):
+            chunk = muts[it * n_sample:(it + 1) * n_sample]
+            t0 = time.perf_counter()
+            O.map_mutations_gt_literal(chunk, S, FP_TRUE, FN_TRUE / 2)
+            dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                times.append(dt)
+        kind = "port"
+        sample = ("%d SNVs per step: map_mutations_gt's per-SNV NumPy loop (run_PT_test.py:421-430) as restated in oracle/pt_oracle.py "
+                  "(oracle/_ref missing); single process" % n_sample)
     ms = 1e3 * float(np.mean(times))
     value = n_sample * n_rows / (ms / 1e3)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "placements/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "coalescent %d cells x %d SNVs per GPU (BASELINE configs[3]); reference arm runs a bounded sample" % (args.cells, args.snvs),
-                       "cells": args.cells, "snvs_per_gpu": args.snvs, "clade_rows": n_rows, "w_max": W_MAXS},
-            "cpu_baseline": {"value": value, "unit": "placements/s", "cores": 1, "kind": "port",
-                             "sample": "%d SNVs per step: map_mutations_gt's per-SNV NumPy loop (run_PT_test.py:421-430) as restated in "
-                                       "oracle/pt_oracle.py; single process (the loop is single-threaded NumPy and needs ~%.0f GB at this size)"
-                                       % (n_sample, 6 * 8 * n_rows * args.cells / 1e9)},
+            "config": {"workload": "coalescent %d cells x %d SNVs (BASELINE configs[3]); reference arm runs a bounded sample" % (args.cells, args.snvs),
+                       "cells": args.cells, "snvs": args.snvs, "clade_rows": n_rows, "w_max": W_MAXS},
+            "cpu_baseline": {"value": value, "unit": "placements/s", "cores": 1, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "placements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -207,9 +240,10 @@ def reference_arm(args):
 # ------------------------------------------------------- replicate-sweep leg
 def sweep_cpu_baseline(tree_s, names, codes, tmp, seconds):
     """PT tests/s of the reference's per-(pair, w_max) loop body (run_PT_test.py:713-718: get_gt_tree -- placement and
-    branch weights --, get_model_data, get_LRT_poisson with SciPy trust-constr) as restated in oracle/pt_oracle.py, on ONE
-    replicate of the sweep's shape and as many w_max values as fit the time budget; single process like the reference."""
-    from oracle import pt_oracle as O
+    branch weights --, get_model_data, get_LRT_poisson with SciPy trust-constr) on ONE replicate of the sweep's shape and as
+    many w_max values as fit the time budget; single process like the reference.  The unmodified reference module
+    (oracle/_ref, kind "reference") when it is there, else its restatement in oracle/pt_oracle.py (kind "port")."""
+    from oracle import ref_module
     tf = os.path.join(tmp, "cpu_rep.raxml.bestTree")
     with open(tf, "w") as f:
         f.write(tree_s.newick(names[:-1], "healthycell", scale=0.05))
@@ -217,21 +251,39 @@ def sweep_cpu_baseline(tree_s, names, codes, tmp, seconds):
         f.write("SEQ_ERROR: %.6f,  ADO_RATE: %.6f\n" % (FP_TRUE, FN_TRUE))
     muts = np.where(codes == 3, np.nan, codes.astype(float))
     muts = np.concatenate([muts, np.zeros((muts.shape[0], 1))], axis=1)
-    mut = {"muts": muts, "samples": np.array(names)}
-    t0 = time.perf_counter()
     done = 0
-    for w_max in W_MAXS:
-        r = O.get_gt_tree(tf, mut, w_max)
-        Y, constr, init, wn, cols = O.get_model_data(r["tree"])
-        with np.errstate(all="ignore"):
-            O.get_LRT_poisson(Y, constr, init, wn[:, 0])
-        done += 1
-        if time.perf_counter() - t0 > seconds:
-            break
-    dt = time.perf_counter() - t0
-    return {"value": done / dt, "unit": "PT tests/s", "cores": 1, "kind": "port",
+    if ref_module.available():
+        import pandas as pd
+        ref = ref_module.load()
+        call_data = (pd.DataFrame(muts, columns=list(names)),)
+        t0 = time.perf_counter()
+        for w_max in W_MAXS:
+            tree, FP, FN, M = ref.get_gt_tree(tf, call_data, w_max)
+            Y, constr, init, wn, cols = ref.get_model_data(tree)
+            ref.get_LRT_poisson(Y, constr, init, wn[:, 0])
+            done += 1
+            if time.perf_counter() - t0 > seconds:
+                break
+        dt = time.perf_counter() - t0
+        np.seterr(all="warn")          # the reference module sets a process-wide np.seterr(all='raise') on import
+        kind, what = "reference", "the unmodified reference's get_gt_tree / get_model_data / get_LRT_poisson (oracle/_ref)"
+    else:
+        from oracle import pt_oracle as O
+        mut = {"muts": muts, "samples": np.array(names)}
+        t0 = time.perf_counter()
+        for w_max in W_MAXS:
+            r = O.get_gt_tree(tf, mut, w_max)
+            Y, constr, init, wn, cols = O.get_model_data(r["tree"])
+            with np.errstate(all="ignore"):
+                O.get_LRT_poisson(Y, constr, init, wn[:, 0])
+            done += 1
+            if time.perf_counter() - t0 > seconds:
+                break
+        dt = time.perf_counter() - t0
+        kind, what = "port", "oracle/pt_oracle.py"
+    return {"value": done / dt, "unit": "PT tests/s", "cores": 1, "kind": kind,
             "sample": "%d (pair, w_max) tests of one replicate (%d cells x %d SNVs): placement + branch weights + model data + SciPy "
-                      "trust-constr LRT per w_max like run_PT_test.py:713-718, oracle/pt_oracle.py, %.1f s" % (done, len(names) - 1, codes.shape[0], dt)}
+                      "trust-constr LRT per w_max like run_PT_test.py:713-718, %s, %.1f s" % (done, len(names) - 1, codes.shape[0], what, dt)}
 
 
 def replicate_sweep(ctx, dev, rank, world, R, n_cells, n_snv, steps, warmup, n_sub=4, cpu_seconds=0.0):
@@ -349,6 +401,151 @@ def replicate_sweep(ctx, dev, rank, world, R, n_cells, n_snv, steps, warmup, n_s
 
 
 # ------------------------------------------------------------------ GPU arm
+class SingleDataset:
+    """One tree + this rank's shard of SNV rows, ready to be timed: the plan, the LRT batch for the ten w_max, the resident
+    step and the host-buffer (e2e) step.  Every rank must construct it at the same time (one all-reduce inside)."""
+
+    def __init__(self, ctx, dev, rank, world, n_cells, n_local, algo, e2e=True, e2e_chunks=0, tree_seed=1234, seed=1000):
+        import torch
+        from scsommerclock_b200 import engine, run_PT_test as P, sharding, synth
+        self.ctx, self.dev, self.world, self.n_cells, self.n_local = ctx, dev, world, n_cells, n_local
+        # ---- the tree (same on every rank), through the product's own tree code
+        self.tree_s = tree_s = make_tree(n_cells, seed=tree_seed)
+        names = ["tumcell%05d" % (i + 1) for i in range(n_cells)]
+        self.columns = columns = names + ["healthycell"]
+        tmp = tempfile.mkdtemp(prefix="scs_bench_")
+        tree_file = os.path.join(tmp, "bench_r%d.newick" % rank)
+        with open(tree_file, "w") as f:
+            f.write(tree_s.newick(names, "healthycell", scale=0.05))
+        tree, outg, _, _ = P.read_tree(tree_file, np.array(columns))
+        self.active = active = np.array([c != outg for c in columns], dtype=np.uint8)
+        self.bits, self.words, nodes = P._clade_bits(tree, columns, active)
+        self.n_rows = n_rows = self.bits.shape[0]
+        self.n_cols = n_cols = len(columns)
+        # ---- this rank's shard of SNV rows, generated on the device in the packed layout
+        lo = torch.as_tensor(tree_s.lo[:-1], device=dev)
+        hi = torch.as_tensor(tree_s.hi[:-1], device=dev)
+        rate = torch.as_tensor(tree_s.branch_len[:-1], device=dev, dtype=torch.float32)
+        self.packed, self.pitch, _ = synth.observe_packed_torch(lo, hi, torch.as_tensor(tree_s.leaf_rank), n_local, FN_TRUE, FP_TRUE, MS_TRUE, dev,
+                                                                seed=seed + rank, rate=rate, extra_cols=1)
+        torch.cuda.synchronize()
+        self.FP, self.FN = FP_TRUE, FN_TRUE / 2        # what get_gt_tree would pass for a CellPhy log with these rates
+        os.environ["SCS_PLACE_ALGO"] = algo
+        self.plan = engine.Placement(ctx, n_local, n_cols, n_rows)
+        self.plan.set_clades_host(self.bits, self.words)
+        self.y_dev = torch.zeros(n_rows, dtype=torch.float64, device=dev)
+        self.stream = torch.cuda.current_stream()
+        # ---- one untimed pass fixes the LRT model (branch order, weights) for the timed steps
+        self.place_step()
+        n_kept, miss = self.plan.prepare_result(stream=self.stream)
+        torch.cuda.synchronize()
+        soft = self.y_dev.cpu().numpy()
+        if world > 1:
+            t = torch.tensor(np.concatenate([[float(n_kept)], miss * n_kept]), dtype=torch.float64, device=dev)
+            sharding.allreduce_soft_weights(t)
+            n_kept = float(t[0].item())
+            miss = (t[1:] / n_kept).cpu().numpy()
+        FP, FN = self.FP, self.FN
+        MS_i = {c: float(np.clip(miss[i], P.LAMBDA_MIN, 1 - FN - 0.2)) for i, c in enumerate(columns) if active[i]}
+        st = {"soft": soft, "MS_i": MS_i, "n_muts": n_kept, "bits": self.bits, "words": self.words, "columns": columns, "weights": {}}
+        P._apply_placement(tree, st)
+        name_row = {n.name: i for i, n in enumerate(nodes)}
+        childs, weights, gathers = [], [], []
+        for w_max in W_MAXS:
+            P.add_br_weights(tree, FP, FN, MS_i, w_max, _state=st)
+            Y, constr, init, wn, cols = P.get_model_data(tree)
+            childs.append(constr.child_int)
+            weights.append(wn[:, 0].copy())
+            gathers.append(np.array([name_row[c] for c in cols], dtype=np.int32))
+        self.lrt = engine.LrtPlan(ctx, childs)
+        self.lrt.set_weights(weights)
+        self.lrt.set_gather(np.concatenate(gathers), n_rows)
+        self.lrt_out = torch.zeros((len(W_MAXS), 8), dtype=torch.float64, device=dev)
+        self.pinned = self.streamer = None
+        if e2e:
+            self.pinned = torch.empty(self.packed.shape, dtype=torch.uint8, pin_memory=True)
+            self.pinned.copy_(self.packed)
+            torch.cuda.synchronize()
+            # host-buffer path: the packed matrix is streamed from pinned host memory in SNV-row chunks
+            # (H2D of chunk c+1 under the kernels of chunk c), see engine.StreamingPlacement
+            self.streamer = engine.StreamingPlacement(ctx, n_local, n_cols, n_rows, n_chunks=e2e_chunks or None, pitch=self.pitch)
+            self.streamer.set_clades_host(self.bits, self.words)
+
+    def place_step(self):
+        from scsommerclock_b200 import sharding
+        # row filter + per-cell missing counts + (interval path) the cell-order pass: one read of the packed matrix, counters
+        # stay on the device; GEMM path: the two reduction kernels + the operand plane(s)
+        self.plan.prepare(self.packed, self.pitch, self.active, True, stream=self.stream)
+        self.plan.run(self.FP, self.FN, self.y_dev, stream=self.stream)
+        sharding.allreduce_soft_weights(self.y_dev)
+
+    def step(self):
+        self.place_step()
+        self.lrt.run(self.y_dev, self.lrt_out, stream=self.stream)
+        return self.lrt_out.cpu()             # the step's result, read back to the host
+
+    def step_e2e(self):
+        from scsommerclock_b200 import sharding
+        self.streamer.run(self.pinned, self.pitch, self.active, True, self.FP, self.FN, self.y_dev)
+        sharding.allreduce_soft_weights(self.y_dev)
+        self.lrt.run(self.y_dev, self.lrt_out, stream=self.stream)
+        return self.lrt_out.cpu()
+
+    def d2h_bytes(self):
+        return int(self.lrt_out.numel() * 8 + self.n_cols * 4 + 8)
+
+    def close(self):
+        import torch
+        if self.streamer is not None:
+            self.streamer.close()
+        self.plan.close()
+        self.lrt.close()
+        self.packed = self.pinned = self.streamer = None
+        torch.cuda.empty_cache()
+
+
+def timed(fn, steps, warmup, plan, dev, sampler=None, lrt_launches_per_step=1):
+    """W untimed + K timed steps between barriers and synchronisations; CUDA events; max over ranks.
+    Returns (total ms, per-step plan kernel times, last result, this library's launches inside the timed region)."""
+    import torch
+    from scsommerclock_b200 import sharding
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    sharding.barrier()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.start()
+    l0 = plan.info()["launches"]
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    times = []
+    e0.record()
+    for _ in range(steps):
+        res = fn()
+        times.append(plan.last_times())
+    e1.record()
+    torch.cuda.synchronize()
+    sharding.barrier()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.stop_flag.set()
+    ms = e0.elapsed_time(e1)
+    # this library's kernels inside the timed region: plan launches (pre-pass, placement, reduce / operand expansion,
+    # two GEMM passes, merge, reduce) + the LRT kernel of every step
+    n_launch = plan.info()["launches"] - l0 + steps * lrt_launches_per_step
+    return sharding.max_over_ranks(ms, dev), times, res, n_launch
+
+
+def ncu_constants():
+    """Per-launch figures that only a profiler can give (DRAM bytes, executed warp instructions), read from the summary
+    the capture script wrote under profiles/ -- never pasted into this file.  {} when no capture of the current kernel exists."""
+    try:
+        return json.load(open(os.path.join(REPO, "profiles", "r02_ncu_constants.json")))
+    except Exception:
+        return {}
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -361,173 +558,101 @@ def main():
     result_fd = os.dup(1)
     os.dup2(2, 1)
     import torch
-    from scsommerclock_b200 import engine, run_PT_test as P, sharding, synth
+    from scsommerclock_b200 import engine, sharding
     rank, world, local = sharding.init_distributed()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     ctx = engine.Context(local)
-    n_cells, n_snv = args.cells, args.snvs
+    n_cells, n_total = args.cells, args.snvs
     pk, pk_kind = peaks()
+    ncu = ncu_constants()
 
-    # ---- the tree (same on every rank), through the product's own tree code
-    tree_s = make_tree(n_cells)
-    names = ["tumcell%05d" % (i + 1) for i in range(n_cells)]
-    columns = names + ["healthycell"]
-    tmp = tempfile.mkdtemp(prefix="scs_bench_")
-    tree_file = os.path.join(tmp, "bench_r%d.newick" % rank)
-    with open(tree_file, "w") as f:
-        f.write(tree_s.newick(names, "healthycell", scale=0.05))
-    tree, outg, _, _ = P.read_tree(tree_file, np.array(columns))
-    active = np.array([c != outg for c in columns], dtype=np.uint8)
-    bits, words, nodes = P._clade_bits(tree, columns, active)
-    n_rows = bits.shape[0]
-    n_cols = len(columns)
-
-    # ---- this rank's shard of SNV rows, generated on the device in the packed layout
-    lo = torch.as_tensor(tree_s.lo[:-1], device=dev)
-    hi = torch.as_tensor(tree_s.hi[:-1], device=dev)
-    rate = torch.as_tensor(tree_s.branch_len[:-1], device=dev, dtype=torch.float32)
-    packed, pitch, _ = synth.observe_packed_torch(lo, hi, torch.as_tensor(tree_s.leaf_rank), n_snv, FN_TRUE, FP_TRUE, MS_TRUE, dev,
-                                                  seed=1000 + rank, rate=rate, extra_cols=1)
-    torch.cuda.synchronize()
-    FP, FN = FP_TRUE, FN_TRUE / 2        # what get_gt_tree would pass for a CellPhy log with these rates
-
-    os.environ["SCS_PLACE_ALGO"] = args.algo
-    plan = engine.Placement(ctx, n_snv, n_cols, n_rows)
-    plan.set_clades_host(bits, words)
-    row_keep = torch.empty(n_snv, dtype=torch.uint8, device=dev)
-    y_dev = torch.zeros(n_rows, dtype=torch.float64, device=dev)
-    stream = torch.cuda.current_stream()
-
-    def place_step():
-        # row filter + per-cell missing counts + (interval path) the cell-order pass: one read of the packed matrix, counters
-        # stay on the device; GEMM path: the two reduction kernels + the operand plane(s)
-        plan.prepare(packed, pitch, active, True, stream=stream)
-        plan.run(FP, FN, y_dev, stream=stream)
-        sharding.allreduce_soft_weights(y_dev)
-
-    # ---- one untimed pass fixes the LRT model (branch order, weights) for the timed steps
-    place_step()
-    n_kept, miss = plan.prepare_result(stream=stream)
-    torch.cuda.synchronize()
-    soft = y_dev.cpu().numpy()
-    if world > 1:
-        t = torch.tensor(np.concatenate([[float(n_kept)], miss * n_kept]), dtype=torch.float64, device=dev)
-        sharding.allreduce_soft_weights(t)
-        n_kept_all = float(t[0].item())
-        miss = (t[1:] / n_kept_all).cpu().numpy()
-    MS_i = {c: float(np.clip(miss[i], P.LAMBDA_MIN, 1 - FN - 0.2)) for i, c in enumerate(columns) if active[i]}
-    st = {"soft": soft, "MS_i": MS_i, "n_muts": n_kept, "bits": bits, "words": words, "columns": columns, "weights": {}}
-    P._apply_placement(tree, st)
-    row_of = {id(n): i for i, n in enumerate(nodes)}
-    name_row = {n.name: i for i, n in enumerate(nodes)}
-    childs, weights, gathers = [], [], []
-    for w_max in W_MAXS:
-        P.add_br_weights(tree, FP, FN, MS_i, w_max, _state=st)
-        Y, constr, init, wn, cols = P.get_model_data(tree)
-        childs.append(constr.child_int)
-        weights.append(wn[:, 0].copy())
-        gathers.append(np.array([name_row[c] for c in cols], dtype=np.int32))
-    lrt = engine.LrtPlan(ctx, childs)
-    lrt.set_weights(weights)
-    lrt.set_gather(np.concatenate(gathers), n_rows)
-    lrt_out = torch.zeros((len(W_MAXS), 8), dtype=torch.float64, device=dev)
-
-    def step():
-        place_step()
-        lrt.run(y_dev, lrt_out, stream=stream)
-        return lrt_out.cpu()             # the step's result, read back to the host
-
-    pinned = None
-    streamer = None
-    if not args.no_e2e:
-        pinned = torch.empty(packed.shape, dtype=torch.uint8, pin_memory=True)
-        pinned.copy_(packed)
-        torch.cuda.synchronize()
-        # host-buffer path: the packed matrix is streamed from pinned host memory in SNV-row chunks
-        # (H2D of chunk c+1 under the GEMMs of chunk c), see engine.StreamingPlacement
-        streamer = engine.StreamingPlacement(ctx, n_snv, n_cols, n_rows, n_chunks=args.e2e_chunks or None, pitch=pitch)
-        streamer.set_clades_host(bits, words)
-
-    def step_e2e():
-        streamer.run(pinned, pitch, active, True, FP, FN, y_dev)
-        sharding.allreduce_soft_weights(y_dev)
-        lrt.run(y_dev, lrt_out, stream=stream)
-        return lrt_out.cpu()
-
-    def timed(fn, steps, warmup, sampler=None, pl=None):
-        pl = pl or plan
-        for _ in range(warmup):
-            fn()
-        torch.cuda.synchronize()
-        sharding.barrier()
-        torch.cuda.synchronize()
-        if sampler:
-            sampler.start()
-        l0 = pl.info()["launches"]
-        e0 = torch.cuda.Event(enable_timing=True)
-        e1 = torch.cuda.Event(enable_timing=True)
-        gemm = []
-        e0.record()
-        for _ in range(steps):
-            res = fn()
-            gemm.append(pl.last_times())
-        e1.record()
-        torch.cuda.synchronize()
-        sharding.barrier()
-        torch.cuda.synchronize()
-        if sampler:
-            sampler.stop_flag.set()
-        ms = e0.elapsed_time(e1)
-        # this library's kernels inside the timed region: plan launches (pre-pass, placement, reduce / operand expansion,
-        # two GEMM passes, merge, reduce) + 1 LRT kernel per step
-        n_launch = pl.info()["launches"] - l0 + steps
-        return sharding.max_over_ranks(ms, dev), gemm, res, n_launch
+    # ---- BASELINE configs[3]: ONE dataset of n_total SNVs, its rows block-partitioned over the ranks (strong scaling)
+    r_lo, r_hi = sharding.shard_range(n_total, rank, world)
+    n_snv = r_hi - r_lo
+    ds = SingleDataset(ctx, dev, rank, world, n_cells, n_snv, args.algo, e2e=not args.no_e2e, e2e_chunks=args.e2e_chunks)
+    n_rows, n_cols, pitch = ds.n_rows, ds.n_cols, ds.pitch
+    plan = ds.plan
 
     sampler = ClockSampler(local) if rank == 0 else None
-    ms_total, gemm_times, res, launches = timed(step, args.steps, args.warmup, sampler)
+    ms_total, gemm_times, res, launches = timed(ds.step, args.steps, args.warmup, plan, dev, sampler)
     plan_info = plan.info()
     ms_step = ms_total / args.steps
-    placements = float(n_snv) * n_rows * world
+    placements = float(n_total) * n_rows
     value = placements / (ms_step / 1e3)
 
     e2e = None
     if not args.no_e2e:
-        y_ref = y_dev.clone()
-        ms_e2e, _, _, _ = timed(step_e2e, args.steps, min(args.warmup, 1))
-        e2e_dev = float((y_dev - y_ref).abs().max() / y_ref.abs().max())     # streamed == resident, to summation order
+        y_ref = ds.y_dev.clone()
+        ms_e2e, _, _, _ = timed(ds.step_e2e, args.steps, min(args.warmup, 1), plan, dev)
+        e2e_dev = float((ds.y_dev - y_ref).abs().max() / y_ref.abs().max())     # streamed == resident, to summation order
         e2e = {"value": placements / (ms_e2e / args.steps / 1e3), "unit": "placements/s",
-               "h2d_bytes_per_step": int(packed.numel()) * world, "d2h_bytes_per_step": int(lrt_out.numel() * 8 + n_cols * 4 + 8) * world,
-               "ms_per_step": ms_e2e / args.steps, "chunks": streamer.n_chunks, "max_rel_dev_vs_resident": e2e_dev}
+               "h2d_bytes_per_step": int(n_total) * pitch, "d2h_bytes_per_step": ds.d2h_bytes() * world,
+               "ms_per_step": ms_e2e / args.steps, "chunks": ds.streamer.n_chunks, "max_rel_dev_vs_resident": e2e_dev}
 
     # ---- the same workload through the tcgen05 GEMM (north_star's formulation), when the headline ran the interval path
     gemm_leg = None
-    if plan_info["algo"] == 2 and not args.no_gemm_leg:
+    if plan_info["algo"] == 2 and not args.no_gemm_leg and world == 1:
         os.environ["SCS_PLACE_ALGO"] = "gemm"
         plan_g = engine.Placement(ctx, n_snv, n_cols, n_rows)
-        plan_g.set_clades_host(bits, words)
+        plan_g.set_clades_host(ds.bits, ds.words)
         os.environ["SCS_PLACE_ALGO"] = args.algo
-        y_g = torch.zeros_like(y_dev)
-        y_iv = y_dev.clone()
+        y_g = torch.zeros_like(ds.y_dev)
+        y_iv = ds.y_dev.clone()
 
         def step_gemm():
-            plan_g.prepare(packed, pitch, active, True, stream=stream)
-            plan_g.run(FP, FN, y_g, stream=stream)
+            plan_g.prepare(ds.packed, pitch, ds.active, True, stream=ds.stream)
+            plan_g.run(ds.FP, ds.FN, y_g, stream=ds.stream)
             sharding.allreduce_soft_weights(y_g)
-            lrt.run(y_g, lrt_out, stream=stream)
-            return lrt_out.cpu()
+            ds.lrt.run(y_g, ds.lrt_out, stream=ds.stream)
+            return ds.lrt_out.cpu()
 
-        ms_g, g_times, _, _ = timed(step_gemm, 2, 1, pl=plan_g)
-        gemm_leg = {"ms_per_step": ms_g / 2, "value": placements / (ms_g / 2 / 1e3), "times": np.array(g_times), "info": plan_g.info(),
+        ms_g, g_times, _, _ = timed(step_gemm, 3, 3, plan_g, dev)
+        gemm_leg = {"ms_per_step": ms_g / 3, "value": placements / (ms_g / 3 / 1e3), "times": np.array(g_times), "info": plan_g.info(),
                     "max_rel_dev_vs_interval": float((y_g - y_iv).abs().max() / y_iv.abs().max())}
         plan_g.close()
         del plan_g, y_g, y_iv
+    lrt_newton = res.numpy().copy()
+    S_cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        S_cpu = np.ascontiguousarray(engine.unpack_clades(ds.bits, n_cols)[:, :n_cells].astype(np.uint8))
+    tree_main = ds.tree_s
+    ds.close()
+    del ds
+
+    # ---- weak-scaling variant beside it (N > 1): n_total SNVs on EVERY rank, same exchange
+    weak = None
+    if world > 1 and not args.no_weak_leg:
+        dw = SingleDataset(ctx, dev, rank, world, n_cells, n_total, args.algo, e2e=False)
+        ms_w, tw, _, _ = timed(dw.step, 3, 3, dw.plan, dev)
+        weak = {"snvs_per_gpu": n_total, "ms_per_step": ms_w / 3, "steps": 3, "warmup": 3,
+                "value": float(n_total) * world * n_rows / (ms_w / 3 / 1e3), "unit": "placements/s",
+                "placement_kernel_ms": float(np.mean([t[2] for t in tw])),
+                "note": "every rank holds its own %d SNVs (the round-1 headline); value = all ranks' placements / max-over-ranks time" % n_total}
+        dw.close()
+        del dw
+
+    # ---- BASELINE configs[2]: 1,000 cells x 100k SNVs, a single PT test on one B200
+    small = None
+    if world == 1 and not args.no_small_leg:
+        d2 = SingleDataset(ctx, dev, rank, world, 1000, 100000, "auto", e2e=not args.no_e2e, e2e_chunks=1, tree_seed=4321, seed=2000)
+        ms_2, t2, r2, l2 = timed(d2.step, 20, 5, d2.plan, dev)
+        info2 = d2.plan.info()
+        small = {"workload": "coalescent 1000 cells x 100000 SNVs, single PT test (10 w_max) on one GPU (BASELINE configs[2])",
+                 "ms_per_step": ms_2 / 20, "steps": 20, "warmup": 5, "value": 100000.0 * d2.n_rows / (ms_2 / 20 / 1e3), "unit": "placements/s",
+                 "algorithm": "interval" if info2["algo"] == 2 else "tcgen05 GEMM", "gpu_launches": int(l2),
+                 "kernel_ms": {"pass1_or_prepass": float(np.mean([t[0] for t in t2])), "merge": float(np.mean([t[1] for t in t2])),
+                               "pass2_or_placement": float(np.mean([t[2] for t in t2])), "reduce": float(np.mean([t[3] for t in t2]))},
+                 "lrt_status": [int(v) for v in r2.numpy()[:, 7]], "newton_iterations": [int(v) for v in r2.numpy()[:, 6]]}
+        if not args.no_e2e:
+            ms_2e, _, _, _ = timed(d2.step_e2e, 20, 3, d2.plan, dev)
+            small["e2e"] = {"ms_per_step": ms_2e / 20, "value": 100000.0 * d2.n_rows / (ms_2e / 20 / 1e3), "unit": "placements/s",
+                            "h2d_bytes_per_step": 100000 * d2.pitch, "d2h_bytes_per_step": d2.d2h_bytes(), "chunks": d2.streamer.n_chunks}
+        d2.close()
+        del d2
 
     rep = None
     if args.replicates > 0:
-        del pinned, streamer
-        plan.close()
-        del packed
         torch.cuda.empty_cache()
         rep = replicate_sweep(ctx, dev, rank, world, args.replicates, args.rep_cells, args.rep_snvs, max(2, args.steps), 1,
                               cpu_seconds=(args.cpu_seconds if (world == 1 and not args.no_cpu_baseline) else 0.0))
@@ -547,8 +672,11 @@ def main():
             t_gemm = float(np.mean(g[:, 0] if cached else np.concatenate([g[:, 0], g[:, 2]])))   # average launch of the dominant kernel
             flop = 2.0 * n_snv * n_rows * n_cols                             # algorithmic: SNV x cells x clade rows, 2 flop per MAC
             achieved = flop / (t_gemm / 1e3) / 1e12
+            traffic = None
+            if full_size and info["mode"] == 1:
+                traffic = (ncu.get("gemm_cache_pass1") or {}).get("dram_bytes") if cached else (ncu.get("gemm_pass") or {}).get("dram_bytes")
             return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": (NCU_TRAFFIC_BYTES_CACHE if cached else NCU_TRAFFIC_BYTES) if (full_size and info["mode"] == 1) else None,
+                    "traffic": traffic,
                     "peak_source": pk_kind + " cuBLAS bf16, sustained (kernel timed inside a long step)",
                     "kernel": "scs_place_kernel (%s), %s" % (
                         "tcgen05 kind::f8f6f4, one radix-packed e5m2 plane" if info["mode"] == 1 else "tcgen05 kind::i8, two u8 planes",
@@ -566,70 +694,77 @@ def main():
                     "note": "radix mode: one exact FP8 GEMM per contraction (counts packed as C1 + 4096*C0); planes mode: two exact u8 GEMMs"}
 
         if plan_info["algo"] == 2:
-            # interval path: the packed 2-bit genotypes are read once (2 bits per (SNV, cell)); nothing else touches HBM but
-            # the per-run partial sums.  The kernel is bound by instruction issue, not by HBM or the tensor pipe -- of the
-            # two rooflines the contract names, HBM is the one its only off-chip traffic belongs to.
-            t_k = float(g[:, 2].mean())                                      # the placement kernel (g[:, 0]: the cell-order pass before it)
+            # interval path: the packed 2-bit genotypes are read once by the pre-pass (row filter, missing counts, cell order) and the
+            # reordered copy once by the placement kernel; nothing else touches HBM but the per-run partial sums.  The kernel is bound
+            # by instruction issue, not by HBM or the tensor pipe -- of the two rooflines the contract names, HBM is the one its only
+            # off-chip traffic belongs to.
+            t_k = float(g[:, 2].mean())                                      # the placement kernel (g[:, 0]: the pre-pass before it)
             alg_bytes = float(n_snv) * pitch
             hbm_peak = pk.get("hbm_gbs_sustained", pk.get("hbm_gbs"))
+            iv = ncu.get("interval_kernel") or {}
+            scale = float(n_snv) / float(iv["snvs"]) if iv.get("snvs") else None
             roofline = {"bound": "hbm", "achieved": alg_bytes / 1e9 / (t_k / 1e3), "peak": hbm_peak, "unit": "GB/s",
                         "frac": alg_bytes / 1e9 / (t_k / 1e3) / hbm_peak,
-                        "traffic": NCU_TRAFFIC_BYTES_INTERVAL if full_size else None,
+                        "traffic": (iv["dram_bytes"] * scale) if (scale and n_cells == 10000 and iv.get("dram_bytes")) else None,
+                        "traffic_source": iv.get("source") if scale else None,
                         "peak_source": pk_kind + " HBM copy bandwidth",
-                        "kernel": "scs_place_interval%s_kernel (prefix counts in shared memory, no GEMM)" % ("3" if plan_info["interval_variant"] == 3 else ""),
-                        "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": t_k, "permute_ms": float(g[:, 0].mean()),
+                        "kernel": "scs_place_iv%d_kernel (prefix counts in shared memory, no GEMM)" % plan_info["interval_variant"],
+                        "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": t_k, "prepass_ms": float(g[:, 0].mean()),
+                        "prepass_GBps": 2.0 * alg_bytes / 1e9 / (float(g[:, 0].mean()) / 1e3) if g[:, 0].mean() > 0 else None,
                         "reduce_ms": float(g[:, 3].mean()),
                         "entries_per_s": float(n_snv) * n_rows / (t_k / 1e3),
-                        "actual_limiter": "instruction issue (ncu: issue slots 67 % busy, ALU pipe 52 %, 8 warps per scheduler, ~12 cycles between "
-                                          "a warp's instructions); HBM traffic is ~50 GB/s because the algorithm needs O(cells + clade rows) work "
-                                          "per SNV instead of the GEMM's O(cells x clade rows) -- see gemm_path for the tensor-pipe roofline of "
-                                          "the same workload through the tcgen05 GEMM",
+                        "actual_limiter": "instruction issue / shared-memory latency: one 640-thread CTA per SM (5 warps per scheduler); HBM traffic is "
+                                          "~0.1 TB/s because the algorithm needs O(cells + clade rows) work per SNV instead of the GEMM's "
+                                          "O(cells x clade rows) -- see issue_roofline, and gemm_path for the tensor-pipe roofline of the same "
+                                          "workload through the tcgen05 GEMM",
                         "smem_bytes": plan_info["interval_smem_bytes"], "threads": plan_info["interval_threads"], "grid": plan_info["interval_grid"]}
-            if full_size:
+            if scale and n_cells == 10000 and iv.get("warp_instructions"):
               try:
                 # the roofline that does bound it: issue slots (4 schedulers per SM, one warp instruction per cycle each)
                 sm_count = getattr(ctx, "sm_count", 148)
                 clk = ((sampler.summary().get("sm_mhz") if sampler else None) or pk.get("sm_max_mhz", 1965.0)) * 1e6
-                inst = NCU_INTERVAL_WARP_INST_PER_SNV * n_snv
+                inst = iv["warp_instructions"] * scale
                 roofline["issue_roofline"] = {"warp_instructions_per_launch": inst, "achieved_per_s": inst / (t_k / 1e3),
                                               "peak_per_s": sm_count * 4 * clk, "frac": inst / (t_k / 1e3) / (sm_count * 4 * clk),
-                                              "note": "instruction count from the ncu capture of the same kernel (250k SNVs, scaled)"}
+                                              "note": "instruction count: smsp__inst_executed.sum of %s, scaled by SNV count" % iv.get("source")}
               except Exception as exc:          # (an explanatory extra: never lose the line over it)
                 roofline["issue_roofline"] = {"error": repr(exc)}
         else:
             roofline = gemm_roofline(g, plan_info)
         gemm_path = None
         if gemm_leg is not None:
-            gemm_path = {"ms_per_step": gemm_leg["ms_per_step"], "value": gemm_leg["value"], "unit": "placements/s", "steps": 2, "warmup": 1,
+            gemm_path = {"ms_per_step": gemm_leg["ms_per_step"], "value": gemm_leg["value"], "unit": "placements/s", "steps": 3, "warmup": 3,
                          "max_rel_dev_soft_weights_vs_interval": gemm_leg["max_rel_dev_vs_interval"],
                          "roofline": gemm_roofline(gemm_leg["times"], gemm_leg["info"]), "tiling": gemm_leg["info"]}
-        out = res.numpy()
+        out = lrt_newton
         line = {
             "metric": METRIC, "value": value, "unit": "placements/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": ("u16 prefix counts (exact integers), f32 softmax terms on exact integer differences (LRT f64)" if plan_info["algo"] == 2 else
                       "fp8_e5m2 operands holding exact integer counts, f32 accumulate (epilogue f32, LRT f64)" if plan_info["mode"] == 1 else
                       "u8 operands, s32 accumulate (epilogue f32, LRT f64)"),
             "data": "synthetic",
-            "config": {"workload": "coalescent %d cells x %d SNVs per GPU (BASELINE configs[3]), SNV rows sharded, one all-reduce of the branch weights, LRT for 10 w_max"
-                                   % (n_cells, n_snv),
-                       "cells": n_cells, "snvs_per_gpu": n_snv, "clade_rows": n_rows, "w_max": W_MAXS, "FN": FN_TRUE, "FP": FP_TRUE, "missing": MS_TRUE,
+            "config": {"workload": "coalescent %d cells x %d SNVs (BASELINE configs[3]): one dataset, SNV rows block-partitioned over the GPUs, "
+                                   "one all-reduce of the branch weights, LRT for 10 w_max" % (n_cells, n_total),
+                       "cells": n_cells, "snvs": n_total, "snvs_per_gpu": n_snv, "clade_rows": n_rows, "w_max": W_MAXS, "FN": FN_TRUE, "FP": FP_TRUE,
+                       "missing": MS_TRUE,
                        "algorithm": "interval path (tree-shaped clade masks: counts = differences of per-SNV prefix counts)" if plan_info["algo"] == 2 else "tcgen05 GEMM",
-                       "l2": ("inputs larger than L2 (packed genotypes %.1f GB per GPU, read once per step)" % (float(n_snv) * pitch / 1e9)) if plan_info["algo"] == 2 else
+                       "l2": ("inputs larger than L2 (packed genotypes %.2f GB per GPU, read once per step)" % (float(n_snv) * pitch / 1e9)) if plan_info["algo"] == 2 else
                              ("inputs larger than L2 (operand plane(s) %.1f GB per GPU)" % ((1 if plan_info["mode"] == 1 else 2) * float(plan_info["M_pad"]) * plan_info["K_pad"] / 1e9)),
                        "tiling": plan_info},
             "e2e": e2e,
             "gpu_launches": int(launches),
             "roofline": roofline,
             "gemm_path": gemm_path,
+            "weak_scaling": weak,
+            "single_test_1k_cells": small,
             "pt_tests": {"per_step": len(W_MAXS), "LR": [float(v) for v in out[:, 0]], "p_value": [float(v) for v in out[:, 3]],
                          "newton_iterations": [int(v) for v in out[:, 6]], "status": [int(v) for v in out[:, 7]]},
             "clocks": sampler.summary() if sampler else None,
             "replicate_sweep": rep,
         }
-        if world == 1 and not args.no_cpu_baseline:
-            S = engine.unpack_clades(bits, n_cols)[:, :n_cells].astype(np.uint8)
-            line["cpu_baseline"] = cpu_port_baseline(tree_s, np.ascontiguousarray(S), n_cells, args.cpu_seconds)
+        if S_cpu is not None:
+            line["cpu_baseline"] = cpu_port_baseline(tree_main, S_cpu, n_cells, args.cpu_seconds)
         os.write(result_fd, (json.dumps(line) + "\n").encode())
     sharding.barrier()
     if world > 1:

@@ -19,7 +19,9 @@
 // the internal node below branch k, or -1 for a leaf.
 #include <cmath>
 #include <cstdio>
+#include <algorithm>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "scs_internal.h"
@@ -463,6 +465,12 @@ scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ 
     }
 }
 
+}  // namespace scs
+
+#include "scs_lrt_tree.cuh"
+
+namespace scs {
+
 // ------------------------------------------------------------ branch weights
 // add_br_weights (run_PT_test.py:451-502): for every node, the probability that
 // all of its cells dropped out / went missing while the others read wild type:
@@ -520,7 +528,111 @@ struct LrtPlanImpl {
     int threads = 128;
     int smem_bytes = 0;    // > 0: per-CTA working set in shared memory (small trees)
     bool warp_mode = false;   // one warp per problem (trees up to 256 leaves)
+    // cluster-per-problem kernel (scs_lrt_tree.cuh): topology renumbered in level order on the host
+    bool tree_mode = false;
+    int tree_cluster = 1, tree_threads = 512, tree_smem = 0;
+    std::vector<int> h_orig;          // [branch, level-order numbering] -> the caller's branch index (global, with br_off)
+    LrtTreeProblem* t_probs = nullptr;
+    int *t_child = nullptr, *t_up = nullptr, *t_orig = nullptr, *t_levoff = nullptr, *t_gather = nullptr;
+    double *t_w = nullptr, *t_hB = nullptr, *t_slots = nullptr, *t_cD = nullptr, *t_cR = nullptr;
+    int* t_ibuf = nullptr;
+    long long* t_prof = nullptr;
+    double* t_dbuf = nullptr;
 };
+
+// Level-order renumbering of every problem of the batch for scs_lrt_tree_kernel.  top_cap: nodes the leader CTA's shared
+// memory holds (32 bytes each).
+static int lrt_tree_prepare(LrtPlanImpl* pl, int n_prob, const int64_t* br_off, const int32_t* child_int, const std::vector<LrtProblem>& probs) {
+    int top_cap = (227 * 1024 - 1024 - LRT_TREE_LEVSM * 4) / 32;
+    if (const char* ev = getenv("SCS_LRT_TOP_CAP")) top_cap = std::max(0, std::min(top_cap, atoi(ev)));     // test knob: forces levels below the cut
+    const size_t nbr = pl->nbr, nnode = pl->nnode;
+    std::vector<LrtTreeProblem> tp((size_t(n_prob)));
+    std::vector<int> t_child(nbr), t_orig(nbr), t_up(nnode, -1), t_levoff;
+    int max_top = 0, max_lev_smem = 0;
+    for (int p = 0; p < n_prob; ++p) {
+        const int nb = probs[p].n_br, m1 = nb / 2;
+        const int32_t* ch = child_int + br_off[p];
+        std::vector<int> level(size_t(m1), 0), pos(size_t(m1), 0);
+        int nlev = 0;
+        for (int i = 0; i < m1; ++i) {          // children have smaller indices (validated by the caller)
+            int lv = 0;
+            for (int c = 0; c < 2; ++c)
+                if (ch[2 * i + c] >= 0) lv = std::max(lv, level[size_t(ch[2 * i + c])] + 1);
+            level[size_t(i)] = lv;
+            nlev = std::max(nlev, lv + 1);
+        }
+        std::vector<int> off(size_t(nlev) + 1, 0);
+        for (int i = 0; i < m1; ++i) off[size_t(level[size_t(i)]) + 1]++;
+        for (int q = 0; q < nlev; ++q) off[size_t(q) + 1] += off[size_t(q)];
+        std::vector<int> cur(off.begin(), off.end() - 1);
+        for (int i = 0; i < m1; ++i) pos[size_t(i)] = cur[size_t(level[size_t(i)])]++;
+        int* tc = t_child.data() + probs[p].br_off;
+        int* to = t_orig.data() + probs[p].br_off;
+        int* tu = t_up.data() + probs[p].node_off;
+        for (int i = 0; i < m1; ++i)
+            for (int c = 0; c < 2; ++c) {
+                const int k = 2 * pos[size_t(i)] + c, j = ch[2 * i + c];
+                tc[k] = j >= 0 ? pos[size_t(j)] : -1;
+                to[k] = 2 * i + c;
+                if (j >= 0) tu[pos[size_t(j)]] = k;
+            }
+        int qc = 1;
+        while (qc < nlev && m1 - off[size_t(qc)] > top_cap) ++qc;
+        int qw = nlev;
+        while (qw > qc && off[size_t(qw)] - off[size_t(qw) - 1] <= 32) --qw;
+        LrtTreeProblem& t = tp[size_t(p)];
+        t.br_off = probs[p].br_off;
+        t.n_br = nb;
+        t.node_off = probs[p].node_off;
+        t.nlev = nlev;
+        t.lev_off = int(t_levoff.size());
+        t.qc = qc;
+        t.qw = qw;
+        t.s_cut = off[size_t(std::min(qc, nlev))];
+        t_levoff.insert(t_levoff.end(), off.begin(), off.end());
+        max_top = std::max(max_top, m1 - t.s_cut);
+        if (nlev + 1 <= LRT_TREE_LEVSM) max_lev_smem = std::max(max_lev_smem, nlev + 1);
+    }
+    pl->h_orig.resize(nbr);
+    for (int p = 0; p < n_prob; ++p)
+        for (int k = 0; k < probs[p].n_br; ++k) pl->h_orig[size_t(probs[p].br_off) + k] = probs[p].br_off + t_orig[size_t(probs[p].br_off) + k];
+    pl->tree_smem = max_top * 32 + max_lev_smem * 4;
+    const int cl_max = std::max(1, pl->ctx->sm_count / std::max(1, n_prob));
+    pl->tree_cluster = cl_max >= 8 ? 8 : (cl_max >= 4 ? 4 : (cl_max >= 2 ? 2 : 1));
+    if (const char* ev = getenv("SCS_LRT_CLUSTER")) {
+        const int c = atoi(ev);
+        if (c == 1 || c == 2 || c == 4 || c == 8) pl->tree_cluster = c;
+    }
+    const int64_t per_cta = (pl->nbr / size_t(n_prob)) / size_t(pl->tree_cluster);
+    pl->tree_threads = per_cta >= 1024 ? 512 : 256;
+    const size_t ints = 3 * nbr + nnode + t_levoff.size();
+    const size_t dbl = 3 * nbr + nnode + size_t(n_prob) * LRT_TREE_SLOT_DOUBLES;
+    if (cudaMalloc(&pl->t_ibuf, ints * sizeof(int)) != cudaSuccess || cudaMalloc(&pl->t_dbuf, dbl * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&pl->t_probs, size_t(n_prob) * sizeof(LrtTreeProblem)) != cudaSuccess)
+        return set_error(SCS_ERR_OOM, "device allocation failed for the LRT batch");
+    int* iq = pl->t_ibuf;
+    pl->t_child = iq; iq += nbr;
+    pl->t_orig = iq; iq += nbr;
+    pl->t_gather = iq; iq += nbr;
+    pl->t_up = iq; iq += nnode;
+    pl->t_levoff = iq;
+    double* dq = pl->t_dbuf;
+    pl->t_cD = dq; dq += nbr;      // (first: 16-byte aligned pairs)
+    pl->t_cR = dq; dq += nbr;
+    pl->t_w = dq; dq += nbr;
+    pl->t_hB = dq; dq += nnode;
+    pl->t_slots = dq;
+    cudaError_t e = cudaMemcpy(pl->t_child, t_child.data(), nbr * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(pl->t_orig, t_orig.data(), nbr * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(pl->t_gather, pl->h_orig.data(), nbr * sizeof(int), cudaMemcpyHostToDevice);     // no gather: the caller's order
+    if (e == cudaSuccess) e = cudaMemcpy(pl->t_up, t_up.data(), nnode * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(pl->t_levoff, t_levoff.data(), t_levoff.size() * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(pl->t_probs, tp.data(), size_t(n_prob) * sizeof(LrtTreeProblem), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(pl->t_slots, 0, size_t(n_prob) * LRT_TREE_SLOT_DOUBLES * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemset(pl->t_cD, 0, 2 * nbr * sizeof(double));
+    if (e != cudaSuccess) return set_error(SCS_ERR_CUDA, "LRT plan upload failed: %s", cudaGetErrorString(e));
+    return SCS_OK;
+}
 
 int scs_lrt_plan_create(scs_ctx* ctx, int32_t n_prob, const int64_t* br_off, const int32_t* child_int, scs_lrt_plan** out) {
     if (!ctx || !br_off || !child_int || !out) return set_error(SCS_ERR_ARG, "null argument");
@@ -598,6 +710,24 @@ int scs_lrt_plan_create(scs_ctx* ctx, int32_t n_prob, const int64_t* br_off, con
         scs_lrt_plan_destroy(reinterpret_cast<scs_lrt_plan*>(pl));
         return set_error(SCS_ERR_CUDA, "LRT plan upload failed: %s", cudaGetErrorString(e));
     }
+    // trees too big for one warp: a thread-block cluster per problem on a level-ordered topology (scs_lrt_tree.cuh);
+    // SCS_LRT_KERNEL = tree | cta | warp forces a kernel (tests play them against each other)
+    pl->tree_mode = !pl->warp_mode;
+    if (const char* ev = getenv("SCS_LRT_KERNEL")) {
+        const std::string k(ev);
+        if (k == "tree") pl->tree_mode = true, pl->warp_mode = false;
+        else if (k == "cta") pl->tree_mode = false, pl->warp_mode = false;
+        else if (k == "warp" && max_nb <= 1024) pl->tree_mode = false, pl->warp_mode = true;
+        if (!pl->warp_mode && pl->threads == 32) pl->threads = max_nb >= 8192 ? 512 : (max_nb >= 2048 ? 256 : (max_nb > 256 ? 128 : 64));
+        if (pl->warp_mode) pl->threads = 32;
+    }
+    if (pl->tree_mode) {
+        const int rc = lrt_tree_prepare(pl, n_prob, br_off, child_int, probs);
+        if (rc != SCS_OK) {
+            scs_lrt_plan_destroy(reinterpret_cast<scs_lrt_plan*>(pl));
+            return rc;
+        }
+    }
     *out = reinterpret_cast<scs_lrt_plan*>(pl);
     return SCS_OK;
 }
@@ -627,6 +757,10 @@ int scs_lrt_plan_device_inputs(scs_lrt_plan* h, int64_t src_len, int32_t** d_chi
     pl->have_gather = true;
     pl->have_w = true;
     pl->src_len = size_t(src_len);
+    if (pl->tree_mode) {            // the level order was made for the placeholder topology: back to one CTA per problem
+        pl->tree_mode = false;
+        if (pl->threads == 32 && !pl->warp_mode) pl->threads = 128;
+    }
     return SCS_OK;
 }
 
@@ -636,6 +770,10 @@ int scs_lrt_plan_destroy(scs_lrt_plan* h) {
     cudaFree(pl->d_buf);
     cudaFree(pl->i_buf);
     cudaFree(pl->d_probs);
+    cudaFree(pl->t_ibuf);
+    cudaFree(pl->t_dbuf);
+    cudaFree(pl->t_probs);
+    cudaFree(pl->t_prof);
     delete pl;
     return SCS_OK;
 }
@@ -644,6 +782,11 @@ int scs_lrt_plan_set_weights(scs_lrt_plan* h, const double* w) {
     LrtPlanImpl* pl = reinterpret_cast<LrtPlanImpl*>(h);
     if (!pl || !w) return set_error(SCS_ERR_ARG, "null argument");
     SCS_CUDA(cudaMemcpy(pl->dw, w, pl->nbr * sizeof(double), cudaMemcpyHostToDevice));
+    if (pl->tree_mode) {
+        std::vector<double> wp(pl->nbr);
+        for (size_t k = 0; k < pl->nbr; ++k) wp[k] = w[size_t(pl->h_orig[k])];
+        SCS_CUDA(cudaMemcpy(pl->t_w, wp.data(), pl->nbr * sizeof(double), cudaMemcpyHostToDevice));
+    }
     pl->have_w = true;
     return SCS_OK;
 }
@@ -653,11 +796,17 @@ int scs_lrt_plan_set_gather(scs_lrt_plan* h, const int32_t* index, int64_t src_l
     if (!pl) return set_error(SCS_ERR_ARG, "null argument");
     if (!index) {
         pl->have_gather = false;
+        if (pl->tree_mode) SCS_CUDA(cudaMemcpy(pl->t_gather, pl->h_orig.data(), pl->nbr * sizeof(int), cudaMemcpyHostToDevice));
         return SCS_OK;
     }
     for (size_t k = 0; k < pl->nbr; ++k)
         if (index[k] < 0 || index[k] >= src_len) return set_error(SCS_ERR_ARG, "gather index %d out of range [0,%lld)", index[k], (long long)src_len);
     SCS_CUDA(cudaMemcpy(pl->d_gather, index, pl->nbr * sizeof(int), cudaMemcpyHostToDevice));
+    if (pl->tree_mode) {
+        std::vector<int> gp(pl->nbr);
+        for (size_t k = 0; k < pl->nbr; ++k) gp[k] = index[size_t(pl->h_orig[k])];
+        SCS_CUDA(cudaMemcpy(pl->t_gather, gp.data(), pl->nbr * sizeof(int), cudaMemcpyHostToDevice));
+    }
     pl->have_gather = true;
     pl->src_len = size_t(src_len);
     return SCS_OK;
@@ -670,6 +819,61 @@ int scs_lrt_plan_run(scs_lrt_plan* h, const double* d_Y, double* d_out, double* 
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     double mu = LRT_MU;
     if (const char* e = getenv("SCS_LRT_MU")) mu = atof(e) > 0.0 ? atof(e) : LRT_MU;      // analysis knob (tools/lrt_sweep_probe.py)
+    if (pl->tree_mode) {
+        LrtTreeArgs a;
+        a.probs = pl->t_probs;
+        a.Ysrc = d_Y;
+        a.gather = pl->t_gather;
+        a.w = pl->t_w;
+        a.child = pl->t_child;
+        a.up = pl->t_up;
+        a.orig = pl->t_orig;
+        a.levoff = pl->t_levoff;
+        a.Y = pl->dY; a.wq = pl->ws.wq; a.l = pl->ws.l; a.dl = pl->ws.dl;
+        a.hA = pl->ws.h; a.hB = pl->t_hB; a.x = pl->ws.x; a.G = pl->ws.G; a.e = pl->ws.e; a.D = pl->ws.D; a.r = pl->ws.r;
+        a.slots = pl->t_slots;
+        a.cD = pl->t_cD; a.cR = pl->t_cR;
+        a.out = d_out ? d_out : pl->d_out;
+        a.x_out = d_x ? d_x : pl->d_x;
+        a.mu = mu;
+        a.prof = nullptr;
+        a.start_mode = 0;
+        if (const char* ev = getenv("SCS_LRT_START")) a.start_mode = atoi(ev) == 1 ? 1 : 0;      // experiment knob (tools/lrt_timing.py)
+        if (getenv("SCS_LRT_PROF")) {          // tools/lrt_timing.py: cycles per phase, printed after the launch (synchronises)
+            if (!pl->t_prof && cudaMalloc(&pl->t_prof, 16 * sizeof(long long)) != cudaSuccess) pl->t_prof = nullptr;
+            if (pl->t_prof) cudaMemsetAsync(pl->t_prof, 0, 16 * sizeof(long long), st);
+            a.prof = pl->t_prof;
+        }
+        auto launch_tree = [&](auto kern) -> cudaError_t {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->tree_smem);
+            if (e != cudaSuccess) return e;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(unsigned(pl->n_prob * pl->tree_cluster));
+            cfg.blockDim = dim3(unsigned(pl->tree_threads));
+            cfg.dynamicSmemBytes = size_t(pl->tree_smem);
+            cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = unsigned(pl->tree_cluster);
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            return cudaLaunchKernelEx(&cfg, kern, a);
+        };
+        SCS_CUDA(pl->tree_threads == 512 ? launch_tree(scs_lrt_tree_kernel<512>) : launch_tree(scs_lrt_tree_kernel<256>));
+        if (a.prof) {
+            long long h[16];
+            if (cudaMemcpyAsync(h, a.prof, sizeof(h), cudaMemcpyDeviceToHost, st) == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess) {
+                static const char* nm[12] = {"rows", "sync", "bottom-up", "fold", "top-up-cta", "thin", "top-down-cta", "x-out+sync", "bottom-down", "step", "reduce", "linesearch"};
+                fprintf(stderr, "lrt phases (cycles, problem 0, %lld iterations, %lld line-search tries):", h[15] + 1, h[14]);
+                for (int i = 0; i < 12; ++i) fprintf(stderr, " %s %lld", nm[i], h[i]);
+                fprintf(stderr, "\n");
+            }
+        }
+        pl->launches++;
+        return SCS_OK;
+    }
     auto launch = [&](auto kern) {
         if (pl->smem_bytes > 0) {
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->smem_bytes);

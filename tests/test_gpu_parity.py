@@ -1014,6 +1014,90 @@ def test_lrt_sweep_against_the_reference(ctx, monkeypatch):
     assert n_bound5 >= 20 and n_zero >= 40 and n_neg >= 5, (n_bound5, n_zero, n_neg)
 
 
+# ------------------------------------------------- the cluster-per-problem LRT kernel (scs_lrt_tree.cuh)
+def _synthetic_lrt_problem(n_leaves, seed, sparse=False):
+    """Counts, weights and get_model_data's child_int of a random coalescent tree (branch 2 i + c hangs below internal node i)."""
+    rng = np.random.default_rng(seed)
+    t = synth.coalescent_tree(n_leaves, rng)
+    left, right = np.asarray(t.left), np.asarray(t.right)
+    m1 = len(left)
+    child = np.empty(2 * m1, dtype=np.int32)
+    child[0::2] = np.where(left >= n_leaves, left - n_leaves, -1)
+    child[1::2] = np.where(right >= n_leaves, right - n_leaves, -1)
+    ids = np.empty(2 * m1, dtype=np.int64)
+    ids[0::2], ids[1::2] = left, right
+    length = np.asarray(t.branch_len, dtype=np.float64)[ids]
+    Y = rng.poisson(length / length.mean() * (0.8 if sparse else 25.0)).astype(np.float64)
+    Y += rng.uniform(0.0, 0.3, size=Y.size) * (Y > 0)           # soft counts are not integers
+    w = rng.uniform(0.4, 1.6, size=Y.size)
+    w *= Y.size / w.sum()
+    return Y, w, child
+
+
+def _assert_same_lrt(a, b, xa=None, xb=None):
+    assert np.array_equal(a[:, 7], b[:, 7]), (a[:, 7], b[:, 7])                 # status
+    ok = a[:, 7] == 0
+    assert np.array_equal(a[ok, 1], b[ok, 1]) and np.array_equal(a[ok, 2], b[ok, 2])          # dof, on_bound
+    np.testing.assert_allclose(a[ok, 0], b[ok, 0], rtol=1e-8, atol=1e-8)        # -2 log LR
+    np.testing.assert_allclose(a[ok, 3], b[ok, 3], rtol=1e-6, atol=1e-300)      # p
+    np.testing.assert_allclose(a[ok, 4], b[ok, 4], rtol=1e-10)                  # ll_H0
+    np.testing.assert_allclose(a[ok, 5], b[ok, 5], rtol=1e-12)                  # ll_H1
+    if xa is not None:
+        for i in np.flatnonzero(ok):
+            np.testing.assert_allclose(xa[i], xb[i], rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("cluster", ["1", "2", "8"])
+@pytest.mark.parametrize("top_cap", [None, "9", "0"])
+def test_lrt_tree_kernel_on_the_reference_sweep(ctx, monkeypatch, cluster, top_cap):
+    """The cluster kernel forced onto the 240 small problems of the reference sweep (where the default is one warp per
+    problem): same statuses, dof, on_bound; LR, p and fitted lengths equal to rounding.  top_cap = 9 / 0 pushes all but
+    the last few levels (every level) below the cut, i.e. through the cluster-wide sweeps in global memory."""
+    g = load("lrt_sweep")
+    off = g["off"]
+    n = len(off) - 1
+    Ys = [g["Y"][off[i]:off[i + 1]] for i in range(n)]
+    ws = [g["w"][off[i]:off[i + 1]] for i in range(n)]
+    chs = [g["child_int"][off[i]:off[i + 1]] for i in range(n)]
+    base, xb = engine.lrt_poisson_batch(ctx, Ys, ws, chs, want_x=True)
+    monkeypatch.setenv("SCS_LRT_KERNEL", "tree")
+    monkeypatch.setenv("SCS_LRT_CLUSTER", cluster)
+    if top_cap is not None:
+        monkeypatch.setenv("SCS_LRT_TOP_CAP", top_cap)
+    out, xt = engine.lrt_poisson_batch(ctx, Ys, ws, chs, want_x=True)
+    _assert_same_lrt(base, out, xb, xt)
+
+
+@pytest.mark.parametrize("n_leaves,n_prob", [(400, 5), (1000, 10), (3000, 3), (10000, 10), (12000, 2)])
+def test_lrt_tree_kernel_on_big_trees(ctx, monkeypatch, n_leaves, n_prob):
+    """Big random trees: the default (cluster kernel, automatic cluster size) against one CTA per problem with the
+    working set in global memory (the round-1 kernel).  12,000 leaves has levels below the cut by itself."""
+    probs = [_synthetic_lrt_problem(n_leaves, 100 * n_leaves + i, sparse=(i % 3 == 2)) for i in range(n_prob)]
+    Ys, ws, chs = [p[0] for p in probs], [p[1] for p in probs], [p[2] for p in probs]
+    out, xt = engine.lrt_poisson_batch(ctx, Ys, ws, chs, want_x=True)
+    monkeypatch.setenv("SCS_LRT_KERNEL", "cta")
+    base, xb = engine.lrt_poisson_batch(ctx, Ys, ws, chs, want_x=True)
+    assert (base[:, 7] == 0).sum() >= n_prob - 1
+    _assert_same_lrt(base, out, xb, xt)
+    # gather + reuse through a plan (what bench.py and the product path do): counts picked from a longer source vector
+    monkeypatch.delenv("SCS_LRT_KERNEL")
+    import torch
+    rng = np.random.default_rng(5)
+    total = sum(len(y) for y in Ys)
+    perm = rng.permutation(total + 7).astype(np.int32)[:total]
+    src = np.zeros(total + 7)
+    src[perm] = np.concatenate(Ys)
+    plan = engine.LrtPlan(ctx, chs)
+    plan.set_weights(ws)
+    plan.set_gather(perm, total + 7)
+    d_out = torch.zeros((n_prob, 8), dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        plan.run(torch.as_tensor(src, device="cuda"), d_out)
+    torch.cuda.synchronize()
+    plan.close()
+    _assert_same_lrt(out, d_out.cpu().numpy())
+
+
 # ------------------------------------------------- the product path under an initialised process group
 def _free_port():
     import socket

@@ -150,3 +150,24 @@ def test_interval_form_of_the_placement_oracle():
             assert set(perm[lo[b]:hi[b]].tolist()) == set(perm2[lo2[b]:hi2[b]].tolist()) == set(np.nonzero(S[b])[0].tolist())
     bad = np.array([[1, 1, 0, 0], [0, 1, 1, 0]], dtype=float)
     assert O.clade_intervals(bad) is None
+
+
+def test_reference_copy_reproduces_a_fixture():
+    """oracle/_ref (the byte-for-byte copy of the reference that bench.py's CPU arms run) gives the fixture's TSV and soft
+    weights -- the arm times the same module that made the golden vectors."""
+    from oracle import ref_module
+    if ref_module.make() is None:
+        pytest.skip("oracle/_ref is made where /root/reference exists")
+    try:
+        ref = ref_module.load()
+        g = load("syn_a")
+        vcf, tree, meta = case_inputs(g)
+        call_data = ref.get_mut_df(vcf, meta["exclude"], meta["include"])
+        t, FP, FN, M = ref.get_gt_tree(tree, call_data, float(g["w_maxs"][0]))
+        np.testing.assert_allclose(M.values.sum(axis=0), g["soft"], rtol=1e-12)
+        Y, constr, init, wn, cols = ref.get_model_data(t)
+        LR, dof, on_bound, p_val, _ = ref.get_LRT_poisson(Y, constr, init, wn[:, 0])
+        assert dof == int(g["dof"][0]) and on_bound == int(g["on_bound"][0])
+        assert abs(LR - g["LR"][0]) <= 1e-6 * max(1.0, abs(g["LR"][0]))
+    finally:
+        np.seterr(all="warn")          # the reference sets np.seterr(all='raise') process-wide on import
