@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--replicates", type=int, default=1250,
                     help="replicate-sweep leg, replicates per GPU and step (BASELINE configs[4]: 10,000 pairs of 100 cells x 10k SNVs "
                          "over 8 GPUs = 1250 per GPU); 0 disables it")
+    ap.add_argument("--rep-sub", type=int, default=4, help="sub-batches of the replicate leg's end-to-end pipeline")
     ap.add_argument("--rep-cells", type=int, default=100)
     ap.add_argument("--rep-snvs", type=int, default=10000)
     return ap.parse_args()
@@ -286,15 +287,31 @@ def sweep_cpu_baseline(tree_s, names, codes, tmp, seconds):
                       "trust-constr LRT per w_max like run_PT_test.py:713-718, %s, %.1f s" % (done, len(names) - 1, codes.shape[0], what, dt)}
 
 
+def _max_rel_dev_lr(rows_a, rows_b):
+    """Largest relative difference of the -2logLR fields of two lists of TSV model lines (sub-batches whose GEMM schedule
+    differs from the whole batch's sum the same soft weights in another order)."""
+    worst = 0.0
+    for a, b in zip(rows_a, rows_b):
+        fa, fb = a.split("\t"), b.split("\t")
+        for i in range(3, min(len(fa), len(fb)), 4):
+            try:
+                x, y = float(fa[i]), float(fb[i])
+            except ValueError:
+                continue
+            if np.isfinite(x) and np.isfinite(y):
+                worst = max(worst, abs(x - y) / max(1.0, abs(y)))
+    return worst
+
+
 def replicate_sweep(ctx, dev, rank, world, R, n_cells, n_snv, steps, warmup, n_sub=4, cpu_seconds=0.0):
     """BASELINE configs[4]: many independent (VCF, tree) pairs, sharded over ranks with no communication.  Every replicate
     has its OWN random tree and its own genotypes.  Two timings of engine.ReplicateSweep (CUDA events, max over ranks):
       * device-resident: packed matrices in HBM, trees parsed beforehand; timed = upload of the clade masks / topology,
         per-group row filters, operand expansion, both placement passes, branch weights + LRT branch order, all R x 10
         clock tests in one launch, result read-back;
-      * e2e: packed matrices in pinned HOST memory + Newick TEXT -> TSV rows.  The batch is cut into n_sub sub-batches on
-        their own streams so that the native tree parsing (host threads) and the H2D copy of sub-batch k + 1 run under the
-        kernels of sub-batch k; the TSV lines are formatted natively (scs_format_pt_rows)."""
+      * e2e: packed matrices in pinned HOST memory + Newick TEXT -> TSV rows through engine.ReplicateSweepStream: n_sub
+        sub-batches, every H2D copy queued up front on a copy stream, trees parsed natively on a worker thread, kernels of
+        sub-batch k as soon as its copy and its trees are there, TSV lines formatted natively (scs_format_pt_rows)."""
     import torch
     from scsommerclock_b200 import engine, sharding, synth
     names = ["tumcell%05d" % (i + 1) for i in range(n_cells)]
@@ -353,39 +370,23 @@ def replicate_sweep(ctx, dev, rank, world, R, n_cells, n_snv, steps, warmup, n_s
     pinned.copy_(packed)
     torch.cuda.synchronize()
     n_sub = max(1, min(n_sub, R))
-    cuts = [R * k // n_sub for k in range(n_sub + 1)]
-    subs = [engine.ReplicateSweep(ctx, [n_snv] * (cuts[k + 1] - cuts[k]), columns, W_MAXS) for k in range(n_sub)]
-    streams = [torch.cuda.Stream(device=dev) for _ in range(n_sub)]
+    pipe = engine.ReplicateSweepStream(ctx, [n_snv] * R, columns, W_MAXS, n_sub=n_sub)
     host_ms = []
 
-    def step_e2e():
-        t0 = time.perf_counter()
-        for k, sub in enumerate(subs):
-            sub.parse_trees(newicks[cuts[k]:cuts[k + 1]])
-            sub.enqueue(pinned[cuts[k] * n_snv:cuts[k + 1] * n_snv], FP, FN, stream=streams[k])
-        rows = []
-        for sub in subs:
-            rows.extend(sub.rows())
-        host_ms.append(1e3 * (time.perf_counter() - t0))
-        return rows
-
-    cur = torch.cuda.current_stream(dev)
-
     def step_e2e_timed():
-        for st in streams:
-            st.wait_stream(cur)                       # the timing events are recorded on the current stream
-        rows = step_e2e()
-        for st in streams:
-            cur.wait_stream(st)
+        t0 = time.perf_counter()
+        rows, _ = pipe.run(pinned, newicks, FP, FN)
+        host_ms.append(1e3 * (time.perf_counter() - t0))
         return rows
 
     ms_e2e, rows = timed(step_e2e_timed, steps, 1)
     result["e2e"] = {"value": R * len(W_MAXS) * world / (ms_e2e / 1e3), "unit": "PT tests/s", "ms_per_step": ms_e2e,
                      "h2d_bytes_per_step": int(pinned.numel() + R * sweep.n_rows * (sweep.words + 2) * 4 + R * 16) * world,
-                     "d2h_bytes_per_step": int(R * len(W_MAXS) * 64 + R * 12) * world, "sub_batches": n_sub,
+                     "d2h_bytes_per_step": int(R * len(W_MAXS) * 64 + R * 12) * world, "sub_batches": pipe.n_sub,
                      "host_wall_ms_per_step": float(np.mean(host_ms[-steps:])),
                      "input": "packed genotype matrices in pinned host memory + Newick text of %d distinct trees" % R,
                      "output": "TSV model lines (scs_format_pt_rows)", "rows_equal_device_leg": bool(rows == ref_rows),
+                     "max_rel_dev_LR_vs_device_leg": _max_rel_dev_lr(rows, ref_rows),
                      "vs_device_resident": ms_e2e / ms}
     if rank == 0 and cpu_seconds > 0:
         codes = synth.observe(trees[0], synth.throw_mutations(trees[0], n_snv, np.random.default_rng(3)), FN_TRUE, FP_TRUE, MS_TRUE,
@@ -394,8 +395,7 @@ def replicate_sweep(ctx, dev, rank, world, R, n_cells, n_snv, steps, warmup, n_s
             result["cpu_baseline"] = sweep_cpu_baseline(trees[0], columns, codes, tmp, cpu_seconds)
         except Exception as exc:          # (a reported extra: never lose the line over it)
             result["cpu_baseline"] = {"error": repr(exc)}
-    for sub in subs:
-        sub.close()
+    pipe.close()
     sweep.close()
     return result
 
@@ -504,7 +504,7 @@ class SingleDataset:
         torch.cuda.empty_cache()
 
 
-def timed(fn, steps, warmup, plan, dev, sampler=None, lrt_launches_per_step=1):
+def timed(fn, steps, warmup, plan, dev, sampler=None, lrt_launches_per_step=1, prep=True):
     """W untimed + K timed steps between barriers and synchronisations; CUDA events; max over ranks.
     Returns (total ms, per-step plan kernel times, last result, this library's launches inside the timed region)."""
     import torch
@@ -523,7 +523,7 @@ def timed(fn, steps, warmup, plan, dev, sampler=None, lrt_launches_per_step=1):
     e0.record()
     for _ in range(steps):
         res = fn()
-        times.append(plan.last_times())
+        times.append(plan.last_times() + [plan.prepare_time() if prep else 0.0])
     e1.record()
     torch.cuda.synchronize()
     sharding.barrier()
@@ -654,7 +654,7 @@ def main():
     rep = None
     if args.replicates > 0:
         torch.cuda.empty_cache()
-        rep = replicate_sweep(ctx, dev, rank, world, args.replicates, args.rep_cells, args.rep_snvs, max(2, args.steps), 1,
+        rep = replicate_sweep(ctx, dev, rank, world, args.replicates, args.rep_cells, args.rep_snvs, max(2, args.steps), 1, n_sub=args.rep_sub,
                               cpu_seconds=(args.cpu_seconds if (world == 1 and not args.no_cpu_baseline) else 0.0))
 
     if rank == 0:
@@ -709,8 +709,9 @@ def main():
                         "traffic_source": iv.get("source") if scale else None,
                         "peak_source": pk_kind + " HBM copy bandwidth",
                         "kernel": "scs_place_iv%d_kernel (prefix counts in shared memory, no GEMM)" % plan_info["interval_variant"],
-                        "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": t_k, "prepass_ms": float(g[:, 0].mean()),
-                        "prepass_GBps": 2.0 * alg_bytes / 1e9 / (float(g[:, 0].mean()) / 1e3) if g[:, 0].mean() > 0 else None,
+                        "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": t_k, "prepass_ms": float(g[:, 4].mean()),
+                        "prepass_GBps": 2.0 * alg_bytes / 1e9 / (float(g[:, 4].mean()) / 1e3) if g[:, 4].mean() > 0 else None,
+                        "prepass_note": "scs_permute_reduce4_kernel: row filter + per-cell missing counts + rows rewritten in depth-first cell order, one read and one write of the packed matrix",
                         "reduce_ms": float(g[:, 3].mean()),
                         "entries_per_s": float(n_snv) * n_rows / (t_k / 1e3),
                         "actual_limiter": "instruction issue / shared-memory latency: one 640-thread CTA per SM (5 warps per scheduler); HBM traffic is "

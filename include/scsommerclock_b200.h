@@ -157,6 +157,8 @@ const void* scs_placement_device_result(scs_placement* plan);
  * (zero when they were still valid), ms[1] is zero, ms[2] the placement kernel.  Waits for
  * that run to finish. */
 int scs_placement_last_times(scs_placement* plan, float* ms);
+/* Device ms of the last scs_placement_prepare's kernels (waits for them). */
+int scs_placement_prepare_time(scs_placement* plan, float* ms);
 /* info[0..9] = M_pad, N_pad, K_pad, tasks, run_len, superblock_width, grid,
  * kernel launches so far, runs, dynamic smem bytes, operand mode (0 = two u8
  * planes / kind::i8, 1 = one radix-packed e5m2 plane / kind::f8f6f4), K chunks,

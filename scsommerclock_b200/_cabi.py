@@ -45,6 +45,7 @@ _SIGNATURES = {
     "scs_placement_run_host": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
     "scs_placement_device_result": (C.c_void_p, [C.c_void_p]),
     "scs_placement_last_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "scs_placement_prepare_time": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "scs_placement_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
     "scs_placement_debug_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "scs_placement_debug_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -1300,6 +1300,8 @@ struct Placement {
     int colpart_rows = 0;
     CUtensorMap tm_s64;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // brackets of the four kernels of run()
+    cudaEvent_t ev_prep[2] = {nullptr, nullptr};                         // brackets of the last scs_placement_prepare's kernels
+    bool prep_timed = false;
     bool timed = false;
     // ---- interval path (scs_place_interval.cuh): chosen by set_clades when the masks are a laminar family
     int algo = 0;                  // 0 undecided (no clades yet), 1 GEMM, 2 interval
@@ -1532,6 +1534,7 @@ int scs_placement_create_batch(scs_ctx* ctx, int32_t n_groups, const int64_t* n_
         set_place_smem<PASS_STATS>();
         set_place_smem<PASS_COLSUM>();
         for (int i = 0; i < 5; ++i) cudaEventCreate(&pl->ev[i]);
+        for (int i = 0; i < 2; ++i) cudaEventCreate(&pl->ev_prep[i]);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) {
             rc = set_error(SCS_ERR_CUDA, "placement plan setup failed: %s", cudaGetErrorString(e));
@@ -1581,6 +1584,8 @@ int scs_placement_destroy(scs_placement* h) {
     cudaFree(pl->d_gconst_d);
     for (int i = 0; i < 5; ++i)
         if (pl->ev[i]) cudaEventDestroy(pl->ev[i]);
+    for (int i = 0; i < 2; ++i)
+        if (pl->ev_prep[i]) cudaEventDestroy(pl->ev_prep[i]);
     delete pl;
     return SCS_OK;
 }
@@ -2001,12 +2006,15 @@ int scs_placement_prepare(scs_placement* h, const uint8_t* d_gt, int64_t pitch_b
         pl->d_prep_bytes = need;
     }
     pl->prep_mode = mode;
+    cudaEventRecord(pl->ev_prep[0], st);
+    pl->prep_timed = true;
     if (!fused) {
         int rc = gt_reduce_launch(pl->ctx, d_gt, pitch_bytes, pl->n_snv, n_cells, col_active, filter_rows, pl->row_keep, pl->d_prep, accumulate != 0, st);
         if (rc != SCS_OK) return rc;
         pl->launches += rw <= 32 ? 1 : 2;
         rc = set_genotypes_impl(pl, d_gt, pitch_bytes, nullptr, st, true);
         pl->have_row_keep = true;
+        cudaEventRecord(pl->ev_prep[1], st);
         return rc;
     }
     if (!accumulate) {
@@ -2039,6 +2047,7 @@ int scs_placement_prepare(scs_placement* h, const uint8_t* d_gt, int64_t pitch_b
             pl->gt_perm, pl->row_keep, reinterpret_cast<unsigned long long*>(pl->d_prep), reinterpret_cast<unsigned int*>(pl->d_prep + off_miss));
     }
     SCS_CUDA(cudaGetLastError());
+    cudaEventRecord(pl->ev_prep[1], st);
     pl->launches++;
     pl->operands_valid = false;
     pl->gt_src = d_gt;             // bound: a later switch to general clade masks builds the GEMM operands from it
@@ -2289,6 +2298,15 @@ int scs_placement_last_times(scs_placement* h, float* ms) {
     if (!pl->timed) return set_error(SCS_ERR_ARG, "scs_placement_run has not been called yet");
     SCS_CUDA(cudaEventSynchronize(pl->ev[4]));
     for (int i = 0; i < 4; ++i) SCS_CUDA(cudaEventElapsedTime(&ms[i], pl->ev[i], pl->ev[i + 1]));
+    return SCS_OK;
+}
+
+int scs_placement_prepare_time(scs_placement* h, float* ms) {
+    Placement* pl = reinterpret_cast<Placement*>(h);
+    if (!pl || !ms) return set_error(SCS_ERR_ARG, "null argument");
+    if (!pl->prep_timed) return set_error(SCS_ERR_ARG, "scs_placement_prepare has not been called yet");
+    SCS_CUDA(cudaEventSynchronize(pl->ev_prep[1]));
+    SCS_CUDA(cudaEventElapsedTime(ms, pl->ev_prep[0], pl->ev_prep[1]));
     return SCS_OK;
 }
 

@@ -5,6 +5,8 @@ every number the PT test reports is produced by the CUDA library.
 """
 import ctypes as C
 
+import time
+
 import numpy as np
 
 from . import _cabi
@@ -214,6 +216,12 @@ class Placement:
         ms = (C.c_float * 4)()
         check(lib().scs_placement_last_times(self._h, ms))
         return [float(v) for v in ms]
+
+    def prepare_time(self):
+        """Device ms of the last ``prepare`` call's kernels."""
+        ms = C.c_float()
+        check(lib().scs_placement_prepare_time(self._h, C.byref(ms)))
+        return float(ms.value)
 
     def device_result_ptr(self):
         return int(lib().scs_placement_device_result(self._h))
@@ -629,3 +637,130 @@ class ReplicateSweep:
         """The TSV model line of every pair (``results`` formatted by scs_format_pt_rows)."""
         out, n_kept, status = self.results()
         return format_pt_rows(out, n_kept, self.FN, self.FP)
+
+
+class ReplicateSweepStream:
+    """A large sweep whose packed genotype matrices sit in (pinned) HOST memory and whose trees are Newick TEXT, through
+    ``ReplicateSweep`` in ``n_sub`` sub-batches so that the three resources work at the same time:
+
+        copy engine     sub-batch k + 1's matrix is copied (own stream) while sub-batch k's kernels run;
+        host threads    a worker thread parses the trees of sub-batch k + 1, k + 2, ... (native code, the GIL is released)
+                        while the main thread enqueues sub-batch k's kernels the moment its trees are parsed and formats the
+                        TSV lines of the sub-batches that have finished (native, on host threads);
+        SMs             sub-batch k's kernels start when its copy has landed.
+
+    Measured before this class existed (tools/sweep_stages.py, 1250 pairs of 100 cells x 10k SNVs in 4 sub-batches): copy
+    1.8 ms + kernels 2.4 ms per sub-batch, but 1.8 ms of tree parsing and 1.9 ms of line formatting per sub-batch in series on
+    the one host thread -- the device idled half the time."""
+
+    def __init__(self, ctx, group_snvs, columns, w_maxs, n_sub=4, outgroup="healthycell"):
+        import torch
+        self.ctx = ctx
+        self.dev = torch.device("cuda", ctx.device)
+        group_snvs = np.ascontiguousarray(group_snvs, dtype=np.int64)
+        G = int(group_snvs.size)
+        n_sub = max(1, min(int(n_sub), G))
+        # a short first sub-batch (the device idles until its trees are parsed and its kernels enqueued) and a short last
+        # one (its result read-back and line formatting are not hidden behind anything): weights 1, 2, 2, ..., 2, 1
+        wts = np.array([1.0] + [2.0] * (n_sub - 2) + [1.0]) if n_sub >= 3 else np.ones(n_sub)
+        edges = np.concatenate([[0.0], np.cumsum(wts)]) / wts.sum()
+        self.cuts = sorted(set(int(round(G * e)) for e in edges))
+        n_sub = len(self.cuts) - 1
+        self.row_cuts = [int(group_snvs[:c].sum()) for c in self.cuts]
+        self.subs = [ReplicateSweep(ctx, group_snvs[self.cuts[k]:self.cuts[k + 1]], columns, w_maxs, outgroup=outgroup) for k in range(n_sub)]
+        for sub in self.subs:
+            sub.d_gt = torch.empty((sub.total, sub.pitch), dtype=torch.uint8, device=self.dev)
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.compute_stream = torch.cuda.Stream(device=self.dev)
+        self.copied = [torch.cuda.Event() for _ in self.subs]
+        self.n_sub = n_sub
+        self.trace = None              # set to a list to collect (what, sub-batch, host ms) records of the next run
+
+    def close(self):
+        for sub in self.subs:
+            sub.close()
+
+    def run(self, host_packed, newicks, FP, FN, strip_tags=False):
+        """``host_packed``: torch uint8 [sum(group_snvs), pitch] in pinned host memory; ``newicks``: one text per pair;
+        ``FP`` / ``FN``: scalars or one value per pair.  Returns (TSV model lines, status int32 per pair)."""
+        import threading
+        import torch
+        G = self.cuts[-1]
+        FP = np.ascontiguousarray(np.broadcast_to(np.asarray(FP, dtype=np.float64), (G,)))
+        FN = np.ascontiguousarray(np.broadcast_to(np.asarray(FN, dtype=np.float64), (G,)))
+        cur = torch.cuda.current_stream(self.dev)
+        self.copy_stream.wait_stream(cur)
+        self.compute_stream.wait_stream(cur)
+
+        trace = self.trace
+        t00 = time.perf_counter()
+
+        def queue_copy(k):
+            # One H2D queue serves every stream in issue order: sub-batch k + 1's matrix is queued only AFTER sub-batch k's
+            # small uploads (masks, topology, per-group constants), which would otherwise wait behind ALL the matrices
+            # (measured: the first kernels started after the last matrix had landed).
+            sub = self.subs[k]
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(sub.done)          # the previous run's kernels on this buffer (a no-op the first time)
+                sub.d_gt.copy_(host_packed[self.row_cuts[k]:self.row_cuts[k + 1]], non_blocking=True)
+                self.copied[k].record(self.copy_stream)
+
+        if trace is not None:
+            self.trace_events = []
+            self.trace_t0 = torch.cuda.Event(enable_timing=True)
+            self.trace_t0.record(cur)
+        queue_copy(0)
+        parsed = [threading.Event() for _ in self.subs]
+        failure = []
+
+        def note(what, k):
+            if trace is not None:
+                trace.append((what, k, 1e3 * (time.perf_counter() - t00)))
+
+        def parse_all():
+            try:
+                for k, sub in enumerate(self.subs):
+                    sub.parse_trees(newicks[self.cuts[k]:self.cuts[k + 1]], strip_tags=strip_tags)
+                    note("parsed", k)
+                    parsed[k].set()
+            except BaseException as exc:          # handed to the caller's thread
+                failure.append(exc)
+                for ev in parsed:
+                    ev.set()
+
+        worker = threading.Thread(target=parse_all, daemon=True)
+        worker.start()
+        rows, status, formatted = [], [], 0
+        for k, sub in enumerate(self.subs):
+            parsed[k].wait()
+            if failure:
+                break
+            self.compute_stream.wait_event(self.copied[k])
+            if trace is not None:                  # device time stamps around the sub-batch's kernels (tools/sweep_stream_trace.py)
+                e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e_a.record(self.compute_stream)
+            sub.enqueue(sub.d_gt, FP[self.cuts[k]:self.cuts[k + 1]], FN[self.cuts[k]:self.cuts[k + 1]], stream=self.compute_stream)
+            if trace is not None:
+                e_b.record(self.compute_stream)
+                self.trace_events.append((k, e_a, e_b))
+            if k + 1 < len(self.subs):
+                queue_copy(k + 1)
+            note("enqueued", k)
+            while formatted < k and self.subs[formatted].done.query():      # lines of sub-batches that are already back
+                rows.extend(self.subs[formatted].rows())
+                status.append(self.subs[formatted].h_status.numpy().copy())
+                note("formatted", formatted)
+                formatted += 1
+        worker.join()
+        if failure:
+            torch.cuda.synchronize(self.dev)
+            raise failure[0]
+        for k in range(formatted, len(self.subs)):
+            sub = self.subs[k]
+            sub.done.synchronize()
+            note("done", k)
+            rows.extend(sub.rows())
+            status.append(sub.h_status.numpy().copy())
+            note("formatted", k)
+        cur.wait_stream(self.compute_stream)
+        return rows, np.concatenate(status)

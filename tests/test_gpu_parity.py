@@ -1014,6 +1014,44 @@ def test_lrt_sweep_against_the_reference(ctx, monkeypatch):
     assert n_bound5 >= 20 and n_zero >= 40 and n_neg >= 5, (n_bound5, n_zero, n_neg)
 
 
+def test_replicate_sweep_stream_equals_one_batch(ctx):
+    """engine.ReplicateSweepStream (host matrices + Newick text, sub-batches pipelined over a copy stream, a parser thread
+    and the compute stream; TSV lines formatted on host threads) gives the lines of ONE ReplicateSweep over the same pairs,
+    character for character, on repeated runs (buffers reused) and with per-pair error rates."""
+    import torch
+    rng = np.random.default_rng(5)
+    n_cells, R = 30, 150
+    names = ["tumcell%05d" % (i + 1) for i in range(n_cells)]
+    columns = names + ["healthycell"]
+    snvs = [int(v) for v in rng.integers(150, 400, size=R)]
+    trees = [synth.coalescent_tree(n_cells, rng) for _ in range(R)]
+    newicks = [t.newick(names, "healthycell", scale=0.05) for t in trees]
+    mats = []
+    for t, m in zip(trees, snvs):
+        codes = synth.observe(t, synth.throw_mutations(t, m, rng), 0.1, 0.01, 0.15, rng)
+        codes = np.concatenate([codes, np.zeros((m, 1), dtype=np.uint8)], axis=1)
+        packed, pitch = engine.pack_genotypes(codes)
+        mats.append(packed)
+    host = torch.as_tensor(np.concatenate(mats, axis=0)).pin_memory()
+    FP = rng.uniform(0.005, 0.02, size=R)
+    FN = rng.uniform(0.03, 0.08, size=R)
+    w = [100.0, 500.0, 1000.0]
+    one = engine.ReplicateSweep(ctx, snvs, columns, w)
+    one.parse_trees(newicks)
+    one.enqueue(host.cuda(), FP, FN)
+    want = one.rows()
+    want_status = one.results()[2].copy()
+    one.close()
+    assert len(want) == R and sum(r.endswith("H0") or r.endswith("H1") for r in want) == R
+    for n_sub in (1, 3, 7):
+        stream = engine.ReplicateSweepStream(ctx, snvs, columns, w, n_sub=n_sub)
+        for _ in range(2):
+            rows, status = stream.run(host, newicks, FP, FN)
+            assert rows == want
+            assert np.array_equal(status, want_status)
+        stream.close()
+
+
 # ------------------------------------------------- the cluster-per-problem LRT kernel (scs_lrt_tree.cuh)
 def _synthetic_lrt_problem(n_leaves, seed, sparse=False):
     """Counts, weights and get_model_data's child_int of a random coalescent tree (branch 2 i + c hangs below internal node i)."""
