@@ -136,6 +136,12 @@ int scs_placement_prepare_result(scs_placement* plan, int64_t* n_kept, double* m
  * and every replicate batch, goes through the tcgen05 GEMM.  SCS_PLACE_ALGO=gemm forces the GEMM,
  * SCS_PLACE_ALGO=interval takes the interval path for tree-shaped masks at any size. */
 int scs_placement_set_clades(scs_placement* plan, const uint32_t* d_bits, int64_t pitch_words, void* stream);
+/* The clade rows of every group given as TREES: d_bits as for scs_placement_set_clades plus the child table and node
+ * counts scs_tree_parse_batch produces (device copies: children[g][n_rows][2], info[g][4]).  Plans of up to 512 cells then
+ * take the interval path for batches of small trees (a few lanes per SNV, no GEMM); anything else is handed to
+ * scs_placement_set_clades.  A group whose child table is not a binary tree over single-cell leaves gets NaN weights. */
+int scs_placement_set_trees(scs_placement* plan, const uint32_t* d_bits, int64_t pitch_words, const int32_t* d_children,
+                            const int32_t* d_info, void* stream);
 int scs_placement_set_clades_host(scs_placement* plan, const uint32_t* bits, int64_t pitch_words, void* stream);
 /* Host-only helper (no device work): *laminar = 1 when the masks are a laminar family, and then
  * perm[k] (optional, [n_cells]) = cell at depth-first position k and lohi[r] (optional, [n_rows]) =

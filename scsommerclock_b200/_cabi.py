@@ -40,6 +40,7 @@ _SIGNATURES = {
     "scs_placement_prepare": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "scs_placement_prepare_result": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p]),
     "scs_placement_set_clades": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "scs_placement_set_trees": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scs_placement_set_clades_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "scs_placement_run": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
     "scs_placement_run_host": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),

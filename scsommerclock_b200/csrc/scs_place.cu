@@ -1186,6 +1186,7 @@ __global__ void scs_reduce_colpart_kernel(const float* __restrict__ colpart, con
 }  // namespace scs
 #include "scs_place_interval.cuh"
 #include "scs_place_iv4.cuh"
+#include "scs_place_iv5.cuh"
 namespace scs {
 
 // ---------------------------------------------------------------- host side
@@ -1326,6 +1327,13 @@ struct Placement {
     bool iv_dcache = false, iv_perm_smem = false;
     size_t iv_smem = 0;
     int iv4_np = 0;                // variant 4 (scs_place_iv4.cuh): pairs of non-leaf rows per thread
+    // ---- batches of small trees (scs_place_iv5.cuh), algo 3: chosen by scs_placement_set_trees
+    int iv5_L = 0, iv5_stride = 0, iv5_ntasks = 0, iv5_grid = 0;
+    uint16_t* iv5_perm = nullptr;
+    uint32_t* iv5_lohi = nullptr;
+    int *iv5_row_slot = nullptr, *iv5_meta = nullptr, *iv5_task0 = nullptr;
+    Iv5Task* iv5_tasks = nullptr;
+    float* iv5_part = nullptr;
     // ---- scs_placement_prepare: row filter + missing counts (+ cell-order pass) with the counters kept on the device
     std::vector<uint16_t> h_perm;  // host copy of the cell order (positions -> cells)
     uint8_t* d_prep = nullptr;     // mode 1: [kept u64 | pad][active mask, rw words (16-byte padded)][missing per POSITION, 16 rw u32]
@@ -1567,6 +1575,13 @@ int scs_placement_destroy(scs_placement* h) {
     cudaFree(pl->d_leafmask);
     cudaFree(pl->gt_perm);
     cudaFree(pl->ipart);
+    cudaFree(pl->iv5_perm);
+    cudaFree(pl->iv5_lohi);
+    cudaFree(pl->iv5_row_slot);
+    cudaFree(pl->iv5_meta);
+    cudaFree(pl->iv5_task0);
+    cudaFree(pl->iv5_tasks);
+    cudaFree(pl->iv5_part);
     cudaFree(pl->d_prep);
     cudaFree(pl->colpart);
     cudaFree(pl->y);
@@ -1615,6 +1630,20 @@ static int set_genotypes_impl(Placement* pl, const uint8_t* d_gt, int64_t pitch_
     pl->operands_valid = false;
     pl->gt_perm_valid = false;
     pl->gt_src = nullptr;
+    if (pl->algo == 3) {
+        // batches of small trees: the kernel reads the caller's packed rows as they are (they must stay alive and
+        // unchanged until the run has finished, like scs_placement_bind_genotypes)
+        pl->gt_src = d_gt;
+        pl->gt_pitch = pitch_bytes;
+        pl->gt_perm_valid = true;
+        if (d_row_keep) {
+            SCS_CUDA(cudaMemcpyAsync(pl->row_keep, d_row_keep, size_t(pl->n_snv), cudaMemcpyDeviceToDevice, st));
+            pl->have_row_keep = true;
+        } else {
+            pl->have_row_keep = false;
+        }
+        return SCS_OK;
+    }
     // GEMM path (or clades not seen yet): the operand plane(s)
     if (pl->algo != 2) {
         int rc = expand_operands(pl, d_gt, pitch_bytes, st);
@@ -1894,6 +1923,59 @@ int scs_placement_set_clades(scs_placement* h, const uint32_t* d_bits, int64_t p
     return SCS_OK;
 }
 
+// Clade rows given as TREES (scs_tree_parse_batch's outputs on the device): every group's rows are the nodes of a binary
+// tree, so the batch can take the interval path for small trees (scs_place_iv5.cuh) -- no operand planes, no GEMM.  Falls
+// back to scs_placement_set_clades (the masks alone, tcgen05 GEMM) for more than 512 cells or SCS_PLACE_ALGO=gemm.
+int scs_placement_set_trees(scs_placement* h, const uint32_t* d_bits, int64_t pitch_words, const int32_t* d_children, const int32_t* d_info,
+                            void* stream) {
+    Placement* pl = reinterpret_cast<Placement*>(h);
+    if (!pl || !d_bits || !d_children || !d_info) return set_error(SCS_ERR_ARG, "null argument");
+    if (pitch_words < (pl->n_cells + 31) / 32) return set_error(SCS_ERR_ARG, "clade mask pitch %lld is smaller than ceil(n_cells/32)", (long long)pitch_words);
+    const char* e = getenv("SCS_PLACE_ALGO");
+    if (pl->n_cells > IV5_MAX_CELLS || pl->n_rows > 4 * IV5_MAX_CELLS || (e && !strcmp(e, "gemm")))
+        return scs_placement_set_clades(h, d_bits, pitch_words, stream);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int G = pl->n_groups;
+    if (pl->iv5_L == 0) {
+        const int L = pl->n_cells <= 128 ? 8 : (pl->n_cells <= 256 ? 16 : 32);
+        const int stride = IV5_MAX_NS * L + 16 * L + 1;
+        int rows_per_task = 2048;
+        if (const char* ev = getenv("SCS_IV5_ROWS")) rows_per_task = std::max(IV5_THREADS / L, atoi(ev));
+        std::vector<Iv5Task> tasks;
+        std::vector<int> task0(size_t(G) + 1, 0);
+        for (int g = 0; g < G; ++g) {
+            task0[size_t(g)] = int(tasks.size());
+            for (int64_t r = 0; r < pl->g_nsnv[size_t(g)]; r += rows_per_task)
+                tasks.push_back(Iv5Task{g, int(std::min<int64_t>(rows_per_task, pl->g_nsnv[size_t(g)] - r)), pl->g_src0[size_t(g)] + r});
+        }
+        task0[size_t(G)] = int(tasks.size());
+        if (cudaMalloc(&pl->iv5_perm, size_t(G) * 16 * L * sizeof(uint16_t)) != cudaSuccess ||
+            cudaMalloc(&pl->iv5_lohi, size_t(G) * IV5_MAX_NS * L * sizeof(uint32_t)) != cudaSuccess ||
+            cudaMalloc(&pl->iv5_row_slot, size_t(G) * pl->n_rows * sizeof(int)) != cudaSuccess ||
+            cudaMalloc(&pl->iv5_meta, size_t(G) * 4 * sizeof(int)) != cudaSuccess ||
+            cudaMalloc(&pl->iv5_task0, task0.size() * sizeof(int)) != cudaSuccess ||
+            cudaMalloc(&pl->iv5_tasks, tasks.size() * sizeof(Iv5Task)) != cudaSuccess ||
+            cudaMalloc(&pl->iv5_part, tasks.size() * size_t(stride) * sizeof(float)) != cudaSuccess)
+            return set_error(SCS_ERR_OOM, "device allocation failed for the batch interval path (%s)", cudaGetErrorString(cudaGetLastError()));
+        SCS_CUDA(cudaMemcpy(pl->iv5_task0, task0.data(), task0.size() * sizeof(int), cudaMemcpyHostToDevice));
+        SCS_CUDA(cudaMemcpy(pl->iv5_tasks, tasks.data(), tasks.size() * sizeof(Iv5Task), cudaMemcpyHostToDevice));
+        pl->iv5_L = L;
+        pl->iv5_stride = stride;
+        pl->iv5_ntasks = int(tasks.size());
+        pl->iv5_grid = int(std::min<int64_t>(int64_t(tasks.size()), int64_t(pl->ctx->sm_count) * 4));
+    }
+    const size_t smem = (size_t(4) * pl->n_rows + 2) * sizeof(int);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(scs_iv5_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    scs_iv5_tables_kernel<<<G, 64, smem, st>>>(d_bits, pitch_words, d_children, d_info, pl->n_rows, pl->n_cells, pl->iv5_L, pl->iv5_perm,
+                                                pl->iv5_lohi, pl->iv5_row_slot, pl->iv5_meta);
+    SCS_CUDA(cudaGetLastError());
+    pl->launches++;
+    pl->algo = 3;
+    pl->operands_valid = false;
+    pl->gt_perm_valid = false;
+    return SCS_OK;
+}
+
 int scs_placement_set_genotypes_host(scs_placement* h, const uint8_t* gt, int64_t pitch_bytes, const uint8_t* row_keep, void* stream) {
     Placement* pl = reinterpret_cast<Placement*>(h);
     if (!pl || !gt) return set_error(SCS_ERR_ARG, "null argument");
@@ -2092,6 +2174,36 @@ int scs_placement_run_batch(scs_placement* h, const double* FP, const double* FN
     SCS_CUDA(cudaMemcpyAsync(pl->d_gconst, gc.data(), gc.size() * sizeof(GroupConst), cudaMemcpyHostToDevice, st));
     SCS_CUDA(cudaMemcpyAsync(pl->d_gconst_d, gd.data(), gd.size() * sizeof(double2), cudaMemcpyHostToDevice, st));
     if (pl->algo == 0) return set_error(SCS_ERR_ARG, "scs_placement_run before scs_placement_set_clades");
+    if (pl->algo == 3) {
+        if (!pl->gt_perm_valid || !pl->gt_src) return set_error(SCS_ERR_ARG, "scs_placement_run before scs_placement_set_genotypes");
+        Iv5Params q;
+        q.gt = pl->gt_src;
+        q.pitch = pl->gt_pitch;
+        q.n_cols = pl->n_cells;
+        q.perm = pl->iv5_perm;
+        q.row_keep = pl->have_row_keep ? pl->row_keep : nullptr;
+        q.tasks = pl->iv5_tasks;
+        q.n_tasks = pl->iv5_ntasks;
+        q.n_rows = pl->n_rows;
+        q.nl_lohi = pl->iv5_lohi;
+        q.meta = pl->iv5_meta;
+        q.gconst = pl->d_gconst;
+        q.part = pl->iv5_part;
+        q.stride = pl->iv5_stride;
+        double* y = d_soft_weights ? d_soft_weights : pl->y;
+        const size_t smem = iv5_smem_bytes(pl->iv5_L, pl->iv5_stride);
+        cudaEventRecord(pl->ev[0], st);
+        cudaEventRecord(pl->ev[1], st);
+        cudaEventRecord(pl->ev[2], st);
+        iv5_launch(pl->iv5_L, (std::max(pl->n_cells - 2, 1) + pl->iv5_L - 1) / pl->iv5_L, q, pl->iv5_grid, smem, st);
+        cudaEventRecord(pl->ev[3], st);          // ms[2] = the placement kernel
+        scs_iv5_reduce_kernel<<<pl->n_groups, 128, 0, st>>>(pl->iv5_part, pl->iv5_stride, pl->iv5_task0, pl->iv5_row_slot, pl->iv5_meta, pl->n_rows, y);
+        cudaEventRecord(pl->ev[4], st);
+        pl->timed = true;
+        pl->launches += 2;
+        SCS_CUDA(cudaGetLastError());
+        return SCS_OK;
+    }
     if (pl->algo == 2) {
         if (!pl->gt_src) return set_error(SCS_ERR_ARG, "scs_placement_run before scs_placement_set_genotypes");
         IntervalParams ip;
@@ -2287,7 +2399,9 @@ int scs_placement_info(scs_placement* h, int64_t* info, int32_t n) {
     const int64_t v[21] = {pl->M_pad, pl->N_pad, pl->K_pad, pl->prm.num_tasks, pl->prm.run_len, pl->prm.sb_width, pl->pair ? pl->grid2 : pl->grid, pl->launches, pl->prm.num_runs,
                            pl->pair ? K2_SMEM_TOTAL : (pl->mode == MODE_RADIX ? ModeCfg<MODE_RADIX>::SMEM_TOTAL : ModeCfg<MODE_PLANES>::SMEM_TOTAL),
                            pl->mode, pl->prm.nchunk, pl->pair ? 1 : 0, pl->n_groups, pl->pass2_mode,
-                           pl->algo, pl->iv_grid, pl->iv_threads, int64_t(pl->iv_smem), pl->iv_runs, pl->iv_variant};
+                           pl->algo, pl->algo == 3 ? pl->iv5_grid : pl->iv_grid, pl->algo == 3 ? IV5_THREADS : pl->iv_threads,
+                           pl->algo == 3 ? int64_t(iv5_smem_bytes(pl->iv5_L, pl->iv5_stride)) : int64_t(pl->iv_smem), pl->algo == 3 ? pl->iv5_ntasks : pl->iv_runs,
+                           pl->algo == 3 ? 5 : pl->iv_variant};
     for (int i = 0; i < n && i < 21; ++i) info[i] = v[i];
     return SCS_OK;
 }

@@ -190,6 +190,11 @@ class Placement:
     def set_clades(self, d_bits, words, stream=None):
         check(lib().scs_placement_set_clades(self._h, _dev_ptr(d_bits), int(words), _stream_handle(stream)))
 
+    def set_trees(self, d_bits, words, d_children, d_info, stream=None):
+        """scs_placement_set_trees: clade rows given as trees (device copies of scs_tree_parse_batch's outputs); batches of
+        up to 512 cells then take the interval path for small trees instead of the GEMM."""
+        check(lib().scs_placement_set_trees(self._h, _dev_ptr(d_bits), int(words), _dev_ptr(d_children), _dev_ptr(d_info), _stream_handle(stream)))
+
     def _rates(self, FP, FN):
         fp = np.ascontiguousarray(np.broadcast_to(np.asarray(FP, dtype=np.float64), (self.n_groups,)))
         fn = np.ascontiguousarray(np.broadcast_to(np.asarray(FN, dtype=np.float64), (self.n_groups,)))
@@ -616,7 +621,7 @@ class ReplicateSweep:
             check(lib().scs_gt_reduce_groups(self.ctx._h, _dev_ptr(d_gt), int(self.pitch), self.G, _dev_ptr(self.d_row0), int(self.group_snvs.max()),
                                              self.n_cols, _dev_ptr(self.d_amask), int(self.has_outg), _dev_ptr(self.d_keep), _dev_ptr(self.d_nkept),
                                              _dev_ptr(self.d_missing), sh))
-            self.place.set_clades(self.d_bits, self.words, stream=st)
+            self.place.set_trees(self.d_bits, self.words, self.d_children, self.d_info, stream=st)
             self.place.set_genotypes(d_gt, self.pitch, self.d_keep, stream=st)
             self.place.run(FP, FN, self.d_y, stream=st)
             check(lib().scs_sweep_model(self.ctx._h, self.G, self.n_rows, self.n_cols, int(self.words), _dev_ptr(self.d_bits), _dev_ptr(self.d_children),
