@@ -1962,7 +1962,7 @@ int scs_placement_set_trees(scs_placement* h, const uint32_t* d_bits, int64_t pi
         pl->iv5_L = L;
         pl->iv5_stride = stride;
         pl->iv5_ntasks = int(tasks.size());
-        pl->iv5_grid = int(std::min<int64_t>(int64_t(tasks.size()), int64_t(pl->ctx->sm_count) * 4));
+        pl->iv5_grid = int(std::min<int64_t>(int64_t(tasks.size()), int64_t(pl->ctx->sm_count) * IV5_MIN_CTAS));
     }
     const size_t smem = (size_t(4) * pl->n_rows + 2) * sizeof(int);
     if (smem > 48 * 1024) cudaFuncSetAttribute(scs_iv5_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));

@@ -26,6 +26,7 @@ namespace scs {
 
 constexpr int IV5_MAX_NS = 16;          // internal-node rows per lane
 constexpr int IV5_THREADS = 128;
+constexpr int IV5_MIN_CTAS = 4;          // resident CTAs per SM the register budget is capped for (128 registers per thread)
 constexpr int IV5_MAX_CELLS = 512;
 
 struct Iv5Task {
@@ -165,7 +166,7 @@ __global__ void scs_iv5_tables_kernel(const uint32_t* __restrict__ bits, long lo
 // -------------------------------------------------------------------------------------------------------------------
 // L lanes per SNV, NS (even) internal-node rows per lane, processed in pairs with packed fp32x2 arithmetic.
 template <int L, int NS>
-__global__ void __launch_bounds__(IV5_THREADS) scs_place_iv5_kernel(const Iv5Params q) {
+__global__ void __launch_bounds__(IV5_THREADS, IV5_MIN_CTAS) scs_place_iv5_kernel(const Iv5Params q) {
     constexpr int NSUB = IV5_THREADS / L;           // SNVs in flight per CTA
     constexpr int PW = 16 * L + 4;                  // words of one prefix-count table: P[0] at word 3, P[k] at 3 + k
     constexpr int NSL = IV5_MAX_NS * L, NPOS = 16 * L, NPAIR = NS / 2;

@@ -33,8 +33,8 @@ def kernel_entry(rep, name_part, source, **extra):
 
 
 out = {
-    "interval_kernel": kernel_entry("gpurun_out/r2_prof_s3_250k.ncu-rep", "scs_place_iv4_kernel", "profiles/r02_ncu_iv4_250k_summary.txt", snvs=250000),
-    "prepass_kernel": kernel_entry("gpurun_out/r2_prof_s3_250k.ncu-rep", "scs_permute_reduce4_kernel", "profiles/r02_ncu_iv4_250k_summary.txt", snvs=250000),
+    "interval_kernel": kernel_entry("gpurun_out/r2e_prof_10k_250k.ncu-rep", "scs_place_iv4_kernel", "profiles/r02_ncu_10k_250k_summary.txt", snvs=250000),
+    "prepass_kernel": kernel_entry("gpurun_out/r2e_prof_10k_250k.ncu-rep", "scs_permute_reduce4_kernel", "profiles/r02_ncu_10k_250k_summary.txt", snvs=250000),
 }
 for key, rep, part, src, scale in (("gemm_pass", "gpurun_out/prof_place_radix.ncu-rep", "scs_place_kernel", "profiles/r01_ncu_place_radix_summary.txt", 1.0),
                                    ("gemm_cache_pass1", "gpurun_out/prof_gemm_cache250.ncu-rep", "scs_place_kernel", "profiles/r01_ncu_place_cache_summary.txt", 4.0)):
