@@ -59,6 +59,11 @@ int scs_ctx_create(int32_t device, scs_ctx** out);
 int scs_ctx_destroy(scs_ctx* ctx);
 /* info[0..5] = sm_count, cc_major, cc_minor, total_mem_MiB, l2_bytes, device */
 int scs_ctx_info(scs_ctx* ctx, int64_t* info, int32_t n);
+/* Host -> device upload of a SMALL page-locked buffer (cudaHostAlloc / cudaHostRegister / torch pin_memory) by a kernel that
+ * reads it over PCIe, not by the copy engine: the device's one H2D queue serves all streams, so a small upload issued while
+ * another stream's 100 MB matrix copy is in flight would wait for it.  The buffer must stay unchanged until the kernel has
+ * run.  Asynchronous on `stream`; falls back to cudaMemcpyAsync when the memory is not page-locked. */
+int scs_upload_async(void* d_dst, const void* h_pinned, int64_t bytes, void* stream);
 
 /* ------------------------------------------------------------------ VCF decode
  * get_mut_df (run_PT_test.py:27-207, filter=True).  `text` is the decompressed

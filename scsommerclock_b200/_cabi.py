@@ -29,6 +29,7 @@ _SIGNATURES = {
     "scs_ctx_create": (C.c_int, [C.c_int32, C.POINTER(C.c_void_p)]),
     "scs_ctx_destroy": (C.c_int, [C.c_void_p]),
     "scs_ctx_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
+    "scs_upload_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "scs_placement_create": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "scs_placement_create_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "scs_placement_run_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

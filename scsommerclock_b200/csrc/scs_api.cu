@@ -1,4 +1,5 @@
 // scs_api.cu -- context, error reporting and the one-shot host entry points.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 
@@ -29,9 +30,60 @@ void* ctx_scratch(scs_ctx* ctx, size_t bytes) {
 }
 }  // namespace scs
 
+namespace scs {
+__global__ void scs_upload_kernel(const unsigned char* __restrict__ src, unsigned char* __restrict__ dst, size_t bytes) {
+    const size_t n16 = (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) ? bytes / 16 : 0;
+    const size_t stride = size_t(gridDim.x) * blockDim.x, i0 = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    for (size_t i = i0; i < n16; i += stride) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+    for (size_t i = n16 * 16 + i0; i < bytes; i += stride) dst[i] = src[i];
+}
+
+int upload_pinned(void* d_dst, const void* h_pinned, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return SCS_OK;
+    void* dev_view = nullptr;
+    if (cudaHostGetDevicePointer(&dev_view, const_cast<void*>(h_pinned), 0) != cudaSuccess) {
+        cudaGetLastError();          // not page-locked after all: the copy engine
+        SCS_CUDA(cudaMemcpyAsync(d_dst, h_pinned, bytes, cudaMemcpyHostToDevice, st));
+        return SCS_OK;
+    }
+    const int threads = 256;
+    const int blocks = int(std::min<size_t>(64, (bytes / 16 + threads - 1) / threads + 1));
+    scs_upload_kernel<<<blocks, threads, 0, st>>>(static_cast<const unsigned char*>(dev_view), static_cast<unsigned char*>(d_dst), bytes);
+    SCS_CUDA(cudaGetLastError());
+    return SCS_OK;
+}
+
+int upload_small(scs_ctx* ctx, void* d_dst, const void* h_src, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return SCS_OK;
+    scs_ctx::PinnedSlot& s = ctx->pin[ctx->pin_next];
+    ctx->pin_next = (ctx->pin_next + 1) % 8;
+    if (s.ev) SCS_CUDA(cudaEventSynchronize(s.ev));        // the slot's previous upload has been read
+    if (bytes > s.bytes) {
+        if (s.ptr) cudaFreeHost(s.ptr);
+        s.ptr = nullptr;
+        s.bytes = 0;
+        const size_t want = (bytes + 4095) / 4096 * 4096;
+        if (cudaHostAlloc(&s.ptr, want, cudaHostAllocDefault) != cudaSuccess) return set_error(SCS_ERR_OOM, "page-locked staging allocation of %zu bytes failed", want);
+        s.bytes = want;
+    }
+    if (!s.ev) SCS_CUDA(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+    memcpy(s.ptr, h_src, bytes);
+    const int rc = upload_pinned(d_dst, s.ptr, bytes, st);
+    if (rc != SCS_OK) return rc;
+    SCS_CUDA(cudaEventRecord(s.ev, st));
+    return SCS_OK;
+}
+}  // namespace scs
+
 using namespace scs;
 
 extern "C" {
+
+// Host -> device upload of a small page-locked buffer by a kernel instead of the copy engine (see scs_internal.h).
+int scs_upload_async(void* d_dst, const void* h_pinned, int64_t bytes, void* stream) {
+    if (!d_dst || !h_pinned || bytes < 0) return set_error(SCS_ERR_ARG, "bad argument");
+    return upload_pinned(d_dst, h_pinned, size_t(bytes), reinterpret_cast<cudaStream_t>(stream));
+}
 
 const char* scs_version(void) { return "scsommerclock_b200 0.1 (sm_100a)"; }
 const char* scs_last_error(void) { return g_err; }
@@ -61,6 +113,11 @@ int scs_ctx_create(int32_t device, scs_ctx** out) {
 
 int scs_ctx_destroy(scs_ctx* ctx) {
     if (ctx && ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx)
+        for (auto& s : ctx->pin) {
+            if (s.ev) cudaEventDestroy(s.ev);
+            if (s.ptr) cudaFreeHost(s.ptr);
+        }
     delete ctx;
     return SCS_OK;
 }

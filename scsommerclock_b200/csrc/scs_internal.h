@@ -16,11 +16,31 @@ struct scs_ctx {
     // device-wide synchronisation -- on the per-chunk path of StreamingPlacement)
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
+    // ring of page-locked staging slots for small host -> device uploads that must not queue behind big copies
+    // (scs::upload_small); each slot waits for its previous user before it is rewritten
+    struct PinnedSlot {
+        void* ptr = nullptr;
+        size_t bytes = 0;
+        cudaEvent_t ev = nullptr;
+    };
+    PinnedSlot pin[8];
+    int pin_next = 0;
 };
 
 namespace scs {
 // Device scratch of at least `bytes` owned by the context (grown, never shrunk); nullptr on failure.
 void* ctx_scratch(scs_ctx* ctx, size_t bytes);
+}  // namespace scs
+
+namespace scs {
+// Small host -> device uploads as a KERNEL that reads page-locked host memory over PCIe instead of a copy-engine transfer:
+// the one H2D queue of the device serves all streams, so a 1 MB upload issued while a 100 MB matrix copy of another stream
+// is in flight waits for it (measured: the small uploads of a replicate sub-batch took 3.8 ms behind the next sub-batch's
+// matrix).  upload_pinned: `h_pinned` is page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory) and stays
+// unchanged until the kernel has run; upload_small: any host memory, staged through the context's ring of pinned slots
+// before the call returns.  Both asynchronous on `st`.
+int upload_pinned(void* d_dst, const void* h_pinned, size_t bytes, cudaStream_t st);
+int upload_small(scs_ctx* ctx, void* d_dst, const void* h_src, size_t bytes, cudaStream_t st);
 }  // namespace scs
 
 namespace scs {

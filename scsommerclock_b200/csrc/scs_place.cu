@@ -2171,8 +2171,12 @@ int scs_placement_run_batch(scs_placement* h, const double* FP, const double* FN
             return set_error(SCS_ERR_ARG, "error rates must lie in (0,1): group %d FP=%g FN=%g", g, FP[g], FN[g]);
         make_constants(pl->n_cells, FP[g], FN[g], &gc[g], &gd[g]);
     }
-    SCS_CUDA(cudaMemcpyAsync(pl->d_gconst, gc.data(), gc.size() * sizeof(GroupConst), cudaMemcpyHostToDevice, st));
-    SCS_CUDA(cudaMemcpyAsync(pl->d_gconst_d, gd.data(), gd.size() * sizeof(double2), cudaMemcpyHostToDevice, st));
+    {
+        // (a kernel reading page-locked staging, not the copy engine: see scs::upload_small)
+        int rc = upload_small(pl->ctx, pl->d_gconst, gc.data(), gc.size() * sizeof(GroupConst), st);
+        if (rc == SCS_OK) rc = upload_small(pl->ctx, pl->d_gconst_d, gd.data(), gd.size() * sizeof(double2), st);
+        if (rc != SCS_OK) return rc;
+    }
     if (pl->algo == 0) return set_error(SCS_ERR_ARG, "scs_placement_run before scs_placement_set_clades");
     if (pl->algo == 3) {
         if (!pl->gt_perm_valid || !pl->gt_src) return set_error(SCS_ERR_ARG, "scs_placement_run before scs_placement_set_genotypes");

@@ -267,7 +267,10 @@ int scs_sweep_model(scs_ctx* ctx, int32_t n_groups, int32_t n_rows, int32_t n_ce
         consts[size_t(n_groups) + g] = FN[g];
     }
     for (int w = 0; w < n_w; ++w) consts[size_t(2) * n_groups + w] = w_max[w];
-    SCS_CUDA(cudaMemcpyAsync(d_consts, consts.data(), consts.size() * sizeof(double), cudaMemcpyHostToDevice, st));   // (pageable: staged before the call returns)
+    {
+        const int urc = upload_small(ctx, d_consts, consts.data(), consts.size() * sizeof(double), st);      // (not the copy engine: scs_internal.h)
+        if (urc != SCS_OK) return urc;
+    }
     int32_t *d_child = nullptr, *d_gather = nullptr;
     double* d_w = nullptr;
     int rc = scs_lrt_plan_device_inputs(plan, int64_t(n_groups) * n_rows, &d_child, &d_gather, &d_w);

@@ -574,6 +574,7 @@ class ReplicateSweep:
         self.h_status = torch.empty(G, dtype=torch.int32, pin_memory=True)
         self.d_gt = None
         self.done = torch.cuda.Event()
+        self.marks = None
 
     def close(self):
         if self._lrt:
@@ -606,7 +607,14 @@ class ReplicateSweep:
         FP = np.ascontiguousarray(np.broadcast_to(np.asarray(FP, dtype=np.float64), (self.G,)))
         FN = np.ascontiguousarray(np.broadcast_to(np.asarray(FN, dtype=np.float64), (self.G,)))
         self.FP, self.FN = FP, FN
+        marks = self.marks                  # tools only: a list collects (stage, event) pairs of this call
+        def mark(what):
+            if marks is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(st)
+                marks.append((what, ev))
         with torch.cuda.stream(st):
+            mark("start")
             if packed.is_cuda:
                 d_gt = packed
             else:
@@ -614,23 +622,31 @@ class ReplicateSweep:
                     self.d_gt = torch.empty((self.total, self.pitch), dtype=torch.uint8, device=self.dev)
                 self.d_gt.copy_(packed, non_blocking=True)
                 d_gt = self.d_gt
-            self.d_bits.copy_(self.h_bits, non_blocking=True)
-            self.d_children.copy_(self.h_children, non_blocking=True)
-            self.d_info.copy_(self.h_info, non_blocking=True)
             sh = _stream_handle(st)
+            # masks / topology / node counts: uploaded by a kernel that reads the pinned staging buffers, not by the copy
+            # engine, whose one queue may be busy with another sub-batch's matrix for milliseconds (scs_upload_async)
+            for dst, src in ((self.d_bits, self.h_bits), (self.d_children, self.h_children), (self.d_info, self.h_info)):
+                check(lib().scs_upload_async(_dev_ptr(dst), C.c_void_p(src.data_ptr()), int(src.numel() * src.element_size()), sh))
+            mark("uploads")
             check(lib().scs_gt_reduce_groups(self.ctx._h, _dev_ptr(d_gt), int(self.pitch), self.G, _dev_ptr(self.d_row0), int(self.group_snvs.max()),
                                              self.n_cols, _dev_ptr(self.d_amask), int(self.has_outg), _dev_ptr(self.d_keep), _dev_ptr(self.d_nkept),
                                              _dev_ptr(self.d_missing), sh))
+            mark("gt_reduce")
             self.place.set_trees(self.d_bits, self.words, self.d_children, self.d_info, stream=st)
             self.place.set_genotypes(d_gt, self.pitch, self.d_keep, stream=st)
+            mark("tables")
             self.place.run(FP, FN, self.d_y, stream=st)
+            mark("placement")
             check(lib().scs_sweep_model(self.ctx._h, self.G, self.n_rows, self.n_cols, int(self.words), _dev_ptr(self.d_bits), _dev_ptr(self.d_children),
                                         _dev_ptr(self.d_info), _dev_ptr(self.d_nkept), _dev_ptr(self.d_missing), ptr(FP), ptr(FN), ptr(self.w_maxs),
                                         self.n_w, _dev_ptr(self.d_y), self.n_br, self._lrt, _dev_ptr(self.d_status), _dev_ptr(self.d_work), sh))
+            mark("model")
             check(lib().scs_lrt_plan_run(self._lrt, _dev_ptr(self.d_y), _dev_ptr(self.d_out), None, sh))
+            mark("lrt")
             self.h_out.copy_(self.d_out, non_blocking=True)
             self.h_nkept.copy_(self.d_nkept, non_blocking=True)
             self.h_status.copy_(self.d_status, non_blocking=True)
+            mark("download")
             self.done.record(st)
 
     def results(self):
@@ -648,7 +664,7 @@ class ReplicateSweepStream:
     """A large sweep whose packed genotype matrices sit in (pinned) HOST memory and whose trees are Newick TEXT, through
     ``ReplicateSweep`` in ``n_sub`` sub-batches so that the three resources work at the same time:
 
-        copy engine     sub-batch k + 1's matrix is copied (own stream) while sub-batch k's kernels run;
+        copy engine     every sub-batch's matrix copy is queued up front on a copy stream;
         host threads    a worker thread parses the trees of sub-batch k + 1, k + 2, ... (native code, the GIL is released)
                         while the main thread enqueues sub-batch k's kernels the moment its trees are parsed and formats the
                         TSV lines of the sub-batches that have finished (native, on host threads);
@@ -699,22 +715,19 @@ class ReplicateSweepStream:
 
         trace = self.trace
         t00 = time.perf_counter()
-
-        def queue_copy(k):
-            # One H2D queue serves every stream in issue order: sub-batch k + 1's matrix is queued only AFTER sub-batch k's
-            # small uploads (masks, topology, per-group constants), which would otherwise wait behind ALL the matrices
-            # (measured: the first kernels started after the last matrix had landed).
-            sub = self.subs[k]
-            with torch.cuda.stream(self.copy_stream):
-                self.copy_stream.wait_event(sub.done)          # the previous run's kernels on this buffer (a no-op the first time)
-                sub.d_gt.copy_(host_packed[self.row_cuts[k]:self.row_cuts[k + 1]], non_blocking=True)
-                self.copied[k].record(self.copy_stream)
-
         if trace is not None:
             self.trace_events = []
             self.trace_t0 = torch.cuda.Event(enable_timing=True)
             self.trace_t0.record(cur)
-        queue_copy(0)
+        # every sub-batch's matrix copy is queued up front on the copy stream: the link is busy from the first microsecond.
+        # (That only works because the small uploads of a sub-batch -- masks, topology, per-group constants -- do NOT go
+        # through the copy engine, scs_upload_async: the device's one H2D queue serves all streams, and with copy-engine
+        # uploads the first kernels started after the LAST matrix had landed.)
+        with torch.cuda.stream(self.copy_stream):
+            for k, sub in enumerate(self.subs):
+                self.copy_stream.wait_event(sub.done)          # the previous run's kernels on this buffer (a no-op the first time)
+                sub.d_gt.copy_(host_packed[self.row_cuts[k]:self.row_cuts[k + 1]], non_blocking=True)
+                self.copied[k].record(self.copy_stream)
         parsed = [threading.Event() for _ in self.subs]
         failure = []
 
@@ -748,8 +761,6 @@ class ReplicateSweepStream:
             if trace is not None:
                 e_b.record(self.compute_stream)
                 self.trace_events.append((k, e_a, e_b))
-            if k + 1 < len(self.subs):
-                queue_copy(k + 1)
             note("enqueued", k)
             while formatted < k and self.subs[formatted].done.query():      # lines of sub-batches that are already back
                 rows.extend(self.subs[formatted].rows())

@@ -30,6 +30,8 @@ pipe = engine.ReplicateSweepStream(ctx, [n_snv] * R, columns, bench.W_MAXS, n_su
 for it in range(4):
     torch.cuda.synchronize()
     pipe.trace = [] if it == 3 else None
+    for sub in pipe.subs:
+        sub.marks = [] if it == 3 else None
     t0 = time.perf_counter()
     rows, status = pipe.run(pinned, newicks, 0.01, 0.05)
     torch.cuda.synchronize()
@@ -37,6 +39,8 @@ for it in range(4):
 print("n_sub %d: %.2f ms" % (n_sub, dt))
 for k, a, b in pipe.trace_events:
     print("  device: sub %d kernels %.2f -> %.2f ms" % (k, pipe.trace_t0.elapsed_time(a), pipe.trace_t0.elapsed_time(b)))
+for k, sub in enumerate(pipe.subs):
+    print("  device stages sub %d:" % k, ", ".join("%s %.2f" % (w, pipe.trace_t0.elapsed_time(e)) for w, e in sub.marks))
 for what, k, t in pipe.trace:
     print("  %6.2f ms  %s %d" % (t, what, k))
 t0 = time.perf_counter(); pipe.subs[0].parse_trees(newicks[:pipe.cuts[1]]); print("parse of one sub-batch alone: %.2f ms" % (1e3 * (time.perf_counter() - t0)))
