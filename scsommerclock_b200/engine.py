@@ -589,9 +589,14 @@ class ReplicateSweep:
             pass
 
     def parse_trees(self, newicks, strip_tags=False, threads=0):
-        """Host part (no device work): trees -> masks / topology in the pinned staging buffers."""
+        """Host part (no device work): trees -> masks / topology in the pinned staging buffers.  ``threads`` = 0: the
+        host cores divided by the ranks on this node (torchrun's LOCAL_WORLD_SIZE), at most 16."""
         n = len(newicks)
         assert n == self.G
+        if threads <= 0:
+            import os
+            local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+            threads = max(1, min(16, (os.cpu_count() or 1) // local_world))
         text, off = _concat_strings(newicks)
         names, noff = _concat_strings(self.columns)
         check(lib().scs_tree_parse_batch(n, text, ptr(off), int(bool(strip_tags)), self.n_cols, names, ptr(noff), self.outgroup.encode(),
