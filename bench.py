@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=0, help="SNV-row chunks of the host-buffer (e2e) leg (0: sized from the matrix, ~96 MB per chunk)")
-    ap.add_argument("--algo", default="auto", choices=["auto", "gemm"],
+    ap.add_argument("--algo", default="auto", choices=["auto", "gemm", "interval"],
                     help="auto: tree-shaped clade masks take the interval path (prefix counts, no GEMM); gemm: force the tcgen05 GEMM")
     ap.add_argument("--no-gemm-leg", action="store_true", help="skip the extra GEMM-path measurement of the same workload")
     ap.add_argument("--replicates", type=int, default=1250,

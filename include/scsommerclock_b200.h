@@ -136,9 +136,10 @@ int scs_placement_prepare_result(scs_placement* plan, int64_t* n_kept, double* m
  * The masks also decide HOW the counts S x genotypes are formed: the clades of a tree are a
  * laminar family, so in a depth-first order of the cells every row is one interval and both
  * counts of a (SNV, clade) pair are a difference of per-SNV prefix counts -- the "interval
- * path" (csrc/scs_place_interval.cuh), used for single-dataset plans of more than 3968 cells
- * whose masks pass that test (below that the GEMM was measured faster).  Any other 0/1 matrix,
- * and every replicate batch, goes through the tcgen05 GEMM.  SCS_PLACE_ALGO=gemm forces the GEMM,
+ * path" (csrc/scs_place_interval.cuh), used for single-dataset plans of at least 100 cells
+ * whose masks pass that test (measured faster than the GEMM from there on).  Any other 0/1 matrix,
+ * and every replicate batch given as masks only, goes through the tcgen05 GEMM (batches given as trees:
+ * scs_placement_set_trees).  SCS_PLACE_ALGO=gemm forces the GEMM,
  * SCS_PLACE_ALGO=interval takes the interval path for tree-shaped masks at any size. */
 int scs_placement_set_clades(scs_placement* plan, const uint32_t* d_bits, int64_t pitch_words, void* stream);
 /* The clade rows of every group given as TREES: d_bits as for scs_placement_set_clades plus the child table and node

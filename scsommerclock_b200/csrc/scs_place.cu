@@ -1708,21 +1708,24 @@ int scs_placement_bind_genotypes(scs_placement* h, const uint8_t* d_gt, int64_t 
 }
 
 // Decide the algorithm for these clade masks (host copy `bits`): interval path when they are a laminar
-// family, the plan is a single dataset of more than 3968 cells and the working set fits shared memory;
+// family, the plan is a single dataset of at least 100 cells and the working set fits shared memory;
 // SCS_PLACE_ALGO = gemm | interval | auto overrides ("interval": whenever the masks are laminar, at any size).
+constexpr int IV_AUTO_MIN_CELLS = 100;
 static int choose_algo(Placement* pl, const uint32_t* bits, int64_t pitch_words, cudaStream_t st) {
     pl->algo = 1;
     pl->gt_perm_valid = false;      // (the cell order may change with the masks)
     const char* e = getenv("SCS_PLACE_ALGO");
     if (e && !strcmp(e, "gemm")) return SCS_OK;
     if (pl->n_groups != 1) return SCS_OK;
-    // Where each algorithm wins was measured, not assumed (bench.py, same run): at 10,000 cells the interval path
-    // is 3.3x faster than the GEMM (51 against 170 ms per step), at 1,000 cells the GEMM -- one K chunk, epilogue
-    // bound, cost proportional to the clade rows like the interval path's but with a smaller constant -- is 1.9x
-    // faster (0.98 against 1.86 ms).  "auto" therefore takes the interval path from the GEMM's own regime change on
-    // (more than one K chunk: > 3968 cells); SCS_PLACE_ALGO=interval takes it for every tree-shaped matrix.
+    // Where each algorithm wins was measured, not assumed (tools/gpu_r2_s18.sh: bench.py --algo gemm | interval, one PT test
+    // over 100k SNVs, ms per step GEMM / interval): 120 cells 0.47 / 0.46, 250 0.52 / 0.49, 400 0.51 / 0.45, 500 0.57 / 0.48,
+    // 1,000 0.86 / 0.62, 2,000 1.86 / 0.96, 3,900 4.46 / 1.71, 10,000 173 / 26.  (Round 1 had the GEMM ahead below 3,968
+    // cells: the per-row barriers of interval variant 3, then the pre-pass and the flush of thousands of tiny runs, were
+    // what lost there -- variant 4, the sub-block pre-pass and whole-wave runs removed them.)  "auto" takes the interval
+    // path for every tree-shaped matrix of at least 100 cells; below that the step is all fixed cost either way and the GEMM
+    // spares the host-side interval analysis.  SCS_PLACE_ALGO=interval takes it at any size.
     const bool forced = e && (!strcmp(e, "interval") || !strcmp(e, "interval1") || !strcmp(e, "interval3"));
-    if (!forced && pl->n_cells <= RADIX_KB_PER_CHUNK * BLOCK_K) return SCS_OK;
+    if (!forced && pl->n_cells < IV_AUTO_MIN_CELLS) return SCS_OK;
     const size_t SMEM_MAX = 227 * 1024;
     // cheapest test first: does even the smallest working set (prefix counts + accumulators) fit shared memory?
     if (interval_smem_bytes(pl->n_cells, pl->n_rows, false, false) > SMEM_MAX) return SCS_OK;
@@ -1878,8 +1881,11 @@ static int choose_algo(Placement* pl, const uint32_t* bits, int64_t pitch_words,
     pl->iv_threads = threads;
     per_sm = std::max(1, per_sm);
     const int64_t slots = int64_t(pl->ctx->sm_count) * per_sm;
-    // runs: short fp32 accumulation chains (<= 256 rows) and at least ~4 runs per resident CTA
-    int rpr = int(std::min<int64_t>(256, std::max<int64_t>(16, (pl->n_snv + 4 * slots - 1) / (4 * slots))));
+    // runs: short fp32 accumulation chains (<= 256 rows), a whole number of waves of the resident CTAs where the matrix
+    // allows it (a run flushes every accumulator: thousands of 17-row runs -- the round-1 rule "four runs per CTA" at 1,000
+    // cells x 100k SNVs -- cost more in partial sums, 70 MB, than the rows themselves)
+    const int64_t waves = std::max<int64_t>(1, (pl->n_snv + 256 * slots - 1) / (256 * slots));
+    int rpr = int(std::min<int64_t>(256, std::max<int64_t>(16, (pl->n_snv + slots * waves - 1) / (slots * waves))));
     if (const char* t = getenv("SCS_IV_ROWS_PER_RUN")) rpr = std::max(1, atoi(t));
     pl->iv_rows_per_run = rpr;
     pl->iv_runs = int((pl->n_snv + rpr - 1) / rpr);
@@ -2123,10 +2129,14 @@ int scs_placement_prepare(scs_placement* h, const uint8_t* d_gt, int64_t pitch_b
             pl->gt_perm, pl->row_keep, reinterpret_cast<unsigned long long*>(pl->d_prep), reinterpret_cast<unsigned int*>(pl->d_prep + off_miss));
     } else {
         const int64_t groups = (pl->n_snv + 3) / 4;
-        const unsigned pgrid = unsigned(std::min<int64_t>(groups, int64_t(pl->ctx->sm_count) * std::max(1, 2048 / pt)));
-        scs_permute_reduce4_kernel<<<pgrid, pt, 2 * (4 * rw + 4) * sizeof(uint32_t), st>>>(
+        // narrow rows: several sub-blocks (one per group of four rows) share a 256-thread block, each seeing >= 32 groups
+        const int nsub = pt >= 256 ? 1 : std::min(PERM4_MAX_SUB, 256 / pt);
+        int64_t sub_blocks = std::min<int64_t>(groups, int64_t(pl->ctx->sm_count) * std::max(1, 2048 / pt));
+        if (nsub > 1) sub_blocks = std::min<int64_t>(sub_blocks, std::max<int64_t>(1, (groups + 31) / 32));
+        const unsigned pgrid = unsigned((sub_blocks + nsub - 1) / nsub);
+        scs_permute_reduce4_kernel<<<pgrid, pt * nsub, size_t(nsub) * 2 * (4 * rw + 4) * sizeof(uint32_t), st>>>(
             d_gt, pitch_bytes, pl->n_snv, n_cells, rw, pl->d_perm, reinterpret_cast<const uint32_t*>(pl->d_prep + off_mask), filter_rows,
-            pl->gt_perm, pl->row_keep, reinterpret_cast<unsigned long long*>(pl->d_prep), reinterpret_cast<unsigned int*>(pl->d_prep + off_miss));
+            pl->gt_perm, pl->row_keep, reinterpret_cast<unsigned long long*>(pl->d_prep), reinterpret_cast<unsigned int*>(pl->d_prep + off_miss), pt);
     }
     SCS_CUDA(cudaGetLastError());
     cudaEventRecord(pl->ev_prep[1], st);
@@ -2284,8 +2294,8 @@ int scs_placement_run_batch(scs_placement* h, const double* FP, const double* FN
             scs_place_interval_kernel<false><<<pl->iv_grid, pl->iv_threads, pl->iv_smem, st>>>(ip);
         }
         cudaEventRecord(pl->ev[3], st);          // ms[2] = the placement kernel
-        scs_reduce_interval_kernel<<<unsigned((pl->iv_entries + 255) / 256), 256, 0, st>>>(pl->ipart, pl->iv_runs, pl->iv_entries, pl->iv_stride,
-                                                                                         pl->d_slot_row, y);
+        scs_reduce_interval_kernel<<<unsigned((pl->iv_entries + 31) / 32), 32 * IV_REDUCE_SLICES, 0, st>>>(pl->ipart, pl->iv_runs, pl->iv_entries,
+                                                                                                           pl->iv_stride, pl->d_slot_row, y);
         cudaEventRecord(pl->ev[4], st);
         pl->timed = true;
         pl->launches += 2;

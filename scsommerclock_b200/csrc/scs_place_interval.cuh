@@ -413,16 +413,25 @@ __global__ void scs_permute_reduce_kernel(const uint8_t* __restrict__ gt, long l
 // sixteen steps fill the word in order, no masking).  ~2.7 instructions and a quarter of a load per (row, cell).
 // Row flags of the four rows are OR-ed over the block through one shared word per group (three rotate, cleared two groups
 // ahead) in front of the group's single barrier.
+// Narrow rows (round 2): a block of `nsub` sub-blocks of `pt` threads each (pt = row words rounded up to a warp), every
+// sub-block walking its own groups of four rows -- at 1,000 cells a 64-thread block per group left the SMs mostly empty and
+// spent its time in per-block set-up and in 1,008 global atomics per block (0.39 ms for 25 MB, 130 GB/s); now 256 threads
+// share the barrier, the missing counts of the sub-blocks are combined in shared memory first, and the grid is sized so
+// that a sub-block sees at least 32 groups.
 constexpr int PERM4_THREADS_MAX = 1024;
+constexpr int PERM4_MAX_SUB = 8;
 __global__ void scs_permute_reduce4_kernel(const uint8_t* __restrict__ gt, long long pitch, long long n_snv, int n_cells, int row_words,
                                            const uint16_t* __restrict__ perm, const uint32_t* __restrict__ active_mask, int filter_rows,
                                            uint32_t* __restrict__ out, uint8_t* __restrict__ row_keep,
-                                           unsigned long long* __restrict__ n_kept, unsigned int* __restrict__ missing_pos) {
-    extern __shared__ uint32_t pm_smem[];          // two buffers of 4 row_words + 4 words (the last four: all ones = "missing" for padding)
-    __shared__ uint32_t s_flags[3];
-    const int t = threadIdx.x, lane = t & 31;
+                                           unsigned long long* __restrict__ n_kept, unsigned int* __restrict__ missing_pos, int pt) {
+    extern __shared__ uint32_t pm_smem[];          // per sub-block: two buffers of 4 row_words + 4 words (the last four: all ones = "missing" for padding)
+    __shared__ uint32_t s_flags[3 * PERM4_MAX_SUB];
+    const int nsub = blockDim.x / pt;
+    const int t = threadIdx.x % pt, sub = threadIdx.x / pt, lane = threadIdx.x & 31;
     const bool own = t < row_words;
     const int buf_words = 4 * row_words + 4;
+    uint32_t* const my_smem = pm_smem + sub * 2 * buf_words;
+    uint32_t* const my_flags = s_flags + 3 * sub;
     // per output position: source word index (= source byte of the row) | shift << 16
     uint32_t src[16];
     uint32_t valid = 0u;                           // bit 2e: output position 16 t + e is a cell
@@ -455,10 +464,11 @@ __global__ void scs_permute_reduce4_kernel(const uint8_t* __restrict__ gt, long 
         a0 = a1 = a2 = a3 = 0u;
         pending = 0;
     };
-    if (t < 3) s_flags[t] = 0u;
-    if (t < 8) pm_smem[(t >> 2) * buf_words + 4 * row_words + (t & 3)] = 0xFFFFFFFFu;
+    if (t < 3) my_flags[t] = 0u;
+    if (t < 8) my_smem[(t >> 2) * buf_words + 4 * row_words + (t & 3)] = 0xFFFFFFFFu;
     __syncthreads();
     const long long n_groups = (n_snv + 3) >> 2;
+    const long long gstride = (long long)gridDim.x * nsub;
     uint32_t wn[4];
     auto load_group = [&](long long g) {
 #pragma unroll
@@ -467,12 +477,14 @@ __global__ void scs_permute_reduce4_kernel(const uint8_t* __restrict__ gt, long 
             wn[i] = (own && r < n_snv) ? reinterpret_cast<const uint32_t*>(gt + size_t(r) * pitch)[t] : 0xFFFFFFFFu;
         }
     };
-    if (blockIdx.x < n_groups) load_group(blockIdx.x);
+    load_group((long long)blockIdx.x * nsub + sub);        // (rows beyond the matrix read as missing)
     int buf = 0, fb = 0;
-    for (long long g = blockIdx.x; g < n_groups; g += gridDim.x, buf ^= 1, fb = fb == 2 ? 0 : fb + 1) {
-        uint32_t* rb = pm_smem + buf * buf_words;
+    // every sub-block makes the trips of sub-block 0 (the barrier is block wide); a trip beyond the matrix has no rows
+    for (long long g0 = (long long)blockIdx.x * nsub; g0 < n_groups; g0 += gstride, buf ^= 1, fb = fb == 2 ? 0 : fb + 1) {
+        const long long g = g0 + sub;
+        uint32_t* rb = my_smem + buf * buf_words;
         const uint32_t w0 = wn[0], w1 = wn[1], w2 = wn[2], w3 = wn[3];
-        if (g + gridDim.x < n_groups) load_group(g + gridDim.x);
+        load_group(g + gstride);
         uint32_t flags = 0u;
         if (own) {
             // 4 x 4 byte transpose: word k of the result holds byte k of the four rows
@@ -485,10 +497,10 @@ __global__ void scs_permute_reduce4_kernel(const uint8_t* __restrict__ gt, long 
                     ((((w2 ^ (w2 >> 1)) & am) != 0u) ? 4u : 0u) | ((((w3 ^ (w3 >> 1)) & am) != 0u) ? 8u : 0u);
         }
         flags = __reduce_or_sync(0xffffffffu, flags);
-        if (lane == 0 && flags) atomicOr(&s_flags[fb], flags);
+        if (lane == 0 && flags) atomicOr(&my_flags[fb], flags);
         __syncthreads();           // the group is staged, its flags are complete
-        uint32_t keep4 = filter_rows ? s_flags[fb] : 0xFu;
-        if (t == 0) s_flags[fb == 0 ? 2 : fb - 1] = 0u;      // the word of group g + 2 (last read one group ago, next written after the next barrier)
+        uint32_t keep4 = filter_rows ? my_flags[fb] : 0xFu;
+        if (t == 0) my_flags[fb == 0 ? 2 : fb - 1] = 0u;      // the word of group g + 2 (last read one group ago, next written after the next barrier)
         if (own) {
             uint32_t o0 = 0u, o1 = 0u, o2 = 0u, o3 = 0u;
 #pragma unroll
@@ -516,7 +528,7 @@ __global__ void scs_permute_reduce4_kernel(const uint8_t* __restrict__ gt, long 
             }
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {                             // (uniform over the block)
+        for (int i = 0; i < 4; ++i) {                             // (uniform over the sub-block)
             const long long r = 4 * g + i;
             if (r < n_snv && ((keep4 >> i) & 1u)) {
                 ++pending;
@@ -527,12 +539,30 @@ __global__ void scs_permute_reduce4_kernel(const uint8_t* __restrict__ gt, long 
         if (t < 4 && 4 * g + t < n_snv) row_keep[4 * g + t] = uint8_t((keep4 >> t) & 1u);
     }
     flush();
+    if (nsub == 1) {
+        if (own) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+                if (total[k]) atomicAdd(&missing_pos[16 * t + k], total[k]);
+        }
+        if (t == 0 && kept_cnt) atomicAdd(n_kept, (unsigned long long)kept_cnt);
+        return;
+    }
+    // several sub-blocks: their counts meet in shared memory (the staging buffers are free now), one global atomic per position
+    __syncthreads();
+    unsigned int* tot_s = pm_smem;                 // [16 row_words] + 1 (kept rows); nsub >= 2 sub-blocks own >= 16 row_words + 16 words
+    for (int k = threadIdx.x; k < 16 * row_words + 1; k += blockDim.x) tot_s[k] = 0u;
+    __syncthreads();
     if (own) {
 #pragma unroll
         for (int k = 0; k < 16; ++k)
-            if (total[k]) atomicAdd(&missing_pos[16 * t + k], total[k]);
+            if (total[k]) atomicAdd(&tot_s[16 * t + k], total[k]);
     }
-    if (t == 0 && kept_cnt) atomicAdd(n_kept, (unsigned long long)kept_cnt);
+    if (t == 0 && kept_cnt) atomicAdd(&tot_s[16 * row_words], kept_cnt);
+    __syncthreads();
+    for (int k = threadIdx.x; k < 16 * row_words; k += blockDim.x)
+        if (tot_s[k]) atomicAdd(&missing_pos[k], tot_s[k]);
+    if (threadIdx.x == 0 && tot_s[16 * row_words]) atomicAdd(n_kept, (unsigned long long)tot_s[16 * row_words]);
 }
 
 // MAXT: largest CTA this instantiation is launched with (register budget); UNR: unroll factor of the three sweeps.
@@ -762,22 +792,36 @@ __global__ void __launch_bounds__(MAXT, 1) scs_place_interval3_kernel(const Inte
 
 // y[row of slot s] = sum over the runs of part[run][s], fixed order, fp64 (slots without a row -- padding,
 // positions without a leaf row -- are skipped)
+constexpr int IV_REDUCE_SLICES = 8;
 __global__ void scs_reduce_interval_kernel(const float* __restrict__ part, int num_runs, int n_entries, int stride,
                                            const int* __restrict__ row_of_slot, double* __restrict__ y) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= n_entries) return;
-    const int row = row_of_slot[b];
-    if (row < 0) return;
+    // block = 32 entries x 8 slices of the runs; a slice sums runs s, s + 8, ... (4 independent chains), the slices are
+    // combined in fixed order: deterministic, and thousands of runs are no longer one thread's sequential walk
+    __shared__ double sm[IV_REDUCE_SLICES][32];
+    const int e = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int b = blockIdx.x * 32 + e;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    int r = 0;
-    for (; r + 3 < num_runs; r += 4) {
-        a0 += double(part[size_t(r) * stride + b]);
-        a1 += double(part[size_t(r + 1) * stride + b]);
-        a2 += double(part[size_t(r + 2) * stride + b]);
-        a3 += double(part[size_t(r + 3) * stride + b]);
+    if (b < n_entries) {
+        int r = sl;
+        for (; r + 3 * IV_REDUCE_SLICES < num_runs; r += 4 * IV_REDUCE_SLICES) {
+            a0 += double(part[size_t(r) * stride + b]);
+            a1 += double(part[size_t(r + IV_REDUCE_SLICES) * stride + b]);
+            a2 += double(part[size_t(r + 2 * IV_REDUCE_SLICES) * stride + b]);
+            a3 += double(part[size_t(r + 3 * IV_REDUCE_SLICES) * stride + b]);
+        }
+        for (; r < num_runs; r += IV_REDUCE_SLICES) a0 += double(part[size_t(r) * stride + b]);
     }
-    for (; r < num_runs; ++r) a0 += double(part[size_t(r) * stride + b]);
-    y[row] = (a0 + a1) + (a2 + a3);
+    sm[sl][e] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (sl == 0 && b < n_entries) {
+        const int row = row_of_slot[b];
+        if (row >= 0) {
+            double s = sm[0][e];
+#pragma unroll
+            for (int k = 1; k < IV_REDUCE_SLICES; ++k) s += sm[k][e];
+            y[row] = s;
+        }
+    }
 }
 
 // ---- host: is the clade matrix a laminar family, and in which cell order is every row an interval?

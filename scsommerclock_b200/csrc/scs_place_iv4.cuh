@@ -25,7 +25,7 @@
 // Shapes: one CTA of T threads per run of SNV rows, T = words of a permuted row rounded up to a warp
 // (<= 640: ~100 registers per thread), NP = ceil(pairs / T) <= 8.  Anything else (more than 10,240 cells,
 // more non-leaf rows than 16 T) keeps variant 3.  Small trees simply get small CTAs and several of
-// them per SM (1,000 cells: 64 threads), which is what makes this path the faster one below 3,968 cells too.
+// them per SM (1,000 cells: 64 threads), which is what makes this path the faster one from 100 cells on (scs_place.cu, choose_algo).
 #pragma once
 
 #include "scs_place_interval.cuh"

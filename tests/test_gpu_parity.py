@@ -197,8 +197,8 @@ def test_interval_path_matches_oracle_and_gemm(ctx, monkeypatch, n_snv, n_cells)
     bits, words = engine.pack_clades(S)
     got = {}
     for algo in ("auto", "gemm"):
-        # "auto" takes the interval path above 3968 cells (where it is faster), "interval" at any size
-        monkeypatch.setenv("SCS_PLACE_ALGO", algo if (algo == "gemm" or n_cells > 3968) else "interval")
+        # "auto" takes the interval path from 100 cells on (where it is faster), "interval" at any size
+        monkeypatch.setenv("SCS_PLACE_ALGO", algo if (algo == "gemm" or n_cells >= 100) else "interval")
         pl = engine.Placement(ctx, n_snv, n_cells, S.shape[0])
         pl.set_clades_host(bits, words)
         pl.set_genotypes_host(packed, pitch, keep)
@@ -254,8 +254,8 @@ def test_interval_path_block_shapes_and_run_lengths(ctx, monkeypatch, threads, r
 
 def test_interval_path_needs_tree_shaped_masks_and_shared_memory(ctx, monkeypatch):
     """Masks that are not a laminar family, replicate batches and trees whose working set exceeds
-    shared memory go through the GEMM; so do, by default, trees of up to 3968 cells (the GEMM is
-    faster there) unless SCS_PLACE_ALGO=interval asks for the interval path."""
+    shared memory go through the GEMM; so do, by default, trees of fewer than 100 cells (all fixed
+    cost either way) unless SCS_PLACE_ALGO=interval asks for the interval path."""
     rng = np.random.default_rng(3)
     codes, S = make_problem(50, 40, seed=1)
     bits, words = engine.pack_clades(S)
