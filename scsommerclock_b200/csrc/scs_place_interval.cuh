@@ -408,9 +408,10 @@ __global__ void scs_permute_reduce_kernel(const uint8_t* __restrict__ gt, long l
 // The same pre-pass, FOUR rows per step.  ncu on the one-row kernel (profiles/r02_ncu_iv4_first_summary.txt): ALU pipe 72 %
 // busy, ~6 instructions and one 3.4-way bank-conflicted byte load per (row, cell).  The cell order is the same for every row,
 // so the rows of a group are staged byte-interleaved -- shared-memory word b holds source byte b of rows 4g .. 4g+3 (a 4 x 4
-// byte transpose in registers, one 16-byte store per thread) -- and ONE 32-bit load then serves a cell of all four rows; a
-// code is moved into its output word with two shifts (funnel shift: the two low bits of the shifted source enter at the top,
-// sixteen steps fill the word in order, no masking).  ~2.7 instructions and a quarter of a load per (row, cell).
+// byte transpose in registers, one 16-byte store per thread) -- and ONE 32-bit load then serves a cell of all four rows.
+// Round 2: the fields are collected byte-sliced (load + rotate + LOP3 per cell quadruple, then a 4 x 4 byte transpose of four
+// accumulators) instead of four funnel shifts + three shifts per cell: ncu had counted 9 instructions per (row, cell), ALU
+// pipe 61 % busy, for a kernel that should stream.
 // Row flags of the four rows are OR-ed over the block through one shared word per group (three rotate, cleared two groups
 // ahead) in front of the group's single barrier.
 // Narrow rows (round 2): a block of `nsub` sub-blocks of `pt` threads each (pt = row words rounded up to a warp), every
@@ -432,18 +433,21 @@ __global__ void scs_permute_reduce4_kernel(const uint8_t* __restrict__ gt, long 
     const int buf_words = 4 * row_words + 4;
     uint32_t* const my_smem = pm_smem + sub * 2 * buf_words;
     uint32_t* const my_flags = s_flags + 3 * sub;
-    // per output position: source word index (= source byte of the row) | shift << 16
-    uint32_t src[16];
+    // per output position 16 t + e: byte address of the staged word that holds its source byte of the four rows, and the
+    // rotation that moves its 2-bit field from bit 2 (c % 4) of every byte lane to bit 2 (e % 4)
+    uint32_t addr[16], rot[16];
     uint32_t valid = 0u;                           // bit 2e: output position 16 t + e is a cell
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
         const int k = 16 * t + e;
         if (own && k < n_cells) {
             const uint32_t c = perm[k];
-            src[e] = (c >> 2) | ((2u * (c & 3u)) << 16);
+            addr[e] = 4u * (c >> 2);
+            rot[e] = uint32_t((2 * int(c & 3u) - 2 * (e & 3)) & 31);
             valid |= 1u << (2 * e);
         } else {
-            src[e] = uint32_t(4 * row_words);      // the all-ones word: code 3
+            addr[e] = 4u * uint32_t(4 * row_words);      // the all-ones word: code 3 whatever the rotation
+            rot[e] = 0u;
         }
     }
     const uint32_t am = own ? active_mask[t] : 0u;
@@ -469,22 +473,27 @@ __global__ void scs_permute_reduce4_kernel(const uint8_t* __restrict__ gt, long 
     __syncthreads();
     const long long n_groups = (n_snv + 3) >> 2;
     const long long gstride = (long long)gridDim.x * nsub;
-    uint32_t wn[4];
-    auto load_group = [&](long long g) {
+    // the rows of the next TWO groups are in flight while one is worked on: with one 640-thread block per SM (80 registers)
+    // a single group ahead left ~10 KB per SM in flight -- 1.4 TB/s by Little's law, which is what the kernel ran at
+    uint32_t wn[4], wn2[4];
+    auto load_group = [&](long long g, uint32_t (&w)[4]) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const long long r = 4 * g + i;
-            wn[i] = (own && r < n_snv) ? reinterpret_cast<const uint32_t*>(gt + size_t(r) * pitch)[t] : 0xFFFFFFFFu;
+            w[i] = (own && r < n_snv) ? reinterpret_cast<const uint32_t*>(gt + size_t(r) * pitch)[t] : 0xFFFFFFFFu;
         }
     };
-    load_group((long long)blockIdx.x * nsub + sub);        // (rows beyond the matrix read as missing)
+    load_group((long long)blockIdx.x * nsub + sub, wn);        // (rows beyond the matrix read as missing)
+    load_group((long long)blockIdx.x * nsub + sub + gstride, wn2);
     int buf = 0, fb = 0;
     // every sub-block makes the trips of sub-block 0 (the barrier is block wide); a trip beyond the matrix has no rows
     for (long long g0 = (long long)blockIdx.x * nsub; g0 < n_groups; g0 += gstride, buf ^= 1, fb = fb == 2 ? 0 : fb + 1) {
         const long long g = g0 + sub;
         uint32_t* rb = my_smem + buf * buf_words;
         const uint32_t w0 = wn[0], w1 = wn[1], w2 = wn[2], w3 = wn[3];
-        load_group(g + gstride);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) wn[i] = wn2[i];
+        load_group(g + 2 * gstride, wn2);
         uint32_t flags = 0u;
         if (own) {
             // 4 x 4 byte transpose: word k of the result holds byte k of the four rows
@@ -502,16 +511,20 @@ __global__ void scs_permute_reduce4_kernel(const uint8_t* __restrict__ gt, long 
         uint32_t keep4 = filter_rows ? my_flags[fb] : 0xFu;
         if (t == 0) my_flags[fb == 0 ? 2 : fb - 1] = 0u;      // the word of group g + 2 (last read one group ago, next written after the next barrier)
         if (own) {
-            uint32_t o0 = 0u, o1 = 0u, o2 = 0u, o3 = 0u;
+            // byte-sliced gather: one load serves a cell of all four rows (byte lane i = row i); a rotation puts the field
+            // at bit 2 (e % 4) of every lane (source and target offsets both lie inside the lane, what wraps around is masked
+            // off), so accumulator q collects positions 4 q .. 4 q + 3 of the four rows: load + rotate + one LOP3 per cell
+            // quadruple.  A 4 x 4 byte transpose then turns the four accumulators into the four output words.
+            uint32_t acc4[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
-                const uint32_t y = rb[src[e] & 0xFFFFu] >> (src[e] >> 16);
-                o0 = __funnelshift_r(o0, y, 2);
-                o1 = __funnelshift_r(o1, y >> 8, 2);
-                o2 = __funnelshift_r(o2, y >> 16, 2);
-                o3 = __funnelshift_r(o3, y >> 24, 2);
+                const uint32_t y = iv_lds_off(rb, addr[e]);
+                acc4[e >> 2] |= __funnelshift_r(y, y, rot[e]) & (0x03030303u << (2 * (e & 3)));
             }
-            const uint32_t ov[4] = {o0, o1, o2, o3};
+            const uint32_t l01 = __byte_perm(acc4[0], acc4[1], 0x5140), h01 = __byte_perm(acc4[0], acc4[1], 0x7362);
+            const uint32_t l23 = __byte_perm(acc4[2], acc4[3], 0x5140), h23 = __byte_perm(acc4[2], acc4[3], 0x7362);
+            const uint32_t ov[4] = {__byte_perm(l01, l23, 0x5410), __byte_perm(l01, l23, 0x7632), __byte_perm(h01, h23, 0x5410),
+                                    __byte_perm(h01, h23, 0x7632)};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const long long r = 4 * g + i;

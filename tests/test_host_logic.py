@@ -74,7 +74,13 @@ def test_set_outgroup_and_delete_child_order():
 
 
 @pytest.mark.parametrize("name", CASES)
-def test_read_tree_and_clade_bits_match_golden(name):
+def test_read_tree_and_clade_bits_match_golden_recorded_on_the_ete3_stand_in(name):
+    """read_tree + the clade rows against the fixtures.  What this pins and what it does not: the fixtures were recorded by the
+    unmodified reference's read_tree (:210-334) running on scsommerclock_b200/tree.py, the restatement of the ete3 3.1.x
+    TreeNode methods it calls (ete3 is not installable here) -- so the reference's renames, regexes, outgroup handling, leaf
+    pruning and S construction are pinned to the reference's code, the tree surgery underneath (set_outgroup, delete,
+    traversal order) to that restatement, whose ete3 semantics are checked by hand-derived cases in
+    test_newick_formats_and_errors / test_set_outgroup_and_delete_child_order, not by ete3 binaries."""
     g = load(name)
     vcf, tree_file, meta = case_inputs(g)
     tree, outg, FP, FN = P.read_tree(tree_file, g["samples"])
