@@ -56,7 +56,7 @@ int upload_pinned(void* d_dst, const void* h_pinned, size_t bytes, cudaStream_t 
 int upload_small(scs_ctx* ctx, void* d_dst, const void* h_src, size_t bytes, cudaStream_t st) {
     if (bytes == 0) return SCS_OK;
     scs_ctx::PinnedSlot& s = ctx->pin[ctx->pin_next];
-    ctx->pin_next = (ctx->pin_next + 1) % 8;
+    ctx->pin_next = (ctx->pin_next + 1) % 32;
     if (s.ev) SCS_CUDA(cudaEventSynchronize(s.ev));        // the slot's previous upload has been read
     if (bytes > s.bytes) {
         if (s.ptr) cudaFreeHost(s.ptr);

@@ -23,7 +23,7 @@ struct scs_ctx {
         size_t bytes = 0;
         cudaEvent_t ev = nullptr;
     };
-    PinnedSlot pin[8];
+    PinnedSlot pin[32];
     int pin_next = 0;
 };
 
