@@ -497,6 +497,11 @@ def map_mutations_gt(tree, muts_in, FP, FN):
     """run_PT_test.py:386-448 for callers that drive the steps themselves: places
     every SNV of ``muts_in`` (a GenotypeMatrix) on ``tree`` and sets
     ``node.mut_no_soft`` / ``node.dist``."""
+    if not np.isscalar(FN) or not np.isscalar(FP):
+        # the reference also accepts a pd.Series of per-cell FN rates (:413-418); nothing on its command-line path passes
+        # one (get_gt_tree always hands over a float), and with per-cell weights the counts C1 / C0 no longer determine the
+        # logits, i.e. it is a different kernel.  Not built -- said loudly instead of averaging the rates behind the caller's back.
+        raise NotImplementedError("per-cell FN / FP rates (the pd.Series branch of run_PT_test.py:413-418) are not supported; pass floats")
     st = _place_on_tree(muts_in.ctx, muts_in, tree, "healthycell", FP, FN)
     _apply_placement(tree, st)
     return PlacementResult(st["n_muts"], [n.name for n in tree.iter_descendants()] + ["FP"], st["soft"])
