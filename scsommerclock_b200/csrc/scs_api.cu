@@ -59,10 +59,13 @@ int upload_small(scs_ctx* ctx, void* d_dst, const void* h_src, size_t bytes, cud
     ctx->pin_next = (ctx->pin_next + 1) % 32;
     if (s.ev) SCS_CUDA(cudaEventSynchronize(s.ev));        // the slot's previous upload has been read
     if (bytes > s.bytes) {
+        // cudaHostAlloc / cudaFreeHost synchronise the whole device (measured: a slot that had to grow while another
+        // stream's matrix copies were in flight stalled the enqueueing thread for 4 ms), so a slot starts at 256 KB --
+        // larger than any upload of per-group constants seen so far -- and one that must grow anyway is grown once
         if (s.ptr) cudaFreeHost(s.ptr);
         s.ptr = nullptr;
         s.bytes = 0;
-        const size_t want = (bytes + 4095) / 4096 * 4096;
+        const size_t want = std::max<size_t>(size_t(256) << 10, (bytes + 65535) / 65536 * 65536);
         if (cudaHostAlloc(&s.ptr, want, cudaHostAllocDefault) != cudaSuccess) return set_error(SCS_ERR_OOM, "page-locked staging allocation of %zu bytes failed", want);
         s.bytes = want;
     }

@@ -1970,7 +1970,7 @@ int scs_placement_set_trees(scs_placement* h, const uint32_t* d_bits, int64_t pi
         pl->iv5_ntasks = int(tasks.size());
         pl->iv5_grid = int(std::min<int64_t>(int64_t(tasks.size()), int64_t(pl->ctx->sm_count) * IV5_MIN_CTAS));
     }
-    const size_t smem = (size_t(4) * pl->n_rows + 2) * sizeof(int);
+    const size_t smem = (size_t(7) * pl->n_rows + 2) * sizeof(int);
     if (smem > 48 * 1024) cudaFuncSetAttribute(scs_iv5_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     scs_iv5_tables_kernel<<<G, 64, smem, st>>>(d_bits, pitch_words, d_children, d_info, pl->n_rows, pl->n_cells, pl->iv5_L, pl->iv5_perm,
                                                 pl->iv5_lohi, pl->iv5_row_slot, pl->iv5_meta);

@@ -66,13 +66,26 @@ __global__ void scs_iv5_tables_kernel(const uint32_t* __restrict__ bits, long lo
     int* hi = lo + n_rows;
     int* stack = hi + n_rows;
     int* is_child = stack + n_rows + 2;
+    int* ch = is_child + n_rows;               // [2 n_rows] the child table
+    int* leafcol = ch + 2 * n_rows;            // [n_rows] column of a leaf row (-1: its mask is not a single cell)
     __shared__ int s_status, s_leaves, s_internal;
     const int nodes = min(max(info[g * 4 + 0], 0), n_rows);
-    const int* ch = children + size_t(g) * n_rows * 2;
     const int NSL = IV5_MAX_NS * L, NPOS = 16 * L;
+    // everything thread 0's walk touches is staged in shared memory first (the walk is one chain of dependent loads)
+    for (int i = t; i < 2 * n_rows; i += blockDim.x) ch[i] = children[size_t(g) * n_rows * 2 + i];
     for (int r = t; r < n_rows; r += blockDim.x) {
         is_child[r] = 0;
         lo[r] = hi[r] = 0;
+        int col = -1, cnt = 0;
+        if (r < nodes)
+            for (int wd = 0; wd < (n_cols + 31) / 32; ++wd) {
+                const uint32_t b = bits[(size_t(g) * n_rows + r) * pitch_words + wd];
+                if (b) {
+                    cnt += __popc(b);
+                    col = wd * 32 + __ffs(b) - 1;
+                }
+            }
+        leafcol[r] = (cnt == 1 && col < n_cols) ? col : -1;
     }
     for (int p = t; p < NPOS; p += blockDim.x) perm[size_t(g) * NPOS + p] = 0xFFFFu;
     for (int j = t; j < NSL; j += blockDim.x) nl_lohi[size_t(g) * NSL + j] = 0u;
@@ -104,15 +117,8 @@ __global__ void scs_iv5_tables_kernel(const uint32_t* __restrict__ bits, long lo
                     lo[row] = next;
                     if (c0 < 0 && c1 < 0) {
                         // a leaf: its column is the single bit of its mask
-                        int col = -1, cnt = 0;
-                        for (int wd = 0; wd < (n_cols + 31) / 32; ++wd) {
-                            const uint32_t b = bits[(size_t(g) * n_rows + row) * pitch_words + wd];
-                            if (b) {
-                                cnt += __popc(b);
-                                col = wd * 32 + __ffs(b) - 1;
-                            }
-                        }
-                        if (cnt != 1 || col >= n_cols || next >= NPOS) {
+                        const int col = leafcol[row];
+                        if (col < 0 || next >= NPOS) {
                             status = 1;
                         } else {
                             perm[size_t(g) * NPOS + next] = uint16_t(col);

@@ -123,11 +123,18 @@ scs_sweep_branch_order_kernel(const int* __restrict__ children, int n_rows, cons
                               double* __restrict__ d_w, int* __restrict__ scratch /*[groups][3 n_rows]*/, int* __restrict__ status) {
     const int g = blockIdx.x, t = threadIdx.x;
     const int n_nodes = info[4 * g], n_leaves = info[4 * g + 1];
-    const int* ch = children + size_t(g) * n_rows * 2;
-    const double* y = soft + size_t(g) * n_rows;
-    int* stack = scratch + size_t(g) * 3 * n_rows;      // [n_rows] node stack, [n_rows] post-order index of internal nodes,
-    int* int_index = stack + n_rows;                   // [n_rows] branch order (node rows)
+    // the child table, the soft weights and the walk's work arrays live in shared memory: thread 0's walk is a chain of
+    // dependent loads, ~100 us per launch from global memory (L2 latency per step) whatever the number of groups
+    extern __shared__ double bo_dyn[];
+    double* y = bo_dyn;                                        // [n_rows]
+    int* ch = reinterpret_cast<int*>(y + n_rows);              // [2 n_rows]
+    int* stack = ch + 2 * n_rows;                              // [n_rows] node stack, [n_rows] post-order index of internal nodes,
+    int* int_index = stack + n_rows;                           // [n_rows] branch order (node rows)
     int* order = int_index + n_rows;
+    for (int i = t; i < n_rows; i += blockDim.x) y[i] = soft[size_t(g) * n_rows + i];
+    for (int i = t; i < 2 * n_rows; i += blockDim.x) ch[i] = children[size_t(g) * n_rows * 2 + i];
+    (void)scratch;
+    __syncthreads();
     __shared__ int s_ok;
     if (t == 0) {
         int ok = (2 * (n_leaves - 1) == n_br && n_nodes == 2 * n_leaves - 1) ? 1 : 0;
@@ -280,8 +287,10 @@ int scs_sweep_model(scs_ctx* ctx, int32_t n_groups, int32_t n_rows, int32_t n_ce
     scs_sweep_weights_kernel<<<n_groups, SW_THREADS, smem, st>>>(d_bits, pitch_words, n_rows, n_cells, d_info,
                                                                   reinterpret_cast<const unsigned long long*>(d_n_kept), d_missing, d_consts,
                                                                   d_consts + n_groups, d_consts + 2 * size_t(n_groups), n_w, d_wn, d_status);
-    scs_sweep_branch_order_kernel<<<n_groups, 64, 0, st>>>(d_children, n_rows, d_info, d_soft, d_wn, n_w, n_br, d_child, d_gather, d_w, d_scratch,
-                                                           d_status);
+    const size_t bo_smem = size_t(n_rows) * (sizeof(double) + 5 * sizeof(int));
+    if (bo_smem > 48 * 1024) cudaFuncSetAttribute(scs_sweep_branch_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bo_smem));
+    scs_sweep_branch_order_kernel<<<n_groups, 64, bo_smem, st>>>(d_children, n_rows, d_info, d_soft, d_wn, n_w, n_br, d_child, d_gather, d_w, d_scratch,
+                                                                 d_status);
     SCS_CUDA(cudaGetLastError());
     return SCS_OK;
 }

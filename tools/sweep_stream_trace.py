@@ -41,6 +41,7 @@ for k, a, b in pipe.trace_events:
     print("  device: sub %d kernels %.2f -> %.2f ms" % (k, pipe.trace_t0.elapsed_time(a), pipe.trace_t0.elapsed_time(b)))
 for k, sub in enumerate(pipe.subs):
     print("  device stages sub %d:" % k, ", ".join("%s %.2f" % (w, pipe.trace_t0.elapsed_time(e)) for w, e in sub.marks))
+print("  per-sub placement kernel times (pre, -, kernel, reduce):", [[round(v, 3) for v in sub.place.last_times()] for sub in pipe.subs])
 for what, k, t in pipe.trace:
     print("  %6.2f ms  %s %d" % (t, what, k))
 t0 = time.perf_counter(); pipe.subs[0].parse_trees(newicks[:pipe.cuts[1]]); print("parse of one sub-batch alone: %.2f ms" % (1e3 * (time.perf_counter() - t0)))
