@@ -17,6 +17,7 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <initializer_list>
 #include <unordered_map>
 #include <vector>
 
@@ -25,10 +26,67 @@
 namespace scs {
 namespace {
 
+// children of a node: four inline slots (a binary tree never needs more than the three a node holds for a moment while one
+// of its children is being deleted), a heap vector beyond that (multifurcating input) -- 200 nodes no longer cost 200 allocations
+struct ChildList {
+    int inl[4];
+    int n = 0;
+    std::vector<int>* big = nullptr;
+    ChildList() = default;
+    ChildList(const ChildList& o) : n(o.n), big(o.big ? new std::vector<int>(*o.big) : nullptr) { memcpy(inl, o.inl, sizeof(inl)); }
+    ChildList(ChildList&& o) noexcept : n(o.n), big(o.big) {
+        memcpy(inl, o.inl, sizeof(inl));
+        o.big = nullptr;
+        o.n = 0;
+    }
+    ChildList& operator=(const ChildList& o) {
+        if (this != &o) {
+            delete big;
+            n = o.n;
+            big = o.big ? new std::vector<int>(*o.big) : nullptr;
+            memcpy(inl, o.inl, sizeof(inl));
+        }
+        return *this;
+    }
+    ChildList& operator=(std::initializer_list<int> l) {
+        clear();
+        for (int v : l) push_back(v);
+        return *this;
+    }
+    ~ChildList() { delete big; }
+    int* begin() { return big ? big->data() : inl; }
+    int* end() { return begin() + n; }
+    const int* begin() const { return big ? big->data() : inl; }
+    const int* end() const { return begin() + n; }
+    size_t size() const { return size_t(n); }
+    bool empty() const { return n == 0; }
+    int operator[](size_t i) const { return begin()[i]; }
+    void push_back(int v) {
+        if (!big && n == 4) big = new std::vector<int>(inl, inl + 4);
+        if (big) big->push_back(v);
+        else inl[n] = v;
+        ++n;
+    }
+    void clear() {
+        delete big;
+        big = nullptr;
+        n = 0;
+    }
+    void erase(int* it) {
+        if (big) {
+            big->erase(big->begin() + (it - big->data()));
+        } else {
+            for (int* p = it; p + 1 < inl + n; ++p) *p = p[1];
+        }
+        --n;
+    }
+};
+
 struct TNode {
     int up = -1;
-    std::vector<int> ch;
+    ChildList ch;
     int name_lo = 0, name_len = 0;      // leaf / internal label (without the distance) inside the cleaned text
+    int col = -1;                       // a leaf's sample column once it has been looked up
 };
 
 struct TreeBuilder {
@@ -54,7 +112,7 @@ struct TreeBuilder {
     void del(int node, bool prevent_nondicotomic) {
         const int parent = nd[node].up;
         if (parent >= 0) {
-            const std::vector<int> kids = nd[node].ch;
+            const ChildList kids = nd[node].ch;
             for (int c : kids) add_child(parent, c);
             nd[node].ch.clear();
             remove_child(parent, node);
@@ -170,6 +228,7 @@ std::string clean_text(const char* s, size_t n, bool strip_tags) {
         t.swap(o);
     }
     // the parser's own clean-up (tree.py:_parse_newick): line breaks and tabs are dropped
+    if (!memchr(t.data(), '\n', t.size()) && !memchr(t.data(), '\r', t.size()) && !memchr(t.data(), '\t', t.size())) return t;
     std::string o;
     o.reserve(t.size());
     for (char c : t)
@@ -190,6 +249,7 @@ bool parse_newick(TreeBuilder& B) {
         B.err = "Parentheses do not match. Broken tree structure?";
         return false;
     }
+    B.nd.reserve(size_t(2 * std::count(t.begin(), t.end(), ',') + 8));      // (a binary tree has 2 leaves - 1 nodes; + the connector of set_outgroup)
     const int root = B.new_node();
     if (t[0] != '(') {                                  // a single node
         if (!split_label(t, 0, n - 1, &B.nd[root].name_lo, &B.nd[root].name_len)) {
@@ -284,7 +344,7 @@ void set_outgroup(TreeBuilder& B, int root, int outgroup) {
     int connector;
     if (nd[root].ch.size() != 1) {
         connector = B.new_node();
-        const std::vector<int> kids = B.nd[root].ch;
+        const ChildList kids = B.nd[root].ch;
         for (int c : kids) {
             B.nd[connector].ch.push_back(c);
             B.nd[c].up = connector;
@@ -322,8 +382,44 @@ void set_outgroup(TreeBuilder& B, int root, int outgroup) {
     B.nd[root].ch = {outgroup, outgroup2};
 }
 
+// sample name -> column: open addressing over FNV-1a of the name, no allocation per lookup (a leaf name used to cost a
+// std::string and an unordered_map probe, twice)
 struct SampleIndex {
-    std::unordered_map<std::string, int> col;
+    std::vector<int> slot;          // column or -1
+    const char* names = nullptr;
+    const int64_t* off = nullptr;
+    uint32_t mask = 0;
+    static uint32_t hash(const char* s, size_t n) {
+        uint32_t h = 2166136261u;
+        for (size_t i = 0; i < n; ++i) h = (h ^ uint8_t(s[i])) * 16777619u;
+        return h;
+    }
+    void build(const char* sample_names, const int64_t* name_off, int n) {
+        names = sample_names;
+        off = name_off;
+        uint32_t cap = 16;
+        while (cap < uint32_t(4 * n)) cap <<= 1;
+        mask = cap - 1;
+        slot.assign(cap, -1);
+        for (int c = 0; c < n; ++c) {
+            uint32_t h = hash(names + off[c], size_t(off[c + 1] - off[c])) & mask;
+            while (slot[h] >= 0) {
+                const int o = slot[h];          // (a duplicated sample name keeps its first column, like dict insertion would not -- VCF samples are unique)
+                if (off[o + 1] - off[o] == off[c + 1] - off[c] && memcmp(names + off[o], names + off[c], size_t(off[c + 1] - off[c])) == 0) break;
+                h = (h + 1) & mask;
+            }
+            if (slot[h] < 0) slot[h] = c;
+        }
+    }
+    int find(const char* s, size_t n) const {
+        uint32_t h = hash(s, n) & mask;
+        while (slot[h] >= 0) {
+            const int o = slot[h];
+            if (size_t(off[o + 1] - off[o]) == n && memcmp(names + off[o], s, n) == 0) return o;
+            h = (h + 1) & mask;
+        }
+        return -1;
+    }
 };
 
 // One tree: everything read_tree and the S rows need.  Returns false with B.err set on failure.
@@ -361,11 +457,11 @@ bool process_tree(const char* s, size_t n, bool strip_tags, const SampleIndex& s
             const int v = stack.back();
             stack.pop_back();
             if (B.nd[v].ch.empty()) leaves.push_back(v);
-            for (auto it = B.nd[v].ch.rbegin(); it != B.nd[v].ch.rend(); ++it) stack.push_back(*it);
+            for (const int* it = B.nd[v].ch.end(); it != B.nd[v].ch.begin();) stack.push_back(*--it);
         }
         for (int v : leaves) {
-            const std::string name(B.text.data() + B.nd[v].name_lo, size_t(B.nd[v].name_len));
-            if (samples.col.find(name) == samples.col.end()) B.del(v, true);
+            B.nd[v].col = samples.find(B.text.data() + B.nd[v].name_lo, size_t(B.nd[v].name_len));
+            if (B.nd[v].col < 0) B.del(v, true);
         }
     }
     // tree.iter_descendants(): level order below the root
@@ -392,13 +488,12 @@ bool process_tree(const char* s, size_t n, bool strip_tags, const SampleIndex& s
         const TNode& v = B.nd[size_t(order[i])];
         uint32_t* row = bits + size_t(i) * pitch_words;
         if (v.ch.empty()) {
-            const std::string name(B.text.data() + v.name_lo, size_t(v.name_len));
-            const auto it = samples.col.find(name);
-            if (it == samples.col.end()) {
-                *err = "leaf " + name + " is not a VCF sample";
+            const int col = v.col >= 0 ? v.col : samples.find(B.text.data() + v.name_lo, size_t(v.name_len));
+            if (col < 0) {
+                *err = "leaf " + std::string(B.text.data() + v.name_lo, size_t(v.name_len)) + " is not a VCF sample";
                 return false;
             }
-            row[it->second >> 5] |= 1u << (it->second & 31);
+            row[col >> 5] |= 1u << (col & 31);
         } else {
             if (v.ch.size() != 2) {
                 *err = "the PT test needs a binary tree";
@@ -432,7 +527,7 @@ int scs_tree_parse_batch(int32_t n_trees, const char* text, const int64_t* text_
     if (n_trees <= 0 || n_samples <= 0 || n_rows <= 0 || pitch_words < (n_samples + 31) / 32)
         return set_error(SCS_ERR_ARG, "bad shape (trees=%d samples=%d rows=%d pitch=%lld)", n_trees, n_samples, n_rows, (long long)pitch_words);
     SampleIndex samples;
-    for (int c = 0; c < n_samples; ++c) samples.col.emplace(std::string(sample_names + name_off[c], size_t(name_off[c + 1] - name_off[c])), c);
+    samples.build(sample_names, name_off, n_samples);
     const std::string outg(outgroup);
     int nt = threads > 0 ? threads : int(std::max(1u, std::min(16u, std::thread::hardware_concurrency())));
     nt = std::max(1, std::min(nt, n_trees));
