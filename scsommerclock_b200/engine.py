@@ -665,6 +665,16 @@ class ReplicateSweep:
         return format_pt_rows(out, n_kept, self.FN, self.FP)
 
 
+def sub_batch_cuts(n_groups, n_sub):
+    """Boundaries [0, ..., n_groups] of at most ``n_sub`` non-empty sub-batches: a short first one (the device idles until
+    its trees are parsed and its kernels enqueued) and a short last one (its result read-back and line formatting are not
+    hidden behind anything) -- weights 1, 2, 2, ..., 2, 1."""
+    n_groups, n_sub = int(n_groups), max(1, min(int(n_sub), int(n_groups)))
+    wts = np.array([1.0] + [2.0] * (n_sub - 2) + [1.0]) if n_sub >= 3 else np.ones(n_sub)
+    edges = np.concatenate([[0.0], np.cumsum(wts)]) / wts.sum()
+    return sorted(set(int(round(n_groups * e)) for e in edges))
+
+
 class ReplicateSweepStream:
     """A large sweep whose packed genotype matrices sit in (pinned) HOST memory and whose trees are Newick TEXT, through
     ``ReplicateSweep`` in ``n_sub`` sub-batches so that the three resources work at the same time:
@@ -685,12 +695,7 @@ class ReplicateSweepStream:
         self.dev = torch.device("cuda", ctx.device)
         group_snvs = np.ascontiguousarray(group_snvs, dtype=np.int64)
         G = int(group_snvs.size)
-        n_sub = max(1, min(int(n_sub), G))
-        # a short first sub-batch (the device idles until its trees are parsed and its kernels enqueued) and a short last
-        # one (its result read-back and line formatting are not hidden behind anything): weights 1, 2, 2, ..., 2, 1
-        wts = np.array([1.0] + [2.0] * (n_sub - 2) + [1.0]) if n_sub >= 3 else np.ones(n_sub)
-        edges = np.concatenate([[0.0], np.cumsum(wts)]) / wts.sum()
-        self.cuts = sorted(set(int(round(G * e)) for e in edges))
+        self.cuts = sub_batch_cuts(G, n_sub)
         n_sub = len(self.cuts) - 1
         self.row_cuts = [int(group_snvs[:c].sum()) for c in self.cuts]
         self.subs = [ReplicateSweep(ctx, group_snvs[self.cuts[k]:self.cuts[k + 1]], columns, w_maxs, outgroup=outgroup) for k in range(n_sub)]

@@ -397,3 +397,16 @@ def test_native_tsv_rows_match_python_formatting():
             else:
                 s += f"\t{LR:0>5.3f}\t{int(dof)}\t{float(p)}\tH{int(p < 0.05)}"
         assert s == rows[i]
+
+
+def test_sub_batch_cuts_cover_every_pair_once():
+    """engine.sub_batch_cuts: strictly increasing boundaries from 0 to the number of pairs, at most n_sub pieces, a short
+    first and last piece when there are at least three."""
+    for G in (1, 2, 3, 5, 17, 150, 1250):
+        for n_sub in (1, 2, 3, 4, 7, 12, 5000):
+            cuts = engine.sub_batch_cuts(G, n_sub)
+            assert cuts[0] == 0 and cuts[-1] == G and all(b > a for a, b in zip(cuts, cuts[1:]))
+            assert len(cuts) - 1 <= max(1, min(n_sub, G))
+    cuts = engine.sub_batch_cuts(1250, 4)
+    sizes = np.diff(cuts)
+    assert list(sizes) == [208, 417, 417, 208]
