@@ -2190,6 +2190,9 @@ int scs_placement_run_batch(scs_placement* h, const double* FP, const double* FN
     if (pl->algo == 0) return set_error(SCS_ERR_ARG, "scs_placement_run before scs_placement_set_clades");
     if (pl->algo == 3) {
         if (!pl->gt_perm_valid || !pl->gt_src) return set_error(SCS_ERR_ARG, "scs_placement_run before scs_placement_set_genotypes");
+        for (int g = 0; g < pl->n_groups; ++g)      // (the kernel parks its unused row slots at counts (0, 65535): needs log(FN / (1 - FP)) < 0)
+            if (!(FN[g] + FP[g] < 1.0))
+                return set_error(SCS_ERR_ARG, "group %d: FN + FP >= 1 (FP=%g FN=%g) is not supported on the small-tree path; SCS_PLACE_ALGO=gemm", g, FP[g], FN[g]);
         Iv5Params q;
         q.gt = pl->gt_src;
         q.pitch = pl->gt_pitch;

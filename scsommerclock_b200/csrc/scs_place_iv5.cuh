@@ -203,13 +203,15 @@ __global__ void __launch_bounds__(IV5_THREADS, IV5_MIN_CTAS) scs_place_iv5_kerne
         for (int e = 0; e < 16; ++e)
             if (q.perm[size_t(g) * NPOS + 16 * sl + e] == 0xFFFFu) padmask |= 3u << (2 * e);
         // this lane's internal-node rows: byte offsets of P[lo], P[hi]; row j = i L + sl
+        // A slot without a row (j >= n_int) points at two constants in front of the table, words 0 and 1 = 0 and 0xFFFF0000:
+        // its "counts" are (0, 65535), its rank value ~ -3e5 and its term exactly 0 -- no predicates in the row loop.
         uint32_t off[NS];
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
-            const uint32_t lh = q.nl_lohi[size_t(g) * NSL + i * L + sl];
-            off[i] = (4u * (3u + (lh & 0xFFFFu))) | ((4u * (3u + (lh >> 16))) << 16);
+            const int j = i * L + sl;
+            const uint32_t lh = q.nl_lohi[size_t(g) * NSL + j];
+            off[i] = j < n_int ? ((4u * (3u + (lh & 0xFFFFu))) | ((4u * (3u + (lh >> 16))) << 16)) : ((4u * 0u) | ((4u * 1u) << 16));
         }
-        const int nvalid = max(0, min(NS, (n_int - sl + L - 1) / L));      // rows j = i L + sl < n_int
         // leaf positions of this lane's word that exist
         const int npos = min(max(n_leaves - 16 * sl, 0), 16);
         const uint32_t lmask = npos >= 16 ? 0x55555555u : (0x55555555u & ((1u << (2 * npos)) - 1u));
@@ -222,6 +224,10 @@ __global__ void __launch_bounds__(IV5_THREADS, IV5_MIN_CTAS) scs_place_iv5_kerne
         if (sl == 0) {
             ptab[3] = 0u;                            // P[0] of both buffers
             ptab[NSUB * PW + 3] = 0u;
+            ptab[0] = 0u;                            // the constants of the slots without a row
+            ptab[1] = 0xFFFF0000u;
+            ptab[NSUB * PW + 0] = 0u;
+            ptab[NSUB * PW + 1] = 0xFFFF0000u;
         }
         __syncthreads();                             // gather table
         const float2 a1f2 = make_float2(gc.a1f, gc.a1f), a0f2 = make_float2(gc.a0f, gc.a0f);
@@ -300,9 +306,7 @@ __global__ void __launch_bounds__(IV5_THREADS, IV5_MIN_CTAS) scs_place_iv5_kerne
                 d[2 * i] = iv_lds_off(P, off[2 * i] >> 16) - iv_lds_off(P, off[2 * i] & 0xFFFFu);
                 d[2 * i + 1] = iv_lds_off(P, off[2 * i + 1] >> 16) - iv_lds_off(P, off[2 * i + 1] & 0xFFFFu);
                 const float2 c1 = __fadd2_rn(iv_lo16(d[2 * i], d[2 * i + 1]), n23), c0 = __fadd2_rn(iv_hi16(d[2 * i], d[2 * i + 1]), n23);
-                float2 v = __ffma2_rn(a1f2, c1, __fmul2_rn(a0f2, c0));
-                if (2 * i >= nvalid) v.x = -INFINITY;
-                if (2 * i + 1 >= nvalid) v.y = -INFINITY;
+                const float2 v = __ffma2_rn(a1f2, c1, __fmul2_rn(a0f2, c0));
                 rank[i] = v;
                 bv = fmaxf(bv, fmaxf(v.x, v.y));
             }
@@ -347,9 +351,7 @@ __global__ void __launch_bounds__(IV5_THREADS, IV5_MIN_CTAS) scs_place_iv5_kerne
                 const float2 sdiff = __ffma2_rn(a1h2, e1, __fmul2_rn(a0h2, e0));
                 const float2 lo = __ffma2_rn(a1l2, e1, __fmul2_rn(a0l2, e0));
                 const float2 x = __fadd2_rn(sdiff, lo);
-                float2 tv = make_float2(ex2_approx(x.x), ex2_approx(x.y));
-                if (2 * i >= nvalid) tv.x = 0.f;
-                if (2 * i + 1 >= nvalid) tv.y = 0.f;
+                const float2 tv = make_float2(ex2_approx(x.x), ex2_approx(x.y));      // (a slot without a row: 2^-3e5 = 0)
                 tt[i] = tv;
                 s2 = __fadd2_rn(s2, tv);
             }
