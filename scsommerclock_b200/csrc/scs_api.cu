@@ -55,21 +55,34 @@ int upload_pinned(void* d_dst, const void* h_pinned, size_t bytes, cudaStream_t 
 
 int upload_small(scs_ctx* ctx, void* d_dst, const void* h_src, size_t bytes, cudaStream_t st) {
     if (bytes == 0) return SCS_OK;
+    // cudaHostAlloc / cudaFreeHost synchronise the whole device (measured: a slot that had to grow while another stream's
+    // matrix copies were in flight stalled the enqueueing thread for 4 ms; slots allocated one by one put a 0.5 ms call into
+    // each of the first dozen steps), so ALL slots are carved out of one arena allocated on first use: 32 x 256 KB, larger
+    // than any upload of per-group constants seen so far.  An upload that does not fit gets its own allocation, once.
+    constexpr size_t SLOT = size_t(256) << 10;
+    constexpr int NSLOT = int(sizeof(ctx->pin) / sizeof(ctx->pin[0]));
+    if (!ctx->pin_arena) {
+        if (cudaHostAlloc(&ctx->pin_arena, SLOT * NSLOT, cudaHostAllocDefault) != cudaSuccess)
+            return set_error(SCS_ERR_OOM, "page-locked staging allocation of %zu bytes failed", SLOT * NSLOT);
+        for (int i = 0; i < NSLOT; ++i) {
+            ctx->pin[i].ptr = static_cast<char*>(ctx->pin_arena) + size_t(i) * SLOT;
+            ctx->pin[i].bytes = SLOT;
+            ctx->pin[i].own = false;
+            SCS_CUDA(cudaEventCreateWithFlags(&ctx->pin[i].ev, cudaEventDisableTiming));
+        }
+    }
     scs_ctx::PinnedSlot& s = ctx->pin[ctx->pin_next];
-    ctx->pin_next = (ctx->pin_next + 1) % 32;
-    if (s.ev) SCS_CUDA(cudaEventSynchronize(s.ev));        // the slot's previous upload has been read
+    ctx->pin_next = (ctx->pin_next + 1) % NSLOT;
+    SCS_CUDA(cudaEventSynchronize(s.ev));        // the slot's previous upload has been read (never recorded: returns at once)
     if (bytes > s.bytes) {
-        // cudaHostAlloc / cudaFreeHost synchronise the whole device (measured: a slot that had to grow while another
-        // stream's matrix copies were in flight stalled the enqueueing thread for 4 ms), so a slot starts at 256 KB --
-        // larger than any upload of per-group constants seen so far -- and one that must grow anyway is grown once
-        if (s.ptr) cudaFreeHost(s.ptr);
+        if (s.own) cudaFreeHost(s.ptr);
         s.ptr = nullptr;
         s.bytes = 0;
-        const size_t want = std::max<size_t>(size_t(256) << 10, (bytes + 65535) / 65536 * 65536);
+        const size_t want = (bytes + 65535) / 65536 * 65536;
         if (cudaHostAlloc(&s.ptr, want, cudaHostAllocDefault) != cudaSuccess) return set_error(SCS_ERR_OOM, "page-locked staging allocation of %zu bytes failed", want);
         s.bytes = want;
+        s.own = true;
     }
-    if (!s.ev) SCS_CUDA(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
     memcpy(s.ptr, h_src, bytes);
     const int rc = upload_pinned(d_dst, s.ptr, bytes, st);
     if (rc != SCS_OK) return rc;
@@ -116,11 +129,13 @@ int scs_ctx_create(int32_t device, scs_ctx** out) {
 
 int scs_ctx_destroy(scs_ctx* ctx) {
     if (ctx && ctx->scratch) cudaFree(ctx->scratch);
-    if (ctx)
+    if (ctx) {
         for (auto& s : ctx->pin) {
             if (s.ev) cudaEventDestroy(s.ev);
-            if (s.ptr) cudaFreeHost(s.ptr);
+            if (s.own && s.ptr) cudaFreeHost(s.ptr);
         }
+        if (ctx->pin_arena) cudaFreeHost(ctx->pin_arena);
+    }
     delete ctx;
     return SCS_OK;
 }

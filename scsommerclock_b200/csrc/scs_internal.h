@@ -22,9 +22,11 @@ struct scs_ctx {
         void* ptr = nullptr;
         size_t bytes = 0;
         cudaEvent_t ev = nullptr;
+        bool own = false;           // its own allocation (an upload larger than an arena slot)
     };
     PinnedSlot pin[32];
     int pin_next = 0;
+    void* pin_arena = nullptr;      // one page-locked allocation that holds all slots
 };
 
 namespace scs {
