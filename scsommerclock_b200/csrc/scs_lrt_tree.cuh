@@ -116,18 +116,6 @@ __device__ __forceinline__ void tree_sync(LrtTreeCtx<T>& cx) {
     else cx.cl.sync();
 }
 
-// 1/d for the moderate, strictly positive magnitudes of this solver (lengths, slacks, pivots: no denormals, infinities or
-// zeros): the hardware seed (~20 bits) and two Newton steps, ~1 ulp -- a third of the instructions of the IEEE division,
-// which is what the single SM that eliminates the top region is bound by.
-__device__ __forceinline__ double tree_rcp(double d) {
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-    double e = fma(-d, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-d, y, 1.0);
-    return fma(y, e, y);
-}
-
 // barrier gradient and curvature of one branch of length lk (scs_lrt_kernel's expressions)
 __device__ __forceinline__ void tree_branch(double lk, double wy, double wq, double U, double mu, double& g, double& d) {
     const double il = tree_rcp(lk), ia = tree_rcp(lk - LRT_LMIN), ib = tree_rcp(U - lk);
