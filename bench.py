@@ -635,7 +635,7 @@ def main():
     # ---- BASELINE configs[2]: 1,000 cells x 100k SNVs, a single PT test on one B200
     small = None
     if world == 1 and not args.no_small_leg:
-        d2 = SingleDataset(ctx, dev, rank, world, 1000, 100000, "auto", e2e=not args.no_e2e, e2e_chunks=4, tree_seed=4321, seed=2000)
+        d2 = SingleDataset(ctx, dev, rank, world, 1000, 100000, "auto", e2e=not args.no_e2e, e2e_chunks=1, tree_seed=4321, seed=2000)
         ms_2, t2, r2, l2 = timed(d2.step, 20, 5, d2.plan, dev)
         info2 = d2.plan.info()
         small = {"workload": "coalescent 1000 cells x 100000 SNVs, single PT test (10 w_max) on one GPU (BASELINE configs[2])",

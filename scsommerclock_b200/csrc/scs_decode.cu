@@ -582,7 +582,10 @@ int gt_reduce_launch(scs_ctx* ctx, const uint8_t* d_gt, int64_t pitch_bytes, int
         for (int c = 0; c < n_cells; ++c)
             if (col_active[c]) amask[c >> 4] |= 1u << (2 * (c & 15));
         SCS_CUDA(cudaMemsetAsync(sc, 0, bytes, st));
-        SCS_CUDA(cudaMemcpyAsync(d_act, amask.data(), size_t(n_words) * 4, cudaMemcpyHostToDevice, st));   // (pageable source: staged before the call returns)
+        {
+            const int urc = upload_small(ctx, d_act, amask.data(), size_t(n_words) * 4, st);      // (not the copy engine: scs_internal.h)
+            if (urc != SCS_OK) return urc;
+        }
     }
     if (n_snv > 0) {
         if (n_words <= 32) {

@@ -2110,7 +2110,10 @@ int scs_placement_prepare(scs_placement* h, const uint8_t* d_gt, int64_t pitch_b
         for (int c = 0; c < n_cells; ++c)
             if (col_active[c]) amask[size_t(c >> 4)] |= 1u << (2 * (c & 15));
         SCS_CUDA(cudaMemsetAsync(pl->d_prep, 0, need, st));
-        SCS_CUDA(cudaMemcpyAsync(pl->d_prep + off_mask, amask.data(), size_t(rw) * 4, cudaMemcpyHostToDevice, st));   // (pageable: staged before the call returns)
+        {
+            const int urc = upload_small(pl->ctx, pl->d_prep + off_mask, amask.data(), size_t(rw) * 4, st);      // (a kernel over pinned staging, not the copy engine, which may be busy with the next chunk of the matrix)
+            if (urc != SCS_OK) return urc;
+        }
     }
     const size_t bytes = size_t(pl->n_snv) * rw * sizeof(uint32_t);
     if (bytes > pl->gt_perm_bytes) {
