@@ -17,7 +17,8 @@ struct scs_ctx {
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
     // ring of page-locked staging slots for small host -> device uploads that must not queue behind big copies
-    // (scs::upload_small); each slot waits for its previous user before it is rewritten
+    // (scs::upload_small); each slot waits for its previous user before it is rewritten.  Not thread safe: a context is
+    // driven by one host thread at a time (the sweep's parser / formatter threads never touch it)
     struct PinnedSlot {
         void* ptr = nullptr;
         size_t bytes = 0;
