@@ -531,8 +531,9 @@ def timed(fn, steps, warmup, plan, dev, sampler=None, lrt_launches_per_step=1, p
     if sampler:
         sampler.stop_flag.set()
     ms = e0.elapsed_time(e1)
-    # this library's kernels inside the timed region: plan launches (pre-pass, placement, reduce / operand expansion,
-    # two GEMM passes, merge, reduce) + the LRT kernel of every step
+    # this library's kernels inside the timed region: plan launches (the small upload kernels of the active-cell mask and
+    # the error-model constants, pre-pass, placement, reduce / operand expansion, two GEMM passes, merge, reduce) + the LRT
+    # kernel of every step
     n_launch = plan.info()["launches"] - l0 + steps * lrt_launches_per_step
     return sharding.max_over_ranks(ms, dev), times, res, n_launch
 

@@ -2113,6 +2113,7 @@ int scs_placement_prepare(scs_placement* h, const uint8_t* d_gt, int64_t pitch_b
         {
             const int urc = upload_small(pl->ctx, pl->d_prep + off_mask, amask.data(), size_t(rw) * 4, st);      // (a kernel over pinned staging, not the copy engine, which may be busy with the next chunk of the matrix)
             if (urc != SCS_OK) return urc;
+            pl->launches++;
         }
     }
     const size_t bytes = size_t(pl->n_snv) * rw * sizeof(uint32_t);
@@ -2189,6 +2190,7 @@ int scs_placement_run_batch(scs_placement* h, const double* FP, const double* FN
         int rc = upload_small(pl->ctx, pl->d_gconst, gc.data(), gc.size() * sizeof(GroupConst), st);
         if (rc == SCS_OK) rc = upload_small(pl->ctx, pl->d_gconst_d, gd.data(), gd.size() * sizeof(double2), st);
         if (rc != SCS_OK) return rc;
+        pl->launches += 2;          // (the two upload kernels)
     }
     if (pl->algo == 0) return set_error(SCS_ERR_ARG, "scs_placement_run before scs_placement_set_clades");
     if (pl->algo == 3) {
