@@ -214,7 +214,9 @@ int scs_branch_weights(scs_ctx* ctx, const uint32_t* clade_bits, int64_t pitch_w
  * branch lengths.  status: 0 converged; 1 iteration limit; 2 degenerate input (the reference's scale_fac is 0 or
  * there are no counts); 3 numerical breakdown of the Newton system; 4 ll_H1 < 0 -- the reference's scale_fac is
  * negative there and its minimiser runs on a sign-flipped objective, so no meaningful value exists to reproduce.
- * Every non-zero status comes with NaN in the first five fields (the reference's failure tuple, :678). */
+ * Every non-zero status comes with NaN in the first five fields (the reference's failure tuple, :678).
+ * A problem whose solve ends with status 1 or 3 is solved a second time by path following over eight barrier parameters
+ * (the reference retries a failed trust-constr solve with SLSQP, :671-678); only what fails twice keeps its status. */
 int scs_lrt_poisson_batch(scs_ctx* ctx, int32_t n_prob, const int64_t* br_off, const double* Y, const double* w,
                           const int32_t* child_int, double* out, double* x_out);
 /* The same batch as a reusable, device-resident plan (topology and workspace are

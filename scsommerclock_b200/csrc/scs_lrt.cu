@@ -21,6 +21,7 @@
 #include <cstdio>
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -143,7 +144,7 @@ template <bool WARP>
 __global__ void __launch_bounds__(WARP ? 32 : LRT_MAX_THREADS)
 scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ Ysrc, const int* __restrict__ gather,
                double* __restrict__ Yall, const double* __restrict__ wall, const int* __restrict__ child_all, LrtWork ws,
-               double* __restrict__ out, double* __restrict__ x_out, int smem_mode, double mu_in) {
+               double* __restrict__ out, double* __restrict__ x_out, int smem_mode, double mu_in, int n_stages, int max_iter) {
     __shared__ double sh[WARP ? 2 : 2 * (LRT_MAX_THREADS / 32)];
     __shared__ int s_nlev;
     const LrtProblem pb = probs[blockIdx.x];
@@ -325,10 +326,17 @@ scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ 
         grp_sync<WARP>();
     }
 
-    const double mu = mu_in;
-    int it = 0, status = 1;
+    // n_stages == 1: the barrier problem at mu_in straight from the feasible start (fewest Newton steps).
+    // n_stages > 1 is the SECOND ATTEMPT after a failed solve (the reference retries with SLSQP, run_PT_test.py:671-678):
+    // path following -- the same Newton iteration at mu_in * 5^(n_stages - 1), ..., mu_in * 5, mu_in, each stage started
+    // from the previous stage's optimum -- slower, but it walks to the same (unique) optimum along the central path.
+    int it = 0, status = 1, it_total = 0;
     double f0 = 0.0;      // barrier objective at the current iterate (carried over from the line search)
-    for (; it < LRT_MAX_ITER; ++it) {
+    for (int stage = 0; stage < n_stages; ++stage) {
+    double mu = mu_in;
+    for (int q = stage; q < n_stages - 1; ++q) mu *= 5.0;
+    status = 1;
+    for (it = 0; it < max_iter; ++it) {
         // branch lengths, barrier gradient and curvature
         double f0p = 0.0;
         for (int k = tid; k < nb; k += LRT_THREADS) {
@@ -434,6 +442,10 @@ scs_lrt_kernel(const LrtProblem* __restrict__ probs, const double* __restrict__ 
         }
         f0 = f1;
     }
+    it_total += it;
+    if (status != 0) break;
+    }
+    it = it_total;
 
     // ---- statistic and p-value (run_PT_test.py:683-695), from the unscaled counts and weights
     double ll_H0 = 0.0, sOB = 0.0;
@@ -540,6 +552,8 @@ struct LrtPlanImpl {
     int threads = 128;
     int smem_bytes = 0;    // > 0: per-CTA working set in shared memory (small trees)
     bool warp_mode = false;   // one warp per problem (trees up to 256 leaves)
+    int n_stages = 1;          // > 1: path following over that many barrier parameters (the second attempt)
+    int max_iter = LRT_MAX_ITER;
     // cluster-per-problem kernel (scs_lrt_tree.cuh): topology renumbered in level order on the host
     bool tree_mode = false;
     int tree_cluster = 1, tree_threads = 512, tree_smem = 0;
@@ -646,7 +660,7 @@ static int lrt_tree_prepare(LrtPlanImpl* pl, int n_prob, const int64_t* br_off, 
     return SCS_OK;
 }
 
-int scs_lrt_plan_create(scs_ctx* ctx, int32_t n_prob, const int64_t* br_off, const int32_t* child_int, scs_lrt_plan** out) {
+static int lrt_plan_create_impl(scs_ctx* ctx, int32_t n_prob, const int64_t* br_off, const int32_t* child_int, scs_lrt_plan** out, bool allow_tree) {
     if (!ctx || !br_off || !child_int || !out) return set_error(SCS_ERR_ARG, "null argument");
     if (n_prob <= 0) return set_error(SCS_ERR_ARG, "empty LRT batch");
     SCS_CUDA(cudaSetDevice(ctx->device));
@@ -725,6 +739,7 @@ int scs_lrt_plan_create(scs_ctx* ctx, int32_t n_prob, const int64_t* br_off, con
     // trees too big for one warp: a thread-block cluster per problem on a level-ordered topology (scs_lrt_tree.cuh);
     // SCS_LRT_KERNEL = tree | cta | warp forces a kernel (tests play them against each other)
     pl->tree_mode = !pl->warp_mode;
+    if (const char* ev = getenv("SCS_LRT_MAX_ITER")) pl->max_iter = std::max(1, atoi(ev));      // test knob: makes the first attempt fail
     if (const char* ev = getenv("SCS_LRT_KERNEL")) {
         const std::string k(ev);
         if (k == "tree") pl->tree_mode = true, pl->warp_mode = false;
@@ -732,6 +747,10 @@ int scs_lrt_plan_create(scs_ctx* ctx, int32_t n_prob, const int64_t* br_off, con
         else if (k == "warp" && max_nb <= 1024) pl->tree_mode = false, pl->warp_mode = true;
         if (!pl->warp_mode && pl->threads == 32) pl->threads = max_nb >= 8192 ? 512 : (max_nb >= 2048 ? 256 : (max_nb > 256 ? 128 : 64));
         if (pl->warp_mode) pl->threads = 32;
+    }
+    if (!allow_tree && pl->tree_mode) {
+        pl->tree_mode = false;
+        if (pl->threads == 32 && !pl->warp_mode) pl->threads = 128;
     }
     if (pl->tree_mode) {
         const int rc = lrt_tree_prepare(pl, n_prob, br_off, child_int, probs);
@@ -742,6 +761,10 @@ int scs_lrt_plan_create(scs_ctx* ctx, int32_t n_prob, const int64_t* br_off, con
     }
     *out = reinterpret_cast<scs_lrt_plan*>(pl);
     return SCS_OK;
+}
+
+int scs_lrt_plan_create(scs_ctx* ctx, int32_t n_prob, const int64_t* br_off, const int32_t* child_int, scs_lrt_plan** out) {
+    return lrt_plan_create_impl(ctx, n_prob, br_off, child_int, out, true);
 }
 
 // A plan of n_prob problems with n_br branches each whose topologies, gather indices and weights are produced ON THE DEVICE
@@ -848,6 +871,7 @@ int scs_lrt_plan_run(scs_lrt_plan* h, const double* d_Y, double* d_out, double* 
         a.out = d_out ? d_out : pl->d_out;
         a.x_out = d_x ? d_x : pl->d_x;
         a.mu = mu;
+        a.max_iter = pl->max_iter;
         a.prof = nullptr;
         a.start_mode = 0;
         if (const char* ev = getenv("SCS_LRT_START")) a.start_mode = atoi(ev) == 1 ? 1 : 0;      // experiment knob (tools/lrt_timing.py)
@@ -893,7 +917,7 @@ int scs_lrt_plan_run(scs_lrt_plan* h, const double* d_Y, double* d_out, double* 
         }
         kern<<<pl->n_prob, pl->threads, pl->smem_bytes, st>>>(pl->d_probs, d_Y, pl->have_gather ? pl->d_gather : nullptr, pl->dY, pl->dw,
                                                               pl->d_child, pl->ws, d_out ? d_out : pl->d_out, d_x ? d_x : pl->d_x,
-                                                              pl->smem_bytes > 0, mu);
+                                                              pl->smem_bytes > 0, mu, pl->n_stages, pl->max_iter);
     };
     if (pl->warp_mode) launch(scs_lrt_kernel<true>);
     else launch(scs_lrt_kernel<false>);
@@ -932,7 +956,45 @@ int scs_lrt_poisson_batch(scs_ctx* ctx, int32_t n_prob, const int64_t* br_off, c
     rc = scs_lrt_plan_set_weights(pl, w);
     if (rc == SCS_OK) rc = scs_lrt_plan_run_host(pl, Y, out, x_out, nullptr);
     scs_lrt_plan_destroy(pl);
-    return rc;
+    if (rc != SCS_OK) return rc;
+    // ---- second attempt for the problems whose solve failed (status 1: iteration limit, 3: numerical breakdown), as the
+    // reference retries a failed trust-constr solve with SLSQP (run_PT_test.py:671-678): path following over eight barrier
+    // parameters down to the same final one (scs_lrt_kernel, n_stages = 8) -- the same unique optimum, reached along the
+    // central path.  What fails twice keeps its failure tuple (:676-678).  Degenerate inputs (status 2, 4) are not retried.
+    std::vector<int> again;
+    for (int p = 0; p < n_prob; ++p)
+        if (out[size_t(p) * 8 + 7] == 1.0 || out[size_t(p) * 8 + 7] == 3.0) again.push_back(p);
+    if (again.empty() || getenv("SCS_LRT_NO_RETRY")) return SCS_OK;
+    std::vector<int64_t> off2(again.size() + 1, 0);
+    for (size_t k = 0; k < again.size(); ++k) off2[k + 1] = off2[k] + (br_off[again[k] + 1] - br_off[again[k]]);
+    std::vector<double> Y2(size_t(off2.back())), w2(size_t(off2.back())), out2(again.size() * 8), x2(size_t(off2.back()));
+    std::vector<int32_t> ch2(size_t(off2.back()));
+    for (size_t k = 0; k < again.size(); ++k) {
+        const int64_t a = br_off[again[k]], n = br_off[again[k] + 1] - a;
+        memcpy(Y2.data() + off2[k], Y + a, size_t(n) * sizeof(double));
+        memcpy(w2.data() + off2[k], w + a, size_t(n) * sizeof(double));
+        memcpy(ch2.data() + off2[k], child_int + a, size_t(n) * sizeof(int32_t));
+    }
+    scs_lrt_plan* pl2 = nullptr;
+    rc = lrt_plan_create_impl(ctx, int(again.size()), off2.data(), ch2.data(), &pl2, false);
+    if (rc != SCS_OK) return rc;
+    {
+        LrtPlanImpl* q = reinterpret_cast<LrtPlanImpl*>(pl2);
+        q->n_stages = 8;
+        q->max_iter = LRT_MAX_ITER;
+    }
+    rc = scs_lrt_plan_set_weights(pl2, w2.data());
+    if (rc == SCS_OK) rc = scs_lrt_plan_run_host(pl2, Y2.data(), out2.data(), x2.data(), nullptr);
+    scs_lrt_plan_destroy(pl2);
+    if (rc != SCS_OK) return rc;
+    for (size_t k = 0; k < again.size(); ++k) {
+        if (out2[k * 8 + 7] != 0.0) continue;               // failed twice: the failure tuple stays
+        const double first_its = out[size_t(again[k]) * 8 + 6];
+        memcpy(out + size_t(again[k]) * 8, out2.data() + k * 8, 8 * sizeof(double));
+        out[size_t(again[k]) * 8 + 6] += std::isfinite(first_its) ? first_its : 0.0;      // Newton iterations of both attempts
+        if (x_out) memcpy(x_out + br_off[again[k]], x2.data() + off2[k], size_t(off2[k + 1] - off2[k]) * sizeof(double));
+    }
+    return SCS_OK;
 }
 
 int scs_branch_weights(scs_ctx* ctx, const uint32_t* clade_bits, int64_t pitch_words, int32_t n_nodes, int32_t n_cells,

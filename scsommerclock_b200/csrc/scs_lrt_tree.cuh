@@ -58,6 +58,7 @@ struct LrtTreeArgs {
     double* out;
     double* x_out;
     double mu;
+    int max_iter;
     int start_mode;          // 0: max-based feasible start (scs_lrt_kernel's), 1: mean-based
     long long* prof;         // tools only (SCS_LRT_PROF): per-phase clock cycles of problem 0's leader, thread 0; nullptr otherwise
 };
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(T, 1) scs_lrt_tree_kernel(LrtTreeArgs A) {
     double f0 = 0.0;
     long long* prof = (A.prof && p == 0 && rank == 0 && tid == 0) ? A.prof : nullptr;
     long long t_mark = prof ? clock64() : 0;
-    for (; it < LRT_MAX_ITER; ++it) {
+    for (; it < A.max_iter; ++it) {
         // ---- per node: lengths of its two child branches and of its up branch, barrier gradient / curvature, the node's
         // row of the Newton system.  Nodes below the cut publish their Schur contribution to the parent's row in the
         // per-branch slots cD / cR (level 0 right here, the other levels when their own row is final).  NB nodes per

@@ -662,6 +662,8 @@ def get_LRT_poisson_batch(problems, ctx=None):
         LR, dof, on_bound, p_val, ll_H0, ll_H1, iters, status = out[i]
         if status != 0 or not np.isfinite(LR):
             print("\nFAILED POISSON OPTIMIZATION\n")
+            if status in (1, 3):          # (the library has already made its second attempt, scs_lrt_poisson_batch: :671-678)
+                print("\nFAILED POISSON OPTIMIZATION, TWICE\n")
             results.append((np.nan, np.nan, np.nan, np.nan, np.nan, np.nan))
             continue
         x = xs[i]
@@ -783,6 +785,9 @@ def run_poisson_tree_test_batch(vcf_files, tree_files, out_files, w_maxs, exclud
         for k, p in enumerate(grp):
             if status[k] != 0:
                 slow.append(p)                    # e.g. a tree that lacks some of the VCF's cells
+                continue
+            if np.isin(out[k, :, 7], (1, 3)).any():
+                slow.append(p)                    # a failed solve: the per-pair path makes the second attempt (:671-678)
                 continue
             if (out[k, :, 7] != 0).any():
                 print("\nFAILED POISSON OPTIMIZATION\n")

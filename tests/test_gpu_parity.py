@@ -1189,6 +1189,40 @@ def test_lrt_tree_kernel_on_big_trees(ctx, monkeypatch, n_leaves, n_prob):
     _assert_same_lrt(out, d_out.cpu().numpy())
 
 
+def test_lrt_second_attempt_after_a_failed_solve(ctx, monkeypatch):
+    """run_PT_test.py:671-678 retries a failed trust-constr solve with SLSQP and returns the failure tuple only when both
+    fail.  Here: scs_lrt_poisson_batch re-solves the problems whose first attempt ended with status 1 / 3 by path following
+    over eight barrier parameters.  The first attempt is made to fail (SCS_LRT_MAX_ITER=2 Newton steps): without the retry
+    every problem reports status 1, with it every problem comes back converged at the answer of an undisturbed run --
+    small trees (warp kernel first) and big ones (cluster kernel first)."""
+    g = load("lrt_sweep")
+    off = g["off"]
+    n = len(off) - 1
+    keep = [i for i in range(n) if g["ll_H1"][i] >= 0][:120]
+    Ys = [g["Y"][off[i]:off[i + 1]] for i in keep]
+    ws = [g["w"][off[i]:off[i + 1]] for i in keep]
+    chs = [g["child_int"][off[i]:off[i + 1]] for i in keep]
+    big = [_synthetic_lrt_problem(1500, 4242 + i, sparse=(i == 1)) for i in range(2)]
+    Ys += [p[0] for p in big]
+    ws += [p[1] for p in big]
+    chs += [p[2] for p in big]
+    base, xb = engine.lrt_poisson_batch(ctx, Ys, ws, chs, want_x=True)
+    assert (base[:, 7] == 0).all()
+    monkeypatch.setenv("SCS_LRT_MAX_ITER", "2")
+    monkeypatch.setenv("SCS_LRT_NO_RETRY", "1")
+    first, _ = engine.lrt_poisson_batch(ctx, Ys, ws, chs, want_x=False)
+    assert (first[:, 7] == 1).all()                                  # the first attempt alone: iteration limit everywhere
+    monkeypatch.delenv("SCS_LRT_NO_RETRY")
+    again, xa = engine.lrt_poisson_batch(ctx, Ys, ws, chs, want_x=True)
+    assert (again[:, 7] == 0).all()
+    assert (again[:, 6] > base[:, 6]).all()                          # it took the long way round
+    assert np.array_equal(again[:, 1], base[:, 1]) and np.array_equal(again[:, 2], base[:, 2])      # dof, on_bound
+    np.testing.assert_allclose(again[:, 0], base[:, 0], rtol=1e-7, atol=1e-7)
+    np.testing.assert_allclose(again[:, 3], base[:, 3], rtol=1e-5, atol=1e-300)
+    for a, b in zip(xa, xb):
+        np.testing.assert_allclose(a, b, rtol=1e-4, atol=1e-9)
+
+
 # ------------------------------------------------- the product path under an initialised process group
 def _free_port():
     import socket
