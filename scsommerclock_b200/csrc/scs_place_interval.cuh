@@ -474,26 +474,38 @@ __global__ void scs_permute_reduce4_kernel(const uint8_t* __restrict__ gt, long 
     const long long n_groups = (n_snv + 3) >> 2;
     const long long gstride = (long long)gridDim.x * nsub;
     // the rows of the next TWO groups are in flight while one is worked on: with one 640-thread block per SM (80 registers)
-    // a single group ahead left ~10 KB per SM in flight -- 1.4 TB/s by Little's law, which is what the kernel ran at
+    // a single group ahead left ~10 KB per SM in flight -- 1.4 TB/s by Little's law, which is what the kernel ran at.
+    // Addresses are walked, not recomputed (one 64-bit add per group instead of a 64-bit multiply per row), and rows beyond
+    // the matrix are handled by a row count per group instead of a 64-bit comparison per row.
+    const long long pitch_w = pitch >> 2;                      // (the ABI asks for 4-byte aligned rows)
     uint32_t wn[4], wn2[4];
-    auto load_group = [&](long long g, uint32_t (&w)[4]) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const long long r = 4 * g + i;
-            w[i] = (own && r < n_snv) ? reinterpret_cast<const uint32_t*>(gt + size_t(r) * pitch)[t] : 0xFFFFFFFFu;
-        }
+    auto rows_of = [&](long long g) -> int {                   // valid rows of group g: 4, or fewer at the end, or none
+        const long long left = n_snv - 4 * g;
+        return left >= 4 ? 4 : (left > 0 ? int(left) : 0);
     };
-    load_group((long long)blockIdx.x * nsub + sub, wn);        // (rows beyond the matrix read as missing)
-    load_group((long long)blockIdx.x * nsub + sub + gstride, wn2);
+    auto load_group = [&](const uint32_t* p, int nv, uint32_t (&w)[4]) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[i] = (own && i < nv) ? p[size_t(i) * pitch_w] : 0xFFFFFFFFu;      // (rows beyond the matrix read as missing)
+    };
+    const long long gfirst = (long long)blockIdx.x * nsub + sub;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(gt) + gfirst * 4 * pitch_w + t;
+    const long long src_step = gstride * 4 * pitch_w;
+    uint32_t* dst = out + gfirst * 4 * row_words + t;
+    const long long dst_step = gstride * 4 * row_words;
+    load_group(src, rows_of(gfirst), wn);
+    load_group(src + src_step, rows_of(gfirst + gstride), wn2);
+    src += 2 * src_step;                                       // -> the group two trips ahead
     int buf = 0, fb = 0;
     // every sub-block makes the trips of sub-block 0 (the barrier is block wide); a trip beyond the matrix has no rows
     for (long long g0 = (long long)blockIdx.x * nsub; g0 < n_groups; g0 += gstride, buf ^= 1, fb = fb == 2 ? 0 : fb + 1) {
         const long long g = g0 + sub;
+        const int nv = rows_of(g);
         uint32_t* rb = my_smem + buf * buf_words;
         const uint32_t w0 = wn[0], w1 = wn[1], w2 = wn[2], w3 = wn[3];
 #pragma unroll
         for (int i = 0; i < 4; ++i) wn[i] = wn2[i];
-        load_group(g + 2 * gstride, wn2);
+        load_group(src, rows_of(g + 2 * gstride), wn2);
+        src += src_step;
         uint32_t flags = 0u;
         if (own) {
             // 4 x 4 byte transpose: word k of the result holds byte k of the four rows
@@ -501,14 +513,15 @@ __global__ void scs_permute_reduce4_kernel(const uint8_t* __restrict__ gt, long 
             const uint32_t l23 = __byte_perm(w2, w3, 0x5140), h23 = __byte_perm(w2, w3, 0x7362);
             reinterpret_cast<uint4*>(rb)[t] = make_uint4(__byte_perm(l01, l23, 0x5410), __byte_perm(l01, l23, 0x7632),
                                                          __byte_perm(h01, h23, 0x5410), __byte_perm(h01, h23, 0x7632));
-            // a cell holds 1 or 2 exactly when its two bits differ (the mask keeps the low bit of the active cells only)
+            // a cell holds 1 or 2 exactly when its two bits differ (the mask keeps the low bit of the active cells only;
+            // a row beyond the matrix is all ones: no such cell)
             flags = ((((w0 ^ (w0 >> 1)) & am) != 0u) ? 1u : 0u) | ((((w1 ^ (w1 >> 1)) & am) != 0u) ? 2u : 0u) |
                     ((((w2 ^ (w2 >> 1)) & am) != 0u) ? 4u : 0u) | ((((w3 ^ (w3 >> 1)) & am) != 0u) ? 8u : 0u);
         }
         flags = __reduce_or_sync(0xffffffffu, flags);
         if (lane == 0 && flags) atomicOr(&my_flags[fb], flags);
         __syncthreads();           // the group is staged, its flags are complete
-        uint32_t keep4 = filter_rows ? my_flags[fb] : 0xFu;
+        const uint32_t keep4 = (filter_rows ? my_flags[fb] : 0xFu) & ((1u << nv) - 1u);      // kept AND inside the matrix
         if (t == 0) my_flags[fb == 0 ? 2 : fb - 1] = 0u;      // the word of group g + 2 (last read one group ago, next written after the next barrier)
         if (own) {
             // byte-sliced gather: one load serves a cell of all four rows (byte lane i = row i); a rotation puts the field
@@ -526,30 +539,27 @@ __global__ void scs_permute_reduce4_kernel(const uint8_t* __restrict__ gt, long 
             const uint32_t ov[4] = {__byte_perm(l01, l23, 0x5410), __byte_perm(l01, l23, 0x7632), __byte_perm(h01, h23, 0x5410),
                                     __byte_perm(h01, h23, 0x7632)};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const long long r = 4 * g + i;
-                if (r < n_snv) {
-                    out[size_t(r) * row_words + t] = ov[i];
-                    if ((keep4 >> i) & 1u) {
-                        const uint32_t m = ov[i] & (ov[i] >> 1) & valid;          // bit 2e set <=> position e missing
-                        a0 += m & 0x01010101u;
-                        a1 += (m >> 2) & 0x01010101u;
-                        a2 += (m >> 4) & 0x01010101u;
-                        a3 += (m >> 6) & 0x01010101u;
-                    }
-                }
-            }
+            for (int i = 0; i < 4; ++i)
+                if (i < nv) dst[size_t(i) * row_words] = ov[i];
+            // missing cells of the kept rows (bit 2e of m_i: position e of row i is missing).  The four rows are added
+            // pairwise while they are still 2-bit fields (0 .. 2 fits), then spread into the byte counters: half the
+            // instructions of four rows done one by one
+            const uint32_t m0 = (keep4 & 1u) ? (ov[0] & (ov[0] >> 1) & valid) : 0u, m1 = (keep4 & 2u) ? (ov[1] & (ov[1] >> 1) & valid) : 0u;
+            const uint32_t m2 = (keep4 & 4u) ? (ov[2] & (ov[2] >> 1) & valid) : 0u, m3 = (keep4 & 8u) ? (ov[3] & (ov[3] >> 1) & valid) : 0u;
+            const uint32_t s01 = m0 + m1, s23 = m2 + m3;
+            a0 += (s01 & 0x03030303u) + (s23 & 0x03030303u);
+            a1 += ((s01 >> 2) & 0x03030303u) + ((s23 >> 2) & 0x03030303u);
+            a2 += ((s01 >> 4) & 0x03030303u) + ((s23 >> 4) & 0x03030303u);
+            a3 += ((s01 >> 6) & 0x03030303u) + ((s23 >> 6) & 0x03030303u);
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {                             // (uniform over the sub-block)
-            const long long r = 4 * g + i;
-            if (r < n_snv && ((keep4 >> i) & 1u)) {
-                ++pending;
-                ++kept_cnt;
-            }
+        dst += dst_step;
+        {
+            const int nk = __popc(keep4);                         // (uniform over the sub-block)
+            pending += nk;
+            kept_cnt += nk;
         }
         if (pending > 250) flush();
-        if (t < 4 && 4 * g + t < n_snv) row_keep[4 * g + t] = uint8_t((keep4 >> t) & 1u);
+        if (t < nv) row_keep[4 * g + t] = uint8_t((keep4 >> t) & 1u);
     }
     flush();
     if (nsub == 1) {
