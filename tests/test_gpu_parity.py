@@ -822,6 +822,51 @@ def test_run_poisson_tree_test_tsv(ctx, name, tmp_path):
         assert rc[i + 3] == gc[i + 3]                                    # H0 / H1
 
 
+@pytest.mark.parametrize("seed", [11, 12, 13, 14])
+def test_whole_path_on_random_datasets_against_the_oracle(ctx, tmp_path, seed):
+    """VCF text + Newick file -> TSV through the product path (GPU decode, row filter, placement, branch weights, LRT) against
+    the oracle's whole path (NumPy + SciPy trust-constr) on random small datasets: a random coalescent tree of 6 .. 40 cells,
+    100 .. 400 SNVs with missing calls, a few records the decoder has to skip, error rates taken from the file path
+    (:287-294).  Same tolerances as the golden TSVs; a w_max where SciPy itself did not reach the optimum (LR above ours by
+    more than the tolerance: the cases test_lrt_sweep_against_the_reference classifies) is allowed to differ in LR / p, never
+    in muts, FN, FP or dof."""
+    import gzip
+    rng = np.random.default_rng(seed)
+    n_cells = int(rng.integers(6, 41))
+    n_snv = int(rng.integers(100, 401))
+    names = ["cell%04d" % (i + 1) for i in range(n_cells)] + ["outgcell"]
+    tree = synth.coalescent_tree(n_cells, rng)
+    codes = synth.observe(tree, synth.throw_mutations(tree, n_snv, rng), 0.15, 0.01, float(rng.uniform(0.05, 0.3)), rng)
+    d = tmp_path / ("sim_WGA0.%d-0-0.0%d" % (1 + seed % 3, 1 + seed % 2))
+    d.mkdir()
+    vcf = d / "rep.vcf.gz"
+    with gzip.open(vcf, "wt") as f:
+        f.write("##fileformat=VCFv4.3\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(names) + "\n")
+        for i in range(n_snv):
+            gts = [".|." if c == 3 else ("0|0" if c == 0 else ("0|1" if c == 1 else "1|1")) for c in codes[i]] + ["0|0"]
+            filt = "PASS" if rng.random() > 0.05 else "LowQual"                       # (skipped by both)
+            f.write("1\t%d\t.\tA\tC\t.\t%s\t.\tGT\t%s\n" % (10 + i, filt, "\t".join(gts)))
+    tf = d / "rep.newick"
+    tf.write_text(tree.newick(names[:-1], names[-1], scale=0.05) + "\n")
+    w = [100.0, 500.0, 1000.0]
+    out = tmp_path / "out.tsv"
+    P.run_poisson_tree_test(str(vcf), str(tf), str(out), w, "", "", None, None)
+    want_tsv, want = O.run_poisson_tree_test(str(vcf), str(tf), w)
+    got = out.read_text().split("\n")
+    ref = want_tsv.split("\n")
+    assert got[0] == ref[0]
+    rc, gc = ref[1].split("\t"), got[1].split("\t")
+    assert rc[:3] == gc[:3]                                              # muts, FN, FP
+    for k, i in enumerate(range(3, len(rc), 4)):
+        assert rc[i + 1] == gc[i + 1]                                    # dof
+        lr_ref, lr_got = float(rc[i]), float(gc[i])
+        if lr_ref - lr_got > 1e-4 * max(1.0, abs(lr_ref)) + 6e-4:
+            continue                                                     # SciPy stopped above the optimum (our null likelihood is the higher one)
+        assert abs(lr_ref - lr_got) <= 1e-4 * max(1.0, abs(lr_ref)) + 6e-4
+        assert abs(float(rc[i + 2]) - float(gc[i + 2])) <= 2e-3 * float(rc[i + 2]) + 1e-300
+        assert rc[i + 3] == gc[i + 3]                                    # H0 / H1
+
+
 def test_run_poisson_tree_test_batch(ctx, tmp_path):
     """A sweep of (VCF, tree) pairs through the batched path: the two example-sized pairs share a
     shape and go through ONE placement launch per pass; every TSV matches the reference's."""
