@@ -709,7 +709,8 @@ def main():
                         "traffic": (iv["dram_bytes"] * scale) if (scale and n_cells == 10000 and iv.get("dram_bytes")) else None,
                         "traffic_source": iv.get("source") if scale else None,
                         "peak_source": pk_kind + " HBM copy bandwidth",
-                        "kernel": "scs_place_iv%d_kernel (prefix counts in shared memory, no GEMM)" % plan_info["interval_variant"],
+                        "kernel": "scs_place_iv%d_kernel (prefix counts in shared memory, no GEMM)%s" % (
+                            plan_info["interval_variant"], " + scs_iv4_leaf_kernel (leaf accumulators, from 2,048 cells on): one timed pair" if n_cells >= 2048 else ""),
                         "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": t_k, "prepass_ms": float(g[:, 4].mean()),
                         "prepass_GBps": 2.0 * alg_bytes / 1e9 / (float(g[:, 4].mean()) / 1e3) if g[:, 4].mean() > 0 else None,
                         "prepass_note": "scs_permute_reduce4_kernel: row filter + per-cell missing counts + rows rewritten in depth-first cell order, one read and one write of the packed matrix",

@@ -1327,6 +1327,8 @@ struct Placement {
     bool iv_dcache = false, iv_perm_smem = false;
     size_t iv_smem = 0;
     int iv4_np = 0;                // variant 4 (scs_place_iv4.cuh): pairs of non-leaf rows per thread
+    float4* iv4_leafw = nullptr;   // variant 4, leaf split: per-SNV leaf weights
+    size_t iv4_leafw_bytes = 0;
     // ---- batches of small trees (scs_place_iv5.cuh), algo 3: chosen by scs_placement_set_trees
     int iv5_L = 0, iv5_stride = 0, iv5_ntasks = 0, iv5_grid = 0;
     uint16_t* iv5_perm = nullptr;
@@ -1575,6 +1577,7 @@ int scs_placement_destroy(scs_placement* h) {
     cudaFree(pl->d_leafmask);
     cudaFree(pl->gt_perm);
     cudaFree(pl->ipart);
+    cudaFree(pl->iv4_leafw);
     cudaFree(pl->iv5_perm);
     cudaFree(pl->iv5_lohi);
     cudaFree(pl->iv5_row_slot);
@@ -2293,6 +2296,28 @@ int scs_placement_run_batch(scs_placement* h, const double* FP, const double* FN
                 q4.leaf_off = pl->iv_leaf_off;
                 q4.rows_per_run = pl->iv_rows_per_run;
                 q4.num_runs = pl->iv_runs;
+                q4.leafw = nullptr;
+                // leaf split: the leaf accumulators leave the placement kernel (where they live in shared memory: 8 LDS / STS
+                // of 16 bytes per thread and row on top of the selects and adds) for scs_iv4_leaf_kernel (registers); measured
+                // at 10,000 cells x 1M SNVs: 20.9 -> 20.3 ms for the pair of kernels.  Default from 2,048 cells on (below that
+                // the second launch costs what the split saves); SCS_IV4_LEAF_SPLIT=0 / 1 overrides.
+                bool split = pl->n_cells >= 2048;
+                if (const char* ev = getenv("SCS_IV4_LEAF_SPLIT")) split = atoi(ev) != 0;
+                {
+                    if (split) {
+                        const size_t lbytes = size_t(pl->n_snv) * sizeof(float4);
+                        if (lbytes > pl->iv4_leafw_bytes) {
+                            cudaFree(pl->iv4_leafw);
+                            pl->iv4_leafw = nullptr;
+                            pl->iv4_leafw_bytes = 0;
+                            if (cudaMalloc(&pl->iv4_leafw, lbytes) != cudaSuccess) return set_error(SCS_ERR_OOM, "device allocation of %zu bytes failed", lbytes);
+                            pl->iv4_leafw_bytes = lbytes;
+                        }
+                        SCS_CUDA(cudaMemsetAsync(pl->iv4_leafw, 0, lbytes, st));      // (rows that are filtered out keep zero weights)
+                        q4.leafw = pl->iv4_leafw;
+                        pl->launches++;
+                    }
+                }
                 iv4_launch(pl->iv4_np, q4, pl->iv_grid, pl->iv_threads, pl->iv_smem, st);
             } else if (pl->iv_threads <= 640) scs_place_interval3_kernel<640, 2><<<pl->iv_grid, pl->iv_threads, pl->iv_smem, st>>>(q);
             else scs_place_interval3_kernel<1024, 1><<<pl->iv_grid, pl->iv_threads, pl->iv_smem, st>>>(q);

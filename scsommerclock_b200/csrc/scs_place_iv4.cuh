@@ -46,6 +46,7 @@ struct Iv4Params {
     float* part;               // [num_runs][part_stride]: non-leaf accumulators, then (at leaf_off) 16 rw leaf accumulators
     int part_stride, leaf_off;
     int rows_per_run, num_runs;
+    float4* leafw;             // SPLIT kernels: [n_snv] (w_wt, w_mut, w_miss, 0) of every kept row for scs_iv4_leaf_kernel (zero elsewhere)
 };
 
 constexpr int IV4_SCRATCH_WORDS = 5 * 32;   // (at the start of shared memory) [0,32) scan totals, [32,64) leaf totals, [64,96) best rank value, [96,128) its counts, [128,160) row sums
@@ -73,7 +74,7 @@ static inline size_t iv4_smem_bytes(int rw, int threads) {
     return 4 * (size_t(iv3_p_words(rw)) + 16 * size_t(threads) + IV4_SCRATCH_WORDS);
 }
 
-template <int NP>
+template <int NP, bool SPLIT>
 __global__ void __launch_bounds__(IV4_MAX_THREADS, 1) scs_place_iv4_kernel(const Iv4Params q) {
     extern __shared__ uint32_t iv_smem[];
     // thread index and CTA size are read ONCE (volatile: ptxas otherwise re-reads the special registers -- S2R, ~20 cycles --
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(IV4_MAX_THREADS, 1) scs_place_iv4_kernel(const
         float2 acc[NP];
 #pragma unroll
         for (int i = 0; i < NP; ++i) acc[i] = make_float2(0.f, 0.f);
-        if (own) {
+        if (!SPLIT && own) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) accL[i * T] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(IV4_MAX_THREADS, 1) scs_place_iv4_kernel(const
             return ltot;
         };
         // stage E: normalised terms into the accumulators
-        auto stage_e = [&](uint32_t w) {
+        auto stage_e = [&](uint32_t w, long long row) {
             float total = lane < nwarp ? __uint_as_float(scr[128 + lane]) : 0.f;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
@@ -207,7 +208,10 @@ __global__ void __launch_bounds__(IV4_MAX_THREADS, 1) scs_place_iv4_kernel(const
             const float2 inv2 = make_float2(inv, inv);
 #pragma unroll
             for (int i = 0; i < NP; ++i) acc[i] = __ffma2_rn(make_float2(__uint_as_float(dx[i]), __uint_as_float(dy[i])), inv2, acc[i]);
-            if (own) {
+            if (SPLIT) {
+                // leaves are accumulated by scs_iv4_leaf_kernel from the three weights of the row
+                if (t == 0) q.leafw[row] = make_float4(tl_wt * inv, tl_mut * inv, tl_miss * inv, 0.f);
+            } else if (own) {
                 // leaves: the term by the position's code (positions without a leaf row collect numbers nobody reads)
                 const uint32_t mm = (w ^ (w >> 1)) & 0x55555555u, wm = ~(w | (w >> 1)) & 0x55555555u;
                 const float w_wt = tl_wt * inv, w_mut = tl_mut * inv, w_miss = tl_miss * inv;
@@ -234,7 +238,7 @@ __global__ void __launch_bounds__(IV4_MAX_THREADS, 1) scs_place_iv4_kernel(const
 
         for (long long r = r0; r < r1; ++r) {
             // ================= phase 1: E(r-1) | C(r) | A(r+1)
-            if (keep_prev) stage_e(w_prev);
+            if (keep_prev) stage_e(w_prev, r - 1);
             if (keep_cur) {
                 // counts of this thread's rows: both counts of a row in one subtraction (no borrow: P is monotone in each half)
                 float bv = -INFINITY;
@@ -366,7 +370,7 @@ __global__ void __launch_bounds__(IV4_MAX_THREADS, 1) scs_place_iv4_kernel(const
             keep_nxt = keep_nn;
             w_nxt = w_nn;
         }
-        if (keep_prev) stage_e(w_prev);
+        if (keep_prev) stage_e(w_prev, r1 - 1);
 
         float* out = q.part + size_t(run) * q.part_stride;
 #pragma unroll
@@ -374,27 +378,61 @@ __global__ void __launch_bounds__(IV4_MAX_THREADS, 1) scs_place_iv4_kernel(const
             const int j = t + i * T;
             if (j < q.n_pairs) reinterpret_cast<float2*>(out)[j] = acc[i];
         }
-        if (own) {
+        if (!SPLIT && own) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(out + q.leaf_off)[4 * t + i] = accL[i * T];
         }
     }
 }
 
+// The leaf accumulators of the SPLIT variant: thread = one word (16 positions) of the rows of one run, accumulators in
+// registers, the row's three weights read once per row (the same address for the whole block).  Same order of additions per
+// leaf as the fused kernel (rows in order).
+__global__ void __launch_bounds__(128) scs_iv4_leaf_kernel(const Iv4Params q) {
+    const int wd = blockIdx.x * blockDim.x + threadIdx.x;
+    const int run = blockIdx.y;
+    if (wd >= q.rw) return;
+    const long long r0 = (long long)run * q.rows_per_run;
+    const long long r1 = r0 + q.rows_per_run < q.n_snv ? r0 + q.rows_per_run : q.n_snv;
+    float acc[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+    const uint32_t* gp = q.gt + size_t(r0) * q.rw + wd;
+    uint32_t w = r0 < r1 ? *gp : 0u;
+    for (long long r = r0; r < r1; ++r) {
+        const float4 lw = __ldg(q.leafw + r);
+        const uint32_t wc = w;
+        gp += q.rw;
+        if (r + 1 < r1) w = *gp;
+        const uint32_t mm = (wc ^ (wc >> 1)) & 0x55555555u, wm = ~(wc | (wc >> 1)) & 0x55555555u;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) acc[e] += ((mm >> (2 * e)) & 1u) ? lw.y : (((wm >> (2 * e)) & 1u) ? lw.x : lw.z);
+    }
+    float* out = q.part + size_t(run) * q.part_stride + q.leaf_off + 16 * wd;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(out)[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+}
+
 template <int NP>
 static void iv4_launch_np(const Iv4Params& q, int grid, int threads, size_t smem, cudaStream_t st) {
-    scs_place_iv4_kernel<NP><<<grid, threads, smem, st>>>(q);
+    if (q.leafw) {
+        cudaFuncSetAttribute(scs_place_iv4_kernel<NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        scs_place_iv4_kernel<NP, true><<<grid, threads, smem, st>>>(q);
+        scs_iv4_leaf_kernel<<<dim3(unsigned((q.rw + 127) / 128), unsigned(q.num_runs)), 128, 0, st>>>(q);
+    } else {
+        scs_place_iv4_kernel<NP, false><<<grid, threads, smem, st>>>(q);
+    }
 }
 
 // Resident CTAs per SM for this shape (0 when the shape is not supported); also raises the kernel's dynamic shared-memory limit.
 template <int NP>
 static int iv4_occupancy_np(int threads, size_t smem) {
     int per_sm = 0;
-    if (cudaFuncSetAttribute(scs_place_iv4_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess) {
+    if (cudaFuncSetAttribute(scs_place_iv4_kernel<NP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scs_place_iv4_kernel<NP>, threads, smem) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scs_place_iv4_kernel<NP, false>, threads, smem) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }

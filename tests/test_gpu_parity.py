@@ -252,6 +252,34 @@ def test_interval_path_block_shapes_and_run_lengths(ctx, monkeypatch, threads, r
     pl.close()
 
 
+@pytest.mark.parametrize("n_snv,n_cells", [(700, 300), (300, 2500), (520, 5000)])
+def test_interval_leaf_split_matches_the_fused_kernel(ctx, monkeypatch, n_snv, n_cells):
+    """Variant 4 with the leaf accumulators in the placement kernel (SCS_IV4_LEAF_SPLIT=0) and in their own kernel (= 1, the
+    default from 2,048 cells on): the same soft weights to summation order, runs that end inside the matrix, filtered rows."""
+    codes, S = shuffled_problem(n_snv, n_cells, seed=7 * n_snv + n_cells)
+    keep = np.ones(n_snv, dtype=np.uint8)
+    keep[::7] = 0
+    packed, pitch = engine.pack_genotypes(codes)
+    bits, words = engine.pack_clades(S)
+    got = {}
+    for split in ("0", "1"):
+        monkeypatch.setenv("SCS_IV4_LEAF_SPLIT", split)
+        monkeypatch.setenv("SCS_PLACE_ALGO", "interval")
+        pl = engine.Placement(ctx, n_snv, n_cells, S.shape[0])
+        pl.set_clades_host(bits, words)
+        pl.set_genotypes_host(packed, pitch, keep)
+        got[split] = pl.run_host(0.01, 0.1)
+        assert pl.info()["algo"] == 2 and pl.info()["interval_variant"] == 4
+        pl.close()
+    np.testing.assert_allclose(got["0"], got["1"], rtol=1e-6, atol=1e-7)
+    monkeypatch.setenv("SCS_PLACE_ALGO", "gemm")
+    pg = engine.Placement(ctx, n_snv, n_cells, S.shape[0])
+    pg.set_clades_host(bits, words)
+    pg.set_genotypes_host(packed, pitch, keep)
+    assert_soft_close(got["1"], pg.run_host(0.01, 0.1))
+    pg.close()
+
+
 def test_interval_path_needs_tree_shaped_masks_and_shared_memory(ctx, monkeypatch):
     """Masks that are not a laminar family, replicate batches and trees whose working set exceeds
     shared memory go through the GEMM; so do, by default, trees of fewer than 100 cells (all fixed
