@@ -11,7 +11,7 @@ echo "launch list (10k x 1M) rc=$?"
 # --- full capture at 250k SNVs: pre-pass, placement, LRT
 CMD2="python bench.py --snvs 250000 --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --replicates 0 --no-gemm-leg --no-small-leg"
 $CMD2 > gpurun_out/r2e_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k "regex:scs_place_iv4|scs_permute_reduce|scs_lrt_tree" -s 3 -c 3 -o gpurun_out/r2e_prof_10k_250k -f $CMD2 > gpurun_out/r2e_ncu_full2.log 2>&1
+ncu --set full --clock-control none --import-source on -k "regex:scs_place_iv4|scs_iv4_leaf|scs_permute_reduce|scs_lrt_tree" -s 4 -c 4 -o gpurun_out/r2e_prof_10k_250k -f $CMD2 > gpurun_out/r2e_ncu_full2.log 2>&1
 echo "full capture (iv4 + prepass + lrt) rc=$?"
 # --- replicate sweep leg (1250 x 100 cells x 10k SNVs): launch list, full capture of the placement and the LRT kernels
 CMD3="python bench.py --cells 2000 --snvs 20000 --steps 2 --warmup 1 --no-cpu-baseline --no-gemm-leg --no-small-leg --no-e2e"
