@@ -708,6 +708,9 @@ def main():
                         "frac": alg_bytes / 1e9 / (t_k / 1e3) / hbm_peak,
                         "traffic": (iv["dram_bytes"] * scale) if (scale and n_cells == 10000 and iv.get("dram_bytes")) else None,
                         "traffic_source": iv.get("source") if scale else None,
+                        "traffic_note": ("the timed pair reads the reordered rows twice (placement kernel, then the leaf kernel): ~2 x the algorithmic "
+                                         "bytes by design -- the second read is 0.4 ms of HBM time, the leaf accumulators it moves out of the "
+                                         "placement kernel's shared memory were worth 3.1 ms there") if n_cells >= 2048 else None,
                         "peak_source": pk_kind + " HBM copy bandwidth",
                         "kernel": "scs_place_iv%d_kernel (prefix counts in shared memory, no GEMM)%s" % (
                             plan_info["interval_variant"], " + scs_iv4_leaf_kernel (leaf accumulators, from 2,048 cells on): one timed pair" if n_cells >= 2048 else ""),
