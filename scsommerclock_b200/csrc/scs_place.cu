@@ -105,7 +105,6 @@ struct PlaceParams {
     int run_len, num_runs, sb_width, num_tasks;
     int l2_hints;              // 1: clade tiles evict-last, genotype tiles evict-first
     int nchunk;                // radix mode: K chunks (accumulators) per tile
-    int num_row_pairs, run_len2, num_runs2, num_tasks2;   // 2-CTA kernel: schedule in row-block pairs
     const TaskEntry* tasks;    // [num_tasks], the 1-CTA kernel's schedule
     const GroupConst* gconst;  // [groups]
     uint2* stats;              // pass 1 out: [num_col_tiles*2][M_pad] {ref counts, sum}
@@ -765,192 +764,6 @@ scs_place_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constan
     }
 }
 
-// ------------------------------------------------------------------- 2-CTA kernel
-// Radix mode on CTA pairs (cluster of 2, tcgen05 cta_group::2): one MMA covers M = 256 SNV
-// rows (128 from each CTA's shared memory) x N = 128 clade rows, of which each CTA stages only
-// its half (64 rows).  Per 64-cycle MMA an SM now reads 4 KB (A) + 2 KB (B) of shared memory
-// instead of 8 KB, and pulls 24 KB instead of 32 KB per K block from L2: the 1-CTA kernel sits
-// at 68 % tensor-pipe utilisation with the shared-memory operand port saturated
-// (profiles/r01_ncu_place_radix_summary.txt).
-// Protocol: every CTA has a TMA producer (its own A rows + its B half), both signal the LEADER's
-// full barrier; only the leader issues MMAs and multicasts the commits (stage free, tile done)
-// to both CTAs; both CTAs' epilogue warps release TMEM slots on the leader's barrier.
-constexpr int K2_STAGES = 8;
-constexpr int K2_STAGE_BYTES = TILE_BYTES + TILE_BYTES / 2;   // A 16 KB + half of B 8 KB
-constexpr int K2_SMEM_TOTAL = K2_STAGES * K2_STAGE_BYTES + SMEM_BARRIER_BYTES + SMEM_RED_BYTES + 1024;
-constexpr uint32_t IDESC_E5M2_2SM = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BLOCK_N >> 3) << 17) | (uint32_t(256 >> 4) << 24);
-
-__host__ __device__ inline void decode_task2(const PlaceParams& p, int t, int& j, int& q0, int& q1) {
-    const int per_sb = p.num_runs2 * p.sb_width;
-    const int nsb_full = p.num_col_tiles / p.sb_width;
-    int sb = t / per_sb;
-    int w = p.sb_width;
-    if (sb >= nsb_full) {
-        sb = nsb_full;
-        w = p.num_col_tiles - nsb_full * p.sb_width;
-    }
-    const int rem = t - sb * per_sb;
-    const int run = rem / w;
-    j = sb * p.sb_width + (rem - run * w);
-    q0 = run * p.run_len2;
-    q1 = min(q0 + p.run_len2, p.num_row_pairs);
-}
-
-template <int PASS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
-scs_place_kernel2(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_s64, const PlaceParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + K2_STAGES * K2_STAGE_BYTES);
-    uint64_t* full_bar = bars;                      // [8] used in the leader only
-    uint64_t* empty_bar = bars + K2_STAGES;         // [8] each CTA, one multicast commit per phase
-    uint64_t* tfull_bar = bars + 2 * K2_STAGES;     // [4] each CTA
-    uint64_t* sempty_bar = bars + 2 * K2_STAGES + 4;  // [4] leader only, both CTAs' epilogues arrive
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * K2_STAGES + 8);
-    float* red = reinterpret_cast<float*>(smem + K2_STAGES * K2_STAGE_BYTES + SMEM_BARRIER_BYTES);
-
-    const int warp_idx = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const uint32_t rank = ptx::cluster_ctarank();
-    const int cluster_id = blockIdx.x >> 1;
-    const int num_clusters = gridDim.x >> 1;
-
-    if (warp_idx == 0 && ptx::elect_one()) {
-        ptx::prefetch_tmap(&tm_x);
-        ptx::prefetch_tmap(&tm_s64);
-        for (int s = 0; s < K2_STAGES; ++s) {
-            ptx::mbar_init(&full_bar[s], 1);
-            ptx::mbar_init(&empty_bar[s], 1);
-        }
-        for (int a = 0; a < 4; ++a) {
-            ptx::mbar_init(&tfull_bar[a], 1);
-            ptx::mbar_init(&sempty_bar[a], 2 * NUM_EPI_WARPS);
-        }
-        ptx::fence_mbar_init();
-    }
-    if (warp_idx == 1) {
-        ptx::tmem_alloc_2sm(tmem_ptr_smem, TMEM_COLS);
-        ptx::tmem_relinquish_2sm();
-    }
-    ptx::tc_fence_before();
-    __syncthreads();
-    ptx::cluster_sync();
-    ptx::tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
-
-    if (warp_idx == 0) {
-        // ============ TMA producer (one lane, in BOTH CTAs) ============
-        if (ptx::elect_one()) {
-            int stage = 0;
-            uint32_t phase = 0;
-            const uint64_t pol_x = p.l2_hints ? ptx::L2_EVICT_FIRST : ptx::L2_EVICT_NORMAL;
-            const uint64_t pol_s = p.l2_hints ? ptx::L2_EVICT_LAST : ptx::L2_EVICT_NORMAL;
-            for (int t = cluster_id; t < p.num_tasks2; t += num_clusters) {
-                int j, q0, q1;
-                decode_task2(p, t, j, q0, q1);
-                for (int q = q0; q < q1; ++q) {
-                    const int rb = 2 * q + int(rank);
-                    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                        uint8_t* st = smem + stage * K2_STAGE_BYTES;
-                        if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * K2_STAGE_BYTES);   // both CTAs' bytes
-                        const uint32_t lead_full = ptx::mapa_u32(&full_bar[stage], 0);
-                        ptx::tma_load_2d_2sm(&tm_x, lead_full, st, kb * BLOCK_K, rb * BLOCK_M, pol_x);
-                        ptx::tma_load_2d_2sm(&tm_s64, lead_full, st + TILE_BYTES, kb * BLOCK_K, j * BLOCK_N + int(rank) * 64, pol_s);
-                        if (++stage == K2_STAGES) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
-                    }
-                }
-            }
-        }
-    } else if (warp_idx == 1) {
-        // ============ MMA issuer (one lane of the LEADER CTA) ============
-        if (rank == 0 && ptx::elect_one()) {
-            int stage = 0;
-            uint32_t phase = 0;
-            const int spt = p.nchunk;
-            uint32_t tile_n = 0;
-            for (int t = cluster_id; t < p.num_tasks2; t += num_clusters) {
-                int j, q0, q1;
-                decode_task2(p, t, j, q0, q1);
-                for (int q = q0; q < q1; ++q, ++tile_n) {
-                    const uint32_t use0 = tile_n * spt;
-                    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-                        const int chunk = kb / RADIX_KB_PER_CHUNK;
-                        const int kin = kb - chunk * RADIX_KB_PER_CHUNK;
-                        if (kin == 0) {
-                            ptx::mbar_wait(&sempty_bar[(use0 + chunk) & 3], (((use0 + chunk) >> 2) & 1) ^ 1);
-                            ptx::tc_fence_after();
-                        }
-                        ptx::mbar_wait(&full_bar[stage], phase);
-                        ptx::tc_fence_after();
-                        const uint32_t st = ptx::smem_u32(smem + stage * K2_STAGE_BYTES);
-                        const uint64_t dx = ptx::make_kmajor_sw128_desc(st);
-                        const uint64_t ds = ptx::make_kmajor_sw128_desc(st + TILE_BYTES);
-                        const uint32_t d = tmem_base + (((use0 + chunk) & 3) * BLOCK_N);
-#pragma unroll
-                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                            const uint64_t koff = uint64_t(k * (UMMA_K >> 4));
-                            ptx::mma_f8_ss_2sm(d, dx + koff, ds + koff, IDESC_E5M2_2SM, (kin | k) != 0);
-                        }
-                        ptx::mma_commit_2sm(&empty_bar[stage], 3);
-                        if (++stage == K2_STAGES) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
-                    }
-                    ptx::mma_commit_2sm(&tfull_bar[tile_n & 3], 3);
-                }
-            }
-        }
-    } else {
-        // ============ epilogue warps (both CTAs, own 128 rows each) ============
-        const int ew = warp_idx - 2;
-        const int q4 = warp_idx & 3;
-        const int hh = ew >> 2;
-        const uint32_t lane_base = uint32_t(q4 * 32) << 16;
-        const int spt = p.nchunk;
-        uint32_t tile_n = 0;
-        for (int t = cluster_id; t < p.num_tasks2; t += num_clusters) {
-            int j, q0, q1;
-            decode_task2(p, t, j, q0, q1);
-            const GroupConst gc = p.gconst[0];          // the 2-CTA kernel handles single-group plans only
-            const int col0 = j * BLOCK_N + hh * 64;
-            const int n_valid = max(0, min(64, p.N - col0));
-            float colacc[64];
-            if (PASS == PASS_COLSUM) {
-#pragma unroll
-                for (int i = 0; i < 64; ++i) colacc[i] = 0.f;
-            }
-            for (int q = q0; q < q1; ++q, ++tile_n) {
-                ptx::mbar_wait(&tfull_bar[tile_n & 3], (tile_n >> 2) & 1);
-                ptx::tc_fence_after();
-                const int row = (2 * q + int(rank)) * BLOCK_M + q4 * 32 + lane;
-                const uint32_t use0 = tile_n * spt;
-                const uint32_t taddr = tmem_base + lane_base + hh * 64;
-                epilogue_tile<PASS, MODE_RADIX>(p, gc, taddr, use0, row, j, hh, col0, n_valid, colacc,
-                                                PASS == PASS_COLSUM ? p.rowref[row] : make_uint2(0u, 0u));
-                ptx::tc_fence_before();
-                __syncwarp();
-                if (lane == 0)
-                    for (int c = 0; c < spt; ++c) ptx::mbar_arrive_cluster(ptx::mapa_u32(&sempty_bar[(use0 + c) & 3], 0));
-            }
-            if (PASS == PASS_COLSUM) epilogue_flush_columns(p, red, colacc, q4, hh, lane, (q0 / p.run_len2) * 2 + int(rank), j);
-        }
-    }
-
-    // both CTAs must be done with TMEM, shared memory and each other's barriers before either leaves
-    ptx::tc_fence_before();
-    __syncthreads();
-    ptx::cluster_sync();
-    if (warp_idx == 1) {
-        ptx::tc_fence_after();
-        ptx::tmem_dealloc_2sm(tmem_base, TMEM_COLS);
-    }
-}
-
 // ------------------------------------------------------- operand expansion
 // Row geometry of a (possibly multi-group) plan: every group's SNVs are padded to whole
 // 256-row units in the operand planes; group_of_unit[u] says whose rows unit u holds.
@@ -1238,13 +1051,7 @@ static void launch_place(int mode, int grid, cudaStream_t st, const CUtensorMap&
 }
 
 template <int PASS>
-static void launch_place2(int grid2, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b64, const PlaceParams& p) {
-    scs_place_kernel2<PASS><<<grid2, NUM_THREADS, K2_SMEM_TOTAL, st>>>(a, b64, p);
-}
-
-template <int PASS>
 static void set_place_smem() {
-    cudaFuncSetAttribute(scs_place_kernel2<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_TOTAL);
     cudaFuncSetAttribute(scs_place_kernel<PASS, MODE_PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModeCfg<MODE_PLANES>::SMEM_TOTAL);
     cudaFuncSetAttribute(scs_place_kernel<PASS, MODE_RADIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModeCfg<MODE_RADIX>::SMEM_TOTAL);
     if (PASS == PASS_STATS) {
@@ -1296,10 +1103,7 @@ struct Placement {
     size_t stage_mask_bytes = 0;
     long long launches = 0;
     int mode = MODE_PLANES;
-    bool pair = false;            // radix mode on CTA pairs (scs_place_kernel2)
-    int grid2 = 0;
     int colpart_rows = 0;
-    CUtensorMap tm_s64;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // brackets of the four kernels of run()
     cudaEvent_t ev_prep[2] = {nullptr, nullptr};                         // brackets of the last scs_placement_prepare's kernels
     bool prep_timed = false;
@@ -1307,6 +1111,9 @@ struct Placement {
     // ---- interval path (scs_place_interval.cuh): chosen by set_clades when the masks are a laminar family
     int algo = 0;                  // 0 undecided (no clades yet), 1 GEMM, 2 interval
     bool operands_valid = false;   // the GEMM operand plane(s) hold the current genotypes
+    bool gemm_ready = false;       // ensure_gemm_buffers has run (operand planes, clade operand, pass-1 partials, tensor maps)
+    std::vector<uint32_t> h_bits;  // interval plans small enough for scs_placement_debug_counts: the clade masks, for the dump's GEMM
+    int64_t h_bits_pitch = 0;
     uint8_t* gt_own = nullptr;     // plan-owned copy of the packed genotypes (set_genotypes)
     size_t gt_own_bytes = 0;
     const uint8_t* gt_src = nullptr;   // what the interval kernel reads: gt_own or the caller's bound buffer
@@ -1394,8 +1201,6 @@ int scs_placement_create_batch(scs_ctx* ctx, int32_t n_groups, const int64_t* n_
         delete pl;
         return set_error(SCS_ERR_ARG, "too many clade rows for one placement plan");
     }
-    const size_t plane = size_t(pl->M_pad) * pl->K_pad;
-    const size_t sbytes = size_t(pl->N_pad) * pl->K_pad;
     PlaceParams& p = pl->prm;
     memset(&p, 0, sizeof(p));
     p.M = int(n_snv_g[0]);
@@ -1477,29 +1282,16 @@ int scs_placement_create_batch(scs_ctx* ctx, int32_t n_groups, const int64_t* n_
     p.num_runs = max_runs;
     p.num_tasks = int(tasks.size());
     pl->grid = std::min(ctx->sm_count, p.num_tasks);
-    // 2-CTA schedule (single-group plans only): the same tasks, in units of row-block pairs
-    p.num_row_pairs = p.num_row_blocks / 2;
-    p.run_len2 = std::max(1, run_len / 2);
-    p.num_runs2 = (p.num_row_pairs + p.run_len2 - 1) / p.run_len2;
-    p.num_tasks2 = p.num_runs2 * p.num_col_tiles;
-    pl->grid2 = std::min(ctx->sm_count & ~1, 2 * p.num_tasks2);
-    // The 2-CTA kernel is opt-in (SCS_PLACE_PAIR=1): it is bit-identical but, measured at
-    // 10k cells x 1M SNVs, not faster -- the same cycle count per pass at lower clocks under the
-    // 1 kW cap (169 ms @1522 MHz vs 140 ms @1815 MHz; profiles/r01_pair_vs_single.txt).  The
-    // 1-CTA kernel already runs at 98.6 % of twice the measured sustained cuBLAS bf16 rate.
-    pl->pair = false;
-    if (const char* e = getenv("SCS_PLACE_PAIR")) pl->pair = pl->mode == MODE_RADIX && n_groups == 1 && atoi(e) != 0;
-    pl->colpart_rows = std::max(max_runs, 2 * p.num_runs2 * (n_groups == 1 ? 1 : 0));
+    pl->colpart_rows = max_runs;
 
     int rc = SCS_OK;
     do {
         std::vector<long long> row0v(pl->g_row0.begin(), pl->g_row0.end()), src0v(pl->g_src0.begin(), pl->g_src0.end());
         std::vector<int> nsnvv(n_groups);
         for (int g = 0; g < n_groups; ++g) nsnvv[g] = int(n_snv_g[g]);
-        if (cudaMalloc(&pl->x1, plane) != cudaSuccess || (pl->mode == MODE_PLANES && cudaMalloc(&pl->x0, plane) != cudaSuccess) ||
-            cudaMalloc(&pl->s, sbytes) != cudaSuccess ||
-            cudaMalloc(&pl->stats, size_t(pl->num_parts) * pl->M_pad * sizeof(uint2)) != cudaSuccess ||
-            cudaMalloc(&pl->rowref, size_t(pl->M_pad) * sizeof(uint2)) != cudaSuccess ||
+        // (the GEMM's own buffers -- operand planes, clade operand, pass-1 partials: 15 GB at 10k cells x 1M SNVs -- are
+        // allocated by ensure_gemm_buffers when the GEMM path is first taken; interval plans never hold them)
+        if (cudaMalloc(&pl->rowref, size_t(pl->M_pad) * sizeof(uint2)) != cudaSuccess ||
             cudaMalloc(&pl->colpart, size_t(pl->colpart_rows) * pl->N_pad * sizeof(float)) != cudaSuccess ||
             cudaMalloc(&pl->y, size_t(n_groups) * n_rows * sizeof(double)) != cudaSuccess ||
             cudaMalloc(&pl->row_keep, size_t(total)) != cudaSuccess ||
@@ -1514,9 +1306,6 @@ int scs_placement_create_batch(scs_ctx* ctx, int32_t n_groups, const int64_t* n_
             rc = set_error(SCS_ERR_OOM, "device allocation failed for placement plan (%s)", cudaGetErrorString(cudaGetLastError()));
             break;
         }
-        cudaMemset(pl->x1, 0, plane);
-        if (pl->x0) cudaMemset(pl->x0, 0, plane);
-        cudaMemset(pl->s, 0, sbytes);
         cudaMemcpy(pl->d_group_of_unit, unit_group.data(), unit_group.size() * sizeof(int), cudaMemcpyHostToDevice);
         cudaMemcpy(pl->d_group_row0, row0v.data(), size_t(n_groups) * sizeof(long long), cudaMemcpyHostToDevice);
         cudaMemcpy(pl->d_group_src0, src0v.data(), size_t(n_groups) * sizeof(long long), cudaMemcpyHostToDevice);
@@ -1527,19 +1316,10 @@ int scs_placement_create_batch(scs_ctx* ctx, int32_t n_groups, const int64_t* n_
         pl->rowmap.group_row0 = pl->d_group_row0;
         pl->rowmap.group_src0 = pl->d_group_src0;
         pl->rowmap.group_nsnv = pl->d_group_nsnv;
-        p.stats = pl->stats;
         p.rowref = pl->rowref;
         p.colpart = pl->colpart;
         p.tasks = pl->d_tasks;
         p.gconst = pl->d_gconst;
-        if ((rc = make_u8_tmap(&pl->tm_x1, pl->x1, pl->M_pad, pl->K_pad, BLOCK_M)) != SCS_OK) break;
-        if (pl->x0) {
-            if ((rc = make_u8_tmap(&pl->tm_x0, pl->x0, pl->M_pad, pl->K_pad, BLOCK_M)) != SCS_OK) break;
-        } else {
-            pl->tm_x0 = pl->tm_x1;
-        }
-        if ((rc = make_u8_tmap(&pl->tm_s, pl->s, pl->N_pad, pl->K_pad, BLOCK_N)) != SCS_OK) break;
-        if ((rc = make_u8_tmap(&pl->tm_s64, pl->s, pl->N_pad, pl->K_pad, BLOCK_N / 2)) != SCS_OK) break;
         set_place_smem<PASS_DUMP>();
         set_place_smem<PASS_STATS>();
         set_place_smem<PASS_COLSUM>();
@@ -1608,8 +1388,46 @@ int scs_placement_destroy(scs_placement* h) {
     return SCS_OK;
 }
 
+// The GEMM path's buffers and tensor maps, on first use: operand plane(s) X, clade operand S (both zero padded) and the
+// pass-1 partials.  A plan that stays on an interval path never calls this.
+static int ensure_gemm_buffers(Placement* pl, cudaStream_t st) {
+    if (pl->gemm_ready) return SCS_OK;
+    const size_t plane = size_t(pl->M_pad) * pl->K_pad;
+    const size_t sbytes = size_t(pl->N_pad) * pl->K_pad;
+    if (cudaMalloc(&pl->x1, plane) != cudaSuccess || (pl->mode == MODE_PLANES && cudaMalloc(&pl->x0, plane) != cudaSuccess) ||
+        cudaMalloc(&pl->s, sbytes) != cudaSuccess ||
+        cudaMalloc(&pl->stats, size_t(pl->num_parts) * pl->M_pad * sizeof(uint2)) != cudaSuccess) {
+        const char* why = cudaGetErrorString(cudaGetLastError());
+        cudaFree(pl->x1);
+        cudaFree(pl->x0);
+        cudaFree(pl->s);
+        cudaFree(pl->stats);
+        pl->x1 = pl->x0 = pl->s = nullptr;
+        pl->stats = nullptr;
+        return set_error(SCS_ERR_OOM, "device allocation failed for the GEMM operands of a placement plan (%s)", why);
+    }
+    SCS_CUDA(cudaMemsetAsync(pl->x1, 0, plane, st));
+    if (pl->x0) SCS_CUDA(cudaMemsetAsync(pl->x0, 0, plane, st));
+    SCS_CUDA(cudaMemsetAsync(pl->s, 0, sbytes, st));
+    pl->prm.stats = pl->stats;
+    int rc;
+    if ((rc = make_u8_tmap(&pl->tm_x1, pl->x1, pl->M_pad, pl->K_pad, BLOCK_M)) != SCS_OK) return rc;
+    if (pl->x0) {
+        if ((rc = make_u8_tmap(&pl->tm_x0, pl->x0, pl->M_pad, pl->K_pad, BLOCK_M)) != SCS_OK) return rc;
+    } else {
+        pl->tm_x0 = pl->tm_x1;
+    }
+    if ((rc = make_u8_tmap(&pl->tm_s, pl->s, pl->N_pad, pl->K_pad, BLOCK_N)) != SCS_OK) return rc;
+    pl->gemm_ready = true;
+    return SCS_OK;
+}
+
 // GEMM operand plane(s) from the packed matrix
 static int expand_operands(Placement* pl, const uint8_t* d_gt, int64_t pitch_bytes, cudaStream_t st) {
+    {
+        const int erc = ensure_gemm_buffers(pl, st);
+        if (erc != SCS_OK) return erc;
+    }
     const int64_t work = pl->M_pad * (pl->K_pad / 16);
     if (pl->K_pad / 16 < 64 && work < (int64_t(1) << 31)) {
         const unsigned grid = unsigned(std::min<int64_t>((work + 255) / 256, int64_t(pl->ctx->sm_count) * 64));
@@ -1647,11 +1465,9 @@ static int set_genotypes_impl(Placement* pl, const uint8_t* d_gt, int64_t pitch_
         }
         return SCS_OK;
     }
-    // GEMM path (or clades not seen yet): the operand plane(s)
-    if (pl->algo != 2) {
-        int rc = expand_operands(pl, d_gt, pitch_bytes, st);
-        if (rc != SCS_OK) return rc;
-    }
+    // GEMM path: the operand plane(s).  Clades not seen yet: a single dataset keeps the packed matrix (below) and builds
+    // the planes at the first run if the masks turn out to need the GEMM; a batch has no such copy and builds them now.
+    bool need_operands = pl->algo == 1 || (pl->algo == 0 && pl->n_groups != 1);
     // interval path (or clades not seen yet): the packed matrix itself -- bound (the caller keeps the buffer
     // alive and unchanged until the run has finished) or copied into the plan
     if (pl->algo != 1 && pl->n_groups == 1) {
@@ -1676,6 +1492,11 @@ static int set_genotypes_impl(Placement* pl, const uint8_t* d_gt, int64_t pitch_
             }
         }
         pl->gt_pitch = pitch_bytes;
+        if (!pl->gt_src) need_operands = true;      // (no room for a copy of the packed matrix)
+    }
+    if (need_operands) {
+        int rc = expand_operands(pl, d_gt, pitch_bytes, st);
+        if (rc != SCS_OK) return rc;
     }
     if (d_row_keep) {
         SCS_CUDA(cudaMemcpyAsync(pl->row_keep, d_row_keep, size_t(pl->n_snv), cudaMemcpyDeviceToDevice, st));
@@ -1912,11 +1733,6 @@ int scs_placement_set_clades(scs_placement* h, const uint32_t* d_bits, int64_t p
     if (pitch_words < (pl->n_cells + 31) / 32) return set_error(SCS_ERR_ARG, "clade mask pitch %lld is smaller than ceil(n_cells/32)", (long long)pitch_words);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int64_t total_rows = int64_t(pl->n_groups) * pl->n_rows;
-    dim3 block(128), grid((pl->K_pad / 4 + 127) / 128, unsigned(std::min<int64_t>(total_rows, 32768)));
-    scs_expand_clades_kernel<<<grid, block, 0, st>>>(d_bits, pitch_words, total_rows, pl->n_rows, pl->N_pad1, pl->n_cells, pl->s, pl->K_pad,
-                                                      pl->mode == MODE_RADIX ? uint32_t(E5M2_ONE) : 1u);
-    pl->launches++;
-    SCS_CUDA(cudaGetLastError());
     if (pl->n_groups == 1) {
         // which algorithm these masks allow is decided on a host copy (tree-shaped masks -> interval path)
         std::vector<uint32_t> hb(size_t(pl->n_rows) * size_t(pitch_words));
@@ -1926,8 +1742,23 @@ int scs_placement_set_clades(scs_placement* h, const uint32_t* d_bits, int64_t p
         int rc = choose_algo(pl, hb.data(), pitch_words, st);
         if (rc != SCS_OK) return rc;
         if (prev == 2 && pl->algo == 1) pl->operands_valid = false;   // genotypes were set for the interval path only
+        pl->h_bits.clear();
+        if (pl->algo == 2 && size_t(pl->M_pad) * pl->N_pad * 2 <= (size_t(1) << 28)) {
+            pl->h_bits.swap(hb);
+            pl->h_bits_pitch = pitch_words;
+        }
     } else {
         pl->algo = 1;
+    }
+    if (pl->algo == 1) {
+        // the GEMM's clade operand (interval plans never read it)
+        const int erc = ensure_gemm_buffers(pl, st);
+        if (erc != SCS_OK) return erc;
+        dim3 block(128), grid((pl->K_pad / 4 + 127) / 128, unsigned(std::min<int64_t>(total_rows, 32768)));
+        scs_expand_clades_kernel<<<grid, block, 0, st>>>(d_bits, pitch_words, total_rows, pl->n_rows, pl->N_pad1, pl->n_cells, pl->s, pl->K_pad,
+                                                          pl->mode == MODE_RADIX ? uint32_t(E5M2_ONE) : 1u);
+        pl->launches++;
+        SCS_CUDA(cudaGetLastError());
     }
     return SCS_OK;
 }
@@ -2053,7 +1884,7 @@ static void choose_pass2_mode(Placement* pl) {
     const char* e = getenv("SCS_PLACE_PASS2");
     if (e && !strcmp(e, "recompute")) return;
     const bool forced = e && !strcmp(e, "cache");
-    if (pl->n_groups != 1 || pl->pair) return;
+    if (pl->n_groups != 1) return;
     if (!forced && pl->K_pad < 2560) return;
     const size_t bytes = size_t(pl->M_pad) * size_t(pl->N_pad) * sizeof(uint32_t);
     size_t free_b = 0, total_b = 0;
@@ -2345,8 +2176,7 @@ int scs_placement_run_batch(scs_placement* h, const double* FP, const double* FN
     const PlaceParams& p = pl->prm;
     const bool cached = pl->pass2_mode == 2;
     cudaEventRecord(pl->ev[0], st);
-    if (pl->pair) launch_place2<PASS_STATS>(pl->grid2, st, pl->tm_x1, pl->tm_s64, p);
-    else launch_place<PASS_STATS>(pl->mode, pl->grid, st, pl->tm_x1, pl->tm_x0, pl->tm_s, p);
+    launch_place<PASS_STATS>(pl->mode, pl->grid, st, pl->tm_x1, pl->tm_x0, pl->tm_s, p);
     cudaEventRecord(pl->ev[1], st);
     scs_merge_stats_kernel<<<unsigned((pl->M_pad + 255) / 256), 256, 0, st>>>(pl->stats, pl->num_parts, pl->M_pad, pl->rowmap,
                                                                               pl->have_row_keep ? pl->row_keep : nullptr, pl->d_gconst_d,
@@ -2356,19 +2186,12 @@ int scs_placement_run_batch(scs_placement* h, const double* FP, const double* FN
         dim3 grid(unsigned((pl->n_rows + BLOCK_N - 1) / BLOCK_N), unsigned(p.num_runs));
         scs_colsum_cached_kernel<<<grid, BLOCK_N, 0, st>>>(pl->cache, pl->rowref_f, pl->d_gconst, p.num_row_blocks, pl->N_pad, pl->n_rows,
                                                            p.run_len, pl->colpart);
-    } else if (pl->pair) {
-        launch_place2<PASS_COLSUM>(pl->grid2, st, pl->tm_x1, pl->tm_s64, p);
     } else {
         launch_place<PASS_COLSUM>(pl->mode, pl->grid, st, pl->tm_x1, pl->tm_x0, pl->tm_s, p);
     }
     cudaEventRecord(pl->ev[3], st);
     double* y = d_soft_weights ? d_soft_weights : pl->y;
     const int64_t total_rows = int64_t(pl->n_groups) * pl->n_rows;
-    if (pl->pair) {
-        // the pair kernel writes 2 * num_runs2 partial rows of the single group
-        const int runs2 = 2 * p.num_runs2;
-        cudaMemcpyAsync(pl->d_group_runs, &runs2, sizeof(int), cudaMemcpyHostToDevice, st);
-    }
     scs_reduce_colpart_kernel<<<unsigned((total_rows + 255) / 256), 256, 0, st>>>(pl->colpart, pl->d_group_runs, total_rows, pl->n_rows,
                                                                                   pl->N_pad1, pl->N_pad, y);
     cudaEventRecord(pl->ev[4], st);
@@ -2415,10 +2238,23 @@ int scs_placement_debug_counts(scs_placement* h, int32_t* counts_host, void* str
         int rc = expand_operands(pl, pl->gt_src, pl->gt_pitch, st);
         if (rc != SCS_OK) return rc;
     }
+    if (pl->algo == 2) {             // ... and neither was the clade operand
+        if (pl->h_bits.empty()) return set_error(SCS_ERR_ARG, "no clade masks kept for the count dump");
+        uint32_t* d_bits = nullptr;
+        const size_t bbytes = pl->h_bits.size() * sizeof(uint32_t);
+        if (cudaMalloc(&d_bits, bbytes) != cudaSuccess) return set_error(SCS_ERR_OOM, "debug dump allocation failed");
+        cudaMemcpyAsync(d_bits, pl->h_bits.data(), bbytes, cudaMemcpyHostToDevice, st);
+        dim3 block(128), grid((pl->K_pad / 4 + 127) / 128, unsigned(std::min<int64_t>(pl->n_rows, 32768)));
+        scs_expand_clades_kernel<<<grid, block, 0, st>>>(d_bits, pl->h_bits_pitch, pl->n_rows, pl->n_rows, pl->N_pad1, pl->n_cells, pl->s, pl->K_pad,
+                                                          pl->mode == MODE_RADIX ? uint32_t(E5M2_ONE) : 1u);
+        pl->launches++;
+        cudaStreamSynchronize(st);
+        cudaFree(d_bits);
+        SCS_CUDA(cudaGetLastError());
+    }
     PlaceParams p = pl->prm;
     p.dump = pl->dump;
-    if (pl->pair) launch_place2<PASS_DUMP>(pl->grid2, st, pl->tm_x1, pl->tm_s64, p);
-    else launch_place<PASS_DUMP>(pl->mode, pl->grid, st, pl->tm_x1, pl->tm_x0, pl->tm_s, p);
+    launch_place<PASS_DUMP>(pl->mode, pl->grid, st, pl->tm_x1, pl->tm_x0, pl->tm_s, p);
     pl->launches++;
     SCS_CUDA(cudaGetLastError());
     std::vector<int> tmp(n);
@@ -2435,6 +2271,7 @@ int scs_placement_debug_stats(scs_placement* h, void* stats_host, void* rowref_h
     Placement* pl = reinterpret_cast<Placement*>(h);
     if (!pl) return set_error(SCS_ERR_ARG, "null argument");
     SCS_CUDA(cudaDeviceSynchronize());
+    if (stats_host && !pl->stats) return set_error(SCS_ERR_ARG, "no pass-1 partials: the plan has not run the GEMM path");
     if (stats_host) SCS_CUDA(cudaMemcpy(stats_host, pl->stats, size_t(pl->num_parts) * pl->M_pad * sizeof(uint2), cudaMemcpyDeviceToHost));
     if (rowref_host) SCS_CUDA(cudaMemcpy(rowref_host, pl->rowref, size_t(pl->M_pad) * sizeof(uint2), cudaMemcpyDeviceToHost));
     return SCS_OK;
@@ -2443,9 +2280,9 @@ int scs_placement_debug_stats(scs_placement* h, void* stats_host, void* rowref_h
 int scs_placement_info(scs_placement* h, int64_t* info, int32_t n) {
     Placement* pl = reinterpret_cast<Placement*>(h);
     if (!pl || !info) return set_error(SCS_ERR_ARG, "null argument");
-    const int64_t v[21] = {pl->M_pad, pl->N_pad, pl->K_pad, pl->prm.num_tasks, pl->prm.run_len, pl->prm.sb_width, pl->pair ? pl->grid2 : pl->grid, pl->launches, pl->prm.num_runs,
-                           pl->pair ? K2_SMEM_TOTAL : (pl->mode == MODE_RADIX ? ModeCfg<MODE_RADIX>::SMEM_TOTAL : ModeCfg<MODE_PLANES>::SMEM_TOTAL),
-                           pl->mode, pl->prm.nchunk, pl->pair ? 1 : 0, pl->n_groups, pl->pass2_mode,
+    const int64_t v[21] = {pl->M_pad, pl->N_pad, pl->K_pad, pl->prm.num_tasks, pl->prm.run_len, pl->prm.sb_width, pl->grid, pl->launches, pl->prm.num_runs,
+                           (pl->mode == MODE_RADIX ? ModeCfg<MODE_RADIX>::SMEM_TOTAL : ModeCfg<MODE_PLANES>::SMEM_TOTAL),
+                           pl->mode, pl->prm.nchunk, 0 /* (was: 2-CTA kernel, removed) */, pl->n_groups, pl->pass2_mode,
                            pl->algo, pl->algo == 3 ? pl->iv5_grid : pl->iv_grid, pl->algo == 3 ? IV5_THREADS : pl->iv_threads,
                            pl->algo == 3 ? int64_t(iv5_smem_bytes(pl->iv5_L, pl->iv5_stride)) : int64_t(pl->iv_smem), pl->algo == 3 ? pl->iv5_ntasks : pl->iv_runs,
                            pl->algo == 3 ? 5 : pl->iv_variant};
