@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--algo", default="auto", choices=["auto", "gemm", "interval"],
                     help="auto: tree-shaped clade masks take the interval path (prefix counts, no GEMM); gemm: force the tcgen05 GEMM")
     ap.add_argument("--no-gemm-leg", action="store_true", help="skip the extra GEMM-path measurement of the same workload")
+    ap.add_argument("--no-percell-leg", action="store_true", help="N = 1: skip the per-cell-FN placement of the same dataset (scs_place_percell)")
     ap.add_argument("--replicates", type=int, default=1250,
                     help="replicate-sweep leg, replicates per GPU and step (BASELINE configs[4]: 10,000 pairs of 100 cells x 10k SNVs "
                          "over 8 GPUs = 1250 per GPU); 0 disables it")
@@ -613,6 +614,26 @@ def main():
                     "max_rel_dev_vs_interval": float((y_g - y_iv).abs().max() / y_iv.abs().max())}
         plan_g.close()
         del plan_g, y_g, y_iv
+    # ---- the same dataset placed with ONE FALSE-NEGATIVE RATE PER CELL (the pd.Series branch of map_mutations_gt, :413-418):
+    # scs_place_percell, float64 prefix sums of per-cell weights.  A side leg -- the reference's command line never takes it.
+    percell = None
+    if world == 1 and not args.no_percell_leg:
+        try:
+            rates = np.clip(np.random.default_rng(5).normal(ds.FN, 0.03, n_cols), 0.01, 0.4)
+            keep = torch.empty(n_snv, dtype=torch.uint8, device=dev)
+            engine.gt_reduce(ctx, ds.packed, pitch, n_snv, n_cols, ds.active, True, keep, stream=ds.stream)
+            y_pc = torch.zeros_like(ds.y_dev)
+            kms = [engine.place_percell(ctx, ds.packed, pitch, n_snv, n_cols, keep, ds.bits, ds.words, ds.FP, rates, y_pc, stream=ds.stream)
+                   for _ in range(4)][1:]
+            engine.place_percell(ctx, ds.packed, pitch, n_snv, n_cols, keep, ds.bits, ds.words, ds.FP, np.full(n_cols, ds.FN), y_pc, stream=ds.stream)
+            percell = {"workload": "the headline dataset (%d cells x %d SNVs), per-cell FN rates ~ N(%.3g, 0.03)" % (n_cells, n_snv, ds.FN),
+                       "kernel_ms": float(np.mean(kms)), "launches_timed": len(kms), "value": placements / (float(np.mean(kms)) / 1e3),
+                       "unit": "placements/s", "kernel": "scs_place_percell_kernel + scs_percell_reduce_kernel (device time; the call also "
+                       "analyses the clade masks on the host and uploads three tables)",
+                       "max_rel_dev_equal_rates_vs_count_kernels": float((y_pc - ds.y_dev).abs().max() / ds.y_dev.abs().max())}
+            del keep, y_pc
+        except Exception as exc:                        # (a side leg: never lose the line over it)
+            percell = {"error": repr(exc)}
     lrt_newton = res.numpy().copy()
     S_cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -764,6 +785,7 @@ def main():
             "gemm_path": gemm_path,
             "weak_scaling": weak,
             "single_test_1k_cells": small,
+            "per_cell_fn": percell,
             "pt_tests": {"per_step": len(W_MAXS), "LR": [float(v) for v in out[:, 0]], "p_value": [float(v) for v in out[:, 3]],
                          "newton_iterations": [int(v) for v in out[:, 6]], "status": [int(v) for v in out[:, 7]]},
             "clocks": sampler.summary() if sampler else None,

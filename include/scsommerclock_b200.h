@@ -6,7 +6,7 @@
  * in place of the NumPy/SciPy bodies of
  *
  *   get_mut_df          run_PT_test.py:27-207    -> scs_vcf_decode*
- *   map_mutations_gt    run_PT_test.py:386-448   -> scs_placement_* / scs_map_mutations
+ *   map_mutations_gt    run_PT_test.py:386-448   -> scs_placement_* / scs_map_mutations / scs_place_percell
  *   _normalize_log_probs run_PT_test.py:368-383  -> fused in the placement epilogue
  *   add_br_weights      run_PT_test.py:451-515   -> scs_branch_weights
  *   get_LRT_poisson     run_PT_test.py:638-700   -> scs_lrt_poisson_batch
@@ -193,6 +193,20 @@ int scs_placement_debug_stats(scs_placement* plan, void* stats, void* rowref);
 int scs_map_mutations(scs_ctx* ctx, const uint8_t* gt, int64_t pitch_bytes, const uint8_t* row_keep,
                       int64_t n_snv, int32_t n_cells, const uint32_t* clade_bits, int64_t pitch_words,
                       int32_t n_rows, double FP, double FN, double* soft_weights);
+
+/* map_mutations_gt with ONE FALSE-NEGATIVE RATE PER CELL -- the `isinstance(FN, pd.Series)` branch of
+ * run_PT_test.py:413-418 (TP_m = S * log(1 - FN_i), FN_m = S * log(FN_i); FP stays a scalar).  d_gt / d_row_keep: the
+ * packed matrix and (optionally, may be NULL) the row flags of scs_gt_reduce on the device; clade_bits: HOST masks
+ * [n_rows][pitch_words] over the matrix columns (the rows of S, zero rows and the final 'FP' row included); FN_cells:
+ * HOST, [n_cells], indexed by matrix column -- columns that belong to no clade (the outgroup) are ignored, every other
+ * rate must lie in (0, 1).  d_soft_weights[n_rows] (device, float64) receives M.sum(axis=0).  The clade masks must be
+ * tree-shaped (a laminar family: every call the reference makes), else SCS_ERR_ARG: the logits are differences of
+ * per-SNV prefix sums of per-cell weights in a depth-first cell order (csrc/scs_place_percell.cuh).  kernel_ms (optional,
+ * may be NULL): device time of the placement + reduction kernels.  Ordered on `stream`, which is synchronised before
+ * the call returns. */
+int scs_place_percell(scs_ctx* ctx, const uint8_t* d_gt, int64_t pitch_bytes, int64_t n_snv, int32_t n_cells,
+                      const uint8_t* d_row_keep, const uint32_t* clade_bits, int64_t pitch_words, int32_t n_rows,
+                      double FP, const double* FN_cells, double* d_soft_weights, float* kernel_ms, void* stream);
 
 /* -------------------------------------------------------------- branch weights
  * add_br_weights (run_PT_test.py:451-515): clade_bits holds the tree's nodes

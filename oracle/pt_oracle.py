@@ -265,7 +265,12 @@ def normalize_log_probs_rows(probs):
 
 
 def placement_log_probs(muts_vals, S, FP, FN):
-    """probs of run_PT_test.py:408-427 for all SNVs at once (float FN)."""
+    """probs of run_PT_test.py:408-427 for all SNVs at once.  ``FN``: a float (:408-412) or one rate per column of
+    ``muts_vals`` / ``S`` (the pd.Series branch :413-418, ``FN_i = FN[muts_in.columns].values``: the same four
+    products with log(1 - FN_i) / log(FN_i) broadcast over the columns of S)."""
+    if not np.isscalar(FN):
+        FN = np.asarray(FN, dtype=np.float64)
+        assert FN.shape == (S.shape[1],), "one FN rate per cell"
     S_inv = 1 - S
     nans = np.isnan(muts_vals)
     muts = np.where(nans, np.nan, muts_vals.astype(bool).astype(float))        # :403
@@ -354,11 +359,19 @@ def map_mutations_gt_interval(muts_vals, S, FP, FN, chunk=2048):
     a1 = np.log(1 - FN) - np.log(FP)
     a0 = np.log(FN) - np.log(1 - FP)
     soft = np.zeros(S.shape[0])
+    percell = not np.isscalar(FN)          # the pd.Series branch (:413-418): prefix sums of per-cell weights instead of counts
     for s in range(0, muts_vals.shape[0], chunk):
         v = muts_vals[s:s + chunk][:, perm]
         obs = ~np.isnan(v)
         mut = obs & (np.nan_to_num(v) != 0)
         wt = obs & ~mut
+        if percell:
+            z = np.zeros((v.shape[0], 1))
+            pw = np.concatenate([z, np.cumsum(mut * a1[perm][None, :] + wt * a0[perm][None, :], axis=1)], axis=1)
+            logit = pw[:, hi] - pw[:, lo]
+            M = np.exp(logit - logit.max(axis=1, keepdims=True))
+            soft += (M / M.sum(axis=1, keepdims=True)).sum(axis=0)
+            continue
         z = np.zeros((v.shape[0], 1), dtype=np.int64)
         p1 = np.concatenate([z, np.cumsum(mut, axis=1)], axis=1)
         p0 = np.concatenate([z, np.cumsum(wt, axis=1)], axis=1)

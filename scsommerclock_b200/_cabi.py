@@ -53,6 +53,8 @@ _SIGNATURES = {
     "scs_placement_debug_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "scs_map_mutations": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
                                     C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_void_p]),
+    "scs_place_percell": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                    C.c_double, C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_void_p]),
     "scs_vcf_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]),
     "scs_vcf_destroy": (C.c_int, [C.c_void_p]),
     "scs_vcf_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),

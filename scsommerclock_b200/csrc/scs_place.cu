@@ -1000,6 +1000,7 @@ __global__ void scs_reduce_colpart_kernel(const float* __restrict__ colpart, con
 #include "scs_place_interval.cuh"
 #include "scs_place_iv4.cuh"
 #include "scs_place_iv5.cuh"
+#include "scs_place_percell.cuh"
 namespace scs {
 
 // ---------------------------------------------------------------- host side
@@ -2311,6 +2312,109 @@ int scs_placement_prepare_time(scs_placement* h, float* ms) {
 const void* scs_placement_device_result(scs_placement* h) {
     Placement* pl = reinterpret_cast<Placement*>(h);
     return pl ? pl->y : nullptr;
+}
+
+// map_mutations_gt with one false-negative rate per cell (the pd.Series branch, run_PT_test.py:413-418): scs_place_percell.cuh.
+int scs_place_percell(scs_ctx* ctx, const uint8_t* d_gt, int64_t pitch_bytes, int64_t n_snv, int32_t n_cells, const uint8_t* d_row_keep,
+                      const uint32_t* clade_bits, int64_t pitch_words, int32_t n_rows, double FP, const double* FN_cells,
+                      double* d_soft_weights, float* kernel_ms, void* stream) {
+    if (!ctx || !clade_bits || !FN_cells || !d_soft_weights || (n_snv > 0 && !d_gt)) return set_error(SCS_ERR_ARG, "null argument");
+    if (n_snv < 0 || n_cells <= 0 || n_cells > 65535 || n_rows <= 0) return set_error(SCS_ERR_ARG, "bad problem size");
+    if (pitch_words < (n_cells + 31) / 32) return set_error(SCS_ERR_ARG, "clade mask pitch %lld is smaller than ceil(n_cells/32)", (long long)pitch_words);
+    if (pitch_bytes < (n_cells + 3) / 4) return set_error(SCS_ERR_ARG, "genotype row pitch %lld is smaller than ceil(n_cells/4)", (long long)pitch_bytes);
+    if ((pitch_bytes & 3) || (reinterpret_cast<uintptr_t>(d_gt) & 3)) return set_error(SCS_ERR_ARG, "packed genotype rows must be 4-byte aligned (pitch %lld)", (long long)pitch_bytes);
+    if (!(FP > 0.0 && FP < 1.0)) return set_error(SCS_ERR_ARG, "FP must lie in (0, 1)");
+    SCS_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    std::vector<uint16_t> perm;
+    std::vector<uint32_t> lohi;
+    if (!clade_intervals(clade_bits, pitch_words, n_rows, n_cells, perm, lohi))
+        return set_error(SCS_ERR_ARG, "per-cell rates need tree-shaped clade masks (the rows are not a laminar family)");
+    // cells that belong to no clade (the outgroup column) carry no weight; every other cell needs a rate in (0, 1)
+    const int words = (n_cells + 31) / 32;
+    std::vector<uint32_t> covered(size_t(words), 0u);
+    for (int r = 0; r < n_rows; ++r)
+        for (int w = 0; w < words; ++w) covered[size_t(w)] |= clade_bits[size_t(r) * pitch_words + w];
+    const double l2e = 1.4426950408889634074;
+    std::vector<double2> wv(static_cast<size_t>(n_cells));
+    for (int k = 0; k < n_cells; ++k) {
+        const int c = perm[size_t(k)];
+        if (!((covered[size_t(c >> 5)] >> (c & 31)) & 1u)) {
+            wv[size_t(k)] = make_double2(0.0, 0.0);
+            continue;
+        }
+        const double fn = FN_cells[c];
+        if (!(fn > 0.0 && fn < 1.0)) return set_error(SCS_ERR_ARG, "FN of cell column %d must lie in (0, 1)", c);
+        wv[size_t(k)] = make_double2((std::log(1.0 - fn) - std::log(FP)) * l2e, (std::log(fn) - std::log(1.0 - FP)) * l2e);
+    }
+    // launch shape: a thread per ~8 clade rows / cells, 64..1024 threads; accumulators and cell order in shared memory when they fit
+    int T = std::max((n_rows + 7) / 8, (n_cells + 7) / 8);
+    T = std::min(1024, std::max(64, (T + 31) / 32 * 32));
+    int max_smem = 0;
+    SCS_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    bool acc_smem = true, perm_smem = true;
+    if (percell_smem_bytes(n_cells, n_rows, acc_smem, perm_smem) > size_t(max_smem)) perm_smem = false;
+    if (percell_smem_bytes(n_cells, n_rows, acc_smem, perm_smem) > size_t(max_smem)) acc_smem = false;
+    const size_t smem = percell_smem_bytes(n_cells, n_rows, acc_smem, perm_smem);
+    if (smem > size_t(max_smem)) return set_error(SCS_ERR_ARG, "per-cell placement: %d cells do not fit shared memory", n_cells);
+    SCS_CUDA(cudaFuncSetAttribute(scs_place_percell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    int per_sm = 0;
+    SCS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scs_place_percell_kernel, T, smem));
+    per_sm = std::max(1, per_sm);
+    const int grid = int(std::max<int64_t>(1, std::min<int64_t>(n_snv, int64_t(ctx->sm_count) * per_sm)));
+    // workspace: tables + per-CTA partial sums, one allocation
+    const size_t off_lohi = (size_t(n_cells) * sizeof(uint16_t) + 15) & ~size_t(15);
+    const size_t off_w = off_lohi + ((size_t(n_rows) * sizeof(uint32_t) + 15) & ~size_t(15));
+    const size_t off_part = off_w + size_t(n_cells) * sizeof(double2);
+    const size_t total = off_part + size_t(grid) * n_rows * sizeof(double);
+    uint8_t* ws = nullptr;
+    if (cudaMalloc(&ws, total) != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(SCS_ERR_OOM, "device allocation of %zu bytes failed", total);
+    }
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int rc = SCS_OK;
+    do {
+        if (cudaMemcpyAsync(ws, perm.data(), size_t(n_cells) * sizeof(uint16_t), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaMemcpyAsync(ws + off_lohi, lohi.data(), size_t(n_rows) * sizeof(uint32_t), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaMemcpyAsync(ws + off_w, wv.data(), size_t(n_cells) * sizeof(double2), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaMemsetAsync(ws + off_part, 0, size_t(grid) * n_rows * sizeof(double), st) != cudaSuccess) {
+            rc = set_error(SCS_ERR_CUDA, "per-cell placement set-up failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        PercellParams q;
+        q.gt = d_gt;
+        q.pitch = pitch_bytes;
+        q.n_snv = n_snv;
+        q.n_cells = n_cells;
+        q.n_rows = n_rows;
+        q.row_words = (n_cells + 15) / 16;
+        q.perm = reinterpret_cast<const uint16_t*>(ws);
+        q.lohi = reinterpret_cast<const uint32_t*>(ws + off_lohi);
+        q.w = reinterpret_cast<const double2*>(ws + off_w);
+        q.row_keep = d_row_keep;
+        q.part = reinterpret_cast<double*>(ws + off_part);
+        q.acc_smem = acc_smem ? 1 : 0;
+        q.perm_smem = perm_smem ? 1 : 0;
+        if (kernel_ms) {
+            cudaEventCreate(&ev0);
+            cudaEventCreate(&ev1);
+            cudaEventRecord(ev0, st);
+        }
+        if (n_snv > 0) scs_place_percell_kernel<<<grid, T, smem, st>>>(q);
+        scs_percell_reduce_kernel<<<(n_rows + 255) / 256, 256, 0, st>>>(q.part, grid, n_rows, d_soft_weights);
+        if (kernel_ms) cudaEventRecord(ev1, st);
+        const cudaError_t e = cudaStreamSynchronize(st);           // the workspace is freed below
+        if (e != cudaSuccess) {
+            rc = set_error(SCS_ERR_CUDA, "per-cell placement failed: %s", cudaGetErrorString(e));
+            break;
+        }
+        if (kernel_ms) cudaEventElapsedTime(kernel_ms, ev0, ev1);
+    } while (0);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    cudaFree(ws);
+    return rc;
 }
 
 }  // extern "C"

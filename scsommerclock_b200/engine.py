@@ -250,6 +250,26 @@ def map_mutations(ctx, packed, pitch, clade_bits, words, n_cells, FP, FN, row_ke
     return out
 
 
+def place_percell(ctx, d_gt, pitch, n_snv, n_cells, d_row_keep, clade_bits, words, FP, FN_cells, d_soft, stream=None):
+    """scs_place_percell: map_mutations_gt with one false-negative rate per cell (the pd.Series branch of
+    run_PT_test.py:413-418).  ``d_gt`` / ``d_row_keep`` / ``d_soft`` are device buffers (torch tensors or raw
+    pointers; ``d_row_keep`` may be None), ``clade_bits`` and ``FN_cells`` (one rate per matrix column) host arrays.
+    Returns the device time of the kernels in ms; ``d_soft`` holds the soft weights when the call returns."""
+    clade_bits = np.ascontiguousarray(clade_bits, dtype=np.uint32)
+    FN_cells = np.ascontiguousarray(FN_cells, dtype=np.float64)
+    if FN_cells.shape != (int(n_cells),):
+        raise ValueError("FN_cells must hold one rate per matrix column (%d), got shape %r" % (n_cells, FN_cells.shape))
+    if stream is None and hasattr(d_gt, "device"):
+        import torch
+        stream = torch.cuda.current_stream(d_gt.device)
+    ms = C.c_float()
+    check(lib().scs_place_percell(ctx._h, _dev_ptr(d_gt), int(pitch), int(n_snv), int(n_cells),
+                                  _dev_ptr(d_row_keep) if d_row_keep is not None else None, ptr(clade_bits), int(words),
+                                  int(clade_bits.shape[0]), float(FP), ptr(FN_cells), _dev_ptr(d_soft), C.byref(ms),
+                                  _stream_handle(stream)))
+    return float(ms.value)
+
+
 class DecodedVcf:
     """Device-resident result of scs_vcf_decode (get_mut_df, run_PT_test.py:27-207)."""
 

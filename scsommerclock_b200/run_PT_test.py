@@ -487,6 +487,56 @@ def _place_on_tree(ctx, muts, tree, outg, FP, FN):
             "weights": {}}
 
 
+def _per_cell_rates(FN, columns, active):
+    """``FN[muts_in.columns].values`` of run_PT_test.py:414 for a pd.Series / dict keyed by sample name, or a plain
+    sequence with one rate per matrix column; columns outside the placement (the outgroup) may be absent."""
+    out = np.full(len(columns), np.nan)
+    if hasattr(FN, "keys"):                                  # pd.Series, dict
+        for i, c in enumerate(columns):
+            if c in FN.keys():
+                out[i] = float(FN[c])
+            elif active[i]:
+                raise KeyError("no FN rate for cell %r" % (c,))
+    else:
+        arr = np.asarray(FN, dtype=np.float64).ravel()
+        n_act = int(np.sum(active))
+        if arr.size == len(columns):
+            out[:] = arr
+        elif arr.size == n_act:                              # rates for the placed cells only, in column order
+            out[np.asarray(active, dtype=bool)] = arr
+        else:
+            raise ValueError("FN holds %d rates for %d cells" % (arr.size, n_act))
+    return out
+
+
+def _place_on_tree_percell(ctx, muts, tree, outg, FP, FN):
+    """map_mutations_gt's per-cell-FN branch (:413-418) on the device: row filter (:350-353) by scs_gt_reduce, placement
+    by scs_place_percell.  Under row sharding the soft weights are summed over the ranks like the scalar path's."""
+    import torch
+    columns = list(muts.columns)
+    active = np.array([c != outg for c in columns], dtype=np.uint8)
+    has_outg = outg in columns
+    n_snv, n_cols = muts.shape
+    dev = torch.device("cuda", ctx.device)
+    cur = torch.cuda.current_stream(dev)
+    bits, words, nodes = _clade_bits(tree, columns, active)
+    rates = _per_cell_rates(FN, columns, active)
+    y = torch.zeros(bits.shape[0], dtype=torch.float64, device=dev)
+    n_kept = 0
+    if n_snv > 0:
+        d_gt = muts._dec.device_ptr()
+        keep = torch.empty(n_snv, dtype=torch.uint8, device=dev)
+        n_kept, _ = engine.gt_reduce(ctx, d_gt, muts._dec.pitch, n_snv, n_cols, active, has_outg, keep, stream=cur)
+        engine.place_percell(ctx, d_gt, muts._dec.pitch, n_snv, n_cols, keep, bits, words, FP, np.where(active.astype(bool), rates, 0.5), y, stream=cur)     # (columns outside the tree carry no weight; a NaN rate of a placed cell is refused by the library)
+    if getattr(muts, "row_sharded", False):
+        from . import sharding
+        t = torch.cat([torch.tensor([float(n_kept)], dtype=torch.float64, device=dev), y])
+        sharding.allreduce_soft_weights(t)
+        n_kept = int(round(t[0].item()))
+        y = t[1:]
+    return {"soft": y.cpu().numpy(), "n_muts": n_kept, "bits": bits, "words": words, "columns": columns}
+
+
 def _apply_placement(tree, st):
     for i, node in enumerate(tree.iter_descendants()):                          # :443-445
         node.mut_no_soft = st["soft"][i]
@@ -497,11 +547,14 @@ def map_mutations_gt(tree, muts_in, FP, FN):
     """run_PT_test.py:386-448 for callers that drive the steps themselves: places
     every SNV of ``muts_in`` (a GenotypeMatrix) on ``tree`` and sets
     ``node.mut_no_soft`` / ``node.dist``."""
-    if not np.isscalar(FN) or not np.isscalar(FP):
-        # the reference also accepts a pd.Series of per-cell FN rates (:413-418); nothing on its command-line path passes
-        # one (get_gt_tree always hands over a float), and with per-cell weights the counts C1 / C0 no longer determine the
-        # logits, i.e. it is a different kernel.  Not built -- said loudly instead of averaging the rates behind the caller's back.
-        raise NotImplementedError("per-cell FN / FP rates (the pd.Series branch of run_PT_test.py:413-418) are not supported; pass floats")
+    if not np.isscalar(FP):
+        raise TypeError("FP is one rate for all cells (run_PT_test.py:409-418 has no per-cell FP branch)")
+    if not np.isscalar(FN):
+        # -- Taking different FN value per cell into account -- (:413-418): its own kernel (csrc/scs_place_percell.cuh),
+        # the logits are prefix sums of per-cell weights, not functions of two integer counts
+        st = _place_on_tree_percell(muts_in.ctx, muts_in, tree, "healthycell", FP, FN)
+        _apply_placement(tree, st)
+        return PlacementResult(st["n_muts"], [n.name for n in tree.iter_descendants()] + ["FP"], st["soft"])
     st = _place_on_tree(muts_in.ctx, muts_in, tree, "healthycell", FP, FN)
     _apply_placement(tree, st)
     return PlacementResult(st["n_muts"], [n.name for n in tree.iter_descendants()] + ["FP"], st["soft"])

@@ -393,8 +393,59 @@ def make_lrt_sweep(ref, n_problems=240, seed=2024):
     shutil.rmtree(tmp, ignore_errors=True)
 
 
+def make_percell_fn(ref, seed=77):
+    """The pd.Series branch of the reference's map_mutations_gt (:413-418): one false-negative rate per cell.  Nothing on
+    the reference's command-line path passes a Series (get_gt_tree hands over a float), so the branch is driven directly:
+    the reference's own get_mut_df and read_tree, the outgroup / empty-row filter of get_gt_tree (:350-353), then ITS
+    map_mutations_gt with random per-cell rates.  One file, percell_fn.npz, keys prefixed by the case name."""
+    import pandas as pd
+    rng = np.random.default_rng(seed)
+    d = os.path.join(HERE, "data")
+    cases = [("syn_a", "syn_a.vcf.gz", "syn_a.raxml.bestTree"), ("syn_c", "syn_c.vcf.gz", "syn_c.newick"),
+             ("syn_b", "syn_b.vcf.gz", "syn_b.raxml.bestTree"),
+             ("example_clock", "data_simulated_clock.vcf.gz", "data_simulated_clock.raxml.bestTree")]
+    out = {"cases": np.array([c[0] for c in cases])}
+    for name, vcf, tree_file in cases:
+        call_data = ref.get_mut_df(os.path.join(d, vcf), "", "")
+        muts = call_data[0]
+        tree, outg, FP, FN = ref.read_tree(os.path.join(d, tree_file), muts.columns.values)
+        FP = max(FP, ref.LAMBDA_MIN)
+        if outg in muts.columns:                                            # :350-353
+            muts_red = muts.drop(outg, axis=1)
+            muts_red = muts_red[muts_red.sum(axis=1) > 0]
+        else:
+            muts_red = muts
+        lo, hi = (0.02, 0.45) if name != "syn_b" else (1e-4, 0.9)           # syn_b: rates spread over four decades
+        rates = np.exp(rng.uniform(np.log(lo), np.log(hi), muts_red.shape[1]))
+        FN_series = pd.Series(rates, index=muts_red.columns)
+        M = ref.map_mutations_gt(tree, muts_red, FP, FN_series)
+        out[name + "_vcf"] = np.array(os.path.join("tests", "golden", "data", vcf))
+        out[name + "_tree"] = np.array(os.path.join("tests", "golden", "data", tree_file))
+        out[name + "_cols"] = np.array(list(muts_red.columns))
+        out[name + "_all_cols"] = np.array(list(muts.columns))
+        out[name + "_codes"] = codes_of(muts_red)                           # what map_mutations_gt was given
+        red_cols = list(muts_red.columns)
+        S = np.zeros((len(M.columns), len(red_cols)), dtype=np.uint8)
+        for i, node in enumerate(tree.iter_descendants()):
+            for leaf in node.name.split("+"):
+                S[i, red_cols.index(leaf)] = 1
+        out[name + "_S"] = S
+        out[name + "_FN_cells"] = rates
+        out[name + "_FP"] = np.array(FP)
+        out[name + "_soft"] = M.values.sum(axis=0)
+        out[name + "_M_head"] = M.values[:32].copy()
+        out[name + "_n_muts"] = np.array(M.shape[0])
+        out[name + "_node_names"] = np.array(list(M.columns))
+        print(f"  percell {name}: {M.shape[0]} SNVs x {M.shape[1]} rows, FN in [{rates.min():.4g}, {rates.max():.4g}]", flush=True)
+    out["meta"] = np.array(json.dumps(dict(META, case="percell_fn", seed=seed)))
+    np.savez_compressed(os.path.join(HERE, "percell_fn.npz"), **out)
+
+
 def main():
     ref = load_reference()
+    if "--only-percell" in sys.argv:
+        make_percell_fn(ref)
+        return
     if "--only-lrt-sweep" in sys.argv:
         make_lrt_sweep(ref)
         return
@@ -463,6 +514,7 @@ def main():
         make_scite_and_path_cases(ref)
     if "--skip-lrt-sweep" not in sys.argv:
         make_lrt_sweep(ref)
+    make_percell_fn(ref)
     print("golden fixtures written to", HERE)
 
 

@@ -1355,3 +1355,112 @@ def test_two_ranks_row_sharded_dataset_and_replicate_sweep(ctx, tmp_path):
     assert pairs == list(range(len(names)))                      # every pair handled by exactly one rank
     for a, b in zip(outs, ref_outs):
         _assert_same_tsv(a, b, 1e-6)
+
+
+# ------------------------------------------------- per-cell false-negative rates
+def test_per_cell_fn_product_path_on_golden_cases(ctx):
+    """map_mutations_gt with a pd.Series of per-cell FN rates (run_PT_test.py:413-418) through the product mirror -- VCF
+    decode, read_tree, row filter, scs_place_percell -- against what the unmodified reference returned (percell_fn.npz).
+    Tolerance: Y_TOL like every soft-weight comparison (fp32 softmax terms on float64 logit differences)."""
+    import pandas as pd
+    from conftest import REPO
+    pc = np.load(golden_path("percell_fn"), allow_pickle=False)
+    for name in pc["cases"]:
+        name = str(name)
+        muts, _, _ = P.get_mut_df(os.path.join(REPO, str(pc[name + "_vcf"])), "", "", ctx=ctx)
+        assert list(muts.columns) == list(pc[name + "_all_cols"])
+        tree, outg, FP0, FN0 = P.read_tree(os.path.join(REPO, str(pc[name + "_tree"])), muts.columns)
+        FP, rates, cols = float(pc[name + "_FP"]), pc[name + "_FN_cells"], [str(c) for c in pc[name + "_cols"]]
+        want = pc[name + "_soft"]
+        M = P.map_mutations_gt(tree, muts, FP, pd.Series(rates, index=cols))
+        assert M.shape == (int(pc[name + "_n_muts"]), want.size)
+        assert M.columns == [str(c) for c in pc[name + "_node_names"]]
+        assert_soft_close(M.soft, want)
+        for node, y in zip(tree.iter_descendants(), want):                   # :443-445
+            assert abs(node.dist - y) <= Y_TOL * max(1.0, abs(y)) and node.mut_no_soft == node.dist
+        # the same rates as a dict and as a plain array over the placed cells
+        assert np.array_equal(P.map_mutations_gt(tree, muts, FP, dict(zip(cols, rates))).soft, M.soft)
+        assert np.array_equal(P.map_mutations_gt(tree, muts, FP, rates).soft, M.soft)
+        with pytest.raises(KeyError):
+            P.map_mutations_gt(tree, muts, FP, dict(zip(cols[1:], rates[1:])))
+        with pytest.raises(TypeError):
+            P.map_mutations_gt(tree, muts, rates, 0.1)
+
+
+@pytest.mark.parametrize("n_snv,n_cells", [(1, 2), (127, 3), (300, 50), (1000, 200), (700, 513), (400, 1100), (150, 4200), (60, 10000),
+                                            (40, 12500), (30, 13500), (24, 16000)])
+def test_per_cell_fn_kernel_matches_oracle(ctx, monkeypatch, n_snv, n_cells):
+    """scs_place_percell against the oracle's float64 prefix-sum form (pinned to the reference by
+    test_per_cell_fn_against_the_reference, and to the dense form below 600 cells) on shuffled random trees: 64..1024
+    threads per CTA, accumulators / cell order in shared memory (up to 12,700 / 14,300 cells) and in global memory beyond,
+    rows dropped by the filter, rates spread over three decades.  With equal rates it must agree with the count kernels."""
+    import torch
+    codes, S = shuffled_problem(n_snv, n_cells, seed=5 * n_snv + n_cells)
+    rng = np.random.default_rng(n_cells)
+    keep = np.ones(n_snv, dtype=np.uint8)
+    if n_snv > 4:
+        keep[::5] = 0
+    rates = np.exp(rng.uniform(np.log(5e-4), np.log(0.6), n_cells))
+    packed, pitch = engine.pack_genotypes(codes)
+    bits, words = engine.pack_clades(S)
+    dev = torch.device("cuda", ctx.device)
+    d_gt = torch.from_numpy(packed).to(dev)
+    d_keep = torch.from_numpy(keep).to(dev)
+    y = torch.zeros(S.shape[0], dtype=torch.float64, device=dev)
+    muts = np.where(codes == 3, np.nan, codes.astype(float))[keep.astype(bool)]
+    ms = engine.place_percell(ctx, d_gt, pitch, n_snv, n_cells, d_keep, bits, words, 0.01, rates, y)
+    got = y.cpu().numpy()
+    assert ms >= 0.0
+    assert_soft_close(got, O.map_mutations_gt_interval(muts, S.astype(float), 0.01, rates))
+    if n_cells <= 600:
+        assert_soft_close(got, O.map_mutations_gt(muts, S.astype(float), 0.01, rates))
+    assert abs(got.sum() - keep.sum()) <= 5e-6 * max(1, keep.sum())          # every kept SNV's row of M sums to 1
+    engine.place_percell(ctx, d_gt, pitch, n_snv, n_cells, d_keep, bits, words, 0.01, rates, y)
+    assert np.array_equal(y.cpu().numpy(), got)                               # fixed reduction order
+    # no row flags: every row placed
+    engine.place_percell(ctx, d_gt, pitch, n_snv, n_cells, None, bits, words, 0.01, rates, y)
+    assert abs(y.sum().item() - n_snv) <= 5e-6 * n_snv
+    # equal rates: the scalar branch, i.e. the count kernels
+    engine.place_percell(ctx, d_gt, pitch, n_snv, n_cells, d_keep, bits, words, 0.02, np.full(n_cells, 0.15), y)
+    pl = engine.Placement(ctx, n_snv, n_cells, S.shape[0])
+    pl.set_clades_host(bits, words)
+    pl.set_genotypes_host(packed, pitch, keep)
+    assert_soft_close(y.cpu().numpy(), pl.run_host(0.02, 0.15))
+    pl.close()
+
+
+def test_per_cell_fn_argument_checks(ctx):
+    import torch
+    codes, S = shuffled_problem(50, 20, seed=3)
+    packed, pitch = engine.pack_genotypes(codes)
+    bits, words = engine.pack_clades(S)
+    dev = torch.device("cuda", ctx.device)
+    d_gt = torch.from_numpy(packed).to(dev)
+    y = torch.zeros(S.shape[0], dtype=torch.float64, device=dev)
+    rates = np.full(20, 0.1)
+    for bad in (0.0, 1.0, -0.1, np.nan):
+        r = rates.copy()
+        r[7] = bad
+        with pytest.raises(engine._cabi.ScsError):
+            engine.place_percell(ctx, d_gt, pitch, 50, 20, None, bits, words, 0.01, r, y)
+    with pytest.raises(engine._cabi.ScsError):
+        engine.place_percell(ctx, d_gt, pitch, 50, 20, None, bits, words, 1.5, rates, y)
+    with pytest.raises(ValueError):
+        engine.place_percell(ctx, d_gt, pitch, 50, 20, None, bits, words, 0.01, rates[:-1], y)
+    crossing = S.copy()
+    crossing[0] = 0
+    crossing[0, [0, 1]] = 1
+    crossing[1] = 0
+    crossing[1, [1, 2]] = 1                                                   # two rows that overlap without nesting
+    cb, cw = engine.pack_clades(crossing)
+    with pytest.raises(engine._cabi.ScsError, match="laminar"):
+        engine.place_percell(ctx, d_gt, pitch, 50, 20, None, cb, cw, 0.01, rates, y)
+    # a column outside every clade (the outgroup) needs no rate
+    S2 = np.concatenate([S, np.zeros((S.shape[0], 1), dtype=S.dtype)], axis=1)
+    codes2 = np.concatenate([codes, np.full((50, 1), 1, dtype=codes.dtype)], axis=1)
+    p2, pitch2 = engine.pack_genotypes(codes2)
+    b2, w2 = engine.pack_clades(S2)
+    engine.place_percell(ctx, torch.from_numpy(p2).to(dev), pitch2, 50, 21, None, b2, w2, 0.01, np.append(rates, np.nan), y)
+    want = y.cpu().numpy().copy()
+    engine.place_percell(ctx, d_gt, pitch, 50, 20, None, bits, words, 0.01, rates, y)
+    np.testing.assert_allclose(y.cpu().numpy(), want, rtol=1e-12, atol=1e-12)

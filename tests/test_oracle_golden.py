@@ -152,6 +152,31 @@ def test_interval_form_of_the_placement_oracle():
     assert O.clade_intervals(bad) is None
 
 
+def percell_case(pc, name):
+    """What the reference's map_mutations_gt was given in one case of percell_fn.npz: the filtered {0,1,2,NaN} matrix, S,
+    FP and the per-cell rates."""
+    codes = pc[name + "_codes"]
+    muts = np.where(codes == 3, np.nan, codes.astype(float))
+    return muts, pc[name + "_S"].astype(float), float(pc[name + "_FP"]), pc[name + "_FN_cells"]
+
+
+def test_per_cell_fn_against_the_reference():
+    """The pd.Series branch of map_mutations_gt (run_PT_test.py:413-418): the oracle's dense and prefix-sum forms against
+    what the unmodified reference returned for random per-cell rates (percell_fn.npz, make_golden.make_percell_fn)."""
+    pc = np.load(golden_path("percell_fn"), allow_pickle=False)
+    for name in pc["cases"]:
+        name = str(name)
+        muts, S, FP, rates = percell_case(pc, name)
+        assert muts.shape[0] == int(pc[name + "_n_muts"])
+        soft, M = O.map_mutations_gt(muts, S, FP, rates, return_M=True)
+        np.testing.assert_allclose(soft, pc[name + "_soft"], rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(M[:32], pc[name + "_M_head"], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(O.map_mutations_gt_interval(muts, S, FP, rates), pc[name + "_soft"], rtol=1e-9, atol=1e-9)
+        # equal rates: the float branch
+        same = np.full(S.shape[1], 0.2)
+        np.testing.assert_allclose(O.map_mutations_gt(muts, S, FP, same), O.map_mutations_gt(muts, S, FP, 0.2), rtol=1e-12, atol=1e-12)
+
+
 def test_reference_copy_reproduces_a_fixture():
     """oracle/_ref (the byte-for-byte copy of the reference that bench.py's CPU arms run) gives the fixture's TSV and soft
     weights -- the arm times the same module that made the golden vectors."""
