@@ -2347,6 +2347,15 @@ int scs_place_percell(scs_ctx* ctx, const uint8_t* d_gt, int64_t pitch_bytes, in
         if (!(fn > 0.0 && fn < 1.0)) return set_error(SCS_ERR_ARG, "FN of cell column %d must lie in (0, 1)", c);
         wv[size_t(k)] = make_double2((std::log(1.0 - fn) - std::log(FP)) * l2e, (std::log(fn) - std::log(1.0 - FP)) * l2e);
     }
+    // clade rows sorted by interval (neighbouring lanes then read neighbouring prefix sums); slot -> caller's row
+    std::vector<int> slot_row(static_cast<size_t>(n_rows));
+    std::iota(slot_row.begin(), slot_row.end(), 0);
+    std::stable_sort(slot_row.begin(), slot_row.end(), [&](int a, int b) {
+        const uint32_t la = lohi[size_t(a)], lb = lohi[size_t(b)];
+        return (la & 0xffffu) != (lb & 0xffffu) ? (la & 0xffffu) < (lb & 0xffffu) : (la >> 16) < (lb >> 16);
+    });
+    std::vector<uint32_t> lohi_sorted(static_cast<size_t>(n_rows));
+    for (int b = 0; b < n_rows; ++b) lohi_sorted[size_t(b)] = lohi[size_t(slot_row[size_t(b)])];
     // launch shape: a thread per ~8 clade rows / cells, 64..1024 threads; accumulators and cell order in shared memory when they fit
     int T = std::max((n_rows + 7) / 8, (n_cells + 7) / 8);
     T = std::min(1024, std::max(64, (T + 31) / 32 * 32));
@@ -2365,7 +2374,8 @@ int scs_place_percell(scs_ctx* ctx, const uint8_t* d_gt, int64_t pitch_bytes, in
     // workspace: tables + per-CTA partial sums, one allocation
     const size_t off_lohi = (size_t(n_cells) * sizeof(uint16_t) + 15) & ~size_t(15);
     const size_t off_w = off_lohi + ((size_t(n_rows) * sizeof(uint32_t) + 15) & ~size_t(15));
-    const size_t off_part = off_w + size_t(n_cells) * sizeof(double2);
+    const size_t off_slot = off_w + size_t(n_cells) * sizeof(double2);
+    const size_t off_part = off_slot + ((size_t(n_rows) * sizeof(int) + 15) & ~size_t(15));
     const size_t total = off_part + size_t(grid) * n_rows * sizeof(double);
     uint8_t* ws = nullptr;
     if (cudaMalloc(&ws, total) != cudaSuccess) {
@@ -2376,7 +2386,8 @@ int scs_place_percell(scs_ctx* ctx, const uint8_t* d_gt, int64_t pitch_bytes, in
     int rc = SCS_OK;
     do {
         if (cudaMemcpyAsync(ws, perm.data(), size_t(n_cells) * sizeof(uint16_t), cudaMemcpyHostToDevice, st) != cudaSuccess ||
-            cudaMemcpyAsync(ws + off_lohi, lohi.data(), size_t(n_rows) * sizeof(uint32_t), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaMemcpyAsync(ws + off_lohi, lohi_sorted.data(), size_t(n_rows) * sizeof(uint32_t), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaMemcpyAsync(ws + off_slot, slot_row.data(), size_t(n_rows) * sizeof(int), cudaMemcpyHostToDevice, st) != cudaSuccess ||
             cudaMemcpyAsync(ws + off_w, wv.data(), size_t(n_cells) * sizeof(double2), cudaMemcpyHostToDevice, st) != cudaSuccess ||
             cudaMemsetAsync(ws + off_part, 0, size_t(grid) * n_rows * sizeof(double), st) != cudaSuccess) {
             rc = set_error(SCS_ERR_CUDA, "per-cell placement set-up failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -2402,7 +2413,7 @@ int scs_place_percell(scs_ctx* ctx, const uint8_t* d_gt, int64_t pitch_bytes, in
             cudaEventRecord(ev0, st);
         }
         if (n_snv > 0) scs_place_percell_kernel<<<grid, T, smem, st>>>(q);
-        scs_percell_reduce_kernel<<<(n_rows + 255) / 256, 256, 0, st>>>(q.part, grid, n_rows, d_soft_weights);
+        scs_percell_reduce_kernel<<<(n_rows + 255) / 256, 256, 0, st>>>(q.part, grid, n_rows, reinterpret_cast<const int*>(ws + off_slot), d_soft_weights);
         if (kernel_ms) cudaEventRecord(ev1, st);
         const cudaError_t e = cudaStreamSynchronize(st);           // the workspace is freed below
         if (e != cudaSuccess) {

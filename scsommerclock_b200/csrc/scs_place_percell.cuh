@@ -12,8 +12,10 @@
 //
 //   per SNV row, one CTA:  row bytes -> shared memory (coalesced);  every thread sums the weights of its contiguous block of
 //   depth-first positions, a block-wide scan turns them into prefix sums P[0..n] (float64 in shared memory: the sums reach
-//   ~10^4 log2 units at 10,000 cells and the logits are differences of them);  sweep 1 over the clade rows keeps a running
-//   (max, sum of 2^(d - max)) per thread, combined over the block;  sweep 2 adds 2^(d - max) / sum to the row's accumulator.
+//   ~10^4 log2 units at 10,000 cells and the logits are differences of them);  three sweeps over the clade rows (sorted by
+//   interval start, four rows in flight per thread): the largest logit, the normaliser sum of 2^(d - max), and 2^(d - max) / sum
+//   onto the row's accumulator -- the logit differences are re-formed from the float64 prefix sums in every sweep (two 64-bit
+//   shared-memory loads and an add: cheaper than keeping 20 values per thread alive at 1024 threads).
 //   Accumulators: fp32 in shared memory, flushed to a per-CTA float64 vector every 256 SNVs (short fp32 chains, fixed order);
 //   a last kernel adds the per-CTA vectors in CTA order.  The softmax terms are exp2f of float64 differences.
 //
@@ -32,10 +34,11 @@ struct PercellParams {
     int n_cells, n_rows;
     int row_words;             // ceil(n_cells / 16)
     const uint16_t* perm;      // [n_cells] column of the cell at depth-first position k
-    const uint32_t* lohi;      // [n_rows] lo | hi << 16 (hi exclusive; lo = hi: empty row, logit 0)
+    const uint32_t* lohi;      // [n_rows] lo | hi << 16 (hi exclusive; lo = hi: empty row, logit 0), the clade rows SORTED by (lo, hi):
+                               // slot -> caller's row in the reduction kernel's slot_row
     const double2* w;          // [n_cells] by depth-first position: {log2((1-FN_c)/FP), log2(FN_c/(1-FP))}; {0,0} for cells in no clade
     const uint8_t* row_keep;   // optional [n_snv]
-    double* part;              // [gridDim.x][n_rows], zeroed by the caller
+    double* part;              // [gridDim.x][n_rows] by slot, zeroed by the caller
     int acc_smem;              // 1: fp32 accumulators in shared memory, 0: straight into `part` (trees too big for that)
     int perm_smem;             // 1: the cell order staged in shared memory
 };
@@ -53,16 +56,6 @@ static inline size_t percell_smem_bytes(int n_cells, int n_rows, bool acc_smem, 
 
 __device__ __forceinline__ double pc_shfl_up(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
 __device__ __forceinline__ double pc_shfl_xor(double v, int d) { return __shfl_xor_sync(0xffffffffu, v, d); }
-
-// (m, s) <- softmax state of the union: s counts 2^(d - m)
-__device__ __forceinline__ void pc_combine(double& m, double& s, double m2, double s2) {
-    if (m2 > m) {
-        s = s * double(exp2f(float(m - m2))) + s2;
-        m = m2;
-    } else {
-        s += s2 * double(exp2f(float(m2 - m)));
-    }
-}
 
 __global__ void __launch_bounds__(1024, 1) scs_place_percell_kernel(const PercellParams p) {
     extern __shared__ double pc_smem[];
@@ -92,11 +85,13 @@ __global__ void __launch_bounds__(1024, 1) scs_place_percell_kernel(const Percel
         __syncthreads();
         // ---- prefix sums of the per-cell weights in depth-first order
         double run = 0.0;
+        const double* wd = reinterpret_cast<const double*>(p.w);
+#pragma unroll 4
         for (int k = k0; k < k1; ++k) {
             const int c = perm[k];
             const uint32_t code = (rowbuf[c >> 4] >> (2 * (c & 15))) & 3u;
-            const double2 wk = p.w[k];
-            run += code == 0u ? wk.y : (code == 3u ? 0.0 : wk.x);
+            const double wk = wd[2 * k + (code == 0u ? 1 : 0)];     // {observed mutated, observed wild type}
+            run += code == 3u ? 0.0 : wk;
             P[k + 1] = run;
         }
         double incl = run;
@@ -120,47 +115,66 @@ __global__ void __launch_bounds__(1024, 1) scs_place_percell_kernel(const Percel
         const double off = scr[32 + warp] + (incl - run);
         for (int k = k0; k < k1; ++k) P[k + 1] += off;
         __syncthreads();
-        // ---- sweep 1: max and sum of 2^(d - max) over the clade rows
-        double m = 0.0, s = 0.0;                                   // (the all-zero 'FP' row guarantees a logit of 0)
-        bool any = false;
-        for (int b = t; b < p.n_rows; b += T) {
-            const uint32_t lh = p.lohi[b];
-            const double d = P[lh >> 16] - P[lh & 0xffffu];
-            if (!any) {
-                m = d;
-                s = 1.0;
-                any = true;
-            } else if (d > m) {
-                s = s * double(exp2f(float(m - d))) + 1.0;
-                m = d;
-            } else {
-                s += double(exp2f(float(d - m)));
+        // ---- sweep 1: the largest logit (four rows in flight per thread; the rows are sorted by interval start, so the lanes of
+        // a warp read neighbouring prefix sums)
+        double m = -1.0e300;
+        for (int b0 = t; b0 < p.n_rows; b0 += 4 * T) {
+            uint32_t lh[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) lh[u] = b0 + u * T < p.n_rows ? p.lohi[b0 + u * T] : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double d = P[lh[u] >> 16] - P[lh[u] & 0xffffu];
+                if (b0 + u * T < p.n_rows && d > m) m = d;         // (no NaNs here: a plain compare, not the library maximum's NaN rules)
             }
         }
-        if (!any) {
-            m = -1.0e300;
-            s = 0.0;
-        }
 #pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) {
-            const double m2 = pc_shfl_xor(m, d), s2 = pc_shfl_xor(s, d);
-            pc_combine(m, s, m2, s2);
+        for (int o = 16; o >= 1; o >>= 1) {
+            const double v = pc_shfl_xor(m, o);
+            m = v > m ? v : m;
         }
-        if (lane == 0) {
-            scr[warp] = m;
-            scr[32 + warp] = s;
-        }
+        if (lane == 0) scr[warp] = m;
         __syncthreads();
-        m = scr[0];
-        s = scr[32];
-        for (int wv = 1; wv < nwarp; ++wv) pc_combine(m, s, scr[wv], scr[32 + wv]);      // same order in every thread
+        m = lane < nwarp ? scr[lane] : -1.0e300;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            const double v = pc_shfl_xor(m, o);
+            m = v > m ? v : m;
+        }
+        // ---- sweep 2: the normaliser, sum of 2^(d - max)
+        float sf = 0.f;
+        for (int b0 = t; b0 < p.n_rows; b0 += 4 * T) {
+            uint32_t lh[4];
+            float e[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) lh[u] = b0 + u * T < p.n_rows ? p.lohi[b0 + u * T] : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) e[u] = ex2_approx(float(P[lh[u] >> 16] - P[lh[u] & 0xffffu] - m));
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (b0 + u * T < p.n_rows) sf += e[u];
+        }
+        double s = double(sf);
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) s += pc_shfl_xor(s, o);
+        if (lane == 0) scr[32 + warp] = s;
+        __syncthreads();
+        s = lane < nwarp ? scr[32 + lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) s += pc_shfl_xor(s, o);            // (a butterfly of commutative adds: the same bits in every lane and warp)
         const float inv = float(1.0 / s);
-        // ---- sweep 2: the normalised terms onto the accumulators (thread t owns rows t, t + T, ...)
+        // ---- sweep 3: the normalised terms onto the accumulators (thread t owns slots t, t + T, ...)
         if (p.acc_smem) {
-            for (int b = t; b < p.n_rows; b += T) {
-                const uint32_t lh = p.lohi[b];
-                const double d = P[lh >> 16] - P[lh & 0xffffu];
-                acc[b] += exp2f(float(d - m)) * inv;
+            for (int b0 = t; b0 < p.n_rows; b0 += 4 * T) {
+                uint32_t lh[4];
+                float e[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) lh[u] = b0 + u * T < p.n_rows ? p.lohi[b0 + u * T] : 0u;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) e[u] = ex2_approx(float(P[lh[u] >> 16] - P[lh[u] & 0xffffu] - m)) * inv;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (b0 + u * T < p.n_rows) acc[b0 + u * T] += e[u];
             }
             if (++since_flush == PC_FLUSH_ROWS) {
                 for (int b = t; b < p.n_rows; b += T) {
@@ -173,7 +187,7 @@ __global__ void __launch_bounds__(1024, 1) scs_place_percell_kernel(const Percel
             for (int b = t; b < p.n_rows; b += T) {
                 const uint32_t lh = p.lohi[b];
                 const double d = P[lh >> 16] - P[lh & 0xffffu];
-                part[b] += double(exp2f(float(d - m)) * inv);
+                part[b] += double(ex2_approx(float(d - m)) * inv);
             }
         }
         __syncthreads();                                           // P, rowbuf and scr are rewritten by the next row
@@ -182,13 +196,13 @@ __global__ void __launch_bounds__(1024, 1) scs_place_percell_kernel(const Percel
         for (int b = t; b < p.n_rows; b += T) part[b] += double(acc[b]);
 }
 
-// y[b] = sum over the CTAs' vectors, in CTA order
-__global__ void scs_percell_reduce_kernel(const double* part, int n_parts, int n_rows, double* y) {
+// y[row of slot b] = sum over the CTAs' vectors, in CTA order
+__global__ void scs_percell_reduce_kernel(const double* part, int n_parts, int n_rows, const int* slot_row, double* y) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_rows) return;
     double s = 0.0;
     for (int g = 0; g < n_parts; ++g) s += part[size_t(g) * n_rows + b];
-    y[b] = s;
+    y[slot_row[b]] = s;
 }
 
 }  // namespace scs

@@ -2,7 +2,9 @@
 """One-off randomized parity sweep on a GPU (not part of the test suite): shapes around the boundaries of the round-2 code paths.
   (1) single datasets, interval path against the GEMM: cell counts around the pre-pass sub-block / thread-count boundaries;
   (2) batches of small trees (iv5) against the GEMM: cell counts around the lane-width boundaries, ragged groups;
-  (3) the cluster LRT kernel against the CTA kernel on random tree sizes."""
+  (3) the cluster LRT kernel against the CTA kernel on random tree sizes;
+  (4) per-cell FN rates (scs_place_percell) against the float64 prefix-sum oracle (oracle/pt_oracle.map_mutations_gt_interval).
+`python tools/fuzz_parity.py SEED SECONDS [percell]`: with a third argument only (4) runs."""
 import os, sys, time
 import numpy as np
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -90,7 +92,37 @@ def lrt(n_leaves, n_prob):
         bad.append(("lrt", n_leaves, n_prob, a[:, [0, 2, 7]].tolist(), b[:, [0, 2, 7]].tolist()))
     return ok
 
+def percell(n_cells, n_snv):
+    from oracle import pt_oracle as O
+    tree = synth.coalescent_tree(n_cells, rng)
+    perm = rng.permutation(n_cells)
+    S = np.ascontiguousarray(tree.clade_matrix()[:, perm])
+    codes = np.ascontiguousarray(synth.observe(tree, synth.throw_mutations(tree, n_snv, rng), 0.1, 0.01, float(rng.uniform(0.0, 0.5)), rng)[:, perm])
+    keep = (rng.random(n_snv) < 0.9).astype(np.uint8)
+    lo = 10.0 ** rng.uniform(-5, -1)
+    rates = np.exp(rng.uniform(np.log(lo), np.log(0.95), n_cells))
+    FP = float(10.0 ** rng.uniform(-4, -0.5))
+    packed, pitch = engine.pack_genotypes(codes)
+    bits, words = engine.pack_clades(S)
+    y = torch.zeros(S.shape[0], dtype=torch.float64, device="cuda")
+    engine.place_percell(ctx, torch.as_tensor(packed).cuda(), pitch, n_snv, n_cells, torch.as_tensor(keep).cuda(), bits, words, FP, rates, y)
+    muts = np.where(codes == 3, np.nan, codes.astype(float))[keep.astype(bool)]
+    want = O.map_mutations_gt_interval(muts, S.astype(float), FP, rates) if muts.shape[0] else np.zeros(S.shape[0])
+    err = float((np.abs(y.cpu().numpy() - want) / np.maximum(1.0, np.abs(want))).max())
+    if err > 2e-5:
+        bad.append(("percell", n_cells, n_snv, FP, lo, err))
+    return err <= 2e-5
+
 t0 = time.time()
+if len(sys.argv) > 3:
+    n4 = 0
+    edge = [2, 3, 31, 32, 33, 63, 64, 65, 255, 256, 257, 511, 512, 513, 1000, 2047, 2048, 2049, 4095, 4097]
+    while time.time() - t0 < budget:
+        percell(edge[n4] if n4 < len(edge) else int(rng.integers(2, 3000)), int(rng.integers(1, 500))); n4 += 1
+    print("percell cases", n4, "failures", len(bad))
+    for b in bad[:20]:
+        print(str(b)[:400])
+    sys.exit(0)
 n = [0, 0, 0]
 edge_cells = [100, 127, 128, 129, 255, 256, 257, 496, 511, 512, 513, 1008, 1024, 1025, 1535, 2047, 2048, 2049, 3071, 4095, 4096, 4097]
 k = 0
