@@ -410,3 +410,22 @@ def test_sub_batch_cuts_cover_every_pair_once():
     cuts = engine.sub_batch_cuts(1250, 4)
     sizes = np.diff(cuts)
     assert list(sizes) == [208, 417, 417, 208]
+
+
+def test_per_cell_rates_alignment():
+    """FN[muts_in.columns].values of run_PT_test.py:414 in the mirror: Series / dict keyed by sample name, or a plain
+    sequence over all columns or over the placed cells; the outgroup column may be absent."""
+    import pandas as pd
+    from scsommerclock_b200 import run_PT_test as P
+    columns = ["tumcell0002", "healthycell", "tumcell0001", "tumcell0003"]
+    active = np.array([1, 0, 1, 1], dtype=np.uint8)
+    ser = pd.Series({"tumcell0001": 0.1, "tumcell0002": 0.2, "tumcell0003": 0.3})
+    want = np.array([0.2, np.nan, 0.1, 0.3])
+    for FN in (ser, dict(ser), [0.2, 0.1, 0.3], np.array([0.2, 0.9, 0.1, 0.3])):
+        got = P._per_cell_rates(FN, columns, active)
+        np.testing.assert_array_equal(np.isnan(got[active == 1]), False)
+        np.testing.assert_allclose(got[active == 1], want[active == 1])
+    with pytest.raises(KeyError):
+        P._per_cell_rates({"tumcell0001": 0.1, "tumcell0002": 0.2}, columns, active)
+    with pytest.raises(ValueError):
+        P._per_cell_rates([0.1, 0.2], columns, active)
