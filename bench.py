@@ -628,7 +628,7 @@ def main():
             engine.place_percell(ctx, ds.packed, pitch, n_snv, n_cols, keep, ds.bits, ds.words, ds.FP, np.full(n_cols, ds.FN), y_pc, stream=ds.stream)
             percell = {"workload": "the headline dataset (%d cells x %d SNVs), per-cell FN rates ~ N(%.3g, 0.03)" % (n_cells, n_snv, ds.FN),
                        "kernel_ms": float(np.mean(kms)), "launches_timed": len(kms), "value": placements / (float(np.mean(kms)) / 1e3),
-                       "unit": "placements/s", "kernel": "scs_place_percell_kernel + scs_percell_reduce_kernel (device time; the call also "
+                       "unit": "placements/s", "kernel": "scs_place_percell2_kernel<R> (1,024..12,287 cells; else scs_place_percell_kernel) + scs_percell_reduce_kernel (device time; the call also "
                        "analyses the clade masks on the host and uploads three tables)",
                        "max_rel_dev_equal_rates_vs_count_kernels": float((y_pc - ds.y_dev).abs().max() / ds.y_dev.abs().max())}
             del keep, y_pc

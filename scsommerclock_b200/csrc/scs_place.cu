@@ -2356,19 +2356,47 @@ int scs_place_percell(scs_ctx* ctx, const uint8_t* d_gt, int64_t pitch_bytes, in
     });
     std::vector<uint32_t> lohi_sorted(static_cast<size_t>(n_rows));
     for (int b = 0; b < n_rows; ++b) lohi_sorted[size_t(b)] = lohi[size_t(slot_row[size_t(b)])];
-    // launch shape: a thread per ~8 clade rows / cells, 64..1024 threads; accumulators and cell order in shared memory when they fit
-    int T = std::max((n_rows + 7) / 8, (n_cells + 7) / 8);
-    T = std::min(1024, std::max(64, (T + 31) / 32 * 32));
     int max_smem = 0;
     SCS_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    // which kernel: trees of 1,024 .. 12,287 cells keep every thread's clade rows in registers (scs_place_percell2_kernel<R>,
+    // 512 threads, R = rows per thread); smaller and bigger trees the general kernel.  SCS_PERCELL_KERNEL = 1 forces the latter.
+    int R2 = 0;
+    {
+        const char* e = getenv("SCS_PERCELL_KERNEL");
+        const int need = (n_rows + PC2_THREADS - 1) / PC2_THREADS;
+        if (!(e && atoi(e) == 1) && n_rows >= 2048 && need <= PC2_MAX_R) {
+            R2 = (need + 7) / 8 * 8;
+            if (percell2_smem_bytes(n_cells, R2) > size_t(max_smem)) R2 = 0;
+        }
+    }
+    // general kernel: a thread per ~8 clade rows / cells, 64..1024 threads; accumulators and cell order in shared memory when they fit
+    int T = std::max((n_rows + 7) / 8, (n_cells + 7) / 8);
+    T = std::min(1024, std::max(64, (T + 31) / 32 * 32));
     bool acc_smem = true, perm_smem = true;
-    if (percell_smem_bytes(n_cells, n_rows, acc_smem, perm_smem) > size_t(max_smem)) perm_smem = false;
-    if (percell_smem_bytes(n_cells, n_rows, acc_smem, perm_smem) > size_t(max_smem)) acc_smem = false;
-    const size_t smem = percell_smem_bytes(n_cells, n_rows, acc_smem, perm_smem);
-    if (smem > size_t(max_smem)) return set_error(SCS_ERR_ARG, "per-cell placement: %d cells do not fit shared memory", n_cells);
-    SCS_CUDA(cudaFuncSetAttribute(scs_place_percell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    size_t smem = 0;
     int per_sm = 0;
-    SCS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scs_place_percell_kernel, T, smem));
+    void (*kern2)(PercellParams) = nullptr;
+    if (R2 > 0) {
+        T = PC2_THREADS;
+        smem = percell2_smem_bytes(n_cells, R2);
+        switch (R2) {
+            case 8: kern2 = scs_place_percell2_kernel<8>; break;
+            case 16: kern2 = scs_place_percell2_kernel<16>; break;
+            case 24: kern2 = scs_place_percell2_kernel<24>; break;
+            case 32: kern2 = scs_place_percell2_kernel<32>; break;
+            case 40: kern2 = scs_place_percell2_kernel<40>; break;
+            default: kern2 = scs_place_percell2_kernel<48>; break;
+        }
+        SCS_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        SCS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern2, T, smem));
+    } else {
+        if (percell_smem_bytes(n_cells, n_rows, acc_smem, perm_smem) > size_t(max_smem)) perm_smem = false;
+        if (percell_smem_bytes(n_cells, n_rows, acc_smem, perm_smem) > size_t(max_smem)) acc_smem = false;
+        smem = percell_smem_bytes(n_cells, n_rows, acc_smem, perm_smem);
+        if (smem > size_t(max_smem)) return set_error(SCS_ERR_ARG, "per-cell placement: %d cells do not fit shared memory", n_cells);
+        SCS_CUDA(cudaFuncSetAttribute(scs_place_percell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        SCS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scs_place_percell_kernel, T, smem));
+    }
     per_sm = std::max(1, per_sm);
     const int grid = int(std::max<int64_t>(1, std::min<int64_t>(n_snv, int64_t(ctx->sm_count) * per_sm)));
     // workspace: tables + per-CTA partial sums, one allocation
@@ -2412,7 +2440,10 @@ int scs_place_percell(scs_ctx* ctx, const uint8_t* d_gt, int64_t pitch_bytes, in
             cudaEventCreate(&ev1);
             cudaEventRecord(ev0, st);
         }
-        if (n_snv > 0) scs_place_percell_kernel<<<grid, T, smem, st>>>(q);
+        if (n_snv > 0) {
+            if (kern2) kern2<<<grid, T, smem, st>>>(q);
+            else scs_place_percell_kernel<<<grid, T, smem, st>>>(q);
+        }
         scs_percell_reduce_kernel<<<(n_rows + 255) / 256, 256, 0, st>>>(q.part, grid, n_rows, reinterpret_cast<const int*>(ws + off_slot), d_soft_weights);
         if (kernel_ms) cudaEventRecord(ev1, st);
         const cudaError_t e = cudaStreamSynchronize(st);           // the workspace is freed below

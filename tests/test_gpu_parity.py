@@ -1387,8 +1387,8 @@ def test_per_cell_fn_product_path_on_golden_cases(ctx):
             P.map_mutations_gt(tree, muts, rates, 0.1)
 
 
-@pytest.mark.parametrize("n_snv,n_cells", [(1, 2), (127, 3), (300, 50), (1000, 200), (700, 513), (400, 1100), (150, 4200), (60, 10000),
-                                            (40, 12500), (30, 13500), (24, 16000)])
+@pytest.mark.parametrize("n_snv,n_cells", [(1, 2), (127, 3), (300, 50), (1000, 200), (700, 513), (400, 1100), (600, 2500), (150, 4200),
+                                            (300, 7000), (60, 10000), (50, 12287), (40, 12500), (30, 13500), (24, 16000)])
 def test_per_cell_fn_kernel_matches_oracle(ctx, monkeypatch, n_snv, n_cells):
     """scs_place_percell against the oracle's float64 prefix-sum form (pinned to the reference by
     test_per_cell_fn_against_the_reference, and to the dense form below 600 cells) on shuffled random trees: 64..1024
@@ -1417,6 +1417,13 @@ def test_per_cell_fn_kernel_matches_oracle(ctx, monkeypatch, n_snv, n_cells):
     assert abs(got.sum() - keep.sum()) <= 5e-6 * max(1, keep.sum())          # every kept SNV's row of M sums to 1
     engine.place_percell(ctx, d_gt, pitch, n_snv, n_cells, d_keep, bits, words, 0.01, rates, y)
     assert np.array_equal(y.cpu().numpy(), got)                               # fixed reduction order
+    # trees of 1,024 .. 12,287 cells took the register kernel (scs_place_percell2_kernel<R>): the general kernel on the same input
+    if 2048 <= S.shape[0] <= 48 * 512:
+        monkeypatch.setenv("SCS_PERCELL_KERNEL", "1")
+        engine.place_percell(ctx, d_gt, pitch, n_snv, n_cells, d_keep, bits, words, 0.01, rates, y)
+        monkeypatch.delenv("SCS_PERCELL_KERNEL")
+        assert_soft_close(y.cpu().numpy(), O.map_mutations_gt_interval(muts, S.astype(float), 0.01, rates))
+        np.testing.assert_allclose(y.cpu().numpy(), got, rtol=1e-5, atol=1e-6)
     # no row flags: every row placed
     engine.place_percell(ctx, d_gt, pitch, n_snv, n_cells, None, bits, words, 0.01, rates, y)
     assert abs(y.sum().item() - n_snv) <= 5e-6 * n_snv
