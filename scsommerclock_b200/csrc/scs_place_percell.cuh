@@ -17,7 +17,9 @@
 //   onto the row's accumulator -- the logit differences are re-formed from the float64 prefix sums in every sweep (two 64-bit
 //   shared-memory loads and an add: cheaper than keeping 20 values per thread alive at 1024 threads).
 //   Accumulators: fp32 in shared memory, flushed to a per-CTA float64 vector every 256 SNVs (short fp32 chains, fixed order);
-//   a last kernel adds the per-CTA vectors in CTA order.  The softmax terms are exp2f of float64 differences.
+//   a last kernel adds the per-CTA vectors in CTA order.  The softmax terms are ex2.approx of float64 differences.
+//   Trees of 1,024 .. 12,287 cells take scs_place_percell2_kernel<R> below: the same arithmetic with every thread's clade
+//   rows in registers (accumulators and terms) and the interval table in shared memory.
 //
 // This is the general-weights sibling of the count kernels, built for completeness of map_mutations_gt's interface (nothing on
 // the reference's command-line path passes per-cell rates); it shares their row order, reduction discipline and C ABI style.
